@@ -1,0 +1,144 @@
+/* inr_b200.h -- C ABI of the B200-native INR fitting engine (libinr_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of luisdavid64/MRI-Implicit-Neural-Representations: the per-batch
+ * body of the training loops (reference src/train.py:158-192 and src/train_kspace_multiscale.py:164-201):
+ * encoder.embedding -> model(x) -> loss -> backward -> Adam.step.  The reference has no native layer
+ * (it is pure PyTorch), so each entry point cites the Python it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative INR_E* code; inr_last_error() gives the message;
+ *    no C++ exception crosses the boundary;
+ *  - all buffers are caller-owned DEVICE pointers (plain pointers + sizes, no torch types); the library
+ *    owns only the immutable plan; nothing allocates or synchronises inside a call except
+ *    inr_plan_create / inr_selftest_umma;
+ *  - every call is asynchronous on the cudaStream_t passed as `void* stream` (0 = default stream);
+ *  - one in-flight step per (plan, workspace).
+ *
+ * Flat parameter buffer: fp32, tensors in reference state_dict order (e.g. model.0.linear.weight [256,512]
+ * row-major, model.0.linear.bias [256], ...), see inr_plan_tensor().
+ */
+#ifndef INR_B200_H
+#define INR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INR_OK 0
+#define INR_EINVAL (-1)      /* bad argument / unsupported shape */
+#define INR_ECUDA (-2)       /* CUDA runtime error (message has the cudaError string) */
+#define INR_EUNSUPPORTED (-3)
+
+/* model kinds (reference src/train.py:55-70) */
+#define INR_MODEL_SIREN 1    /* src/models/networks.py:99-124 */
+#define INR_MODEL_FFN 2      /* src/models/networks.py:48-69  */
+/* encoders (src/models/networks.py:7-35) */
+#define INR_ENC_NONE 0       /* x is the dense [bs, in] fp32 network input */
+#define INR_ENC_GAUSS 1      /* gamma(x) = [sin(2 pi x B^T), cos(2 pi x B^T)] computed in-kernel from coords */
+/* last-layer activation */
+#define INR_LAST_LINEAR 0
+#define INR_LAST_TANH 1      /* SIREN last_tanh, src/models/networks.py:94-95 */
+#define INR_LAST_SIGMOID 2   /* FFN, src/models/networks.py:63 */
+/* losses as weighted by the training loop (src/train.py:81-98,178-182) */
+#define INR_LOSS_NONE 0
+#define INR_LOSS_L2 1        /* 0.5 * torch.nn.MSELoss */
+#define INR_LOSS_L1 2        /* 0.5 * torch.nn.L1Loss */
+#define INR_LOSS_MSLE 3      /* 0.5 * MSLELoss, src/metrics/losses.py:18-27 */
+#define INR_LOSS_TANH 4      /* TanhL2Loss, src/metrics/losses.py:121-139 */
+#define INR_LOSS_LSL 5       /* 0.5 * LogSpaceLoss, src/metrics/losses.py:204-223 */
+#define INR_LOSS_HDR 6       /* HDRLoss_FF, src/metrics/losses.py:226-264 */
+
+typedef struct inr_model_desc {
+  int32_t model;            /* INR_MODEL_* */
+  int32_t in_features;      /* net.network_input_size */
+  int32_t out_features;     /* net.network_output_size */
+  int32_t depth;            /* net.network_depth */
+  int32_t width;            /* net.network_width */
+  int32_t last_act;         /* INR_LAST_* */
+  int32_t encoder;          /* INR_ENC_* */
+  int32_t enc_size;         /* encoder.embedding_size (gauss) */
+  float w0;                 /* SIREN: 30 (hard-wired in the reference, src/models/networks.py:75) */
+} inr_model_desc;
+
+typedef struct inr_loss_desc {
+  int32_t kind;             /* INR_LOSS_* */
+  float hdr_eps, hdr_sigma, hdr_factor;   /* loss_opts of src/metrics/losses.py:230-234 */
+} inr_loss_desc;
+
+typedef struct inr_tensor_info {
+  int64_t offset;           /* float offset inside the flat parameter buffer */
+  int32_t rows, cols;       /* weight [rows, cols]; bias: rows = n, cols = 1 */
+  int32_t layer, is_bias;
+} inr_tensor_info;
+
+/* hyper-parameter block read from DEVICE memory each step (so a captured CUDA graph sees updates):
+ * float[8] = { lr, beta1, beta2, eps, weight_decay, reg_l1, reg_l2, unused }
+ * (torch.optim.Adam, src/train.py:76; Regularization_L1/L2, src/models/regularization.py:21-36). */
+#define INR_HYPER_FLOATS 8
+/* step scalars the backward pass leaves at the head of the workspace scalar block, readable with
+ * inr_scalars_offset(): loss, grad scale S, cA, cB, masked row count, HDR filter mean, HDR reg term, 1/S */
+#define INR_SCALAR_FLOATS 16
+
+typedef struct inr_plan inr_plan;
+
+const char* inr_last_error(void);
+
+/* replaces: model construction dispatch, src/train.py:55-70 */
+int inr_plan_create(const inr_model_desc* desc, inr_plan** out);
+int inr_plan_destroy(inr_plan* plan);
+int inr_plan_param_count(const inr_plan* plan, int64_t* n_params);
+int inr_plan_tensor_count(const inr_plan* plan, int32_t* n);
+int inr_plan_tensor(const inr_plan* plan, int32_t index, inr_tensor_info* out);
+/* bytes of the fp16 operand copies of the weights (caller allocates, 1024-aligned) */
+int inr_wpack_bytes(const inr_plan* plan, size_t* bytes);
+/* bytes of activation/gradient workspace for batches of up to `bs` coordinates */
+int inr_workspace_bytes(const inr_plan* plan, int64_t bs, size_t* bytes);
+/* byte offset of the INR_SCALAR_FLOATS step scalars inside a workspace sized for `bs` */
+int inr_scalars_offset(const inr_plan* plan, int64_t bs, size_t* offset);
+
+/* debugging / tests: byte offsets of the workspace regions for batches of `bs`:
+ * out[0..11] = H image of layer l input, out[12..23] = act' images, out[24..35] = dZ images,
+ * out[36] = dZ_last, [37] = loss gradient pieces, [38] = tile partials, [39] = scalars, [40] = split-K partials,
+ * [41] = n_tiles, [42] = n_split, [43] = total bytes. `n` must be >= 44. */
+int inr_workspace_layout(const inr_plan* plan, int64_t bs, uint64_t* out, int32_t n);
+
+/* (re)build the fp16 operand copies from the fp32 parameters: after init / load_state_dict
+ * (src/train.py:117-121) or any external edit of the parameters */
+int inr_pack_weights(const inr_plan* plan, const float* params, void* wpack, void* stream);
+
+/* replaces: encoder.embedding + model(coords), src/train.py:163-169 / :206-213.
+ * input: coords [bs,3] fp32 when the plan's encoder is GAUSS (encB = [enc_size,3] fp32),
+ *        x [bs,in_features] fp32 when the encoder is NONE.
+ * train != 0 saves the activation images a later inr_backward needs. */
+int inr_forward(const inr_plan* plan, const float* params, const void* wpack, const float* input,
+                const float* encB, int64_t bs, void* workspace, float* out, int32_t train, void* stream);
+
+/* replaces: loss.backward() for an externally computed dL/dout [bs,out] (arbitrary PyTorch loss on top of
+ * the fused model, e.g. CenterLoss), src/train.py:189.  grads = flat fp32 buffer like params. */
+int inr_backward(const inr_plan* plan, const float* params, const void* wpack, const float* dout,
+                 int64_t bs, void* workspace, float* grads, void* stream);
+
+/* replaces: optim.step() (+ regulariser gradient), src/train.py:185-190; re-packs the fp16 copies. */
+int inr_adam_step(const inr_plan* plan, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  void* wpack, const float* hyper_dev, const int32_t* step_dev, void* stream);
+
+/* replaces: the whole loop body src/train.py:160-192 for fusable model+loss combinations:
+ * forward, loss (+ row mask, src/train.py:172-177), backward, Adam, fp16 re-pack.
+ *  coords/gt/mask are the RESIDENT arrays of the slice; the batch is rows
+ *  [*row_cursor_dev, *row_cursor_dev + bs) when row_cursor_dev != NULL (then advanced by `bs` on the
+ *  device at the end of the step, so a captured graph walks the slice in grid order), else [0, bs).
+ *  step_dev is incremented on the device before use; loss_out_dev (optional) receives the step's loss. */
+int inr_train_step(const inr_plan* plan, const inr_loss_desc* loss, float* params, float* exp_avg,
+                   float* exp_avg_sq, void* wpack, const float* hyper_dev, int32_t* step_dev,
+                   const float* coords, const float* input_x, const float* encB, const float* gt,
+                   const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev, void* workspace,
+                   float* out, float* loss_out_dev, void* stream);
+
+/* one tcgen05 GEMM per operand-layout family against a host loop (allocates + synchronises; test only) */
+int inr_selftest_umma(int mode, int variant, float* max_abs_err, float* ref_absmax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

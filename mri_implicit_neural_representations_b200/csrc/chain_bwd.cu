@@ -1,0 +1,272 @@
+// Fused whole-MLP backward (dgrad chain) for width-256 real-valued chains.
+//
+// Prologue (every CTA, fixed reduction order => bit-reproducible): reduce the forward kernel's
+// per-tile loss partials into the step scalars: masked row count m, HDR filter mean A, the loss
+// value, the normalisation factors cA / cB and a power-of-two gradient scale S chosen from the
+// amax of dL/dz_last so that every dZ fits fp16 (hard part 1).
+//
+// Per 128-row tile:  dZ_last = S (cA gA + cB gB)                       (CUDA cores, fp32)
+//                    dZ_{L-1} = (dZ_last W_last) * act'(z_{L-1})        (CUDA cores, K = out_f <= 4)
+//                    dZ_{l-1} = (dZ_l W_l) * act'(z_{l-1})              (tcgen05, fp32 accumulate in TMEM)
+// Every dZ_l is written as an fp16 operand image for the split-K wgrad kernel; the image of the
+// current layer also stays in shared memory (in place) as the A operand of the next dgrad GEMM.
+// act'(z) images come from the forward kernel (w0*cos(w0 z) for SIREN, 1[z>0] for ReLU).
+#include <cuda_runtime.h>
+#include <cmath>
+#include "inr_ptx.cuh"
+#include "inr_kernels.cuh"
+
+namespace inr {
+
+constexpr int kBwdStages = 6;
+constexpr int kBwdThreads = 384;
+constexpr int kBwdSmem = 2 * kActBytes + kBwdStages * kStageBytes + 1024;
+
+// Fixed-order block reduction of the tile partials; result broadcast through shared memory.
+__device__ void reduce_step_scalars(const BwdArgs& a, float* sc /* smem[kScalars] */) {
+  __shared__ float part[kBwdThreads / 32][6];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* p = reinterpret_cast<const float*>(a.ws + a.w.part_off);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, m4 = 0.f, m5 = 0.f;
+  for (int t = tid; t < a.w.n_tiles; t += kBwdThreads) {
+    const float* q = p + static_cast<size_t>(t) * kPartialsPerTile;
+    s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3];
+    m4 = fmaxf(m4, q[4]); m5 = fmaxf(m5, q[5]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off); s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+    m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, off)); m5 = fmaxf(m5, __shfl_xor_sync(0xffffffffu, m5, off));
+  }
+  if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; part[warp][3] = s3; part[warp][4] = m4; part[warp][5] = m5; }
+  __syncthreads();
+  if (tid == 0) {
+    float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
+    for (int w = 0; w < kBwdThreads / 32; ++w) {
+      lA += part[w][0]; lB += part[w][1]; fs += part[w][2]; cnt += part[w][3];
+      amA = fmaxf(amA, part[w][4]); amB = fmaxf(amB, part[w][5]);
+    }
+    const float m = fmaxf(cnt, 1.f);
+    const float of = static_cast<float>(a.m.out_f);
+    float cA = 0.f, cB = 0.f, loss = 0.f, fmean = 0.f;
+    switch (a.loss.kind) {      // weights of src/train.py:178-182 folded in
+      case LOSS_L2:   cA = 1.f / (m * of);         loss = lA * 0.5f / (m * of); break;
+      case LOSS_L1:   cA = 0.5f / (m * of);        loss = lA * 0.5f / (m * of); break;
+      case LOSS_MSLE: cA = 1.f / (m * of);         loss = lA * 0.5f / (m * of); break;
+      case LOSS_TANH: cA = 2.f / (m * of);         loss = lA / (m * of); break;
+      case LOSS_LSL:  cA = 1.f / m;                loss = lA * 0.5f / m; break;
+      case LOSS_HDR:
+        fmean = fs / static_cast<float>(a.bs_k > 0 ? a.bs_k : 1);
+        cA = 1.f / m; cB = a.loss.factor * fmean / m;
+        loss = lA / m + a.loss.factor * fmean * lB / m;
+        sc[SC_REG] = a.loss.factor * fmean * lB / m;
+        break;
+      default: cA = 1.f; break;   // external dout: gA holds dL/dout already
+    }
+    const float amax = cA * amA + fabsf(cB) * amB;
+    float S = 1.f;
+    if (amax > 0.f && isfinite(amax)) {
+      int e = static_cast<int>(floorf(log2f(256.f / amax)));
+      e = e < -60 ? -60 : (e > 60 ? 60 : e);
+      S = exp2f(static_cast<float>(e));
+    }
+    sc[SC_LOSS] = loss; sc[SC_SCALE] = S; sc[SC_CA] = cA; sc[SC_CB] = cB; sc[SC_COUNT] = cnt; sc[SC_FMEAN] = fmean;
+    sc[SC_INV_SCALE] = 1.f / S;
+    if (a.loss.kind != LOSS_HDR) sc[SC_REG] = 0.f;
+    if (blockIdx.x == 0) {
+      float* g = reinterpret_cast<float*>(a.ws + a.w.scal_off);
+      for (int i = 0; i < 8; ++i) g[i] = sc[i];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* act = smem;                       // dZ_l image: A operand, rewritten in place per layer
+  uint8_t* dimg = smem + kActBytes;          // act'(z) image of the layer being produced
+  uint8_t* wring = smem + 2 * kActBytes;
+  __shared__ uint64_t w_full[kBwdStages], w_empty[kBwdStages], d_full[4], d_empty, act_full[4], acc_full[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sc[kScalars];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const ChainModel& M = a.m;
+  const int n_tiles = a.w.n_tiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < kBwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&act_full[i], 128); }
+    mbar_init(&d_empty, 256);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  reduce_step_scalars(a, sc);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: act' images + dgrad weight stages
+    if (lane == 0) {
+      uint32_t it = 0, dq = 0;
+      auto load_dimg = [&](int l, int tile) {
+        mbar_wait(&d_empty, (dq & 1) ^ 1);
+        ++dq;
+        const uint8_t* src = a.ws + a.w.d_off[l] + static_cast<size_t>(tile) * kActBytes;
+        for (int c = 0; c < 4; ++c) {
+          mbar_arrive_expect_tx(&d_full[c], kChunkBytes);
+          bulk_g2s(dimg + c * kChunkBytes, src + c * kChunkBytes, kChunkBytes, &d_full[c]);
+        }
+      };
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        load_dimg(M.n_gemm - 1, tile);
+        for (int l = M.n_gemm - 1; l >= 1; --l) {
+          const uint8_t* src = a.wpack + M.wd_off[l];
+          for (int s = 0; s < kWidth / kStageK; ++s, ++it) {
+            const uint32_t slot = it % kBwdStages, ph = (it / kBwdStages) & 1;
+            mbar_wait(&w_empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&w_full[slot], kStageBytes);
+            bulk_g2s(wring + slot * kStageBytes, src + static_cast<size_t>(s) * kStageBytes, kStageBytes, &w_full[slot]);
+          }
+          load_dimg(l - 1, tile);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: dH_{l-1} = dZ_l * W_l
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, kWidth, false, false);
+      uint32_t it = 0, act_use = 0;
+      const uint32_t act_s = smem_u32(act), wring_s = smem_u32(wring);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = M.n_gemm - 1; l >= 1; --l, ++act_use) {
+          const uint32_t acc = tmem + (l & 1) * kWidth;
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(&act_full[c], act_use & 1);
+            tc_fence_after();
+            const uint32_t a_base = act_s + c * kChunkBytes;
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2, ++it) {
+              const uint32_t slot = it % kBwdStages;
+              mbar_wait(&w_full[slot], (it / kBwdStages) & 1);
+              tc_fence_after();
+              const uint32_t b_base = wring_s + slot * kStageBytes;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t da = umma_smem_desc(a_base + (s2 * 2 + kk) * 4096, 2048, 128);
+                const uint64_t db = umma_smem_desc(b_base + kk * 8192, 4096, 128);
+                umma_f16(acc, da, db, idesc, (c | s2 | kk) != 0);
+              }
+              umma_commit(&w_empty[slot]);
+            }
+          }
+          umma_commit(&acc_full[l & 1]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ compute warps
+    const int q = warp & 3, half = (warp - 4) >> 2, row = q * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
+    const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
+    const float* Wl = a.params + M.w_off[M.n_gemm];
+    uint32_t dq = 0, acc_ph[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int grow = tile * kTileM + row;
+      const bool valid = grow < a.bs;
+      // ---- dZ_last (fp32) and its padded fp16 image
+      float dz[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        if (a.dout) {
+          for (int o = 0; o < M.out_f; ++o) dz[o] = S * a.dout[static_cast<size_t>(grow) * M.out_f + o];
+        } else {
+          const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.g_off) +
+                                                             (static_cast<size_t>(tile) * kTileM + row) * 4);
+          dz[0] = S * (cA * g.x + cB * g.z);
+          dz[1] = S * (cA * g.y + cB * g.w);
+        }
+      }
+      if (half == 0) {
+        uint8_t* zl = a.ws + a.w.dzlast_off + static_cast<size_t>(tile) * kDzLastBytes;
+        st_global_v4(zl + row * 16, make_uint4(pack_h2(dz[0], dz[1]), pack_h2(dz[2], dz[3]), 0u, 0u));
+        st_global_v4(zl + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
+      }
+      // ---- layers, top down.  step == n_gemm-1: CUDA-core product with W_last; below: TMEM accumulators
+      for (int l = M.n_gemm - 1; l >= 0; --l) {
+        const bool from_last = (l == M.n_gemm - 1);
+        uint8_t* dz_img = a.ws + a.w.dz_off[l] + static_cast<size_t>(tile) * kActBytes;
+        if (!from_last) {
+          mbar_wait(&acc_full[(l + 1) & 1], acc_ph[(l + 1) & 1]);
+          acc_ph[(l + 1) & 1] ^= 1;
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          const int col0 = half * 128 + g * 32;
+          const int chunk = half * 2 + (g >> 1);
+          if ((g & 1) == 0) mbar_wait(&d_full[chunk], dq & 1);
+          float v[32];
+          if (from_last) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float acc = 0.f;
+#pragma unroll
+              for (int o = 0; o < kMaxOut; ++o)
+                if (o < M.out_f) acc = fmaf(dz[o], __ldg(Wl + o * kWidth + col0 + i), acc);
+              v[i] = acc;
+            }
+          } else {
+            tmem_ld32(tmem + t_lane + ((l + 1) & 1) * kWidth + col0, v);
+            tmem_ld_wait();
+          }
+          const int kg0 = col0 >> 3;
+          uint4 zv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 dr = *reinterpret_cast<const uint4*>(dimg + (kg0 + j) * 2048 + row * 16);
+            const __half2* dh = reinterpret_cast<const __half2*>(&dr);
+            float z[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 d2 = __half22float2(dh[i]);
+              z[2 * i] = v[8 * j + 2 * i] * d2.x;
+              z[2 * i + 1] = v[8 * j + 2 * i + 1] * d2.y;
+            }
+            zv[j] = make_uint4(pack_h2(z[0], z[1]), pack_h2(z[2], z[3]), pack_h2(z[4], z[5]), pack_h2(z[6], z[7]));
+          }
+          if (l >= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(act + (kg0 + j) * 2048 + row * 16) = zv[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_global_v4(dz_img + (kg0 + j) * 2048 + row * 16, zv[j]);
+          if (l >= 1 && (g & 1)) {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&act_full[chunk]);
+          }
+        }
+        ++dq;
+        mbar_arrive(&d_empty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+cudaError_t launch_chain_bwd(const BwdArgs& a, int n_sm, cudaStream_t stream) {
+  const int grid = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
+  if (grid <= 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+  if (e != cudaSuccess) return e;
+  chain_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace inr

@@ -1,0 +1,402 @@
+// Fused whole-MLP forward for width-256 real-valued chains (SIREN, FFN):
+//   positional encoding -> [tcgen05 GEMM -> bias + activation epilogue] x n_gemm -> final small linear
+//   -> last activation -> loss pieces, one CTA per 128-coordinate tile, persistent over tiles.
+//
+// Warp roles (384 threads): warp 0 = weight-stage producer (1-D bulk TMA copies into a ring),
+// warp 1 = MMA issuer (one thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM, two
+// accumulators ping-ponged by layer), warp 2 = TMEM allocator, warps 4..11 = compute: they generate
+// the encoding chunks that feed layer 0 and run every epilogue.  Activations never leave the SM
+// between layers: the epilogue writes the fp16 A-operand image of the next layer in place, 64
+// columns at a time, and the next layer's MMAs trail it chunk by chunk.
+//
+// Mirrors (results, not code): src/models/networks.py:23-35 (encoder), :74-124 (SIREN), :48-69 (FFN);
+// loss pieces follow src/metrics/losses.py and src/train.py:178-182 (see loss_row below).
+#include <cuda_runtime.h>
+#include "inr_ptx.cuh"
+#include "inr_kernels.cuh"
+
+namespace inr {
+
+constexpr int kFwdStages = 8;
+constexpr int kFwdThreads = 384;
+constexpr int kFwdSmem = kActBytes + kFwdStages * kStageBytes + 1024;
+
+__device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
+
+// Per-row loss pieces.  y = network output, t = target.  Returns unnormalised dL/dy parts gA, gB and
+// loss numerators; the normalisation by the (masked) row count happens in the backward prologue.
+struct RowLoss {
+  float lossA, lossB, gA[kMaxOut], gB[kMaxOut];
+};
+__device__ __forceinline__ RowLoss loss_row(const LossDesc& L, int out_f, const float* y, const float* t) {
+  RowLoss r;
+  r.lossA = 0.f; r.lossB = 0.f;
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) { r.gA[o] = 0.f; r.gB[o] = 0.f; }
+  switch (L.kind) {
+    case LOSS_L2:
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) { float e = y[o] - t[o]; r.lossA += e * e; r.gA[o] = e; }
+      break;
+    case LOSS_L1:
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
+        float e = y[o] - t[o]; r.lossA += fabsf(e); r.gA[o] = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
+      }
+      break;
+    case LOSS_MSLE:   // src/metrics/losses.py:26 (NaN for arguments <= 0, as the reference)
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
+        float ax = y[o] + 1.f + 1e-9f;
+        float d = logf(ax) - logf(t[o] + 1.f + 1e-9f);
+        r.lossA += d * d; r.gA[o] = d / ax;
+      }
+      break;
+    case LOSS_TANH:   // src/metrics/losses.py:131
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
+        float tx = tanh_acc(y[o]), ty = tanh_acc(t[o]);
+        float d = tx - ty; r.lossA += d * d; r.gA[o] = d * (1.f - tx * tx);
+      }
+      break;
+    case LOSS_LSL: {  // src/metrics/losses.py:221-223, complex pairs, |x| detached
+      float e0 = y[0] - t[0], e1 = y[1] - t[1];
+      float d = sqrtf(y[0] * y[0] + y[1] * y[1]) + L.eps;
+      float inv = 1.f / (d * d);
+      r.lossA = (e0 * e0 + e1 * e1) * inv; r.gA[0] = e0 * inv; r.gA[1] = e1 * inv;
+    } break;
+    case LOSS_HDR: {  // src/metrics/losses.py:250-259 in separable form
+      float e0 = y[0] - t[0], e1 = y[1] - t[1];
+      float ae2 = e0 * e0 + e1 * e1;
+      float ax2 = y[0] * y[0] + y[1] * y[1];
+      float d = sqrtf(ax2) + L.eps;
+      float lg = logf(sqrtf(ae2) / d);
+      float inv = 1.f / (d * d);
+      r.lossA = lg * lg;
+      r.lossB = ax2 * inv;
+      float c = 2.f * lg / ae2;
+      r.gA[0] = c * e0; r.gA[1] = c * e1;
+      r.gB[0] = 2.f * y[0] * inv; r.gB[1] = 2.f * y[1] * inv;
+    } break;
+    default: break;
+  }
+  return r;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_constant__ FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* act = smem;
+  uint8_t* wring = smem + kActBytes;
+  __shared__ uint64_t w_full[kFwdStages], w_empty[kFwdStages], in_full[4], in_empty[4], act_full[4], acc_full[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float out_part[kTileM][kMaxOut];
+  __shared__ float red[4][8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const ChainModel& M = a.m;
+  const int n_tiles = a.w.n_tiles;
+  const int row_base = a.row_offset ? *a.row_offset : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < kFwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 256); mbar_init(&in_empty[i], 1); mbar_init(&act_full[i], 128); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_fence_init();
+    if (blockIdx.x == 0 && a.step_counter) *a.step_counter += 1;
+  }
+  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weight-stage producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < M.n_gemm; ++l) {
+          const int nst = (l == 0 ? M.k0 : kWidth) / kStageK;
+          const uint8_t* src = a.wpack + M.wf_off[l];
+          for (int s = 0; s < nst; ++s, ++it) {
+            const uint32_t slot = it % kFwdStages, ph = (it / kFwdStages) & 1;
+            mbar_wait(&w_empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&w_full[slot], kStageBytes);
+            bulk_g2s(wring + slot * kStageBytes, src + static_cast<size_t>(s) * kStageBytes, kStageBytes, &w_full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, kWidth, false, false);
+      uint32_t it = 0, inq = 0, act_use = 0;
+      const uint32_t act_s = smem_u32(act), wring_s = smem_u32(wring);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < M.n_gemm; ++l) {
+          const uint32_t acc = tmem + (l & 1) * kWidth;
+          const int nchunks = (l == 0 ? M.k0 : kWidth) / kChunkCols;
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t a_base, in_slot = 0;
+            if (l == 0) {
+              in_slot = inq & 3;
+              mbar_wait(&in_full[in_slot], (inq >> 2) & 1);
+              a_base = act_s + in_slot * kChunkBytes;
+            } else {
+              mbar_wait(&act_full[c], act_use & 1);
+              a_base = act_s + c * kChunkBytes;
+            }
+            tc_fence_after();
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2, ++it) {
+              const uint32_t slot = it % kFwdStages;
+              mbar_wait(&w_full[slot], (it / kFwdStages) & 1);
+              tc_fence_after();
+              const uint32_t b_base = wring_s + slot * kStageBytes;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t da = umma_smem_desc(a_base + (s2 * 2 + kk) * 4096, 2048, 128);
+                const uint64_t db = umma_smem_desc(b_base + kk * 8192, 4096, 128);
+                umma_f16(acc, da, db, idesc, (c | s2 | kk) != 0);
+              }
+              umma_commit(&w_empty[slot]);
+            }
+            if (l == 0) { umma_commit(&in_empty[in_slot]); ++inq; }
+          }
+          umma_commit(&acc_full[l & 1]);
+          if (l > 0) ++act_use;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ compute warps
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;       // column half (0: cols 0..127, 1: cols 128..255)
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t inq = 0, acc_ph[2] = {0, 0};
+    const float* Wl = a.params + M.w_off[M.n_gemm];
+    const float* bl = a.params + M.b_off[M.n_gemm];
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int grow = tile * kTileM + row;            // row inside the batch
+      const bool valid = grow < a.bs;
+      const size_t srow = static_cast<size_t>(row_base) + grow;   // row inside the resident arrays
+      // ---------------- layer-0 input chunks (64 K-columns each) into the 4-slot ring
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+      if (M.input_kind == INPUT_GAUSS && valid) {
+        cx = a.coords[srow * 3 + 0]; cy = a.coords[srow * 3 + 1]; cz = a.coords[srow * 3 + 2];
+      }
+      uint8_t* h0_img = a.ws + a.w.h_off[0] + static_cast<size_t>(tile) * (kTileM * M.k0 * 2);
+      const int n_in_chunks = M.k0 / kChunkCols;
+      for (int c = 0; c < n_in_chunks; ++c, ++inq) {
+        const uint32_t slot = inq & 3;
+        mbar_wait(&in_empty[slot], ((inq >> 2) & 1) ^ 1);
+        uint8_t* dst = act + slot * kChunkBytes;
+        uint4 v[4];
+        int g0, g1;   // the two pairs of 16-byte k-groups (within the chunk) this thread fills
+        if (M.input_kind == INPUT_GAUSS) {
+          // chunk c holds [sin f | cos f] for the 32 encoder features f = 32c .. 32c+31; this thread does 16 of them
+          const int f0 = c * 32 + half * 16;
+          float s[16], co[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float* b = a.encB + (f0 + i) * 3;
+            float t = fmaf(cx, __ldg(b), fmaf(cy, __ldg(b + 1), cz * __ldg(b + 2)));   // revolutions
+            t = t - rintf(t);                                                             // exact reduction
+            const float ang = t * 6.283185307179586f;
+            s[i] = fast_sin(ang); co[i] = fast_cos(ang);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            v[j] = make_uint4(pack_h2(s[8 * j], s[8 * j + 1]), pack_h2(s[8 * j + 2], s[8 * j + 3]),
+                              pack_h2(s[8 * j + 4], s[8 * j + 5]), pack_h2(s[8 * j + 6], s[8 * j + 7]));
+            v[2 + j] = make_uint4(pack_h2(co[8 * j], co[8 * j + 1]), pack_h2(co[8 * j + 2], co[8 * j + 3]),
+                                  pack_h2(co[8 * j + 4], co[8 * j + 5]), pack_h2(co[8 * j + 6], co[8 * j + 7]));
+          }
+          g0 = half * 2; g1 = 4 + half * 2;
+        } else {
+          // dense fp32 input: natural column order, this thread converts 32 of the chunk's 64 columns
+          const float* xr = a.x + srow * M.k0 + c * kChunkCols + half * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 p0 = valid ? *reinterpret_cast<const float4*>(xr + 8 * j) : make_float4(0, 0, 0, 0);
+            float4 p1 = valid ? *reinterpret_cast<const float4*>(xr + 8 * j + 4) : make_float4(0, 0, 0, 0);
+            v[j] = make_uint4(pack_h2(p0.x, p0.y), pack_h2(p0.z, p0.w), pack_h2(p1.x, p1.y), pack_h2(p1.z, p1.w));
+          }
+          g0 = half * 4; g1 = half * 4 + 2;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          *reinterpret_cast<uint4*>(dst + (g0 + j) * 2048 + row * 16) = v[j];
+          *reinterpret_cast<uint4*>(dst + (g1 + j) * 2048 + row * 16) = v[2 + j];
+        }
+        if (a.train) {
+          uint8_t* gdst = h0_img + static_cast<size_t>(c) * kChunkBytes;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            st_global_v4(gdst + (g0 + j) * 2048 + row * 16, v[j]);
+            st_global_v4(gdst + (g1 + j) * 2048 + row * 16, v[2 + j]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&in_full[slot]);
+      }
+      // ---------------- epilogues
+      float po[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+      for (int l = 0; l < M.n_gemm; ++l) {
+        const bool last_gemm = (l == M.n_gemm - 1);
+        const float* bias = a.params + M.b_off[l];
+        uint8_t* h_img = a.ws + a.w.h_off[l + 1] + static_cast<size_t>(tile) * kActBytes;
+        uint8_t* d_img = a.ws + a.w.d_off[l] + static_cast<size_t>(tile) * kActBytes;
+        mbar_wait(&acc_full[l & 1], acc_ph[l & 1]);
+        acc_ph[l & 1] ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          const int col0 = half * 128 + g * 32;
+          float v[32];
+          tmem_ld32(tmem + t_lane + (l & 1) * kWidth + col0, v);
+          tmem_ld_wait();
+          uint4 hv[4], dv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float h[8], d[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float z = v[8 * j + i] + __ldg(bias + col0 + 8 * j + i);
+              if (ACT == ACT_SIN) {
+                const float arg = M.w0 * z;
+                h[i] = fast_sin(arg);
+                d[i] = M.w0 * fast_cos(arg);
+              } else {
+                h[i] = fmaxf(z, 0.f);
+                d[i] = z > 0.f ? 1.f : 0.f;
+              }
+            }
+            hv[j] = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            dv[j] = make_uint4(pack_h2(d[0], d[1]), pack_h2(d[2], d[3]), pack_h2(d[4], d[5]), pack_h2(d[6], d[7]));
+            if (last_gemm) {
+#pragma unroll
+              for (int o = 0; o < kMaxOut; ++o)
+                if (o < M.out_f) {
+                  const float* w = Wl + o * kWidth + col0 + 8 * j;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) po[o] = fmaf(h[i], __ldg(w + i), po[o]);
+                }
+            }
+          }
+          const int kg0 = col0 >> 3;
+          if (!last_gemm) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(act + (kg0 + j) * 2048 + row * 16) = hv[j];
+          }
+          if (a.train) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              st_global_v4(h_img + (kg0 + j) * 2048 + row * 16, hv[j]);
+              st_global_v4(d_img + (kg0 + j) * 2048 + row * 16, dv[j]);
+            }
+          }
+          if (!last_gemm && (g & 1)) {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&act_full[half * 2 + (g >> 1)]);
+          }
+        }
+      }
+      // ---------------- final linear (CUDA cores) + last activation + loss pieces
+      if (half == 1) {
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) out_part[row][o] = po[o];
+      }
+      named_bar_sync(1, 256);
+      if (half == 0) {
+        float y[kMaxOut], t[kMaxOut], dact[kMaxOut];
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+          y[o] = 0.f; t[o] = 0.f; dact[o] = 1.f;
+          if (o < M.out_f) {
+            const float z = po[o] + out_part[row][o] + __ldg(bl + o);
+            if (M.last_act == LAST_TANH) { y[o] = tanh_acc(z); dact[o] = 1.f - y[o] * y[o]; }
+            else if (M.last_act == LAST_SIGMOID) { y[o] = 1.f / (1.f + expf(-z)); dact[o] = y[o] * (1.f - y[o]); }
+            else y[o] = z;
+          }
+        }
+        if (valid && a.out) {
+          for (int o = 0; o < M.out_f; ++o) a.out[(static_cast<size_t>(grow)) * M.out_f + o] = y[o];
+        }
+        if (a.train) {
+          float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
+          float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && a.gt && a.loss.kind != LOSS_NONE) {
+            const bool in_loss = a.mask ? (a.mask[srow] != 0) : true;
+            if (a.loss.kind == LOSS_HDR) {   // filter term runs over ALL batch rows (unmasked kcoords)
+              const float kx = a.coords[srow * 3 + 1], ky = a.coords[srow * 3 + 2];
+              const float f = expf(-(kx * kx + ky * ky) / (2.f * a.loss.sigma * a.loss.sigma));
+              fs = (1.f - f) * (1.f - f);
+            }
+            if (in_loss) {
+              for (int o = 0; o < M.out_f; ++o) t[o] = a.gt[srow * M.out_f + o];
+              RowLoss r = loss_row(a.loss, M.out_f, y, t);
+              lA = r.lossA; lB = r.lossB; cnt = 1.f;
+              float ga[kMaxOut], gb[kMaxOut];
+#pragma unroll
+              for (int o = 0; o < kMaxOut; ++o) {
+                ga[o] = r.gA[o] * dact[o]; gb[o] = r.gB[o] * dact[o];
+                amA = fmaxf(amA, fabsf(ga[o])); amB = fmaxf(amB, fabsf(gb[o]));
+              }
+              gq = make_float4(ga[0], ga[1], gb[0], gb[1]);
+            }
+          }
+          // gradient pieces (out_f <= 2 packs A,B in one float4; wider outputs use A only, 4 floats)
+          float* gdst = reinterpret_cast<float*>(a.ws + a.w.g_off) + (static_cast<size_t>(tile) * kTileM + row) * 4;
+          *reinterpret_cast<float4*>(gdst) = gq;
+          // deterministic tile partials: warp shuffle tree, then 4 warps in fixed order
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            lA += __shfl_xor_sync(0xffffffffu, lA, off); lB += __shfl_xor_sync(0xffffffffu, lB, off);
+            fs += __shfl_xor_sync(0xffffffffu, fs, off); cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+            amA = fmaxf(amA, __shfl_xor_sync(0xffffffffu, amA, off));
+            amB = fmaxf(amB, __shfl_xor_sync(0xffffffffu, amB, off));
+          }
+          if (lane == 0) { red[q][0] = lA; red[q][1] = lB; red[q][2] = fs; red[q][3] = cnt; red[q][4] = amA; red[q][5] = amB; }
+          named_bar_sync(2, 128);
+          if (q == 0 && lane == 0) {
+            float* pdst = reinterpret_cast<float*>(a.ws + a.w.part_off) + static_cast<size_t>(tile) * kPartialsPerTile;
+            pdst[0] = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+            pdst[1] = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+            pdst[2] = (red[0][2] + red[1][2]) + (red[2][2] + red[3][2]);
+            pdst[3] = (red[0][3] + red[1][3]) + (red[2][3] + red[3][3]);
+            pdst[4] = fmaxf(fmaxf(red[0][4], red[1][4]), fmaxf(red[2][4], red[3][4]));
+            pdst[5] = fmaxf(fmaxf(red[0][5], red[1][5]), fmaxf(red[2][5], red[3][5]));
+            pdst[6] = 0.f; pdst[7] = 0.f;
+          }
+          named_bar_sync(2, 128);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+cudaError_t launch_chain_fwd(const FwdArgs& a, int n_sm, cudaStream_t stream) {
+  const int grid = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
+  if (grid <= 0) return cudaSuccess;
+  cudaError_t e;
+  if (a.m.act == ACT_SIN) {
+    e = cudaFuncSetAttribute(chain_fwd_kernel<ACT_SIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+    if (e != cudaSuccess) return e;
+    chain_fwd_kernel<ACT_SIN><<<grid, kFwdThreads, kFwdSmem, stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(chain_fwd_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+    if (e != cudaSuccess) return e;
+    chain_fwd_kernel<ACT_RELU><<<grid, kFwdThreads, kFwdSmem, stream>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace inr

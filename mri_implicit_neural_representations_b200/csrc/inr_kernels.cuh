@@ -1,0 +1,146 @@
+// Shared host/device descriptors for the fused coordinate-MLP ("chain") training kernels.
+//
+// Data layout in HBM (all fp16 "images" are exact shared-memory pictures of UMMA operands):
+//   activation / gradient image of one 128-row tile, F features:
+//       elem(row r, feature f) at byte (f/8)*2048 + r*16 + (f%8)*2          (size 256*F bytes)
+//     - read as a K-major A operand (K = features) by forward / dgrad   (LBO 2048, SBO 128)
+//     - read as an MN-major operand (K = rows)      by wgrad            (LBO 128,  SBO 2048)
+//   packed weight stage (256 outputs x 32 K):  elem(n, kk) at (kk/8)*4096 + n*16 + (kk%8)*2  (16 KB)
+#pragma once
+#include <cstdint>
+
+namespace inr {
+
+constexpr int kTileM = 128;          // coordinates per tile (UMMA M)
+constexpr int kWidth = 256;          // hidden width handled by one UMMA N
+constexpr int kStageK = 32;          // K columns per packed weight stage
+constexpr int kStageBytes = kWidth * kStageK * 2;   // 16384
+constexpr int kChunkCols = 64;       // activation chunk that gates the trailing MMA
+constexpr int kChunkBytes = kTileM * kChunkCols * 2;  // 16384
+constexpr int kActBytes = kTileM * kWidth * 2;        // 65536
+constexpr int kMaxLayers = 12;
+constexpr int kMaxOut = 4;
+constexpr int kDzLastCols = 16;      // last-layer dZ image is padded to one UMMA N=16
+constexpr int kDzLastBytes = kTileM * kDzLastCols * 2;  // 4096
+constexpr int kPartialsPerTile = 8;  // lossA, lossB, fsum, count, amaxA, amaxB, -, -
+constexpr int kScalars = 16;
+
+enum Act { ACT_SIN = 0, ACT_RELU = 1 };
+enum LastAct { LAST_LINEAR = 0, LAST_TANH = 1, LAST_SIGMOID = 2 };
+enum InputKind { INPUT_GAUSS = 0, INPUT_DENSE = 1 };
+enum LossKind { LOSS_NONE = 0, LOSS_L2 = 1, LOSS_L1 = 2, LOSS_MSLE = 3, LOSS_TANH = 4, LOSS_LSL = 5, LOSS_HDR = 6 };
+// scalar slots written by the backward prologue (device memory, fp32)
+enum Scalar { SC_LOSS = 0, SC_SCALE = 1, SC_CA = 2, SC_CB = 3, SC_COUNT = 4, SC_FMEAN = 5, SC_REG = 6, SC_INV_SCALE = 7 };
+
+struct ChainModel {
+  int n_gemm;        // tensor-core layers (reference depth - 1)
+  int k0;            // input features of layer 0 (multiple of 64)
+  int out_f;         // outputs of the final CUDA-core layer (<= kMaxOut)
+  int act;           // Act
+  int last_act;      // LastAct
+  int input_kind;    // InputKind
+  int enc_size;      // E for the gauss encoder (k0 == 2E)
+  float w0;          // 30 for SIREN
+  int w_off[kMaxLayers];     // float offsets of weight [out,in] in the flat parameter buffer; [n_gemm] = last layer
+  int b_off[kMaxLayers];
+  uint32_t wf_off[kMaxLayers];   // byte offsets of forward-packed stages in wpack
+  uint32_t wd_off[kMaxLayers];   // byte offsets of dgrad-packed stages (layers >= 1)
+  int n_params;
+  uint32_t wpack_bytes;
+};
+
+struct LossDesc {
+  int kind;
+  float eps, sigma, factor;   // HDR / LSL options
+};
+
+// Workspace byte offsets for a batch of n_tiles tiles (computed on the host by plan_workspace()).
+struct Workspace {
+  uint64_t h_off[kMaxLayers];    // H image of the input of layer l, l = 0..n_gemm
+  uint64_t d_off[kMaxLayers];    // activation-derivative image of layer l, l = 0..n_gemm-1
+  uint64_t dz_off[kMaxLayers];   // dZ image of layer l, l = 0..n_gemm-1
+  uint64_t dzlast_off;
+  uint64_t g_off;                // [rows_pad][4] fp32: unnormalised dL/dz_last parts A and B
+  uint64_t part_off;             // [n_tiles][8] fp32
+  uint64_t scal_off;             // [16] fp32
+  uint64_t gpart_off;            // [n_split][n_params] fp32 split-K gradient partials (scaled)
+  uint64_t total;
+  int n_tiles, n_split;
+};
+
+struct FwdArgs {
+  ChainModel m;
+  Workspace w;
+  LossDesc loss;
+  const float* params;
+  const uint8_t* wpack;
+  const float* coords;   // [bs,3]
+  const float* x;        // [bs,k0] when input_kind == INPUT_DENSE
+  const float* encB;     // [E,3]
+  const float* gt;       // [bs,out_f] (training) or null
+  const uint8_t* mask;   // [bs] 0/1 or null
+  float* out;            // [bs,out_f] or null
+  uint8_t* ws;
+  const int* row_offset; // optional device scalar added to the batch start row (graph replay)
+  int* step_counter;     // optional: incremented once per launch by block 0 (Adam bias correction)
+  int bs;
+  int train;             // 1: store images + loss pieces
+};
+
+struct BwdArgs {
+  ChainModel m;
+  Workspace w;
+  LossDesc loss;
+  const float* params;
+  const uint8_t* wpack;
+  const float* dout;     // optional external dL/dout [bs,out_f] (autograd path); null -> use loss pieces
+  uint8_t* ws;
+  int bs;
+  int bs_k;              // rows of (unmasked) kcoords for HDR's filter mean
+};
+
+struct WgradUnit {
+  uint64_t a_off, b_off;        // byte offsets of the operand image families inside ws
+  uint32_t a_tile_stride, b_tile_stride, a_sub, b_sub;   // bytes
+  uint32_t a_bytes, b_bytes;    // bytes copied per tile
+  int n;                        // UMMA N (128 or 16)
+  int transposed;               // 1: D[i][o] -> dW[o][i]  (last layer)
+  int out_off, out_ld;          // float offset / leading dim of the weight gradient
+  int row0, col0;               // sub-block origin inside the weight
+  int rows_valid, cols_valid;
+  int bias_off;                 // float offset of the bias gradient or -1
+  int perm_e;                   // >0: columns are in sin/cos-interleaved order with E = perm_e
+};
+
+constexpr int kMaxUnits = 64;
+struct WgradArgs {
+  WgradUnit u[kMaxUnits];
+  int n_units, n_split, n_tiles, n_params;
+  uint8_t* ws;
+  uint64_t gpart_off;
+};
+
+struct SegDesc {          // one parameter tensor for the optimiser / packer
+  int off, rows, cols;    // flat float offset; weight [rows, cols] or bias (rows = n, cols = 1)
+  int layer;              // chain layer index or -1 (not packed)
+  int pack_fwd, pack_bwd; // 1: write fp16 copies
+  int perm_e;             // forward K permutation (gauss input layer)
+  uint32_t wf_off, wd_off;
+};
+constexpr int kMaxSegs = 64;
+struct AdamArgs {
+  SegDesc seg[kMaxSegs];
+  int n_seg, n_params, n_split, n_tiles;
+  float* params; float* m; float* v;
+  float* grads;             // optional: unscaled fp32 gradients are written here when non-null
+  uint8_t* wpack;
+  const float* gpart;       // [n_split][n_params] gradient partials (scaled by S), or plain gradients (n_split 1)
+  const float* scal;        // step scalars written by the backward prologue, or null (scale 1, no loss)
+  const float* hyper;       // device: lr, beta1, beta2, eps, weight_decay, reg_l1, reg_l2
+  const int* step;          // device: 1-based step count for bias correction
+  float* loss_out;          // optional device scalar: loss of this step
+  int* row_offset; int row_advance;   // optional: advance the device-side batch cursor
+  int do_adam;              // 0: only reduce partials into grads
+};
+
+}  // namespace inr

@@ -1,0 +1,127 @@
+// Fused optimiser step over the flat parameter buffer (torch.optim.Adam semantics, src/train.py:76,190):
+//   g = (sum over split-K partials, fixed order) / S  [+ L1/L2 regulariser gradient, src/models/regularization.py]
+//   Adam update in fp32, then the fp16 operand copies of every tensor-core weight are re-packed in the
+//   same pass (forward stages, dgrad stages), so the next step's kernels never touch fp32 weights.
+// Also here: the standalone packer (after load_state_dict) and the amax pre-pass for external dL/dout.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include "inr_kernels.cuh"
+
+namespace inr {
+
+__device__ __forceinline__ int find_seg(const SegDesc* seg, int n_seg, int p) {
+  int lo = 0, hi = n_seg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg[mid].off <= p) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void pack_store(const SegDesc& s, uint8_t* wpack, int local, float val) {
+  const int o = local / s.cols, i = local - o * s.cols;
+  const __half h = __float2half_rn(val);
+  if (s.pack_fwd) {
+    int kp = i;
+    if (s.perm_e > 0) {
+      if (i < s.perm_e) kp = 64 * (i >> 5) + (i & 31);
+      else { const int j = i - s.perm_e; kp = 64 * (j >> 5) + 32 + (j & 31); }
+    }
+    const int st = kp >> 5, kk = kp & 31;
+    *reinterpret_cast<__half*>(wpack + s.wf_off + static_cast<size_t>(st) * kStageBytes + (kk >> 3) * 4096 + o * 16 + (kk & 7) * 2) = h;
+  }
+  if (s.pack_bwd) {
+    const int st = o >> 5, kk = o & 31;
+    *reinterpret_cast<__half*>(wpack + s.wd_off + static_cast<size_t>(st) * kStageBytes + (kk >> 3) * 4096 + i * 16 + (kk & 7) * 2) = h;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
+  __shared__ float s_c[4];   // step_size, sqrt(bc2), inv_scale, -
+  if (threadIdx.x == 0) {
+    const float* sc = a.scal;
+    s_c[2] = sc ? sc[SC_INV_SCALE] : 1.f;
+    if (a.do_adam) {
+      const int t = *a.step;
+      const double b1 = a.hyper[1], b2 = a.hyper[2];
+      const double bc1 = 1.0 - pow(b1, static_cast<double>(t));
+      const double bc2 = 1.0 - pow(b2, static_cast<double>(t));
+      s_c[0] = static_cast<float>(static_cast<double>(a.hyper[0]) / bc1);
+      s_c[1] = static_cast<float>(sqrt(bc2));
+    }
+    if (blockIdx.x == 0) {
+      if (a.loss_out && sc) *a.loss_out = sc[SC_LOSS];
+      if (a.row_offset) *a.row_offset += a.row_advance;
+    }
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_params) return;
+  const float* gp = a.gpart;
+  float g = 0.f;
+  for (int s = 0; s < a.n_split; ++s) g += gp[static_cast<size_t>(s) * a.n_params + p];
+  g *= s_c[2];
+  float w = a.params[p];
+  if (a.do_adam) {
+    const float l1 = a.hyper[5], l2 = a.hyper[6];
+    if (l1 != 0.f) g += l1 * (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f));
+    if (l2 != 0.f) g += 2.f * l2 * w;
+  }
+  if (a.grads) a.grads[p] = g;
+  if (!a.do_adam) return;
+  const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
+  if (wd != 0.f) g = fmaf(wd, w, g);
+  const float m = b1 * a.m[p] + (1.f - b1) * g;
+  const float v = b2 * a.v[p] + (1.f - b2) * g * g;
+  a.m[p] = m; a.v[p] = v;
+  const float denom = sqrtf(v) / s_c[1] + eps;
+  w = w - s_c[0] * (m / denom);
+  a.params[p] = w;
+  const int si = find_seg(a.seg, a.n_seg, p);
+  const SegDesc& sg = a.seg[si];
+  if (sg.pack_fwd | sg.pack_bwd) pack_store(sg, a.wpack, p - sg.off, w);
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ AdamArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_params) return;
+  const int si = find_seg(a.seg, a.n_seg, p);
+  const SegDesc& sg = a.seg[si];
+  if (sg.pack_fwd | sg.pack_bwd) pack_store(sg, a.wpack, p - sg.off, a.params[p]);
+}
+
+// Tile partials for an externally supplied dL/dout (autograd path): amax only.
+__global__ void __launch_bounds__(128) dout_amax_kernel(const float* dout, int bs, int out_f, float* partials) {
+  __shared__ float red[4];
+  const int tile = blockIdx.x, row = tile * kTileM + threadIdx.x;
+  float am = 0.f;
+  if (row < bs)
+    for (int o = 0; o < out_f; ++o) am = fmaxf(am, fabsf(dout[static_cast<size_t>(row) * out_f + o]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = am;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* p = partials + static_cast<size_t>(tile) * kPartialsPerTile;
+    p[0] = 0.f; p[1] = 0.f; p[2] = 0.f; p[3] = 0.f;
+    p[4] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    p[5] = 0.f; p[6] = 0.f; p[7] = 0.f;
+  }
+}
+
+cudaError_t launch_adam(const AdamArgs& a, cudaStream_t stream) {
+  const int grid = (a.n_params + 255) / 256;
+  adam_kernel<<<grid, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack(const AdamArgs& a, cudaStream_t stream) {
+  const int grid = (a.n_params + 255) / 256;
+  pack_kernel<<<grid, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_dout_amax(const float* dout, int bs, int out_f, float* partials, int n_tiles, cudaStream_t stream) {
+  dout_amax_kernel<<<n_tiles, 128, 0, stream>>>(dout, bs, out_f, partials);
+  return cudaGetLastError();
+}
+
+}  // namespace inr

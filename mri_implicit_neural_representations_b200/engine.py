@@ -1,0 +1,212 @@
+"""Host-side engine: flat fp32 parameter / Adam buffers, fp16 operand copies, workspace, CUDA graphs.
+
+Mirrors the per-batch body of the reference training loop (src/train.py:158-192): every public method
+is a thin wrapper that turns torch tensors into raw device pointers for one C-ABI call."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def selftest_umma(mode: int, variant: int = 0):
+    err, ref = C.c_float(), C.c_float()
+    L.check(L.lib.inr_selftest_umma(mode, variant, C.byref(err), C.byref(ref)), "inr_selftest_umma")
+    return err.value, ref.value
+
+
+class Plan:
+    """Immutable description of one model (inr_plan): layer table, parameter layout, work units."""
+
+    def __init__(self, model: str, net: dict, encoder: Optional[dict] = None):
+        enc = encoder or {"embedding": "none"}
+        if model not in L.MODEL:
+            raise NotImplementedError(model)                      # src/train.py:69-70
+        if model == "FFN":
+            last = "sigmoid"                                       # src/models/networks.py:63
+        elif net.get("last_tanh", False):
+            last = "tanh"                                          # src/models/networks.py:94-95
+        elif not net.get("network_last_linear", True):
+            raise L.InrError("SIREN with a sine output layer is not built")
+        else:
+            last = "linear"
+        kind = enc.get("embedding", "none")
+        if kind not in L.ENC:
+            raise L.InrError(f"encoder '{kind}' is not built into the fused kernels")
+        self.desc = L.ModelDesc(L.MODEL[model], int(net["network_input_size"]), int(net["network_output_size"]),
+                                int(net["network_depth"]), int(net["network_width"]), L.LAST[last],
+                                L.ENC[kind], int(enc.get("embedding_size", 0)) if kind == "gauss" else 0, 30.0)
+        self.model, self.net, self.encoder = model, dict(net), dict(enc)
+        h = C.c_void_p()
+        L.check(L.lib.inr_plan_create(C.byref(self.desc), C.byref(h)), "inr_plan_create")
+        self.handle = h
+        n = C.c_int64()
+        L.check(L.lib.inr_plan_param_count(h, C.byref(n)), "inr_plan_param_count")
+        self.n_params = n.value
+        nt = C.c_int32()
+        L.check(L.lib.inr_plan_tensor_count(h, C.byref(nt)), "inr_plan_tensor_count")
+        self.tensors = []
+        for i in range(nt.value):
+            ti = L.TensorInfo()
+            L.check(L.lib.inr_plan_tensor(h, i, C.byref(ti)), "inr_plan_tensor")
+            self.tensors.append((ti.offset, ti.rows, ti.cols, ti.layer, bool(ti.is_bias)))
+        b = C.c_size_t()
+        L.check(L.lib.inr_wpack_bytes(h, C.byref(b)), "inr_wpack_bytes")
+        self.wpack_bytes = b.value
+
+    def workspace_bytes(self, bs: int) -> int:
+        b = C.c_size_t()
+        L.check(L.lib.inr_workspace_bytes(self.handle, bs, C.byref(b)), "inr_workspace_bytes")
+        return b.value
+
+    def scalars_offset(self, bs: int) -> int:
+        b = C.c_size_t()
+        L.check(L.lib.inr_scalars_offset(self.handle, bs, C.byref(b)), "inr_scalars_offset")
+        return b.value
+
+    def workspace_layout(self, bs: int) -> dict:
+        arr = (C.c_uint64 * 44)()
+        L.check(L.lib.inr_workspace_layout(self.handle, bs, arr, 44), "inr_workspace_layout")
+        v = list(arr)
+        return {"h": v[0:12], "d": v[12:24], "dz": v[24:36], "dzlast": v[36], "g": v[37], "part": v[38],
+                "scal": v[39], "gpart": v[40], "n_tiles": int(v[41]), "n_split": int(v[42]), "total": v[43]}
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            L.lib.inr_plan_destroy(h)
+            self.handle = None
+
+
+class ChainEngine:
+    """Owns the device state of one fit: parameters, Adam moments, fp16 operand copies, workspace."""
+
+    def __init__(self, plan: Plan, max_batch: int, device="cuda", lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, reg_l1=0.0, reg_l2=0.0):
+        if not torch.cuda.is_available():
+            raise L.InrError("ChainEngine needs a CUDA device (no CPU fallback)")
+        self.plan, self.device, self.max_batch = plan, torch.device(device), int(max_batch)
+        P = plan.n_params
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(P, **f32)
+        self.grads = torch.zeros(P, **f32)
+        self.exp_avg = torch.zeros(P, **f32)
+        self.exp_avg_sq = torch.zeros(P, **f32)
+        self.wpack = torch.zeros(plan.wpack_bytes + 1024, dtype=torch.uint8, device=self.device)
+        self.workspace = torch.zeros(plan.workspace_bytes(self.max_batch), dtype=torch.uint8, device=self.device)
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, reg_l1, reg_l2, 0.0], **f32)
+        self.step = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.cursor = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.loss_out = torch.zeros(1, **f32)
+        self.encB = None
+        self._graphs = {}
+
+    # ---- parameters -------------------------------------------------------------------------------
+    def param_views(self):
+        """Views into the flat buffer, one per reference tensor, in state_dict order."""
+        out = []
+        for off, rows, cols, layer, is_bias in self.plan.tensors:
+            v = self.params[off:off + rows * cols]
+            out.append(v if is_bias else v.view(rows, cols))
+        return out
+
+    def grad_views(self):
+        out = []
+        for off, rows, cols, layer, is_bias in self.plan.tensors:
+            v = self.grads[off:off + rows * cols]
+            out.append(v if is_bias else v.view(rows, cols))
+        return out
+
+    def load_tensors(self, tensors):
+        """Copy a list of tensors (reference state_dict values, same order) into the flat buffer and repack."""
+        views = self.param_views()
+        assert len(tensors) == len(views), (len(tensors), len(views))
+        with torch.no_grad():
+            for v, t in zip(views, tensors):
+                v.copy_(t.to(self.device, torch.float32).reshape(v.shape))
+        self.pack()
+
+    def set_encoder(self, B: Optional[torch.Tensor]):
+        self.encB = None if B is None else B.to(self.device, torch.float32).contiguous()
+
+    def set_lr(self, lr: float):
+        self.hyper[0:1].fill_(lr)
+
+    def pack(self):
+        L.check(L.lib.inr_pack_weights(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _stream()), "inr_pack_weights")
+
+    # ---- unfused API (keeps arbitrary PyTorch losses working) --------------------------------------
+    def forward(self, inp: torch.Tensor, train: bool = False) -> torch.Tensor:
+        bs = inp.shape[0]
+        assert bs <= self.max_batch
+        inp = inp.to(self.device, torch.float32).contiguous()
+        out = torch.empty(bs, self.plan.desc.out_features, dtype=torch.float32, device=self.device)
+        L.check(L.lib.inr_forward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(inp), _ptr(self.encB), bs,
+                                  _ptr(self.workspace), _ptr(out), 1 if train else 0, _stream()), "inr_forward")
+        return out
+
+    def backward(self, dout: torch.Tensor) -> torch.Tensor:
+        bs = dout.shape[0]
+        dout = dout.to(self.device, torch.float32).contiguous()
+        L.check(L.lib.inr_backward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(dout), bs,
+                                   _ptr(self.workspace), _ptr(self.grads), _stream()), "inr_backward")
+        return self.grads
+
+    def adam_step(self):
+        self.step += 1
+        L.check(L.lib.inr_adam_step(self.plan.handle, _ptr(self.params), _ptr(self.grads), _ptr(self.exp_avg),
+                                    _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _stream()),
+                "inr_adam_step")
+
+    # ---- fused step --------------------------------------------------------------------------------
+    def train_step(self, loss: str, coords: Optional[torch.Tensor], gt: torch.Tensor, bs: int, x: Optional[torch.Tensor] = None,
+                   mask: Optional[torch.Tensor] = None, loss_opts: Optional[dict] = None, use_cursor: bool = False,
+                   out: Optional[torch.Tensor] = None):
+        """One fused forward+loss+backward+Adam step on rows [cursor, cursor+bs) (or [0, bs)) of the resident
+        arrays.  Asynchronous; the loss lands in self.loss_out."""
+        o = loss_opts or {}
+        ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
+                        float(o.get("hdr_ff_factor", 0.0)))
+        L.check(L.lib.inr_train_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                     _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords), _ptr(x), _ptr(self.encB),
+                                     _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None, _ptr(self.workspace),
+                                     _ptr(out), _ptr(self.loss_out), _stream()), "inr_train_step")
+
+    def read_image(self, kind: str, layer: int, bs: int) -> torch.Tensor:
+        """Decode one saved fp16 operand image family back to a [rows_pad, F] fp32 matrix (tests / debugging).
+        kind: 'h' (input of `layer`), 'd' (act'(z) of `layer`), 'dz' (dZ of `layer`), 'dzlast'."""
+        lay = self.plan.workspace_layout(bs)
+        T = lay["n_tiles"]
+        n_gemm = self.plan.desc.depth - 1
+        if kind == "dzlast":
+            F, off = 16, lay["dzlast"]
+        else:
+            F = self.plan.desc.in_features if (kind == "h" and layer == 0) else self.plan.desc.width
+            off = lay[kind][layer]
+        nbytes = T * 128 * F * 2
+        img = self.workspace[off:off + nbytes].view(torch.float16).view(T, F // 8, 128, 8)
+        mat = img.permute(0, 2, 1, 3).reshape(T * 128, F).float()
+        if kind == "h" and layer == 0 and self.plan.desc.encoder == L.ENC["gauss"]:
+            E = self.plan.desc.enc_size           # undo the sin/cos chunk interleave of the in-kernel encoder
+            kp = torch.arange(F, device=mat.device)
+            c64, kk = kp // 64, kp % 64
+            real = torch.where(kk < 32, 32 * c64 + kk, E + 32 * c64 + kk - 32)
+            out = torch.empty_like(mat)
+            out[:, real] = mat
+            mat = out
+        return mat
+
+    def scalars(self, bs: int) -> torch.Tensor:
+        off = self.plan.scalars_offset(bs)
+        return self.workspace[off:off + 64].view(torch.float32).clone()

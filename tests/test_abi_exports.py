@@ -1,0 +1,74 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/inr_b200.h declares,
+and the host-only entry points (plan construction, layout arithmetic, argument validation) behave."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def inr():
+    from mri_implicit_neural_representations_b200 import build
+    build.build()
+    import mri_implicit_neural_representations_b200 as m
+    return m
+
+
+def test_library_exports_every_declared_symbol(inr):
+    header = open(os.path.join(ROOT, "include", "inr_b200.h")).read()
+    declared = set(re.findall(r"\b(inr_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(inr.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    from mri_implicit_neural_representations_b200 import _lib
+    assert declared == set(_lib.EXPORTS)
+
+
+NET = {"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256}
+ENC = {"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3}
+
+
+def test_plan_layout_matches_reference_state_dict_order(inr):
+    from oracle import inr_oracle as O
+    plan = inr.Plan("SIREN", NET, ENC)
+    sd = O.siren_init(dict(NET))
+    assert plan.n_params == sum(v.numel() for v in sd.values()) == 263426
+    off = 0
+    for (o, rows, cols, layer, is_bias), (k, v) in zip(plan.tensors, sd.items()):
+        assert o == off and rows * cols == v.numel(), k
+        assert is_bias == k.endswith("bias")
+        off += v.numel()
+
+
+def test_workspace_layout_is_consistent(inr):
+    plan = inr.Plan("SIREN", NET, ENC)
+    for bs in (1, 128, 129, 10000, 102400):
+        lay = plan.workspace_layout(bs)
+        assert lay["n_tiles"] == (bs + 127) // 128
+        assert lay["total"] == plan.workspace_bytes(bs)
+        regions = sorted([lay["scal"], lay["part"], lay["g"], *lay["h"][:4], *lay["d"][:3], *lay["dz"][:3],
+                          lay["dzlast"], lay["gpart"]])
+        assert len(set(regions)) == len(regions) and regions[-1] < lay["total"]
+        assert 1 <= lay["n_split"] <= lay["n_tiles"]
+
+
+def test_unsupported_shapes_fail_loudly(inr):
+    with pytest.raises(inr.InrError):
+        inr.Plan("SIREN", dict(NET, network_width=192), ENC)
+    with pytest.raises(inr.InrError):
+        inr.Plan("SIREN", dict(NET, network_input_size=500), {"embedding": "none"})
+    with pytest.raises(NotImplementedError):
+        inr.Plan("NoSuchModel", NET, ENC)
+
+
+def test_no_cpu_fallback(inr):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    plan = inr.Plan("SIREN", NET, ENC)
+    with pytest.raises(inr.InrError):
+        inr.ChainEngine(plan, max_batch=256)

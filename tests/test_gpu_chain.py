@@ -1,0 +1,138 @@
+"""GPU parity tests of the fused chain kernels (SIREN / FFN) through the C ABI.
+
+Oracle: oracle/inr_oracle.py (CPU, fp32) on the same seeded inputs; golden digests from the
+reference itself (tests/golden).  Tolerance: north_star's <= 1e-3 relative L2 per layer."""
+import pytest
+import torch
+
+from oracle import golden_util as G
+from oracle import inr_oracle as O
+from oracle.cases import case_setup, loss_and_grad
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def inr():
+    import mri_implicit_neural_representations_b200 as m
+    return m
+
+
+def _engine(inr, name, bs=None):
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup(name)
+    plan = inr.Plan(model_kind, net, enc_cfg)
+    eng = inr.ChainEngine(plan, max_batch=bs or coords.shape[0], lr=G.LR)
+    eng.load_tensors(list(sd.values()))
+    eng.set_encoder(encB)
+    return plan, eng
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_umma_selftest(inr, mode):
+    err, ref = inr.selftest_umma(mode, 0)
+    assert err <= 2e-3 * max(ref, 1.0), (mode, err, ref)
+
+
+@pytest.mark.parametrize("name", ["siren_l2", "siren_tanh", "ffn_l2"])
+def test_forward_per_layer(inr, name):
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup(name)
+    plan, eng = _engine(inr, name)
+    bs, depth = coords.shape[0], net["network_depth"]
+    x = O.encode(coords, encB, enc_cfg["embedding"])
+    tr = []
+    out_ref = O.model_forward(model_kind, sd, x, net, trace=tr)
+    out = eng.forward(coords.cuda(), train=True)
+    assert rel(eng.read_image("h", 0, bs)[:bs], x) <= TOL
+    for l in range(depth - 1):
+        assert rel(eng.read_image("h", l + 1, bs)[:bs], tr[l][1]) <= TOL, f"H{l+1}"
+    assert rel(out, out_ref) <= TOL
+
+
+@pytest.mark.parametrize("name", ["siren_l2", "ffn_l2"])
+def test_forward_dense_input_and_inference(inr, name):
+    """encoder 'none' plan: the [bs,512] embedding is passed in as the reference's model(x) receives it."""
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup(name)
+    plan = inr.Plan(model_kind, net, {"embedding": "none"})
+    eng = inr.ChainEngine(plan, max_batch=coords.shape[0])
+    eng.load_tensors(list(sd.values()))
+    x = O.encode(coords, encB, "gauss")
+    out_ref = O.model_forward(model_kind, sd, x, net)
+    out = eng.forward(x.cuda(), train=False)
+    assert rel(out, out_ref) <= TOL
+
+
+@pytest.mark.parametrize("name", ["siren_l2", "siren_tanh", "ffn_l2"])
+def test_backward_external_dout(inr, name):
+    """inr_backward (autograd path): dgrad images and every weight / bias gradient vs the explicit oracle."""
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup(name)
+    plan, eng = _engine(inr, name)
+    bs, depth = coords.shape[0], net["network_depth"]
+    x = O.encode(coords, encB, enc_cfg["embedding"])
+    tr = []
+    out_ref = O.model_forward(model_kind, sd, x, net, trace=tr)
+    _, dout = loss_and_grad(loss_kind, opts, out_ref, gt, coords)
+    if model_kind == "SIREN":
+        grads_ref, dzs = O.siren_backward(sd, x, tr, dout, depth, net.get("last_tanh", False))
+    else:
+        grads_ref, dzs = O.ffn_backward(sd, x, tr, dout, depth)
+    eng.forward(coords.cuda(), train=True)
+    g = eng.backward(dzs[depth - 1].cuda())          # contract: dL/dz_last
+    S = float(eng.scalars(bs)[1])
+    for l in range(depth - 1):
+        assert rel(eng.read_image("dz", l, bs)[:bs] / S, dzs[l]) <= TOL, f"dZ{l}"
+    for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
+        gv = g[off:off + rows * cols].view(grads_ref[k].shape)
+        assert rel(gv, grads_ref[k]) <= TOL, k
+
+
+@pytest.mark.parametrize("name", ["siren_l2", "siren_tanh", "siren_l1", "ffn_l2", "ffn_msle"])
+def test_fused_train_steps_vs_reference_golden(inr, name):
+    """Three fused steps (forward + loss + backward + Adam) against the reference's own run
+    (tests/golden/<name>.json): loss of every step and final parameters."""
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup(name)
+    plan, eng = _engine(inr, name)
+    bs = coords.shape[0]
+    gold = G.load_golden(name)
+    cd, gd = coords.cuda(), gt.cuda()
+    out = torch.empty(bs, 2, device="cuda")
+    for step in range(G.N_ADAM_STEPS):
+        eng.train_step(loss_kind, cd, gd, bs, loss_opts=opts, out=out if step == 0 else None)
+        loss = float(eng.loss_out)
+        assert abs(loss - gold["losses"][step]) <= 2e-3 * abs(gold["losses"][step]), (step, loss)
+        if step == 0:
+            assert not G.digest_close(gold["out"], G.tensor_digest(out.cpu()), 2e-3)
+    assert int(eng.step) == G.N_ADAM_STEPS
+    for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
+        dg = G.tensor_digest(eng.params[off:off + rows * cols].cpu())
+        gf = gold["final"][k]
+        assert abs(dg["l2"] - gf["l2"]) <= 1e-3 * gf["l2"], k
+
+
+def test_ragged_batch_and_mask(inr):
+    """bs not a multiple of 128 and a row mask (src/train.py:172-177): loss and gradients vs oracle."""
+    name = "siren_l2"
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, _ = case_setup(name)
+    bs = 333
+    coords, gt = coords[:bs], gt[:bs]
+    mask = (torch.arange(bs) % 3 != 0)
+    plan, eng = _engine(inr, name, bs=bs)
+    x = O.encode(coords, encB, "gauss")
+    tr = []
+    out_ref = O.model_forward(model_kind, sd, x, net, trace=tr)
+    val, dsel = O.loss_l2(out_ref[mask], gt[mask])
+    dout = torch.zeros_like(out_ref)
+    dout[mask] = dsel
+    grads_ref, _ = O.siren_backward(sd, x, tr, dout, net["network_depth"])
+    eng.hyper[0:1].fill_(0.0)     # lr 0: parameters stay, gradients are still produced
+    eng.train_step("L2", coords.cuda(), gt.cuda(), bs, mask=mask.to(torch.uint8).cuda())
+    assert abs(float(eng.loss_out) - float(val)) <= 1e-3 * float(val)
+    # first Adam moment after one step = (1-beta1) * g
+    for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
+        gv = eng.exp_avg[off:off + rows * cols].view(grads_ref[k].shape) / 0.1
+        assert rel(gv, grads_ref[k]) <= TOL, k
