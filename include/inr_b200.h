@@ -135,6 +135,13 @@ int inr_train_step(const inr_plan* plan, const inr_loss_desc* loss, float* param
                    const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev, void* workspace,
                    float* out, float* loss_out_dev, void* stream);
 
+/* measurement only: runs inr_train_step `reps` times with CUDA events between its four kernels and returns the
+ * average duration in ms of {forward, dgrad, wgrad, optimiser} in ms_out4 (host).  Synchronises. */
+int inr_profile_step(const inr_plan* plan, const inr_loss_desc* loss, float* params, float* exp_avg,
+                     float* exp_avg_sq, void* wpack, const float* hyper_dev, int32_t* step_dev,
+                     const float* coords, const float* input_x, const float* encB, const float* gt,
+                     const uint8_t* mask, int64_t bs, void* workspace, int32_t reps, float* ms_out4, void* stream);
+
 /* one tcgen05 GEMM per operand-layout family against a host loop (allocates + synchronises; test only) */
 int inr_selftest_umma(int mode, int variant, float* max_abs_err, float* ref_absmax);
 

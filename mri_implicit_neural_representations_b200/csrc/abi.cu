@@ -251,13 +251,14 @@ extern "C" int inr_forward(const inr_plan* p, const float* params, const void* w
 }
 
 static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& loss, const float* params, const void* wpack,
-                        const float* dout, int64_t bs, void* ws, cudaStream_t st) {
+                        const float* dout, int64_t bs, void* ws, cudaStream_t st, cudaEvent_t mid = nullptr) {
   BwdArgs b{};
   b.m = p->model; b.w = w; b.loss = loss;
   b.params = params; b.wpack = static_cast<const uint8_t*>(wpack); b.dout = dout;
   b.ws = static_cast<uint8_t*>(ws); b.bs = static_cast<int>(bs); b.bs_k = static_cast<int>(bs);
   cudaError_t e = launch_chain_bwd(b, p->n_sm, st);
   if (e != cudaSuccess) return cuda_fail(e, "chain_bwd_kernel");
+  if (mid) cudaEventRecord(mid, st);
   WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g);
   e = launch_wgrad(g, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel");
@@ -294,10 +295,10 @@ extern "C" int inr_adam_step(const inr_plan* p, float* params, const float* grad
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "adam_kernel");
 }
 
-extern "C" int inr_train_step(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
-                              const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
-                              const float* encB, const float* gt, const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev,
-                              void* workspace, float* out, float* loss_out_dev, void* stream) {
+static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
+                           const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
+                           const float* encB, const float* gt, const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev,
+                           void* workspace, float* out, float* loss_out_dev, cudaStream_t st, cudaEvent_t* ev) {
   if (!p || !loss || !params || !m || !v || !wpack || !hyper_dev || !step_dev || !gt || !workspace || bs <= 0)
     return fail(INR_EINVAL, "bad argument");
   const bool gauss = p->model.input_kind == INPUT_GAUSS;
@@ -308,15 +309,17 @@ extern "C" int inr_train_step(const inr_plan* p, const inr_loss_desc* loss, floa
     return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
   if (loss->kind == INR_LOSS_HDR && !coords) return fail(INR_EINVAL, "HDR loss needs kcoords");
   if (p->model.out_f > 2) return fail(INR_EUNSUPPORTED, "fused loss path packs at most 2 outputs");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace w = plan_workspace(p, bs);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   LossDesc L{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
+  if (ev) cudaEventRecord(ev[0], st);
   int rc = run_forward(p, w, L, params, wpack, coords, input_x, encB, gt, mask, bs, workspace, out, 1, row_cursor_dev,
                        step_dev, st);
   if (rc) return rc;
-  rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st);
+  if (ev) cudaEventRecord(ev[1], st);
+  rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st, ev ? ev[2] : nullptr);
   if (rc) return rc;
+  if (ev) cudaEventRecord(ev[3], st);
   AdamArgs a; fill_adam(p, a);
   a.n_split = w.n_split; a.n_tiles = w.n_tiles;
   a.params = params; a.m = m; a.v = v; a.wpack = static_cast<uint8_t*>(wpack);
@@ -326,5 +329,37 @@ extern "C" int inr_train_step(const inr_plan* p, const inr_loss_desc* loss, floa
   a.row_offset = row_cursor_dev; a.row_advance = static_cast<int>(bs);
   a.do_adam = 1;
   cudaError_t e = launch_adam(a, st);
+  if (ev) cudaEventRecord(ev[4], st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "adam_kernel");
+}
+
+extern "C" int inr_train_step(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
+                              const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
+                              const float* encB, const float* gt, const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev,
+                              void* workspace, float* out, float* loss_out_dev, void* stream) {
+  return train_step_impl(p, loss, params, m, v, wpack, hyper_dev, step_dev, coords, input_x, encB, gt, mask, bs,
+                         row_cursor_dev, workspace, out, loss_out_dev, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+extern "C" int inr_profile_step(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
+                                const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
+                                const float* encB, const float* gt, const uint8_t* mask, int64_t bs, void* workspace,
+                                int32_t reps, float* ms_out4, void* stream) {
+  if (!ms_out4 || reps <= 0) return fail(INR_EINVAL, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t ev[5];
+  for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
+  double acc[4] = {0, 0, 0, 0};
+  int rc = INR_OK;
+  for (int r = 0; r < reps && rc == INR_OK; ++r) {
+    rc = train_step_impl(p, loss, params, m, v, wpack, hyper_dev, step_dev, coords, input_x, encB, gt, mask, bs, nullptr,
+                         workspace, nullptr, nullptr, st, ev);
+    if (rc) break;
+    cudaError_t e = cudaEventSynchronize(ev[4]);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "profile step"); break; }
+    for (int k = 0; k < 4; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); acc[k] += ms; }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int k = 0; k < 4; ++k) ms_out4[k] = static_cast<float>(acc[k] / reps);
+  return rc;
 }

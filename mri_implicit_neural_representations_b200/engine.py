@@ -183,6 +183,18 @@ class ChainEngine:
                                      _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None, _ptr(self.workspace),
                                      _ptr(out), _ptr(self.loss_out), _stream()), "inr_train_step")
 
+    def profile_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, reps: int = 20):
+        """Average device time (ms) of the four kernels of one step: forward, dgrad, wgrad, optimiser."""
+        o = loss_opts or {}
+        ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
+                        float(o.get("hdr_ff_factor", 0.0)))
+        ms = (C.c_float * 4)()
+        L.check(L.lib.inr_profile_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg),
+                                       _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords),
+                                       _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.workspace), reps, ms,
+                                       _stream()), "inr_profile_step")
+        return {"forward": ms[0], "dgrad": ms[1], "wgrad": ms[2], "optimiser": ms[3]}
+
     def read_image(self, kind: str, layer: int, bs: int) -> torch.Tensor:
         """Decode one saved fp16 operand image family back to a [rows_pad, F] fp32 matrix (tests / debugging).
         kind: 'h' (input of `layer`), 'd' (act'(z) of `layer`), 'dz' (dZ of `layer`), 'dzlast'."""

@@ -469,12 +469,18 @@ def siren_backward(sd, x, trace, dout, depth, last_tanh=False, w0=30.0):
     return grads, dzs
 
 
-def ffn_backward(sd, x, trace, dout, depth):
+def ffn_backward(sd, x, trace, dout, depth, masks=None):
+    """``masks`` (optional list of 0/1 tensors per hidden layer) teacher-forces the ReLU derivative: the sign of
+    a pre-activation within rounding error of 0 is precision-dependent, so per-layer gradient parity is
+    judged with the masks of the implementation under test."""
     grads, dzs = {}, [None] * depth
     dh = dout
     for i in reversed(range(depth)):
         z, h = trace[i]
-        dz = dh * h * (1 - h) if i == depth - 1 else dh * (z > 0).to(dh.dtype)
+        if i == depth - 1:
+            dz = dh * h * (1 - h)
+        else:
+            dz = dh * ((z > 0).to(dh.dtype) if masks is None else masks[i].to(dh.dtype))
         dzs[i] = dz
         hin = x if i == 0 else trace[i - 1][1]
         grads[f"model.{2 * i}.weight"] = dz.t() @ hin
