@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the INR fitting hot path (forward + loss + backward + Adam) -- training coordinates / second.
+
+    python bench.py --gpus N --steps K --warmup W              # this engine, N GPUs of one node
+    python bench.py --impl reference --steps K --warmup W      # the reference's CPU path (oracle port), host cores
+
+One "step" = one grid-order batch of the configured size through the whole hot path.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+# BASELINE.json configs[0]: SIREN depth 4 width 256, gauss-512 encoding, image space, L2, batch 10000
+WORKLOADS = {
+    "siren_image_l2_bs10000": dict(
+        model="SIREN", loss="L2", loss_opts=None, batch=10000, image_space=True,
+        net={"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256},
+        encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
+        flop_per_coord=1313792, fwd_flop_per_coord=525312),
+}
+DEFAULT_WORKLOAD = "siren_image_l2_bs10000"
+SLICE = (15, 320, 320)                 # fastMRI-knee-shaped: 15 coils x 320 x 320 after the reference's crop
+LR = 5e-4
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "source": "measured"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self._stop, self.max_mhz = [], set(), threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def build_engine(wl, device, seed):
+    import mri_implicit_neural_representations_b200 as inr
+    from mri_implicit_neural_representations_b200 import init as pinit
+    torch.manual_seed(seed)
+    encB = pinit.encoder_matrix(wl["encoder"])
+    tensors = [t for _, t in pinit.chain_tensors(wl["model"], wl["net"])]
+    plan = inr.Plan(wl["model"], wl["net"], wl["encoder"])
+    eng = inr.ChainEngine(plan, max_batch=wl["batch"], device=device, lr=LR)
+    eng.load_tensors(tensors)
+    eng.set_encoder(encB)
+    return eng, tensors, encB
+
+
+def resident_arrays(wl, device, seed, min_bytes):
+    """Coordinates + targets of enough synthetic slices to exceed L2 (grid-order walk = cold inputs)."""
+    from mri_implicit_neural_representations_b200 import synthetic
+    C, H, W = SLICE
+    coords, gt = [], []
+    n = 0
+    while n * 20 < min_bytes:
+        c, g, _ = synthetic.make_fit_arrays(seed + len(coords), C, H, W, image_space=wl["image_space"])
+        coords.append(c)
+        gt.append(g)
+        n += c.shape[0]
+    return torch.cat(coords).to(device), torch.cat(gt).to(device)
+
+
+def cpu_port_steps(wl, n_steps, warmup, rows_per_step, seed=1234):
+    """The reference's CPU path (oracle port: plain torch fp32 + autograd + Adam) on the host cores."""
+    from oracle import inr_oracle as O
+    from mri_implicit_neural_representations_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(seed)
+    encB = O.encoder_init(wl["encoder"])
+    sd = O.MODEL_INIT[wl["model"]](dict(wl["net"]))
+    C, H, W = SLICE
+    coords, gt, _ = synthetic.make_fit_arrays(seed, C, H, W, image_space=wl["image_space"])
+    need = (n_steps + warmup) * rows_per_step
+    reps = (need + coords.shape[0] - 1) // coords.shape[0]
+    if reps > 1:
+        coords, gt = coords.repeat(reps, 1), gt.repeat(reps, 1)
+    opts = None
+    if wl["loss_opts"]:
+        opts = {"sigma": wl["loss_opts"]["hdr_ff_sigma"], "eps": wl["loss_opts"]["hdr_eps"],
+                "factor": wl["loss_opts"]["hdr_ff_factor"]}
+    if warmup:
+        O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords, gt, warmup, rows_per_step, LR,
+                      wl["loss"], opts)
+    t0 = time.perf_counter()
+    O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords[warmup * rows_per_step:],
+                  gt[warmup * rows_per_step:], n_steps, rows_per_step, LR, wl["loss"], opts)
+    dt = time.perf_counter() - t0
+    return n_steps * rows_per_step / dt, dt
+
+
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bs = wl["batch"]
+    # bound the run: probe one step, shrink the per-step sample if K steps would take > ~150 s
+    v1, dt1 = cpu_port_steps(wl, 1, 1, bs)
+    rows = bs
+    if dt1 * args.steps > 150.0:
+        rows = max(256, int(bs * 150.0 / (dt1 * args.steps)) // 128 * 128)
+    value, dt = cpu_port_steps(wl, args.steps, args.warmup, rows)
+    cores = os.cpu_count() or 1
+    sample = f"{args.steps} steps x {rows} coords of the {bs}-coord batch workload, torch CPU fp32, {torch.get_num_threads()} threads"
+    line = {"impl": "reference", "metric": "train coords/sec (fwd+bwd+Adam)", "value": value, "unit": "coords/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "batch": bs, "slice": list(SLICE)},
+            "cpu_baseline": {"value": value, "unit": "coords/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "coords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=device)
+    bs = wl["batch"]
+    peaks = load_peaks()
+
+    # ---- state: one independent fit per rank (one slice set per GPU, no data-path collective)
+    eng, tensors, encB = build_engine(wl, device, seed=1234 + rank)
+    coords, gt = resident_arrays(wl, device, 1234 + 100 * rank, min_bytes=200 << 20)
+    n_rows = coords.shape[0]
+    steps_per_pass = n_rows // bs
+
+    def reset_cursor():
+        eng.cursor.zero_()
+
+    # eager warm-up (also sets kernel attributes outside capture), then capture one step in a CUDA graph
+    for _ in range(3):
+        eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+    reset_cursor()
+
+    def run_steps(n):
+        done = 0
+        while done < n:
+            pos = int(done % steps_per_pass)
+            if pos == 0 and done > 0:
+                reset_cursor()
+            chunk = min(n - done, steps_per_pass - pos)
+            for _ in range(chunk):
+                graph.replay()
+            done += chunk
+
+    # ---- device-resident throughput (`value`)
+    # clocks ramp over tens of ms from idle: warm up for at least W steps AND ~1.5 s of continuous load
+    run_steps(args.warmup)
+    t_end = time.perf_counter() + 1.5
+    while time.perf_counter() < t_end:
+        run_steps(50)
+        torch.cuda.synchronize()
+    reset_cursor()
+    run_steps(args.warmup % steps_per_pass)      # leave the cursor where a W-step warm-up would
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        e0.record()
+        # steps_per_pass is >> K for the default sizes, so the timed region is a straight run of graph replays
+        for _ in range(args.steps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = world * args.steps * bs / (ms * 1e-3)
+    loss_dev = float(eng.loss_out)
+
+    # ---- per-kernel device times (CUDA events between the four kernels of a step, same stream)
+    reset_cursor()
+    prof = eng.profile_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], reps=200)
+    kern_ms = prof["forward"]
+    fwd_tflops = wl["fwd_flop_per_coord"] * bs / (kern_ms * 1e-3) / 1e12
+    step_tflops = wl["flop_per_coord"] * bs / (ms / args.steps * 1e-3) / 1e12
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + step + D2H of the loss every step
+    h_coords = coords[: bs * 64].cpu().pin_memory()
+    h_gt = gt[: bs * 64].cpu().pin_memory()
+    d_c = torch.empty(bs, 3, device=device)
+    d_g = torch.empty(bs, 2, device=device)
+    h_loss = torch.empty(1).pin_memory()
+
+    def e2e_step(i):
+        j = (i % 64) * bs
+        d_c.copy_(h_coords[j:j + bs], non_blocking=True)
+        d_g.copy_(h_gt[j:j + bs], non_blocking=True)
+        eng.train_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
+        h_loss.copy_(eng.loss_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(h_loss)
+
+    for i in range(max(10, args.warmup // 4)):
+        e2e_step(i)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n_e2e = args.steps
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(n_e2e):
+        e2e_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms_e2e = max(e0.elapsed_time(e1), wall * 1e3)
+    if dist:
+        t = torch.tensor([ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t)
+    e2e_value = world * n_e2e * bs / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v1, dt1 = cpu_port_steps(wl, 1, 1, bs)
+        n_cpu = max(5, min(200, int(12.0 / max(dt1, 1e-3))))
+        v, dt = cpu_port_steps(wl, n_cpu, 1, bs)
+        cpu = {"value": v, "unit": "coords/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{n_cpu} steps x {bs} coords, oracle port (torch CPU fp32, autograd, Adam), {torch.get_num_threads()} threads, {dt:.1f} s"}
+
+    clocks = clk.summary()
+    line = {
+        "metric": "train coords/sec (fwd+bwd+Adam)", "value": value, "unit": "coords/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
+        "config": {"workload": args.workload, "model": wl["model"], "batch_per_gpu": bs, "slice": list(SLICE),
+                   "parallelism": f"independent fit per GPU x{world}" if world > 1 else "single GPU",
+                   "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
+                   "step": "CUDA graph of 4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",
+                   "loss_last_step": loss_dev},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": bs * 20, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / n_e2e, "api": "ChainEngine.train_step (C ABI inr_train_step), pinned host batches"},
+        "gpu_launches": 4 * args.steps,
+        "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                     "frac": fwd_tflops / peaks["tflops_burst"], "traffic": None,
+                     "kernel": "chain_fwd_kernel<SIN>", "kernel_ms": kern_ms,
+                     "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['source']})",
+                     "step_tflops": step_tflops, "step_frac_of_sustained": step_tflops / peaks["tflops_sustained"],
+                     "kernels_ms": prof},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
 
   if (tid == 0) {
     for (int i = 0; i < kBwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&act_full[i], 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&act_full[i], 256); }
     mbar_init(&d_empty, 256);
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_fence_init();
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
         }
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          const int col0 = half * 128 + g * 32;
-          const int chunk = half * 2 + (g >> 1);
-          if ((g & 1) == 0) mbar_wait(&d_full[chunk], dq & 1);
+          const int col0 = (2 * g + half) * 32;   // both halves finish chunk g together -> in-order trailing MMAs
+          const int chunk = g;
+          mbar_wait(&d_full[chunk], dq & 1);
           float v[32];
           if (from_last) {
 #pragma unroll
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) st_global_v4(dz_img + (kg0 + j) * 2048 + row * 16, zv[j]);
-          if (l >= 1 && (g & 1)) {
+          if (l >= 1) {
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&act_full[chunk]);
@@ -263,8 +263,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
 cudaError_t launch_chain_bwd(const BwdArgs& a, int n_sm, cudaStream_t stream) {
   const int grid = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
   if (grid <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-  if (e != cudaSuccess) return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
   chain_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, stream>>>(a);
   return cudaGetLastError();
 }

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
 
   if (tid == 0) {
     for (int i = 0; i < kFwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 256); mbar_init(&in_empty[i], 1); mbar_init(&act_full[i], 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 256); mbar_init(&in_empty[i], 1); mbar_init(&act_full[i], 256); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_fence_init();
     if (blockIdx.x == 0 && a.step_counter) *a.step_counter += 1;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ compute warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;       // column half (0: cols 0..127, 1: cols 128..255)
+    const int half = (warp - 4) >> 2;       // which 32-column half of every 64-column chunk this warp owns
     const int row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
     uint32_t inq = 0, acc_ph[2] = {0, 0};
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
         tc_fence_after();
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          const int col0 = half * 128 + g * 32;
+          const int col0 = (2 * g + half) * 32;   // chunk g completes after step g: the next layer's MMAs trail in order
           float v[32];
           tmem_ld32(tmem + t_lane + (l & 1) * kWidth + col0, v);
           tmem_ld_wait();
@@ -299,10 +299,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
               st_global_v4(d_img + (kg0 + j) * 2048 + row * 16, dv[j]);
             }
           }
-          if (!last_gemm && (g & 1)) {
+          if (!last_gemm) {
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(&act_full[half * 2 + (g >> 1)]);
+            mbar_arrive(&act_full[g]);
           }
         }
       }
@@ -386,16 +386,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
 cudaError_t launch_chain_fwd(const FwdArgs& a, int n_sm, cudaStream_t stream) {
   const int grid = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
   if (grid <= 0) return cudaSuccess;
-  cudaError_t e;
-  if (a.m.act == ACT_SIN) {
-    e = cudaFuncSetAttribute(chain_fwd_kernel<ACT_SIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+  static bool attr_done = false;     // once per process: keeps attribute calls out of graph capture
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(chain_fwd_kernel<ACT_SIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
     if (e != cudaSuccess) return e;
-    chain_fwd_kernel<ACT_SIN><<<grid, kFwdThreads, kFwdSmem, stream>>>(a);
-  } else {
     e = cudaFuncSetAttribute(chain_fwd_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
     if (e != cudaSuccess) return e;
-    chain_fwd_kernel<ACT_RELU><<<grid, kFwdThreads, kFwdSmem, stream>>>(a);
+    attr_done = true;
   }
+  if (a.m.act == ACT_SIN) chain_fwd_kernel<ACT_SIN><<<grid, kFwdThreads, kFwdSmem, stream>>>(a);
+  else chain_fwd_kernel<ACT_RELU><<<grid, kFwdThreads, kFwdSmem, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -163,8 +163,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   const int grid = a.n_units * a.n_split;
   if (grid <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
-  if (e != cudaSuccess) return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
   wgrad_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(a);
   return cudaGetLastError();
 }
