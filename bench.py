@@ -203,9 +203,6 @@ def main():
     n_rows = coords.shape[0]
     steps_per_pass = n_rows // bs
 
-    def reset_cursor():
-        eng.cursor.zero_()
-
     # eager warm-up (also sets kernel attributes outside capture), then capture one step in a CUDA graph
     for _ in range(3):
         eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
@@ -213,18 +210,22 @@ def main():
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
-    reset_cursor()
+
+    pos = [0]                                   # host mirror of the device-side batch cursor, in steps
+
+    def reset_cursor():
+        eng.cursor.zero_()
+        pos[0] = 0
 
     def run_steps(n):
-        done = 0
-        while done < n:
-            pos = int(done % steps_per_pass)
-            if pos == 0 and done > 0:
+        while n > 0:
+            if pos[0] >= steps_per_pass:
                 reset_cursor()
-            chunk = min(n - done, steps_per_pass - pos)
+            chunk = min(n, steps_per_pass - pos[0])
             for _ in range(chunk):
                 graph.replay()
-            done += chunk
+            pos[0] += chunk
+            n -= chunk
 
     # ---- device-resident throughput (`value`)
     # clocks ramp over tens of ms from idle: warm up for at least W steps AND ~1.5 s of continuous load
@@ -235,6 +236,7 @@ def main():
         torch.cuda.synchronize()
     reset_cursor()
     run_steps(args.warmup % steps_per_pass)      # leave the cursor where a W-step warm-up would
+    assert args.steps <= steps_per_pass - pos[0], "timed region must fit one pass over the resident rows"
     torch.cuda.synchronize()
     if dist:
         dist.barrier()

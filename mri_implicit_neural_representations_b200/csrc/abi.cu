@@ -51,6 +51,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   } else if (d->encoder != INR_ENC_NONE) {
     return fail(INR_EUNSUPPORTED, "encoder kind not built yet");
   }
+  if (d->encoder == INR_ENC_GAUSS && d->enc_size > 512) return fail(INR_EUNSUPPORTED, "embedding_size above 512 is not staged in shared memory");
   if (d->in_features % 64 != 0 || d->in_features > 2048) return fail(INR_EUNSUPPORTED, "network_input_size must be a multiple of 64");
   inr_plan* p = new (std::nothrow) inr_plan();
   if (!p) return fail(INR_EINVAL, "out of host memory");
@@ -74,6 +75,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
     p->tensors.push_back({off, rows, cols, l, 0});
     SegDesc sw{};
     sw.off = off; sw.rows = rows; sw.cols = cols; sw.layer = l;
+    sw.fwd_scale = sw.bwd_scale = (M.act == ACT_SIN) ? M.w0 : 1.f;
     if (l < M.n_gemm) {
       sw.pack_fwd = 1;
       sw.perm_e = (l == 0 && M.input_kind == INPUT_GAUSS) ? M.enc_size : 0;
@@ -251,8 +253,10 @@ extern "C" int inr_forward(const inr_plan* p, const float* params, const void* w
 }
 
 static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& loss, const float* params, const void* wpack,
-                        const float* dout, int64_t bs, void* ws, cudaStream_t st, cudaEvent_t mid = nullptr) {
+                        const float* dout, int64_t bs, void* ws, cudaStream_t st, cudaEvent_t mid = nullptr,
+                        const float* hyper = nullptr, const int* step = nullptr) {
   BwdArgs b{};
+  b.hyper = hyper; b.step = step;
   b.m = p->model; b.w = w; b.loss = loss;
   b.params = params; b.wpack = static_cast<const uint8_t*>(wpack); b.dout = dout;
   b.ws = static_cast<uint8_t*>(ws); b.bs = static_cast<int>(bs); b.bs_k = static_cast<int>(bs);
@@ -317,7 +321,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
                        step_dev, st);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[1], st);
-  rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st, ev ? ev[2] : nullptr);
+  rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st, ev ? ev[2] : nullptr, hyper_dev, step_dev);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[3], st);
   AdamArgs a; fill_adam(p, a);
@@ -327,7 +331,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   a.scal = reinterpret_cast<const float*>(ws + w.scal_off);
   a.hyper = hyper_dev; a.step = step_dev; a.loss_out = loss_out_dev;
   a.row_offset = row_cursor_dev; a.row_advance = static_cast<int>(bs);
-  a.do_adam = 1;
+  a.do_adam = 1; a.scal_has_bc = 1;
   cudaError_t e = launch_adam(a, st);
   if (ev) cudaEventRecord(ev[4], st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "adam_kernel");

@@ -10,7 +10,8 @@
 //                    dZ_{l-1} = (dZ_l W_l) * act'(z_{l-1})              (tcgen05, fp32 accumulate in TMEM)
 // Every dZ_l is written as an fp16 operand image for the split-K wgrad kernel; the image of the
 // current layer also stays in shared memory (in place) as the A operand of the next dgrad GEMM.
-// act'(z) images come from the forward kernel (w0*cos(w0 z) for SIREN, 1[z>0] for ReLU).
+// act'(z) images come from the forward kernel (cos(w0 z) for SIREN -- the w0 factor rides in the packed dgrad
+// weights and in the staged W_last --, 1[z>0] for ReLU).
 #include <cuda_runtime.h>
 #include <cmath>
 #include "inr_ptx.cuh"
@@ -18,9 +19,11 @@
 
 namespace inr {
 
-constexpr int kBwdStages = 6;
-constexpr int kBwdThreads = 384;
-constexpr int kBwdSmem = 2 * kActBytes + kBwdStages * kStageBytes + 1024;
+constexpr int kBwdStages = 5;
+constexpr int kBwdComputeThreads = 512;                   // warps 4..19
+constexpr int kBwdThreads = 128 + kBwdComputeThreads;
+constexpr int kBwdSmem = 2 * kActBytes + kBwdStages * kStageBytes + kMaxOut * kWidth * 4 + 1024;
+static_assert(kBwdSmem <= 227 * 1024, "backward kernel shared memory budget");
 
 // Fixed-order block reduction of the tile partials; result broadcast through shared memory.
 __device__ void reduce_step_scalars(const BwdArgs& a, float* sc /* smem[kScalars] */) {
@@ -75,8 +78,14 @@ __device__ void reduce_step_scalars(const BwdArgs& a, float* sc /* smem[kScalars
     sc[SC_INV_SCALE] = 1.f / S;
     if (a.loss.kind != LOSS_HDR) sc[SC_REG] = 0.f;
     if (blockIdx.x == 0) {
+      sc[SC_STEP_SIZE] = 0.f; sc[SC_BC2_SQRT] = 1.f;
+      if (a.hyper && a.step) {     // torch.optim.Adam: step_size = lr / (1 - b1^t), denom uses sqrt(1 - b2^t)
+        const double t = static_cast<double>(*a.step);
+        sc[SC_STEP_SIZE] = static_cast<float>(static_cast<double>(a.hyper[0]) / (1.0 - pow(static_cast<double>(a.hyper[1]), t)));
+        sc[SC_BC2_SQRT] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.hyper[2]), t)));
+      }
       float* g = reinterpret_cast<float*>(a.ws + a.w.scal_off);
-      for (int i = 0; i < 8; ++i) g[i] = sc[i];
+      for (int i = 0; i < 10; ++i) g[i] = sc[i];
     }
   }
   __syncthreads();
@@ -87,6 +96,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
   uint8_t* act = smem;                       // dZ_l image: A operand, rewritten in place per layer
   uint8_t* dimg = smem + kActBytes;          // act'(z) image of the layer being produced
   uint8_t* wring = smem + 2 * kActBytes;
+  float* c_wlast = reinterpret_cast<float*>(smem + 2 * kActBytes + kBwdStages * kStageBytes);   // [kMaxOut][256] * zscale
   __shared__ uint64_t w_full[kBwdStages], w_empty[kBwdStages], d_full[4], d_empty, act_full[4], acc_full[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sc[kScalars];
@@ -94,14 +104,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ChainModel& M = a.m;
   const int n_tiles = a.w.n_tiles;
+  const float zscale = (M.act == ACT_SIN) ? M.w0 : 1.f;   // act' images hold cos(w0 z); w0 rides in the weights
 
   if (tid == 0) {
     for (int i = 0; i < kBwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&act_full[i], 256); }
-    mbar_init(&d_empty, 256);
+    for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&act_full[i], kBwdComputeThreads); }
+    mbar_init(&d_empty, kBwdComputeThreads);
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_fence_init();
   }
+  for (int i = tid; i < M.out_f * kWidth; i += kBwdThreads) c_wlast[i] = zscale * a.params[M.w_off[M.n_gemm] + i];
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
@@ -169,11 +181,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ compute warps
-    const int q = warp & 3, half = (warp - 4) >> 2, row = q * 32 + lane;
+    // ------------------------------------------------------------------ compute warps (16)
+    const int q = warp & 3, sub = (warp - 4) >> 2, row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
     const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
-    const float* Wl = a.params + M.w_off[M.n_gemm];
     uint32_t dq = 0, acc_ph[2] = {0, 0};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int grow = tile * kTileM + row;
@@ -190,12 +201,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
           dz[1] = S * (cA * g.y + cB * g.w);
         }
       }
-      if (half == 0) {
+      if (sub == 0) {
         uint8_t* zl = a.ws + a.w.dzlast_off + static_cast<size_t>(tile) * kDzLastBytes;
         st_global_v4(zl + row * 16, make_uint4(pack_h2(dz[0], dz[1]), pack_h2(dz[2], dz[3]), 0u, 0u));
         st_global_v4(zl + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
       }
-      // ---- layers, top down.  step == n_gemm-1: CUDA-core product with W_last; below: TMEM accumulators
+      // ---- layers, top down.  l == n_gemm-1: CUDA-core product with W_last; below: TMEM accumulators
       for (int l = M.n_gemm - 1; l >= 0; --l) {
         const bool from_last = (l == M.n_gemm - 1);
         uint8_t* dz_img = a.ws + a.w.dz_off[l] + static_cast<size_t>(tile) * kActBytes;
@@ -206,27 +217,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
         }
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          const int col0 = (2 * g + half) * 32;   // both halves finish chunk g together -> in-order trailing MMAs
-          const int chunk = g;
-          mbar_wait(&d_full[chunk], dq & 1);
-          float v[32];
+          const int col0 = g * kChunkCols + sub * 16;
+          mbar_wait(&d_full[g], dq & 1);
+          float v[16];
           if (from_last) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float acc = 0.f;
+            for (int i4 = 0; i4 < 4; ++i4) {
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
               for (int o = 0; o < kMaxOut; ++o)
-                if (o < M.out_f) acc = fmaf(dz[o], __ldg(Wl + o * kWidth + col0 + i), acc);
-              v[i] = acc;
+                if (o < M.out_f) {
+                  const float4 w = *reinterpret_cast<const float4*>(c_wlast + o * kWidth + col0 + 4 * i4);
+                  acc.x = fmaf(dz[o], w.x, acc.x); acc.y = fmaf(dz[o], w.y, acc.y);
+                  acc.z = fmaf(dz[o], w.z, acc.z); acc.w = fmaf(dz[o], w.w, acc.w);
+                }
+              v[4 * i4] = acc.x; v[4 * i4 + 1] = acc.y; v[4 * i4 + 2] = acc.z; v[4 * i4 + 3] = acc.w;
             }
           } else {
-            tmem_ld32(tmem + t_lane + ((l + 1) & 1) * kWidth + col0, v);
+            tmem_ld16(tmem + t_lane + ((l + 1) & 1) * kWidth + col0, v);
             tmem_ld_wait();
           }
           const int kg0 = col0 >> 3;
-          uint4 zv[4];
+          uint4 zv[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             const uint4 dr = *reinterpret_cast<const uint4*>(dimg + (kg0 + j) * 2048 + row * 16);
             const __half2* dh = reinterpret_cast<const __half2*>(&dr);
             float z[8];
@@ -239,15 +253,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
             zv[j] = make_uint4(pack_h2(z[0], z[1]), pack_h2(z[2], z[3]), pack_h2(z[4], z[5]), pack_h2(z[6], z[7]));
           }
           if (l >= 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(act + (kg0 + j) * 2048 + row * 16) = zv[j];
+            *reinterpret_cast<uint4*>(act + kg0 * 2048 + row * 16) = zv[0];
+            *reinterpret_cast<uint4*>(act + (kg0 + 1) * 2048 + row * 16) = zv[1];
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) st_global_v4(dz_img + (kg0 + j) * 2048 + row * 16, zv[j]);
+          st_global_v4(dz_img + kg0 * 2048 + row * 16, zv[0]);
+          st_global_v4(dz_img + (kg0 + 1) * 2048 + row * 16, zv[1]);
           if (l >= 1) {
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(&act_full[chunk]);
+            mbar_arrive(&act_full[g]);
           }
         }
         ++dq;

@@ -2,10 +2,10 @@
 //   positional encoding -> [tcgen05 GEMM -> bias + activation epilogue] x n_gemm -> final small linear
 //   -> last activation -> loss pieces, one CTA per 128-coordinate tile, persistent over tiles.
 //
-// Warp roles (384 threads): warp 0 = weight-stage producer (1-D bulk TMA copies into a ring),
+// Warp roles (640 threads): warp 0 = weight-stage producer (1-D bulk TMA copies into a ring),
 // warp 1 = MMA issuer (one thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM, two
-// accumulators ping-ponged by layer), warp 2 = TMEM allocator, warps 4..11 = compute: they generate
-// the encoding chunks that feed layer 0 and run every epilogue.  Activations never leave the SM
+// accumulators ping-ponged by layer), warp 2 = TMEM allocator, warps 4..19 = compute (4 per TMEM lane
+// quarter): they generate the encoding chunks that feed layer 0 and run every epilogue.  Activations never leave the SM
 // between layers: the epilogue writes the fp16 A-operand image of the next layer in place, 64
 // columns at a time, and the next layer's MMAs trail it chunk by chunk.
 //
@@ -18,8 +18,12 @@
 namespace inr {
 
 constexpr int kFwdStages = 8;
-constexpr int kFwdThreads = 384;
-constexpr int kFwdSmem = kActBytes + kFwdStages * kStageBytes + 1024;
+constexpr int kFwdComputeThreads = 512;                   // warps 4..19
+constexpr int kFwdThreads = 128 + kFwdComputeThreads;
+constexpr int kFwdMaxEnc = 512;                           // encoder features staged in shared memory
+constexpr int kFwdConstBytes = ((kMaxLayers - 1) * kWidth + kMaxOut * kWidth + kFwdMaxEnc * 3) * 4;
+constexpr int kFwdSmem = kActBytes + kFwdStages * kStageBytes + kFwdConstBytes + 1024;
+static_assert(kFwdSmem <= 227 * 1024, "forward kernel shared memory budget");
 
 __device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
 
@@ -88,23 +92,35 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;
   uint8_t* wring = smem + kActBytes;
+  float* c_bias = reinterpret_cast<float*>(smem + kActBytes + kFwdStages * kStageBytes);   // [n_gemm][256], pre-scaled
+  float* c_wlast = c_bias + (kMaxLayers - 1) * kWidth;                                      // [kMaxOut][256]
+  float* c_encB = c_wlast + kMaxOut * kWidth;                                               // [E][3]
   __shared__ uint64_t w_full[kFwdStages], w_empty[kFwdStages], in_full[4], in_empty[4], act_full[4], acc_full[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float out_part[kTileM][kMaxOut];
+  __shared__ float out_part[3][kTileM][kMaxOut];
   __shared__ float red[4][8];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ChainModel& M = a.m;
   const int n_tiles = a.w.n_tiles;
   const int row_base = a.row_offset ? *a.row_offset : 0;
+  const float zscale = (ACT == ACT_SIN) ? M.w0 : 1.f;     // packed weights carry the same factor (optim.cu)
 
   if (tid == 0) {
     for (int i = 0; i < kFwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 256); mbar_init(&in_empty[i], 1); mbar_init(&act_full[i], 256); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&in_full[i], kFwdComputeThreads); mbar_init(&in_empty[i], 1); mbar_init(&act_full[i], kFwdComputeThreads);
+    }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_fence_init();
     if (blockIdx.x == 0 && a.step_counter) *a.step_counter += 1;
   }
+  // stage the small per-model constants once per CTA (broadcast LDS.128 in the epilogues instead of uniform LDGs)
+  for (int i = tid; i < M.n_gemm * kWidth; i += kFwdThreads)
+    c_bias[i] = zscale * a.params[M.b_off[i / kWidth] + (i % kWidth)];
+  for (int i = tid; i < M.out_f * kWidth; i += kFwdThreads) c_wlast[i] = a.params[M.w_off[M.n_gemm] + i];
+  if (M.input_kind == INPUT_GAUSS)
+    for (int i = tid; i < M.enc_size * 3; i += kFwdThreads) c_encB[i] = a.encB[i];
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
@@ -171,14 +187,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ compute warps
+    // ------------------------------------------------------------------ compute warps (16): 4 per TMEM lane quarter
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;       // which 32-column half of every 64-column chunk this warp owns
+    const int sub = (warp - 4) >> 2;        // which 16 columns of every 64-column chunk this warp owns
     const int row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
     uint32_t inq = 0, acc_ph[2] = {0, 0};
-    const float* Wl = a.params + M.w_off[M.n_gemm];
-    const float* bl = a.params + M.b_off[M.n_gemm];
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int grow = tile * kTileM + row;            // row inside the batch
       const bool valid = grow < a.bs;
@@ -194,51 +208,38 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
         const uint32_t slot = inq & 3;
         mbar_wait(&in_empty[slot], ((inq >> 2) & 1) ^ 1);
         uint8_t* dst = act + slot * kChunkBytes;
-        uint4 v[4];
-        int g0, g1;   // the two pairs of 16-byte k-groups (within the chunk) this thread fills
+        uint4 v0, v1;
+        int g0, g1;   // the two 16-byte k-groups (within the chunk) this thread fills
         if (M.input_kind == INPUT_GAUSS) {
-          // chunk c holds [sin f | cos f] for the 32 encoder features f = 32c .. 32c+31; this thread does 16 of them
-          const int f0 = c * 32 + half * 16;
-          float s[16], co[16];
+          // chunk c holds [sin f | cos f] for the 32 encoder features f = 32c .. 32c+31; this thread does 8 of them
+          const float* b = c_encB + (c * 32 + sub * 8) * 3;
+          float s[8], co[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float* b = a.encB + (f0 + i) * 3;
-            float t = fmaf(cx, __ldg(b), fmaf(cy, __ldg(b + 1), cz * __ldg(b + 2)));   // revolutions
-            t = t - rintf(t);                                                             // exact reduction
+          for (int i = 0; i < 8; ++i) {
+            float t = fmaf(cx, b[3 * i], fmaf(cy, b[3 * i + 1], cz * b[3 * i + 2]));   // revolutions
+            t = t - rintf(t);                                                            // exact reduction
             const float ang = t * 6.283185307179586f;
             s[i] = fast_sin(ang); co[i] = fast_cos(ang);
           }
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            v[j] = make_uint4(pack_h2(s[8 * j], s[8 * j + 1]), pack_h2(s[8 * j + 2], s[8 * j + 3]),
-                              pack_h2(s[8 * j + 4], s[8 * j + 5]), pack_h2(s[8 * j + 6], s[8 * j + 7]));
-            v[2 + j] = make_uint4(pack_h2(co[8 * j], co[8 * j + 1]), pack_h2(co[8 * j + 2], co[8 * j + 3]),
-                                  pack_h2(co[8 * j + 4], co[8 * j + 5]), pack_h2(co[8 * j + 6], co[8 * j + 7]));
-          }
-          g0 = half * 2; g1 = 4 + half * 2;
+          v0 = make_uint4(pack_h2(s[0], s[1]), pack_h2(s[2], s[3]), pack_h2(s[4], s[5]), pack_h2(s[6], s[7]));
+          v1 = make_uint4(pack_h2(co[0], co[1]), pack_h2(co[2], co[3]), pack_h2(co[4], co[5]), pack_h2(co[6], co[7]));
+          g0 = sub; g1 = 4 + sub;
         } else {
-          // dense fp32 input: natural column order, this thread converts 32 of the chunk's 64 columns
-          const float* xr = a.x + srow * M.k0 + c * kChunkCols + half * 32;
+          // dense fp32 input: natural column order, this thread converts 16 of the chunk's 64 columns
+          const float* xr = a.x + srow * M.k0 + c * kChunkCols + sub * 16;
+          float4 p[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 p0 = valid ? *reinterpret_cast<const float4*>(xr + 8 * j) : make_float4(0, 0, 0, 0);
-            float4 p1 = valid ? *reinterpret_cast<const float4*>(xr + 8 * j + 4) : make_float4(0, 0, 0, 0);
-            v[j] = make_uint4(pack_h2(p0.x, p0.y), pack_h2(p0.z, p0.w), pack_h2(p1.x, p1.y), pack_h2(p1.z, p1.w));
-          }
-          g0 = half * 4; g1 = half * 4 + 2;
+          for (int j = 0; j < 4; ++j) p[j] = valid ? *reinterpret_cast<const float4*>(xr + 4 * j) : make_float4(0, 0, 0, 0);
+          v0 = make_uint4(pack_h2(p[0].x, p[0].y), pack_h2(p[0].z, p[0].w), pack_h2(p[1].x, p[1].y), pack_h2(p[1].z, p[1].w));
+          v1 = make_uint4(pack_h2(p[2].x, p[2].y), pack_h2(p[2].z, p[2].w), pack_h2(p[3].x, p[3].y), pack_h2(p[3].z, p[3].w));
+          g0 = sub * 2; g1 = sub * 2 + 1;
         }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          *reinterpret_cast<uint4*>(dst + (g0 + j) * 2048 + row * 16) = v[j];
-          *reinterpret_cast<uint4*>(dst + (g1 + j) * 2048 + row * 16) = v[2 + j];
-        }
+        *reinterpret_cast<uint4*>(dst + g0 * 2048 + row * 16) = v0;
+        *reinterpret_cast<uint4*>(dst + g1 * 2048 + row * 16) = v1;
         if (a.train) {
           uint8_t* gdst = h0_img + static_cast<size_t>(c) * kChunkBytes;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            st_global_v4(gdst + (g0 + j) * 2048 + row * 16, v[j]);
-            st_global_v4(gdst + (g1 + j) * 2048 + row * 16, v[2 + j]);
-          }
+          st_global_v4(gdst + g0 * 2048 + row * 16, v0);
+          st_global_v4(gdst + g1 * 2048 + row * 16, v1);
         }
         fence_proxy_async_smem();
         mbar_arrive(&in_full[slot]);
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
       float po[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
       for (int l = 0; l < M.n_gemm; ++l) {
         const bool last_gemm = (l == M.n_gemm - 1);
-        const float* bias = a.params + M.b_off[l];
+        const float* bias = c_bias + l * kWidth;
         uint8_t* h_img = a.ws + a.w.h_off[l + 1] + static_cast<size_t>(tile) * kActBytes;
         uint8_t* d_img = a.ws + a.w.d_off[l] + static_cast<size_t>(tile) * kActBytes;
         mbar_wait(&acc_full[l & 1], acc_ph[l & 1]);
@@ -255,25 +256,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
         tc_fence_after();
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          const int col0 = (2 * g + half) * 32;   // chunk g completes after step g: the next layer's MMAs trail in order
-          float v[32];
-          tmem_ld32(tmem + t_lane + (l & 1) * kWidth + col0, v);
+          const int col0 = g * kChunkCols + sub * 16;   // chunk g completes after step g: the next layer's MMAs trail in order
+          float v[16];
+          tmem_ld16(tmem + t_lane + (l & 1) * kWidth + col0, v);
           tmem_ld_wait();
-          uint4 hv[4], dv[4];
+          uint4 hv[2], dv[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             float h[8], d[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + 8 * j + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float z = v[8 * j + i] + __ldg(bias + col0 + 8 * j + i);
-              if (ACT == ACT_SIN) {
-                const float arg = M.w0 * z;
-                h[i] = fast_sin(arg);
-                d[i] = M.w0 * fast_cos(arg);
-              } else {
-                h[i] = fmaxf(z, 0.f);
-                d[i] = z > 0.f ? 1.f : 0.f;
-              }
+              const float z = v[8 * j + i] + bb[i];          // SIREN: already w0 * (x W^T + b)
+              if (ACT == ACT_SIN) { h[i] = fast_sin(z); d[i] = fast_cos(z); }
+              else { h[i] = fmaxf(z, 0.f); d[i] = z > 0.f ? 1.f : 0.f; }
             }
             hv[j] = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
             dv[j] = make_uint4(pack_h2(d[0], d[1]), pack_h2(d[2], d[3]), pack_h2(d[4], d[5]), pack_h2(d[6], d[7]));
@@ -281,23 +279,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
 #pragma unroll
               for (int o = 0; o < kMaxOut; ++o)
                 if (o < M.out_f) {
-                  const float* w = Wl + o * kWidth + col0 + 8 * j;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) po[o] = fmaf(h[i], __ldg(w + i), po[o]);
+                  const float4 w0v = *reinterpret_cast<const float4*>(c_wlast + o * kWidth + col0 + 8 * j);
+                  const float4 w1v = *reinterpret_cast<const float4*>(c_wlast + o * kWidth + col0 + 8 * j + 4);
+                  po[o] = fmaf(h[0], w0v.x, fmaf(h[1], w0v.y, fmaf(h[2], w0v.z, fmaf(h[3], w0v.w, po[o]))));
+                  po[o] = fmaf(h[4], w1v.x, fmaf(h[5], w1v.y, fmaf(h[6], w1v.z, fmaf(h[7], w1v.w, po[o]))));
                 }
             }
           }
           const int kg0 = col0 >> 3;
           if (!last_gemm) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(act + (kg0 + j) * 2048 + row * 16) = hv[j];
+            *reinterpret_cast<uint4*>(act + kg0 * 2048 + row * 16) = hv[0];
+            *reinterpret_cast<uint4*>(act + (kg0 + 1) * 2048 + row * 16) = hv[1];
           }
           if (a.train) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              st_global_v4(h_img + (kg0 + j) * 2048 + row * 16, hv[j]);
-              st_global_v4(d_img + (kg0 + j) * 2048 + row * 16, dv[j]);
-            }
+            st_global_v4(h_img + kg0 * 2048 + row * 16, hv[0]);
+            st_global_v4(h_img + (kg0 + 1) * 2048 + row * 16, hv[1]);
+            st_global_v4(d_img + kg0 * 2048 + row * 16, dv[0]);
+            st_global_v4(d_img + (kg0 + 1) * 2048 + row * 16, dv[1]);
           }
           if (!last_gemm) {
             fence_proxy_async_smem();
@@ -307,18 +305,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
         }
       }
       // ---------------- final linear (CUDA cores) + last activation + loss pieces
-      if (half == 1) {
+      if (sub > 0) {
 #pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) out_part[row][o] = po[o];
+        for (int o = 0; o < kMaxOut; ++o) out_part[sub - 1][row][o] = po[o];
       }
-      named_bar_sync(1, 256);
-      if (half == 0) {
+      named_bar_sync(1, kFwdComputeThreads);
+      if (sub == 0) {
         float y[kMaxOut], t[kMaxOut], dact[kMaxOut];
+        const float* bl = a.params + M.b_off[M.n_gemm];
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) {
           y[o] = 0.f; t[o] = 0.f; dact[o] = 1.f;
           if (o < M.out_f) {
-            const float z = po[o] + out_part[row][o] + __ldg(bl + o);
+            const float z = ((po[o] + out_part[0][row][o]) + (out_part[1][row][o] + out_part[2][row][o])) + __ldg(bl + o);
             if (M.last_act == LAST_TANH) { y[o] = tanh_acc(z); dact[o] = 1.f - y[o] * y[o]; }
             else if (M.last_act == LAST_SIGMOID) { y[o] = 1.f / (1.f + expf(-z)); dact[o] = y[o] * (1.f - y[o]); }
             else y[o] = z;
@@ -350,7 +349,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
               gq = make_float4(ga[0], ga[1], gb[0], gb[1]);
             }
           }
-          // gradient pieces (out_f <= 2 packs A,B in one float4; wider outputs use A only, 4 floats)
           float* gdst = reinterpret_cast<float*>(a.ws + a.w.g_off) + (static_cast<size_t>(tile) * kTileM + row) * 4;
           *reinterpret_cast<float4*>(gdst) = gq;
           // deterministic tile partials: warp shuffle tree, then 4 warps in fixed order

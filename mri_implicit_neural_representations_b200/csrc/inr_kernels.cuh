@@ -30,7 +30,8 @@ enum LastAct { LAST_LINEAR = 0, LAST_TANH = 1, LAST_SIGMOID = 2 };
 enum InputKind { INPUT_GAUSS = 0, INPUT_DENSE = 1 };
 enum LossKind { LOSS_NONE = 0, LOSS_L2 = 1, LOSS_L1 = 2, LOSS_MSLE = 3, LOSS_TANH = 4, LOSS_LSL = 5, LOSS_HDR = 6 };
 // scalar slots written by the backward prologue (device memory, fp32)
-enum Scalar { SC_LOSS = 0, SC_SCALE = 1, SC_CA = 2, SC_CB = 3, SC_COUNT = 4, SC_FMEAN = 5, SC_REG = 6, SC_INV_SCALE = 7 };
+enum Scalar { SC_LOSS = 0, SC_SCALE = 1, SC_CA = 2, SC_CB = 3, SC_COUNT = 4, SC_FMEAN = 5, SC_REG = 6, SC_INV_SCALE = 7,
+              SC_STEP_SIZE = 8, SC_BC2_SQRT = 9 };   // Adam bias corrections, computed once per step (fp64) by the backward prologue
 
 struct ChainModel {
   int n_gemm;        // tensor-core layers (reference depth - 1)
@@ -97,6 +98,8 @@ struct BwdArgs {
   uint8_t* ws;
   int bs;
   int bs_k;              // rows of (unmasked) kcoords for HDR's filter mean
+  const float* hyper;    // optional (fused step): Adam hyper-parameters, to pre-compute the bias corrections
+  const int* step;       // optional: 1-based step count (already incremented by the forward kernel)
 };
 
 struct WgradUnit {
@@ -126,6 +129,7 @@ struct SegDesc {          // one parameter tensor for the optimiser / packer
   int pack_fwd, pack_bwd; // 1: write fp16 copies
   int perm_e;             // forward K permutation (gauss input layer)
   uint32_t wf_off, wd_off;
+  float fwd_scale, bwd_scale;   // factor folded into the fp16 copies (SIREN: w0, so the accumulators hold w0*z)
 };
 constexpr int kMaxSegs = 64;
 struct AdamArgs {
@@ -141,6 +145,7 @@ struct AdamArgs {
   float* loss_out;          // optional device scalar: loss of this step
   int* row_offset; int row_advance;   // optional: advance the device-side batch cursor
   int do_adam;              // 0: only reduce partials into grads
+  int scal_has_bc;          // 1: scal[SC_STEP_SIZE], scal[SC_BC2_SQRT] are valid for this step
 };
 
 }  // namespace inr

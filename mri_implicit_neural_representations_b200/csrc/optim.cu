@@ -20,8 +20,8 @@ __device__ __forceinline__ int find_seg(const SegDesc* seg, int n_seg, int p) {
 
 __device__ __forceinline__ void pack_store(const SegDesc& s, uint8_t* wpack, int local, float val) {
   const int o = local / s.cols, i = local - o * s.cols;
-  const __half h = __float2half_rn(val);
   if (s.pack_fwd) {
+    const __half h = __float2half_rn(val * s.fwd_scale);
     int kp = i;
     if (s.perm_e > 0) {
       if (i < s.perm_e) kp = 64 * (i >> 5) + (i & 31);
@@ -31,6 +31,7 @@ __device__ __forceinline__ void pack_store(const SegDesc& s, uint8_t* wpack, int
     *reinterpret_cast<__half*>(wpack + s.wf_off + static_cast<size_t>(st) * kStageBytes + (kk >> 3) * 4096 + o * 16 + (kk & 7) * 2) = h;
   }
   if (s.pack_bwd) {
+    const __half h = __float2half_rn(val * s.bwd_scale);
     const int st = o >> 5, kk = o & 31;
     *reinterpret_cast<__half*>(wpack + s.wd_off + static_cast<size_t>(st) * kStageBytes + (kk >> 3) * 4096 + i * 16 + (kk & 7) * 2) = h;
   }
@@ -41,7 +42,9 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
   if (threadIdx.x == 0) {
     const float* sc = a.scal;
     s_c[2] = sc ? sc[SC_INV_SCALE] : 1.f;
-    if (a.do_adam) {
+    if (a.do_adam && a.scal_has_bc && sc) {
+      s_c[0] = sc[SC_STEP_SIZE]; s_c[1] = sc[SC_BC2_SQRT];
+    } else if (a.do_adam) {
       const int t = *a.step;
       const double b1 = a.hyper[1], b2 = a.hyper[2];
       const double bc1 = 1.0 - pow(b1, static_cast<double>(t));

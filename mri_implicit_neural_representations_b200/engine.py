@@ -84,7 +84,7 @@ class Plan:
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h:
+        if h and getattr(L, "lib", None) is not None:
             L.lib.inr_plan_destroy(h)
             self.handle = None
 
@@ -93,20 +93,24 @@ class ChainEngine:
     """Owns the device state of one fit: parameters, Adam moments, fp16 operand copies, workspace."""
 
     def __init__(self, plan: Plan, max_batch: int, device="cuda", lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
-                 weight_decay=0.0, reg_l1=0.0, reg_l2=0.0):
+                 weight_decay=0.0, reg_l1=0.0, reg_l2=0.0, shared: Optional[dict] = None):
         if not torch.cuda.is_available():
             raise L.InrError("ChainEngine needs a CUDA device (no CPU fallback)")
         self.plan, self.device, self.max_batch = plan, torch.device(device), int(max_batch)
         P = plan.n_params
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.params = torch.zeros(P, **f32)
-        self.grads = torch.zeros(P, **f32)
-        self.exp_avg = torch.zeros(P, **f32)
-        self.exp_avg_sq = torch.zeros(P, **f32)
+        sh = shared or {}                         # engines of one module share parameters / Adam state
+        self.params = sh.get("params", None) if sh else None
+        if self.params is None:
+            self.params = torch.zeros(P, **f32)
+        assert self.params.numel() == P and self.params.is_cuda and self.params.dtype == torch.float32
+        self.grads = sh["grads"] if "grads" in sh else torch.zeros(P, **f32)
+        self.exp_avg = sh["exp_avg"] if "exp_avg" in sh else torch.zeros(P, **f32)
+        self.exp_avg_sq = sh["exp_avg_sq"] if "exp_avg_sq" in sh else torch.zeros(P, **f32)
         self.wpack = torch.zeros(plan.wpack_bytes + 1024, dtype=torch.uint8, device=self.device)
         self.workspace = torch.zeros(plan.workspace_bytes(self.max_batch), dtype=torch.uint8, device=self.device)
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, reg_l1, reg_l2, 0.0], **f32)
-        self.step = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.step = sh["step"] if "step" in sh else torch.zeros(1, dtype=torch.int32, device=self.device)
         self.cursor = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.loss_out = torch.zeros(1, **f32)
         self.encB = None
