@@ -142,6 +142,10 @@ int inr_profile_step(const inr_plan* plan, const inr_loss_desc* loss, float* par
                      const float* coords, const float* input_x, const float* encB, const float* gt,
                      const uint8_t* mask, int64_t bs, void* workspace, int32_t reps, float* ms_out4, void* stream);
 
+/* debugging: CTA 0 of the forward kernel writes %globaltimer stamps of its phases into this device buffer of
+ * 64 uint64 (NULL switches tracing off; off by default).  Process-global, not thread-safe. */
+int inr_debug_set_trace(void* dev_u64_buffer_64);
+
 /* one tcgen05 GEMM per operand-layout family against a host loop (allocates + synchronises; test only) */
 int inr_selftest_umma(int mode, int variant, float* max_abs_err, float* ref_absmax);
 

@@ -31,6 +31,7 @@ struct inr_plan {
 };
 
 static thread_local std::string g_err;
+static unsigned long long* g_trace = nullptr;   // debug: device buffer for in-kernel phase stamps (inr_debug_set_trace)
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static int cuda_fail(cudaError_t e, const char* where) {
   return fail(INR_ECUDA, std::string(where) + ": " + cudaGetErrorString(e));
@@ -38,6 +39,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 extern "C" const char* inr_last_error(void) { return g_err.c_str(); }
+extern "C" int inr_debug_set_trace(void* dev_u64_buffer_64) { g_trace = static_cast<unsigned long long*>(dev_u64_buffer_64); return INR_OK; }
 
 extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (!d || !out) return fail(INR_EINVAL, "null argument");
@@ -235,7 +237,7 @@ static int run_forward(const inr_plan* p, const Workspace& w, const LossDesc& lo
   f.params = params; f.wpack = static_cast<const uint8_t*>(wpack);
   f.coords = coords; f.x = x; f.encB = encB; f.gt = gt; f.mask = mask; f.out = out;
   f.ws = static_cast<uint8_t*>(ws); f.row_offset = row_off; f.step_counter = step;
-  f.bs = static_cast<int>(bs); f.train = train;
+  f.bs = static_cast<int>(bs); f.train = train; f.trace = g_trace;
   cudaError_t e = launch_chain_fwd(f, p->n_sm, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "chain_fwd_kernel");
 }

@@ -17,6 +17,9 @@
 
 namespace inr {
 
+// debug trace: slot i of the buffer <- %globaltimer (ns); only CTA 0, only when a buffer is supplied
+#define INR_TRACE(args, slot) do { if ((args).trace && blockIdx.x == 0) (args).trace[(slot)] = global_ns(); } while (0)
+
 constexpr int kFwdStages = 8;
 constexpr int kFwdComputeThreads = 512;                   // warps 4..19
 constexpr int kFwdThreads = 128 + kFwdComputeThreads;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
   const int n_tiles = a.w.n_tiles;
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const float zscale = (ACT == ACT_SIN) ? M.w0 : 1.f;     // packed weights carry the same factor (optim.cu)
+  if (tid == 0) INR_TRACE(a, 0);
 
   if (tid == 0) {
     for (int i = 0; i < kFwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -120,12 +124,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
     c_bias[i] = zscale * a.params[M.b_off[i / kWidth] + (i % kWidth)];
   for (int i = tid; i < M.out_f * kWidth; i += kFwdThreads) c_wlast[i] = a.params[M.w_off[M.n_gemm] + i];
   if (M.input_kind == INPUT_GAUSS)
-    for (int i = tid; i < M.enc_size * 3; i += kFwdThreads) c_encB[i] = a.encB[i];
+    for (int i = tid; i < M.enc_size * 3; i += kFwdThreads) c_encB[i] = 6.283185307179586f * a.encB[i];   // radians per unit coordinate
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (tid == 0) INR_TRACE(a, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight-stage producer
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
             for (int s2 = 0; s2 < 2; ++s2, ++it) {
               const uint32_t slot = it % kFwdStages;
               mbar_wait(&w_full[slot], (it / kFwdStages) & 1);
+              if (it < 8) INR_TRACE(a, 48 + it);         // MMA thread: first eight weight stages landed
               tc_fence_after();
               const uint32_t b_base = wring_s + slot * kStageBytes;
 #pragma unroll
@@ -182,6 +188,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
             if (l == 0) { umma_commit(&in_empty[in_slot]); ++inq; }
           }
           umma_commit(&acc_full[l & 1]);
+          if (tile == 0) INR_TRACE(a, 40 + l);          // MMA thread: layer l fully issued
           if (l > 0) ++act_use;
         }
       }
@@ -202,6 +209,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
       if (M.input_kind == INPUT_GAUSS && valid) {
         cx = a.coords[srow * 3 + 0]; cy = a.coords[srow * 3 + 1]; cz = a.coords[srow * 3 + 2];
       }
+      float t_pref[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+      bool in_loss_pref = false;
+      if (sub == 0 && a.train && valid && a.gt && a.loss.kind != LOSS_NONE) {   // loss inputs: fetched now, used at the tile's end
+        in_loss_pref = a.mask ? (a.mask[srow] != 0) : true;
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) if (o < M.out_f) t_pref[o] = a.gt[srow * M.out_f + o];
+      }
       uint8_t* h0_img = a.ws + a.w.h_off[0] + static_cast<size_t>(tile) * (kTileM * M.k0 * 2);
       const int n_in_chunks = M.k0 / kChunkCols;
       for (int c = 0; c < n_in_chunks; ++c, ++inq) {
@@ -216,9 +230,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
           float s[8], co[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float t = fmaf(cx, b[3 * i], fmaf(cy, b[3 * i + 1], cz * b[3 * i + 2]));   // revolutions
-            t = t - rintf(t);                                                            // exact reduction
-            const float ang = t * 6.283185307179586f;
+            // 2*pi*(x . B_f); sin.approx's own range reduction (x * 1/2pi -> MUFU) is accurate to ~1e-5 rad
+            // at |arg| ~ 100, far below the fp16 rounding of the stored feature
+            const float ang = fmaf(cx, b[3 * i], fmaf(cy, b[3 * i + 1], cz * b[3 * i + 2]));
             s[i] = fast_sin(ang); co[i] = fast_cos(ang);
           }
           v0 = make_uint4(pack_h2(s[0], s[1]), pack_h2(s[2], s[3]), pack_h2(s[4], s[5]), pack_h2(s[6], s[7]));
@@ -243,6 +257,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
         }
         fence_proxy_async_smem();
         mbar_arrive(&in_full[slot]);
+        if (tid == 128 && tile == 0) INR_TRACE(a, 2 + c);      // compute: encoding chunk c written
       }
       // ---------------- epilogues
       float po[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
@@ -254,6 +269,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
         mbar_wait(&acc_full[l & 1], acc_ph[l & 1]);
         acc_ph[l & 1] ^= 1;
         tc_fence_after();
+        if (tid == 128 && tile == 0) INR_TRACE(a, 12 + 5 * l);  // compute: accumulator of layer l ready
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           const int col0 = g * kChunkCols + sub * 16;   // chunk g completes after step g: the next layer's MMAs trail in order
@@ -302,6 +318,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
             tc_fence_before();
             mbar_arrive(&act_full[g]);
           }
+          if (tid == 128 && tile == 0) INR_TRACE(a, 13 + 5 * l + g);   // compute: epilogue step g of layer l done
         }
       }
       // ---------------- final linear (CUDA cores) + last activation + loss pieces
@@ -330,14 +347,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
           float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
           float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid && a.gt && a.loss.kind != LOSS_NONE) {
-            const bool in_loss = a.mask ? (a.mask[srow] != 0) : true;
+            const bool in_loss = in_loss_pref;
             if (a.loss.kind == LOSS_HDR) {   // filter term runs over ALL batch rows (unmasked kcoords)
               const float kx = a.coords[srow * 3 + 1], ky = a.coords[srow * 3 + 2];
               const float f = expf(-(kx * kx + ky * ky) / (2.f * a.loss.sigma * a.loss.sigma));
               fs = (1.f - f) * (1.f - f);
             }
             if (in_loss) {
-              for (int o = 0; o < M.out_f; ++o) t[o] = a.gt[srow * M.out_f + o];
+#pragma unroll
+              for (int o = 0; o < kMaxOut; ++o) t[o] = t_pref[o];
               RowLoss r = loss_row(a.loss, M.out_f, y, t);
               lA = r.lossA; lB = r.lossB; cnt = 1.f;
               float ga[kMaxOut], gb[kMaxOut];
@@ -376,8 +394,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
       }
     }
   }
+  if (tid == 128) INR_TRACE(a, 38);                      // compute thread: all tiles done
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) INR_TRACE(a, 39);
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 

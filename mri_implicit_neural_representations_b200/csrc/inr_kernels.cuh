@@ -86,6 +86,7 @@ struct FwdArgs {
   int* step_counter;     // optional: incremented once per launch by block 0 (Adam bias correction)
   int bs;
   int train;             // 1: store images + loss pieces
+  unsigned long long* trace;   // debug: per-phase %globaltimer stamps of CTA 0 (null in production)
 };
 
 struct BwdArgs {
@@ -100,6 +101,7 @@ struct BwdArgs {
   int bs_k;              // rows of (unmasked) kcoords for HDR's filter mean
   const float* hyper;    // optional (fused step): Adam hyper-parameters, to pre-compute the bias corrections
   const int* step;       // optional: 1-based step count (already incremented by the forward kernel)
+  unsigned long long* trace;
 };
 
 struct WgradUnit {

@@ -1,0 +1,212 @@
+"""Training script -- drop-in for the reference's src/train.py (same CLI, config keys, checkpoint layout).
+
+The inner batch loop (reference :158-192) is replaced by the B200 engine:
+  * fusable model + loss (+ regulariser): FusedTrainer -- encoder, model, loss, backward and Adam in one CUDA
+    graph per batch, inputs resident on the device, loss read back only every log_iter steps;
+  * anything else: the reference's own loop shape (model(x) -> loss -> backward -> optim.step) on the fused
+    model's autograd face.
+"""
+import argparse
+import os
+import shutil
+import sys
+from datetime import datetime
+
+import torch
+from torch.optim.lr_scheduler import LambdaLR
+
+_SRC = os.path.dirname(os.path.abspath(__file__))
+if _SRC not in sys.path:
+    sys.path.insert(0, _SRC)
+
+from models.networks import FFN, SIREN, WIRE, Positional_Encoder            # noqa: E402
+from models.regularization import Regularization_L1, Regularization_L2       # noqa: E402
+from metrics.losses import HDRLoss_FF, MSLELoss, TanhL2Loss, tv_loss          # noqa: E402
+from data.slices import get_data_loader                                      # noqa: E402
+from log_handler.logger import INRLogger                                     # noqa: E402
+from utils import get_config, set_default_configs                            # noqa: E402
+from mri_implicit_neural_representations_b200 import metrics as M            # noqa: E402
+from mri_implicit_neural_representations_b200.trainer import FUSABLE_LOSSES, FusedAdam, FusedTrainer  # noqa: E402
+
+opts = None      # the reference reads a module-global `opts` (src/train.py:35,45-48); kept for callers that set it
+
+
+def get_device(net_name=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("this engine has no CPU fallback: a CUDA device (B200) is required")
+    return torch.device("cuda")
+
+
+def build_model(config):
+    name = config["model"]
+    if name == "SIREN":
+        return SIREN(config["net"])
+    if name == "FFN":
+        return FFN(config["net"])
+    if name == "WIRE":
+        return WIRE(config["net"])
+    raise NotImplementedError(name)            # reference :69-70
+
+
+def build_loss(config):
+    loss = config["loss"]
+    if loss == "L2":
+        return torch.nn.MSELoss()
+    if loss == "MSLE":
+        return MSLELoss()
+    if loss == "L1":
+        return torch.nn.L1Loss()
+    if loss == "HDR":
+        return HDRLoss_FF(config["loss_opts"])
+    if loss == "tanh":
+        return TanhL2Loss()
+    return None                                # reference falls through silently (:97-98)
+
+
+def training_script(config, dataset, data_loader, val_loader, sample, slice_no, output_path=None, config_path=None,
+                    verbose=True):
+    """Same positional signature as the reference.  Returns the list of (epoch, psnr, ssim) validations."""
+    max_epoch = config["max_epoch"]
+    in_image_space = config["transform"]
+    device = get_device(config["model"])
+    out_root = output_path or (opts.output_path if opts else ".")
+    cfg_path = config_path or (opts.config if opts else None)
+    tag = os.path.splitext(os.path.basename(cfg_path))[0] if cfg_path else "config"
+    model_name = os.path.join(tag, "{}/img_sample{}_slice{}_{}_{}_{}_{}_{}_lr{:.2g}_encoder_{}".format(
+        config["data"], sample, slice_no, config["model"], config["net"]["network_input_size"],
+        config["net"]["network_width"], config["net"]["network_depth"], config["loss"], config["lr"],
+        config["encoder"]["embedding"]))
+    model_name += datetime.now().strftime("%Y-%m-%d_%H-%M-%S")
+    train_writer = INRLogger(os.path.join(out_root, "logs", model_name))
+    checkpoint_directory = os.path.join(out_root, "outputs", model_name, "checkpoints")
+    os.makedirs(checkpoint_directory, exist_ok=True)
+    if cfg_path and os.path.exists(cfg_path):
+        shutil.copy(cfg_path, os.path.join(out_root, "outputs", model_name, "config.yaml"))
+
+    encoder = Positional_Encoder(config["encoder"], device=device)
+    model = build_model(config)
+    model.to(device=device)
+    model.train()
+    if config["optimizer"] == "Adam":
+        optim = FusedAdam(model, lr=config["lr"], betas=(config["beta1"], config["beta2"]), weight_decay=config["weight_decay"])
+    else:
+        raise NotImplementedError(config["optimizer"])
+    loss_fn = build_loss(config)
+
+    reg_type = config["regularization"]["type"]
+    regularization = None
+    if reg_type not in ("none", "None", None):
+        lam = config["regularization"]["strenght"]
+        regularization = {"L1": Regularization_L1(lam), "L2": Regularization_L2(lam)}.get(reg_type)
+        if regularization is not None:
+            optim.reg_l1 = lam if reg_type == "L1" else 0.0
+            optim.reg_l2 = lam if reg_type == "L2" else 0.0
+
+    if "pretrain" in config:                    # reference :117-121
+        ckpt = torch.load(config["pretrain"], map_location=device)
+        model.load_state_dict(ckpt["net"])
+        optim.load_state_dict(ckpt["opt"])
+        encoder.B = ckpt["enc"]
+
+    bs = config["batch_size"]
+    C, H, W, S = dataset.img_shape
+    train_ds = data_loader.ds
+    gt_image = M.reconstruct(dataset.image.to(device), (C, H, W), in_image_space)
+
+    fused = (config["loss"] in FUSABLE_LOSSES and config["encoder"]["embedding"] == "gauss"
+             and not config.get("use_tv", False) and not config.get("per_coil", False))
+    trainer = None
+    if fused:
+        mask = train_ds.coords_mask[:, 0] if train_ds.coords_mask is not None else None
+        trainer = FusedTrainer(model, encoder, optim, config["loss"], bs, train_ds.coords, train_ds.image, mask,
+                               config.get("loss_opts"))
+    elif verbose:
+        print("unfused path: model(x) -> loss -> backward -> optim.step through the engine's autograd face")
+
+    scheduler = LambdaLR(optim, lambda x: 0.2 ** min(x / max_epoch, 1))
+    history = []
+    log_iter = config["log_iter"]
+    for epoch in range(max_epoch):
+        model.train()
+        if trainer is not None:
+            for it in range(trainer.steps_per_epoch):
+                loss_dev = trainer.step()
+                if it % log_iter == log_iter - 1:              # the only host sync of the training loop
+                    train_loss = float(loss_dev)
+                    train_writer.log_train(train_loss, epoch * trainer.steps_per_epoch + it + 1)
+                    if verbose:
+                        print("[Epoch: {}/{}, Iteration: {}] Train loss: {:.4g}".format(epoch + 1, max_epoch, it, train_loss))
+        else:
+            for it, (coords, gt, dist_to_center, mask_coords) in enumerate(data_loader):
+                kcoords = coords.to(device)
+                gt = gt.to(device)
+                x = encoder.embedding(kcoords)
+                out = model(x)
+                optim.zero_grad()
+                train_loss = 0
+                if len(mask_coords) != 0:
+                    if config["use_tv"]:
+                        train_loss = train_loss + tv_loss(out.view((H, W, 2)))
+                    sel = mask_coords.to(device)[:, 0]
+                    out, gt = out[sel], gt[sel]
+                if config["loss"] in ["HDR", "tanh"]:
+                    loss, _ = loss_fn(out, gt, kcoords)
+                    train_loss = train_loss + loss
+                else:
+                    train_loss = train_loss + 0.5 * loss_fn(out, gt)
+                if regularization is not None:
+                    train_loss = train_loss + regularization(model.parameters())
+                    l1, l2 = optim.reg_l1, optim.reg_l2        # autograd already carries the penalty here
+                    optim.reg_l1 = optim.reg_l2 = 0.0
+                train_loss.backward()
+                optim.step()
+                if regularization is not None:
+                    optim.reg_l1, optim.reg_l2 = l1, l2
+                if it % log_iter == log_iter - 1:
+                    train_writer.log_train(float(train_loss), epoch * len(data_loader) + it + 1)
+        if (epoch + 1) % config["val_epoch"] == 0:
+            model.eval()
+            with torch.no_grad():
+                if trainer is not None:
+                    flat = trainer.predict(dataset.coords, chunk=bs)
+                else:
+                    flat = torch.cat([model(encoder.embedding(c.to(device))) for c, _, _, _ in val_loader])
+                recon = M.reconstruct(flat, (C, H, W), in_image_space)
+                test_psnr = float(M.psnr(gt_image, recon))
+                test_ssim = float(M.ssim(gt_image, recon))
+            history.append((epoch + 1, test_psnr, test_ssim))
+            train_writer.log_test(0.0, test_psnr, test_ssim, epoch + 1)
+            if verbose:
+                print("[Validation Epoch: {}/{}] Test psnr: {:.4g} | Test ssim: {:.4g}".format(epoch + 1, max_epoch, test_psnr, test_ssim))
+        if (epoch + 1) % config["image_save_epoch"] == 0:
+            torch.save({"net": model.state_dict(), "enc": encoder.B, "opt": optim.state_dict()},
+                       os.path.join(checkpoint_directory, "model_%06d.pt" % (epoch + 1)))
+        scheduler.step()
+    return history
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--config", type=str, default="src/config/config_image.yaml", help="Path to the config file.")
+    parser.add_argument("--data_samples", type=str, default="", help="Path to the config file.")
+    parser.add_argument("--output_path", type=str, default=".", help="outputs path")
+    opts = parser.parse_args()
+    config = set_default_configs(get_config(opts.config))
+    data_samples = get_config(opts.data_samples)
+
+    def loaders(sample, slice_no):
+        return get_data_loader(data=config["data"], data_root=config["data_root"], set=config["set"],
+                               batch_size=config["batch_size"], transform=config["transform"], num_workers=0,
+                               sample=sample, slice=slice_no, shuffle=True, full_norm=config["full_norm"],
+                               normalization=config["normalization"], undersampling=config["undersampling"],
+                               use_dists="no", per_coil=config["per_coil"])
+
+    if not data_samples:
+        dataset, data_loader, val_loader = loaders(config["sample"], config["slice"])
+        training_script(config, dataset, data_loader, val_loader, config["sample"], config["slice"])
+    else:
+        for sample, slices in data_samples["samples"].items():
+            for _slice in slices:
+                # the reference always loads config["sample"] here (src/train.py:304); kept
+                dataset, data_loader, val_loader = loaders(config["sample"], _slice)
+                training_script(config, dataset, data_loader, val_loader, sample, _slice)

@@ -1,0 +1,99 @@
+"""CPU-side checks of the drop-in layer: module trees / state_dict keys, init parity, metrics, data conventions."""
+import os
+import sys
+import warnings
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "src")
+
+from oracle import inr_oracle as O
+
+NET = {"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256}
+
+
+@pytest.fixture(scope="module")
+def src_path():
+    sys.path.insert(0, SRC)
+    yield
+    sys.path.remove(SRC)
+
+
+def test_module_keys_and_init_match_oracle(src_path):
+    from models.networks import FFN, SIREN
+    for cls, init in [(SIREN, O.siren_init), (FFN, O.ffn_init)]:
+        torch.manual_seed(9)
+        m = cls(dict(NET))
+        torch.manual_seed(9)
+        sd = init(dict(NET))
+        msd = m.state_dict()
+        assert list(msd.keys()) == list(sd.keys())
+        for k in sd:
+            assert torch.equal(msd[k], sd[k]), k
+        # parameters are views of one flat buffer, in state_dict order
+        flat = m._flat
+        off = 0
+        for p in m.parameters():
+            assert p.data_ptr() == flat.data_ptr() + 4 * off
+            off += p.numel()
+        assert off == flat.numel() == 263426
+
+
+def test_load_state_dict_writes_through_to_flat_buffer(src_path):
+    from models.networks import SIREN
+    torch.manual_seed(1)
+    a, b = SIREN(dict(NET)), SIREN(dict(NET))
+    b.load_state_dict(a.state_dict())
+    assert torch.equal(a._flat, b._flat)
+
+
+def test_cpu_forward_fails_loudly(src_path):
+    from models.networks import SIREN
+    from mri_implicit_neural_representations_b200 import InrError
+    m = SIREN(dict(NET))
+    with pytest.raises(InrError):
+        m(torch.zeros(4, 512))
+
+
+def test_metrics_match_oracle():
+    from mri_implicit_neural_representations_b200 import metrics as M
+    torch.manual_seed(0)
+    a = torch.rand(40, 36)
+    b = a + 0.05 * torch.randn(40, 36)
+    assert abs(float(M.psnr(a, b)) - float(O.psnr(a, b))) < 1e-5
+    assert abs(float(M.ssim(a, b)) - O.ssim(a.numpy(), b.numpy())) < 1e-9
+    k = torch.randn(3, 16, 12, 2)
+    assert torch.allclose(M.ifft2c(k), O.ifft2c(k), atol=1e-6)
+    # Parseval for the orthonormal centred transform
+    assert abs(float((M.ifft2c(k) ** 2).sum()) - float((k ** 2).sum())) < 1e-3
+
+
+def test_slice_data_conventions(src_path):
+    from data.slices import get_data_loader
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ds, tl, vl = get_data_loader("knee", "data", "train", 1000, transform=False, normalization="coil",
+                                     undersampling="grid-2*1", shape=(3, 32, 24))
+    C, H, W, S = ds.img_shape
+    assert (C, H, W, S) == (3, 32, 24, 2) and len(ds) == C * H * W
+    # coordinates: coil-major flattening of linspace(-1,1) grids (reference create_coords)
+    assert torch.equal(ds.coords[0], torch.tensor([-1.0, -1.0, -1.0]))
+    assert torch.allclose(ds.coords[W], torch.tensor([-1.0, -1.0 + 2 / (H - 1), -1.0]))
+    # coil normalisation: every coil's complex magnitude peaks at 1
+    mag = ds.image.reshape(C, -1, 2).pow(2).sum(-1).sqrt().max(dim=1)[0]
+    assert torch.allclose(mag, torch.ones(C), atol=1e-5)
+    # grid-2*1 keeps every other row; last batch is short; masks are [bs,3] bool
+    batches = list(tl)
+    assert sum(b[0].shape[0] for b in batches) == len(ds) and batches[-1][0].shape[0] == len(ds) % 1000
+    m = tl.ds.coords_mask[:, 0].reshape(C, H, W)
+    assert bool(m[:, ::2].all()) and not bool(m[:, 1::2].any())
+
+
+def test_train_script_has_reference_cli(src_path):
+    import train
+    assert callable(train.training_script)
+    import inspect
+    params = list(inspect.signature(train.training_script).parameters)
+    assert params[:6] == ["config", "dataset", "data_loader", "val_loader", "sample", "slice_no"]
