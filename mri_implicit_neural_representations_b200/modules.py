@@ -37,7 +37,7 @@ class _Wrap(nn.Module):
 class _ChainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, module, *params):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = any(ctx.needs_input_grad[2:])      # grad mode is off inside Function.forward; ask autograd instead
         out = module._engine_forward(x, train=need_grad)
         ctx.module = module
         ctx.bs = x.shape[0]
