@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "independent"],
+                    help="N>1: dp = one fit, per-GPU batch shard + NCCL gradient all-reduce; independent = one fit per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -197,19 +199,39 @@ def main():
     bs = wl["batch"]
     peaks = load_peaks()
 
-    # ---- state: one independent fit per rank (one slice set per GPU, no data-path collective)
-    eng, tensors, encB = build_engine(wl, device, seed=1234 + rank)
+    # ---- state.  dp: identical replicas (same seed), every rank walks its own slice set, gradients all-reduced
+    # (SURVEY 8e-2).  independent: one fit per rank, no data-path collective.
+    dp = world > 1 and args.parallel == "dp"
+    eng, tensors, encB = build_engine(wl, device, seed=1234 if dp else 1234 + rank)
     coords, gt = resident_arrays(wl, device, 1234 + 100 * rank, min_bytes=200 << 20)
     n_rows = coords.shape[0]
     steps_per_pass = n_rows // bs
 
+    def one_step():
+        if dp:      # forward+loss+backward -> all-reduce(mean) of the flat fp32 gradients -> Adam (+ fp16 re-pack)
+            eng.grad_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)
+            eng.adam_step()
+        else:
+            eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+
     # eager warm-up (also sets kernel attributes outside capture), then capture one step in a CUDA graph
     for _ in range(3):
-        eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+        one_step()
     torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+    graph_mode = "cuda graph"
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_step()
+    except Exception as e:          # e.g. a collective that refuses capture: fall back to eager launches
+        graph_mode = f"eager ({type(e).__name__})"
+        torch.cuda.synchronize()
+
+        class _Eager:
+            def replay(self):
+                one_step()
+        graph = _Eager()
 
     pos = [0]                                   # host mirror of the device-side batch cursor, in steps
 
@@ -272,7 +294,12 @@ def main():
         j = (i % 64) * bs
         d_c.copy_(h_coords[j:j + bs], non_blocking=True)
         d_g.copy_(h_gt[j:j + bs], non_blocking=True)
-        eng.train_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
+        if dp:
+            eng.grad_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)
+            eng.adam_step()
+        else:
+            eng.train_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
         h_loss.copy_(eng.loss_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(h_loss)
@@ -317,14 +344,17 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
         "config": {"workload": args.workload, "model": wl["model"], "batch_per_gpu": bs, "slice": list(SLICE),
-                   "parallelism": f"independent fit per GPU x{world}" if world > 1 else "single GPU",
+                   "parallelism": ("single GPU" if world == 1 else
+                                   (f"dp{world}: replicated weights, per-GPU batch {bs}, NCCL all-reduce(avg) of {eng.plan.n_params * 4} B fp32 gradients per step"
+                                    if dp else f"independent fit per GPU x{world}, no collective")),
+                   "launch": graph_mode,
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
                    "step": "CUDA graph of 4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",
                    "loss_last_step": loss_dev},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": bs * 20, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / n_e2e, "api": "ChainEngine.train_step (C ABI inr_train_step), pinned host batches"},
-        "gpu_launches": 4 * args.steps,
+        "gpu_launches": (5 if dp else 4) * args.steps,
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"], "traffic": None,
                      "kernel": "chain_fwd_kernel<SIN>", "kernel_ms": kern_ms,

@@ -135,6 +135,14 @@ int inr_train_step(const inr_plan* plan, const inr_loss_desc* loss, float* param
                    const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev, void* workspace,
                    float* out, float* loss_out_dev, void* stream);
 
+/* inr_train_step without the optimiser: forward + loss + backward, gradients (unscaled fp32, flat, reference
+ * parameter order) into `grads`.  For data-parallel training: all-reduce `grads` across ranks, then
+ * inr_adam_step.  Replaces src/train.py:160-189 (everything up to optim.step()). */
+int inr_grad_step(const inr_plan* plan, const inr_loss_desc* loss, const float* params, const void* wpack,
+                  const float* coords, const float* input_x, const float* encB, const float* gt,
+                  const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev, void* workspace, float* out,
+                  float* grads, float* loss_out_dev, void* stream);
+
 /* measurement only: runs inr_train_step `reps` times with CUDA events between its four kernels and returns the
  * average duration in ms of {forward, dgrad, wgrad, optimiser} in ms_out4 (host).  Synchronises. */
 int inr_profile_step(const inr_plan* plan, const inr_loss_desc* loss, float* params, float* exp_avg,

@@ -304,9 +304,11 @@ extern "C" int inr_adam_step(const inr_plan* p, float* params, const float* grad
 static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
                            const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
                            const float* encB, const float* gt, const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev,
-                           void* workspace, float* out, float* loss_out_dev, cudaStream_t st, cudaEvent_t* ev) {
-  if (!p || !loss || !params || !m || !v || !wpack || !hyper_dev || !step_dev || !gt || !workspace || bs <= 0)
-    return fail(INR_EINVAL, "bad argument");
+                           void* workspace, float* out, float* loss_out_dev, cudaStream_t st, cudaEvent_t* ev,
+                           float* grads_only = nullptr) {
+  const bool no_adam = grads_only != nullptr;
+  if (!p || !loss || !params || !wpack || !gt || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
+  if (!no_adam && (!m || !v || !hyper_dev || !step_dev)) return fail(INR_EINVAL, "bad argument");
   const bool gauss = p->model.input_kind == INPUT_GAUSS;
   if (gauss && (!coords || !encB)) return fail(INR_EINVAL, "gauss encoder needs coords and encB");
   if (!gauss && !input_x) return fail(INR_EINVAL, "dense input needs input_x");
@@ -320,10 +322,11 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   LossDesc L{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
   if (ev) cudaEventRecord(ev[0], st);
   int rc = run_forward(p, w, L, params, wpack, coords, input_x, encB, gt, mask, bs, workspace, out, 1, row_cursor_dev,
-                       step_dev, st);
+                       no_adam ? nullptr : step_dev, st);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[1], st);
-  rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st, ev ? ev[2] : nullptr, hyper_dev, step_dev);
+  rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st, ev ? ev[2] : nullptr,
+                    no_adam ? nullptr : hyper_dev, no_adam ? nullptr : step_dev);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[3], st);
   AdamArgs a; fill_adam(p, a);
@@ -333,7 +336,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   a.scal = reinterpret_cast<const float*>(ws + w.scal_off);
   a.hyper = hyper_dev; a.step = step_dev; a.loss_out = loss_out_dev;
   a.row_offset = row_cursor_dev; a.row_advance = static_cast<int>(bs);
-  a.do_adam = 1; a.scal_has_bc = 1;
+  a.do_adam = no_adam ? 0 : 1; a.scal_has_bc = no_adam ? 0 : 1; a.grads = grads_only;
   cudaError_t e = launch_adam(a, st);
   if (ev) cudaEventRecord(ev[4], st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "adam_kernel");
@@ -345,6 +348,16 @@ extern "C" int inr_train_step(const inr_plan* p, const inr_loss_desc* loss, floa
                               void* workspace, float* out, float* loss_out_dev, void* stream) {
   return train_step_impl(p, loss, params, m, v, wpack, hyper_dev, step_dev, coords, input_x, encB, gt, mask, bs,
                          row_cursor_dev, workspace, out, loss_out_dev, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+extern "C" int inr_grad_step(const inr_plan* p, const inr_loss_desc* loss, const float* params, const void* wpack,
+                             const float* coords, const float* input_x, const float* encB, const float* gt,
+                             const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev, void* workspace, float* out,
+                             float* grads, float* loss_out_dev, void* stream) {
+  if (!grads) return fail(INR_EINVAL, "grads must not be null");
+  return train_step_impl(p, loss, const_cast<float*>(params), nullptr, nullptr, const_cast<void*>(wpack), nullptr, nullptr,
+                         coords, input_x, encB, gt, mask, bs, row_cursor_dev, workspace, out, loss_out_dev,
+                         static_cast<cudaStream_t>(stream), nullptr, grads);
 }
 
 extern "C" int inr_profile_step(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,

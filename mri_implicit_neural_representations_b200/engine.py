@@ -223,6 +223,17 @@ class ChainEngine:
             mat = out
         return mat
 
+    def grad_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, use_cursor: bool = False, out=None):
+        """forward + loss + backward only; gradients land in self.grads (data-parallel: all-reduce them, then adam_step)."""
+        o = loss_opts or {}
+        ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
+                        float(o.get("hdr_ff_factor", 0.0)))
+        L.check(L.lib.inr_grad_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords), _ptr(x),
+                                    _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None,
+                                    _ptr(self.workspace), _ptr(out), _ptr(self.grads), _ptr(self.loss_out), _stream()),
+                "inr_grad_step")
+        return self.grads
+
     def scalars(self, bs: int) -> torch.Tensor:
         off = self.plan.scalars_offset(bs)
         return self.workspace[off:off + 64].view(torch.float32).clone()
