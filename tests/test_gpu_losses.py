@@ -47,26 +47,30 @@ def test_fused_loss_value_and_gradients(inr, loss, masked):
     if loss == "MSLE":
         gt = gt.abs()
     mask = (torch.arange(bs) % 2 == 0) if masked else torch.ones(bs, dtype=torch.bool)
-    o_sel, g_sel = out_ref[mask], gt[mask]
+    out_dev = torch.empty(bs, 2, device="cuda")
+    g = eng.grad_step(loss, coords.cuda(), gt.cuda(), bs, mask=mask.to(torch.uint8).cuda() if masked else None,
+                      loss_opts=HDR, out=out_dev)
+    torch.cuda.synchronize()
+    assert rel(out_dev, out_ref) <= TOL
+    # The loss stage is judged teacher-forced on the engine's own network output: L1's sign(e) is discontinuous and
+    # HDR's 2 log(|e|/d) e/|e|^2 has a 1/|e|^2 sensitivity, so the 1.5e-4 forward error would otherwise dominate.
+    o_in = out_dev.cpu() if loss in ("L1", "HDR") else out_ref
+    o_sel, g_sel = o_in[mask], gt[mask]
     if loss == "HDR":
         val, dsel, _ = O.loss_hdr(o_sel, g_sel, coords, HDR["hdr_ff_sigma"], HDR["hdr_eps"], HDR["hdr_ff_factor"])
     elif loss == "LSL":
         val, dsel = O.loss_logspace(o_sel, g_sel, HDR["hdr_eps"])
     else:
         val, dsel = O.LOSS_TRAIN[loss](o_sel, g_sel)
+    if loss == "MSLE" and not torch.isfinite(val):
+        pytest.skip("MSLE undefined for this draw (log of a negative prediction), as in the reference")
     dout = torch.zeros_like(out_ref)
     dout[mask] = dsel
     grads_ref, _ = O.siren_backward(sd, x, tr, dout, 4)
-    g = eng.grad_step(loss, coords.cuda(), gt.cuda(), bs, mask=mask.to(torch.uint8).cuda() if masked else None, loss_opts=HDR)
-    torch.cuda.synchronize()
-    if loss == "MSLE" and not torch.isfinite(val):
-        pytest.skip("MSLE undefined for this draw (log of a negative prediction), as in the reference")
     assert abs(float(eng.loss_out) - float(val)) <= TOL * abs(float(val)), (float(eng.loss_out), float(val))
     for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
         gv = g[off:off + rows * cols].view(grads_ref[k].shape)
-        # L1's sign(e) and HDR's 1/|e| make dL/dout discontinuous / ill-conditioned in out: judge those two at 3e-3
-        tol = 3e-3 if loss in ("L1", "HDR") else TOL
-        assert rel(gv, grads_ref[k]) <= tol, (k, rel(gv, grads_ref[k]))
+        assert rel(gv, grads_ref[k]) <= TOL, (k, rel(gv, grads_ref[k]))
 
 
 @pytest.mark.parametrize("kind", ["L1", "L2"])
