@@ -196,6 +196,7 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=device)
+    from mri_implicit_neural_representations_b200.parallel import allreduce_mean_
     bs = wl["batch"]
     peaks = load_peaks()
 
@@ -210,7 +211,7 @@ def main():
     def one_step():
         if dp:      # forward+loss+backward -> all-reduce(mean) of the flat fp32 gradients -> Adam (+ fp16 re-pack)
             eng.grad_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
-            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)
+            allreduce_mean_(eng.grads)
             eng.adam_step()
         else:
             eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
@@ -296,7 +297,7 @@ def main():
         d_g.copy_(h_gt[j:j + bs], non_blocking=True)
         if dp:
             eng.grad_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
-            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)
+            allreduce_mean_(eng.grads)
             eng.adam_step()
         else:
             eng.train_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
