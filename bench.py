@@ -325,10 +325,16 @@ def main():
         ms_e2e = float(t)
     e2e_value = world * n_e2e * bs / (ms_e2e * 1e-3)
 
-    if rank != 0:
+    def finish():
+        # a CUDA graph that captured NCCL kernels can wedge destroy_process_group(); results are out, leave hard
         if dist:
+            torch.cuda.synchronize()
             dist.barrier()
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     cpu = None
@@ -365,9 +371,7 @@ def main():
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if dist:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
