@@ -33,6 +33,7 @@ extern "C" {
 /* model kinds (reference src/train.py:55-70) */
 #define INR_MODEL_SIREN 1    /* src/models/networks.py:99-124 */
 #define INR_MODEL_FFN 2      /* src/models/networks.py:48-69  */
+#define INR_MODEL_WIRE 3     /* src/models/networks.py:160-260 (complex Gabor; in 3, hidden int(width/sqrt 2) complex) */
 /* encoders (src/models/networks.py:7-35) */
 #define INR_ENC_NONE 0       /* x is the dense [bs, in] fp32 network input */
 #define INR_ENC_GAUSS 1      /* gamma(x) = [sin(2 pi x B^T), cos(2 pi x B^T)] computed in-kernel from coords */
@@ -58,7 +59,9 @@ typedef struct inr_model_desc {
   int32_t last_act;         /* INR_LAST_* */
   int32_t encoder;          /* INR_ENC_* */
   int32_t enc_size;         /* encoder.embedding_size (gauss) */
-  float w0;                 /* SIREN: 30 (hard-wired in the reference, src/models/networks.py:75) */
+  float w0;                 /* SIREN: 30 (hard-wired in the reference, src/models/networks.py:75); WIRE: first_omega_0 */
+  float hidden_omega_0;     /* WIRE: net.hidden_omega_0 */
+  float sigma0;             /* WIRE: net.scale */
 } inr_model_desc;
 
 typedef struct inr_loss_desc {
@@ -70,6 +73,8 @@ typedef struct inr_tensor_info {
   int64_t offset;           /* float offset inside the flat parameter buffer */
   int32_t rows, cols;       /* weight [rows, cols]; bias: rows = n, cols = 1 */
   int32_t layer, is_bias;
+  int32_t is_complex;       /* complex64 tensor: rows*cols interleaved (re, im) float pairs */
+  int32_t frozen;           /* requires_grad False in the reference (WIRE omega_0 / scale_0): never updated */
 } inr_tensor_info;
 
 /* hyper-parameter block read from DEVICE memory each step (so a captured CUDA graph sees updates):

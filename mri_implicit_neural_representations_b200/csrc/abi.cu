@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include "../../include/inr_b200.h"
 #include "inr_kernels.cuh"
+#include "wire.cuh"
 
 namespace inr {
 cudaError_t launch_chain_fwd(const FwdArgs& a, int n_sm, cudaStream_t stream);
@@ -16,12 +17,22 @@ cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream);
 cudaError_t launch_adam(const AdamArgs& a, cudaStream_t stream);
 cudaError_t launch_pack(const AdamArgs& a, cudaStream_t stream);
 cudaError_t launch_dout_amax(const float* dout, int bs, int out_f, float* partials, int n_tiles, cudaStream_t stream);
+cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream);
+cudaError_t launch_wire_first(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_wire_last(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_wire_scalars(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_wire_dout_amax(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_wire_blast(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st);
+cudaError_t launch_wire_adam_flat(const WireAdamArgs& a, cudaStream_t st);
 }  // namespace inr
 
 using namespace inr;
 
 struct inr_plan {
   inr_model_desc desc;
+  bool is_wire = false;
+  WireModel wm;
   ChainModel model;
   std::vector<inr_tensor_info> tensors;
   std::vector<SegDesc> segs;
@@ -41,8 +52,12 @@ static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 extern "C" const char* inr_last_error(void) { return g_err.c_str(); }
 extern "C" int inr_debug_set_trace(void* dev_u64_buffer_64) { g_trace = static_cast<unsigned long long*>(dev_u64_buffer_64); return INR_OK; }
 
+static int wire_plan_create(const inr_model_desc* d, inr_plan** out);
+static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs);
+
 extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (!d || !out) return fail(INR_EINVAL, "null argument");
+  if (d->model == INR_MODEL_WIRE) return wire_plan_create(d, out);
   if (d->model != INR_MODEL_SIREN && d->model != INR_MODEL_FFN) return fail(INR_EUNSUPPORTED, "model kind not built yet");
   if (d->width != kWidth) return fail(INR_EUNSUPPORTED, "tensor-core chain kernels are built for network_width 256");
   if (d->depth < 2 || d->depth - 1 > kMaxLayers - 1) return fail(INR_EINVAL, "network_depth out of range");
@@ -74,7 +89,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
     const int rows = l == M.n_gemm ? M.out_f : kWidth;
     const int cols = l == 0 ? M.k0 : kWidth;
     M.w_off[l] = off;
-    p->tensors.push_back({off, rows, cols, l, 0});
+    p->tensors.push_back({off, rows, cols, l, 0, 0, 0});
     SegDesc sw{};
     sw.off = off; sw.rows = rows; sw.cols = cols; sw.layer = l;
     sw.fwd_scale = sw.bwd_scale = (M.act == ACT_SIN) ? M.w0 : 1.f;
@@ -87,7 +102,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
     p->segs.push_back(sw);
     off += rows * cols;
     M.b_off[l] = off;
-    p->tensors.push_back({off, rows, 1, l, 1});
+    p->tensors.push_back({off, rows, 1, l, 1, 0, 0});
     SegDesc sb{};
     sb.off = off; sb.rows = rows; sb.cols = 1; sb.layer = l;
     p->segs.push_back(sb);
@@ -141,7 +156,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
 extern "C" int inr_plan_destroy(inr_plan* p) { delete p; return INR_OK; }
 extern "C" int inr_plan_param_count(const inr_plan* p, int64_t* n) {
   if (!p || !n) return fail(INR_EINVAL, "null argument");
-  *n = p->model.n_params; return INR_OK;
+  *n = p->is_wire ? p->wm.n_params : p->model.n_params; return INR_OK;
 }
 extern "C" int inr_plan_tensor_count(const inr_plan* p, int32_t* n) {
   if (!p || !n) return fail(INR_EINVAL, "null argument");
@@ -153,7 +168,7 @@ extern "C" int inr_plan_tensor(const inr_plan* p, int32_t i, inr_tensor_info* ou
 }
 extern "C" int inr_wpack_bytes(const inr_plan* p, size_t* b) {
   if (!p || !b) return fail(INR_EINVAL, "null argument");
-  *b = p->model.wpack_bytes; return INR_OK;
+  *b = p->is_wire ? p->wm.wpack_bytes : p->model.wpack_bytes; return INR_OK;
 }
 
 static Workspace plan_workspace(const inr_plan* p, int64_t bs) {
@@ -183,15 +198,25 @@ static Workspace plan_workspace(const inr_plan* p, int64_t bs) {
 
 extern "C" int inr_workspace_bytes(const inr_plan* p, int64_t bs, size_t* bytes) {
   if (!p || !bytes || bs <= 0) return fail(INR_EINVAL, "bad argument");
-  *bytes = plan_workspace(p, bs).total; return INR_OK;
+  *bytes = p->is_wire ? wire_workspace(p, bs).total : plan_workspace(p, bs).total; return INR_OK;
 }
 extern "C" int inr_scalars_offset(const inr_plan* p, int64_t bs, size_t* off) {
   if (!p || !off || bs <= 0) return fail(INR_EINVAL, "bad argument");
-  *off = plan_workspace(p, bs).scal_off; return INR_OK;
+  *off = p->is_wire ? wire_workspace(p, bs).scal : plan_workspace(p, bs).scal_off; return INR_OK;
 }
 
 extern "C" int inr_workspace_layout(const inr_plan* p, int64_t bs, uint64_t* out, int32_t n) {
   if (!p || !out || bs <= 0 || n < 44) return fail(INR_EINVAL, "bad argument");
+  if (p->is_wire) {   // H_hi at [l], H_lo at [12+l] is not representable in 12 slots each: report hi / ab / dz families
+    const WireWorkspace w = wire_workspace(p, bs);
+    for (int l = 0; l < kMaxLayers; ++l) {
+      out[l] = l <= p->wm.depth + 1 ? w.hhi[l] : 0; out[12 + l] = l <= p->wm.depth ? w.ab[l] : 0;
+      out[24 + l] = l <= p->wm.depth ? w.dz[l] : 0;
+    }
+    out[36] = w.dzlast; out[37] = w.g; out[38] = w.part; out[39] = w.scal; out[40] = w.gpart;
+    out[41] = static_cast<uint64_t>(w.n_tiles); out[42] = static_cast<uint64_t>(w.n_split); out[43] = w.total;
+    return INR_OK;
+  }
   const Workspace w = plan_workspace(p, bs);
   for (int l = 0; l < kMaxLayers; ++l) { out[l] = w.h_off[l]; out[12 + l] = w.d_off[l]; out[24 + l] = w.dz_off[l]; }
   out[36] = w.dzlast_off; out[37] = w.g_off; out[38] = w.part_off; out[39] = w.scal_off; out[40] = w.gpart_off;
@@ -221,8 +246,215 @@ static void fill_wgrad(const inr_plan* p, const Workspace& w, uint8_t* ws, Wgrad
   g.ws = ws; g.gpart_off = w.gpart_off;
 }
 
+
+// =====================================================================================================================
+// WIRE (complex Gabor) path
+// =====================================================================================================================
+static int query_sm_count() {
+  int dev = 0, n = 0, sm = 148;
+  if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0 && cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sm = v;
+  } else {
+    cudaGetLastError();
+  }
+  return sm;
+}
+
+static int wire_plan_create(const inr_model_desc* d, inr_plan** out) {
+  const int c = static_cast<int>(static_cast<double>(d->width) / 1.4142135623730951);   // int(width / sqrt(2)), networks.py:228
+  if (d->in_features != 3) return fail(INR_EUNSUPPORTED, "WIRE kernels take raw (coil, kx, ky) coordinates: network_input_size 3");
+  if (d->encoder != INR_ENC_NONE) return fail(INR_EUNSUPPORTED, "WIRE is used without positional encoding");
+  if (c < 8 || c > kWP) return fail(INR_EUNSUPPORTED, "WIRE kernels are built for complex width <= 192 (network_width <= 271)");
+  if (d->depth < 1 || d->depth > kWMaxDepth) return fail(INR_EINVAL, "network_depth out of range");
+  if (d->out_features < 1 || d->out_features > 2) return fail(INR_EUNSUPPORTED, "network_output_size must be 1 or 2");
+  inr_plan* p = new (std::nothrow) inr_plan();
+  if (!p) return fail(INR_EINVAL, "out of host memory");
+  p->desc = *d;
+  p->is_wire = true;
+  WireModel& M = p->wm;
+  std::memset(&M, 0, sizeof(M));
+  M.depth = d->depth; M.c = c; M.in_f = 3; M.out_f = d->out_features;
+  M.omega_first = d->w0; M.omega_hidden = d->hidden_omega_0; M.sigma = d->sigma0;
+  int off = 0;
+  const int L = M.depth + 1;
+  for (int l = 0; l <= L; ++l) {
+    if (l < L) {
+      M.omega_off[l] = off; p->tensors.push_back({off, 1, 1, l, 0, 0, 1}); off += 1;
+      M.scale_off[l] = off; p->tensors.push_back({off, 1, 1, l, 0, 0, 1}); off += 1;
+    }
+    if (l == 0) {
+      M.w_off[l] = off; p->tensors.push_back({off, c, 3, l, 0, 0, 0}); off += c * 3;
+      M.b_off[l] = off; p->tensors.push_back({off, c, 1, l, 1, 0, 0}); off += c;
+    } else {
+      const int rows = l == L ? M.out_f : c;
+      M.w_off[l] = off; p->tensors.push_back({off, rows, c, l, 0, 1, 0}); off += rows * c * 2;
+      M.b_off[l] = off; p->tensors.push_back({off, rows, 1, l, 1, 1, 0}); off += rows * 2;
+    }
+  }
+  M.n_params = off;
+  const uint32_t blk = 2u * (kW2 / kStageK) * kWStageBBytes;      // two N-blocks of one packed operand
+  uint32_t wo = 0;
+  for (int l = 1; l <= M.depth; ++l) {
+    M.wf_hi[l] = wo; wo += blk;
+    M.wf_lo[l] = wo; wo += blk;
+    M.wd_hi[l] = wo; wo += blk;
+  }
+  M.wpack_bytes = wo;
+  int go = 0;
+  for (int l = 1; l <= M.depth; ++l) { M.gd_hidden[l] = go; go += kW2 * kW2 + kW2; }
+  M.gd_final = go; go += 16 * kW2 + 16;
+  M.gd_first = go; go += 256 * 16;
+  M.gd_floats = go;
+  // wgrad units (offsets into the workspace are filled per call)
+  for (int l = 1; l <= M.depth; ++l)
+    for (int mc = 0; mc < 3; ++mc)
+      for (int nc = 0; nc < 3; ++nc) {
+        WgradUnit u{};
+        u.a_tile_stride = kWTileBytes; u.a_sub = mc * 32768; u.a_bytes = 32768;
+        u.b_tile_stride = kWTileBytes; u.b_sub = nc * 32768; u.b_bytes = 32768;
+        u.n = 128; u.transposed = 0;
+        u.out_off = M.gd_hidden[l]; u.out_ld = kW2; u.row0 = mc * 128; u.col0 = nc * 128;
+        u.rows_valid = 128; u.cols_valid = 128;
+        u.bias_off = nc == 0 ? M.gd_hidden[l] + kW2 * kW2 : -1;
+        p->units.push_back(u); p->unit_layer.push_back(l);
+      }
+  for (int mc = 0; mc < 3; ++mc) {          // final layer, transposed: D^T[o][f] = sum_rows dz_last[o] * [hr|hi][f]
+    WgradUnit u{};
+    u.a_tile_stride = kWTileBytes; u.a_sub = mc * 32768; u.a_bytes = 32768;
+    u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+    u.n = kDzLastCols; u.transposed = 1;
+    u.out_off = M.gd_final; u.out_ld = kW2; u.row0 = 0; u.col0 = mc * 128;
+    u.rows_valid = M.out_f; u.cols_valid = 128;
+    u.bias_off = mc == 0 ? M.gd_final + 16 * kW2 : -1;
+    p->units.push_back(u); p->unit_layer.push_back(L);
+  }
+  for (int mc = 0; mc < 2; ++mc) {          // first layer: D0[o][col] = sum_rows dza0[o] * ximg[col]
+    WgradUnit u{};
+    u.a_tile_stride = kWTileBytes; u.a_sub = mc * 32768; u.a_bytes = 32768;
+    u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+    u.n = kDzLastCols; u.transposed = 0;
+    u.out_off = M.gd_first; u.out_ld = 16; u.row0 = mc * 128; u.col0 = 0;
+    u.rows_valid = 128; u.cols_valid = 16;
+    u.bias_off = -1;
+    p->units.push_back(u); p->unit_layer.push_back(0);
+  }
+  if (static_cast<int>(p->units.size()) > kMaxUnits) { delete p; return fail(INR_EUNSUPPORTED, "WIRE model too deep for the static unit table"); }
+  p->n_sm = query_sm_count();
+  *out = p;
+  return INR_OK;
+}
+
+static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
+  const WireModel& M = p->wm;
+  WireWorkspace w{};
+  const int T = static_cast<int>((bs + kTileM - 1) / kTileM);
+  w.n_tiles = T;
+  int ns = p->n_sm / static_cast<int>(p->units.size());
+  if (ns < 1) ns = 1;
+  if (ns > T) ns = T > 0 ? T : 1;
+  w.n_split = ns;
+  uint64_t o = 0;
+  w.scal = o; o += align_up(kScalars * 4, 1024);
+  w.part = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
+  w.g = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
+  w.outacc = o;
+  const uint64_t img = static_cast<uint64_t>(T) * kWTileBytes;
+  for (int l = 1; l <= M.depth + 1; ++l) { w.hhi[l] = o; o += img; w.hlo[l] = o; o += img; }
+  for (int l = 0; l <= M.depth; ++l) { w.ab[l] = o; o += img; }
+  for (int l = 0; l <= M.depth; ++l) { w.dz[l] = o; o += img; }
+  w.dzlast = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024);
+  w.ximg = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024);
+  w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * M.gd_floats * 4, 1024);
+  w.total = o;
+  return w;
+}
+
+static void wire_aux_fill(const inr_plan* p, const WireWorkspace& w, WireAuxArgs& x, const float* params, void* ws, int64_t bs) {
+  std::memset(&x, 0, sizeof(x));
+  x.m = p->wm; x.w = w; x.params = params; x.ws = static_cast<uint8_t*>(ws);
+  x.bs = static_cast<int>(bs); x.bs_k = static_cast<int>(bs);
+  x.loss = LossDesc{LOSS_NONE, 0.f, 0.f, 0.f};
+}
+
+static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
+                             const float* coords, const float* gt, const uint8_t* mask, int64_t bs, void* ws, float* out, int train,
+                             const int* row_off, int* step, cudaStream_t st) {
+  const WireModel& M = p->wm;
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const uint8_t* wp = static_cast<const uint8_t*>(wpack);
+  WireAuxArgs x; wire_aux_fill(p, w, x, params, ws, bs);
+  x.loss = loss; x.coords = coords; x.gt = gt; x.mask = mask; x.out = out; x.train = train;
+  x.row_offset = row_off; x.step_counter = step;
+  cudaError_t e = launch_wire_first(x, st);
+  if (e != cudaSuccess) return cuda_fail(e, "wire_first_kernel");
+  for (int l = 1; l <= M.depth; ++l) {
+    LGemmArgs g{};
+    g.a_hi = W + w.hhi[l]; g.a_lo = W + w.hlo[l];
+    g.b_hi = wp + M.wf_hi[l]; g.b_lo = wp + M.wf_lo[l];
+    g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 3; g.mode = LG_WIRE_FWD;
+    g.bias = params + M.b_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.train = train;
+    g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
+    e = launch_lgemm(g, p->n_sm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(fwd)");
+  }
+  x.step_counter = nullptr;
+  e = launch_wire_last(x, st);
+  return e == cudaSuccess ? INR_OK : cuda_fail(e, "wire_last_kernel");
+}
+
+static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
+                              const float* dout, int64_t bs, void* ws, const float* hyper, const int* step, cudaStream_t st) {
+  const WireModel& M = p->wm;
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const uint8_t* wp = static_cast<const uint8_t*>(wpack);
+  WireAuxArgs x; wire_aux_fill(p, w, x, params, ws, bs);
+  x.loss = loss; x.dout = dout; x.hyper = hyper; x.step = step;
+  cudaError_t e;
+  if (dout) { e = launch_wire_dout_amax(x, st); if (e != cudaSuccess) return cuda_fail(e, "wire_dout_amax_kernel"); }
+  e = launch_wire_scalars(x, st);
+  if (e != cudaSuccess) return cuda_fail(e, "wire_scalars_kernel");
+  e = launch_wire_blast(x, st);
+  if (e != cudaSuccess) return cuda_fail(e, "wire_blast_kernel");
+  for (int l = M.depth; l >= 1; --l) {      // dL/dh_{l-1} = dZ_l * conj-block(W_l), then the Gabor derivative of layer l-1
+    LGemmArgs g{};
+    g.a_hi = W + w.dz[l]; g.a_lo = nullptr; g.b_hi = wp + M.wd_hi[l]; g.b_lo = nullptr;
+    g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 1; g.mode = LG_WIRE_DGRAD;
+    g.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c;
+    g.real_first = (l - 1 == 0) ? 1 : 0;
+    g.in_y = W + w.hhi[l]; g.in_ab = W + w.ab[l - 1]; g.out_dz = W + w.dz[l - 1];
+    e = launch_lgemm(g, p->n_sm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(dgrad)");
+  }
+  WgradArgs wg; std::memset(&wg, 0, sizeof(wg));
+  wg.n_units = static_cast<int>(p->units.size());
+  const int L = M.depth + 1;
+  for (int i = 0; i < wg.n_units; ++i) {
+    WgradUnit u = p->units[i];
+    const int l = p->unit_layer[i];
+    if (l == 0) { u.a_off = w.dz[0]; u.b_off = w.ximg; }
+    else if (l == L) { u.a_off = w.hhi[L]; u.b_off = w.dzlast; }
+    else { u.a_off = w.dz[l]; u.b_off = w.hhi[l]; }
+    wg.u[i] = u;
+  }
+  wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = M.gd_floats; wg.ws = W; wg.gpart_off = w.gpart;
+  e = launch_wgrad(wg, st);
+  return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel(wire)");
+}
+
+static void wire_adam_fill(const inr_plan* p, WireAdamArgs& a) {
+  std::memset(&a, 0, sizeof(a));
+  a.m = p->wm;
+}
+
 extern "C" int inr_pack_weights(const inr_plan* p, const float* params, void* wpack, void* stream) {
   if (!p || !params || !wpack) return fail(INR_EINVAL, "null argument");
+  if (p->is_wire) {
+    WireAdamArgs wa; wire_adam_fill(p, wa);
+    wa.params = const_cast<float*>(params); wa.wpack = static_cast<uint8_t*>(wpack); wa.pack_only = 1;
+    cudaError_t we = launch_wire_adam(wa, static_cast<cudaStream_t>(stream));
+    return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_kernel(pack)");
+  }
   AdamArgs a; fill_adam(p, a);
   a.params = const_cast<float*>(params); a.wpack = static_cast<uint8_t*>(wpack);
   cudaError_t e = launch_pack(a, static_cast<cudaStream_t>(stream));
@@ -246,6 +478,12 @@ extern "C" int inr_forward(const inr_plan* p, const float* params, const void* w
                            int64_t bs, void* workspace, float* out, int32_t train, void* stream) {
   if (!p || !params || !wpack || !input || !out || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (train && !workspace) return fail(INR_EINVAL, "training forward needs a workspace");
+  if (p->is_wire) {
+    if (!workspace) return fail(INR_EINVAL, "WIRE forward streams its activations through the workspace");
+    const WireWorkspace ww = wire_workspace(p, bs);
+    return wire_forward_impl(p, ww, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, input, nullptr, nullptr, bs, workspace, out,
+                             train ? 1 : 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  }
   const bool gauss = p->model.input_kind == INPUT_GAUSS;
   if (gauss && !encB) return fail(INR_EINVAL, "gauss encoder needs encB");
   Workspace w = plan_workspace(p, bs);
@@ -274,6 +512,17 @@ extern "C" int inr_backward(const inr_plan* p, const float* params, const void* 
                             void* workspace, float* grads, void* stream) {
   if (!p || !params || !wpack || !dout || !workspace || !grads || bs <= 0) return fail(INR_EINVAL, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->is_wire) {
+    const WireWorkspace ww = wire_workspace(p, bs);
+    int rcw = wire_backward_impl(p, ww, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, dout, bs, workspace, nullptr, nullptr, st);
+    if (rcw) return rcw;
+    WireAdamArgs wa; wire_adam_fill(p, wa);
+    wa.n_split = ww.n_split; wa.params = const_cast<float*>(params); wa.grads = grads;
+    wa.gpart = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + ww.gpart);
+    wa.scal = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + ww.scal);
+    cudaError_t we = launch_wire_adam(wa, st);
+    return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_kernel(reduce)");
+  }
   Workspace w = plan_workspace(p, bs);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   cudaError_t e = launch_dout_amax(dout, static_cast<int>(bs), p->model.out_f, reinterpret_cast<float*>(ws + w.part_off), w.n_tiles, st);
@@ -294,6 +543,13 @@ extern "C" int inr_backward(const inr_plan* p, const float* params, const void* 
 extern "C" int inr_adam_step(const inr_plan* p, float* params, const float* grads, float* m, float* v, void* wpack,
                              const float* hyper_dev, const int32_t* step_dev, void* stream) {
   if (!p || !params || !grads || !m || !v || !wpack || !hyper_dev || !step_dev) return fail(INR_EINVAL, "null argument");
+  if (p->is_wire) {
+    WireAdamArgs wa; wire_adam_fill(p, wa);
+    wa.params = params; wa.mom = m; wa.var = v; wa.wpack = static_cast<uint8_t*>(wpack); wa.gpart = grads;
+    wa.hyper = hyper_dev; wa.step = step_dev; wa.do_adam = 1;
+    cudaError_t we = launch_wire_adam_flat(wa, static_cast<cudaStream_t>(stream));
+    return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_flat_kernel");
+  }
   AdamArgs a; fill_adam(p, a);
   a.n_split = 1; a.params = params; a.m = m; a.v = v; a.wpack = static_cast<uint8_t*>(wpack);
   a.gpart = grads; a.scal = nullptr; a.hyper = hyper_dev; a.step = step_dev; a.do_adam = 1;
@@ -309,6 +565,33 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   const bool no_adam = grads_only != nullptr;
   if (!p || !loss || !params || !wpack || !gt || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (!no_adam && (!m || !v || !hyper_dev || !step_dev)) return fail(INR_EINVAL, "bad argument");
+  if (p->is_wire) {
+    if (!coords) return fail(INR_EINVAL, "WIRE needs coords");
+    if (loss->kind < INR_LOSS_L2 || loss->kind > INR_LOSS_HDR) return fail(INR_EINVAL, "unknown loss kind");
+    if ((loss->kind == INR_LOSS_HDR || loss->kind == INR_LOSS_LSL) && p->wm.out_f != 2)
+      return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
+    const WireWorkspace ww = wire_workspace(p, bs);
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    const LossDesc WL{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
+    if (ev) cudaEventRecord(ev[0], st);
+    int rcw = wire_forward_impl(p, ww, WL, params, wpack, coords, gt, mask, bs, workspace, out, 1, row_cursor_dev,
+                                no_adam ? nullptr : step_dev, st);
+    if (rcw) return rcw;
+    if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
+    rcw = wire_backward_impl(p, ww, WL, params, wpack, nullptr, bs, workspace, no_adam ? nullptr : hyper_dev,
+                             no_adam ? nullptr : step_dev, st);
+    if (rcw) return rcw;
+    if (ev) cudaEventRecord(ev[3], st);
+    WireAdamArgs wa; wire_adam_fill(p, wa);
+    wa.n_split = ww.n_split; wa.params = params; wa.mom = m; wa.var = v; wa.wpack = static_cast<uint8_t*>(wpack);
+    wa.gpart = reinterpret_cast<const float*>(wsb + ww.gpart); wa.scal = reinterpret_cast<const float*>(wsb + ww.scal);
+    wa.hyper = hyper_dev; wa.step = step_dev; wa.loss_out = loss_out_dev;
+    wa.row_offset = row_cursor_dev; wa.row_advance = static_cast<int>(bs);
+    wa.do_adam = no_adam ? 0 : 1; wa.scal_has_bc = no_adam ? 0 : 1; wa.grads = grads_only;
+    cudaError_t we = launch_wire_adam(wa, st);
+    if (ev) cudaEventRecord(ev[4], st);
+    return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_kernel");
+  }
   const bool gauss = p->model.input_kind == INPUT_GAUSS;
   if (gauss && (!coords || !encB)) return fail(INR_EINVAL, "gauss encoder needs coords and encB");
   if (!gauss && !input_x) return fail(INR_EINVAL, "dense input needs input_x");

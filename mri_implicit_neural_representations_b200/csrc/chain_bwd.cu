@@ -16,6 +16,7 @@
 #include <cmath>
 #include "inr_ptx.cuh"
 #include "inr_kernels.cuh"
+#include "inr_loss.cuh"
 
 namespace inr {
 
@@ -24,72 +25,6 @@ constexpr int kBwdComputeThreads = 512;                   // warps 4..19
 constexpr int kBwdThreads = 128 + kBwdComputeThreads;
 constexpr int kBwdSmem = 2 * kActBytes + kBwdStages * kStageBytes + kMaxOut * kWidth * 4 + 1024;
 static_assert(kBwdSmem <= 227 * 1024, "backward kernel shared memory budget");
-
-// Fixed-order block reduction of the tile partials; result broadcast through shared memory.
-__device__ void reduce_step_scalars(const BwdArgs& a, float* sc /* smem[kScalars] */) {
-  __shared__ float part[kBwdThreads / 32][6];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* p = reinterpret_cast<const float*>(a.ws + a.w.part_off);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, m4 = 0.f, m5 = 0.f;
-  for (int t = tid; t < a.w.n_tiles; t += kBwdThreads) {
-    const float* q = p + static_cast<size_t>(t) * kPartialsPerTile;
-    s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3];
-    m4 = fmaxf(m4, q[4]); m5 = fmaxf(m5, q[5]);
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, off); s3 += __shfl_xor_sync(0xffffffffu, s3, off);
-    m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, off)); m5 = fmaxf(m5, __shfl_xor_sync(0xffffffffu, m5, off));
-  }
-  if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; part[warp][3] = s3; part[warp][4] = m4; part[warp][5] = m5; }
-  __syncthreads();
-  if (tid == 0) {
-    float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
-    for (int w = 0; w < kBwdThreads / 32; ++w) {
-      lA += part[w][0]; lB += part[w][1]; fs += part[w][2]; cnt += part[w][3];
-      amA = fmaxf(amA, part[w][4]); amB = fmaxf(amB, part[w][5]);
-    }
-    const float m = fmaxf(cnt, 1.f);
-    const float of = static_cast<float>(a.m.out_f);
-    float cA = 0.f, cB = 0.f, loss = 0.f, fmean = 0.f;
-    switch (a.loss.kind) {      // weights of src/train.py:178-182 folded in
-      case LOSS_L2:   cA = 1.f / (m * of);         loss = lA * 0.5f / (m * of); break;
-      case LOSS_L1:   cA = 0.5f / (m * of);        loss = lA * 0.5f / (m * of); break;
-      case LOSS_MSLE: cA = 1.f / (m * of);         loss = lA * 0.5f / (m * of); break;
-      case LOSS_TANH: cA = 2.f / (m * of);         loss = lA / (m * of); break;
-      case LOSS_LSL:  cA = 1.f / m;                loss = lA * 0.5f / m; break;
-      case LOSS_HDR:
-        fmean = fs / static_cast<float>(a.bs_k > 0 ? a.bs_k : 1);
-        cA = 1.f / m; cB = a.loss.factor * fmean / m;
-        loss = lA / m + a.loss.factor * fmean * lB / m;
-        sc[SC_REG] = a.loss.factor * fmean * lB / m;
-        break;
-      default: cA = 1.f; break;   // external dout: gA holds dL/dout already
-    }
-    const float amax = cA * amA + fabsf(cB) * amB;
-    float S = 1.f;
-    if (amax > 0.f && isfinite(amax)) {
-      int e = static_cast<int>(floorf(log2f(256.f / amax)));
-      e = e < -60 ? -60 : (e > 60 ? 60 : e);
-      S = exp2f(static_cast<float>(e));
-    }
-    sc[SC_LOSS] = loss; sc[SC_SCALE] = S; sc[SC_CA] = cA; sc[SC_CB] = cB; sc[SC_COUNT] = cnt; sc[SC_FMEAN] = fmean;
-    sc[SC_INV_SCALE] = 1.f / S;
-    if (a.loss.kind != LOSS_HDR) sc[SC_REG] = 0.f;
-    if (blockIdx.x == 0) {
-      sc[SC_STEP_SIZE] = 0.f; sc[SC_BC2_SQRT] = 1.f;
-      if (a.hyper && a.step) {     // torch.optim.Adam: step_size = lr / (1 - b1^t), denom uses sqrt(1 - b2^t)
-        const double t = static_cast<double>(*a.step);
-        sc[SC_STEP_SIZE] = static_cast<float>(static_cast<double>(a.hyper[0]) / (1.0 - pow(static_cast<double>(a.hyper[1]), t)));
-        sc[SC_BC2_SQRT] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.hyper[2]), t)));
-      }
-      float* g = reinterpret_cast<float*>(a.ws + a.w.scal_off);
-      for (int i = 0; i < 10; ++i) g[i] = sc[i];
-    }
-  }
-  __syncthreads();
-}
 
 __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -119,7 +54,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  reduce_step_scalars(a, sc);
+  reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part_off), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step,
+                      blockIdx.x == 0 ? reinterpret_cast<float*>(a.ws + a.w.scal_off) : nullptr, sc);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: act' images + dgrad weight stages

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include "inr_ptx.cuh"
 #include "inr_kernels.cuh"
+#include "inr_loss.cuh"
 
 namespace inr {
 
@@ -27,68 +28,6 @@ constexpr int kFwdMaxEnc = 512;                           // encoder features st
 constexpr int kFwdConstBytes = ((kMaxLayers - 1) * kWidth + kMaxOut * kWidth + kFwdMaxEnc * 3) * 4;
 constexpr int kFwdSmem = kActBytes + kFwdStages * kStageBytes + kFwdConstBytes + 1024;
 static_assert(kFwdSmem <= 227 * 1024, "forward kernel shared memory budget");
-
-__device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
-
-// Per-row loss pieces.  y = network output, t = target.  Returns unnormalised dL/dy parts gA, gB and
-// loss numerators; the normalisation by the (masked) row count happens in the backward prologue.
-struct RowLoss {
-  float lossA, lossB, gA[kMaxOut], gB[kMaxOut];
-};
-__device__ __forceinline__ RowLoss loss_row(const LossDesc& L, int out_f, const float* y, const float* t) {
-  RowLoss r;
-  r.lossA = 0.f; r.lossB = 0.f;
-#pragma unroll
-  for (int o = 0; o < kMaxOut; ++o) { r.gA[o] = 0.f; r.gB[o] = 0.f; }
-  switch (L.kind) {
-    case LOSS_L2:
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) { float e = y[o] - t[o]; r.lossA += e * e; r.gA[o] = e; }
-      break;
-    case LOSS_L1:
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
-        float e = y[o] - t[o]; r.lossA += fabsf(e); r.gA[o] = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
-      }
-      break;
-    case LOSS_MSLE:   // src/metrics/losses.py:26 (NaN for arguments <= 0, as the reference)
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
-        float ax = y[o] + 1.f + 1e-9f;
-        float d = logf(ax) - logf(t[o] + 1.f + 1e-9f);
-        r.lossA += d * d; r.gA[o] = d / ax;
-      }
-      break;
-    case LOSS_TANH:   // src/metrics/losses.py:131
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
-        float tx = tanh_acc(y[o]), ty = tanh_acc(t[o]);
-        float d = tx - ty; r.lossA += d * d; r.gA[o] = d * (1.f - tx * tx);
-      }
-      break;
-    case LOSS_LSL: {  // src/metrics/losses.py:221-223, complex pairs, |x| detached
-      float e0 = y[0] - t[0], e1 = y[1] - t[1];
-      float d = sqrtf(y[0] * y[0] + y[1] * y[1]) + L.eps;
-      float inv = 1.f / (d * d);
-      r.lossA = (e0 * e0 + e1 * e1) * inv; r.gA[0] = e0 * inv; r.gA[1] = e1 * inv;
-    } break;
-    case LOSS_HDR: {  // src/metrics/losses.py:250-259 in separable form
-      float e0 = y[0] - t[0], e1 = y[1] - t[1];
-      float ae2 = e0 * e0 + e1 * e1;
-      float ax2 = y[0] * y[0] + y[1] * y[1];
-      float d = sqrtf(ax2) + L.eps;
-      float lg = logf(sqrtf(ae2) / d);
-      float inv = 1.f / (d * d);
-      r.lossA = lg * lg;
-      r.lossB = ax2 * inv;
-      float c = 2.f * lg / ae2;
-      r.gA[0] = c * e0; r.gA[1] = c * e1;
-      r.gB[0] = 2.f * y[0] * inv; r.gB[1] = 2.f * y[1] * inv;
-    } break;
-    default: break;
-  }
-  return r;
-}
 
 template <int ACT>
 __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_constant__ FwdArgs a) {

@@ -1,0 +1,139 @@
+// Loss pieces shared by every model family: per-row loss numerators / unnormalised gradients (forward side) and the
+// fixed-order reduction of the per-tile partials into the step scalars (backward side).
+#pragma once
+#include <cmath>
+#include "inr_kernels.cuh"
+
+namespace inr {
+
+__device__ __forceinline__ float tanh_acc(float x) { return tanhf(x); }
+
+// Per-row loss pieces.  y = network output, t = target.  Returns unnormalised dL/dy parts gA, gB and
+// loss numerators; the normalisation by the (masked) row count happens in the backward prologue.
+struct RowLoss {
+  float lossA, lossB, gA[kMaxOut], gB[kMaxOut];
+};
+__device__ __forceinline__ RowLoss loss_row(const LossDesc& L, int out_f, const float* y, const float* t) {
+  RowLoss r;
+  r.lossA = 0.f; r.lossB = 0.f;
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) { r.gA[o] = 0.f; r.gB[o] = 0.f; }
+  switch (L.kind) {
+    case LOSS_L2:
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) { float e = y[o] - t[o]; r.lossA += e * e; r.gA[o] = e; }
+      break;
+    case LOSS_L1:
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
+        float e = y[o] - t[o]; r.lossA += fabsf(e); r.gA[o] = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
+      }
+      break;
+    case LOSS_MSLE:   // src/metrics/losses.py:26 (NaN for arguments <= 0, as the reference)
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
+        float ax = y[o] + 1.f + 1e-9f;
+        float d = logf(ax) - logf(t[o] + 1.f + 1e-9f);
+        r.lossA += d * d; r.gA[o] = d / ax;
+      }
+      break;
+    case LOSS_TANH:   // src/metrics/losses.py:131
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < out_f) {
+        float tx = tanh_acc(y[o]), ty = tanh_acc(t[o]);
+        float d = tx - ty; r.lossA += d * d; r.gA[o] = d * (1.f - tx * tx);
+      }
+      break;
+    case LOSS_LSL: {  // src/metrics/losses.py:221-223, complex pairs, |x| detached
+      float e0 = y[0] - t[0], e1 = y[1] - t[1];
+      float d = sqrtf(y[0] * y[0] + y[1] * y[1]) + L.eps;
+      float inv = 1.f / (d * d);
+      r.lossA = (e0 * e0 + e1 * e1) * inv; r.gA[0] = e0 * inv; r.gA[1] = e1 * inv;
+    } break;
+    case LOSS_HDR: {  // src/metrics/losses.py:250-259 in separable form
+      float e0 = y[0] - t[0], e1 = y[1] - t[1];
+      float ae2 = e0 * e0 + e1 * e1;
+      float ax2 = y[0] * y[0] + y[1] * y[1];
+      float d = sqrtf(ax2) + L.eps;
+      float lg = logf(sqrtf(ae2) / d);
+      float inv = 1.f / (d * d);
+      r.lossA = lg * lg;
+      r.lossB = ax2 * inv;
+      float c = 2.f * lg / ae2;
+      r.gA[0] = c * e0; r.gA[1] = c * e1;
+      r.gB[0] = 2.f * y[0] * inv; r.gB[1] = 2.f * y[1] * inv;
+    } break;
+    default: break;
+  }
+  return r;
+}
+
+
+// Fixed-order block reduction of the tile partials -> step scalars sc[kScalars] in shared memory (all threads of the
+// block must call this; works for any blockDim.x that is a multiple of 32, up to 1024).  Bit-reproducible.
+//   loss value, masked row count m, HDR filter mean, normalisers cA / cB (training-loop weights of
+//   src/train.py:178-182 folded in), power-of-two gradient scale S = 2^floor(log2(256 / amax)), Adam bias corrections.
+__device__ inline void reduce_step_scalars(const float* part_g, int n_tiles, const LossDesc& loss, int out_f, int bs_k,
+                                           const float* hyper, const int* step, float* scal_global, float* sc) {
+  __shared__ float part[32][6];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, m4 = 0.f, m5 = 0.f;
+  for (int t = tid; t < n_tiles; t += blockDim.x) {
+    const float* q = part_g + static_cast<size_t>(t) * kPartialsPerTile;
+    s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3];
+    m4 = fmaxf(m4, q[4]); m5 = fmaxf(m5, q[5]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off); s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+    m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, off)); m5 = fmaxf(m5, __shfl_xor_sync(0xffffffffu, m5, off));
+  }
+  if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; part[warp][3] = s3; part[warp][4] = m4; part[warp][5] = m5; }
+  __syncthreads();
+  if (tid == 0) {
+    float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      lA += part[w][0]; lB += part[w][1]; fs += part[w][2]; cnt += part[w][3];
+      amA = fmaxf(amA, part[w][4]); amB = fmaxf(amB, part[w][5]);
+    }
+    const float m = fmaxf(cnt, 1.f);
+    const float of = static_cast<float>(out_f);
+    float cA = 0.f, cB = 0.f, lossv = 0.f, fmean = 0.f, reg = 0.f;
+    switch (loss.kind) {
+      case LOSS_L2:   cA = 1.f / (m * of);  lossv = lA * 0.5f / (m * of); break;
+      case LOSS_L1:   cA = 0.5f / (m * of); lossv = lA * 0.5f / (m * of); break;
+      case LOSS_MSLE: cA = 1.f / (m * of);  lossv = lA * 0.5f / (m * of); break;
+      case LOSS_TANH: cA = 2.f / (m * of);  lossv = lA / (m * of); break;
+      case LOSS_LSL:  cA = 1.f / m;         lossv = lA * 0.5f / m; break;
+      case LOSS_HDR:
+        fmean = fs / static_cast<float>(bs_k > 0 ? bs_k : 1);
+        cA = 1.f / m; cB = loss.factor * fmean / m;
+        reg = loss.factor * fmean * lB / m;
+        lossv = lA / m + reg;
+        break;
+      default: cA = 1.f; break;   // external dout: gA holds dL/dz_last already
+    }
+    const float amax = cA * amA + fabsf(cB) * amB;
+    float S = 1.f;
+    if (amax > 0.f && isfinite(amax)) {
+      int e = static_cast<int>(floorf(log2f(256.f / amax)));
+      e = e < -60 ? -60 : (e > 60 ? 60 : e);
+      S = exp2f(static_cast<float>(e));
+    }
+    sc[SC_LOSS] = lossv; sc[SC_SCALE] = S; sc[SC_CA] = cA; sc[SC_CB] = cB; sc[SC_COUNT] = cnt; sc[SC_FMEAN] = fmean;
+    sc[SC_REG] = reg; sc[SC_INV_SCALE] = 1.f / S;
+    sc[SC_STEP_SIZE] = 0.f; sc[SC_BC2_SQRT] = 1.f;
+    if (scal_global) {
+      if (hyper && step) {     // torch.optim.Adam: step_size = lr / (1 - b1^t), denom uses sqrt(1 - b2^t)
+        const double t = static_cast<double>(*step);
+        sc[SC_STEP_SIZE] = static_cast<float>(static_cast<double>(hyper[0]) / (1.0 - pow(static_cast<double>(hyper[1]), t)));
+        sc[SC_BC2_SQRT] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(hyper[2]), t)));
+      }
+      for (int i = 0; i < 10; ++i) scal_global[i] = sc[i];
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace inr

@@ -1,0 +1,98 @@
+// Descriptors of the WIRE (complex Gabor) path.
+//
+// Complex layers run as real block GEMMs: a complex feature vector h (C features, padded to P = 192) is the real
+// row [hr(0..P) | hi(0..P)] (K2 = 2P = 384); z = h W^T + b becomes  a = [hr|hi].[Wr|-Wi]^T,  b = [hr|hi].[Wi|Wr]^T.
+// Forward GEMMs use a 3-pass fp16 split (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation): one fp16 pass
+// misses the 1e-3 per-layer bar because the Gabor wavelet multiplies pre-activation errors by ~(omega + 2 sigma^2|z|)
+// (hard part 1).  dgrad / wgrad run one fp16 pass on loss-scaled gradients.
+//
+// Images (same byte layout as the chain kernels: elem(r,f) at (f/8)*2048 + r*16 + (f%8)*2 per 128-row tile):
+//   H_hi[l], H_lo[l] : fp16 hi / lo parts of the complex input of layer l (l = 1 .. depth+1), 384 features
+//   AB[l]            : fp16 pre-activation (a | b) of layer l (l = 0 .. depth)
+//   dZ[l]            : fp16 S * dL/d(a | b) of layer l
+#pragma once
+#include <cstdint>
+#include "inr_kernels.cuh"
+
+namespace inr {
+
+constexpr int kWP = 192;                 // padded complex width
+constexpr int kW2 = 2 * kWP;             // real block width (K and N of hidden layers)
+constexpr int kWNT = 192;                // accumulator columns per work item: 96 features x (a, b)
+constexpr int kWFeatPerBlock = 96;
+constexpr int kWTileBytes = kTileM * kW2 * 2;         // 98304: one 128-row image of 384 fp16 features
+constexpr int kWStageBBytes = kWNT * kStageK * 2;     // 12288: B stage (192 rows x 32 K)
+constexpr int kWStageABytes = kTileM * kStageK * 2;   // 8192:  A stage (128 rows x 32 K)
+constexpr int kWMaxDepth = 8;
+
+enum LGemmMode { LG_WIRE_FWD = 1, LG_WIRE_DGRAD = 2 };
+
+struct LGemmArgs {
+  const uint8_t* a_hi;      // A images (tile stride kWTileBytes)
+  const uint8_t* a_lo;      // null for 1-pass
+  const uint8_t* b_hi;      // packed B, per N-block: [K/32 stages][192 x 32]
+  const uint8_t* b_lo;
+  int n_tiles, n_nblocks, passes, mode;
+  // ---- epilogue operands
+  const float* bias;        // WIRE_FWD: complex bias, interleaved (re, im), C entries
+  float omega, sigma;       // Gabor constants of the layer whose activation / derivative is evaluated
+  int c_valid;              // real complex width (181)
+  int train;                // WIRE_FWD: also store AB
+  int real_first;           // WIRE_DGRAD: target layer is the real first layer (b == 0, only dza is meaningful)
+  uint8_t* out_hi;          // WIRE_FWD: H_hi / H_lo of the next layer, AB of this layer
+  uint8_t* out_lo;
+  uint8_t* out_ab;
+  const uint8_t* in_y;      // WIRE_DGRAD: H_hi of the layer's input (= y of the target layer), AB of the target layer
+  const uint8_t* in_ab;
+  uint8_t* out_dz;          // WIRE_DGRAD: dZ image of the target layer
+};
+
+struct WireModel {
+  int depth;                // hidden complex layers
+  int c;                    // complex width (181)
+  int in_f, out_f;          // 3, 2
+  float omega_first, omega_hidden, sigma;
+  // float offsets in the flat parameter buffer (reference state_dict order)
+  int omega_off[kWMaxDepth + 1], scale_off[kWMaxDepth + 1];   // frozen scalars
+  int w_off[kWMaxDepth + 2], b_off[kWMaxDepth + 2];            // layer 0 real [c,3]; 1..depth complex [c,c]; depth+1 complex [out,c]
+  int n_params;
+  // packed operand copies (bytes in wpack): forward hi/lo and dgrad per hidden layer
+  uint32_t wf_hi[kWMaxDepth + 1], wf_lo[kWMaxDepth + 1], wd_hi[kWMaxDepth + 1];
+  uint32_t wpack_bytes;
+  // virtual gradient blocks (float offsets inside one split of gpart)
+  int gd_hidden[kWMaxDepth + 1];      // [384][384] + bias [384]
+  int gd_final, gd_first;             // [16][384] + bias[16];  [256][16]
+  int gd_floats;
+};
+
+struct WireWorkspace {
+  uint64_t hhi[kWMaxDepth + 2], hlo[kWMaxDepth + 2], ab[kWMaxDepth + 1], dz[kWMaxDepth + 1];
+  uint64_t dzlast, ximg, outacc, g, part, scal, gpart, total;
+  int n_tiles, n_split;
+};
+
+struct WireAuxArgs {
+  WireModel m;
+  WireWorkspace w;
+  LossDesc loss;
+  const float* params;
+  const float* coords; const float* gt; const uint8_t* mask;
+  float* out;
+  uint8_t* ws;
+  const int* row_offset; int* step_counter;
+  const float* hyper; const int* step;
+  const float* dout;
+  int bs, train, bs_k;
+};
+
+struct WireAdamArgs {
+  WireModel m;
+  int n_split;
+  float* params; float* mom; float* var; float* grads;
+  uint8_t* wpack;
+  const float* gpart; const float* scal; const float* hyper; const int* step;
+  float* loss_out; int* row_offset; int row_advance;
+  int do_adam, scal_has_bc, pack_only;
+};
+
+}  // namespace inr

@@ -1,0 +1,286 @@
+// CUDA-core kernels around the WIRE layer GEMMs (HBM-bound elementwise / small-K work):
+//   wire_first_kernel   : real first layer 3 -> C + Gabor wavelet (reference networks.py:185-204 with is_first), writes the
+//                         hi/lo operand images of hidden layer 1, the (a) image for backward and the coordinate image
+//                         used by the first layer's wgrad
+//   wire_last_kernel    : final complex linear C -> out, real part (networks.py:247-258) + per-row loss pieces
+//   wire_scalars_kernel : step scalars from the tile partials (one block)
+//   wire_blast_kernel   : backward of the final layer + Gabor derivative of the last hidden layer
+#include <cuda_runtime.h>
+#include "inr_ptx.cuh"
+#include "wire.cuh"
+#include "inr_loss.cuh"
+
+namespace inr {
+
+__device__ __forceinline__ void wire_split8(const float (&y)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void wire_unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// ------------------------------------------------------------------------------------------------ first layer
+__global__ void __launch_bounds__(256) wire_first_kernel(const __grid_constant__ WireAuxArgs a) {
+  __shared__ float sW[kWP * 3], sB[kWP];
+  const WireModel& M = a.m;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < kWP * 3; i += 256) sW[i] = (i / 3) < M.c ? a.params[M.w_off[0] + i] : 0.f;
+  for (int i = tid; i < kWP; i += 256) sB[i] = i < M.c ? a.params[M.b_off[0] + i] : 0.f;
+  if (tile == 0 && tid == 0 && a.step_counter) *a.step_counter += 1;
+  __syncthreads();
+  const int row_base = a.row_offset ? *a.row_offset : 0;
+  const float w = M.omega_first, s2 = M.sigma * M.sigma;
+  uint8_t* hhi = a.ws + a.w.hhi[1] + static_cast<size_t>(tile) * kWTileBytes;
+  uint8_t* hlo = a.ws + a.w.hlo[1] + static_cast<size_t>(tile) * kWTileBytes;
+  uint8_t* ab = a.ws + a.w.ab[0] + static_cast<size_t>(tile) * kWTileBytes;
+  for (int idx = tid; idx < kTileM * (kWP / 8); idx += 256) {
+    const int row = idx & (kTileM - 1), kg = idx >> 7;
+    const int grow = tile * kTileM + row;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    if (grow < a.bs) {
+      const float* c = a.coords + (static_cast<size_t>(row_base) + grow) * 3;
+      x0 = c[0]; x1 = c[1]; x2 = c[2];
+    }
+    float za[8], yr[8], yi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int f = kg * 8 + e;
+      const float z = fmaf(x0, sW[3 * f], fmaf(x1, sW[3 * f + 1], fmaf(x2, sW[3 * f + 2], sB[f])));
+      za[e] = z;
+      const float mag = __expf(-s2 * z * z);
+      const bool live = f < M.c;
+      yr[e] = live ? mag * fast_cos(w * z) : 0.f;
+      yi[e] = live ? mag * fast_sin(w * z) : 0.f;
+    }
+    uint4 rh, rl, ih, il;
+    wire_split8(yr, rh, rl);
+    wire_split8(yi, ih, il);
+    const size_t off_r = static_cast<size_t>(kg) * 2048 + row * 16, off_i = static_cast<size_t>(kWP / 8 + kg) * 2048 + row * 16;
+    st_global_v4(hhi + off_r, rh); st_global_v4(hhi + off_i, ih);
+    st_global_v4(hlo + off_r, rl); st_global_v4(hlo + off_i, il);
+    if (a.train) {
+      st_global_v4(ab + off_r, make_uint4(pack_h2(za[0], za[1]), pack_h2(za[2], za[3]), pack_h2(za[4], za[5]), pack_h2(za[6], za[7])));
+      if (kg == 0) {
+        // coordinate image for the first layer's wgrad: [x_hi(3), 1, x_lo(3), 0 | 0 x 8]
+        const float xs[3] = {x0, x1, x2};
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float h = __half2float(__float2half_rn(xs[c]));
+          v[c] = h; v[4 + c] = xs[c] - h;
+        }
+        v[3] = grow < a.bs ? 1.f : 0.f; v[7] = 0.f;
+        uint8_t* xi = a.ws + a.w.ximg + static_cast<size_t>(tile) * kDzLastBytes;
+        st_global_v4(xi + row * 16, make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7])));
+        st_global_v4(xi + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ final layer + loss
+__global__ void __launch_bounds__(128) wire_last_kernel(const __grid_constant__ WireAuxArgs a) {
+  __shared__ float sWr[kMaxOut][kWP], sWi[kMaxOut][kWP];
+  __shared__ float red[4][8];
+  const WireModel& M = a.m;
+  const int tile = blockIdx.x, row = threadIdx.x, lane = row & 31, q = row >> 5;
+  const int L = M.depth + 1;
+  for (int i = row; i < kMaxOut * kWP; i += 128) {
+    const int o = i / kWP, j = i % kWP;
+    const bool ok = o < M.out_f && j < M.c;
+    sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
+    sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
+  }
+  __syncthreads();
+  const int row_base = a.row_offset ? *a.row_offset : 0;
+  const int grow = tile * kTileM + row;
+  const bool valid = grow < a.bs;
+  const size_t srow = static_cast<size_t>(row_base) + grow;
+  const uint8_t* hhi = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
+  const uint8_t* hlo = a.ws + a.w.hlo[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
+  float acc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+  for (int kg = 0; kg < kWP / 8; ++kg) {
+    float rh[8], rl[8], ih[8], il[8];
+    wire_unpack8(ld_global_nc_v4(hhi + static_cast<size_t>(kg) * 2048), rh);
+    wire_unpack8(ld_global_nc_v4(hlo + static_cast<size_t>(kg) * 2048), rl);
+    wire_unpack8(ld_global_nc_v4(hhi + static_cast<size_t>(kWP / 8 + kg) * 2048), ih);
+    wire_unpack8(ld_global_nc_v4(hlo + static_cast<size_t>(kWP / 8 + kg) * 2048), il);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float hr = rh[e] + rl[e], hi = ih[e] + il[e];
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o)
+        if (o < M.out_f) acc[o] = fmaf(hr, sWr[o][kg * 8 + e], fmaf(-hi, sWi[o][kg * 8 + e], acc[o]));
+    }
+  }
+  float y[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, t[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o)
+    if (o < M.out_f) y[o] = acc[o] + a.params[M.b_off[L] + 2 * o];      // real part of the complex bias
+  if (valid && a.out)
+    for (int o = 0; o < M.out_f; ++o) a.out[static_cast<size_t>(grow) * M.out_f + o] = y[o];
+  if (!a.train) return;
+  float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
+  float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid && a.gt && a.loss.kind != LOSS_NONE) {
+    const bool in_loss = a.mask ? (a.mask[srow] != 0) : true;
+    if (a.loss.kind == LOSS_HDR) {
+      const float kx = a.coords[srow * 3 + 1], ky = a.coords[srow * 3 + 2];
+      const float f = expf(-(kx * kx + ky * ky) / (2.f * a.loss.sigma * a.loss.sigma));
+      fs = (1.f - f) * (1.f - f);
+    }
+    if (in_loss) {
+      for (int o = 0; o < M.out_f; ++o) t[o] = a.gt[srow * M.out_f + o];
+      RowLoss r = loss_row(a.loss, M.out_f, y, t);
+      lA = r.lossA; lB = r.lossB; cnt = 1.f;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) { amA = fmaxf(amA, fabsf(r.gA[o])); amB = fmaxf(amB, fabsf(r.gB[o])); }
+      gq = make_float4(r.gA[0], r.gA[1], r.gB[0], r.gB[1]);
+    }
+  }
+  float* gdst = reinterpret_cast<float*>(a.ws + a.w.g) + (static_cast<size_t>(tile) * kTileM + row) * 4;
+  *reinterpret_cast<float4*>(gdst) = gq;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lA += __shfl_xor_sync(0xffffffffu, lA, off); lB += __shfl_xor_sync(0xffffffffu, lB, off);
+    fs += __shfl_xor_sync(0xffffffffu, fs, off); cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    amA = fmaxf(amA, __shfl_xor_sync(0xffffffffu, amA, off)); amB = fmaxf(amB, __shfl_xor_sync(0xffffffffu, amB, off));
+  }
+  if (lane == 0) { red[q][0] = lA; red[q][1] = lB; red[q][2] = fs; red[q][3] = cnt; red[q][4] = amA; red[q][5] = amB; }
+  __syncthreads();
+  if (row == 0) {
+    float* pdst = reinterpret_cast<float*>(a.ws + a.w.part) + static_cast<size_t>(tile) * kPartialsPerTile;
+    pdst[0] = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+    pdst[1] = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+    pdst[2] = (red[0][2] + red[1][2]) + (red[2][2] + red[3][2]);
+    pdst[3] = (red[0][3] + red[1][3]) + (red[2][3] + red[3][3]);
+    pdst[4] = fmaxf(fmaxf(red[0][4], red[1][4]), fmaxf(red[2][4], red[3][4]));
+    pdst[5] = fmaxf(fmaxf(red[0][5], red[1][5]), fmaxf(red[2][5], red[3][5]));
+    pdst[6] = 0.f; pdst[7] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ step scalars
+__global__ void __launch_bounds__(256) wire_scalars_kernel(const __grid_constant__ WireAuxArgs a) {
+  __shared__ float sc[kScalars];
+  reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step,
+                      reinterpret_cast<float*>(a.ws + a.w.scal), sc);
+}
+
+// amax partials for an externally supplied dL/dout (autograd path)
+__global__ void __launch_bounds__(128) wire_dout_amax_kernel(const float* dout, int bs, int out_f, float* partials) {
+  __shared__ float red[4];
+  const int tile = blockIdx.x, row = tile * kTileM + threadIdx.x;
+  float am = 0.f;
+  if (row < bs)
+    for (int o = 0; o < out_f; ++o) am = fmaxf(am, fabsf(dout[static_cast<size_t>(row) * out_f + o]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = am;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* p = partials + static_cast<size_t>(tile) * kPartialsPerTile;
+    for (int i = 0; i < 8; ++i) p[i] = 0.f;
+    p[4] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward of the final layer
+__global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__ WireAuxArgs a) {
+  __shared__ float sWr[kMaxOut][kWP], sWi[kMaxOut][kWP];
+  const WireModel& M = a.m;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int L = M.depth + 1;
+  for (int i = tid; i < kMaxOut * kWP; i += 256) {
+    const int o = i / kWP, j = i % kWP;
+    const bool ok = o < M.out_f && j < M.c;
+    sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
+    sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
+  }
+  __syncthreads();
+  const float* sc = reinterpret_cast<const float*>(a.ws + a.w.scal);
+  const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
+  const float w = M.depth >= 1 ? M.omega_hidden : M.omega_first, s2 = M.sigma * M.sigma;
+  const uint8_t* yimg = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes;
+  const uint8_t* abimg = a.ws + a.w.ab[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
+  uint8_t* dzimg = a.ws + a.w.dz[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
+  for (int idx = tid; idx < kTileM * (kWP / 8); idx += 256) {
+    const int row = idx & (kTileM - 1), kg = idx >> 7;
+    const int grow = tile * kTileM + row;
+    float dz[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+    if (grow < a.bs) {
+      if (a.dout) {
+        for (int o = 0; o < M.out_f; ++o) dz[o] = S * a.dout[static_cast<size_t>(grow) * M.out_f + o];
+      } else {
+        const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.g) +
+                                                           (static_cast<size_t>(tile) * kTileM + row) * 4);
+        dz[0] = S * (cA * g.x + cB * g.z);
+        dz[1] = S * (cA * g.y + cB * g.w);
+      }
+    }
+    if (kg == 0) {
+      uint8_t* zl = a.ws + a.w.dzlast + static_cast<size_t>(tile) * kDzLastBytes;
+      st_global_v4(zl + row * 16, make_uint4(pack_h2(dz[0], dz[1]), pack_h2(dz[2], dz[3]), 0u, 0u));
+      st_global_v4(zl + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
+    }
+    const size_t off_r = static_cast<size_t>(kg) * 2048 + row * 16, off_i = static_cast<size_t>(kWP / 8 + kg) * 2048 + row * 16;
+    float yr[8], yi[8], za[8], zb[8], da[8], db[8];
+    wire_unpack8(ld_global_nc_v4(yimg + off_r), yr);
+    wire_unpack8(ld_global_nc_v4(yimg + off_i), yi);
+    wire_unpack8(ld_global_nc_v4(abimg + off_r), za);
+    if (M.depth >= 1) wire_unpack8(ld_global_nc_v4(abimg + off_i), zb);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) zb[e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = kg * 8 + e;
+      float gr = 0.f, gi = 0.f;     // dL/d Re(h_j), dL/d Im(h_j) for out = Re(h W^T + b)
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o)
+        if (o < M.out_f) { gr = fmaf(dz[o], sWr[o][j], gr); gi = fmaf(-dz[o], sWi[o][j], gi); }
+      const float P = gr * yr[e] + gi * yi[e];
+      const float Q = gr * yi[e] - gi * yr[e];
+      da[e] = -2.f * s2 * za[e] * P - w * Q;
+      db[e] = M.depth >= 1 ? -(w + 2.f * s2 * zb[e]) * P : 0.f;
+    }
+    st_global_v4(dzimg + off_r, make_uint4(pack_h2(da[0], da[1]), pack_h2(da[2], da[3]), pack_h2(da[4], da[5]), pack_h2(da[6], da[7])));
+    st_global_v4(dzimg + off_i, make_uint4(pack_h2(db[0], db[1]), pack_h2(db[2], db[3]), pack_h2(db[4], db[5]), pack_h2(db[6], db[7])));
+  }
+}
+
+cudaError_t launch_wire_first(const WireAuxArgs& a, cudaStream_t st) {
+  wire_first_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_wire_last(const WireAuxArgs& a, cudaStream_t st) {
+  wire_last_kernel<<<a.w.n_tiles, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_wire_scalars(const WireAuxArgs& a, cudaStream_t st) {
+  wire_scalars_kernel<<<1, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_wire_dout_amax(const WireAuxArgs& a, cudaStream_t st) {
+  wire_dout_amax_kernel<<<a.w.n_tiles, 128, 0, st>>>(a.dout, a.bs, a.m.out_f, reinterpret_cast<float*>(a.ws + a.w.part));
+  return cudaGetLastError();
+}
+cudaError_t launch_wire_blast(const WireAuxArgs& a, cudaStream_t st) {
+  wire_blast_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace inr

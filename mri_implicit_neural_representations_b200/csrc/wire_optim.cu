@@ -1,0 +1,165 @@
+// WIRE optimiser / packer: one thread per real parameter component of the flat buffer (complex tensors are interleaved
+// (re, im) pairs updated as independent reals, exactly what torch.optim.Adam does through view_as_real).
+//   gradient gather from the split-K "virtual" blocks D = dZ^T [hr|hi] (see wire.cuh):
+//     dL/dWr[o,i] = D[o,i] + D[P+o,P+i]       dL/dWi[o,i] = D[P+o,i] - D[o,P+i]          (P = 192)
+//     final layer (out = Re(h W^T + b)):  dL/dWr[o,j] = DT[o,j],  dL/dWi[o,j] = -DT[o,P+j],  dL/d Im(b) = 0
+//     first layer (real):  dL/dW[o,c] = D0[o,c] + D0[o,4+c] (hi + lo coordinate columns),  dL/db[o] = D0[o,3]
+//   then torch-semantics Adam and re-packing of the fp16 hi/lo block operands of the hidden layers:
+//     forward  rows  a_j = [Wr_j | -Wi_j],  b_j = [Wi_j | Wr_j]            (N-blocks of 96 features: a-rows then b-rows)
+//     dgrad    rows  dhr_i = [Wr_:i | Wi_:i],  dhi_i = [-Wi_:i | Wr_:i]
+// Frozen parameters (omega_0, scale_0; reference networks.py:191-192) are never touched.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include "wire.cuh"
+
+namespace inr {
+
+// byte offset of element (n, k) inside one N-block image [12 stages][192 x 32]
+__device__ __forceinline__ uint32_t wblk_off(int n, int k) {
+  const int s = k >> 5, kk = k & 31;
+  return static_cast<uint32_t>(s) * kWStageBBytes + (kk >> 3) * (kWNT * 16) + n * 16 + (kk & 7) * 2;
+}
+constexpr uint32_t kWBlockBytes = (kW2 / kStageK) * kWStageBBytes;   // 147456 per N-block
+
+__device__ __forceinline__ void put_hi_lo(uint8_t* hi, uint8_t* lo, uint32_t off, float v) {
+  const __half h = __float2half_rn(v);
+  *reinterpret_cast<__half*>(hi + off) = h;
+  if (lo) *reinterpret_cast<__half*>(lo + off) = __float2half_rn(v - __half2float(h));
+}
+
+__device__ void wire_pack_hidden(const WireModel& M, uint8_t* wpack, int l, int o, int i, int comp, float v) {
+  uint8_t* fh = wpack + M.wf_hi[l];
+  uint8_t* fl = wpack + M.wf_lo[l];
+  uint8_t* dh = wpack + M.wd_hi[l];
+  const int nbo = o / kWFeatPerBlock, no = o % kWFeatPerBlock;     // forward: N over output features
+  const int nbi = i / kWFeatPerBlock, ni = i % kWFeatPerBlock;     // dgrad:   N over input features
+  if (comp == 0) {   // Wr
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(no, i), v);
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(kWFeatPerBlock + no, kWP + i), v);
+    put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(ni, o), v);
+    put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(kWFeatPerBlock + ni, kWP + o), v);
+  } else {           // Wi
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(no, kWP + i), -v);
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(kWFeatPerBlock + no, i), v);
+    put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(ni, kWP + o), v);
+    put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(kWFeatPerBlock + ni, o), -v);
+  }
+}
+
+__global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ WireAdamArgs a) {
+  __shared__ float s_c[4];
+  const WireModel& M = a.m;
+  if (threadIdx.x == 0) {
+    const float* sc = a.scal;
+    s_c[2] = sc ? sc[SC_INV_SCALE] : 1.f;
+    if (a.do_adam && a.scal_has_bc && sc) {
+      s_c[0] = sc[SC_STEP_SIZE]; s_c[1] = sc[SC_BC2_SQRT];
+    } else if (a.do_adam) {
+      const double t = static_cast<double>(*a.step);
+      s_c[0] = static_cast<float>(static_cast<double>(a.hyper[0]) / (1.0 - pow(static_cast<double>(a.hyper[1]), t)));
+      s_c[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.hyper[2]), t)));
+    }
+    if (blockIdx.x == 0 && !a.pack_only) {
+      if (a.loss_out && sc) *a.loss_out = sc[SC_LOSS];
+      if (a.row_offset) *a.row_offset += a.row_advance;
+    }
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_params) return;
+  // ---- locate the tensor
+  int layer = -1, kind = -1, idx = 0;     // kind: 0 weight, 1 bias, 2 frozen
+  const int L = M.depth + 1;
+  for (int l = 0; l <= L; ++l) {
+    const int wn = (l == 0) ? M.c * M.in_f : (l == L ? M.out_f * M.c * 2 : M.c * M.c * 2);
+    const int bn = (l == 0) ? M.c : (l == L ? M.out_f * 2 : M.c * 2);
+    if (l < L && (p == M.omega_off[l] || p == M.scale_off[l])) { layer = l; kind = 2; break; }
+    if (p >= M.w_off[l] && p < M.w_off[l] + wn) { layer = l; kind = 0; idx = p - M.w_off[l]; break; }
+    if (p >= M.b_off[l] && p < M.b_off[l] + bn) { layer = l; kind = 1; idx = p - M.b_off[l]; break; }
+  }
+  if (kind == 2 || kind < 0) { if (a.grads && !a.pack_only) a.grads[p] = 0.f; return; }
+  float w = a.params[p];
+  int o = 0, i = 0, comp = 0;
+  if (layer >= 1 && layer < L && kind == 0) { const int e = idx >> 1; comp = idx & 1; o = e / M.c; i = e % M.c; }
+  if (!a.pack_only) {
+    // ---- gradient gather (fixed split order)
+    float g = 0.f;
+    for (int s = 0; s < a.n_split; ++s) {
+      const float* G = a.gpart + static_cast<size_t>(s) * M.gd_floats;
+      if (layer == 0) {
+        const float* D0 = G + M.gd_first;
+        if (kind == 0) { const int oo = idx / M.in_f, cc = idx % M.in_f; g += D0[oo * 16 + cc] + D0[oo * 16 + 4 + cc]; }
+        else g += D0[idx * 16 + 3];
+      } else if (layer < L) {
+        const float* D = G + M.gd_hidden[layer];
+        if (kind == 0) {
+          g += comp == 0 ? D[o * kW2 + i] + D[(kWP + o) * kW2 + kWP + i] : D[(kWP + o) * kW2 + i] - D[o * kW2 + kWP + i];
+        } else {
+          const int oo = idx >> 1;
+          g += D[kW2 * kW2 + ((idx & 1) ? kWP + oo : oo)];
+        }
+      } else {
+        const float* DT = G + M.gd_final;
+        if (kind == 0) {
+          const int e = idx >> 1, oo = e / M.c, j = e % M.c;
+          g += (idx & 1) ? -DT[oo * kW2 + kWP + j] : DT[oo * kW2 + j];
+        } else {
+          g += (idx & 1) ? 0.f : DT[16 * kW2 + (idx >> 1)];
+        }
+      }
+    }
+    g *= s_c[2];
+    if (a.grads) a.grads[p] = g;
+    if (!a.do_adam) return;
+    const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
+    if (wd != 0.f) g = fmaf(wd, w, g);
+    const float m = b1 * a.mom[p] + (1.f - b1) * g;
+    const float v = b2 * a.var[p] + (1.f - b2) * g * g;
+    a.mom[p] = m; a.var[p] = v;
+    w = w - s_c[0] * (m / (sqrtf(v) / s_c[1] + eps));
+    a.params[p] = w;
+  }
+  if (layer >= 1 && layer < L && kind == 0) wire_pack_hidden(M, a.wpack, layer, o, i, comp, w);
+}
+
+// Adam on externally reduced gradients (data-parallel path): gpart = plain flat gradients in parameter order.
+__global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_constant__ WireAdamArgs a) {
+  __shared__ float s_c[2];
+  const WireModel& M = a.m;
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(*a.step);
+    s_c[0] = static_cast<float>(static_cast<double>(a.hyper[0]) / (1.0 - pow(static_cast<double>(a.hyper[1]), t)));
+    s_c[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.hyper[2]), t)));
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_params) return;
+  const int L = M.depth + 1;
+  int layer = -1, idx = 0;
+  bool frozen = false;
+  for (int l = 0; l <= L; ++l) {
+    if (l < L && (p == M.omega_off[l] || p == M.scale_off[l])) { frozen = true; break; }
+    if (l >= 1 && l < L && p >= M.w_off[l] && p < M.w_off[l] + M.c * M.c * 2) { layer = l; idx = p - M.w_off[l]; break; }
+  }
+  if (frozen) return;
+  float g = a.gpart[p], w = a.params[p];
+  const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
+  if (wd != 0.f) g = fmaf(wd, w, g);
+  const float m = b1 * a.mom[p] + (1.f - b1) * g;
+  const float v = b2 * a.var[p] + (1.f - b2) * g * g;
+  a.mom[p] = m; a.var[p] = v;
+  w = w - s_c[0] * (m / (sqrtf(v) / s_c[1] + eps));
+  a.params[p] = w;
+  if (layer >= 1) { const int e = idx >> 1; wire_pack_hidden(M, a.wpack, layer, e / M.c, e % M.c, idx & 1, w); }
+}
+
+cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st) {
+  wire_adam_kernel<<<(a.m.n_params + 255) / 256, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_wire_adam_flat(const WireAdamArgs& a, cudaStream_t st) {
+  wire_adam_flat_kernel<<<(a.m.n_params + 255) / 256, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace inr

@@ -33,7 +33,9 @@ class Plan:
         enc = encoder or {"embedding": "none"}
         if model not in L.MODEL:
             raise NotImplementedError(model)                      # src/train.py:69-70
-        if model == "FFN":
+        if model == "WIRE":
+            last = "linear"                                        # output = real part of the final complex linear
+        elif model == "FFN":
             last = "sigmoid"                                       # src/models/networks.py:63
         elif net.get("last_tanh", False):
             last = "tanh"                                          # src/models/networks.py:94-95
@@ -46,7 +48,9 @@ class Plan:
             raise L.InrError(f"encoder '{kind}' is not built into the fused kernels")
         self.desc = L.ModelDesc(L.MODEL[model], int(net["network_input_size"]), int(net["network_output_size"]),
                                 int(net["network_depth"]), int(net["network_width"]), L.LAST[last],
-                                L.ENC[kind], int(enc.get("embedding_size", 0)) if kind == "gauss" else 0, 30.0)
+                                L.ENC[kind], int(enc.get("embedding_size", 0)) if kind == "gauss" else 0,
+                                float(net.get("first_omega_0", 30.0)) if model == "WIRE" else 30.0,
+                                float(net.get("hidden_omega_0", 30.0)), float(net.get("scale", 10.0)))
         self.model, self.net, self.encoder = model, dict(net), dict(enc)
         h = C.c_void_p()
         L.check(L.lib.inr_plan_create(C.byref(self.desc), C.byref(h)), "inr_plan_create")
@@ -56,11 +60,12 @@ class Plan:
         self.n_params = n.value
         nt = C.c_int32()
         L.check(L.lib.inr_plan_tensor_count(h, C.byref(nt)), "inr_plan_tensor_count")
-        self.tensors = []
+        self.tensors, self.tensor_flags = [], []
         for i in range(nt.value):
             ti = L.TensorInfo()
             L.check(L.lib.inr_plan_tensor(h, i, C.byref(ti)), "inr_plan_tensor")
             self.tensors.append((ti.offset, ti.rows, ti.cols, ti.layer, bool(ti.is_bias)))
+            self.tensor_flags.append((bool(ti.is_complex), bool(ti.frozen)))
         b = C.c_size_t()
         L.check(L.lib.inr_wpack_bytes(h, C.byref(b)), "inr_wpack_bytes")
         self.wpack_bytes = b.value
@@ -117,20 +122,22 @@ class ChainEngine:
         self._graphs = {}
 
     # ---- parameters -------------------------------------------------------------------------------
-    def param_views(self):
-        """Views into the flat buffer, one per reference tensor, in state_dict order."""
+    def _views(self, flat):
         out = []
-        for off, rows, cols, layer, is_bias in self.plan.tensors:
-            v = self.params[off:off + rows * cols]
-            out.append(v if is_bias else v.view(rows, cols))
+        for (off, rows, cols, layer, is_bias), (is_complex, frozen) in zip(self.plan.tensors, self.plan.tensor_flags):
+            if is_complex:      # interleaved (re, im) pairs == torch complex64 storage
+                v = torch.view_as_complex(flat[off:off + rows * cols * 2].view(rows * cols, 2))
+            else:
+                v = flat[off:off + rows * cols]
+            out.append(v if (is_bias or (rows == 1 and cols == 1)) else v.view(rows, cols))
         return out
 
+    def param_views(self):
+        """Views into the flat buffer, one per reference tensor, in state_dict order."""
+        return self._views(self.params)
+
     def grad_views(self):
-        out = []
-        for off, rows, cols, layer, is_bias in self.plan.tensors:
-            v = self.grads[off:off + rows * cols]
-            out.append(v if is_bias else v.view(rows, cols))
-        return out
+        return self._views(self.grads)
 
     def load_tensors(self, tensors):
         """Copy a list of tensors (reference state_dict values, same order) into the flat buffer and repack."""
@@ -138,7 +145,7 @@ class ChainEngine:
         assert len(tensors) == len(views), (len(tensors), len(views))
         with torch.no_grad():
             for v, t in zip(views, tensors):
-                v.copy_(t.to(self.device, torch.float32).reshape(v.shape))
+                v.copy_(t.to(self.device, v.dtype).reshape(v.shape))
         self.pack()
 
     def set_encoder(self, B: Optional[torch.Tensor]):
@@ -155,7 +162,7 @@ class ChainEngine:
         bs = inp.shape[0]
         assert bs <= self.max_batch
         inp = inp.to(self.device, torch.float32).contiguous()
-        out = torch.empty(bs, self.plan.desc.out_features, dtype=torch.float32, device=self.device)
+        out = torch.zeros(bs, self.plan.desc.out_features, dtype=torch.float32, device=self.device)
         L.check(L.lib.inr_forward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(inp), _ptr(self.encB), bs,
                                   _ptr(self.workspace), _ptr(out), 1 if train else 0, _stream()), "inr_forward")
         return out
@@ -233,6 +240,28 @@ class ChainEngine:
                                     _ptr(self.workspace), _ptr(out), _ptr(self.grads), _ptr(self.loss_out), _stream()),
                 "inr_grad_step")
         return self.grads
+
+    def read_wire_image(self, kind: str, layer: int, bs: int) -> torch.Tensor:
+        """WIRE only (tests / debugging): decode a 384-feature image family to a complex [rows_pad, 192] matrix.
+        kind: 'h' (hi + lo parts of the complex input of `layer`), 'ab' (pre-activation a + jb of `layer`),
+        'dz' (S * dL/d(a + jb) of `layer`)."""
+        lay = self.plan.workspace_layout(bs)
+        T = lay["n_tiles"]
+        nbytes = T * 128 * 384 * 2
+
+        def dec(off):
+            img = self.workspace[off:off + nbytes].view(torch.float16).view(T, 48, 128, 8)
+            return img.permute(0, 2, 1, 3).reshape(T * 128, 384).float()
+
+        if kind == "h":
+            hi = dec(lay["h"][layer])
+            lo = dec(lay["h"][layer] + nbytes)          # H_lo[l] is laid out right after H_hi[l]
+            m = hi + lo
+        elif kind == "ab":
+            m = dec(lay["d"][layer])
+        else:
+            m = dec(lay["dz"][layer])
+        return torch.complex(m[:, :192], m[:, 192:])
 
     def scalars(self, bs: int) -> torch.Tensor:
         off = self.plan.scalars_offset(bs)
