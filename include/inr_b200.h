@@ -83,7 +83,7 @@ typedef struct inr_tensor_info {
 #define INR_HYPER_FLOATS 8
 /* step scalars the backward pass leaves at the head of the workspace scalar block, readable with
  * inr_scalars_offset(): loss, grad scale S, cA, cB, masked row count, HDR filter mean, HDR reg term, 1/S */
-#define INR_SCALAR_FLOATS 16
+#define INR_SCALAR_FLOATS 64
 
 typedef struct inr_plan inr_plan;
 

@@ -423,6 +423,7 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
     g.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c;
     g.real_first = (l - 1 == 0) ? 1 : 0;
     g.in_y = W + w.hhi[l]; g.in_ab = W + w.ab[l - 1]; g.out_dz = W + w.dz[l - 1];
+    g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = l; g.dst_layer = l - 1;
     e = launch_lgemm(g, p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(dgrad)");
   }

@@ -23,7 +23,7 @@ constexpr int kMaxOut = 4;
 constexpr int kDzLastCols = 16;      // last-layer dZ image is padded to one UMMA N=16
 constexpr int kDzLastBytes = kTileM * kDzLastCols * 2;  // 4096
 constexpr int kPartialsPerTile = 8;  // lossA, lossB, fsum, count, amaxA, amaxB, -, -
-constexpr int kScalars = 16;
+constexpr int kScalars = 64;          // step scalars + per-layer gradient scales + amax accumulators (WIRE)
 
 enum Act { ACT_SIN = 0, ACT_RELU = 1 };
 enum LastAct { LAST_LINEAR = 0, LAST_TANH = 1, LAST_SIGMOID = 2 };
@@ -31,7 +31,9 @@ enum InputKind { INPUT_GAUSS = 0, INPUT_DENSE = 1 };
 enum LossKind { LOSS_NONE = 0, LOSS_L2 = 1, LOSS_L1 = 2, LOSS_MSLE = 3, LOSS_TANH = 4, LOSS_LSL = 5, LOSS_HDR = 6 };
 // scalar slots written by the backward prologue (device memory, fp32)
 enum Scalar { SC_LOSS = 0, SC_SCALE = 1, SC_CA = 2, SC_CB = 3, SC_COUNT = 4, SC_FMEAN = 5, SC_REG = 6, SC_INV_SCALE = 7,
-              SC_STEP_SIZE = 8, SC_BC2_SQRT = 9 };   // Adam bias corrections, computed once per step (fp64) by the backward prologue
+              SC_STEP_SIZE = 8, SC_BC2_SQRT = 9,
+              SC_LAYER_SCALE = 16,   // [16 .. 16+depth]: power-of-two scale of the dZ image of layer l (WIRE)
+              SC_LAYER_AMAX = 40 };  // [40 .. 40+depth]: amax (float bits, atomicMax) of the scaled dZ of layer l, this step   // Adam bias corrections, computed once per step (fp64) by the backward prologue
 
 struct ChainModel {
   int n_gemm;        // tensor-core layers (reference depth - 1)

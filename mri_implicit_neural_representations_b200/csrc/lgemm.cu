@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     const int q = warp & 3, sub = (warp - 4) >> 2, row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
     const float w = a.omega, s2 = a.sigma * a.sigma;
+    // per-layer power-of-two gradient scales: WIRE's gradient norm grows ~10x per layer towards the input, one global
+    // loss scale would saturate the fp16 dZ images of the lower layers
+    float ratio = 1.f, amax = 0.f;
+    if (a.mode == LG_WIRE_DGRAD) ratio = a.scal[SC_LAYER_SCALE + a.dst_layer] / a.scal[SC_LAYER_SCALE + a.src_layer];
     uint32_t n_done = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
       const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
@@ -178,8 +182,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           for (int e = 0; e < 8; ++e) {
             const float P = va[e] * yr[e] + vb[e] * yi[e];
             const float Q = va[e] * yi[e] - vb[e] * yr[e];
-            da[e] = -2.f * s2 * za[e] * P - w * Q;
-            db[e] = a.real_first ? 0.f : -(w + 2.f * s2 * zb[e]) * P;
+            da[e] = ratio * (-2.f * s2 * za[e] * P - w * Q);
+            db[e] = a.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * P);
+            amax = fmaxf(amax, fmaxf(fabsf(da[e]), fabsf(db[e])));
           }
           st_global_v4(a.out_dz + off_r, make_uint4(pack_h2(da[0], da[1]), pack_h2(da[2], da[3]), pack_h2(da[4], da[5]), pack_h2(da[6], da[7])));
           st_global_v4(a.out_dz + off_i, make_uint4(pack_h2(db[0], db[1]), pack_h2(db[2], db[3]), pack_h2(db[4], db[5]), pack_h2(db[6], db[7])));
@@ -187,6 +192,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
+    }
+    if (a.mode == LG_WIRE_DGRAD) {      // amax of the stored (scaled) values -> next step's scale; order-independent
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+      if (lane == 0 && amax > 0.f && isfinite(amax))
+        atomicMax(reinterpret_cast<unsigned int*>(const_cast<float*>(a.scal)) + SC_LAYER_AMAX + a.dst_layer, __float_as_uint(amax));
     }
   }
   tc_fence_before();

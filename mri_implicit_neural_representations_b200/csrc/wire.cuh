@@ -45,6 +45,8 @@ struct LGemmArgs {
   const uint8_t* in_y;      // WIRE_DGRAD: H_hi of the layer's input (= y of the target layer), AB of the target layer
   const uint8_t* in_ab;
   uint8_t* out_dz;          // WIRE_DGRAD: dZ image of the target layer
+  const float* scal;        // WIRE_DGRAD: step scalars (per-layer scales at SC_LAYER_SCALE, amax at SC_LAYER_AMAX)
+  int src_layer, dst_layer; // WIRE_DGRAD: A holds S[src] * dZ_src, the epilogue stores S[dst] * dZ_dst
 };
 
 struct WireModel {

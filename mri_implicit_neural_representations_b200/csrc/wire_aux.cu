@@ -175,8 +175,29 @@ __global__ void __launch_bounds__(128) wire_last_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------ step scalars
 __global__ void __launch_bounds__(256) wire_scalars_kernel(const __grid_constant__ WireAuxArgs a) {
   __shared__ float sc[kScalars];
-  reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step,
-                      reinterpret_cast<float*>(a.ws + a.w.scal), sc);
+  float* g = reinterpret_cast<float*>(a.ws + a.w.scal);
+  reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step, g, sc);
+  if (threadIdx.x == 0) {
+    // per-layer dZ scales for this step from the previous step's amax (lagged dynamic scaling, 2^10 headroom below
+    // the fp16 maximum); uncalibrated layers start 16x below the layer above (gradients grow ~10x per layer downwards)
+    unsigned int* am = reinterpret_cast<unsigned int*>(g) + SC_LAYER_AMAX;
+    float above = sc[SC_SCALE];
+    for (int l = a.m.depth; l >= 0; --l) {
+      const float old = g[SC_LAYER_SCALE + l];
+      const float seen = __uint_as_float(am[l]);
+      float S;
+      if (old > 0.f && seen > 0.f && isfinite(seen) && isfinite(old)) {
+        int e = static_cast<int>(floorf(log2f(64.f * old / seen)));
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        S = exp2f(static_cast<float>(e));
+      } else {
+        S = above * 0.0625f;
+      }
+      g[SC_LAYER_SCALE + l] = S;
+      am[l] = 0u;
+      above = S;
+    }
+  }
 }
 
 // amax partials for an externally supplied dL/dout (autograd path)
@@ -212,6 +233,8 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
   __syncthreads();
   const float* sc = reinterpret_cast<const float*>(a.ws + a.w.scal);
   const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
+  const float ratio = sc[SC_LAYER_SCALE + M.depth] / S;      // dz_last carries S, the stored dZ of the last hidden layer S[depth]
+  float amax = 0.f;
   const float w = M.depth >= 1 ? M.omega_hidden : M.omega_first, s2 = M.sigma * M.sigma;
   const uint8_t* yimg = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes;
   const uint8_t* abimg = a.ws + a.w.ab[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
@@ -254,12 +277,17 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
         if (o < M.out_f) { gr = fmaf(dz[o], sWr[o][j], gr); gi = fmaf(-dz[o], sWi[o][j], gi); }
       const float P = gr * yr[e] + gi * yi[e];
       const float Q = gr * yi[e] - gi * yr[e];
-      da[e] = -2.f * s2 * za[e] * P - w * Q;
-      db[e] = M.depth >= 1 ? -(w + 2.f * s2 * zb[e]) * P : 0.f;
+      da[e] = ratio * (-2.f * s2 * za[e] * P - w * Q);
+      db[e] = M.depth >= 1 ? ratio * (-(w + 2.f * s2 * zb[e]) * P) : 0.f;
+      amax = fmaxf(amax, fmaxf(fabsf(da[e]), fabsf(db[e])));
     }
     st_global_v4(dzimg + off_r, make_uint4(pack_h2(da[0], da[1]), pack_h2(da[2], da[3]), pack_h2(da[4], da[5]), pack_h2(da[6], da[7])));
     st_global_v4(dzimg + off_i, make_uint4(pack_h2(db[0], db[1]), pack_h2(db[2], db[3]), pack_h2(db[4], db[5]), pack_h2(db[6], db[7])));
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  if ((tid & 31) == 0 && amax > 0.f && isfinite(amax))
+    atomicMax(reinterpret_cast<unsigned int*>(a.ws + a.w.scal) + SC_LAYER_AMAX + M.depth, __float_as_uint(amax));
 }
 
 cudaError_t launch_wire_first(const WireAuxArgs& a, cudaStream_t st) {

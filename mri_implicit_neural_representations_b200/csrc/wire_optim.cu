@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
   int o = 0, i = 0, comp = 0;
   if (layer >= 1 && layer < L && kind == 0) { const int e = idx >> 1; comp = idx & 1; o = e / M.c; i = e % M.c; }
   if (!a.pack_only) {
-    // ---- gradient gather (fixed split order)
+    // ---- gradient gather (fixed split order); every layer's block carries that layer's own dZ scale
+    float inv_scale = s_c[2];
+    if (a.scal && layer < L) inv_scale = 1.f / a.scal[SC_LAYER_SCALE + layer];
     float g = 0.f;
     for (int s = 0; s < a.n_split; ++s) {
       const float* G = a.gpart + static_cast<size_t>(s) * M.gd_floats;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
         }
       }
     }
-    g *= s_c[2];
+    g *= inv_scale;
     if (a.grads) a.grads[p] = g;
     if (!a.do_adam) return;
     const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];

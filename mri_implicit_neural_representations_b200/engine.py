@@ -265,4 +265,4 @@ class ChainEngine:
 
     def scalars(self, bs: int) -> torch.Tensor:
         off = self.plan.scalars_offset(bs)
-        return self.workspace[off:off + 64].view(torch.float32).clone()
+        return self.workspace[off:off + 256].view(torch.float32).clone()

@@ -58,6 +58,23 @@ def main():
     g = eng.grad_step(loss_kind, cd, gd, bs, mask=md, loss_opts=opts, out=out_dev)
     torch.cuda.synchronize()
     print("loss engine", float(eng.loss_out), "fp64", float(val), "scalars", eng.scalars(bs)[:8].tolist())
+    scal = eng.scalars(bs)
+    Sl = scal[16:16 + depth + 1].tolist()
+    print("per-layer scales", Sl)
+    # teacher-forced backward per layer: dZ_{l-1} recomputed in fp64 from the engine's own dZ_l, h_l and (a,b)_{l-1}
+    for l in range(depth, 0, -1):
+        dz_l = eng.read_wire_image("dz", l, bs)[:bs, :C].cpu().to(torch.complex128) / Sl[l]
+        dh = dz_l @ sd64[f"net.{l}.linear.weight"].conj()
+        y = eng.read_wire_image("h", l, bs)[:bs, :C].cpu().to(torch.complex128)
+        ab = eng.read_wire_image("ab", l - 1, bs)[:bs, :C].cpu().to(torch.complex128)
+        w_, s2 = float(sd[f"net.{l-1}.omega_0"]), float(sd[f"net.{l-1}.scale_0"]) ** 2
+        Pq = dh.conj() * y
+        P, Q = Pq.real, Pq.imag
+        da = -2 * s2 * ab.real * P - w_ * Q
+        db = -(w_ + 2 * s2 * ab.imag) * P if l - 1 > 0 else torch.zeros_like(da)
+        ref = torch.complex(da, db)
+        got = eng.read_wire_image("dz", l - 1, bs)[:bs, :C].cpu().to(torch.complex128) / Sl[l - 1]
+        print(f"    teacher-forced dZ{l-1} from dZ{l}: {rel(got, ref):.3e}  (amax scaled {float(torch.view_as_real(got).abs().max() * Sl[l-1]):.3e})")
     gv = dict(zip(sd.keys(), eng._views(eng.grads)))
     for k in live:
         print(f"grad {k}: rel err {rel(gv[k], gr64[k]):.3e} (norm {float(torch.view_as_real(gr64[k]).norm() if gr64[k].is_complex() else gr64[k].norm()):.3e})")
