@@ -22,15 +22,24 @@ if ROOT not in sys.path:
 
 import torch
 
-# BASELINE.json configs[0]: SIREN depth 4 width 256, gauss-512 encoding, image space, L2, batch 10000
 WORKLOADS = {
+    # BASELINE.json configs[1] (the configuration the metric is quoted on): WIRE complex Gabor depth 4 width 256
+    # (-> 181 complex), k-space fit, HDR loss, batch 25000, undersampling grid-2*1 (every other row enters the loss)
+    "wire_kspace_hdr_bs25000": dict(
+        model="WIRE", loss="HDR", loss_opts={"hdr_eps": 1e-2, "hdr_ff_sigma": 1.0, "hdr_ff_factor": 0.5}, batch=25000,
+        image_space=False, normalization="max", undersampling="grid-2*1",
+        net={"network_input_size": 3, "network_output_size": 2, "network_depth": 4, "network_width": 256,
+             "first_omega_0": 30, "hidden_omega_0": 30, "scale": 15},
+        encoder={"embedding": "none", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
+        flop_per_coord=3155916, fwd_flop_per_coord=4 * 181 * 181 * 8, issued_fwd_flop_per_coord=4 * 3 * 2 * 384 * 384),
+    # BASELINE.json configs[0]: SIREN depth 4 width 256, gauss-512 encoding, image space, L2, batch 10000
     "siren_image_l2_bs10000": dict(
-        model="SIREN", loss="L2", loss_opts=None, batch=10000, image_space=True,
+        model="SIREN", loss="L2", loss_opts=None, batch=10000, image_space=True, normalization="max", undersampling=None,
         net={"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256},
         encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
         flop_per_coord=1313792, fwd_flop_per_coord=525312),
 }
-DEFAULT_WORKLOAD = "siren_image_l2_bs10000"
+DEFAULT_WORKLOAD = "wire_kspace_hdr_bs25000"
 SLICE = (15, 320, 320)                 # fastMRI-knee-shaped: 15 coils x 320 x 320 after the reference's crop
 LR = 5e-4
 
@@ -96,7 +105,10 @@ def build_engine(wl, device, seed):
     from mri_implicit_neural_representations_b200 import init as pinit
     torch.manual_seed(seed)
     encB = pinit.encoder_matrix(wl["encoder"])
-    tensors = [t for _, t in pinit.chain_tensors(wl["model"], wl["net"])]
+    if wl["model"] == "WIRE":
+        tensors = [t for _, t in pinit.wire_tensors(wl["net"])]
+    else:
+        tensors = [t for _, t in pinit.chain_tensors(wl["model"], wl["net"])]
     plan = inr.Plan(wl["model"], wl["net"], wl["encoder"])
     eng = inr.ChainEngine(plan, max_batch=wl["batch"], device=device, lr=LR)
     eng.load_tensors(tensors)
@@ -111,11 +123,20 @@ def resident_arrays(wl, device, seed, min_bytes):
     coords, gt = [], []
     n = 0
     while n * 20 < min_bytes:
-        c, g, _ = synthetic.make_fit_arrays(seed + len(coords), C, H, W, image_space=wl["image_space"])
+        c, g, _ = synthetic.make_fit_arrays(seed + len(coords), C, H, W, image_space=wl["image_space"],
+                                            normalization=wl["normalization"])
         coords.append(c)
         gt.append(g)
         n += c.shape[0]
-    return torch.cat(coords).to(device), torch.cat(gt).to(device)
+    coords, gt = torch.cat(coords), torch.cat(gt)
+    mask = None
+    if wl["undersampling"]:          # grid-x*y: rows ::x, columns ::y are sampled (reference undersampler.py:79-91)
+        gx, gy = (int(v) for v in wl["undersampling"].split("-")[1].split("*"))
+        m = torch.zeros(H, W, dtype=torch.bool)
+        m[::gx, ::gy] = True
+        mask = m[None].expand(C, H, W).reshape(-1).repeat(coords.shape[0] // (C * H * W))
+        gt = gt * mask[:, None]      # unsampled k-space points are zero-filled (undersampler.py:59-61)
+    return coords.to(device), gt.to(device), (None if mask is None else mask.to(torch.uint8).to(device))
 
 
 def cpu_port_steps(wl, n_steps, warmup, rows_per_step, seed=1234):
@@ -127,21 +148,30 @@ def cpu_port_steps(wl, n_steps, warmup, rows_per_step, seed=1234):
     encB = O.encoder_init(wl["encoder"])
     sd = O.MODEL_INIT[wl["model"]](dict(wl["net"]))
     C, H, W = SLICE
-    coords, gt, _ = synthetic.make_fit_arrays(seed, C, H, W, image_space=wl["image_space"])
+    coords, gt, _ = synthetic.make_fit_arrays(seed, C, H, W, image_space=wl["image_space"], normalization=wl["normalization"])
+    mask = None
+    if wl["undersampling"]:
+        gx, gy = (int(v) for v in wl["undersampling"].split("-")[1].split("*"))
+        m = torch.zeros(H, W, dtype=torch.bool)
+        m[::gx, ::gy] = True
+        mask = m[None].expand(C, H, W).reshape(-1)
+        gt = gt * mask[:, None]
     need = (n_steps + warmup) * rows_per_step
     reps = (need + coords.shape[0] - 1) // coords.shape[0]
     if reps > 1:
         coords, gt = coords.repeat(reps, 1), gt.repeat(reps, 1)
+        mask = None if mask is None else mask.repeat(reps)
     opts = None
     if wl["loss_opts"]:
         opts = {"sigma": wl["loss_opts"]["hdr_ff_sigma"], "eps": wl["loss_opts"]["hdr_eps"],
                 "factor": wl["loss_opts"]["hdr_ff_factor"]}
     if warmup:
         O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords, gt, warmup, rows_per_step, LR,
-                      wl["loss"], opts)
+                      wl["loss"], opts, mask=mask)
+    o = warmup * rows_per_step
     t0 = time.perf_counter()
-    O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords[warmup * rows_per_step:],
-                  gt[warmup * rows_per_step:], n_steps, rows_per_step, LR, wl["loss"], opts)
+    O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords[o:], gt[o:], n_steps, rows_per_step, LR,
+                  wl["loss"], opts, mask=None if mask is None else mask[o:])
     dt = time.perf_counter() - t0
     return n_steps * rows_per_step / dt, dt
 
@@ -152,10 +182,12 @@ def run_reference(args, wl, name):
         return
     bs = wl["batch"]
     # bound the run: probe one step, shrink the per-step sample if K steps would take > ~150 s
-    v1, dt1 = cpu_port_steps(wl, 1, 1, bs)
+    probe = min(bs, 2048)
+    v1, dt1 = cpu_port_steps(wl, 1, 1, probe)
+    est = dt1 * bs / probe                       # HDR / complex GEMMs scale ~linearly in the batch
     rows = bs
-    if dt1 * args.steps > 150.0:
-        rows = max(256, int(bs * 150.0 / (dt1 * args.steps)) // 128 * 128)
+    if est * (args.steps + args.warmup) > 150.0:
+        rows = max(256, int(bs * 150.0 / (est * (args.steps + args.warmup))) // 128 * 128)
     value, dt = cpu_port_steps(wl, args.steps, args.warmup, rows)
     cores = os.cpu_count() or 1
     sample = f"{args.steps} steps x {rows} coords of the {bs}-coord batch workload, torch CPU fp32, {torch.get_num_threads()} threads"
@@ -204,17 +236,18 @@ def main():
     # (SURVEY 8e-2).  independent: one fit per rank, no data-path collective.
     dp = world > 1 and args.parallel == "dp"
     eng, tensors, encB = build_engine(wl, device, seed=1234 if dp else 1234 + rank)
-    coords, gt = resident_arrays(wl, device, 1234 + 100 * rank, min_bytes=200 << 20)
+    coords, gt, mask = resident_arrays(wl, device, 1234 + 100 * rank, min_bytes=200 << 20)
     n_rows = coords.shape[0]
+    wire = wl["model"] == "WIRE"
     steps_per_pass = n_rows // bs
 
     def one_step():
         if dp:      # forward+loss+backward -> all-reduce(mean) of the flat fp32 gradients -> Adam (+ fp16 re-pack)
-            eng.grad_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+            eng.grad_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True)
             allreduce_mean_(eng.grads)
             eng.adam_step()
         else:
-            eng.train_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], use_cursor=True)
+            eng.train_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True)
 
     # eager warm-up (also sets kernel attributes outside capture), then capture one step in a CUDA graph
     for _ in range(3):
@@ -279,28 +312,34 @@ def main():
 
     # ---- per-kernel device times (CUDA events between the four kernels of a step, same stream)
     reset_cursor()
-    prof = eng.profile_step(wl["loss"], coords, gt, bs, loss_opts=wl["loss_opts"], reps=200)
-    kern_ms = prof["forward"]
-    fwd_tflops = wl["fwd_flop_per_coord"] * bs / (kern_ms * 1e-3) / 1e12
+    prof = eng.profile_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], reps=100)
+    wire = wl["model"] == "WIRE"
+    kern_ms = prof["forward_layer_gemms"] / wl["net"]["network_depth"] if wire else prof["forward"]
+    kern_flop = (wl["fwd_flop_per_coord"] / wl["net"]["network_depth"] if wire else wl["fwd_flop_per_coord"]) * bs
+    fwd_tflops = kern_flop / (kern_ms * 1e-3) / 1e12
     step_tflops = wl["flop_per_coord"] * bs / (ms / args.steps * 1e-3) / 1e12
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + step + D2H of the loss every step
     h_coords = coords[: bs * 64].cpu().pin_memory()
     h_gt = gt[: bs * 64].cpu().pin_memory()
+    h_mask = None if mask is None else mask[: bs * 64].cpu().pin_memory()
     d_c = torch.empty(bs, 3, device=device)
     d_g = torch.empty(bs, 2, device=device)
+    d_m = None if mask is None else torch.empty(bs, dtype=torch.uint8, device=device)
     h_loss = torch.empty(1).pin_memory()
 
     def e2e_step(i):
         j = (i % 64) * bs
         d_c.copy_(h_coords[j:j + bs], non_blocking=True)
         d_g.copy_(h_gt[j:j + bs], non_blocking=True)
+        if d_m is not None:
+            d_m.copy_(h_mask[j:j + bs], non_blocking=True)
         if dp:
-            eng.grad_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
+            eng.grad_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"])
             allreduce_mean_(eng.grads)
             eng.adam_step()
         else:
-            eng.train_step(wl["loss"], d_c, d_g, bs, loss_opts=wl["loss_opts"])
+            eng.train_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"])
         h_loss.copy_(eng.loss_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(h_loss)
@@ -356,15 +395,20 @@ def main():
                                     if dp else f"independent fit per GPU x{world}, no collective")),
                    "launch": graph_mode,
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
-                   "step": "CUDA graph of 4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",
+                   "step": ("14 kernels: first layer, 4 layer GEMMs (3-pass split fp16 + complex Gabor epilogue), final layer + HDR loss, "
+                            "scalars, final-layer backward, 4 dgrad layer GEMMs, split-K wgrad, complex Adam + repack") if wire else
+                           "4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",
+                   "loss": wl["loss"], "undersampling": wl["undersampling"],
                    "loss_last_step": loss_dev},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": bs * 20, "d2h_bytes_per_step": 4,
+        "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": bs * (21 if mask is not None else 20), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / n_e2e, "api": "ChainEngine.train_step (C ABI inr_train_step), pinned host batches"},
-        "gpu_launches": (5 if dp else 4) * args.steps,
+        "gpu_launches": ((15 if dp else 14) if wire else (5 if dp else 4)) * args.steps,
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"], "traffic": None,
-                     "kernel": "chain_fwd_kernel<SIN>", "kernel_ms": kern_ms,
+                     "kernel": "lgemm_kernel (WIRE forward layer GEMM + Gabor epilogue; one of 4 launches/step)" if wire else "chain_fwd_kernel<SIN>",
+                     "kernel_ms": kern_ms,
+                     "issued_tflops": (wl["issued_fwd_flop_per_coord"] / wl["net"]["network_depth"] * bs / (kern_ms * 1e-3) / 1e12) if wire else None,
                      "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['source']})",
                      "step_tflops": step_tflops, "step_frac_of_sustained": step_tflops / peaks["tflops_sustained"],
                      "kernels_ms": prof},

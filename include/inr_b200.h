@@ -149,7 +149,8 @@ int inr_grad_step(const inr_plan* plan, const inr_loss_desc* loss, const float* 
                   float* grads, float* loss_out_dev, void* stream);
 
 /* measurement only: runs inr_train_step `reps` times with CUDA events between its four kernels and returns the
- * average duration in ms of {forward, dgrad, wgrad, optimiser} in ms_out4 (host).  Synchronises. */
+ * average duration in ms of {forward, dgrad, wgrad, optimiser, forward layer-GEMM launches (WIRE only)} in
+ * ms_out4, a host array of at least 5 floats.  WIRE reports backward (dgrad + wgrad) in the third slot.  Synchronises. */
 int inr_profile_step(const inr_plan* plan, const inr_loss_desc* loss, float* params, float* exp_avg,
                      float* exp_avg_sq, void* wpack, const float* hyper_dev, int32_t* step_dev,
                      const float* coords, const float* input_x, const float* encB, const float* gt,

@@ -379,7 +379,7 @@ static void wire_aux_fill(const inr_plan* p, const WireWorkspace& w, WireAuxArgs
 
 static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
                              const float* coords, const float* gt, const uint8_t* mask, int64_t bs, void* ws, float* out, int train,
-                             const int* row_off, int* step, cudaStream_t st) {
+                             const int* row_off, int* step, cudaStream_t st, cudaEvent_t* gemm_ev = nullptr) {
   const WireModel& M = p->wm;
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
@@ -388,6 +388,7 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
   x.row_offset = row_off; x.step_counter = step;
   cudaError_t e = launch_wire_first(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "wire_first_kernel");
+  if (gemm_ev) cudaEventRecord(gemm_ev[0], st);
   for (int l = 1; l <= M.depth; ++l) {
     LGemmArgs g{};
     g.a_hi = W + w.hhi[l]; g.a_lo = W + w.hlo[l];
@@ -398,6 +399,7 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
     e = launch_lgemm(g, p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(fwd)");
   }
+  if (gemm_ev) cudaEventRecord(gemm_ev[1], st);
   x.step_counter = nullptr;
   e = launch_wire_last(x, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wire_last_kernel");
@@ -576,7 +578,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
     const LossDesc WL{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
     if (ev) cudaEventRecord(ev[0], st);
     int rcw = wire_forward_impl(p, ww, WL, params, wpack, coords, gt, mask, bs, workspace, out, 1, row_cursor_dev,
-                                no_adam ? nullptr : step_dev, st);
+                                no_adam ? nullptr : step_dev, st, ev ? ev + 5 : nullptr);
     if (rcw) return rcw;
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     rcw = wire_backward_impl(p, ww, WL, params, wpack, nullptr, bs, workspace, no_adam ? nullptr : hyper_dev,
@@ -650,9 +652,9 @@ extern "C" int inr_profile_step(const inr_plan* p, const inr_loss_desc* loss, fl
                                 int32_t reps, float* ms_out4, void* stream) {
   if (!ms_out4 || reps <= 0) return fail(INR_EINVAL, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaEvent_t ev[5];
+  cudaEvent_t ev[7];
   for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaEventCreate");
-  double acc[4] = {0, 0, 0, 0};
+  double acc[5] = {0, 0, 0, 0, 0};
   int rc = INR_OK;
   for (int r = 0; r < reps && rc == INR_OK; ++r) {
     rc = train_step_impl(p, loss, params, m, v, wpack, hyper_dev, step_dev, coords, input_x, encB, gt, mask, bs, nullptr,
@@ -661,8 +663,10 @@ extern "C" int inr_profile_step(const inr_plan* p, const inr_loss_desc* loss, fl
     cudaError_t e = cudaEventSynchronize(ev[4]);
     if (e != cudaSuccess) { rc = cuda_fail(e, "profile step"); break; }
     for (int k = 0; k < 4; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); acc[k] += ms; }
+    if (p->is_wire) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[5], ev[6]); acc[4] += ms; }
   }
   for (auto& e : ev) cudaEventDestroy(e);
   for (int k = 0; k < 4; ++k) ms_out4[k] = static_cast<float>(acc[k] / reps);
+  ms_out4[4] = static_cast<float>(acc[4] / reps);      // WIRE: the `depth` forward layer-GEMM launches together
   return rc;
 }

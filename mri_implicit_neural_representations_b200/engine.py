@@ -199,11 +199,13 @@ class ChainEngine:
         o = loss_opts or {}
         ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
                         float(o.get("hdr_ff_factor", 0.0)))
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 8)()
         L.check(L.lib.inr_profile_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg),
                                        _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords),
                                        _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.workspace), reps, ms,
                                        _stream()), "inr_profile_step")
+        if self.plan.model == "WIRE":
+            return {"forward": ms[0], "backward": ms[2], "optimiser": ms[3], "forward_layer_gemms": ms[4]}
         return {"forward": ms[0], "dgrad": ms[1], "wgrad": ms[2], "optimiser": ms[3]}
 
     def read_image(self, kind: str, layer: int, bs: int) -> torch.Tensor:

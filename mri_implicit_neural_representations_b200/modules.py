@@ -54,7 +54,7 @@ class _ChainFn(torch.autograd.Function):
         elif m._last_act == "sigmoid":
             dz = dout * out * (1 - out)
         grads = m._engine_backward(dz.contiguous(), ctx.bs)
-        return (None, None, *[g.clone() for g in grads])
+        return (None, None, *[g.clone() if need else None for g, need in zip(grads, ctx.needs_input_grad[2:])])
 
 
 class FusedChain(nn.Module):
@@ -66,15 +66,16 @@ class FusedChain(nn.Module):
     def __init__(self, params: dict):
         super().__init__()
         self.net = dict(params)
-        named = pinit.chain_tensors(self.MODEL, self.net)       # reference init, reference RNG order
-        n = sum(t.numel() for _, t in named)
+        named = self._init_tensors()                            # reference init, reference RNG order
+        n = sum(t.numel() * (2 if t.is_complex() else 1) for _, t in named)
         flat = torch.empty(n, dtype=torch.float32)
         self._slices = []
         off = 0
         for name, t in named:
-            flat[off:off + t.numel()] = t.reshape(-1)
-            self._slices.append((name, off, tuple(t.shape)))
-            off += t.numel()
+            r = torch.view_as_real(t).reshape(-1) if t.is_complex() else t.reshape(-1)
+            flat[off:off + r.numel()] = r
+            self._slices.append((name, off, tuple(t.shape), t.is_complex()))
+            off += r.numel()
         self._flat = flat
         self._last_act = "sigmoid" if self.MODEL == "FFN" else ("tanh" if self.net.get("last_tanh", False) else "linear")
         self._build_tree()
@@ -84,8 +85,20 @@ class FusedChain(nn.Module):
         self._max_batch = 0
 
     # ---- module tree with the reference's key names -------------------------------------------------
+    def _init_tensors(self):
+        return pinit.chain_tensors(self.MODEL, self.net)
+
     def _views(self, flat):
-        return [flat[off:off + int(torch.tensor(shape).prod())].view(shape) for _, off, shape in self._slices]
+        out = []
+        for _, off, shape, is_complex in self._slices:
+            n = 1
+            for d in shape:
+                n *= d
+            if is_complex:      # interleaved (re, im) float pairs == complex64 storage
+                out.append(torch.view_as_complex(flat[off:off + 2 * n].view(*shape, 2)))
+            else:
+                out.append(flat[off:off + n].view(shape))
+        return out
 
     def _build_tree(self):
         raise NotImplementedError
@@ -93,14 +106,15 @@ class FusedChain(nn.Module):
     def _leaves(self) -> List[_Leaf]:
         raise NotImplementedError
 
+    def _params_in_order(self):
+        """Parameters in flat-buffer (= state_dict) order."""
+        return [p for leaf in self._leaves() for p in (leaf.weight, leaf.bias)]
+
     def _rebind(self, flat: torch.Tensor):
         self._flat = flat
-        views = self._views(flat)
-        for i, leaf in enumerate(self._leaves()):
-            leaf.weight.data = views[2 * i]
-            leaf.bias.data = views[2 * i + 1]
-            leaf.weight.grad = None
-            leaf.bias.grad = None
+        for p, v in zip(self._params_in_order(), self._views(flat)):
+            p.data = v
+            p.grad = None
         self._engines = {}
         self._state = None
 
@@ -133,6 +147,8 @@ class FusedChain(nn.Module):
         eng = self._engines.get(key)
         if eng is None or eng.max_batch < max_batch:
             plan = Plan(self.MODEL, self.net, encoder if key == "gauss" else {"embedding": "none"})
+            if self.MODEL == "WIRE":
+                assert key == "none", "WIRE takes raw coordinates"
             eng = ChainEngine(plan, max_batch=max(max_batch, 128), device=self._flat.device,
                               shared={"params": self._flat, **st})
             eng.packed_epoch = -1
@@ -161,8 +177,7 @@ class FusedChain(nn.Module):
         return self._views(eng.grads)
 
     def forward(self, x):
-        params = [p for leaf in self._leaves() for p in (leaf.weight, leaf.bias)]
-        return _ChainFn.apply(x, self, *params)
+        return _ChainFn.apply(x, self, *self._params_in_order())
 
 
 class SIREN(FusedChain):
@@ -192,6 +207,56 @@ class FFN(FusedChain):
 
     def _leaves(self):
         return [m for m in self.model if isinstance(m, _Leaf)]
+
+
+class _GaborHolder(nn.Module):
+    """One ComplexGaborLayer's parameters under the reference names: omega_0, scale_0 (frozen), linear.{weight,bias}."""
+
+    def __init__(self, omega, scale, weight, bias):
+        super().__init__()
+        self.omega_0 = nn.Parameter(omega, requires_grad=False)
+        self.scale_0 = nn.Parameter(scale, requires_grad=False)
+        self.linear = _Leaf(weight, bias)
+
+
+class WIRE(FusedChain):
+    """reference src/models/networks.py:206-260 -- keys net.<i>.{omega_0,scale_0,linear.weight,linear.bias},
+    net.<depth+1>.{weight,bias}; complex64 hidden / final tensors are views of interleaved (re, im) floats of the flat
+    buffer.  forward(coords [bs,3]) returns the real part of the final complex linear."""
+    MODEL = "WIRE"
+
+    def _init_tensors(self):
+        return pinit.wire_tensors(self.net)
+
+    def _build_tree(self):
+        v = self._views(self._flat)
+        depth = self.net["network_depth"]
+        mods = [_GaborHolder(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) for i in range(depth + 1)]
+        mods.append(_Leaf(v[4 * (depth + 1)], v[4 * (depth + 1) + 1]))
+        self.net_modules = mods
+        self.net_tree = nn.Sequential(*mods)
+
+    def __setattr__(self, name, value):
+        # the reference keeps both the config dict (constructor arg) and the nn.Sequential under the name `net`;
+        # state_dict keys need the Sequential registered as "net"
+        super().__setattr__(name, value)
+
+    def _params_in_order(self):
+        out = []
+        for m in self.net_modules[:-1]:
+            out += [m.omega_0, m.scale_0, m.linear.weight, m.linear.bias]
+        out += [self.net_modules[-1].weight, self.net_modules[-1].bias]
+        return out
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        return type(sd)((k.replace("net_tree.", "net.", 1), v) for k, v in sd.items())
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        renamed = {k.replace("net.", "net_tree.", 1) if k.startswith("net.") else k: v for k, v in state_dict.items()}
+        res = nn.Module.load_state_dict(self, renamed, strict=strict)
+        self._param_epoch += 1
+        return res
 
 
 class Positional_Encoder:

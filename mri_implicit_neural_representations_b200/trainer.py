@@ -87,7 +87,10 @@ class FusedTrainer:
                  use_graph: bool = True):
         if loss not in FUSABLE_LOSSES:
             raise L.InrError(f"loss '{loss}' is not fused; use the unfused model(x)/backward path")
-        if encoder.embedding_type not in ("gauss",):
+        wire = getattr(model, "MODEL", None) == "WIRE"
+        if wire and encoder.embedding_type != "none":
+            raise L.InrError("WIRE is fitted on raw coordinates (encoder.embedding: none)")
+        if not wire and encoder.embedding_type not in ("gauss",):
             raise L.InrError("the fused step needs the gauss encoder (dense inputs go through the unfused path)")
         dev = model._flat.device
         self.model, self.encoder, self.optim = model, encoder, optim
@@ -96,7 +99,8 @@ class FusedTrainer:
         self.gt = gt.to(dev, torch.float32).contiguous()
         self.mask = None if mask is None else mask.to(dev).to(torch.uint8).contiguous()
         self.n = self.coords.shape[0]
-        self.eng = model.engine(encoder.params, self.bs)
+        self._enc_params = None if wire else encoder.params
+        self.eng = model.engine(self._enc_params, self.bs)
         self.eng.set_encoder(encoder.B)
         self.use_graph = use_graph
         self._graphs = {}
@@ -118,7 +122,7 @@ class FusedTrainer:
         bs = min(self.bs, self.n - self.pos)
         self.optim.sync_hyper(self.eng)
         # engines of this module share the parameters: make sure this one's fp16 copies are current
-        self.model.engine(self.encoder.params, self.bs)
+        self.model.engine(self._enc_params, self.bs)
         g = self._graphs.get(bs) if self.use_graph else None
         if g is not None:
             g.replay()
@@ -147,7 +151,7 @@ class FusedTrainer:
         """Full-grid inference (validation, src/train.py:199-220) through the fused forward, chunked."""
         coords = self.coords if coords is None else coords.to(self.coords.device, torch.float32).contiguous()
         chunk = chunk or self.bs
-        eng = self.model.engine(self.encoder.params, chunk)
+        eng = self.model.engine(self._enc_params, chunk)
         eng.set_encoder(self.encoder.B)
         outs = [eng.forward(coords[i:i + chunk], train=False) for i in range(0, coords.shape[0], chunk)]
         return torch.cat(outs)

@@ -588,7 +588,7 @@ def model_forward(kind, sd, x, net, trace=None):
 
 
 def train_steps(kind, net, sd, encB, enc_kind, coords, gt, n_steps, batch, lr,
-                loss="L2", loss_opts=None, betas=(0.9, 0.999)):
+                loss="L2", loss_opts=None, betas=(0.9, 0.999), mask=None):
     """Grid-order mini-batches (shuffle=False, src/models/utils.py:84-90) through
     forward -> loss -> autograd backward -> Adam, exactly the loop body of src/train.py:158-192
     restricted to fused-kernel territory.  Returns (losses, final sd)."""
@@ -608,6 +608,9 @@ def train_steps(kind, net, sd, encB, enc_kind, coords, gt, n_steps, batch, lr,
         c, y = coords[pos:pos + batch], gt[pos:pos + batch]
         pos += batch
         out = model_forward(kind, params, encode(c, encB, enc_kind), net)
+        if mask is not None:                      # src/train.py:172-177
+            mb = mask[pos - batch:pos]
+            out, y = out[mb], y[mb]
         if loss == "HDR":
             val, g, _ = loss_hdr(out.detach(), y, c, **loss_opts)
         elif loss == "LSL":

@@ -7,9 +7,4 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from mri_implicit_neural_representations_b200.modules import FFN, SIREN, Positional_Encoder  # noqa: E402,F401
-
-
-class WIRE:   # src/models/networks.py:206-260
-    def __init__(self, params):
-        raise NotImplementedError("WIRE (complex Gabor) kernels are not built yet in this round")
+from mri_implicit_neural_representations_b200.modules import FFN, SIREN, WIRE, Positional_Encoder  # noqa: E402,F401
