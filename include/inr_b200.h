@@ -34,6 +34,9 @@ extern "C" {
 #define INR_MODEL_SIREN 1    /* src/models/networks.py:99-124 */
 #define INR_MODEL_FFN 2      /* src/models/networks.py:48-69  */
 #define INR_MODEL_WIRE 3     /* src/models/networks.py:160-260 (complex Gabor; in 3, hidden int(width/sqrt 2) complex) */
+#define INR_MODEL_FOURIER 4  /* FourierNet, src/models/mfn.py:61-94 (one head after stage `depth`) */
+#define INR_MODEL_MS_FOURIER 5          /* MultiscaleKFourier, src/models/mfn.py:206-267 (heads at output_layers) */
+#define INR_MODEL_MS_BOUNDED_FOURIER 6  /* MultiscaleBoundedFourier, src/models/mfn.py:288-356 (BoundedLinear row masks) */
 /* encoders (src/models/networks.py:7-35) */
 #define INR_ENC_NONE 0       /* x is the dense [bs, in] fp32 network input */
 #define INR_ENC_GAUSS 1      /* gamma(x) = [sin(2 pi x B^T), cos(2 pi x B^T)] computed in-kernel from coords */
@@ -62,6 +65,8 @@ typedef struct inr_model_desc {
   float w0;                 /* SIREN: 30 (hard-wired in the reference, src/models/networks.py:75); WIRE: first_omega_0 */
   float hidden_omega_0;     /* WIRE: net.hidden_omega_0 */
   float sigma0;             /* WIRE: net.scale */
+  int32_t head_mask;        /* multiscale MFN: bit i set = output_linear[i] is returned (reference output_layers, default [1,3,5,7]) */
+  float bounds[20];         /* MS_BOUNDED_FOURIER: (lo, hi) of BoundedLinear i at [2i], [2i+1] (reference `boundaries`) */
 } inr_model_desc;
 
 typedef struct inr_loss_desc {

@@ -18,7 +18,7 @@ class ModelDesc(C.Structure):
     _fields_ = [("model", C.c_int32), ("in_features", C.c_int32), ("out_features", C.c_int32),
                 ("depth", C.c_int32), ("width", C.c_int32), ("last_act", C.c_int32),
                 ("encoder", C.c_int32), ("enc_size", C.c_int32), ("w0", C.c_float),
-                ("hidden_omega_0", C.c_float), ("sigma0", C.c_float)]
+                ("hidden_omega_0", C.c_float), ("sigma0", C.c_float), ("head_mask", C.c_int32), ("bounds", C.c_float * 20)]
 
 
 class LossDesc(C.Structure):
@@ -30,7 +30,7 @@ class TensorInfo(C.Structure):
                 ("layer", C.c_int32), ("is_bias", C.c_int32), ("is_complex", C.c_int32), ("frozen", C.c_int32)]
 
 
-MODEL = {"SIREN": 1, "FFN": 2, "WIRE": 3}
+MODEL = {"SIREN": 1, "FFN": 2, "WIRE": 3, "Fourier": 4, "MultiscaleFourier": 5, "BoundedFourier": 6}
 ENC = {"none": 0, "gauss": 1}
 LAST = {"linear": 0, "tanh": 1, "sigmoid": 2}
 LOSS = {"none": 0, "L2": 1, "L1": 2, "MSLE": 3, "tanh": 4, "LSL": 5, "HDR": 6}

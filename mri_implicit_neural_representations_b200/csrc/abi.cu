@@ -9,6 +9,7 @@
 #include "../../include/inr_b200.h"
 #include "inr_kernels.cuh"
 #include "wire.cuh"
+#include "mfn.cuh"
 
 namespace inr {
 cudaError_t launch_chain_fwd(const FwdArgs& a, int n_sm, cudaStream_t stream);
@@ -25,6 +26,11 @@ cudaError_t launch_wire_dout_amax(const WireAuxArgs& a, cudaStream_t st);
 cudaError_t launch_wire_blast(const WireAuxArgs& a, cudaStream_t st);
 cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st);
 cudaError_t launch_wire_adam_flat(const WireAdamArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_encode(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_head(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_dout_amax(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_scalars(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_top(const MfnAuxArgs& a, cudaStream_t st);
 }  // namespace inr
 
 using namespace inr;
@@ -33,6 +39,8 @@ struct inr_plan {
   inr_model_desc desc;
   bool is_wire = false;
   WireModel wm;
+  bool is_mfn = false;
+  MfnModel mm;
   ChainModel model;
   std::vector<inr_tensor_info> tensors;
   std::vector<SegDesc> segs;
@@ -54,10 +62,14 @@ extern "C" int inr_debug_set_trace(void* dev_u64_buffer_64) { g_trace = static_c
 
 static int wire_plan_create(const inr_model_desc* d, inr_plan** out);
 static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs);
+static int mfn_plan_create(const inr_model_desc* d, inr_plan** out);
+static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs);
 
 extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (!d || !out) return fail(INR_EINVAL, "null argument");
   if (d->model == INR_MODEL_WIRE) return wire_plan_create(d, out);
+  if (d->model == INR_MODEL_FOURIER || d->model == INR_MODEL_MS_FOURIER || d->model == INR_MODEL_MS_BOUNDED_FOURIER)
+    return mfn_plan_create(d, out);
   if (d->model != INR_MODEL_SIREN && d->model != INR_MODEL_FFN) return fail(INR_EUNSUPPORTED, "model kind not built yet");
   if (d->width != kWidth) return fail(INR_EUNSUPPORTED, "tensor-core chain kernels are built for network_width 256");
   if (d->depth < 2 || d->depth - 1 > kMaxLayers - 1) return fail(INR_EINVAL, "network_depth out of range");
@@ -93,6 +105,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
     SegDesc sw{};
     sw.off = off; sw.rows = rows; sw.cols = cols; sw.layer = l;
     sw.fwd_scale = sw.bwd_scale = (M.act == ACT_SIN) ? M.w0 : 1.f;
+    sw.scale_slot = -1;
     if (l < M.n_gemm) {
       sw.pack_fwd = 1;
       sw.perm_e = (l == 0 && M.input_kind == INPUT_GAUSS) ? M.enc_size : 0;
@@ -104,7 +117,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
     M.b_off[l] = off;
     p->tensors.push_back({off, rows, 1, l, 1, 0, 0});
     SegDesc sb{};
-    sb.off = off; sb.rows = rows; sb.cols = 1; sb.layer = l;
+    sb.off = off; sb.rows = rows; sb.cols = 1; sb.layer = l; sb.scale_slot = -1;
     p->segs.push_back(sb);
     off += rows;
   }
@@ -156,7 +169,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
 extern "C" int inr_plan_destroy(inr_plan* p) { delete p; return INR_OK; }
 extern "C" int inr_plan_param_count(const inr_plan* p, int64_t* n) {
   if (!p || !n) return fail(INR_EINVAL, "null argument");
-  *n = p->is_wire ? p->wm.n_params : p->model.n_params; return INR_OK;
+  *n = p->is_wire ? p->wm.n_params : (p->is_mfn ? p->mm.n_params : p->model.n_params); return INR_OK;
 }
 extern "C" int inr_plan_tensor_count(const inr_plan* p, int32_t* n) {
   if (!p || !n) return fail(INR_EINVAL, "null argument");
@@ -168,7 +181,7 @@ extern "C" int inr_plan_tensor(const inr_plan* p, int32_t i, inr_tensor_info* ou
 }
 extern "C" int inr_wpack_bytes(const inr_plan* p, size_t* b) {
   if (!p || !b) return fail(INR_EINVAL, "null argument");
-  *b = p->is_wire ? p->wm.wpack_bytes : p->model.wpack_bytes; return INR_OK;
+  *b = p->is_wire ? p->wm.wpack_bytes : (p->is_mfn ? p->mm.wpack_bytes : p->model.wpack_bytes); return INR_OK;
 }
 
 static Workspace plan_workspace(const inr_plan* p, int64_t bs) {
@@ -198,11 +211,11 @@ static Workspace plan_workspace(const inr_plan* p, int64_t bs) {
 
 extern "C" int inr_workspace_bytes(const inr_plan* p, int64_t bs, size_t* bytes) {
   if (!p || !bytes || bs <= 0) return fail(INR_EINVAL, "bad argument");
-  *bytes = p->is_wire ? wire_workspace(p, bs).total : plan_workspace(p, bs).total; return INR_OK;
+  *bytes = p->is_wire ? wire_workspace(p, bs).total : (p->is_mfn ? mfn_workspace(p, bs).total : plan_workspace(p, bs).total); return INR_OK;
 }
 extern "C" int inr_scalars_offset(const inr_plan* p, int64_t bs, size_t* off) {
   if (!p || !off || bs <= 0) return fail(INR_EINVAL, "bad argument");
-  *off = p->is_wire ? wire_workspace(p, bs).scal : plan_workspace(p, bs).scal_off; return INR_OK;
+  *off = p->is_wire ? wire_workspace(p, bs).scal : (p->is_mfn ? mfn_workspace(p, bs).scal : plan_workspace(p, bs).scal_off); return INR_OK;
 }
 
 extern "C" int inr_workspace_layout(const inr_plan* p, int64_t bs, uint64_t* out, int32_t n) {
@@ -217,6 +230,15 @@ extern "C" int inr_workspace_layout(const inr_plan* p, int64_t bs, uint64_t* out
     out[41] = static_cast<uint64_t>(w.n_tiles); out[42] = static_cast<uint64_t>(w.n_split); out[43] = w.total;
     return INR_OK;
   }
+  if (p->is_mfn) {     // z images at [l], sin(p) at [12+l], dp at [24+l]
+    const MfnWorkspace w = mfn_workspace(p, bs);
+    for (int l = 0; l < kMaxLayers; ++l) {
+      out[l] = l <= p->mm.top ? w.z[l] : 0; out[12 + l] = l <= p->mm.top ? w.g[l] : 0; out[24 + l] = l <= p->mm.top ? w.dp[l] : 0;
+    }
+    out[36] = w.x; out[37] = w.gl; out[38] = w.part; out[39] = w.scal; out[40] = w.gpart;
+    out[41] = static_cast<uint64_t>(w.n_tiles); out[42] = static_cast<uint64_t>(w.n_split); out[43] = w.total;
+    return INR_OK;
+  }
   const Workspace w = plan_workspace(p, bs);
   for (int l = 0; l < kMaxLayers; ++l) { out[l] = w.h_off[l]; out[12 + l] = w.d_off[l]; out[24 + l] = w.dz_off[l]; }
   out[36] = w.dzlast_off; out[37] = w.g_off; out[38] = w.part_off; out[39] = w.scal_off; out[40] = w.gpart_off;
@@ -228,7 +250,7 @@ static void fill_adam(const inr_plan* p, AdamArgs& a) {
   std::memset(&a, 0, sizeof(a));
   a.n_seg = static_cast<int>(p->segs.size());
   for (int i = 0; i < a.n_seg; ++i) a.seg[i] = p->segs[i];
-  a.n_params = p->model.n_params;
+  a.n_params = p->is_mfn ? p->mm.n_params : p->model.n_params;
 }
 
 static void fill_wgrad(const inr_plan* p, const Workspace& w, uint8_t* ws, WgradArgs& g) {
@@ -391,8 +413,9 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
   if (gemm_ev) cudaEventRecord(gemm_ev[0], st);
   for (int l = 1; l <= M.depth; ++l) {
     LGemmArgs g{};
-    g.a_hi = W + w.hhi[l]; g.a_lo = W + w.hlo[l];
-    g.b_hi = wp + M.wf_hi[l]; g.b_lo = wp + M.wf_lo[l];
+    g.seg[0].a_hi = W + w.hhi[l]; g.seg[0].a_lo = W + w.hlo[l];
+    g.seg[0].b_hi = wp + M.wf_hi[l]; g.seg[0].b_lo = wp + M.wf_lo[l];
+    g.seg[0].a_tile_bytes = kWTileBytes; g.seg[0].k_stages = kW2 / kStageK; g.seg[0].acc_col = 0; g.n_seg = 1; g.nt = kWNT;
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 3; g.mode = LG_WIRE_FWD;
     g.bias = params + M.b_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.train = train;
     g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
@@ -420,7 +443,8 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
   if (e != cudaSuccess) return cuda_fail(e, "wire_blast_kernel");
   for (int l = M.depth; l >= 1; --l) {      // dL/dh_{l-1} = dZ_l * conj-block(W_l), then the Gabor derivative of layer l-1
     LGemmArgs g{};
-    g.a_hi = W + w.dz[l]; g.a_lo = nullptr; g.b_hi = wp + M.wd_hi[l]; g.b_lo = nullptr;
+    g.seg[0].a_hi = W + w.dz[l]; g.seg[0].b_hi = wp + M.wd_hi[l];
+    g.seg[0].a_tile_bytes = kWTileBytes; g.seg[0].k_stages = kW2 / kStageK; g.seg[0].acc_col = 0; g.n_seg = 1; g.nt = kWNT;
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 1; g.mode = LG_WIRE_DGRAD;
     g.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c;
     g.real_first = (l - 1 == 0) ? 1 : 0;
@@ -448,6 +472,234 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
 static void wire_adam_fill(const inr_plan* p, WireAdamArgs& a) {
   std::memset(&a, 0, sizeof(a));
   a.m = p->wm;
+}
+
+// =====================================================================================================================
+// MFN (multiplicative filter network) path: FourierNet, MultiscaleKFourier, MultiscaleBoundedFourier
+// =====================================================================================================================
+static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
+  if (d->model == INR_MODEL_MS_BOUNDED_FOURIER)
+    return fail(INR_EUNSUPPORTED, "MultiscaleBoundedFourier: the dist_to_center input is not plumbed through the C ABI yet");
+  if (d->width % kMfnNT != 0 || d->width > 512 || d->width < 128) return fail(INR_EUNSUPPORTED, "MFN kernels are built for network_width 128..512, multiple of 128");
+  if (d->in_features % 128 != 0 || d->in_features > 1024) return fail(INR_EUNSUPPORTED, "MFN network_input_size must be a multiple of 128");
+  if (d->depth < 1 || d->depth + 1 > kMfnMaxStages) return fail(INR_EINVAL, "network_depth out of range");
+  if (d->out_features < 1 || d->out_features > 2) return fail(INR_EUNSUPPORTED, "network_output_size must be 1 or 2");
+  if (d->encoder == INR_ENC_GAUSS && d->in_features != 2 * d->enc_size) return fail(INR_EINVAL, "gauss encoder needs network_input_size == 2*embedding_size");
+  inr_plan* p = new (std::nothrow) inr_plan();
+  if (!p) return fail(INR_EINVAL, "out of host memory");
+  p->desc = *d;
+  p->is_mfn = true;
+  MfnModel& M = p->mm;
+  std::memset(&M, 0, sizeof(M));
+  const int L = d->depth, W = d->width, IN = d->in_features, OF = d->out_features;
+  M.L = L; M.width = W; M.in_f = IN; M.out_f = OF;
+  M.input_kind = d->encoder == INR_ENC_GAUSS ? INPUT_GAUSS : INPUT_DENSE;
+  M.enc_size = d->enc_size;
+  const bool multi = d->model != INR_MODEL_FOURIER;
+  M.bounded = d->model == INR_MODEL_MS_BOUNDED_FOURIER ? 1 : 0;
+  for (int i = 0; i < kMfnMaxStages; ++i) { M.stage_head[i] = -1; M.bound_lo[i] = 0.f; M.bound_hi[i] = 3.0e38f; }
+  if (multi) {
+    M.n_heads = L + 1;
+    const int mask = d->head_mask ? d->head_mask : 0xAA;      // reference default output_layers = [1,3,5,7]
+    int live = 0;
+    for (int k = 0; k <= L; ++k) {
+      M.head_stage[k] = k;
+      M.head_live[k] = (k >= 1 && ((mask >> k) & 1)) ? 1 : 0;
+      if (M.head_live[k]) { M.stage_head[k] = live++; M.top = k; }
+    }
+    M.n_out = live;
+    if (live == 0) { delete p; return fail(INR_EINVAL, "no output layer selected"); }
+  } else {
+    M.n_heads = 1; M.head_stage[0] = L; M.head_live[0] = 1; M.stage_head[L] = 0; M.top = L; M.n_out = 1;
+  }
+  if (M.bounded)
+    for (int i = 1; i <= L; ++i) { M.bound_lo[i] = d->bounds[2 * (i - 1)]; M.bound_hi[i] = d->bounds[2 * (i - 1) + 1]; }
+  // ---- parameter layout = reference state_dict order: linear.*, output_linear(.*), filters.*
+  int off = 0;
+  uint32_t wo = 0;
+  auto add_seg = [&](int o, int rows, int cols, int stage, bool is_bias, bool dead, int scale_slot, int pf, int pb,
+                     uint32_t wf, uint32_t wd) {
+    p->tensors.push_back({o, rows, cols, stage, is_bias ? 1 : 0, 0, dead ? 1 : 0});
+    SegDesc s{};
+    s.off = o; s.rows = rows; s.cols = cols; s.layer = stage; s.pack_fwd = pf; s.pack_bwd = pb; s.wf_off = wf; s.wd_off = wd;
+    s.fwd_scale = 1.f; s.bwd_scale = 1.f; s.layout = 1; s.nt = kMfnNT; s.scale_slot = scale_slot; s.frozen = dead ? 1 : 0;
+    p->segs.push_back(s);
+  };
+  for (int i = 1; i <= L; ++i) {
+    const bool dead = i > M.top;
+    M.lin_w[i] = off; M.pk_lin[i] = wo; wo += static_cast<uint32_t>(W) * W * 2; M.pk_lin_t[i] = wo; wo += static_cast<uint32_t>(W) * W * 2;
+    add_seg(off, W, W, i, false, dead, SC_LAYER_SCALE + i, 1, 1, M.pk_lin[i], M.pk_lin_t[i]); off += W * W;
+    M.lin_b[i] = off; add_seg(off, W, 1, i, true, dead, SC_LAYER_SCALE + i, 0, 0, 0, 0); off += W;
+  }
+  for (int k = 0; k < M.n_heads; ++k) {
+    const bool dead = !M.head_live[k];
+    M.head_w[k] = off; add_seg(off, OF, W, M.head_stage[k], false, dead, -1, 0, 0, 0, 0); off += OF * W;
+    M.head_b[k] = off; add_seg(off, OF, 1, M.head_stage[k], true, dead, -1, 0, 0, 0, 0); off += OF;
+  }
+  for (int i = 0; i <= L; ++i) {
+    const bool dead = i > M.top;
+    M.filt_w[i] = off; M.pk_filt[i] = wo; wo += static_cast<uint32_t>(W) * IN * 2;
+    add_seg(off, W, IN, i, false, dead, SC_LAYER_SCALE + i, 1, 0, M.pk_filt[i], 0); off += W * IN;
+    M.filt_b[i] = off; add_seg(off, W, 1, i, true, dead, SC_LAYER_SCALE + i, 0, 0, 0, 0); off += W;
+  }
+  M.n_params = off;
+  M.wpack_bytes = wo;
+  // ---- wgrad units
+  const int wc = W / 128, ic = IN / 128;
+  const uint32_t wtile = static_cast<uint32_t>(kTileM) * W * 2, xtile = static_cast<uint32_t>(kTileM) * IN * 2;
+  for (int i = 1; i <= M.top; ++i)          // dW_i = DH[i]^T Z[i-1], db_i = sum DH[i]
+    for (int mc = 0; mc < wc; ++mc)
+      for (int nc = 0; nc < wc; ++nc) {
+        WgradUnit u{};
+        u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+        u.b_tile_stride = wtile; u.b_sub = nc * 32768; u.b_bytes = 32768;
+        u.n = 128; u.out_off = M.lin_w[i]; u.out_ld = W; u.row0 = mc * 128; u.col0 = nc * 128;
+        u.rows_valid = 128; u.cols_valid = 128; u.bias_off = nc == 0 ? M.lin_b[i] : -1;
+        p->units.push_back(u); p->unit_layer.push_back(100 + i);
+      }
+  for (int i = 0; i <= M.top; ++i)          // dOm_i = DP[i]^T X, dphi_i = sum DP[i]
+    for (int mc = 0; mc < wc; ++mc)
+      for (int nc = 0; nc < ic; ++nc) {
+        WgradUnit u{};
+        u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+        u.b_tile_stride = xtile; u.b_sub = nc * 32768; u.b_bytes = 32768;
+        u.n = 128; u.out_off = M.filt_w[i]; u.out_ld = IN; u.row0 = mc * 128; u.col0 = nc * 128;
+        u.rows_valid = 128; u.cols_valid = 128; u.bias_off = nc == 0 ? M.filt_b[i] : -1;
+        p->units.push_back(u); p->unit_layer.push_back(200 + i);
+      }
+  for (int k = 0; k < M.n_heads; ++k) {     // dV_k^T[o][f] = sum_rows dy_k[o] z[f]
+    if (!M.head_live[k]) continue;
+    for (int mc = 0; mc < wc; ++mc) {
+      WgradUnit u{};
+      u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+      u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+      u.n = kDzLastCols; u.transposed = 1; u.out_off = M.head_w[k]; u.out_ld = W; u.row0 = 0; u.col0 = mc * 128;
+      u.rows_valid = OF; u.cols_valid = 128; u.bias_off = mc == 0 ? M.head_b[k] : -1;
+      p->units.push_back(u); p->unit_layer.push_back(300 + k);
+    }
+  }
+  if (static_cast<int>(p->units.size()) > kMaxUnits || static_cast<int>(p->segs.size()) > kMaxSegs) {
+    delete p;
+    return fail(INR_EUNSUPPORTED, "MFN model too large for the static unit / segment tables");
+  }
+  p->n_sm = query_sm_count();
+  *out = p;
+  return INR_OK;
+}
+
+static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs) {
+  const MfnModel& M = p->mm;
+  MfnWorkspace w{};
+  const int T = static_cast<int>((bs + kTileM - 1) / kTileM);
+  w.n_tiles = T;
+  int ns = p->n_sm / static_cast<int>(p->units.size());
+  if (ns < 1) ns = 1;
+  if (ns > T) ns = T > 0 ? T : 1;
+  w.n_split = ns;
+  uint64_t o = 0;
+  w.scal = o; o += align_up(kScalars * 4, 1024);
+  w.part = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
+  w.gl = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
+  const uint64_t wimg = static_cast<uint64_t>(T) * kTileM * M.width * 2, ximg = static_cast<uint64_t>(T) * kTileM * M.in_f * 2;
+  w.x = o; o += ximg;
+  for (int i = 0; i <= M.top; ++i) { w.z[i] = o; o += wimg; w.g[i] = o; o += wimg; w.cp[i] = o; o += wimg; w.dp[i] = o; o += wimg; }
+  for (int i = 1; i <= M.top; ++i) { w.h[i] = o; o += wimg; w.dh[i] = o; o += wimg; }
+  for (int k = 0; k < M.n_out; ++k) { w.dout[k] = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024); }
+  w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * M.n_params * 4, 1024);
+  w.total = o;
+  return w;
+}
+
+static void mfn_aux_fill(const inr_plan* p, const MfnWorkspace& w, MfnAuxArgs& x, const float* params, void* ws, int64_t bs) {
+  std::memset(&x, 0, sizeof(x));
+  x.m = p->mm; x.w = w; x.params = params; x.ws = static_cast<uint8_t*>(ws);
+  x.bs = static_cast<int>(bs); x.bs_k = static_cast<int>(bs);
+  x.loss = LossDesc{LOSS_NONE, 0.f, 0.f, 0.f};
+}
+
+static int mfn_forward_impl(const inr_plan* p, const MfnWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
+                            const float* coords, const float* xin, const float* encB, const float* gt, const uint8_t* mask,
+                            const float* dist, int64_t bs, void* ws, float* out, int train, const int* row_off, int* step,
+                            cudaStream_t st) {
+  const MfnModel& M = p->mm;
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const uint8_t* wp = static_cast<const uint8_t*>(wpack);
+  if (M.bounded && !dist) return fail(INR_EINVAL, "BoundedFourier needs dist_to_center");
+  MfnAuxArgs x; mfn_aux_fill(p, w, x, params, ws, bs);
+  x.loss = loss; x.coords = coords; x.x = xin; x.encB = encB; x.gt = gt; x.mask = mask; x.dist = dist; x.out = out; x.train = train;
+  x.row_offset = row_off; x.step_counter = step;
+  cudaError_t e = launch_mfn_encode(x, st);
+  if (e != cudaSuccess) return cuda_fail(e, "mfn_encode_kernel");
+  const uint32_t wtile = static_cast<uint32_t>(kTileM) * M.width * 2, xtile = static_cast<uint32_t>(kTileM) * M.in_f * 2;
+  for (int i = 0; i <= M.top; ++i) {
+    LGemmArgs g{};
+    g.seg[0].a_hi = W + w.x; g.seg[0].b_hi = wp + M.pk_filt[i]; g.seg[0].a_tile_bytes = xtile; g.seg[0].k_stages = M.in_f / 32; g.seg[0].acc_col = 0;
+    g.n_seg = 1;
+    if (i >= 1) {
+      g.seg[1].a_hi = W + w.z[i - 1]; g.seg[1].b_hi = wp + M.pk_lin[i]; g.seg[1].a_tile_bytes = wtile; g.seg[1].k_stages = M.width / 32;
+      g.seg[1].acc_col = kMfnNT; g.n_seg = 2;
+      g.bias = params + M.lin_b[i];
+    }
+    g.nt = kMfnNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.width / kMfnNT; g.passes = 1; g.mode = LG_MFN_FWD;
+    g.phi = params + M.filt_b[i]; g.train = train;
+    g.out_hi = W + w.z[i]; g.out_lo = W + w.g[i]; g.out_ab = W + w.cp[i]; g.out_h = i >= 1 ? W + w.h[i] : nullptr;
+    g.feat_tile_bytes = wtile; g.bs = static_cast<int>(bs);
+    if (M.bounded && i >= 1) { g.dist = dist; g.bound_lo = M.bound_lo[i]; g.bound_hi = M.bound_hi[i]; }
+    e = launch_lgemm(g, p->n_sm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn fwd)");
+  }
+  x.step_counter = nullptr;
+  e = launch_mfn_head(x, st);
+  return e == cudaSuccess ? INR_OK : cuda_fail(e, "mfn_head_kernel");
+}
+
+static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
+                             const float* dout, const float* dist, int64_t bs, void* ws, const float* hyper, const int* step,
+                             cudaStream_t st) {
+  const MfnModel& M = p->mm;
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const uint8_t* wp = static_cast<const uint8_t*>(wpack);
+  MfnAuxArgs x; mfn_aux_fill(p, w, x, params, ws, bs);
+  x.loss = loss; x.dout = dout; x.dist = dist; x.hyper = hyper; x.step = step;
+  cudaError_t e;
+  if (dout) { e = launch_mfn_dout_amax(x, st); if (e != cudaSuccess) return cuda_fail(e, "mfn_dout_amax_kernel"); }
+  e = launch_mfn_scalars(x, st);
+  if (e != cudaSuccess) return cuda_fail(e, "mfn_scalars_kernel");
+  e = launch_mfn_top(x, st);
+  if (e != cudaSuccess) return cuda_fail(e, "mfn_top_kernel");
+  const uint32_t wtile = static_cast<uint32_t>(kTileM) * M.width * 2;
+  for (int i = M.top; i >= 1; --i) {        // dz_{i-1} = dh_i W_i (+ head gradient of stage i-1), then (dh, dp) of stage i-1
+    LGemmArgs g{};
+    g.seg[0].a_hi = W + w.dh[i]; g.seg[0].b_hi = wp + M.pk_lin_t[i]; g.seg[0].a_tile_bytes = wtile; g.seg[0].k_stages = M.width / 32;
+    g.seg[0].acc_col = 0; g.n_seg = 1;
+    g.nt = kMfnNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.width / kMfnNT; g.passes = 1; g.mode = LG_MFN_DGRAD;
+    g.real_first = (i - 1 == 0) ? 1 : 0;
+    g.in_y = W + w.g[i - 1]; g.in_ab = W + w.cp[i - 1]; g.in_h = i - 1 >= 1 ? W + w.h[i - 1] : nullptr;
+    g.out_dz = i - 1 >= 1 ? W + w.dh[i - 1] : nullptr; g.out_dp = W + w.dp[i - 1];
+    g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = i; g.dst_layer = i - 1;
+    g.feat_tile_bytes = wtile; g.bs = static_cast<int>(bs); g.out_f = M.out_f;
+    if (dout && M.stage_head[i - 1] >= 0) {
+      int kk = -1, seen = 0;
+      for (int k = 0; k < M.n_heads; ++k) if (M.head_live[k]) { if (seen == M.stage_head[i - 1]) { kk = k; break; } ++seen; }
+      g.head_dout = dout; g.head_w = params + M.head_w[kk]; g.head_col = M.stage_head[i - 1] * M.out_f; g.head_ld = M.n_out * M.out_f;
+    }
+    if (M.bounded) { g.dist = dist; g.bound_lo = M.bound_lo[i]; g.bound_hi = M.bound_hi[i]; }
+    e = launch_lgemm(g, p->n_sm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn dgrad)");
+  }
+  WgradArgs wg; std::memset(&wg, 0, sizeof(wg));
+  wg.n_units = static_cast<int>(p->units.size());
+  for (int i = 0; i < wg.n_units; ++i) {
+    WgradUnit u = p->units[i];
+    const int code = p->unit_layer[i];
+    if (code >= 300) { const int k = code - 300; u.a_off = w.z[M.head_stage[k]]; u.b_off = w.dout[M.stage_head[M.head_stage[k]]]; }
+    else if (code >= 200) { u.a_off = w.dp[code - 200]; u.b_off = w.x; }
+    else { const int s = code - 100; u.a_off = w.dh[s]; u.b_off = w.z[s - 1]; }
+    wg.u[i] = u;
+  }
+  wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = M.n_params; wg.ws = W; wg.gpart_off = w.gpart;
+  e = launch_wgrad(wg, st);
+  return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel(mfn)");
 }
 
 extern "C" int inr_pack_weights(const inr_plan* p, const float* params, void* wpack, void* stream) {
@@ -481,6 +733,14 @@ extern "C" int inr_forward(const inr_plan* p, const float* params, const void* w
                            int64_t bs, void* workspace, float* out, int32_t train, void* stream) {
   if (!p || !params || !wpack || !input || !out || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (train && !workspace) return fail(INR_EINVAL, "training forward needs a workspace");
+  if (p->is_mfn) {
+    if (!workspace) return fail(INR_EINVAL, "MFN forward streams its activations through the workspace");
+    const bool mg = p->mm.input_kind == INPUT_GAUSS;
+    if (mg && !encB) return fail(INR_EINVAL, "gauss encoder needs encB");
+    const MfnWorkspace mw = mfn_workspace(p, bs);
+    return mfn_forward_impl(p, mw, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, mg ? input : nullptr, mg ? nullptr : input, encB,
+                            nullptr, nullptr, nullptr, bs, workspace, out, train ? 1 : 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  }
   if (p->is_wire) {
     if (!workspace) return fail(INR_EINVAL, "WIRE forward streams its activations through the workspace");
     const WireWorkspace ww = wire_workspace(p, bs);
@@ -515,6 +775,19 @@ extern "C" int inr_backward(const inr_plan* p, const float* params, const void* 
                             void* workspace, float* grads, void* stream) {
   if (!p || !params || !wpack || !dout || !workspace || !grads || bs <= 0) return fail(INR_EINVAL, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->is_mfn) {
+    const MfnWorkspace mw = mfn_workspace(p, bs);
+    int rcm = mfn_backward_impl(p, mw, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, dout, nullptr, bs, workspace, nullptr, nullptr, st);
+    if (rcm) return rcm;
+    AdamArgs ma; fill_adam(p, ma);
+    ma.n_split = mw.n_split; ma.n_tiles = mw.n_tiles;
+    ma.params = const_cast<float*>(params); ma.grads = grads;
+    ma.gpart = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.gpart);
+    ma.scal = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.scal);
+    ma.do_adam = 0;
+    cudaError_t me = launch_adam(ma, st);
+    return me == cudaSuccess ? INR_OK : cuda_fail(me, "adam_kernel(reduce, mfn)");
+  }
   if (p->is_wire) {
     const WireWorkspace ww = wire_workspace(p, bs);
     int rcw = wire_backward_impl(p, ww, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, dout, bs, workspace, nullptr, nullptr, st);
@@ -568,6 +841,37 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   const bool no_adam = grads_only != nullptr;
   if (!p || !loss || !params || !wpack || !gt || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (!no_adam && (!m || !v || !hyper_dev || !step_dev)) return fail(INR_EINVAL, "bad argument");
+  if (p->is_mfn) {
+    const bool mg = p->mm.input_kind == INPUT_GAUSS;
+    if (mg && (!coords || !encB)) return fail(INR_EINVAL, "gauss encoder needs coords and encB");
+    if (!mg && !input_x) return fail(INR_EINVAL, "dense input needs input_x");
+    if (p->mm.n_out != 1) return fail(INR_EUNSUPPORTED, "multi-head MFN losses run through the autograd face (inr_forward / inr_backward)");
+    if (loss->kind < INR_LOSS_L2 || loss->kind > INR_LOSS_HDR) return fail(INR_EINVAL, "unknown loss kind");
+    if ((loss->kind == INR_LOSS_HDR || loss->kind == INR_LOSS_LSL) && p->mm.out_f != 2)
+      return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
+    const MfnWorkspace mw = mfn_workspace(p, bs);
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    const LossDesc ML{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
+    if (ev) cudaEventRecord(ev[0], st);
+    int rcm = mfn_forward_impl(p, mw, ML, params, wpack, coords, input_x, encB, gt, mask, nullptr, bs, workspace, out, 1,
+                               row_cursor_dev, no_adam ? nullptr : step_dev, st);
+    if (rcm) return rcm;
+    if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
+    rcm = mfn_backward_impl(p, mw, ML, params, wpack, nullptr, nullptr, bs, workspace, no_adam ? nullptr : hyper_dev,
+                            no_adam ? nullptr : step_dev, st);
+    if (rcm) return rcm;
+    if (ev) cudaEventRecord(ev[3], st);
+    AdamArgs ma; fill_adam(p, ma);
+    ma.n_split = mw.n_split; ma.n_tiles = mw.n_tiles;
+    ma.params = params; ma.m = m; ma.v = v; ma.wpack = static_cast<uint8_t*>(wpack);
+    ma.gpart = reinterpret_cast<const float*>(wsb + mw.gpart); ma.scal = reinterpret_cast<const float*>(wsb + mw.scal);
+    ma.hyper = hyper_dev; ma.step = step_dev; ma.loss_out = loss_out_dev;
+    ma.row_offset = row_cursor_dev; ma.row_advance = static_cast<int>(bs);
+    ma.do_adam = no_adam ? 0 : 1; ma.scal_has_bc = no_adam ? 0 : 1; ma.grads = grads_only;
+    cudaError_t me = launch_adam(ma, st);
+    if (ev) { cudaEventRecord(ev[4], st); cudaEventRecord(ev[5], st); cudaEventRecord(ev[6], st); }
+    return me == cudaSuccess ? INR_OK : cuda_fail(me, "adam_kernel(mfn)");
+  }
   if (p->is_wire) {
     if (!coords) return fail(INR_EINVAL, "WIRE needs coords");
     if (loss->kind < INR_LOSS_L2 || loss->kind > INR_LOSS_HDR) return fail(INR_EINVAL, "unknown loss kind");

@@ -119,7 +119,7 @@ struct WgradUnit {
   int perm_e;                   // >0: columns are in sin/cos-interleaved order with E = perm_e
 };
 
-constexpr int kMaxUnits = 64;
+constexpr int kMaxUnits = 320;      // by-value kernel parameter: 320 x 88 B < 32 KB
 struct WgradArgs {
   WgradUnit u[kMaxUnits];
   int n_units, n_split, n_tiles, n_params;
@@ -134,6 +134,10 @@ struct SegDesc {          // one parameter tensor for the optimiser / packer
   int perm_e;             // forward K permutation (gauss input layer)
   uint32_t wf_off, wd_off;
   float fwd_scale, bwd_scale;   // factor folded into the fp16 copies (SIREN: w0, so the accumulators hold w0*z)
+  int layout;             // 0: chain stages (256 rows x 32 K); 1: lgemm N-blocks of `nt` rows x 32 K
+  int nt;
+  int scale_slot;         // >= 0: this tensor's gradient partials carry scal[scale_slot] instead of the global loss scale
+  int frozen;             // no gradient ever reaches this tensor (dead stage / unused head): skipped like grad None in torch
 };
 constexpr int kMaxSegs = 64;
 struct AdamArgs {

@@ -1,26 +1,30 @@
-// Streaming layer GEMM with fused epilogues ("lgemm"): D[128 x 192] = sum_passes A[128 x 384] * B[192 x 384]^T per work
-// item (row tile, N-block), A and B both streamed from HBM operand images through a 5-stage bulk-TMA ring,
-// tcgen05.mma kind::f16 with fp32 accumulation in TMEM, two accumulators ping-ponged between work items so the
-// epilogue of item i overlaps the MMAs of item i+1.  Persistent CTAs (one per SM) walk the items.
+// Streaming layer GEMM with fused epilogues ("lgemm").  A work item is (row tile, N-block); it accumulates one or two
+// GEMM segments  acc[:, col_s : col_s + nt] = sum_passes A_s[128 x K_s] * B_s[nt x K_s]^T  with A and B streamed from
+// HBM operand images through a bulk-TMA ring, tcgen05.mma kind::f16 with fp32 accumulation in TMEM.  Two 256-column
+// accumulators ping-pong between work items so the epilogue of item i overlaps the MMAs of item i+1.  Persistent
+// CTAs (one per SM) walk the items.
 //
 // Epilogues:
 //   LG_WIRE_FWD   : complex Gabor wavelet  y = exp(j w z - |s z|^2),  z = a + jb = acc + bias
-//                   (reference src/models/networks.py:199-204), written as the fp16 hi/lo operand images of the next
-//                   layer plus the fp16 (a|b) image the backward pass needs.  3-pass split GEMM.
+//                   (reference src/models/networks.py:199-204) -> fp16 hi/lo operand images of the next layer plus
+//                   the fp16 (a|b) image the backward pass needs.  3-pass split GEMM, nt = 192 (96 features x (a,b)).
 //   LG_WIRE_DGRAD : dL/d(a,b) of the previous layer from dL/dh = acc:
-//                   P = Re(conj(g) y), Q = Im(conj(g) y);  dza = -2 s^2 a P - w Q;  dzb = -(w + 2 s^2 b) P.  1-pass GEMM.
+//                   P = Re(conj(g) y), Q = Im(conj(g) y);  dza = -2 s^2 a P - w Q;  dzb = -(w + 2 s^2 b) P.  1 pass.
+//   LG_MFN_FWD    : multiplicative filter stage  z_i = sin(x Om_i^T + phi_i) * (z_{i-1} W_i^T + b_i)
+//                   (reference src/models/mfn.py:34-38,57-58; BoundedLinear :281-286 as a row mask on the linear term).
+//                   Two segments (filter GEMM, linear GEMM), nt = 128; stage 0 has the filter segment only.
+//   LG_MFN_DGRAD  : dz_{i-1} = dh_i W_i (+ head gradient), then dh_{i-1} = dz g, dp_{i-1} = dz h cos(p).
 #include <cuda_runtime.h>
 #include "inr_ptx.cuh"
 #include "wire.cuh"
 
 namespace inr {
 
-constexpr int kLgStages = 5;
-constexpr int kLgStageBytes = 2 * kWStageABytes + 2 * kWStageBBytes;   // 40960
+constexpr int kLgMaxSlots = 12;
+constexpr int kLgRingBytes = 5 * 40960;                                // 204800
 constexpr int kLgComputeThreads = 512;
 constexpr int kLgThreads = 128 + kLgComputeThreads;
-constexpr int kLgSmem = kLgStages * kLgStageBytes + 1024;
-constexpr int kLgKStages = kW2 / kStageK;                              // 12
+constexpr int kLgSmem = kLgRingBytes + 1024;
 
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
@@ -34,18 +38,28 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+}
 
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full[kLgStages], empty[kLgStages], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_ba[kWP], s_bb[kWP];
+  __shared__ float s_ba[512], s_bb[512];     // WIRE: bias re / im (192 used);  MFN: b_i / phi_i (width <= 512)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = a.n_tiles * a.n_nblocks;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 64;            // one B stage: nt rows x 32 K x 2 B
+  const uint32_t a_lo_off = kWStageABytes;
+  const uint32_t b_hi_off = a.passes == 3 ? 2 * kWStageABytes : kWStageABytes;
+  const uint32_t b_lo_off = b_hi_off + b_bytes;
+  const uint32_t slot_bytes = a.passes == 3 ? 2 * (kWStageABytes + b_bytes) : (kWStageABytes + b_bytes);
+  int n_slots = kLgRingBytes / slot_bytes;
+  if (n_slots > kLgMaxSlots) n_slots = kLgMaxSlots;
 
   if (tid == 0) {
-    for (int i = 0; i < kLgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kLgMaxSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads); }
     mbar_fence_init();
   }
@@ -54,13 +68,18 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       s_ba[j] = j < a.c_valid ? a.bias[2 * j] : 0.f;
       s_bb[j] = j < a.c_valid ? a.bias[2 * j + 1] : 0.f;
     }
+  } else if (a.mode == LG_MFN_FWD) {
+    const int width = a.n_nblocks * a.nt;
+    for (int j = tid; j < width; j += kLgThreads) {
+      s_ba[j] = a.bias ? a.bias[j] : 0.f;
+      s_bb[j] = a.phi[j];
+    }
   }
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t stage_tx = a.passes == 3 ? kLgStageBytes : (kWStageABytes + kWStageBBytes);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -68,19 +87,21 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       uint32_t it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
-        const size_t a_off = static_cast<size_t>(tile) * kWTileBytes;
-        const size_t b_off = static_cast<size_t>(nb) * (kLgKStages * kWStageBBytes);
-        for (int s = 0; s < kLgKStages; ++s, ++it) {
-          const uint32_t slot = it % kLgStages, ph = (it / kLgStages) & 1;
-          mbar_wait(&empty[slot], ph ^ 1);
-          mbar_arrive_expect_tx(&full[slot], stage_tx);
-          uint8_t* dst = smem + slot * kLgStageBytes;
-          bulk_g2s(dst, a.a_hi + a_off + static_cast<size_t>(s) * kWStageABytes, kWStageABytes, &full[slot]);
-          bulk_g2s(dst + 2 * kWStageABytes, a.b_hi + b_off + static_cast<size_t>(s) * kWStageBBytes, kWStageBBytes, &full[slot]);
-          if (a.passes == 3) {
-            bulk_g2s(dst + kWStageABytes, a.a_lo + a_off + static_cast<size_t>(s) * kWStageABytes, kWStageABytes, &full[slot]);
-            bulk_g2s(dst + 2 * kWStageABytes + kWStageBBytes, a.b_lo + b_off + static_cast<size_t>(s) * kWStageBBytes,
-                     kWStageBBytes, &full[slot]);
+        for (int sg = 0; sg < a.n_seg; ++sg) {
+          const LGemmSeg& S = a.seg[sg];
+          const size_t a_off = static_cast<size_t>(tile) * S.a_tile_bytes;
+          const size_t b_off = static_cast<size_t>(nb) * S.k_stages * b_bytes;
+          for (int s = 0; s < S.k_stages; ++s, ++it) {
+            const uint32_t slot = it % n_slots, ph = (it / n_slots) & 1;
+            mbar_wait(&empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&full[slot], slot_bytes);
+            uint8_t* dst = smem + slot * slot_bytes;
+            bulk_g2s(dst, S.a_hi + a_off + static_cast<size_t>(s) * kWStageABytes, kWStageABytes, &full[slot]);
+            bulk_g2s(dst + b_hi_off, S.b_hi + b_off + static_cast<size_t>(s) * b_bytes, b_bytes, &full[slot]);
+            if (a.passes == 3) {
+              bulk_g2s(dst + a_lo_off, S.a_lo + a_off + static_cast<size_t>(s) * kWStageABytes, kWStageABytes, &full[slot]);
+              bulk_g2s(dst + b_lo_off, S.b_lo + b_off + static_cast<size_t>(s) * b_bytes, b_bytes, &full[slot]);
+            }
           }
         }
       }
@@ -88,33 +109,35 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kTileM, kWNT, false, false);
+      const uint32_t idesc = umma_idesc_f16(kTileM, a.nt, false, false);
+      const uint32_t b_lbo = static_cast<uint32_t>(a.nt) * 16, b_kstep = 2 * b_lbo;
       uint32_t it = 0, n_done = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
         const uint32_t ab = n_done & 1, use = n_done >> 1;
         mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem + ab * 256;
-        for (int s = 0; s < kLgKStages; ++s, ++it) {
-          const uint32_t slot = it % kLgStages;
-          mbar_wait(&full[slot], (it / kLgStages) & 1);
-          tc_fence_after();
-          const uint32_t base = smem_u32(smem + slot * kLgStageBytes);
-          const uint32_t a_hi = base, a_lo = base + kWStageABytes;
-          const uint32_t b_hi = base + 2 * kWStageABytes, b_lo = b_hi + kWStageBBytes;
+        for (int sg = 0; sg < a.n_seg; ++sg) {
+          const LGemmSeg& S = a.seg[sg];
+          const uint32_t acc = tmem + ab * 256 + S.acc_col;
+          for (int s = 0; s < S.k_stages; ++s, ++it) {
+            const uint32_t slot = it % n_slots;
+            mbar_wait(&full[slot], (it / n_slots) & 1);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + slot * slot_bytes);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t dah = umma_smem_desc(a_hi + kk * 4096, 2048, 128);
-            const uint64_t dbh = umma_smem_desc(b_hi + kk * 6144, 3072, 128);
-            umma_f16(acc, dah, dbh, idesc, (s | kk) != 0);
-            if (a.passes == 3) {
-              const uint64_t dal = umma_smem_desc(a_lo + kk * 4096, 2048, 128);
-              const uint64_t dbl = umma_smem_desc(b_lo + kk * 6144, 3072, 128);
-              umma_f16(acc, dal, dbh, idesc, 1);
-              umma_f16(acc, dah, dbl, idesc, 1);
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t dah = umma_smem_desc(base + kk * 4096, 2048, 128);
+              const uint64_t dbh = umma_smem_desc(base + b_hi_off + kk * b_kstep, b_lbo, 128);
+              umma_f16(acc, dah, dbh, idesc, (s | kk) != 0);
+              if (a.passes == 3) {
+                const uint64_t dal = umma_smem_desc(base + a_lo_off + kk * 4096, 2048, 128);
+                const uint64_t dbl = umma_smem_desc(base + b_lo_off + kk * b_kstep, b_lbo, 128);
+                umma_f16(acc, dal, dbh, idesc, 1);
+                umma_f16(acc, dah, dbl, idesc, 1);
+              }
             }
+            umma_commit(&empty[slot]);
           }
-          umma_commit(&empty[slot]);
         }
         umma_commit(&acc_full[ab]);
       }
@@ -124,76 +147,143 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     const int q = warp & 3, sub = (warp - 4) >> 2, row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
     const float w = a.omega, s2 = a.sigma * a.sigma;
-    // per-layer power-of-two gradient scales: WIRE's gradient norm grows ~10x per layer towards the input, one global
-    // loss scale would saturate the fp16 dZ images of the lower layers
-    float ratio = 1.f, amax = 0.f;
-    if (a.mode == LG_WIRE_DGRAD) ratio = a.scal[SC_LAYER_SCALE + a.dst_layer] / a.scal[SC_LAYER_SCALE + a.src_layer];
+    const bool dgrad = a.mode == LG_WIRE_DGRAD || a.mode == LG_MFN_DGRAD;
+    // per-layer power-of-two gradient scales (WIRE's gradient norm grows ~10x per layer towards the input; one global
+    // loss scale would saturate the fp16 images of the lower layers)
+    float ratio = 1.f, amax = 0.f, s_dst = 1.f;
+    if (dgrad) {
+      s_dst = a.scal[SC_LAYER_SCALE + a.dst_layer];
+      ratio = s_dst / a.scal[SC_LAYER_SCALE + a.src_layer];
+    }
     uint32_t n_done = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
       const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
       const uint32_t ab = n_done & 1, use = n_done >> 1;
-      const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16;
       mbar_wait(&acc_full[ab], use & 1);
       tc_fence_after();
+      const uint32_t acc = tmem + t_lane + ab * 256;
+      if (a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD) {
+        const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16;
 #pragma unroll 1
-      for (int i = 0; i < 3; ++i) {
-        const int c0 = 24 * sub + 8 * i;                 // feature inside the N-block
-        const int f0 = kWFeatPerBlock * nb + c0;         // complex feature index (multiple of 8)
-        const size_t off_r = img + static_cast<size_t>(f0 >> 3) * 2048;               // real-part k-group
-        const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;       // imaginary-part k-group
-        float va[8], vb[8];
-        if (a.mode == LG_WIRE_FWD) {
-          tmem_ld8(tmem + t_lane + ab * 256 + c0, va);
-          tmem_ld8(tmem + t_lane + ab * 256 + kWFeatPerBlock + c0, vb);
-          tmem_ld_wait();
-          float yr[8], yi[8];
+        for (int i = 0; i < 3; ++i) {
+          const int c0 = 24 * sub + 8 * i;                 // feature inside the N-block
+          const int f0 = kWFeatPerBlock * nb + c0;         // complex feature index (multiple of 8)
+          const size_t off_r = img + static_cast<size_t>(f0 >> 3) * 2048;               // real-part k-group
+          const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;       // imaginary-part k-group
+          float va[8], vb[8];
+          if (a.mode == LG_WIRE_FWD) {
+            tmem_ld8(acc + c0, va);
+            tmem_ld8(acc + kWFeatPerBlock + c0, vb);
+            tmem_ld_wait();
+            float yr[8], yi[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float za = va[e] + s_ba[f0 + e], zb = vb[e] + s_bb[f0 + e];
-            va[e] = za; vb[e] = zb;
-            const float mag = __expf(-w * zb - s2 * (za * za + zb * zb));
-            const float ang = w * za;
-            const bool live = (f0 + e) < a.c_valid;
-            yr[e] = live ? mag * fast_cos(ang) : 0.f;
-            yi[e] = live ? mag * fast_sin(ang) : 0.f;
-          }
-          uint4 rh, rl, ih, il;
-          split_h2(yr[0], yr[1], rh.x, rl.x); split_h2(yr[2], yr[3], rh.y, rl.y);
-          split_h2(yr[4], yr[5], rh.z, rl.z); split_h2(yr[6], yr[7], rh.w, rl.w);
-          split_h2(yi[0], yi[1], ih.x, il.x); split_h2(yi[2], yi[3], ih.y, il.y);
-          split_h2(yi[4], yi[5], ih.z, il.z); split_h2(yi[6], yi[7], ih.w, il.w);
-          st_global_v4(a.out_hi + off_r, rh); st_global_v4(a.out_hi + off_i, ih);
-          st_global_v4(a.out_lo + off_r, rl); st_global_v4(a.out_lo + off_i, il);
-          if (a.train) {
-            st_global_v4(a.out_ab + off_r, make_uint4(pack_h2(va[0], va[1]), pack_h2(va[2], va[3]), pack_h2(va[4], va[5]), pack_h2(va[6], va[7])));
-            st_global_v4(a.out_ab + off_i, make_uint4(pack_h2(vb[0], vb[1]), pack_h2(vb[2], vb[3]), pack_h2(vb[4], vb[5]), pack_h2(vb[6], vb[7])));
-          }
-        } else {
-          const uint4 yr4 = ld_global_nc_v4(a.in_y + off_r), yi4 = ld_global_nc_v4(a.in_y + off_i);
-          const uint4 a4 = ld_global_nc_v4(a.in_ab + off_r);
-          uint4 b4 = make_uint4(0u, 0u, 0u, 0u);
-          if (!a.real_first) b4 = ld_global_nc_v4(a.in_ab + off_i);
-          tmem_ld8(tmem + t_lane + ab * 256 + c0, va);                       // dL/d Re(h)
-          tmem_ld8(tmem + t_lane + ab * 256 + kWFeatPerBlock + c0, vb);      // dL/d Im(h)
-          tmem_ld_wait();
-          float yr[8], yi[8], za[8], zb[8], da[8], db[8];
-          unpack8(yr4, yr); unpack8(yi4, yi); unpack8(a4, za); unpack8(b4, zb);
+            for (int e = 0; e < 8; ++e) {
+              const float za = va[e] + s_ba[f0 + e], zb = vb[e] + s_bb[f0 + e];
+              va[e] = za; vb[e] = zb;
+              const float mag = __expf(-w * zb - s2 * (za * za + zb * zb));
+              const float ang = w * za;
+              const bool live = (f0 + e) < a.c_valid;
+              yr[e] = live ? mag * fast_cos(ang) : 0.f;
+              yi[e] = live ? mag * fast_sin(ang) : 0.f;
+            }
+            uint4 rh, rl, ih, il;
+            split_h2(yr[0], yr[1], rh.x, rl.x); split_h2(yr[2], yr[3], rh.y, rl.y);
+            split_h2(yr[4], yr[5], rh.z, rl.z); split_h2(yr[6], yr[7], rh.w, rl.w);
+            split_h2(yi[0], yi[1], ih.x, il.x); split_h2(yi[2], yi[3], ih.y, il.y);
+            split_h2(yi[4], yi[5], ih.z, il.z); split_h2(yi[6], yi[7], ih.w, il.w);
+            st_global_v4(a.out_hi + off_r, rh); st_global_v4(a.out_hi + off_i, ih);
+            st_global_v4(a.out_lo + off_r, rl); st_global_v4(a.out_lo + off_i, il);
+            if (a.train) {
+              st_global_v4(a.out_ab + off_r, pack8(va));
+              st_global_v4(a.out_ab + off_i, pack8(vb));
+            }
+          } else {
+            const uint4 yr4 = ld_global_nc_v4(a.in_y + off_r), yi4 = ld_global_nc_v4(a.in_y + off_i);
+            const uint4 a4 = ld_global_nc_v4(a.in_ab + off_r);
+            uint4 b4 = make_uint4(0u, 0u, 0u, 0u);
+            if (!a.real_first) b4 = ld_global_nc_v4(a.in_ab + off_i);
+            tmem_ld8(acc + c0, va);                       // dL/d Re(h)
+            tmem_ld8(acc + kWFeatPerBlock + c0, vb);      // dL/d Im(h)
+            tmem_ld_wait();
+            float yr[8], yi[8], za[8], zb[8], da[8], db[8];
+            unpack8(yr4, yr); unpack8(yi4, yi); unpack8(a4, za); unpack8(b4, zb);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float P = va[e] * yr[e] + vb[e] * yi[e];
-            const float Q = va[e] * yi[e] - vb[e] * yr[e];
-            da[e] = ratio * (-2.f * s2 * za[e] * P - w * Q);
-            db[e] = a.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * P);
-            amax = fmaxf(amax, fmaxf(fabsf(da[e]), fabsf(db[e])));
+            for (int e = 0; e < 8; ++e) {
+              const float P = va[e] * yr[e] + vb[e] * yi[e];
+              const float Q = va[e] * yi[e] - vb[e] * yr[e];
+              da[e] = ratio * (-2.f * s2 * za[e] * P - w * Q);
+              db[e] = a.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * P);
+              amax = fmaxf(amax, fmaxf(fabsf(da[e]), fabsf(db[e])));
+            }
+            st_global_v4(a.out_dz + off_r, pack8(da));
+            st_global_v4(a.out_dz + off_i, pack8(db));
           }
-          st_global_v4(a.out_dz + off_r, make_uint4(pack_h2(da[0], da[1]), pack_h2(da[2], da[3]), pack_h2(da[4], da[5]), pack_h2(da[6], da[7])));
-          st_global_v4(a.out_dz + off_i, make_uint4(pack_h2(db[0], db[1]), pack_h2(db[2], db[3]), pack_h2(db[4], db[5]), pack_h2(db[6], db[7])));
+        }
+      } else {
+        // ---------------- MFN stages: nt = 128 columns per N-block, this warp owns 32 of them (4 steps of 8)
+        const size_t img = static_cast<size_t>(tile) * a.feat_tile_bytes + row * 16;
+        const int grow = tile * kTileM + row;
+        bool masked = false;            // BoundedLinear: this row's input to the linear was zeroed
+        if (a.dist && grow < a.bs) { const float d = a.dist[grow]; masked = (d < a.bound_lo) || (d > a.bound_hi); }
+        float hd[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+        if (a.mode == LG_MFN_DGRAD && a.head_dout && grow < a.bs) {
+#pragma unroll
+          for (int o = 0; o < kMaxOut; ++o)
+            if (o < a.out_f) hd[o] = s_dst * a.head_dout[static_cast<size_t>(grow) * a.head_ld + a.head_col + o];
+        }
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 32 * sub + 8 * i;                 // column inside the N-block
+          const int f0 = a.nt * nb + c0;                   // feature index
+          const size_t off = img + static_cast<size_t>(f0 >> 3) * 2048;
+          float vp[8], vh[8];
+          if (a.mode == LG_MFN_FWD) {
+            tmem_ld8(acc + c0, vp);                        // filter pre-activation  x Om^T
+            if (a.n_seg == 2) tmem_ld8(acc + a.nt + c0, vh);   // linear  z_{i-1} W^T
+            tmem_ld_wait();
+            float g[8], c[8], h[8], z[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float p = vp[e] + s_bb[f0 + e];
+              g[e] = fast_sin(p); c[e] = fast_cos(p);
+              h[e] = a.n_seg == 2 ? ((masked ? 0.f : vh[e]) + s_ba[f0 + e]) : 1.f;
+              z[e] = g[e] * h[e];
+            }
+            st_global_v4(a.out_hi + off, pack8(z));
+            if (a.train) {
+              st_global_v4(a.out_lo + off, pack8(g));
+              st_global_v4(a.out_ab + off, pack8(c));
+              if (a.n_seg == 2) st_global_v4(a.out_h + off, pack8(h));
+            }
+          } else {
+            const uint4 g4 = ld_global_nc_v4(a.in_y + off), c4 = ld_global_nc_v4(a.in_ab + off);
+            uint4 h4 = make_uint4(0u, 0u, 0u, 0u);
+            if (!a.real_first) h4 = ld_global_nc_v4(a.in_h + off);
+            tmem_ld8(acc + c0, vp);                        // S[src] * dh_i W_i  = S[src] * dz_{i-1} (before heads)
+            tmem_ld_wait();
+            float g[8], c[8], h[8], dh[8], dp[8];
+            unpack8(g4, g); unpack8(c4, c); unpack8(h4, h);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float dz = masked ? 0.f : ratio * vp[e];     // masked rows fed zeros to this linear: no gradient flows back
+              if (a.head_dout) {
+#pragma unroll
+                for (int o = 0; o < kMaxOut; ++o)
+                  if (o < a.out_f) dz = fmaf(hd[o], __ldg(a.head_w + o * (a.n_nblocks * a.nt) + f0 + e), dz);
+              }
+              if (a.real_first) { dh[e] = 0.f; dp[e] = dz * c[e]; }
+              else { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; }
+              amax = fmaxf(amax, fmaxf(fabsf(dh[e]), fabsf(dp[e])));
+            }
+            if (!a.real_first) st_global_v4(a.out_dz + off, pack8(dh));
+            st_global_v4(a.out_dp + off, pack8(dp));
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
     }
-    if (a.mode == LG_WIRE_DGRAD) {      // amax of the stored (scaled) values -> next step's scale; order-independent
+    if (dgrad) {      // amax of the stored (scaled) values -> next step's scale; order-independent
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
       if (lane == 0 && amax > 0.f && isfinite(amax))

@@ -1,0 +1,62 @@
+// Descriptors of the multiplicative-filter-network path (FourierNet, MultiscaleKFourier, MultiscaleBoundedFourier;
+// reference src/models/mfn.py).  z_0 = sin(Om_0 x + phi_0);  z_i = sin(Om_i x + phi_i) * (W_i z_{i-1} + b_i), i = 1..L,
+// heads y_k = V_k z_{s_k} + c_k at stages s_k.  Every stage is one lgemm launch with two GEMM segments.
+//
+// Images per 128-row tile, `width` features, fp16, layout elem(r,f) at (f/8)*2048 + r*16 + (f%8)*2:
+//   X (encoded input), Z[i], G[i] = sin p_i, CP[i] = cos p_i (i = 0..L), H[i] = W_i z_{i-1} + b_i (i = 1..L),
+//   DH[i] = S_i dL/dh_i (i = 1..L), DP[i] = S_i dL/dp_i (i = 0..L), DOUT[k] = S dL/dy_k padded to 16 columns.
+#pragma once
+#include <cstdint>
+#include "inr_kernels.cuh"
+
+namespace inr {
+
+constexpr int kMfnMaxStages = 10;     // L + 1 <= 10
+constexpr int kMfnNT = 128;
+
+struct MfnModel {
+  int L;                 // linear layers (reference network_depth); stages 0..L
+  int width, in_f, out_f;
+  int n_heads;           // FourierNet: 1 (output_linear at stage L); multiscale: L + 1 (output_linear.i), few are live
+  int head_stage[kMfnMaxStages];      // stage of head k
+  int head_live[kMfnMaxStages];       // 1: head k is returned by forward (reference output_layers)
+  int stage_head[kMfnMaxStages];      // live head index attached to stage i, or -1
+  int top;               // highest stage with a live head: stages above it are dead (reference computes and discards them)
+  int n_out;             // number of live heads (columns of `out` = n_out * out_f, in stage order)
+  int bounded;           // MultiscaleBoundedFourier: rows with dist outside [lo, hi] are zeroed before linear i
+  float bound_lo[kMfnMaxStages], bound_hi[kMfnMaxStages];   // indexed by stage (stage i uses reference linear[i-1])
+  int input_kind;        // INPUT_GAUSS / INPUT_DENSE
+  int enc_size;
+  // float offsets in the flat parameter buffer
+  int lin_w[kMfnMaxStages], lin_b[kMfnMaxStages];       // stage i = 1..L
+  int head_w[kMfnMaxStages], head_b[kMfnMaxStages];
+  int filt_w[kMfnMaxStages], filt_b[kMfnMaxStages];     // stage i = 0..L
+  int n_params;
+  // packed fp16 operands (bytes in wpack)
+  uint32_t pk_filt[kMfnMaxStages], pk_lin[kMfnMaxStages], pk_lin_t[kMfnMaxStages];
+  uint32_t wpack_bytes;
+};
+
+struct MfnWorkspace {
+  uint64_t x, z[kMfnMaxStages], g[kMfnMaxStages], cp[kMfnMaxStages], h[kMfnMaxStages], dh[kMfnMaxStages], dp[kMfnMaxStages];
+  uint64_t dout[kMfnMaxStages];      // per live head
+  uint64_t gl, part, scal, gpart, total;
+  int n_tiles, n_split;
+};
+
+struct MfnAuxArgs {
+  MfnModel m;
+  MfnWorkspace w;
+  LossDesc loss;
+  const float* params;
+  const float* coords; const float* x; const float* encB;
+  const float* gt; const uint8_t* mask; const float* dist;
+  float* out;
+  const float* dout;       // external dL/dout [bs, n_out*out_f] (autograd path) or null (fused single-head loss)
+  uint8_t* ws;
+  const int* row_offset; int* step_counter;
+  const float* hyper; const int* step;
+  int bs, train, bs_k;
+};
+
+}  // namespace inr

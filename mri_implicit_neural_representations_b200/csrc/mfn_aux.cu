@@ -1,0 +1,279 @@
+// CUDA-core kernels around the MFN stage GEMMs (HBM-bound elementwise / small-N work):
+//   mfn_encode_kernel  : gauss positional encoding (reference networks.py:30-33) or dense [bs,in] input -> fp16 X image
+//   mfn_head_kernel    : output heads y_k = V_k z_{s_k} + c_k (reference mfn.py:38,92,262-263) (+ fused loss pieces for
+//                        single-head models)
+//   mfn_scalars_kernel : step scalars + per-stage gradient scales
+//   mfn_top_kernel     : backward entry: fp16 dL/dy images per head and (dh, dp) of the top live stage
+#include <cuda_runtime.h>
+#include "inr_ptx.cuh"
+#include "mfn.cuh"
+#include "inr_loss.cuh"
+
+namespace inr {
+
+__device__ __forceinline__ void mfn_unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 mfn_pack8(const float (&f)[8]) {
+  return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------ input image
+__global__ void __launch_bounds__(256) mfn_encode_kernel(const __grid_constant__ MfnAuxArgs a) {
+  const MfnModel& M = a.m;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  if (tile == 0 && tid == 0 && a.step_counter) *a.step_counter += 1;
+  const int row_base = a.row_offset ? *a.row_offset : 0;
+  const uint32_t tile_bytes = kTileM * M.in_f * 2;
+  uint8_t* ximg = a.ws + a.w.x + static_cast<size_t>(tile) * tile_bytes;
+  const int n_kg = M.in_f / 8;
+  for (int idx = tid; idx < kTileM * n_kg; idx += 256) {
+    const int row = idx & (kTileM - 1), kg = idx >> 7;
+    const int grow = tile * kTileM + row;
+    const size_t srow = static_cast<size_t>(row_base) + grow;
+    float v[8];
+    if (M.input_kind == INPUT_GAUSS) {
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+      if (grow < a.bs) { const float* c = a.coords + srow * 3; x0 = c[0]; x1 = c[1]; x2 = c[2]; }
+      const bool is_cos = kg * 8 >= M.enc_size;
+      const int f0 = kg * 8 - (is_cos ? M.enc_size : 0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float* b = a.encB + (f0 + e) * 3;
+        const float ang = 6.283185307179586f * fmaf(x0, __ldg(b), fmaf(x1, __ldg(b + 1), x2 * __ldg(b + 2)));
+        v[e] = is_cos ? fast_cos(ang) : fast_sin(ang);
+      }
+    } else {
+      const float* xr = a.x + srow * M.in_f + kg * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = grow < a.bs ? xr[e] : 0.f;
+    }
+    st_global_v4(ximg + static_cast<size_t>(kg) * 2048 + row * 16, mfn_pack8(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ heads (+ fused loss)
+__global__ void __launch_bounds__(128) mfn_head_kernel(const __grid_constant__ MfnAuxArgs a) {
+  __shared__ float sW[kMaxOut][512];
+  __shared__ float red[4][8];
+  const MfnModel& M = a.m;
+  const int tile = blockIdx.x, row = threadIdx.x, lane = row & 31, q = row >> 5;
+  // live head handled by this block
+  int k = -1, seen = 0;
+  for (int kk = 0; kk < M.n_heads; ++kk)
+    if (M.head_live[kk]) { if (seen == static_cast<int>(blockIdx.y)) { k = kk; break; } ++seen; }
+  const int stage = M.head_stage[k];
+  for (int i = row; i < kMaxOut * M.width; i += 128) {
+    const int o = i / M.width, j = i % M.width;
+    sW[o][j] = o < M.out_f ? a.params[M.head_w[k] + o * M.width + j] : 0.f;
+  }
+  __syncthreads();
+  const int row_base = a.row_offset ? *a.row_offset : 0;
+  const int grow = tile * kTileM + row;
+  const bool valid = grow < a.bs;
+  const size_t srow = static_cast<size_t>(row_base) + grow;
+  const uint32_t tile_bytes = kTileM * M.width * 2;
+  const uint8_t* zimg = a.ws + a.w.z[stage] + static_cast<size_t>(tile) * tile_bytes + row * 16;
+  float acc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+  for (int kg = 0; kg < M.width / 8; ++kg) {
+    float z[8];
+    mfn_unpack8(ld_global_nc_v4(zimg + static_cast<size_t>(kg) * 2048), z);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o)
+        if (o < M.out_f) acc[o] = fmaf(z[e], sW[o][kg * 8 + e], acc[o]);
+  }
+  float y[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, t[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o)
+    if (o < M.out_f) y[o] = acc[o] + a.params[M.head_b[k] + o];
+  const int out_ld = M.n_out * M.out_f, col = static_cast<int>(blockIdx.y) * M.out_f;
+  if (valid && a.out)
+    for (int o = 0; o < M.out_f; ++o) a.out[static_cast<size_t>(grow) * out_ld + col + o] = y[o];
+  if (!a.train || a.loss.kind == LOSS_NONE || M.n_out != 1) return;
+  // ---- fused loss pieces (single-head models)
+  float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
+  float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid && a.gt) {
+    const bool in_loss = a.mask ? (a.mask[srow] != 0) : true;
+    if (a.loss.kind == LOSS_HDR && a.coords) {
+      const float kx = a.coords[srow * 3 + 1], ky = a.coords[srow * 3 + 2];
+      const float f = expf(-(kx * kx + ky * ky) / (2.f * a.loss.sigma * a.loss.sigma));
+      fs = (1.f - f) * (1.f - f);
+    }
+    if (in_loss) {
+      for (int o = 0; o < M.out_f; ++o) t[o] = a.gt[srow * M.out_f + o];
+      RowLoss r = loss_row(a.loss, M.out_f, y, t);
+      lA = r.lossA; lB = r.lossB; cnt = 1.f;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) { amA = fmaxf(amA, fabsf(r.gA[o])); amB = fmaxf(amB, fabsf(r.gB[o])); }
+      gq = make_float4(r.gA[0], r.gA[1], r.gB[0], r.gB[1]);
+    }
+  }
+  float* gdst = reinterpret_cast<float*>(a.ws + a.w.gl) + (static_cast<size_t>(tile) * kTileM + row) * 4;
+  *reinterpret_cast<float4*>(gdst) = gq;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lA += __shfl_xor_sync(0xffffffffu, lA, off); lB += __shfl_xor_sync(0xffffffffu, lB, off);
+    fs += __shfl_xor_sync(0xffffffffu, fs, off); cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    amA = fmaxf(amA, __shfl_xor_sync(0xffffffffu, amA, off)); amB = fmaxf(amB, __shfl_xor_sync(0xffffffffu, amB, off));
+  }
+  if (lane == 0) { red[q][0] = lA; red[q][1] = lB; red[q][2] = fs; red[q][3] = cnt; red[q][4] = amA; red[q][5] = amB; }
+  __syncthreads();
+  if (row == 0) {
+    float* pdst = reinterpret_cast<float*>(a.ws + a.w.part) + static_cast<size_t>(tile) * kPartialsPerTile;
+    pdst[0] = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+    pdst[1] = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+    pdst[2] = (red[0][2] + red[1][2]) + (red[2][2] + red[3][2]);
+    pdst[3] = (red[0][3] + red[1][3]) + (red[2][3] + red[3][3]);
+    pdst[4] = fmaxf(fmaxf(red[0][4], red[1][4]), fmaxf(red[2][4], red[3][4]));
+    pdst[5] = fmaxf(fmaxf(red[0][5], red[1][5]), fmaxf(red[2][5], red[3][5]));
+    pdst[6] = 0.f; pdst[7] = 0.f;
+  }
+}
+
+// amax partials of an external dL/dout [bs, n_out*out_f]
+__global__ void __launch_bounds__(128) mfn_dout_amax_kernel(const float* dout, int bs, int ld, float* partials) {
+  __shared__ float red[4];
+  const int tile = blockIdx.x, row = tile * kTileM + threadIdx.x;
+  float am = 0.f;
+  if (row < bs)
+    for (int o = 0; o < ld; ++o) am = fmaxf(am, fabsf(dout[static_cast<size_t>(row) * ld + o]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = am;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* p = partials + static_cast<size_t>(tile) * kPartialsPerTile;
+    for (int i = 0; i < 8; ++i) p[i] = 0.f;
+    p[4] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ step scalars
+__global__ void __launch_bounds__(256) mfn_scalars_kernel(const __grid_constant__ MfnAuxArgs a) {
+  __shared__ float sc[kScalars];
+  float* g = reinterpret_cast<float*>(a.ws + a.w.scal);
+  reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step, g, sc);
+  if (threadIdx.x == 0) {
+    // per-stage scales from the previous step's amax (lagged dynamic scaling, 2^10 headroom below the fp16 maximum);
+    // uncalibrated stages start at the loss scale divided by 16
+    unsigned int* am = reinterpret_cast<unsigned int*>(g) + SC_LAYER_AMAX;
+    for (int l = a.m.top; l >= 0; --l) {
+      const float old = g[SC_LAYER_SCALE + l];
+      const float seen = __uint_as_float(am[l]);
+      float S;
+      if (old > 0.f && seen > 0.f && isfinite(seen) && isfinite(old)) {
+        int e = static_cast<int>(floorf(log2f(64.f * old / seen)));
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        S = exp2f(static_cast<float>(e));
+      } else {
+        S = sc[SC_SCALE] * 0.0625f;
+      }
+      g[SC_LAYER_SCALE + l] = S;
+      am[l] = 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward entry
+// dL/dy_k images for the head wgrad units, and (dh, dp) of the top live stage from its head gradient.
+__global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ MfnAuxArgs a) {
+  const MfnModel& M = a.m;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const float* sc = reinterpret_cast<const float*>(a.ws + a.w.scal);
+  const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
+  const int top = M.top;
+  const float St = sc[SC_LAYER_SCALE + top];
+  const int out_ld = M.n_out * M.out_f;
+  const uint32_t tile_bytes = kTileM * M.width * 2;
+  const int hk = M.stage_head[top];                   // live head index of the top stage
+  int k_top = -1, seen = 0;
+  for (int kk = 0; kk < M.n_heads; ++kk)
+    if (M.head_live[kk]) { if (seen == hk) { k_top = kk; break; } ++seen; }
+  const float* Wt = a.params + M.head_w[k_top];
+  const uint8_t* gimg = a.ws + a.w.g[top] + static_cast<size_t>(tile) * tile_bytes;
+  const uint8_t* cimg = a.ws + a.w.cp[top] + static_cast<size_t>(tile) * tile_bytes;
+  const uint8_t* himg = a.ws + a.w.h[top] + static_cast<size_t>(tile) * tile_bytes;
+  uint8_t* dhimg = a.ws + a.w.dh[top] + static_cast<size_t>(tile) * tile_bytes;
+  uint8_t* dpimg = a.ws + a.w.dp[top] + static_cast<size_t>(tile) * tile_bytes;
+  float amax = 0.f;
+  const int n_kg = M.width / 8;
+  for (int idx = tid; idx < kTileM * n_kg; idx += 256) {
+    const int row = idx & (kTileM - 1), kg = idx >> 7;
+    const int grow = tile * kTileM + row;
+    // ---- dL/dy of every live head for this row (unscaled, fp32)
+    if (kg < M.n_out) {       // one thread per (row, head) writes that head's padded fp16 image
+      float d[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+      if (grow < a.bs) {
+        if (a.dout) {
+          for (int o = 0; o < M.out_f; ++o) d[o] = S * a.dout[static_cast<size_t>(grow) * out_ld + kg * M.out_f + o];
+        } else {
+          const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.gl) +
+                                                             (static_cast<size_t>(tile) * kTileM + row) * 4);
+          d[0] = S * (cA * g.x + cB * g.z); d[1] = S * (cA * g.y + cB * g.w);
+        }
+      }
+      uint8_t* zl = a.ws + a.w.dout[kg] + static_cast<size_t>(tile) * kDzLastBytes;
+      st_global_v4(zl + row * 16, make_uint4(pack_h2(d[0], d[1]), pack_h2(d[2], d[3]), 0u, 0u));
+      st_global_v4(zl + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
+    }
+    float dy[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+    if (grow < a.bs) {
+      if (a.dout) {
+        for (int o = 0; o < M.out_f; ++o) dy[o] = St * a.dout[static_cast<size_t>(grow) * out_ld + hk * M.out_f + o];
+      } else {
+        const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.gl) +
+                                                           (static_cast<size_t>(tile) * kTileM + row) * 4);
+        dy[0] = St * (cA * g.x + cB * g.z); dy[1] = St * (cA * g.y + cB * g.w);
+      }
+    }
+    const size_t off = static_cast<size_t>(kg) * 2048 + row * 16;
+    float g[8], c[8], h[8], dh[8], dp[8];
+    mfn_unpack8(ld_global_nc_v4(gimg + off), g);
+    mfn_unpack8(ld_global_nc_v4(cimg + off), c);
+    if (top >= 1) mfn_unpack8(ld_global_nc_v4(himg + off), h);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = 0.f;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o)
+        if (o < M.out_f) dz = fmaf(dy[o], __ldg(Wt + o * M.width + kg * 8 + e), dz);
+      if (top >= 1) { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; }
+      else { dh[e] = 0.f; dp[e] = dz * c[e]; }
+      amax = fmaxf(amax, fmaxf(fabsf(dh[e]), fabsf(dp[e])));
+    }
+    if (top >= 1) st_global_v4(dhimg + off, mfn_pack8(dh));
+    st_global_v4(dpimg + off, mfn_pack8(dp));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  if ((tid & 31) == 0 && amax > 0.f && isfinite(amax))
+    atomicMax(reinterpret_cast<unsigned int*>(a.ws + a.w.scal) + SC_LAYER_AMAX + top, __float_as_uint(amax));
+}
+
+cudaError_t launch_mfn_encode(const MfnAuxArgs& a, cudaStream_t st) {
+  mfn_encode_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_mfn_head(const MfnAuxArgs& a, cudaStream_t st) {
+  mfn_head_kernel<<<dim3(a.w.n_tiles, a.m.n_out), 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_mfn_dout_amax(const MfnAuxArgs& a, cudaStream_t st) {
+  mfn_dout_amax_kernel<<<a.w.n_tiles, 128, 0, st>>>(a.dout, a.bs, a.m.n_out * a.m.out_f, reinterpret_cast<float*>(a.ws + a.w.part));
+  return cudaGetLastError();
+}
+cudaError_t launch_mfn_scalars(const MfnAuxArgs& a, cudaStream_t st) {
+  mfn_scalars_kernel<<<1, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_mfn_top(const MfnAuxArgs& a, cudaStream_t st) {
+  mfn_top_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace inr

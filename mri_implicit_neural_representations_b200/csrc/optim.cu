@@ -20,6 +20,20 @@ __device__ __forceinline__ int find_seg(const SegDesc* seg, int n_seg, int p) {
 
 __device__ __forceinline__ void pack_store(const SegDesc& s, uint8_t* wpack, int local, float val) {
   const int o = local / s.cols, i = local - o * s.cols;
+  if (s.layout == 1) {      // lgemm operands: N-blocks of nt rows, K stages of 32 columns
+    const uint32_t stage_b = static_cast<uint32_t>(s.nt) * 64;
+    if (s.pack_fwd) {       // B[n = out, k = in]
+      const int nb = o / s.nt, n = o % s.nt, st = i >> 5, kk = i & 31;
+      *reinterpret_cast<__half*>(wpack + s.wf_off + (static_cast<size_t>(nb) * (s.cols >> 5) + st) * stage_b + (kk >> 3) * (s.nt * 16) +
+                                 n * 16 + (kk & 7) * 2) = __float2half_rn(val * s.fwd_scale);
+    }
+    if (s.pack_bwd) {       // B^T[n = in, k = out]
+      const int nb = i / s.nt, n = i % s.nt, st = o >> 5, kk = o & 31;
+      *reinterpret_cast<__half*>(wpack + s.wd_off + (static_cast<size_t>(nb) * (s.rows >> 5) + st) * stage_b + (kk >> 3) * (s.nt * 16) +
+                                 n * 16 + (kk & 7) * 2) = __float2half_rn(val * s.bwd_scale);
+    }
+    return;
+  }
   if (s.pack_fwd) {
     const __half h = __float2half_rn(val * s.fwd_scale);
     int kp = i;
@@ -60,10 +74,13 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.n_params) return;
+  const int si = find_seg(a.seg, a.n_seg, p);
+  const SegDesc& sg = a.seg[si];
+  if (sg.frozen) { if (a.grads) a.grads[p] = 0.f; return; }
   const float* gp = a.gpart;
   float g = 0.f;
   for (int s = 0; s < a.n_split; ++s) g += gp[static_cast<size_t>(s) * a.n_params + p];
-  g *= s_c[2];
+  g *= (sg.scale_slot >= 0 && a.scal) ? 1.f / a.scal[sg.scale_slot] : s_c[2];
   float w = a.params[p];
   if (a.do_adam) {
     const float l1 = a.hyper[5], l2 = a.hyper[6];
@@ -80,8 +97,6 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
   const float denom = sqrtf(v) / s_c[1] + eps;
   w = w - s_c[0] * (m / denom);
   a.params[p] = w;
-  const int si = find_seg(a.seg, a.n_seg, p);
-  const SegDesc& sg = a.seg[si];
   if (sg.pack_fwd | sg.pack_bwd) pack_store(sg, a.wpack, p - sg.off, w);
 }
 

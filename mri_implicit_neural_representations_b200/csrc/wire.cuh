@@ -25,28 +25,49 @@ constexpr int kWStageBBytes = kWNT * kStageK * 2;     // 12288: B stage (192 row
 constexpr int kWStageABytes = kTileM * kStageK * 2;   // 8192:  A stage (128 rows x 32 K)
 constexpr int kWMaxDepth = 8;
 
-enum LGemmMode { LG_WIRE_FWD = 1, LG_WIRE_DGRAD = 2 };
+enum LGemmMode { LG_WIRE_FWD = 1, LG_WIRE_DGRAD = 2, LG_MFN_FWD = 3, LG_MFN_DGRAD = 4 };
+
+// One GEMM segment of a work item: acc[:, acc_col : acc_col + nt] = A[128 x K] * B_block[nt x K]^T
+struct LGemmSeg {
+  const uint8_t* a_hi;      // A images, tile stride a_tile_bytes = 128 * K * 2
+  const uint8_t* a_lo;      // null for 1-pass
+  const uint8_t* b_hi;      // packed B, per N-block: [K/32 stages][nt x 32]
+  const uint8_t* b_lo;
+  uint32_t a_tile_bytes;
+  int k_stages;             // K / 32
+  int acc_col;              // column offset inside the item's accumulator
+};
 
 struct LGemmArgs {
-  const uint8_t* a_hi;      // A images (tile stride kWTileBytes)
-  const uint8_t* a_lo;      // null for 1-pass
-  const uint8_t* b_hi;      // packed B, per N-block: [K/32 stages][192 x 32]
-  const uint8_t* b_lo;
+  LGemmSeg seg[2];
+  int n_seg;                // 1 (WIRE) or 2 (MFN stage: filter GEMM + linear GEMM)
+  int nt;                   // UMMA N of every segment; n_seg * nt <= 256 (two 256-column accumulators ping-pong)
   int n_tiles, n_nblocks, passes, mode;
   // ---- epilogue operands
-  const float* bias;        // WIRE_FWD: complex bias, interleaved (re, im), C entries
-  float omega, sigma;       // Gabor constants of the layer whose activation / derivative is evaluated
-  int c_valid;              // real complex width (181)
-  int train;                // WIRE_FWD: also store AB
-  int real_first;           // WIRE_DGRAD: target layer is the real first layer (b == 0, only dza is meaningful)
-  uint8_t* out_hi;          // WIRE_FWD: H_hi / H_lo of the next layer, AB of this layer
-  uint8_t* out_lo;
-  uint8_t* out_ab;
-  const uint8_t* in_y;      // WIRE_DGRAD: H_hi of the layer's input (= y of the target layer), AB of the target layer
-  const uint8_t* in_ab;
-  uint8_t* out_dz;          // WIRE_DGRAD: dZ image of the target layer
-  const float* scal;        // WIRE_DGRAD: step scalars (per-layer scales at SC_LAYER_SCALE, amax at SC_LAYER_AMAX)
-  int src_layer, dst_layer; // WIRE_DGRAD: A holds S[src] * dZ_src, the epilogue stores S[dst] * dZ_dst
+  const float* bias;        // WIRE_FWD: complex bias, interleaved (re, im); MFN_FWD: linear bias b_i [width]
+  const float* phi;         // MFN_FWD: filter bias phi_i [width]
+  float omega, sigma;       // WIRE: Gabor constants of the layer whose activation / derivative is evaluated
+  int c_valid;              // WIRE: real complex width (181)
+  int train;                // FWD: also store what backward needs
+  int real_first;           // WIRE_DGRAD: target layer is the real first layer;  MFN: target stage is stage 0 (z_0 = sin p_0)
+  uint8_t* out_hi;          // WIRE_FWD: H_hi / H_lo of the next layer, AB of this layer.  MFN_FWD: z_i image
+  uint8_t* out_lo;          //                                                             MFN_FWD: sin(p_i) image
+  uint8_t* out_ab;          //                                                             MFN_FWD: cos(p_i) image
+  uint8_t* out_h;           // MFN_FWD: linear output h_i image
+  const uint8_t* in_y;      // WIRE_DGRAD: H_hi of the layer's input, AB of the target layer.  MFN_DGRAD: sin(p) of the target stage
+  const uint8_t* in_ab;     //                                                                  MFN_DGRAD: cos(p) of the target stage
+  const uint8_t* in_h;      // MFN_DGRAD: h of the target stage
+  uint8_t* out_dz;          // WIRE_DGRAD: dZ image of the target layer.  MFN_DGRAD: dh image of the target stage
+  uint8_t* out_dp;          // MFN_DGRAD: dp image of the target stage
+  const float* scal;        // DGRAD: step scalars (per-layer scales at SC_LAYER_SCALE, amax at SC_LAYER_AMAX)
+  int src_layer, dst_layer; // DGRAD: A holds S[src] * grad_src, the epilogue stores S[dst] * grad_dst
+  // MFN_DGRAD head-gradient injection and BoundedLinear masking
+  const float* head_dout;   // [rows, head_ld] fp32 dL/dout (unscaled) or null
+  const float* head_w;      // [out_f, width] weight of the head attached to the target stage
+  int head_col, head_ld, out_f, bs;
+  const float* dist;        // BoundedLinear: per-row distance [rows] or null
+  float bound_lo, bound_hi; // rows with dist < lo or dist > hi are zeroed before this stage's linear
+  uint32_t feat_tile_bytes; // bytes of one 128-row image of the epilogue's feature images (MFN: 128 * width * 2)
 };
 
 struct WireModel {

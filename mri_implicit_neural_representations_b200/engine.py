@@ -33,8 +33,8 @@ class Plan:
         enc = encoder or {"embedding": "none"}
         if model not in L.MODEL:
             raise NotImplementedError(model)                      # src/train.py:69-70
-        if model == "WIRE":
-            last = "linear"                                        # output = real part of the final complex linear
+        if model in ("WIRE", "Fourier", "MultiscaleFourier", "BoundedFourier"):
+            last = "linear"                                        # WIRE: real part of the final complex linear; MFN: plain heads
         elif model == "FFN":
             last = "sigmoid"                                       # src/models/networks.py:63
         elif net.get("last_tanh", False):
@@ -51,6 +51,16 @@ class Plan:
                                 L.ENC[kind], int(enc.get("embedding_size", 0)) if kind == "gauss" else 0,
                                 float(net.get("first_omega_0", 30.0)) if model == "WIRE" else 30.0,
                                 float(net.get("hidden_omega_0", 30.0)), float(net.get("scale", 10.0)))
+        self.out_cols = int(net["network_output_size"])
+        if model in ("MultiscaleFourier", "BoundedFourier"):
+            layers = list(net.get("output_layers", [1, 3, 5, 7]))
+            mask = 0
+            for i in layers:
+                mask |= 1 << int(i)
+            self.desc.head_mask = mask
+            self.out_cols = len(layers) * int(net["network_output_size"])
+            for i, (lo, hi) in enumerate(net.get("boundaries", []) or []):
+                self.desc.bounds[2 * i], self.desc.bounds[2 * i + 1] = float(lo), float(hi)
         self.model, self.net, self.encoder = model, dict(net), dict(enc)
         h = C.c_void_p()
         L.check(L.lib.inr_plan_create(C.byref(self.desc), C.byref(h)), "inr_plan_create")
@@ -162,7 +172,7 @@ class ChainEngine:
         bs = inp.shape[0]
         assert bs <= self.max_batch
         inp = inp.to(self.device, torch.float32).contiguous()
-        out = torch.zeros(bs, self.plan.desc.out_features, dtype=torch.float32, device=self.device)
+        out = torch.zeros(bs, self.plan.out_cols, dtype=torch.float32, device=self.device)
         L.check(L.lib.inr_forward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(inp), _ptr(self.encB), bs,
                                   _ptr(self.workspace), _ptr(out), 1 if train else 0, _stream()), "inr_forward")
         return out
@@ -242,6 +252,14 @@ class ChainEngine:
                                     _ptr(self.workspace), _ptr(out), _ptr(self.grads), _ptr(self.loss_out), _stream()),
                 "inr_grad_step")
         return self.grads
+
+    def read_mfn_image(self, kind: str, stage: int, bs: int) -> torch.Tensor:
+        """MFN only (tests / debugging): 'z' (stage output), 'g' (sin p), 'dp' (S_stage * dL/dp) as [rows_pad, width]."""
+        lay = self.plan.workspace_layout(bs)
+        T, F = lay["n_tiles"], self.plan.desc.width
+        off = {"z": lay["h"], "g": lay["d"], "dp": lay["dz"]}[kind][stage]
+        img = self.workspace[off:off + T * 128 * F * 2].view(torch.float16).view(T, F // 8, 128, 8)
+        return img.permute(0, 2, 1, 3).reshape(T * 128, F).float()
 
     def read_wire_image(self, kind: str, layer: int, bs: int) -> torch.Tensor:
         """WIRE only (tests / debugging): decode a 384-feature image family to a complex [rows_pad, 192] matrix.

@@ -57,3 +57,39 @@ def wire_tensors(net: dict):
     out.append((f"net.{depth + 1}.weight", lin.weight.detach().clone()))
     out.append((f"net.{depth + 1}.bias", lin.bias.detach().clone()))
     return out
+
+
+def mfn_tensors(model: str, net: dict, input_scale: float = 2.0, weight_scale: float = 1.0):
+    """[(name, tensor)] in reference state_dict order for FourierNet ('Fourier') and the multiscale variants
+    ('MultiscaleFourier', 'BoundedFourier'), same torch calls in the same order as reference src/models/mfn.py
+    (:15-30 MFNBase, :50-55 FourierLayer, :61-83, :216-251, :300-340)."""
+    L, hid = net["network_depth"], net["network_width"]
+    fin, fout = net["network_input_size"], net["network_output_size"]
+    lins = [nn.Linear(hid, hid, True) for _ in range(L)]
+    out_lin = nn.Linear(hid, fout)
+    b = math.sqrt(weight_scale / hid)
+    for lin in lins:
+        lin.weight.data.uniform_(-b, b)
+    multi = model != "Fourier"
+    if model == "BoundedFourier":                       # BoundedLinear replaces the scaled-uniform linears (default init)
+        lins = [nn.Linear(hid, hid, True) for _ in range(L)]
+    fscale = (weight_scale if multi else input_scale) / math.sqrt(L + 1)
+    filt = []
+    for _ in range(L + 1):
+        f = nn.Linear(fin, hid)
+        f.weight.data *= fscale
+        f.bias.data.uniform_(-math.pi, math.pi)
+        filt.append(f)
+    outs = [nn.Linear(hid, fout) for _ in range(L + 1)] if multi else None
+    res = []
+    for i, l in enumerate(lins):
+        pre = f"linear.{i}.linear" if model == "BoundedFourier" else f"linear.{i}"
+        res += [(pre + ".weight", l.weight.detach().clone()), (pre + ".bias", l.bias.detach().clone())]
+    if multi:
+        for i, o in enumerate(outs):
+            res += [(f"output_linear.{i}.weight", o.weight.detach().clone()), (f"output_linear.{i}.bias", o.bias.detach().clone())]
+    else:
+        res += [("output_linear.weight", out_lin.weight.detach().clone()), ("output_linear.bias", out_lin.bias.detach().clone())]
+    for i, f in enumerate(filt):
+        res += [(f"filters.{i}.linear.weight", f.weight.detach().clone()), (f"filters.{i}.linear.bias", f.bias.detach().clone())]
+    return res
