@@ -54,7 +54,9 @@ class _ChainFn(torch.autograd.Function):
         elif m._last_act == "sigmoid":
             dz = dout * out * (1 - out)
         grads = m._engine_backward(dz.contiguous(), ctx.bs)
-        return (None, None, *[g.clone() if need else None for g, need in zip(grads, ctx.needs_input_grad[2:])])
+        dead = m._dead_param_flags()
+        return (None, None, *[g.clone() if (need and not d) else None
+                              for g, need, d in zip(grads, ctx.needs_input_grad[2:], dead)])
 
 
 class FusedChain(nn.Module):
@@ -167,6 +169,11 @@ class FusedChain(nn.Module):
         self._param_epoch += 1
         eng.packed_epoch = self._epoch_token()      # the fused optimiser re-packed this engine's copies itself
 
+    def _dead_param_flags(self):
+        """True for parameters no gradient ever reaches (reference autograd leaves their .grad None)."""
+        eng = next(iter(self._engines.values()))
+        return [frozen for (_, frozen) in eng.plan.tensor_flags]
+
     def _engine_forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
         eng = self.engine(None, x.shape[0])
         return eng.forward(x, train=train)
@@ -257,6 +264,71 @@ class WIRE(FusedChain):
         res = nn.Module.load_state_dict(self, renamed, strict=strict)
         self._param_epoch += 1
         return res
+
+
+class FourierNet(FusedChain):
+    """reference src/models/mfn.py:61-94 -- keys linear.<i>.{weight,bias}, output_linear.{weight,bias},
+    filters.<i>.linear.{weight,bias}.  forward(x [bs, in]) -> [bs, out]."""
+    MODEL = "Fourier"
+    N_OUT = None
+
+    def __init__(self, params, out_size=1.0, input_scale=2.0, weight_scale=1.0, bias=True, output_act=False):
+        if output_act or not bias:
+            raise L.InrError("output_act / bias=False variants of the MFNs are not built")
+        self._scales = (input_scale, weight_scale)
+        super().__init__(params)
+
+    def _init_tensors(self):
+        return pinit.mfn_tensors(self.MODEL, self.net, *self._scales)
+
+    def _build_tree(self):
+        v = self._views(self._flat)
+        L_ = self.net["network_depth"]
+        self.linear = nn.ModuleList([self._lin_holder(v[2 * i], v[2 * i + 1]) for i in range(L_)])
+        nh = self._n_head_tensors()
+        o = 2 * L_
+        if nh == 1:
+            self.output_linear = _Leaf(v[o], v[o + 1])
+        else:
+            self.output_linear = nn.ModuleList([_Leaf(v[o + 2 * k], v[o + 2 * k + 1]) for k in range(nh)])
+        o += 2 * nh
+        self.filters = nn.ModuleList([_Wrap("linear", _Leaf(v[o + 2 * i], v[o + 2 * i + 1])) for i in range(L_ + 1)])
+
+    def _lin_holder(self, w, b):
+        return _Leaf(w, b)
+
+    def _n_head_tensors(self):
+        return 1
+
+    def _leaves(self):
+        lins = [m if isinstance(m, _Leaf) else m.linear for m in self.linear]
+        heads = [self.output_linear] if isinstance(self.output_linear, _Leaf) else list(self.output_linear)
+        return lins + heads + [f.linear for f in self.filters]
+
+    def forward(self, x, dist_to_center=None):
+        return _ChainFn.apply(x, self, *self._params_in_order())
+
+
+class MultiscaleKFourier(FourierNet):
+    """reference src/models/mfn.py:206-267 -- heads output_linear.<i> at `output_layers`; forward(coords=x) returns the
+    LIST of head outputs in stage order.  Parameters of dead stages / unused heads never receive gradients."""
+    MODEL = "MultiscaleFourier"
+
+    def __init__(self, params, weight_scale=1.0, bias=True, output_act=False, centered=True, output_layers=(1, 3, 5, 7),
+                 reuse_filters=False):
+        params = dict(params)
+        params["output_layers"] = list(output_layers) if output_layers is not None else list(range(1, params["network_depth"] + 1))
+        self.output_layers = params["output_layers"]
+        self.stop_after = None
+        FourierNet.__init__(self, params, input_scale=2.0, weight_scale=weight_scale, bias=bias, output_act=output_act)
+
+    def _n_head_tensors(self):
+        return self.net["network_depth"] + 1
+
+    def forward(self, coords, **args):
+        out = _ChainFn.apply(coords, self, *self._params_in_order())
+        f = self.net["network_output_size"]
+        return [out[:, f * k:f * (k + 1)] for k in range(len(self.output_layers))]
 
 
 class Positional_Encoder:

@@ -61,6 +61,23 @@ class HDRLoss_FF(torch.nn.Module):          # reference :226-264, evaluated in i
         return loss.mean() + reg, reg
 
 
+class ConsistencyLoss(torch.nn.Module):    # reference :292-324
+    """Supervises output i+1 with (detached) output i on the points OUTSIDE disc i."""
+
+    def __init__(self, bounds):
+        super().__init__()
+        self.bounds = bounds
+
+    def forward(self, input, dist):
+        loss = 0
+        for i in range(len(self.bounds) - 1):
+            lo, hi = self.bounds[i]
+            ind = torch.where((dist < lo) | (dist > hi))
+            if ind[0].numel():
+                loss = loss + torch.nn.functional.mse_loss(input[i][ind].detach(), input[i + 1][ind])
+        return loss
+
+
 def tv_loss(img, weight=0.0001):            # reference :326-343
     w_variance = torch.nn.functional.l1_loss(img[:, :-1, :], img[:, 1:, :])
     h_variance = torch.nn.functional.l1_loss(img[:-1, :, :], img[1:, :, :])

@@ -20,6 +20,7 @@ if _SRC not in sys.path:
     sys.path.insert(0, _SRC)
 
 from models.networks import FFN, SIREN, WIRE, Positional_Encoder            # noqa: E402
+from models.mfn import FourierNet, GaborNet, KGaborNet                       # noqa: E402
 from models.regularization import Regularization_L1, Regularization_L2       # noqa: E402
 from metrics.losses import HDRLoss_FF, MSLELoss, TanhL2Loss, tv_loss          # noqa: E402
 from data.slices import get_data_loader                                      # noqa: E402
@@ -45,6 +46,12 @@ def build_model(config):
         return FFN(config["net"])
     if name == "WIRE":
         return WIRE(config["net"])
+    if name == "Fourier":
+        return FourierNet(config["net"])
+    if name == "Gabor":
+        return GaborNet(config["net"])
+    if name == "KGabor":
+        return KGaborNet(config["net"])
     raise NotImplementedError(name)            # reference :69-70
 
 
@@ -113,7 +120,8 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
     train_ds = data_loader.ds
     gt_image = M.reconstruct(dataset.image.to(device), (C, H, W), in_image_space)
 
-    fused = (config["loss"] in FUSABLE_LOSSES and config["encoder"]["embedding"] == "gauss"
+    enc_ok = config["encoder"]["embedding"] == ("none" if config["model"] == "WIRE" else "gauss")
+    fused = (config["loss"] in FUSABLE_LOSSES and enc_ok
              and not config.get("use_tv", False) and not config.get("per_coil", False))
     trainer = None
     if fused:

@@ -1,0 +1,139 @@
+"""Multi-scale k-space training -- drop-in for the reference's src/train_kspace_multiscale.py (same CLI and config keys).
+
+The model body (nine filter GEMMs + eight linear GEMMs per batch and their backward) runs on the B200 engine through
+MultiscaleKFourier's autograd face; the composite loss of the reference loop (:164-201) -- per-head loss on the FULL
+target (`limit_kspace` is a no-op there), 0.1 * ConsistencyLoss, optional TV on the last head -- stays in PyTorch on
+the [bs, 2] head outputs.  `model: BoundedFourier` is rejected until dist_to_center is plumbed through the C ABI."""
+import argparse
+import os
+import sys
+
+import torch
+from torch.optim.lr_scheduler import LambdaLR
+
+_SRC = os.path.dirname(os.path.abspath(__file__))
+if _SRC not in sys.path:
+    sys.path.insert(0, _SRC)
+
+from models.networks import Positional_Encoder                               # noqa: E402
+from models.mfn import MultiscaleKFourier, MultiscaleBoundedFourier           # noqa: E402
+from metrics.losses import ConsistencyLoss, HDRLoss_FF, LogSpaceLoss, MSLELoss, TanhL2Loss, tv_loss  # noqa: E402
+from data.slices import get_data_loader                                      # noqa: E402
+from utils import get_config, set_default_configs                            # noqa: E402
+from mri_implicit_neural_representations_b200 import metrics as M            # noqa: E402
+from mri_implicit_neural_representations_b200.trainer import FusedAdam       # noqa: E402
+
+
+def create_pairs(radii):
+    """reference :42-47 -- discs (0, r_i), the last one open to 5."""
+    pairs = [(0, float(r)) for r in radii[:-1]] + [(0, 5)]
+    return pairs
+
+
+def partition_radii(dist, magnitude, no_steps=40, no_models=4):
+    """Ring partition of k-space (reference src/clustering.py:19-92): `no_steps` equal-width rings, k-means of their
+    log mean magnitude into `no_models` contiguous groups; returns the outer radius of every group."""
+    import numpy as np
+    from sklearn.cluster import KMeans
+    edges = torch.linspace(0, float(dist.max()) + 1e-6, no_steps + 1)
+    means = []
+    for i in range(no_steps):
+        sel = (dist >= edges[i]) & (dist < edges[i + 1])
+        means.append(float(torch.log(magnitude[sel].mean() + 1e-12)) if sel.any() else -30.0)
+    km = KMeans(n_clusters=no_models, n_init=10, random_state=0).fit(np.array(means)[:, None])
+    labels = km.labels_
+    radii, cur = [], labels[0]
+    for i in range(1, no_steps):
+        if labels[i] != cur and len(radii) < no_models - 1:
+            radii.append(float(edges[i]))
+            cur = labels[i]
+    while len(radii) < no_models - 1:
+        radii.append(float(edges[(len(radii) + 1) * no_steps // no_models]))
+    return radii + [float(edges[-1])]
+
+
+def training_multiscale(config, dataset, data_loader, val_loader, output_path=".", verbose=True):
+    if not torch.cuda.is_available():
+        raise RuntimeError("this engine has no CPU fallback: a CUDA device (B200) is required")
+    device = torch.device("cuda")
+    max_epoch = config["max_epoch"]
+    C, H, W, S = dataset.img_shape
+    train_ds = data_loader.ds
+    mag = train_ds.image.pow(2).sum(-1).sqrt()
+    radii = partition_radii(train_ds.dist_to_center, mag, config["partition"]["no_steps"], config["partition"]["no_models"])
+    pairs = create_pairs(radii)
+    encoder = Positional_Encoder(config["encoder"], device=device)
+    if config["model"] == "Fourier":
+        model = MultiscaleKFourier(config["net"])
+    elif config["model"] == "BoundedFourier":
+        model = MultiscaleBoundedFourier(config["net"])
+    else:
+        raise NotImplementedError(config["model"])
+    model.to(device)
+    model.train()
+    optim = FusedAdam(model, lr=config["lr"], betas=(config["beta1"], config["beta2"]), weight_decay=config["weight_decay"])
+    loss_name = config["loss"]
+    if loss_name == "L2":
+        loss_fn = torch.nn.MSELoss()
+    elif loss_name == "LSL":
+        loss_fn = LogSpaceLoss(config["loss_opts"])
+    elif loss_name == "MSLE":
+        loss_fn = MSLELoss()
+    elif loss_name == "HDR":
+        loss_fn = HDRLoss_FF(config["loss_opts"])
+    elif loss_name == "tanh":
+        loss_fn = TanhL2Loss()
+    else:
+        raise NotImplementedError(loss_name)
+    consistency = ConsistencyLoss(pairs)
+    scheduler = LambdaLR(optim, lambda x: 0.2 ** min(x / max_epoch, 1))
+    gt_image = M.reconstruct(dataset.image.to(device), (C, H, W), config["transform"])
+    history = []
+    for epoch in range(max_epoch):
+        for it, (coords, gt, dist, mask_coords) in enumerate(data_loader):
+            kcoords = coords.to(device)
+            gt = gt.to(device)
+            dist = dist.to(device)
+            outs = model(coords=encoder.embedding(kcoords), dist_to_center=dist)
+            optim.zero_grad()
+            loss = 0
+            if len(mask_coords) != 0 and config["use_tv"]:
+                loss = loss + tv_loss(outs[-1].view((H, W, 2)))
+            if len(mask_coords) != 0:
+                sel = mask_coords.to(device)[:, 0]
+                outs = [o[sel] for o in outs]
+                gt, dist = gt[sel], dist[sel]
+            loss = loss + 0.1 * consistency(outs, dist)
+            for o in outs:                      # every head is supervised on the FULL target (reference :34-39 no-op)
+                if loss_name in ("HDR", "tanh"):
+                    l, _ = loss_fn(o, gt, kcoords)
+                    loss = loss + l
+                else:
+                    loss = loss + 0.5 * loss_fn(o, gt)
+            loss.backward()
+            optim.step()
+        if (epoch + 1) % config["val_epoch"] == 0:
+            model.eval()
+            with torch.no_grad():
+                flat = torch.cat([model(coords=encoder.embedding(c.to(device)))[-1] for c, _, _, _ in val_loader])
+                recon = M.reconstruct(flat, (C, H, W), config["transform"])
+                history.append((epoch + 1, float(loss), float(M.psnr(gt_image, recon)), float(M.ssim(gt_image, recon))))
+            if verbose:
+                print("[Validation Epoch: {}/{}] loss {:.4g} psnr {:.4g} ssim {:.4g}".format(epoch + 1, max_epoch, *history[-1][1:]))
+            model.train()
+        scheduler.step()
+    return history
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--config", type=str, default="src/config/config_image.yaml", help="Path to the config file.")
+    parser.add_argument("--output_path", type=str, default=".", help="outputs path")
+    opts = parser.parse_args()
+    config = set_default_configs(get_config(opts.config))
+    dataset, data_loader, val_loader = get_data_loader(
+        data=config["data"], data_root=config["data_root"], set=config["set"], batch_size=config["batch_size"],
+        transform=config["transform"], num_workers=0, sample=config["sample"], slice=config["slice"], shuffle=True,
+        full_norm=config["full_norm"], normalization=config["normalization"], undersampling=config["undersampling"],
+        use_dists="yes", per_coil=config["per_coil"])
+    training_multiscale(config, dataset, data_loader, val_loader, opts.output_path)
