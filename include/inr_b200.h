@@ -129,6 +129,15 @@ int inr_forward(const inr_plan* plan, const float* params, const void* wpack, co
 int inr_backward(const inr_plan* plan, const float* params, const void* wpack, const float* dout,
                  int64_t bs, void* workspace, float* grads, void* stream);
 
+/* multiscale MFN variants of inr_forward / inr_backward with the per-row distance to the k-space centre
+ * (reference MultiscaleBoundedFourier.forward(coords, dist_to_center), src/models/mfn.py:344-356; BoundedLinear :281-286
+ * with a 1-D dist: whole rows are zeroed).  `out` / `dout` have n_heads * out_features columns, heads in stage order. */
+int inr_forward_dist(const inr_plan* plan, const float* params, const void* wpack, const float* input,
+                     const float* encB, const float* dist, int64_t bs, void* workspace, float* out, int32_t train,
+                     void* stream);
+int inr_backward_dist(const inr_plan* plan, const float* params, const void* wpack, const float* dout,
+                      const float* dist, int64_t bs, void* workspace, float* grads, void* stream);
+
 /* replaces: optim.step() (+ regulariser gradient), src/train.py:185-190; re-packs the fp16 copies. */
 int inr_adam_step(const inr_plan* plan, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                   void* wpack, const float* hyper_dev, const int32_t* step_dev, void* stream);

@@ -38,7 +38,8 @@ LOSS = {"none": 0, "L2": 1, "L1": 2, "MSLE": 3, "tanh": 4, "LSL": 5, "HDR": 6}
 # every symbol include/inr_b200.h declares (tests check the library exports all of them)
 EXPORTS = ["inr_last_error", "inr_plan_create", "inr_plan_destroy", "inr_plan_param_count",
            "inr_plan_tensor_count", "inr_plan_tensor", "inr_wpack_bytes", "inr_workspace_bytes",
-           "inr_scalars_offset", "inr_workspace_layout", "inr_pack_weights", "inr_forward", "inr_backward", "inr_adam_step",
+           "inr_scalars_offset", "inr_workspace_layout", "inr_pack_weights", "inr_forward", "inr_backward",
+           "inr_forward_dist", "inr_backward_dist", "inr_adam_step",
            "inr_train_step", "inr_grad_step", "inr_profile_step", "inr_debug_set_trace", "inr_selftest_umma"]
 
 
@@ -62,6 +63,8 @@ def _load():
     lib.inr_pack_weights.argtypes = [vp, vp, vp, vp]
     lib.inr_forward.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp]
     lib.inr_backward.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+    lib.inr_forward_dist.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, vp]
+    lib.inr_backward_dist.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp]
     lib.inr_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.inr_train_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp,
                                    vp, vp, vp]

@@ -478,8 +478,6 @@ static void wire_adam_fill(const inr_plan* p, WireAdamArgs& a) {
 // MFN (multiplicative filter network) path: FourierNet, MultiscaleKFourier, MultiscaleBoundedFourier
 // =====================================================================================================================
 static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
-  if (d->model == INR_MODEL_MS_BOUNDED_FOURIER)
-    return fail(INR_EUNSUPPORTED, "MultiscaleBoundedFourier: the dist_to_center input is not plumbed through the C ABI yet");
   if (d->width % kMfnNT != 0 || d->width > 512 || d->width < 128) return fail(INR_EUNSUPPORTED, "MFN kernels are built for network_width 128..512, multiple of 128");
   if (d->in_features % 128 != 0 || d->in_features > 1024) return fail(INR_EUNSUPPORTED, "MFN network_input_size must be a multiple of 128");
   if (d->depth < 1 || d->depth + 1 > kMfnMaxStages) return fail(INR_EINVAL, "network_depth out of range");
@@ -554,8 +552,18 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
         u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
         u.b_tile_stride = wtile; u.b_sub = nc * 32768; u.b_bytes = 32768;
         u.n = 128; u.out_off = M.lin_w[i]; u.out_ld = W; u.row0 = mc * 128; u.col0 = nc * 128;
-        u.rows_valid = 128; u.cols_valid = 128; u.bias_off = nc == 0 ? M.lin_b[i] : -1;
+        u.rows_valid = 128; u.cols_valid = 128; u.bias_off = (nc == 0 && !M.bounded) ? M.lin_b[i] : -1;
         p->units.push_back(u); p->unit_layer.push_back(100 + i);
+      }
+  if (M.bounded)                           // db_i = sum_rows of the UNMASKED dh_i: D[o][0] against a ones operand
+    for (int i = 1; i <= M.top; ++i)
+      for (int mc = 0; mc < wc; ++mc) {
+        WgradUnit u{};
+        u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+        u.b_tile_stride = 0; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+        u.n = kDzLastCols; u.out_off = M.lin_b[i]; u.out_ld = 1; u.row0 = mc * 128; u.col0 = 0;
+        u.rows_valid = 128; u.cols_valid = 1; u.bias_off = -1;
+        p->units.push_back(u); p->unit_layer.push_back(400 + i);
       }
   for (int i = 0; i <= M.top; ++i)          // dOm_i = DP[i]^T X, dphi_i = sum DP[i]
     for (int mc = 0; mc < wc; ++mc)
@@ -605,6 +613,10 @@ static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs) {
   for (int i = 0; i <= M.top; ++i) { w.z[i] = o; o += wimg; w.g[i] = o; o += wimg; w.cp[i] = o; o += wimg; w.dp[i] = o; o += wimg; }
   for (int i = 1; i <= M.top; ++i) { w.h[i] = o; o += wimg; w.dh[i] = o; o += wimg; }
   for (int k = 0; k < M.n_out; ++k) { w.dout[k] = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024); }
+  if (M.bounded) {
+    for (int i = 1; i <= M.top; ++i) { w.dhu[i] = o; o += wimg; }
+    w.ones = o; o += 4096;
+  }
   w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * M.n_params * 4, 1024);
   w.total = o;
   return w;
@@ -659,6 +671,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
   const MfnModel& M = p->mm;
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
+  if (M.bounded && !dist) return fail(INR_EINVAL, "BoundedFourier needs dist_to_center");
   MfnAuxArgs x; mfn_aux_fill(p, w, x, params, ws, bs);
   x.loss = loss; x.dout = dout; x.dist = dist; x.hyper = hyper; x.step = step;
   cudaError_t e;
@@ -676,6 +689,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
     g.real_first = (i - 1 == 0) ? 1 : 0;
     g.in_y = W + w.g[i - 1]; g.in_ab = W + w.cp[i - 1]; g.in_h = i - 1 >= 1 ? W + w.h[i - 1] : nullptr;
     g.out_dz = i - 1 >= 1 ? W + w.dh[i - 1] : nullptr; g.out_dp = W + w.dp[i - 1];
+    g.out_dzu = (M.bounded && i - 1 >= 1) ? W + w.dhu[i - 1] : nullptr;
     g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = i; g.dst_layer = i - 1;
     g.feat_tile_bytes = wtile; g.bs = static_cast<int>(bs); g.out_f = M.out_f;
     if (dout && M.stage_head[i - 1] >= 0) {
@@ -683,7 +697,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
       for (int k = 0; k < M.n_heads; ++k) if (M.head_live[k]) { if (seen == M.stage_head[i - 1]) { kk = k; break; } ++seen; }
       g.head_dout = dout; g.head_w = params + M.head_w[kk]; g.head_col = M.stage_head[i - 1] * M.out_f; g.head_ld = M.n_out * M.out_f;
     }
-    if (M.bounded) { g.dist = dist; g.bound_lo = M.bound_lo[i]; g.bound_hi = M.bound_hi[i]; }
+    if (M.bounded && i - 1 >= 1) { g.dist = dist; g.bound_lo = M.bound_lo[i - 1]; g.bound_hi = M.bound_hi[i - 1]; }
     e = launch_lgemm(g, p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn dgrad)");
   }
@@ -692,7 +706,8 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
   for (int i = 0; i < wg.n_units; ++i) {
     WgradUnit u = p->units[i];
     const int code = p->unit_layer[i];
-    if (code >= 300) { const int k = code - 300; u.a_off = w.z[M.head_stage[k]]; u.b_off = w.dout[M.stage_head[M.head_stage[k]]]; }
+    if (code >= 400) { u.a_off = w.dhu[code - 400]; u.b_off = w.ones; }
+    else if (code >= 300) { const int k = code - 300; u.a_off = w.z[M.head_stage[k]]; u.b_off = w.dout[M.stage_head[M.head_stage[k]]]; }
     else if (code >= 200) { u.a_off = w.dp[code - 200]; u.b_off = w.x; }
     else { const int s = code - 100; u.a_off = w.dh[s]; u.b_off = w.z[s - 1]; }
     wg.u[i] = u;
@@ -753,6 +768,35 @@ extern "C" int inr_forward(const inr_plan* p, const float* params, const void* w
   LossDesc none{LOSS_NONE, 0.f, 0.f, 0.f};
   return run_forward(p, w, none, params, wpack, gauss ? input : nullptr, gauss ? nullptr : input, encB, nullptr, nullptr, bs,
                      workspace, out, train ? 1 : 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int inr_forward_dist(const inr_plan* p, const float* params, const void* wpack, const float* input, const float* encB,
+                                const float* dist, int64_t bs, void* workspace, float* out, int32_t train, void* stream) {
+  if (!p || !params || !wpack || !input || !out || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
+  if (!p->is_mfn) return fail(INR_EINVAL, "inr_forward_dist is for the multiscale MFN models");
+  const bool mg = p->mm.input_kind == INPUT_GAUSS;
+  if (mg && !encB) return fail(INR_EINVAL, "gauss encoder needs encB");
+  const MfnWorkspace mw = mfn_workspace(p, bs);
+  return mfn_forward_impl(p, mw, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, mg ? input : nullptr, mg ? nullptr : input, encB,
+                          nullptr, nullptr, dist, bs, workspace, out, train ? 1 : 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int inr_backward_dist(const inr_plan* p, const float* params, const void* wpack, const float* dout, const float* dist,
+                                 int64_t bs, void* workspace, float* grads, void* stream) {
+  if (!p || !params || !wpack || !dout || !workspace || !grads || bs <= 0) return fail(INR_EINVAL, "bad argument");
+  if (!p->is_mfn) return fail(INR_EINVAL, "inr_backward_dist is for the multiscale MFN models");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const MfnWorkspace mw = mfn_workspace(p, bs);
+  int rcm = mfn_backward_impl(p, mw, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, dout, dist, bs, workspace, nullptr, nullptr, st);
+  if (rcm) return rcm;
+  AdamArgs ma; fill_adam(p, ma);
+  ma.n_split = mw.n_split; ma.n_tiles = mw.n_tiles;
+  ma.params = const_cast<float*>(params); ma.grads = grads;
+  ma.gpart = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.gpart);
+  ma.scal = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.scal);
+  ma.do_adam = 0;
+  cudaError_t me = launch_adam(ma, st);
+  return me == cudaSuccess ? INR_OK : cuda_fail(me, "adam_kernel(reduce, mfn)");
 }
 
 static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& loss, const float* params, const void* wpack,

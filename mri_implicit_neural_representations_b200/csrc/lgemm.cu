@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             unpack8(g4, g); unpack8(c4, c); unpack8(h4, h);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float dz = masked ? 0.f : ratio * vp[e];     // masked rows fed zeros to this linear: no gradient flows back
+              float dz = ratio * vp[e];    // rows masked in the source stage arrive as zeros (its stored dh is masked)
               if (a.head_dout) {
 #pragma unroll
                 for (int o = 0; o < kMaxOut; ++o)
@@ -275,7 +275,14 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               else { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; }
               amax = fmaxf(amax, fmaxf(fabsf(dh[e]), fabsf(dp[e])));
             }
-            if (!a.real_first) st_global_v4(a.out_dz + off, pack8(dh));
+            if (!a.real_first) {
+              if (a.out_dzu) st_global_v4(a.out_dzu + off, pack8(dh));     // unmasked copy: bias gradient
+              if (masked) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dh[e] = 0.f;                    // this row fed zeros to the target stage's linear
+              }
+              st_global_v4(a.out_dz + off, pack8(dh));
+            }
             st_global_v4(a.out_dp + off, pack8(dp));
           }
         }

@@ -40,6 +40,8 @@ struct MfnModel {
 struct MfnWorkspace {
   uint64_t x, z[kMfnMaxStages], g[kMfnMaxStages], cp[kMfnMaxStages], h[kMfnMaxStages], dh[kMfnMaxStages], dp[kMfnMaxStages];
   uint64_t dout[kMfnMaxStages];      // per live head
+  uint64_t dhu[kMfnMaxStages];       // bounded: dh with NO row mask (bias gradient); dh[] then holds the masked rows
+  uint64_t ones;                     // bounded: [128 x 16] fp16 ones, B operand of the bias units
   uint64_t gl, part, scal, gpart, total;
   int n_tiles, n_split;
 };

@@ -246,8 +246,23 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
       else { dh[e] = 0.f; dp[e] = dz * c[e]; }
       amax = fmaxf(amax, fmaxf(fabsf(dh[e]), fabsf(dp[e])));
     }
-    if (top >= 1) st_global_v4(dhimg + off, mfn_pack8(dh));
+    if (top >= 1) {
+      if (M.bounded) {
+        st_global_v4(a.ws + a.w.dhu[top] + static_cast<size_t>(tile) * tile_bytes + off, mfn_pack8(dh));
+        bool masked = false;
+        if (grow < a.bs) { const float dd = a.dist[grow]; masked = (dd < M.bound_lo[top]) || (dd > M.bound_hi[top]); }
+        if (masked) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dh[e] = 0.f;
+        }
+      }
+      st_global_v4(dhimg + off, mfn_pack8(dh));
+    }
     st_global_v4(dpimg + off, mfn_pack8(dp));
+    if (M.bounded && kg < 2) {        // ones image [128 x 16] for the bias units (identical for every tile)
+      const uint32_t one2 = 0x3C003C00u;
+      st_global_v4(a.ws + a.w.ones + static_cast<size_t>(kg) * 2048 + row * 16, make_uint4(one2, one2, one2, one2));
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));

@@ -59,6 +59,7 @@ struct LGemmArgs {
   const uint8_t* in_h;      // MFN_DGRAD: h of the target stage
   uint8_t* out_dz;          // WIRE_DGRAD: dZ image of the target layer.  MFN_DGRAD: dh image of the target stage
   uint8_t* out_dp;          // MFN_DGRAD: dp image of the target stage
+  uint8_t* out_dzu;         // MFN_DGRAD, bounded: dh of the target stage without its row mask (bias gradient) or null
   const float* scal;        // DGRAD: step scalars (per-layer scales at SC_LAYER_SCALE, amax at SC_LAYER_AMAX)
   int src_layer, dst_layer; // DGRAD: A holds S[src] * grad_src, the epilogue stores S[dst] * grad_dst
   // MFN_DGRAD head-gradient injection and BoundedLinear masking
@@ -66,7 +67,8 @@ struct LGemmArgs {
   const float* head_w;      // [out_f, width] weight of the head attached to the target stage
   int head_col, head_ld, out_f, bs;
   const float* dist;        // BoundedLinear: per-row distance [rows] or null
-  float bound_lo, bound_hi; // rows with dist < lo or dist > hi are zeroed before this stage's linear
+  float bound_lo, bound_hi; // FWD: rows with dist outside [lo, hi] are zeroed before THIS stage's linear;
+                            // DGRAD: the same mask of the TARGET stage, applied to the stored dh (W-wgrad and dgrad operand)
   uint32_t feat_tile_bytes; // bytes of one 128-row image of the epilogue's feature images (MFN: 128 * width * 2)
 };
 

@@ -168,18 +168,29 @@ class ChainEngine:
         L.check(L.lib.inr_pack_weights(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _stream()), "inr_pack_weights")
 
     # ---- unfused API (keeps arbitrary PyTorch losses working) --------------------------------------
-    def forward(self, inp: torch.Tensor, train: bool = False) -> torch.Tensor:
+    def forward(self, inp: torch.Tensor, train: bool = False, dist: Optional[torch.Tensor] = None) -> torch.Tensor:
         bs = inp.shape[0]
         assert bs <= self.max_batch
         inp = inp.to(self.device, torch.float32).contiguous()
         out = torch.zeros(bs, self.plan.out_cols, dtype=torch.float32, device=self.device)
+        if dist is not None:
+            dist = dist.to(self.device, torch.float32).contiguous()
+            L.check(L.lib.inr_forward_dist(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(inp), _ptr(self.encB),
+                                           _ptr(dist), bs, _ptr(self.workspace), _ptr(out), 1 if train else 0, _stream()),
+                    "inr_forward_dist")
+            return out
         L.check(L.lib.inr_forward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(inp), _ptr(self.encB), bs,
                                   _ptr(self.workspace), _ptr(out), 1 if train else 0, _stream()), "inr_forward")
         return out
 
-    def backward(self, dout: torch.Tensor) -> torch.Tensor:
+    def backward(self, dout: torch.Tensor, dist: Optional[torch.Tensor] = None) -> torch.Tensor:
         bs = dout.shape[0]
         dout = dout.to(self.device, torch.float32).contiguous()
+        if dist is not None:
+            dist = dist.to(self.device, torch.float32).contiguous()
+            L.check(L.lib.inr_backward_dist(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(dout), _ptr(dist), bs,
+                                            _ptr(self.workspace), _ptr(self.grads), _stream()), "inr_backward_dist")
+            return self.grads
         L.check(L.lib.inr_backward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(dout), bs,
                                    _ptr(self.workspace), _ptr(self.grads), _stream()), "inr_backward")
         return self.grads

@@ -36,10 +36,11 @@ class _Wrap(nn.Module):
 
 class _ChainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, module, *params):
-        need_grad = any(ctx.needs_input_grad[2:])      # grad mode is off inside Function.forward; ask autograd instead
-        out = module._engine_forward(x, train=need_grad)
+    def forward(ctx, x, module, dist, *params):
+        need_grad = any(ctx.needs_input_grad[3:])      # grad mode is off inside Function.forward; ask autograd instead
+        out = module._engine_forward(x, train=need_grad, dist=dist)
         ctx.module = module
+        ctx.dist = dist
         ctx.bs = x.shape[0]
         ctx.save_for_backward(out)
         return out
@@ -53,10 +54,10 @@ class _ChainFn(torch.autograd.Function):
             dz = dout * (1 - out * out)
         elif m._last_act == "sigmoid":
             dz = dout * out * (1 - out)
-        grads = m._engine_backward(dz.contiguous(), ctx.bs)
+        grads = m._engine_backward(dz.contiguous(), ctx.bs, dist=ctx.dist)
         dead = m._dead_param_flags()
-        return (None, None, *[g.clone() if (need and not d) else None
-                              for g, need, d in zip(grads, ctx.needs_input_grad[2:], dead)])
+        return (None, None, None, *[g.clone() if (need and not d) else None
+                                    for g, need, d in zip(grads, ctx.needs_input_grad[3:], dead)])
 
 
 class FusedChain(nn.Module):
@@ -174,17 +175,17 @@ class FusedChain(nn.Module):
         eng = next(iter(self._engines.values()))
         return [frozen for (_, frozen) in eng.plan.tensor_flags]
 
-    def _engine_forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
+    def _engine_forward(self, x: torch.Tensor, train: bool, dist=None) -> torch.Tensor:
         eng = self.engine(None, x.shape[0])
-        return eng.forward(x, train=train)
+        return eng.forward(x, train=train, dist=dist)
 
-    def _engine_backward(self, dz: torch.Tensor, bs: int):
+    def _engine_backward(self, dz: torch.Tensor, bs: int, dist=None):
         eng = self.engine(None, bs)
-        eng.backward(dz)
+        eng.backward(dz, dist=dist)
         return self._views(eng.grads)
 
     def forward(self, x):
-        return _ChainFn.apply(x, self, *self._params_in_order())
+        return _ChainFn.apply(x, self, None, *self._params_in_order())
 
 
 class SIREN(FusedChain):
@@ -306,7 +307,7 @@ class FourierNet(FusedChain):
         return lins + heads + [f.linear for f in self.filters]
 
     def forward(self, x, dist_to_center=None):
-        return _ChainFn.apply(x, self, *self._params_in_order())
+        return _ChainFn.apply(x, self, None, *self._params_in_order())
 
 
 class MultiscaleKFourier(FourierNet):
@@ -326,7 +327,41 @@ class MultiscaleKFourier(FourierNet):
         return self.net["network_depth"] + 1
 
     def forward(self, coords, **args):
-        out = _ChainFn.apply(coords, self, *self._params_in_order())
+        out = _ChainFn.apply(coords, self, None, *self._params_in_order())
+        f = self.net["network_output_size"]
+        return [out[:, f * k:f * (k + 1)] for k in range(len(self.output_layers))]
+
+
+class _BoundedHolder(nn.Module):
+    def __init__(self, weight, bias, bounds):
+        super().__init__()
+        self.linear = _Leaf(weight, bias)
+        self.bounds = bounds
+
+
+class MultiscaleBoundedFourier(MultiscaleKFourier):
+    """reference src/models/mfn.py:288-356 -- BoundedLinear layers (keys linear.<i>.linear.{weight,bias}) zero the rows whose
+    distance to the k-space centre lies outside `boundaries[i]` before linear i (1-D dist_to_center: whole rows)."""
+    MODEL = "BoundedFourier"
+
+    def __init__(self, params, weight_scale=1.0, bias=True, output_act=False, centered=True, output_layers=(1, 3, 5, 7),
+                 reuse_filters=False, boundaries=None):
+        params = dict(params)
+        if boundaries is None or len(boundaries) < params["network_depth"]:
+            raise L.InrError("MultiscaleBoundedFourier needs one (lo, hi) boundary per linear layer")
+        params["boundaries"] = [tuple(float(v) for v in b) for b in boundaries]
+        MultiscaleKFourier.__init__(self, params, weight_scale, bias, output_act, centered, output_layers, reuse_filters)
+
+    def _lin_holder(self, w, b):
+        return _BoundedHolder(w, b, None)
+
+    def forward(self, coords, dist_to_center=None):
+        if dist_to_center is None:
+            raise L.InrError("MultiscaleBoundedFourier.forward needs dist_to_center")
+        d = dist_to_center
+        if d.dim() != 1:
+            raise L.InrError("only the 1-D dist_to_center convention (whole rows zeroed) is built; the per-coil [HW,1] quirk is not")
+        out = _ChainFn.apply(coords, self, d.to(coords.device, torch.float32).contiguous(), *self._params_in_order())
         f = self.net["network_output_size"]
         return [out[:, f * k:f * (k + 1)] for k in range(len(self.output_layers))]
 

@@ -1,5 +1,5 @@
 """Drop-in for the reference's src/models/mfn.py: FourierNet and MultiscaleKFourier run on the B200 engine (same
-constructor arguments and state_dict keys).  GaborNet / KGaborNet / MultiscaleBoundedFourier are not built yet."""
+constructor arguments and state_dict keys).  GaborNet / KGaborNet are not built yet."""
 import os
 import sys
 
@@ -7,7 +7,8 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from mri_implicit_neural_representations_b200.modules import FourierNet, MultiscaleKFourier  # noqa: E402,F401
+from mri_implicit_neural_representations_b200.modules import (FourierNet, MultiscaleBoundedFourier,  # noqa: E402,F401
+                                                                MultiscaleKFourier)
 
 
 def _not_built(name):
@@ -20,4 +21,3 @@ def _not_built(name):
 
 GaborNet = _not_built("GaborNet")
 KGaborNet = _not_built("KGaborNet")
-MultiscaleBoundedFourier = _not_built("MultiscaleBoundedFourier")

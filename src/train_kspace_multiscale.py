@@ -3,7 +3,7 @@
 The model body (nine filter GEMMs + eight linear GEMMs per batch and their backward) runs on the B200 engine through
 MultiscaleKFourier's autograd face; the composite loss of the reference loop (:164-201) -- per-head loss on the FULL
 target (`limit_kspace` is a no-op there), 0.1 * ConsistencyLoss, optional TV on the last head -- stays in PyTorch on
-the [bs, 2] head outputs.  `model: BoundedFourier` is rejected until dist_to_center is plumbed through the C ABI."""
+the [bs, 2] head outputs."""
 import argparse
 import os
 import sys
@@ -66,7 +66,8 @@ def training_multiscale(config, dataset, data_loader, val_loader, output_path=".
     if config["model"] == "Fourier":
         model = MultiscaleKFourier(config["net"])
     elif config["model"] == "BoundedFourier":
-        model = MultiscaleBoundedFourier(config["net"])
+        pairs_model = [p_ for p_ in pairs for _ in (0, 1)]          # reference :85,:96 -- each disc twice -> 8 BoundedLinears
+        model = MultiscaleBoundedFourier(config["net"], boundaries=pairs_model)
     else:
         raise NotImplementedError(config["model"])
     model.to(device)

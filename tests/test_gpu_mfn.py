@@ -154,3 +154,37 @@ def test_multiscale_module_composite_loss_vs_torch(inr):
         else:
             # LSL's 1/(|x|+eps)^2 weighting is evaluated on the engine's own (fp16-operand) outputs: not teacher-forced
             assert rel(named[k].grad, P[k].grad) <= 5e-3, (k, rel(named[k].grad, P[k].grad))
+
+
+def test_bounded_fourier_forward_and_gradients(inr):
+    """MultiscaleBoundedFourier (BASELINE config 4's model): BoundedLinear row masks from a 1-D dist_to_center, heads and
+    every parameter gradient vs torch autograd on the oracle (reference mfn.py:281-286,344-356)."""
+    from mri_implicit_neural_representations_b200.modules import MultiscaleBoundedFourier, Positional_Encoder
+    torch.manual_seed(43)
+    enc = Positional_Encoder(G.ENC_GAUSS, device="cuda")
+    radii = [(0, 0.45), (0, 0.8), (0, 1.1), (0, 5)]
+    bounds = [p for p in radii for _ in (0, 1)]
+    model = MultiscaleBoundedFourier(dict(G.NET_MFN), boundaries=bounds).to("cuda")
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    assert "linear.0.linear.weight" in sd
+    bs = 700
+    coords = torch.rand(bs, 3) * 2 - 1
+    dist = torch.sqrt(coords[:, 1] ** 2 + coords[:, 2] ** 2)
+    outs = model(coords=enc.embedding(coords.cuda()), dist_to_center=dist.cuda())
+    g0 = torch.Generator().manual_seed(9)
+    douts = [torch.randn(bs, 2, generator=g0) * 1e-3 for _ in outs]
+    torch.autograd.backward(outs, [d.cuda() for d in douts])
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = O.encode(coords, enc.B.cpu(), "gauss")
+    routs = O.multiscale_forward(P, x, 8, dist, bounds)
+    for a, b in zip(outs, routs):
+        assert rel(a, b) <= TOL
+    grs = torch.autograd.grad(routs, list(P.values()), grad_outputs=douts, allow_unused=True)
+    named = dict(model.named_parameters())
+    frac_masked = float(((dist < 0) | (dist > 0.45)).float().mean())
+    assert 0.2 < frac_masked < 0.95          # the masks actually bite in this draw
+    for k, ref in zip(P.keys(), grs):
+        if ref is None:
+            assert named[k].grad is None, k
+        else:
+            assert rel(named[k].grad, ref) <= 1.5e-3, (k, rel(named[k].grad, ref))
