@@ -91,13 +91,15 @@ __global__ void __launch_bounds__(256) wire_first_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------ final layer + loss
-__global__ void __launch_bounds__(128) wire_last_kernel(const __grid_constant__ WireAuxArgs a) {
+__global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ WireAuxArgs a) {
   __shared__ float sWr[kMaxOut][kWP], sWi[kMaxOut][kWP];
   __shared__ float red[4][8];
+  __shared__ float s_part[3][kTileM][kMaxOut];
   const WireModel& M = a.m;
-  const int tile = blockIdx.x, row = threadIdx.x, lane = row & 31, q = row >> 5;
+  // 4 threads per row, each reduces 6 of the 24 feature groups (independent 16-byte loads in flight), then one combines
+  const int tile = blockIdx.x, row = threadIdx.x & (kTileM - 1), part = threadIdx.x >> 7, lane = row & 31, q = row >> 5;
   const int L = M.depth + 1;
-  for (int i = row; i < kMaxOut * kWP; i += 128) {
+  for (int i = threadIdx.x; i < kMaxOut * kWP; i += 512) {
     const int o = i / kWP, j = i % kWP;
     const bool ok = o < M.out_f && j < M.c;
     sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
@@ -111,7 +113,8 @@ __global__ void __launch_bounds__(128) wire_last_kernel(const __grid_constant__ 
   const uint8_t* hhi = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
   const uint8_t* hlo = a.ws + a.w.hlo[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
   float acc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
-  for (int kg = 0; kg < kWP / 8; ++kg) {
+#pragma unroll 2
+  for (int kg = part * (kWP / 32); kg < (part + 1) * (kWP / 32); ++kg) {
     float rh[8], rl[8], ih[8], il[8];
     wire_unpack8(ld_global_nc_v4(hhi + static_cast<size_t>(kg) * 2048), rh);
     wire_unpack8(ld_global_nc_v4(hlo + static_cast<size_t>(kg) * 2048), rl);
@@ -125,10 +128,17 @@ __global__ void __launch_bounds__(128) wire_last_kernel(const __grid_constant__ 
         if (o < M.out_f) acc[o] = fmaf(hr, sWr[o][kg * 8 + e], fmaf(-hi, sWi[o][kg * 8 + e], acc[o]));
     }
   }
+  if (part > 0) {
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) s_part[part - 1][row][o] = acc[o];
+  }
+  __syncthreads();
+  if (part > 0) return;
   float y[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, t[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o)
-    if (o < M.out_f) y[o] = acc[o] + a.params[M.b_off[L] + 2 * o];      // real part of the complex bias
+    if (o < M.out_f)      // fixed combination order; real part of the complex bias
+      y[o] = ((acc[o] + s_part[0][row][o]) + (s_part[1][row][o] + s_part[2][row][o])) + a.params[M.b_off[L] + 2 * o];
   if (valid && a.out)
     for (int o = 0; o < M.out_f; ++o) a.out[static_cast<size_t>(grow) * M.out_f + o] = y[o];
   if (!a.train) return;
@@ -159,7 +169,7 @@ __global__ void __launch_bounds__(128) wire_last_kernel(const __grid_constant__ 
     amA = fmaxf(amA, __shfl_xor_sync(0xffffffffu, amA, off)); amB = fmaxf(amB, __shfl_xor_sync(0xffffffffu, amB, off));
   }
   if (lane == 0) { red[q][0] = lA; red[q][1] = lB; red[q][2] = fs; red[q][3] = cnt; red[q][4] = amA; red[q][5] = amB; }
-  __syncthreads();
+  named_bar_sync(1, 128);
   if (row == 0) {
     float* pdst = reinterpret_cast<float*>(a.ws + a.w.part) + static_cast<size_t>(tile) * kPartialsPerTile;
     pdst[0] = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
@@ -295,7 +305,7 @@ cudaError_t launch_wire_first(const WireAuxArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_wire_last(const WireAuxArgs& a, cudaStream_t st) {
-  wire_last_kernel<<<a.w.n_tiles, 128, 0, st>>>(a);
+  wire_last_kernel<<<a.w.n_tiles, 512, 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_wire_scalars(const WireAuxArgs& a, cudaStream_t st) {
