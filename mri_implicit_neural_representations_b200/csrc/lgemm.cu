@@ -42,6 +42,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
 }
 
+template <int PASSES>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2];
@@ -50,11 +51,15 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = a.n_tiles * a.n_nblocks;
-  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 64;            // one B stage: nt rows x 32 K x 2 B
-  const uint32_t a_lo_off = kWStageABytes;
-  const uint32_t b_hi_off = a.passes == 3 ? 2 * kWStageABytes : kWStageABytes;
+  // A ring slot holds KS consecutive K=32 stages of every operand: 1 for the 3-pass GEMMs, 2 (K = 64) for the 1-pass
+  // GEMMs, so the single producer / MMA threads pay their per-slot barrier overhead half as often
+  constexpr int KS = PASSES == 3 ? 1 : 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 64 * KS;       // B part of a slot: KS x (nt rows x 32 K x 2 B)
+  constexpr uint32_t a_bytes = kWStageABytes * KS;
+  const uint32_t a_lo_off = a_bytes;
+  const uint32_t b_hi_off = PASSES == 3 ? 2 * a_bytes : a_bytes;
   const uint32_t b_lo_off = b_hi_off + b_bytes;
-  const uint32_t slot_bytes = a.passes == 3 ? 2 * (kWStageABytes + b_bytes) : (kWStageABytes + b_bytes);
+  const uint32_t slot_bytes = PASSES == 3 ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes);
   int n_slots = kLgRingBytes / slot_bytes;
   if (n_slots > kLgMaxSlots) n_slots = kLgMaxSlots;
 
@@ -84,24 +89,29 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t slot = 0, ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
-          const size_t a_off = static_cast<size_t>(tile) * S.a_tile_bytes;
-          const size_t b_off = static_cast<size_t>(nb) * S.k_stages * b_bytes;
-          for (int s = 0; s < S.k_stages; ++s, ++it) {
-            const uint32_t slot = it % n_slots, ph = (it / n_slots) & 1;
+          const int n_it = S.k_stages / KS;
+          const uint8_t* ah = S.a_hi + static_cast<size_t>(tile) * S.a_tile_bytes;
+          const uint8_t* al = PASSES == 3 ? S.a_lo + static_cast<size_t>(tile) * S.a_tile_bytes : nullptr;
+          const uint8_t* bh = S.b_hi + static_cast<size_t>(nb) * n_it * b_bytes;
+          const uint8_t* bl = PASSES == 3 ? S.b_lo + static_cast<size_t>(nb) * n_it * b_bytes : nullptr;
+          for (int s = 0; s < n_it; ++s) {
             mbar_wait(&empty[slot], ph ^ 1);
             mbar_arrive_expect_tx(&full[slot], slot_bytes);
             uint8_t* dst = smem + slot * slot_bytes;
-            bulk_g2s(dst, S.a_hi + a_off + static_cast<size_t>(s) * kWStageABytes, kWStageABytes, &full[slot]);
-            bulk_g2s(dst + b_hi_off, S.b_hi + b_off + static_cast<size_t>(s) * b_bytes, b_bytes, &full[slot]);
-            if (a.passes == 3) {
-              bulk_g2s(dst + a_lo_off, S.a_lo + a_off + static_cast<size_t>(s) * kWStageABytes, kWStageABytes, &full[slot]);
-              bulk_g2s(dst + b_lo_off, S.b_lo + b_off + static_cast<size_t>(s) * b_bytes, b_bytes, &full[slot]);
+            bulk_g2s(dst, ah, a_bytes, &full[slot]);
+            bulk_g2s(dst + b_hi_off, bh, b_bytes, &full[slot]);
+            if (PASSES == 3) {
+              bulk_g2s(dst + a_lo_off, al, a_bytes, &full[slot]);
+              bulk_g2s(dst + b_lo_off, bl, b_bytes, &full[slot]);
+              al += a_bytes; bl += b_bytes;
             }
+            ah += a_bytes; bh += b_bytes;
+            if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
           }
         }
       }
@@ -110,8 +120,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kTileM, a.nt, false, false);
-      const uint32_t b_lbo = static_cast<uint32_t>(a.nt) * 16, b_kstep = 2 * b_lbo;
-      uint32_t it = 0, n_done = 0;
+      const uint32_t b_lbo = static_cast<uint32_t>(a.nt) * 16;
+      // descriptors differ only in their 14-bit start-address field (bytes >> 4): build once, add offsets
+      const uint64_t da0 = umma_smem_desc(smem_u32(smem), 2048, 128);
+      const uint64_t db0 = umma_smem_desc(smem_u32(smem), b_lbo, 128);
+      const uint32_t bk16 = (2 * b_lbo) >> 4;                            // one K=16 step inside a B stage
+      const uint32_t bstage16 = (static_cast<uint32_t>(a.nt) * 64) >> 4;  // one K=32 stage of B
+      uint32_t slot = 0, ph = 0, n_done = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
         const uint32_t ab = n_done & 1, use = n_done >> 1;
         mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
@@ -119,24 +134,25 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
           const uint32_t acc = tmem + ab * 256 + S.acc_col;
-          for (int s = 0; s < S.k_stages; ++s, ++it) {
-            const uint32_t slot = it % n_slots;
-            mbar_wait(&full[slot], (it / n_slots) & 1);
+          const int n_it = S.k_stages / KS;
+          for (int s = 0; s < n_it; ++s) {
+            mbar_wait(&full[slot], ph);
             tc_fence_after();
-            const uint32_t base = smem_u32(smem + slot * slot_bytes);
+            const uint32_t so = (slot * slot_bytes) >> 4;
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const uint64_t dah = umma_smem_desc(base + kk * 4096, 2048, 128);
-              const uint64_t dbh = umma_smem_desc(base + b_hi_off + kk * b_kstep, b_lbo, 128);
-              umma_f16(acc, dah, dbh, idesc, (s | kk) != 0);
-              if (a.passes == 3) {
-                const uint64_t dal = umma_smem_desc(base + a_lo_off + kk * 4096, 2048, 128);
-                const uint64_t dbl = umma_smem_desc(base + b_lo_off + kk * b_kstep, b_lbo, 128);
+            for (int k = 0; k < 2 * KS; ++k) {          // K = 16 steps inside the slot
+              const uint64_t dah = da0 + so + k * 256;                                            // 4096 B per step
+              const uint64_t dbh = db0 + so + (b_hi_off >> 4) + (k >> 1) * bstage16 + (k & 1) * bk16;
+              umma_f16(acc, dah, dbh, idesc, (s | k) != 0);
+              if (PASSES == 3) {
+                const uint64_t dal = dah + (a_lo_off >> 4);
+                const uint64_t dbl = dbh + (b_bytes >> 4);
                 umma_f16(acc, dal, dbh, idesc, 1);
                 umma_f16(acc, dah, dbl, idesc, 1);
               }
             }
             umma_commit(&empty[slot]);
+            if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
           }
         }
         umma_commit(&acc_full[ab]);
@@ -308,11 +324,14 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   if (grid <= 0) return cudaSuccess;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(lgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
+    cudaError_t e = cudaFuncSetAttribute(lgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lgemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  lgemm_kernel<<<grid, kLgThreads, kLgSmem, stream>>>(a);
+  if (a.passes == 3) lgemm_kernel<3><<<grid, kLgThreads, kLgSmem, stream>>>(a);
+  else lgemm_kernel<1><<<grid, kLgThreads, kLgSmem, stream>>>(a);
   return cudaGetLastError();
 }
 
