@@ -123,18 +123,19 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   }
   M.n_params = off;
   M.wpack_bytes = woff;
-  // wgrad work units
+  // wgrad work units: 128 output features x up to 3 chunks of 128 input features per unit
   for (int l = 0; l < M.n_gemm; ++l) {
     const int K = l == 0 ? M.k0 : kWidth;
     for (int mh = 0; mh < kWidth / 128; ++mh)
-      for (int nc = 0; nc < K / 128; ++nc) {
+      for (int c0 = 0; c0 < K / 128; c0 += 3) {
+        const int nch = (K / 128 - c0) < 3 ? (K / 128 - c0) : 3;
         WgradUnit u{};
         u.a_tile_stride = kActBytes; u.a_sub = mh * 32768; u.a_bytes = 32768;
-        u.b_tile_stride = kTileM * K * 2; u.b_sub = nc * 32768; u.b_bytes = 32768;
-        u.n = 128; u.transposed = 0;
-        u.out_off = M.w_off[l]; u.out_ld = K; u.row0 = mh * 128; u.col0 = nc * 128;
-        u.rows_valid = 128; u.cols_valid = 128;
-        u.bias_off = nc == 0 ? M.b_off[l] : -1;
+        u.b_tile_stride = kTileM * K * 2; u.b_sub = c0 * 32768; u.b_bytes = 32768;
+        u.n = 128; u.n_chunks = nch; u.transposed = 0;
+        u.out_off = M.w_off[l]; u.out_ld = K; u.row0 = mh * 128; u.col0 = c0 * 128;
+        u.rows_valid = 128; u.cols_valid = 128 * nch;
+        u.bias_off = c0 == 0 ? M.b_off[l] : -1;
         u.perm_e = (l == 0 && M.input_kind == INPUT_GAUSS) ? M.enc_size : 0;
         p->units.push_back(u); p->unit_layer.push_back(l);
       }
@@ -330,17 +331,16 @@ static int wire_plan_create(const inr_model_desc* d, inr_plan** out) {
   M.gd_floats = go;
   // wgrad units (offsets into the workspace are filled per call)
   for (int l = 1; l <= M.depth; ++l)
-    for (int mc = 0; mc < 3; ++mc)
-      for (int nc = 0; nc < 3; ++nc) {
-        WgradUnit u{};
-        u.a_tile_stride = kWTileBytes; u.a_sub = mc * 32768; u.a_bytes = 32768;
-        u.b_tile_stride = kWTileBytes; u.b_sub = nc * 32768; u.b_bytes = 32768;
-        u.n = 128; u.transposed = 0;
-        u.out_off = M.gd_hidden[l]; u.out_ld = kW2; u.row0 = mc * 128; u.col0 = nc * 128;
-        u.rows_valid = 128; u.cols_valid = 128;
-        u.bias_off = nc == 0 ? M.gd_hidden[l] + kW2 * kW2 : -1;
-        p->units.push_back(u); p->unit_layer.push_back(l);
-      }
+    for (int mc = 0; mc < 3; ++mc) {         // 128 rows of D = dZ^T [hr|hi] against all 384 columns (3 chunks)
+      WgradUnit u{};
+      u.a_tile_stride = kWTileBytes; u.a_sub = mc * 32768; u.a_bytes = 32768;
+      u.b_tile_stride = kWTileBytes; u.b_sub = 0; u.b_bytes = 32768;
+      u.n = 128; u.n_chunks = 3; u.transposed = 0;
+      u.out_off = M.gd_hidden[l]; u.out_ld = kW2; u.row0 = mc * 128; u.col0 = 0;
+      u.rows_valid = 128; u.cols_valid = kW2;
+      u.bias_off = M.gd_hidden[l] + kW2 * kW2;
+      p->units.push_back(u); p->unit_layer.push_back(l);
+    }
   for (int mc = 0; mc < 3; ++mc) {          // final layer, transposed: D^T[o][f] = sum_rows dz_last[o] * [hr|hi][f]
     WgradUnit u{};
     u.a_tile_stride = kWTileBytes; u.a_sub = mc * 32768; u.a_bytes = 32768;
@@ -547,12 +547,13 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
   const uint32_t wtile = static_cast<uint32_t>(kTileM) * W * 2, xtile = static_cast<uint32_t>(kTileM) * IN * 2;
   for (int i = 1; i <= M.top; ++i)          // dW_i = DH[i]^T Z[i-1], db_i = sum DH[i]
     for (int mc = 0; mc < wc; ++mc)
-      for (int nc = 0; nc < wc; ++nc) {
+      for (int c0 = 0; c0 < wc; c0 += 3) {
+        const int nch = (wc - c0) < 3 ? (wc - c0) : 3;
         WgradUnit u{};
         u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
-        u.b_tile_stride = wtile; u.b_sub = nc * 32768; u.b_bytes = 32768;
-        u.n = 128; u.out_off = M.lin_w[i]; u.out_ld = W; u.row0 = mc * 128; u.col0 = nc * 128;
-        u.rows_valid = 128; u.cols_valid = 128; u.bias_off = (nc == 0 && !M.bounded) ? M.lin_b[i] : -1;
+        u.b_tile_stride = wtile; u.b_sub = c0 * 32768; u.b_bytes = 32768;
+        u.n = 128; u.n_chunks = nch; u.out_off = M.lin_w[i]; u.out_ld = W; u.row0 = mc * 128; u.col0 = c0 * 128;
+        u.rows_valid = 128; u.cols_valid = 128 * nch; u.bias_off = (c0 == 0 && !M.bounded) ? M.lin_b[i] : -1;
         p->units.push_back(u); p->unit_layer.push_back(100 + i);
       }
   if (M.bounded)                           // db_i = sum_rows of the UNMASKED dh_i: D[o][0] against a ones operand
@@ -567,12 +568,13 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
       }
   for (int i = 0; i <= M.top; ++i)          // dOm_i = DP[i]^T X, dphi_i = sum DP[i]
     for (int mc = 0; mc < wc; ++mc)
-      for (int nc = 0; nc < ic; ++nc) {
+      for (int c0 = 0; c0 < ic; c0 += 3) {
+        const int nch = (ic - c0) < 3 ? (ic - c0) : 3;
         WgradUnit u{};
         u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
-        u.b_tile_stride = xtile; u.b_sub = nc * 32768; u.b_bytes = 32768;
-        u.n = 128; u.out_off = M.filt_w[i]; u.out_ld = IN; u.row0 = mc * 128; u.col0 = nc * 128;
-        u.rows_valid = 128; u.cols_valid = 128; u.bias_off = nc == 0 ? M.filt_b[i] : -1;
+        u.b_tile_stride = xtile; u.b_sub = c0 * 32768; u.b_bytes = 32768;
+        u.n = 128; u.n_chunks = nch; u.out_off = M.filt_w[i]; u.out_ld = IN; u.row0 = mc * 128; u.col0 = c0 * 128;
+        u.rows_valid = 128; u.cols_valid = 128 * nch; u.bias_off = c0 == 0 ? M.filt_b[i] : -1;
         p->units.push_back(u); p->unit_layer.push_back(200 + i);
       }
   for (int k = 0; k < M.n_heads; ++k) {     // dV_k^T[o][f] = sum_rows dy_k[o] z[f]

@@ -117,6 +117,7 @@ struct WgradUnit {
   int rows_valid, cols_valid;
   int bias_off;                 // float offset of the bias gradient or -1
   int perm_e;                   // >0: columns are in sin/cos-interleaved order with E = perm_e
+  int n_chunks;                 // B chunks of 128 features swept against one resident A sub-image (0/1: single chunk)
 };
 
 constexpr int kMaxUnits = 320;      // by-value kernel parameter: 320 x 88 B < 32 KB

@@ -4,7 +4,9 @@
 // backward kernels saved, consumed as MN-major UMMA operands with no transposition pass.  A work
 // item is (unit, split): a 128 x N block of one weight matrix accumulated over a contiguous range
 // of row tiles; partial sums go to gpart[split][param] (fixed layout, no atomics) and are added in
-// a fixed order by the optimiser kernel, so the whole step is bit-reproducible.
+// a fixed order by the optimiser kernel, so the whole step is bit-reproducible.  A unit keeps one A sub-image (128
+// output features) per row tile and sweeps up to three 128-feature B chunks against it (N up to 384), which cuts the
+// L2->SM operand traffic that bounds this kernel by a third compared with square 128 x 128 units.
 // Bias gradients ride along as one extra N=16 MMA against an all-ones operand.
 // The last (out_f-wide) layer is computed transposed: D[in_chunk, 16] = H^T dZ_last.
 #include <cuda_runtime.h>
@@ -13,80 +15,92 @@
 
 namespace inr {
 
-constexpr int kWgStages = 3;
-constexpr int kWgStageBytes = 65536;            // A sub-image (32 KB) + B sub-image (<= 32 KB)
-constexpr int kWgOnesBytes = 4096;         // all-ones operand: any descriptor stride lands on 1.0
+constexpr int kWgSlots = 6;                     // ring of 32 KB slots: an A sub-image or one B chunk each
+constexpr int kWgSlotBytes = 32768;
+constexpr int kWgOnesBytes = 4096;              // all-ones operand: any descriptor stride lands on 1.0
 constexpr int kWgThreads = 192;                 // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
-constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgOnesBytes + 4 * 32 * 33 * 4 + 1024;
+constexpr int kWgSmem = kWgSlots * kWgSlotBytes + kWgOnesBytes + 4 * 32 * 33 * 4 + 1024;
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* stages = smem;
-  __half* ones = reinterpret_cast<__half*>(smem + kWgStages * kWgStageBytes);
-  float* tr = reinterpret_cast<float*>(smem + kWgStages * kWgStageBytes + kWgOnesBytes);   // 4 x [32][33]
-  __shared__ uint64_t full[kWgStages], empty[kWgStages], acc_full;
+  uint8_t* ring = smem;
+  __half* ones = reinterpret_cast<__half*>(smem + kWgSlots * kWgSlotBytes);
+  float* tr = reinterpret_cast<float*>(smem + kWgSlots * kWgSlotBytes + kWgOnesBytes);   // 4 x [32][33]
+  __shared__ uint64_t full[kWgSlots], empty[kWgSlots], acc_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int unit = blockIdx.x % a.n_units, split = blockIdx.x / a.n_units;
   const WgradUnit& U = a.u[unit];
+  const int nch = U.n_chunks > 1 ? U.n_chunks : 1;
+  const int bias_col = 128 * nch;               // accumulator columns of the bias MMA
   const int t0 = static_cast<int>((static_cast<long long>(a.n_tiles) * split) / a.n_split);
   const int t1 = static_cast<int>((static_cast<long long>(a.n_tiles) * (split + 1)) / a.n_split);
 
   if (tid == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWgSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&acc_full, 1);
     mbar_fence_init();
   }
   for (int i = tid; i < kWgOnesBytes / 2; i += kWgThreads) ones[i] = __float2half(1.0f);
   fence_proxy_async_smem();
-  if (warp == 2) tmem_alloc<256>(&tmem_base_s);
+  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ producer: per tile  A, B_0 .. B_{nch-1}
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t slot = it % kWgStages, ph = (it / kWgStages) & 1;
-        mbar_wait(&empty[slot], ph ^ 1);
-        mbar_arrive_expect_tx(&full[slot], U.a_bytes + U.b_bytes);
-        uint8_t* dst = stages + slot * kWgStageBytes;
-        bulk_g2s(dst, a.ws + U.a_off + static_cast<size_t>(t) * U.a_tile_stride + U.a_sub, U.a_bytes, &full[slot]);
-        bulk_g2s(dst + 32768, a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub, U.b_bytes, &full[slot]);
+      uint32_t slot = 0, ph = 0;
+      for (int t = t0; t < t1; ++t) {
+        for (int c = -1; c < nch; ++c) {
+          mbar_wait(&empty[slot], ph ^ 1);
+          const uint32_t bytes = c < 0 ? U.a_bytes : U.b_bytes;
+          const uint8_t* src = c < 0 ? a.ws + U.a_off + static_cast<size_t>(t) * U.a_tile_stride + U.a_sub
+                                     : a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub + static_cast<size_t>(c) * kWgSlotBytes;
+          mbar_arrive_expect_tx(&full[slot], bytes);
+          bulk_g2s(ring + slot * kWgSlotBytes, src, bytes, &full[slot]);
+          if (++slot == kWgSlots) { slot = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kTileM, U.n, true, true);
       constexpr uint32_t idesc_bias = umma_idesc_f16(kTileM, 16, true, true);
-      const uint32_t ones_s = smem_u32(ones);
-      uint32_t it = 0;
-      for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t slot = it % kWgStages;
-        mbar_wait(&full[slot], (it / kWgStages) & 1);
+      const uint64_t d_ones = umma_smem_desc(smem_u32(ones), 128, 128);
+      const uint64_t d0 = umma_smem_desc(smem_u32(ring), 128, 2048);     // MN-major image: LBO 128 (K groups), SBO 2048
+      uint32_t slot = 0, ph = 0, first = 1;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&full[slot], ph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(stages + slot * kWgStageBytes), b_base = a_base + 32768;
+        const uint32_t a_slot = slot;
+        const uint64_t da0 = d0 + ((a_slot * kWgSlotBytes) >> 4);
+        if (++slot == kWgSlots) { slot = 0; ph ^= 1; }
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(&full[slot], ph);
+          tc_fence_after();
+          const uint64_t db0 = d0 + ((slot * kWgSlotBytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < kTileM / 16; ++k) {
-          const uint64_t da = umma_smem_desc(a_base + k * 256, 128, 2048);
-          const uint64_t db = umma_smem_desc(b_base + k * 256, 128, 2048);
-          umma_f16(tmem, da, db, idesc, (it | k) != 0);
-        }
-        if (U.bias_off >= 0) {
-          // normal unit: bias[o] = sum_rows dZ[row,o] * 1  -> A = dZ image, B = ones, accumulator columns 128..143
-          // transposed unit: bias[o] = sum_rows 1 * dZ_last[row,o] -> A = ones, B = dZ_last image
+          for (int k = 0; k < kTileM / 16; ++k)          // K = 16 batch rows per MMA: 256 B of every 2 KB feature group
+            umma_f16(tmem + 128 * c, da0 + k * 16, db0 + k * 16, idesc, (first ^ 1) | (k != 0));
+          if (U.bias_off >= 0 && c == nch - 1) {
+            // normal unit: bias[o] = sum_rows dZ[row,o] * 1  -> A = dZ image, B = ones
+            // transposed unit: bias[o] = sum_rows 1 * dZ_last[row,o] -> A = ones, B = dZ_last image
 #pragma unroll
-          for (int k = 0; k < kTileM / 16; ++k) {
-            const uint64_t d_ones = umma_smem_desc(ones_s, 128, 128);
-            const uint64_t da = U.transposed ? d_ones : umma_smem_desc(a_base + k * 256, 128, 2048);
-            const uint64_t db = U.transposed ? umma_smem_desc(b_base + k * 256, 128, 2048) : d_ones;
-            umma_f16(tmem + 128, da, db, idesc_bias, (it | k) != 0);
+            for (int k = 0; k < kTileM / 16; ++k) {
+              const uint64_t da = U.transposed ? d_ones : da0 + k * 16;
+              const uint64_t db = U.transposed ? db0 + k * 16 : d_ones;
+              umma_f16(tmem + bias_col, da, db, idesc_bias, (first ^ 1) | (k != 0));
+            }
           }
+          if (c == nch - 1) umma_commit(&empty[a_slot]);   // commits cover every MMA issued so far
+          umma_commit(&empty[slot]);
+          if (++slot == kWgSlots) { slot = 0; ph ^= 1; }
         }
-        umma_commit(&empty[slot]);
+        first = 0;
       }
       umma_commit(&acc_full);
     }
@@ -100,7 +114,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     const bool have = t1 > t0;
     if (have) { mbar_wait(&acc_full, 0); tc_fence_after(); }
     if (!U.transposed) {
-      for (int c0 = 0; c0 < U.n; c0 += 32) {
+      const int n_cols = nch > 1 ? 128 * nch : U.n;
+      for (int c0 = 0; c0 < n_cols; c0 += 32) {
         float v[32];
         if (have) { tmem_ld32(tmem + t_lane + c0, v); tmem_ld_wait(); }
         else {
@@ -126,7 +141,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       }
       if (U.bias_off >= 0) {
         float v[16];
-        if (have) { tmem_ld16(tmem + t_lane + 128, v); tmem_ld_wait(); } else v[0] = 0.f;
+        if (have) { tmem_ld16(tmem + t_lane + bias_col, v); tmem_ld_wait(); } else v[0] = 0.f;
         if (r_local < U.rows_valid) gp[U.bias_off + U.row0 + r_local] = v[0];
       }
     } else {
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         if (o < U.rows_valid && r_local < U.cols_valid) gp[U.out_off + o * U.out_ld + U.col0 + r_local] = v[o];
       if (U.bias_off >= 0) {
         float b[16];
-        if (have) { tmem_ld16(tmem + t_lane + 128, b); tmem_ld_wait(); }
+        if (have) { tmem_ld16(tmem + t_lane + bias_col, b); tmem_ld_wait(); }
         else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) b[i] = 0.f;
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<256>(tmem);
+  if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
