@@ -50,6 +50,12 @@ struct inr_plan {
 };
 
 static thread_local std::string g_err;
+// wgrad units sweep up to three 128-feature B chunks per resident A sub-image: split `n` chunks into equal groups
+static int chunk_group(int n) { const int groups = (n + 2) / 3; return (n + groups - 1) / groups; }
+
+// float stride between split-K partial copies: a multiple of 4 so every row the wgrad epilogue bulk-stores stays 16 B aligned
+static int gpart_stride(int n_params) { return (n_params + 3) & ~3; }
+
 static unsigned long long* g_trace = nullptr;   // debug: device buffer for in-kernel phase stamps (inr_debug_set_trace)
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static int cuda_fail(cudaError_t e, const char* where) {
@@ -127,8 +133,8 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   for (int l = 0; l < M.n_gemm; ++l) {
     const int K = l == 0 ? M.k0 : kWidth;
     for (int mh = 0; mh < kWidth / 128; ++mh)
-      for (int c0 = 0; c0 < K / 128; c0 += 3) {
-        const int nch = (K / 128 - c0) < 3 ? (K / 128 - c0) : 3;
+      for (int c0 = 0, per = chunk_group(K / 128); c0 < K / 128; c0 += per) {
+        const int nch = (K / 128 - c0) < per ? (K / 128 - c0) : per;
         WgradUnit u{};
         u.a_tile_stride = kActBytes; u.a_sub = mh * 32768; u.a_bytes = 32768;
         u.b_tile_stride = kTileM * K * 2; u.b_sub = c0 * 32768; u.b_bytes = 32768;
@@ -205,7 +211,7 @@ static Workspace plan_workspace(const inr_plan* p, int64_t bs) {
   for (int l = 0; l < M.n_gemm; ++l) { w.d_off[l] = o; o += static_cast<uint64_t>(T) * kActBytes; }
   for (int l = 0; l < M.n_gemm; ++l) { w.dz_off[l] = o; o += static_cast<uint64_t>(T) * kActBytes; }
   w.dzlast_off = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024);
-  w.gpart_off = o; o += align_up(static_cast<uint64_t>(ns) * M.n_params * 4, 1024);
+  w.gpart_off = o; o += align_up(static_cast<uint64_t>(ns) * gpart_stride(M.n_params) * 4, 1024);
   w.total = o;
   return w;
 }
@@ -252,6 +258,7 @@ static void fill_adam(const inr_plan* p, AdamArgs& a) {
   a.n_seg = static_cast<int>(p->segs.size());
   for (int i = 0; i < a.n_seg; ++i) a.seg[i] = p->segs[i];
   a.n_params = p->is_mfn ? p->mm.n_params : p->model.n_params;
+  a.gstride = gpart_stride(a.n_params);
 }
 
 static void fill_wgrad(const inr_plan* p, const Workspace& w, uint8_t* ws, WgradArgs& g) {
@@ -265,7 +272,7 @@ static void fill_wgrad(const inr_plan* p, const Workspace& w, uint8_t* ws, Wgrad
     else { u.a_off = w.h_off[M.n_gemm]; u.b_off = w.dzlast_off; }
     g.u[i] = u;
   }
-  g.n_split = w.n_split; g.n_tiles = w.n_tiles; g.n_params = M.n_params;
+  g.n_split = w.n_split; g.n_tiles = w.n_tiles; g.n_params = gpart_stride(M.n_params);
   g.ws = ws; g.gpart_off = w.gpart_off;
 }
 
@@ -453,7 +460,7 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
     e = launch_lgemm(g, p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(dgrad)");
   }
-  WgradArgs wg; std::memset(&wg, 0, sizeof(wg));
+  WgradArgs wg; std::memset(&wg, 0, sizeof(wg)); wg.trace = g_trace;
   wg.n_units = static_cast<int>(p->units.size());
   const int L = M.depth + 1;
   for (int i = 0; i < wg.n_units; ++i) {
@@ -547,8 +554,8 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
   const uint32_t wtile = static_cast<uint32_t>(kTileM) * W * 2, xtile = static_cast<uint32_t>(kTileM) * IN * 2;
   for (int i = 1; i <= M.top; ++i)          // dW_i = DH[i]^T Z[i-1], db_i = sum DH[i]
     for (int mc = 0; mc < wc; ++mc)
-      for (int c0 = 0; c0 < wc; c0 += 3) {
-        const int nch = (wc - c0) < 3 ? (wc - c0) : 3;
+      for (int c0 = 0, per = chunk_group(wc); c0 < wc; c0 += per) {
+        const int nch = (wc - c0) < per ? (wc - c0) : per;
         WgradUnit u{};
         u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
         u.b_tile_stride = wtile; u.b_sub = c0 * 32768; u.b_bytes = 32768;
@@ -568,8 +575,8 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
       }
   for (int i = 0; i <= M.top; ++i)          // dOm_i = DP[i]^T X, dphi_i = sum DP[i]
     for (int mc = 0; mc < wc; ++mc)
-      for (int c0 = 0; c0 < ic; c0 += 3) {
-        const int nch = (ic - c0) < 3 ? (ic - c0) : 3;
+      for (int c0 = 0, per = chunk_group(ic); c0 < ic; c0 += per) {
+        const int nch = (ic - c0) < per ? (ic - c0) : per;
         WgradUnit u{};
         u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
         u.b_tile_stride = xtile; u.b_sub = c0 * 32768; u.b_bytes = 32768;
@@ -619,7 +626,7 @@ static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs) {
     for (int i = 1; i <= M.top; ++i) { w.dhu[i] = o; o += wimg; }
     w.ones = o; o += 4096;
   }
-  w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * M.n_params * 4, 1024);
+  w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * gpart_stride(M.n_params) * 4, 1024);
   w.total = o;
   return w;
 }
@@ -703,7 +710,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
     e = launch_lgemm(g, p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn dgrad)");
   }
-  WgradArgs wg; std::memset(&wg, 0, sizeof(wg));
+  WgradArgs wg; std::memset(&wg, 0, sizeof(wg)); wg.trace = g_trace;
   wg.n_units = static_cast<int>(p->units.size());
   for (int i = 0; i < wg.n_units; ++i) {
     WgradUnit u = p->units[i];
@@ -714,7 +721,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
     else { const int s = code - 100; u.a_off = w.dh[s]; u.b_off = w.z[s - 1]; }
     wg.u[i] = u;
   }
-  wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = M.n_params; wg.ws = W; wg.gpart_off = w.gpart;
+  wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = gpart_stride(M.n_params); wg.ws = W; wg.gpart_off = w.gpart;
   e = launch_wgrad(wg, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel(mfn)");
 }
@@ -812,7 +819,7 @@ static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& l
   cudaError_t e = launch_chain_bwd(b, p->n_sm, st);
   if (e != cudaSuccess) return cuda_fail(e, "chain_bwd_kernel");
   if (mid) cudaEventRecord(mid, st);
-  WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g);
+  WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g); g.trace = g_trace;
   e = launch_wgrad(g, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel");
 }

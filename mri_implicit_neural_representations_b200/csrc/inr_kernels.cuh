@@ -66,7 +66,7 @@ struct Workspace {
   uint64_t g_off;                // [rows_pad][4] fp32: unnormalised dL/dz_last parts A and B
   uint64_t part_off;             // [n_tiles][8] fp32
   uint64_t scal_off;             // [16] fp32
-  uint64_t gpart_off;            // [n_split][n_params] fp32 split-K gradient partials (scaled)
+  uint64_t gpart_off;            // [n_split][n_params rounded up to 4] fp32 split-K gradient partials (scaled)
   uint64_t total;
   int n_tiles, n_split;
 };
@@ -126,6 +126,7 @@ struct WgradArgs {
   int n_units, n_split, n_tiles, n_params;
   uint8_t* ws;
   uint64_t gpart_off;
+  unsigned long long* trace;   // debug: 8 %globaltimer stamps per CTA starting at slot 64 (null in production)
 };
 
 struct SegDesc {          // one parameter tensor for the optimiser / packer
@@ -144,6 +145,7 @@ constexpr int kMaxSegs = 64;
 struct AdamArgs {
   SegDesc seg[kMaxSegs];
   int n_seg, n_params, n_split, n_tiles;
+  int gstride;              // floats between consecutive split copies of gpart (n_params rounded up to 4)
   float* params; float* m; float* v;
   float* grads;             // optional: unscaled fp32 gradients are written here when non-null
   uint8_t* wpack;

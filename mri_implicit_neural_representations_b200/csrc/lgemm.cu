@@ -42,7 +42,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
 }
 
-template <int PASSES>
+template <int PASSES, int MODE>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2];
@@ -68,12 +68,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads); }
     mbar_fence_init();
   }
-  if (a.mode == LG_WIRE_FWD) {
+  if (MODE == LG_WIRE_FWD) {
     for (int j = tid; j < kWP; j += kLgThreads) {
       s_ba[j] = j < a.c_valid ? a.bias[2 * j] : 0.f;
       s_bb[j] = j < a.c_valid ? a.bias[2 * j + 1] : 0.f;
     }
-  } else if (a.mode == LG_MFN_FWD) {
+  } else if (MODE == LG_MFN_FWD) {
     const int width = a.n_nblocks * a.nt;
     for (int j = tid; j < width; j += kLgThreads) {
       s_ba[j] = a.bias ? a.bias[j] : 0.f;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     const int q = warp & 3, sub = (warp - 4) >> 2, row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
     const float w = a.omega, s2 = a.sigma * a.sigma;
-    const bool dgrad = a.mode == LG_WIRE_DGRAD || a.mode == LG_MFN_DGRAD;
+    const bool dgrad = MODE == LG_WIRE_DGRAD || MODE == LG_MFN_DGRAD;
     // per-layer power-of-two gradient scales (WIRE's gradient norm grows ~10x per layer towards the input; one global
     // loss scale would saturate the fp16 images of the lower layers)
     float ratio = 1.f, amax = 0.f, s_dst = 1.f;
@@ -175,19 +175,32 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
       const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
       const uint32_t ab = n_done & 1, use = n_done >> 1;
-      mbar_wait(&acc_full[ab], use & 1);
-      tc_fence_after();
       const uint32_t acc = tmem + t_lane + ab * 256;
-      if (a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD) {
+      if (MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) {
         const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16;
-#pragma unroll 1
+        // dgrad: the saved activations do not depend on the accumulator -- fetch all of them before waiting for the MMAs
+        uint4 pre[3][4];
+        if (MODE == LG_WIRE_DGRAD) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int f0 = kWFeatPerBlock * nb + 24 * sub + 8 * i;
+            const size_t off_r = img + static_cast<size_t>(f0 >> 3) * 2048;
+            const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;
+            pre[i][0] = ld_global_nc_v4(a.in_y + off_r); pre[i][1] = ld_global_nc_v4(a.in_y + off_i);
+            pre[i][2] = ld_global_nc_v4(a.in_ab + off_r);
+            pre[i][3] = a.real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(a.in_ab + off_i);
+          }
+        }
+        mbar_wait(&acc_full[ab], use & 1);
+        tc_fence_after();
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int c0 = 24 * sub + 8 * i;                 // feature inside the N-block
           const int f0 = kWFeatPerBlock * nb + c0;         // complex feature index (multiple of 8)
           const size_t off_r = img + static_cast<size_t>(f0 >> 3) * 2048;               // real-part k-group
           const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;       // imaginary-part k-group
           float va[8], vb[8];
-          if (a.mode == LG_WIRE_FWD) {
+          if (MODE == LG_WIRE_FWD) {
             tmem_ld8(acc + c0, va);
             tmem_ld8(acc + kWFeatPerBlock + c0, vb);
             tmem_ld_wait();
@@ -214,10 +227,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               st_global_v4(a.out_ab + off_i, pack8(vb));
             }
           } else {
-            const uint4 yr4 = ld_global_nc_v4(a.in_y + off_r), yi4 = ld_global_nc_v4(a.in_y + off_i);
-            const uint4 a4 = ld_global_nc_v4(a.in_ab + off_r);
-            uint4 b4 = make_uint4(0u, 0u, 0u, 0u);
-            if (!a.real_first) b4 = ld_global_nc_v4(a.in_ab + off_i);
+            const uint4 yr4 = pre[i][0], yi4 = pre[i][1], a4 = pre[i][2], b4 = pre[i][3];
             tmem_ld8(acc + c0, va);                       // dL/d Re(h)
             tmem_ld8(acc + kWFeatPerBlock + c0, vb);      // dL/d Im(h)
             tmem_ld_wait();
@@ -238,22 +248,33 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       } else {
         // ---------------- MFN stages: nt = 128 columns per N-block, this warp owns 32 of them (4 steps of 8)
         const size_t img = static_cast<size_t>(tile) * a.feat_tile_bytes + row * 16;
+        uint4 pre[4][3];
+        if (MODE == LG_MFN_DGRAD) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const size_t off = img + static_cast<size_t>((a.nt * nb + 32 * sub + 8 * i) >> 3) * 2048;
+            pre[i][0] = ld_global_nc_v4(a.in_y + off); pre[i][1] = ld_global_nc_v4(a.in_ab + off);
+            pre[i][2] = a.real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(a.in_h + off);
+          }
+        }
+        mbar_wait(&acc_full[ab], use & 1);
+        tc_fence_after();
         const int grow = tile * kTileM + row;
         bool masked = false;            // BoundedLinear: this row's input to the linear was zeroed
         if (a.dist && grow < a.bs) { const float d = a.dist[grow]; masked = (d < a.bound_lo) || (d > a.bound_hi); }
         float hd[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
-        if (a.mode == LG_MFN_DGRAD && a.head_dout && grow < a.bs) {
+        if (MODE == LG_MFN_DGRAD && a.head_dout && grow < a.bs) {
 #pragma unroll
           for (int o = 0; o < kMaxOut; ++o)
             if (o < a.out_f) hd[o] = s_dst * a.head_dout[static_cast<size_t>(grow) * a.head_ld + a.head_col + o];
         }
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c0 = 32 * sub + 8 * i;                 // column inside the N-block
           const int f0 = a.nt * nb + c0;                   // feature index
           const size_t off = img + static_cast<size_t>(f0 >> 3) * 2048;
           float vp[8], vh[8];
-          if (a.mode == LG_MFN_FWD) {
+          if (MODE == LG_MFN_FWD) {
             tmem_ld8(acc + c0, vp);                        // filter pre-activation  x Om^T
             if (a.n_seg == 2) tmem_ld8(acc + a.nt + c0, vh);   // linear  z_{i-1} W^T
             tmem_ld_wait();
@@ -272,9 +293,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               if (a.n_seg == 2) st_global_v4(a.out_h + off, pack8(h));
             }
           } else {
-            const uint4 g4 = ld_global_nc_v4(a.in_y + off), c4 = ld_global_nc_v4(a.in_ab + off);
-            uint4 h4 = make_uint4(0u, 0u, 0u, 0u);
-            if (!a.real_first) h4 = ld_global_nc_v4(a.in_h + off);
+            const uint4 g4 = pre[i][0], c4 = pre[i][1], h4 = pre[i][2];
             tmem_ld8(acc + c0, vp);                        // S[src] * dh_i W_i  = S[src] * dz_{i-1} (before heads)
             tmem_ld_wait();
             float g[8], c[8], h[8], dh[8], dp[8];
@@ -324,14 +343,22 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   if (grid <= 0) return cudaSuccess;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(lgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lgemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
+    cudaError_t e = cudaFuncSetAttribute(lgemm_kernel<3, LG_WIRE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lgemm_kernel<1, LG_WIRE_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lgemm_kernel<1, LG_MFN_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lgemm_kernel<1, LG_MFN_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  if (a.passes == 3) lgemm_kernel<3><<<grid, kLgThreads, kLgSmem, stream>>>(a);
-  else lgemm_kernel<1><<<grid, kLgThreads, kLgSmem, stream>>>(a);
+  const int expect_passes = a.mode == LG_WIRE_FWD ? 3 : 1;
+  if (a.passes != expect_passes) return cudaErrorInvalidValue;
+  switch (a.mode) {
+    case LG_WIRE_FWD:   lgemm_kernel<3, LG_WIRE_FWD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
+    case LG_WIRE_DGRAD: lgemm_kernel<1, LG_WIRE_DGRAD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
+    case LG_MFN_FWD:    lgemm_kernel<1, LG_MFN_FWD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
+    case LG_MFN_DGRAD:  lgemm_kernel<1, LG_MFN_DGRAD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

@@ -15,11 +15,14 @@
 
 namespace inr {
 
+#define WG_TRACE(slot) do { if (a.trace) a.trace[64 + blockIdx.x * 8 + (slot)] = global_ns(); } while (0)
+
 constexpr int kWgSlots = 6;                     // ring of 32 KB slots: an A sub-image or one B chunk each
 constexpr int kWgSlotBytes = 32768;
 constexpr int kWgOnesBytes = 4096;              // all-ones operand: any descriptor stride lands on 1.0
 constexpr int kWgThreads = 192;                 // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
 constexpr int kWgSmem = kWgSlots * kWgSlotBytes + kWgOnesBytes + 4 * 32 * 33 * 4 + 1024;
+static_assert(128 * (384 * 4 + 16) <= kWgSmem - 1024, "epilogue staging (128 rows x 384 fp32 + 16 B pitch pad) must fit the dead ring");
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -34,10 +37,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const WgradUnit& U = a.u[unit];
   const int nch = U.n_chunks > 1 ? U.n_chunks : 1;
   const int bias_col = 128 * nch;               // accumulator columns of the bias MMA
+  const uint32_t nA = nch == 1 ? 3 : 2, nB = kWgSlots - nA;
   const int t0 = static_cast<int>((static_cast<long long>(a.n_tiles) * split) / a.n_split);
   const int t1 = static_cast<int>((static_cast<long long>(a.n_tiles) * (split + 1)) / a.n_split);
 
   if (tid == 0) {
+    WG_TRACE(0);
     for (int i = 0; i < kWgSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&acc_full, 1);
     mbar_fence_init();
@@ -49,20 +54,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (tid == 0) WG_TRACE(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: per tile  A, B_0 .. B_{nch-1}
+    // A sub-images and B chunks live in separate sub-rings (slots [0,nA) and [nA,6)) so that the A slot a unit holds
+    // for all of its chunks never blocks the in-order prefetch of the following B chunks.
     if (lane == 0) {
-      uint32_t slot = 0, ph = 0;
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
       for (int t = t0; t < t1; ++t) {
-        for (int c = -1; c < nch; ++c) {
-          mbar_wait(&empty[slot], ph ^ 1);
-          const uint32_t bytes = c < 0 ? U.a_bytes : U.b_bytes;
-          const uint8_t* src = c < 0 ? a.ws + U.a_off + static_cast<size_t>(t) * U.a_tile_stride + U.a_sub
-                                     : a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub + static_cast<size_t>(c) * kWgSlotBytes;
-          mbar_arrive_expect_tx(&full[slot], bytes);
-          bulk_g2s(ring + slot * kWgSlotBytes, src, bytes, &full[slot]);
-          if (++slot == kWgSlots) { slot = 0; ph ^= 1; }
+        mbar_wait(&empty[as], aph ^ 1);
+        mbar_arrive_expect_tx(&full[as], U.a_bytes);
+        bulk_g2s(ring + as * kWgSlotBytes, a.ws + U.a_off + static_cast<size_t>(t) * U.a_tile_stride + U.a_sub, U.a_bytes, &full[as]);
+        if (++as == nA) { as = 0; aph ^= 1; }
+        for (int c = 0; c < nch; ++c) {
+          const uint32_t slot = nA + bs;
+          mbar_wait(&empty[slot], bph ^ 1);
+          mbar_arrive_expect_tx(&full[slot], U.b_bytes);
+          bulk_g2s(ring + slot * kWgSlotBytes,
+                   a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub + static_cast<size_t>(c) * kWgSlotBytes, U.b_bytes, &full[slot]);
+          if (++bs == nB) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -72,15 +83,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       constexpr uint32_t idesc_bias = umma_idesc_f16(kTileM, 16, true, true);
       const uint64_t d_ones = umma_smem_desc(smem_u32(ones), 128, 128);
       const uint64_t d0 = umma_smem_desc(smem_u32(ring), 128, 2048);     // MN-major image: LBO 128 (K groups), SBO 2048
-      uint32_t slot = 0, ph = 0, first = 1;
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, first = 1;
       for (int t = t0; t < t1; ++t) {
-        mbar_wait(&full[slot], ph);
+        mbar_wait(&full[as], aph);
         tc_fence_after();
-        const uint32_t a_slot = slot;
-        const uint64_t da0 = d0 + ((a_slot * kWgSlotBytes) >> 4);
-        if (++slot == kWgSlots) { slot = 0; ph ^= 1; }
+        if (t == t0) WG_TRACE(2);
+        const uint64_t da0 = d0 + ((as * kWgSlotBytes) >> 4);
         for (int c = 0; c < nch; ++c) {
-          mbar_wait(&full[slot], ph);
+          const uint32_t slot = nA + bs;
+          mbar_wait(&full[slot], bph);
           tc_fence_after();
           const uint64_t db0 = d0 + ((slot * kWgSlotBytes) >> 4);
 #pragma unroll
@@ -96,13 +107,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
               umma_f16(tmem + bias_col, da, db, idesc_bias, (first ^ 1) | (k != 0));
             }
           }
-          if (c == nch - 1) umma_commit(&empty[a_slot]);   // commits cover every MMA issued so far
-          umma_commit(&empty[slot]);
-          if (++slot == kWgSlots) { slot = 0; ph ^= 1; }
+          umma_commit(&empty[slot]);                       // commits cover every MMA issued so far
+          if (++bs == nB) { bs = 0; bph ^= 1; }
         }
+        umma_commit(&empty[as]);
+        if (++as == nA) { as = 0; aph ^= 1; }
         first = 0;
       }
       umma_commit(&acc_full);
+      WG_TRACE(3);
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> gpart[split]
@@ -113,8 +126,41 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     float* my_tr = tr + (warp - 2) * 32 * 33;
     const bool have = t1 > t0;
     if (have) { mbar_wait(&acc_full, 0); tc_fence_after(); }
+    if (tid == 64) WG_TRACE(4);
     if (!U.transposed) {
       const int n_cols = nch > 1 ? 128 * nch : U.n;
+      // Fast path: the operand ring is dead once acc_full fired, so the whole 128 x n_cols fp32 block is staged there
+      // (row pitch +16 B: conflict-free 16 B stores) and every thread bulk-stores its own row -- no transposition pass.
+      const uint32_t row_bytes = static_cast<uint32_t>(n_cols) * 4, pitch = row_bytes + 16;
+      float* dst_row = gp + U.out_off + static_cast<size_t>(U.row0 + r_local) * U.out_ld;
+      const int seg_cols = U.perm_e > 0 ? n_cols / 2 : n_cols;               // gauss first layer: two destination runs
+      const int dcol0 = U.perm_e > 0 ? 32 * (U.col0 >> 6) : U.col0;
+      const bool fast = have && n_cols >= 128 && U.rows_valid == 128 && U.cols_valid == n_cols && (U.out_ld & 3) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(dst_row + dcol0) | reinterpret_cast<uintptr_t>(dst_row + U.perm_e + dcol0)) & 15) == 0 &&
+                        (U.perm_e == 0 || (U.col0 & 63) == 0);
+      if (fast) {
+        uint8_t* srow = smem + static_cast<size_t>(r_local) * pitch;
+        for (int c0 = 0; c0 < n_cols; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem + t_lane + c0, v);
+          tmem_ld_wait();
+          int sc = c0;                                                      // staging column of this 32-column chunk
+          if (U.perm_e > 0) sc = ((c0 & 32) ? seg_cols : 0) + 32 * (c0 >> 6);
+          float4* d = reinterpret_cast<float4*>(srow + sc * 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        bulk_s2g(dst_row + dcol0, srow, seg_cols * 4);
+        if (U.perm_e > 0) bulk_s2g(dst_row + U.perm_e + dcol0, srow + seg_cols * 4, seg_cols * 4);
+        bulk_commit();
+        if (U.bias_off >= 0) {
+          float v[16];
+          tmem_ld16(tmem + t_lane + bias_col, v); tmem_ld_wait();
+          gp[U.bias_off + U.row0 + r_local] = v[0];
+        }
+        bulk_wait_read0();
+      } else {
       for (int c0 = 0; c0 < n_cols; c0 += 32) {
         float v[32];
         if (have) { tmem_ld32(tmem + t_lane + c0, v); tmem_ld_wait(); }
@@ -144,6 +190,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         if (have) { tmem_ld16(tmem + t_lane + bias_col, v); tmem_ld_wait(); } else v[0] = 0.f;
         if (r_local < U.rows_valid) gp[U.bias_off + U.row0 + r_local] = v[0];
       }
+      }
     } else {
       // D[i_local, o] -> dW[o][col0 + i_local]; lanes write consecutive i (coalesced)
       float v[16];
@@ -170,9 +217,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       }
     }
   }
+  if (tid == 64) WG_TRACE(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem);
+  if (tid == 0) WG_TRACE(6);
 }
 
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
