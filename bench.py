@@ -405,7 +405,11 @@ def main():
                 "ms_per_step": ms_e2e / n_e2e, "api": "ChainEngine.train_step (C ABI inr_train_step), pinned host batches"},
         "gpu_launches": ((15 if dp else 14) if wire else (5 if dp else 4)) * args.steps,
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
-                     "frac": fwd_tflops / peaks["tflops_burst"], "traffic": None,
+                     "frac": fwd_tflops / peaks["tflops_burst"],
+                     # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture
+                     "traffic": (44.3e6 if wire and bs == 25000 else None),
+                     "traffic_source": ("profiles/r01_ncu_lgemm_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, cold L2)"
+                                        if wire and bs == 25000 else None),
                      "kernel": "lgemm_kernel (WIRE forward layer GEMM + Gabor epilogue; one of 4 launches/step)" if wire else "chain_fwd_kernel<SIN>",
                      "kernel_ms": kern_ms,
                      "issued_tflops": (wl["issued_fwd_flop_per_coord"] / wl["net"]["network_depth"] * bs / (kern_ms * 1e-3) / 1e12) if wire else None,

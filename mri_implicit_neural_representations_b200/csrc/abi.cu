@@ -2,6 +2,7 @@
 // layout, and the launch sequences of the fused kernels.  No exceptions leave this file.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <new>
@@ -64,7 +65,16 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 extern "C" const char* inr_last_error(void) { return g_err.c_str(); }
-extern "C" int inr_debug_set_trace(void* dev_u64_buffer_64) { g_trace = static_cast<unsigned long long*>(dev_u64_buffer_64); return INR_OK; }
+static int g_trace_lgemm_sel = -1, g_trace_lgemm_count = 0;   // debug: which layer-GEMM launch after set_trace gets the buffer
+extern "C" int inr_debug_set_trace(void* dev_u64_buffer_64) {
+  g_trace = static_cast<unsigned long long*>(dev_u64_buffer_64);
+  const char* sel = std::getenv("INR_TRACE_LGEMM");
+  g_trace_lgemm_sel = sel ? std::atoi(sel) : -1;
+  g_trace_lgemm_count = 0;
+  return INR_OK;
+}
+static int lgemm_dbg() { static int v = -1; if (v < 0) { const char* e = std::getenv("INR_LGEMM_DBG"); v = e ? std::atoi(e) : 0; } return v; }
+static unsigned long long* lgemm_trace_ptr() { return (g_trace && g_trace_lgemm_count++ == g_trace_lgemm_sel) ? g_trace : nullptr; }
 
 static int wire_plan_create(const inr_model_desc* d, inr_plan** out);
 static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs);
@@ -426,7 +436,7 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 3; g.mode = LG_WIRE_FWD;
     g.bias = params + M.b_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.train = train;
     g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
-    e = launch_lgemm(g, p->n_sm, st);
+    e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(fwd)");
   }
   if (gemm_ev) cudaEventRecord(gemm_ev[1], st);
@@ -457,7 +467,7 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
     g.real_first = (l - 1 == 0) ? 1 : 0;
     g.in_y = W + w.hhi[l]; g.in_ab = W + w.ab[l - 1]; g.out_dz = W + w.dz[l - 1];
     g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = l; g.dst_layer = l - 1;
-    e = launch_lgemm(g, p->n_sm, st);
+    e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(dgrad)");
   }
   WgradArgs wg; std::memset(&wg, 0, sizeof(wg)); wg.trace = g_trace;
@@ -666,7 +676,7 @@ static int mfn_forward_impl(const inr_plan* p, const MfnWorkspace& w, const Loss
     g.out_hi = W + w.z[i]; g.out_lo = W + w.g[i]; g.out_ab = W + w.cp[i]; g.out_h = i >= 1 ? W + w.h[i] : nullptr;
     g.feat_tile_bytes = wtile; g.bs = static_cast<int>(bs);
     if (M.bounded && i >= 1) { g.dist = dist; g.bound_lo = M.bound_lo[i]; g.bound_hi = M.bound_hi[i]; }
-    e = launch_lgemm(g, p->n_sm, st);
+    e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn fwd)");
   }
   x.step_counter = nullptr;
@@ -707,7 +717,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
       g.head_dout = dout; g.head_w = params + M.head_w[kk]; g.head_col = M.stage_head[i - 1] * M.out_f; g.head_ld = M.n_out * M.out_f;
     }
     if (M.bounded && i - 1 >= 1) { g.dist = dist; g.bound_lo = M.bound_lo[i - 1]; g.bound_hi = M.bound_hi[i - 1]; }
-    e = launch_lgemm(g, p->n_sm, st);
+    e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn dgrad)");
   }
   WgradArgs wg; std::memset(&wg, 0, sizeof(wg)); wg.trace = g_trace;

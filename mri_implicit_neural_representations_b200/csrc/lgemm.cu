@@ -20,11 +20,14 @@
 
 namespace inr {
 
+#define LG_TRACE(slot) do { if (a.trace && (slot) < 16) a.trace[64 + blockIdx.x * 32 + (slot)] = global_ns(); } while (0)
+
 constexpr int kLgMaxSlots = 12;
 constexpr int kLgRingBytes = 5 * 40960;                                // 204800
 constexpr int kLgComputeThreads = 512;
 constexpr int kLgThreads = 128 + kLgComputeThreads;
 constexpr int kLgSmem = kLgRingBytes + 1024;
+
 
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
@@ -42,7 +45,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
 }
 
-template <int PASSES, int MODE>
+template <int PASSES, int MODE, int KSTEPS>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2];
@@ -51,11 +54,10 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = a.n_tiles * a.n_nblocks;
-  // A ring slot holds KS consecutive K=32 stages of every operand: 1 for the 3-pass GEMMs, 2 (K = 64) for the 1-pass
-  // GEMMs, so the single producer / MMA threads pay their per-slot barrier overhead half as often
-  constexpr int KS = PASSES == 3 ? 1 : 2;
-  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 64 * KS;       // B part of a slot: KS x (nt rows x 32 K x 2 B)
-  constexpr uint32_t a_bytes = kWStageABytes * KS;
+  // A ring slot holds KSTEPS consecutive K=16 steps of every operand (a K=32 stage image is two contiguous halves):
+  // few steps per slot = deeper ring of smaller copies, many = fewer barrier round trips for the single producer / MMA threads
+  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 32 * KSTEPS;    // B part of a slot: KSTEPS x (nt rows x 16 K x 2 B)
+  constexpr uint32_t a_bytes = (kWStageABytes / 2) * KSTEPS;
   const uint32_t a_lo_off = a_bytes;
   const uint32_t b_hi_off = PASSES == 3 ? 2 * a_bytes : a_bytes;
   const uint32_t b_lo_off = b_hi_off + b_bytes;
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   if (n_slots > kLgMaxSlots) n_slots = kLgMaxSlots;
 
   if (tid == 0) {
+    LG_TRACE(0);
     for (int i = 0; i < kLgMaxSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads); }
     mbar_fence_init();
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (tid == 0) LG_TRACE(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -94,13 +98,14 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
-          const int n_it = S.k_stages / KS;
+          const int n_it = S.k_stages * 2 / KSTEPS;
           const uint8_t* ah = S.a_hi + static_cast<size_t>(tile) * S.a_tile_bytes;
           const uint8_t* al = PASSES == 3 ? S.a_lo + static_cast<size_t>(tile) * S.a_tile_bytes : nullptr;
           const uint8_t* bh = S.b_hi + static_cast<size_t>(nb) * n_it * b_bytes;
           const uint8_t* bl = PASSES == 3 ? S.b_lo + static_cast<size_t>(nb) * n_it * b_bytes : nullptr;
           for (int s = 0; s < n_it; ++s) {
             mbar_wait(&empty[slot], ph ^ 1);
+            if (a.dbg & 2) { mbar_arrive(&full[slot]); if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; } continue; }
             mbar_arrive_expect_tx(&full[slot], slot_bytes);
             uint8_t* dst = smem + slot * slot_bytes;
             bulk_g2s(dst, ah, a_bytes, &full[slot]);
@@ -124,8 +129,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       // descriptors differ only in their 14-bit start-address field (bytes >> 4): build once, add offsets
       const uint64_t da0 = umma_smem_desc(smem_u32(smem), 2048, 128);
       const uint64_t db0 = umma_smem_desc(smem_u32(smem), b_lbo, 128);
-      const uint32_t bk16 = (2 * b_lbo) >> 4;                            // one K=16 step inside a B stage
-      const uint32_t bstage16 = (static_cast<uint32_t>(a.nt) * 64) >> 4;  // one K=32 stage of B
+      const uint32_t bk16 = (2 * b_lbo) >> 4;                            // one K=16 step of B: two k-groups of nt x 16 B
       uint32_t slot = 0, ph = 0, n_done = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
         const uint32_t ab = n_done & 1, use = n_done >> 1;
@@ -134,15 +138,16 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
           const uint32_t acc = tmem + ab * 256 + S.acc_col;
-          const int n_it = S.k_stages / KS;
+          const int n_it = S.k_stages * 2 / KSTEPS;
           for (int s = 0; s < n_it; ++s) {
             mbar_wait(&full[slot], ph);
             tc_fence_after();
             const uint32_t so = (slot * slot_bytes) >> 4;
+            if (!(a.dbg & 1))
 #pragma unroll
-            for (int k = 0; k < 2 * KS; ++k) {          // K = 16 steps inside the slot
+            for (int k = 0; k < KSTEPS; ++k) {          // K = 16 steps inside the slot
               const uint64_t dah = da0 + so + k * 256;                                            // 4096 B per step
-              const uint64_t dbh = db0 + so + (b_hi_off >> 4) + (k >> 1) * bstage16 + (k & 1) * bk16;
+              const uint64_t dbh = db0 + so + (b_hi_off >> 4) + k * bk16;
               umma_f16(acc, dah, dbh, idesc, (s | k) != 0);
               if (PASSES == 3) {
                 const uint64_t dal = dah + (a_lo_off >> 4);
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           }
         }
         umma_commit(&acc_full[ab]);
+        LG_TRACE(2 + 3 * n_done);
       }
     }
   } else if (warp >= 4) {
@@ -193,6 +199,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         }
         mbar_wait(&acc_full[ab], use & 1);
         tc_fence_after();
+        if (tid == 128) LG_TRACE(3 + 3 * n_done);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int c0 = 24 * sub + 8 * i;                 // feature inside the N-block
@@ -259,6 +266,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         }
         mbar_wait(&acc_full[ab], use & 1);
         tc_fence_after();
+        if (tid == 128) LG_TRACE(3 + 3 * n_done);
         const int grow = tile * kTileM + row;
         bool masked = false;            // BoundedLinear: this row's input to the linear was zeroed
         if (a.dist && grow < a.bs) { const float d = a.dist[grow]; masked = (d < a.bound_lo) || (d > a.bound_hi); }
@@ -322,6 +330,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           }
         }
       }
+      if (tid == 128) LG_TRACE(4 + 3 * n_done);
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
     }
@@ -335,30 +344,35 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem);
+  if (tid == 0) LG_TRACE(15);
 }
 
 cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   const int items = a.n_tiles * a.n_nblocks;
   const int grid = items < n_sm ? items : n_sm;
   if (grid <= 0) return cudaSuccess;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(lgemm_kernel<3, LG_WIRE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lgemm_kernel<1, LG_WIRE_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lgemm_kernel<1, LG_MFN_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lgemm_kernel<1, LG_MFN_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
   const int expect_passes = a.mode == LG_WIRE_FWD ? 3 : 1;
   if (a.passes != expect_passes) return cudaErrorInvalidValue;
+#define LG_LAUNCH(P, M, K)                                                                                        \
+  do {                                                                                                            \
+    static bool attr = false;                                                                                     \
+    if (!attr) {                                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(lgemm_kernel<P, M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem); \
+      if (e != cudaSuccess) return e;                                                                             \
+      attr = true;                                                                                                \
+    }                                                                                                             \
+    lgemm_kernel<P, M, K><<<grid, kLgThreads, kLgSmem, stream>>>(a);                                              \
+  } while (0)
   switch (a.mode) {
-    case LG_WIRE_FWD:   lgemm_kernel<3, LG_WIRE_FWD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
-    case LG_WIRE_DGRAD: lgemm_kernel<1, LG_WIRE_DGRAD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
-    case LG_MFN_FWD:    lgemm_kernel<1, LG_MFN_FWD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
-    case LG_MFN_DGRAD:  lgemm_kernel<1, LG_MFN_DGRAD><<<grid, kLgThreads, kLgSmem, stream>>>(a); break;
+    case LG_WIRE_FWD:
+      LG_LAUNCH(3, LG_WIRE_FWD, 2);
+      break;
+    case LG_WIRE_DGRAD: LG_LAUNCH(1, LG_WIRE_DGRAD, 4); break;
+    case LG_MFN_FWD:    LG_LAUNCH(1, LG_MFN_FWD, 4); break;
+    case LG_MFN_DGRAD:  LG_LAUNCH(1, LG_MFN_DGRAD, 4); break;
     default: return cudaErrorInvalidValue;
   }
+#undef LG_LAUNCH
   return cudaGetLastError();
 }
 

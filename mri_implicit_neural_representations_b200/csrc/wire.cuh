@@ -70,6 +70,8 @@ struct LGemmArgs {
   float bound_lo, bound_hi; // FWD: rows with dist outside [lo, hi] are zeroed before THIS stage's linear;
                             // DGRAD: the same mask of the TARGET stage, applied to the stored dh (W-wgrad and dgrad operand)
   uint32_t feat_tile_bytes; // bytes of one 128-row image of the epilogue's feature images (MFN: 128 * width * 2)
+  int dbg;                  // debug (INR_LGEMM_DBG): bit 0 skip MMAs, bit 1 skip operand copies (timing experiments only)
+  unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)
 };
 
 struct WireModel {
