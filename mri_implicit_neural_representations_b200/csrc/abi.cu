@@ -32,6 +32,8 @@ cudaError_t launch_mfn_head(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_dout_amax(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_scalars(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_top(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_gabor_prep(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_gabor_grad(const MfnAuxArgs& a, cudaStream_t st);
 }  // namespace inr
 
 using namespace inr;
@@ -84,7 +86,8 @@ static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs);
 extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (!d || !out) return fail(INR_EINVAL, "null argument");
   if (d->model == INR_MODEL_WIRE) return wire_plan_create(d, out);
-  if (d->model == INR_MODEL_FOURIER || d->model == INR_MODEL_MS_FOURIER || d->model == INR_MODEL_MS_BOUNDED_FOURIER)
+  if (d->model == INR_MODEL_FOURIER || d->model == INR_MODEL_MS_FOURIER || d->model == INR_MODEL_MS_BOUNDED_FOURIER ||
+      d->model == INR_MODEL_GABOR)
     return mfn_plan_create(d, out);
   if (d->model != INR_MODEL_SIREN && d->model != INR_MODEL_FFN) return fail(INR_EUNSUPPORTED, "model kind not built yet");
   if (d->width != kWidth) return fail(INR_EUNSUPPORTED, "tensor-core chain kernels are built for network_width 256");
@@ -121,7 +124,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
     SegDesc sw{};
     sw.off = off; sw.rows = rows; sw.cols = cols; sw.layer = l;
     sw.fwd_scale = sw.bwd_scale = (M.act == ACT_SIN) ? M.w0 : 1.f;
-    sw.scale_slot = -1;
+    sw.scale_slot = -1; sw.gfin_off = -1;
     if (l < M.n_gemm) {
       sw.pack_fwd = 1;
       sw.perm_e = (l == 0 && M.input_kind == INPUT_GAUSS) ? M.enc_size : 0;
@@ -133,7 +136,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
     M.b_off[l] = off;
     p->tensors.push_back({off, rows, 1, l, 1, 0, 0});
     SegDesc sb{};
-    sb.off = off; sb.rows = rows; sb.cols = 1; sb.layer = l; sb.scale_slot = -1;
+    sb.off = off; sb.rows = rows; sb.cols = 1; sb.layer = l; sb.scale_slot = -1; sb.gfin_off = -1;
     p->segs.push_back(sb);
     off += rows;
   }
@@ -254,6 +257,11 @@ extern "C" int inr_workspace_layout(const inr_plan* p, int64_t bs, uint64_t* out
     }
     out[36] = w.x; out[37] = w.gl; out[38] = w.part; out[39] = w.scal; out[40] = w.gpart;
     out[41] = static_cast<uint64_t>(w.n_tiles); out[42] = static_cast<uint64_t>(w.n_split); out[43] = w.total;
+    if (n >= 60) {     // Gabor extras: q images at [44+l], then gfin, gpart float stride, aux offset of stage 0, envelope image
+      for (int l = 0; l < kMaxLayers; ++l) out[44 + l] = (p->mm.gabor && l <= p->mm.top) ? w.q[l] : 0;
+      out[56] = w.gfin; out[57] = static_cast<uint64_t>(gpart_stride(p->mm.g_floats));
+      out[58] = static_cast<uint64_t>(p->mm.gabor ? p->mm.aux_off[0] : 0); out[59] = w.e;
+    }
     return INR_OK;
   }
   const Workspace w = plan_workspace(p, bs);
@@ -268,7 +276,7 @@ static void fill_adam(const inr_plan* p, AdamArgs& a) {
   a.n_seg = static_cast<int>(p->segs.size());
   for (int i = 0; i < a.n_seg; ++i) a.seg[i] = p->segs[i];
   a.n_params = p->is_mfn ? p->mm.n_params : p->model.n_params;
-  a.gstride = gpart_stride(a.n_params);
+  a.gstride = gpart_stride(p->is_mfn ? p->mm.g_floats : a.n_params);
 }
 
 static void fill_wgrad(const inr_plan* p, const Workspace& w, uint8_t* ws, WgradArgs& g) {
@@ -510,7 +518,8 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
   M.L = L; M.width = W; M.in_f = IN; M.out_f = OF;
   M.input_kind = d->encoder == INR_ENC_GAUSS ? INPUT_GAUSS : INPUT_DENSE;
   M.enc_size = d->enc_size;
-  const bool multi = d->model != INR_MODEL_FOURIER;
+  const bool multi = d->model == INR_MODEL_MS_FOURIER || d->model == INR_MODEL_MS_BOUNDED_FOURIER;
+  M.gabor = d->model == INR_MODEL_GABOR ? 1 : 0;
   M.bounded = d->model == INR_MODEL_MS_BOUNDED_FOURIER ? 1 : 0;
   for (int i = 0; i < kMfnMaxStages; ++i) { M.stage_head[i] = -1; M.bound_lo[i] = 0.f; M.bound_hi[i] = 3.0e38f; }
   if (multi) {
@@ -533,11 +542,11 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
   int off = 0;
   uint32_t wo = 0;
   auto add_seg = [&](int o, int rows, int cols, int stage, bool is_bias, bool dead, int scale_slot, int pf, int pb,
-                     uint32_t wf, uint32_t wd) {
+                     uint32_t wf, uint32_t wd, int gfin_off = -1) {
     p->tensors.push_back({o, rows, cols, stage, is_bias ? 1 : 0, 0, dead ? 1 : 0});
     SegDesc s{};
     s.off = o; s.rows = rows; s.cols = cols; s.layer = stage; s.pack_fwd = pf; s.pack_bwd = pb; s.wf_off = wf; s.wd_off = wd;
-    s.fwd_scale = 1.f; s.bwd_scale = 1.f; s.layout = 1; s.nt = kMfnNT; s.scale_slot = scale_slot; s.frozen = dead ? 1 : 0;
+    s.fwd_scale = 1.f; s.bwd_scale = 1.f; s.layout = 1; s.nt = kMfnNT; s.scale_slot = scale_slot; s.frozen = dead ? 1 : 0; s.gfin_off = gfin_off;
     p->segs.push_back(s);
   };
   for (int i = 1; i <= L; ++i) {
@@ -551,14 +560,26 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
     M.head_w[k] = off; add_seg(off, OF, W, M.head_stage[k], false, dead, -1, 0, 0, 0, 0); off += OF * W;
     M.head_b[k] = off; add_seg(off, OF, 1, M.head_stage[k], true, dead, -1, 0, 0, 0, 0); off += OF;
   }
+  int gfin = 0;
   for (int i = 0; i <= L; ++i) {
     const bool dead = i > M.top;
+    if (M.gabor) {      // filters.i.mu, filters.i.gamma come first (module parameters before the `linear` child)
+      M.mu_off[i] = off; M.pk_mu[i] = wo; wo += static_cast<uint32_t>(W) * IN * 2; M.gfin_mu[i] = gfin; gfin += W * IN;
+      add_seg(off, W, IN, i, false, dead, SC_LAYER_SCALE + i, 1, 0, M.pk_mu[i], 0, M.gfin_mu[i]); off += W * IN;
+      M.gamma_off[i] = off; M.gfin_gamma[i] = gfin; gfin += W;
+      add_seg(off, W, 1, i, true, dead, SC_LAYER_SCALE + i, 0, 0, 0, 0, M.gfin_gamma[i]); off += W;
+    }
     M.filt_w[i] = off; M.pk_filt[i] = wo; wo += static_cast<uint32_t>(W) * IN * 2;
     add_seg(off, W, IN, i, false, dead, SC_LAYER_SCALE + i, 1, 0, M.pk_filt[i], 0); off += W * IN;
     M.filt_b[i] = off; add_seg(off, W, 1, i, true, dead, SC_LAYER_SCALE + i, 0, 0, 0, 0); off += W;
   }
   M.n_params = off;
   M.wpack_bytes = wo;
+  M.gfin_floats = gfin;
+  int goff = gpart_stride(off);
+  if (M.gabor)
+    for (int i = 0; i <= M.top; ++i) { M.aux_off[i] = goff; goff += W * 16; }
+  M.g_floats = goff;
   // ---- wgrad units
   const int wc = W / 128, ic = IN / 128;
   const uint32_t wtile = static_cast<uint32_t>(kTileM) * W * 2, xtile = static_cast<uint32_t>(kTileM) * IN * 2;
@@ -593,6 +614,25 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
         u.n = 128; u.n_chunks = nch; u.out_off = M.filt_w[i]; u.out_ld = IN; u.row0 = mc * 128; u.col0 = c0 * 128;
         u.rows_valid = 128; u.cols_valid = 128 * nch; u.bias_off = c0 == 0 ? M.filt_b[i] : -1;
         p->units.push_back(u); p->unit_layer.push_back(200 + i);
+      }
+  if (M.gabor)
+    for (int i = 0; i <= M.top; ++i)
+      for (int mc = 0; mc < wc; ++mc) {
+        for (int c0 = 0, per = chunk_group(ic); c0 < ic; c0 += per) {      // Qx_i = Q[i]^T X  (at mu_i's offset)
+          const int nch = (ic - c0) < per ? (ic - c0) : per;
+          WgradUnit u{};
+          u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+          u.b_tile_stride = xtile; u.b_sub = c0 * 32768; u.b_bytes = 32768;
+          u.n = 128; u.n_chunks = nch; u.out_off = M.mu_off[i]; u.out_ld = IN; u.row0 = mc * 128; u.col0 = c0 * 128;
+          u.rows_valid = 128; u.cols_valid = 128 * nch; u.bias_off = -1;
+          p->units.push_back(u); p->unit_layer.push_back(500 + i);
+        }
+        WgradUnit u{};                                                      // (s, u)_i = Q[i]^T [1 | |x|^2]
+        u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+        u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+        u.n = kDzLastCols; u.out_off = M.aux_off[i]; u.out_ld = 16; u.row0 = mc * 128; u.col0 = 0;
+        u.rows_valid = 128; u.cols_valid = 16; u.bias_off = -1;
+        p->units.push_back(u); p->unit_layer.push_back(600 + i);
       }
   for (int k = 0; k < M.n_heads; ++k) {     // dV_k^T[o][f] = sum_rows dy_k[o] z[f]
     if (!M.head_live[k]) continue;
@@ -636,7 +676,15 @@ static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs) {
     for (int i = 1; i <= M.top; ++i) { w.dhu[i] = o; o += wimg; }
     w.ones = o; o += 4096;
   }
-  w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * gpart_stride(M.n_params) * 4, 1024);
+  if (M.gabor) {
+    for (int i = 0; i <= M.top; ++i) { w.q[i] = o; o += wimg; }
+    w.e = o; o += wimg;
+    w.xa = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024);
+    w.xn = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 4, 1024);
+    w.mn = o; o += align_up(static_cast<uint64_t>(M.top + 1) * M.width * 4, 1024);
+    w.gfin = o; o += align_up(static_cast<uint64_t>(M.gfin_floats) * 4, 1024);
+  }
+  w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * gpart_stride(M.g_floats) * 4, 1024);
   w.total = o;
   return w;
 }
@@ -662,8 +710,24 @@ static int mfn_forward_impl(const inr_plan* p, const MfnWorkspace& w, const Loss
   cudaError_t e = launch_mfn_encode(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "mfn_encode_kernel");
   const uint32_t wtile = static_cast<uint32_t>(kTileM) * M.width * 2, xtile = static_cast<uint32_t>(kTileM) * M.in_f * 2;
+  if (M.gabor) {
+    e = launch_mfn_gabor_prep(x, st);
+    if (e != cudaSuccess) return cuda_fail(e, "mfn_gabor_prep_kernel");
+  }
   for (int i = 0; i <= M.top; ++i) {
+    if (M.gabor) {      // envelope of stage i: E = exp(-gamma/2 (|x|^2 + |mu|^2 - 2 x mu^T))
+      LGemmArgs ge{};
+      ge.seg[0].a_hi = W + w.x; ge.seg[0].b_hi = wp + M.pk_mu[i]; ge.seg[0].a_tile_bytes = xtile; ge.seg[0].k_stages = M.in_f / 32;
+      ge.seg[0].acc_col = 0; ge.n_seg = 1;
+      ge.nt = kMfnNT; ge.n_tiles = w.n_tiles; ge.n_nblocks = M.width / kMfnNT; ge.passes = 1; ge.mode = LG_GABOR_E;
+      ge.xn = reinterpret_cast<const float*>(W + w.xn); ge.gamma = params + M.gamma_off[i];
+      ge.mn = reinterpret_cast<const float*>(W + w.mn) + static_cast<size_t>(i) * M.width;
+      ge.out_hi = W + w.e; ge.feat_tile_bytes = wtile; ge.bs = static_cast<int>(bs);
+      e = launch_lgemm((ge.trace = lgemm_trace_ptr(), ge.dbg = lgemm_dbg(), ge), p->n_sm, st);
+      if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(gabor envelope)");
+    }
     LGemmArgs g{};
+    if (M.gabor) g.in_e = W + w.e;
     g.seg[0].a_hi = W + w.x; g.seg[0].b_hi = wp + M.pk_filt[i]; g.seg[0].a_tile_bytes = xtile; g.seg[0].k_stages = M.in_f / 32; g.seg[0].acc_col = 0;
     g.n_seg = 1;
     if (i >= 1) {
@@ -709,6 +773,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
     g.in_y = W + w.g[i - 1]; g.in_ab = W + w.cp[i - 1]; g.in_h = i - 1 >= 1 ? W + w.h[i - 1] : nullptr;
     g.out_dz = i - 1 >= 1 ? W + w.dh[i - 1] : nullptr; g.out_dp = W + w.dp[i - 1];
     g.out_dzu = (M.bounded && i - 1 >= 1) ? W + w.dhu[i - 1] : nullptr;
+    g.out_q = M.gabor ? W + w.q[i - 1] : nullptr;
     g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = i; g.dst_layer = i - 1;
     g.feat_tile_bytes = wtile; g.bs = static_cast<int>(bs); g.out_f = M.out_f;
     if (dout && M.stage_head[i - 1] >= 0) {
@@ -725,15 +790,22 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
   for (int i = 0; i < wg.n_units; ++i) {
     WgradUnit u = p->units[i];
     const int code = p->unit_layer[i];
-    if (code >= 400) { u.a_off = w.dhu[code - 400]; u.b_off = w.ones; }
+    if (code >= 600) { u.a_off = w.q[code - 600]; u.b_off = w.xa; }
+    else if (code >= 500) { u.a_off = w.q[code - 500]; u.b_off = w.x; }
+    else if (code >= 400) { u.a_off = w.dhu[code - 400]; u.b_off = w.ones; }
     else if (code >= 300) { const int k = code - 300; u.a_off = w.z[M.head_stage[k]]; u.b_off = w.dout[M.stage_head[M.head_stage[k]]]; }
     else if (code >= 200) { u.a_off = w.dp[code - 200]; u.b_off = w.x; }
     else { const int s = code - 100; u.a_off = w.dh[s]; u.b_off = w.z[s - 1]; }
     wg.u[i] = u;
   }
-  wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = gpart_stride(M.n_params); wg.ws = W; wg.gpart_off = w.gpart;
+  wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = gpart_stride(M.g_floats); wg.ws = W; wg.gpart_off = w.gpart;
   e = launch_wgrad(wg, st);
-  return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel(mfn)");
+  if (e != cudaSuccess) return cuda_fail(e, "wgrad_kernel(mfn)");
+  if (M.gabor) {
+    e = launch_mfn_gabor_grad(x, st);
+    if (e != cudaSuccess) return cuda_fail(e, "mfn_gabor_grad_kernel");
+  }
+  return INR_OK;
 }
 
 extern "C" int inr_pack_weights(const inr_plan* p, const float* params, void* wpack, void* stream) {
@@ -812,6 +884,7 @@ extern "C" int inr_backward_dist(const inr_plan* p, const float* params, const v
   ma.n_split = mw.n_split; ma.n_tiles = mw.n_tiles;
   ma.params = const_cast<float*>(params); ma.grads = grads;
   ma.gpart = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.gpart);
+  ma.gfin = p->mm.gabor ? reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.gfin) : nullptr;
   ma.scal = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.scal);
   ma.do_adam = 0;
   cudaError_t me = launch_adam(ma, st);
@@ -846,6 +919,8 @@ extern "C" int inr_backward(const inr_plan* p, const float* params, const void* 
     ma.n_split = mw.n_split; ma.n_tiles = mw.n_tiles;
     ma.params = const_cast<float*>(params); ma.grads = grads;
     ma.gpart = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.gpart);
+  ma.gfin = p->mm.gabor ? reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.gfin) : nullptr;
+    ma.gfin = p->mm.gabor ? reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.gfin) : nullptr;
     ma.scal = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + mw.scal);
     ma.do_adam = 0;
     cudaError_t me = launch_adam(ma, st);
@@ -928,6 +1003,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
     ma.n_split = mw.n_split; ma.n_tiles = mw.n_tiles;
     ma.params = params; ma.m = m; ma.v = v; ma.wpack = static_cast<uint8_t*>(wpack);
     ma.gpart = reinterpret_cast<const float*>(wsb + mw.gpart); ma.scal = reinterpret_cast<const float*>(wsb + mw.scal);
+    ma.gfin = p->mm.gabor ? reinterpret_cast<const float*>(wsb + mw.gfin) : nullptr;
     ma.hyper = hyper_dev; ma.step = step_dev; ma.loss_out = loss_out_dev;
     ma.row_offset = row_cursor_dev; ma.row_advance = static_cast<int>(bs);
     ma.do_adam = no_adam ? 0 : 1; ma.scal_has_bc = no_adam ? 0 : 1; ma.grads = grads_only;

@@ -139,6 +139,7 @@ struct SegDesc {          // one parameter tensor for the optimiser / packer
   int layout;             // 0: chain stages (256 rows x 32 K); 1: lgemm N-blocks of `nt` rows x 32 K
   int nt;
   int scale_slot;         // >= 0: this tensor's gradient partials carry scal[scale_slot] instead of the global loss scale
+  int gfin_off;           // >= 0: the (scaled) gradient is read from gfin[gfin_off + index] instead of the split partials
   int frozen;             // no gradient ever reaches this tensor (dead stage / unused head): skipped like grad None in torch
 };
 constexpr int kMaxSegs = 64;
@@ -149,6 +150,7 @@ struct AdamArgs {
   float* params; float* m; float* v;
   float* grads;             // optional: unscaled fp32 gradients are written here when non-null
   uint8_t* wpack;
+  const float* gfin;        // finalised gradients of the tensors with gfin_off >= 0 (Gabor mu / gamma) or null
   const float* gpart;       // [n_split][n_params] gradient partials (scaled by S), or plain gradients (n_split 1)
   const float* scal;        // step scalars written by the backward prologue, or null (scale 1, no loss)
   const float* hyper;       // device: lr, beta1, beta2, eps, weight_decay, reg_l1, reg_l2

@@ -14,6 +14,9 @@
 //                   (reference src/models/mfn.py:34-38,57-58; BoundedLinear :281-286 as a row mask on the linear term).
 //                   Two segments (filter GEMM, linear GEMM), nt = 128; stage 0 has the filter segment only.
 //   LG_MFN_DGRAD  : dz_{i-1} = dh_i W_i (+ head gradient), then dh_{i-1} = dz g, dp_{i-1} = dz h cos(p).
+//   LG_GABOR_E    : Gabor envelope E = exp(-gamma/2 (|x|^2 + |mu|^2 - 2 x mu^T)) (reference mfn.py:117-131) as an fp16
+//                   image; MFN_FWD then stores f = sin(p) E and cos(p) E in place of sin / cos, which makes the
+//                   backward epilogue of a Gabor stage identical to the Fourier one plus the q = dL/df * f image.
 #include <cuda_runtime.h>
 #include "inr_ptx.cuh"
 #include "wire.cuh"
@@ -81,6 +84,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     for (int j = tid; j < width; j += kLgThreads) {
       s_ba[j] = a.bias ? a.bias[j] : 0.f;
       s_bb[j] = a.phi[j];
+    }
+  } else if (MODE == LG_GABOR_E) {
+    const int width = a.n_nblocks * a.nt;
+    for (int j = tid; j < width; j += kLgThreads) {
+      s_ba[j] = a.gamma[j];
+      s_bb[j] = a.mn[j];
     }
   }
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
@@ -286,11 +295,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             tmem_ld8(acc + c0, vp);                        // filter pre-activation  x Om^T
             if (a.n_seg == 2) tmem_ld8(acc + a.nt + c0, vh);   // linear  z_{i-1} W^T
             tmem_ld_wait();
-            float g[8], c[8], h[8], z[8];
+            float g[8], c[8], h[8], z[8], env[8];
+            if (a.in_e) unpack8(ld_global_nc_v4(a.in_e + off), env);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float p = vp[e] + s_bb[f0 + e];
               g[e] = fast_sin(p); c[e] = fast_cos(p);
+              if (a.in_e) { g[e] *= env[e]; c[e] *= env[e]; }     // Gabor: f = sin(p) E, d f / d p = cos(p) E
               h[e] = a.n_seg == 2 ? ((masked ? 0.f : vh[e]) + s_ba[f0 + e]) : 1.f;
               z[e] = g[e] * h[e];
             }
@@ -300,11 +311,19 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               st_global_v4(a.out_ab + off, pack8(c));
               if (a.n_seg == 2) st_global_v4(a.out_h + off, pack8(h));
             }
+          } else if (MODE == LG_GABOR_E) {
+            tmem_ld8(acc + c0, vp);                        // x mu^T
+            tmem_ld_wait();
+            const float xn = a.xn[grow];
+            float env[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) env[e] = __expf(-0.5f * s_ba[f0 + e] * (xn + s_bb[f0 + e] - 2.f * vp[e]));
+            st_global_v4(a.out_hi + off, pack8(env));
           } else {
             const uint4 g4 = pre[i][0], c4 = pre[i][1], h4 = pre[i][2];
             tmem_ld8(acc + c0, vp);                        // S[src] * dh_i W_i  = S[src] * dz_{i-1} (before heads)
             tmem_ld_wait();
-            float g[8], c[8], h[8], dh[8], dp[8];
+            float g[8], c[8], h[8], dh[8], dp[8], q[8];
             unpack8(g4, g); unpack8(c4, c); unpack8(h4, h);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -314,10 +333,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
                 for (int o = 0; o < kMaxOut; ++o)
                   if (o < a.out_f) dz = fmaf(hd[o], __ldg(a.head_w + o * (a.n_nblocks * a.nt) + f0 + e), dz);
               }
-              if (a.real_first) { dh[e] = 0.f; dp[e] = dz * c[e]; }
-              else { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; }
+              if (a.real_first) { dh[e] = 0.f; dp[e] = dz * c[e]; q[e] = dz * g[e]; }
+              else { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; q[e] = dh[e] * h[e]; }
               amax = fmaxf(amax, fmaxf(fabsf(dh[e]), fabsf(dp[e])));
+              if (a.out_q) amax = fmaxf(amax, fabsf(q[e]));
             }
+            if (a.out_q) st_global_v4(a.out_q + off, pack8(q));      // Gabor: q = dL/df * f (g holds f = sin(p) E)
             if (!a.real_first) {
               if (a.out_dzu) st_global_v4(a.out_dzu + off, pack8(dh));     // unmasked copy: bias gradient
               if (masked) {
@@ -370,6 +391,7 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
     case LG_WIRE_DGRAD: LG_LAUNCH(1, LG_WIRE_DGRAD, 4); break;
     case LG_MFN_FWD:    LG_LAUNCH(1, LG_MFN_FWD, 4); break;
     case LG_MFN_DGRAD:  LG_LAUNCH(1, LG_MFN_DGRAD, 4); break;
+    case LG_GABOR_E:    LG_LAUNCH(1, LG_GABOR_E, 4); break;
     default: return cudaErrorInvalidValue;
   }
 #undef LG_LAUNCH

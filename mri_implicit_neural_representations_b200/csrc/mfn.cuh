@@ -32,8 +32,18 @@ struct MfnModel {
   int head_w[kMfnMaxStages], head_b[kMfnMaxStages];
   int filt_w[kMfnMaxStages], filt_b[kMfnMaxStages];     // stage i = 0..L
   int n_params;
+  // Gabor filters (GaborNet / KGaborNet, reference mfn.py:96-204): per stage mu [width, in_f] and gamma [width] precede
+  // linear.{weight,bias} in the state_dict.  Their gradients come from three split-K reductions of q = dL/df * f:
+  //   Qx = q^T x (written at mu's own offset), s = sum_rows q, u = sum_rows q |x|^2 (aux block [width][16], cols 0 / 1)
+  //   d mu_j = gamma_j (Qx_j - s_j mu_j),   d gamma_j = -1/2 (u_j + |mu_j|^2 s_j - 2 mu_j . Qx_j)
+  int gabor;
+  int mu_off[kMfnMaxStages], gamma_off[kMfnMaxStages];
+  int aux_off[kMfnMaxStages];        // float offset of the stage's aux block inside one gpart split copy (>= n_params)
+  int gfin_mu[kMfnMaxStages], gfin_gamma[kMfnMaxStages];   // float offsets in the finalised-gradient buffer
+  int g_floats;                      // floats of one gpart split copy: n_params (+ aux blocks)
+  int gfin_floats;
   // packed fp16 operands (bytes in wpack)
-  uint32_t pk_filt[kMfnMaxStages], pk_lin[kMfnMaxStages], pk_lin_t[kMfnMaxStages];
+  uint32_t pk_filt[kMfnMaxStages], pk_lin[kMfnMaxStages], pk_lin_t[kMfnMaxStages], pk_mu[kMfnMaxStages];
   uint32_t wpack_bytes;
 };
 
@@ -42,6 +52,12 @@ struct MfnWorkspace {
   uint64_t dout[kMfnMaxStages];      // per live head
   uint64_t dhu[kMfnMaxStages];       // bounded: dh with NO row mask (bias gradient); dh[] then holds the masked rows
   uint64_t ones;                     // bounded: [128 x 16] fp16 ones, B operand of the bias units
+  uint64_t q[kMfnMaxStages];         // Gabor: q_i = S_i dL/df_i * f_i images
+  uint64_t e;                        // Gabor: envelope image of the stage being evaluated (transient)
+  uint64_t xa;                       // Gabor: per tile [128 x 16] fp16 image, column 0 = 1, column 1 = |x|^2
+  uint64_t xn;                       // Gabor: |x|^2 per row, fp32
+  uint64_t mn;                       // Gabor: |mu_j|^2 per stage and feature, fp32 [top + 1][width]
+  uint64_t gfin;                     // Gabor: finalised (still scaled) d mu / d gamma, fp32
   uint64_t gl, part, scal, gpart, total;
   int n_tiles, n_split;
 };

@@ -22,8 +22,10 @@ __device__ __forceinline__ uint4 mfn_pack8(const float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------------------ input image
 __global__ void __launch_bounds__(256) mfn_encode_kernel(const __grid_constant__ MfnAuxArgs a) {
+  __shared__ float s_xn[2][kTileM];     // Gabor: |x|^2 partial sums of the two threads that share a row (fixed order)
   const MfnModel& M = a.m;
   const int tile = blockIdx.x, tid = threadIdx.x;
+  float xn_part = 0.f;
   if (tile == 0 && tid == 0 && a.step_counter) *a.step_counter += 1;
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const uint32_t tile_bytes = kTileM * M.in_f * 2;
@@ -51,7 +53,69 @@ __global__ void __launch_bounds__(256) mfn_encode_kernel(const __grid_constant__
       for (int e = 0; e < 8; ++e) v[e] = grow < a.bs ? xr[e] : 0.f;
     }
     st_global_v4(ximg + static_cast<size_t>(kg) * 2048 + row * 16, mfn_pack8(v));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xn_part = fmaf(v[e], v[e], xn_part);     // thread tid always owns row tid & 127
   }
+  if (M.gabor) {
+    // |x|^2 per row from the fp32 values (reference mfn.py:127) and the [1 | |x|^2] image the (s, u) wgrad units read
+    s_xn[tid >> 7][tid & (kTileM - 1)] = xn_part;
+    __syncthreads();
+    if (tid < kTileM) {
+      const float xn = s_xn[0][tid] + s_xn[1][tid];
+      reinterpret_cast<float*>(a.ws + a.w.xn)[static_cast<size_t>(tile) * kTileM + tid] = xn;
+      const bool valid = tile * kTileM + tid < a.bs;
+      uint8_t* xa = a.ws + a.w.xa + static_cast<size_t>(tile) * kDzLastBytes;
+      st_global_v4(xa + tid * 16, make_uint4(valid ? pack_h2(1.f, xn) : 0u, 0u, 0u, 0u));
+      st_global_v4(xa + 2048 + tid * 16, make_uint4(0u, 0u, 0u, 0u));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Gabor helpers
+// |mu_j|^2 for every live stage (one warp per feature row), consumed by the envelope epilogue.
+__global__ void __launch_bounds__(256) mfn_gabor_prep_kernel(const __grid_constant__ MfnAuxArgs a) {
+  const MfnModel& M = a.m;
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= (M.top + 1) * M.width) return;
+  const int i = warp / M.width, j = warp % M.width;
+  const float* mu = a.params + M.mu_off[i] + static_cast<size_t>(j) * M.in_f;
+  float acc = 0.f;
+  for (int k = lane; k < M.in_f; k += 32) acc = fmaf(mu[k], mu[k], acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) reinterpret_cast<float*>(a.ws + a.w.mn)[warp] = acc;
+}
+
+// Finalise d mu and d gamma from the split-K reductions (still carrying the stage scale S_i; the optimiser divides):
+//   d mu_jk = gamma_j (Qx_jk - s_j mu_jk),   d gamma_j = -1/2 (u_j + |mu_j|^2 s_j - 2 sum_k mu_jk Qx_jk)
+// (derivation: f_j = sin(p_j) exp(-gamma_j D_j / 2), D_j = |x|^2 + |mu_j|^2 - 2 x.mu_j, q_j = dL/df_j f_j;
+//  dL/dmu_j = sum_rows q_j gamma_j (x - mu_j), dL/dgamma_j = -1/2 sum_rows q_j D_j; reference mfn.py:117-131.)
+// One warp per (stage, feature); all split partials are added in split order, so the result is run-to-run identical.
+__global__ void __launch_bounds__(256) mfn_gabor_grad_kernel(const __grid_constant__ MfnAuxArgs a, int n_split, int gstride) {
+  const MfnModel& M = a.m;
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= (M.top + 1) * M.width) return;
+  const int i = warp / M.width, j = warp % M.width;
+  const float* gp = reinterpret_cast<const float*>(a.ws + a.w.gpart);
+  float* gfin = reinterpret_cast<float*>(a.ws + a.w.gfin);
+  float sj = 0.f, uj = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float* aux = gp + static_cast<size_t>(s) * gstride + M.aux_off[i] + j * 16;
+    sj += aux[0]; uj += aux[1];
+  }
+  const float gamma = a.params[M.gamma_off[i] + j];
+  const float* mu = a.params + M.mu_off[i] + static_cast<size_t>(j) * M.in_f;
+  float dot = 0.f, mn = 0.f;
+  for (int k = lane; k < M.in_f; k += 32) {
+    float qx = 0.f;
+    for (int s = 0; s < n_split; ++s) qx += gp[static_cast<size_t>(s) * gstride + M.mu_off[i] + static_cast<size_t>(j) * M.in_f + k];
+    const float m = mu[k];
+    gfin[M.gfin_mu[i] + static_cast<size_t>(j) * M.in_f + k] = gamma * (qx - sj * m);
+    dot = fmaf(m, qx, dot); mn = fmaf(m, m, mn);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, off); mn += __shfl_xor_sync(0xffffffffu, mn, off); }
+  if (lane == 0) gfin[M.gfin_gamma[i] + j] = -0.5f * (uj + mn * sj - 2.f * dot);
 }
 
 // ------------------------------------------------------------------------------------------------ heads (+ fused loss)
@@ -232,7 +296,7 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
       }
     }
     const size_t off = static_cast<size_t>(kg) * 2048 + row * 16;
-    float g[8], c[8], h[8], dh[8], dp[8];
+    float g[8], c[8], h[8], dh[8], dp[8], q[8];
     mfn_unpack8(ld_global_nc_v4(gimg + off), g);
     mfn_unpack8(ld_global_nc_v4(cimg + off), c);
     if (top >= 1) mfn_unpack8(ld_global_nc_v4(himg + off), h);
@@ -242,10 +306,12 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
 #pragma unroll
       for (int o = 0; o < kMaxOut; ++o)
         if (o < M.out_f) dz = fmaf(dy[o], __ldg(Wt + o * M.width + kg * 8 + e), dz);
-      if (top >= 1) { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; }
-      else { dh[e] = 0.f; dp[e] = dz * c[e]; }
+      if (top >= 1) { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; q[e] = dh[e] * h[e]; }
+      else { dh[e] = 0.f; dp[e] = dz * c[e]; q[e] = dz * g[e]; }
       amax = fmaxf(amax, fmaxf(fabsf(dh[e]), fabsf(dp[e])));
+      if (M.gabor) amax = fmaxf(amax, fabsf(q[e]));
     }
+    if (M.gabor) st_global_v4(a.ws + a.w.q[top] + static_cast<size_t>(tile) * tile_bytes + off, mfn_pack8(q));
     if (top >= 1) {
       if (M.bounded) {
         st_global_v4(a.ws + a.w.dhu[top] + static_cast<size_t>(tile) * tile_bytes + off, mfn_pack8(dh));
@@ -272,6 +338,17 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
 
 cudaError_t launch_mfn_encode(const MfnAuxArgs& a, cudaStream_t st) {
   mfn_encode_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_mfn_gabor_prep(const MfnAuxArgs& a, cudaStream_t st) {
+  const int warps = (a.m.top + 1) * a.m.width;
+  mfn_gabor_prep_kernel<<<(warps + 7) / 8, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_mfn_gabor_grad(const MfnAuxArgs& a, cudaStream_t st) {
+  const int warps = (a.m.top + 1) * a.m.width;
+  const int gstride = (a.m.g_floats + 3) & ~3;
+  mfn_gabor_grad_kernel<<<(warps + 7) / 8, 256, 0, st>>>(a, a.w.n_split, gstride);
   return cudaGetLastError();
 }
 cudaError_t launch_mfn_head(const MfnAuxArgs& a, cudaStream_t st) {

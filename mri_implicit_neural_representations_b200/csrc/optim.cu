@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
   if (sg.frozen) { if (a.grads) a.grads[p] = 0.f; return; }
   const float* gp = a.gpart;
   float g = 0.f;
-  for (int s = 0; s < a.n_split; ++s) g += gp[static_cast<size_t>(s) * a.gstride + p];
+  if (sg.gfin_off >= 0 && a.gfin) g = a.gfin[sg.gfin_off + (p - sg.off)];
+  else
+    for (int s = 0; s < a.n_split; ++s) g += gp[static_cast<size_t>(s) * a.gstride + p];
   g *= (sg.scale_slot >= 0 && a.scal) ? 1.f / a.scal[sg.scale_slot] : s_c[2];
   float w = a.params[p];
   if (a.do_adam) {

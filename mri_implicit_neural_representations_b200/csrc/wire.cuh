@@ -25,7 +25,7 @@ constexpr int kWStageBBytes = kWNT * kStageK * 2;     // 12288: B stage (192 row
 constexpr int kWStageABytes = kTileM * kStageK * 2;   // 8192:  A stage (128 rows x 32 K)
 constexpr int kWMaxDepth = 8;
 
-enum LGemmMode { LG_WIRE_FWD = 1, LG_WIRE_DGRAD = 2, LG_MFN_FWD = 3, LG_MFN_DGRAD = 4 };
+enum LGemmMode { LG_WIRE_FWD = 1, LG_WIRE_DGRAD = 2, LG_MFN_FWD = 3, LG_MFN_DGRAD = 4, LG_GABOR_E = 5 };
 
 // One GEMM segment of a work item: acc[:, acc_col : acc_col + nt] = A[128 x K] * B_block[nt x K]^T
 struct LGemmSeg {
@@ -69,6 +69,12 @@ struct LGemmArgs {
   const float* dist;        // BoundedLinear: per-row distance [rows] or null
   float bound_lo, bound_hi; // FWD: rows with dist outside [lo, hi] are zeroed before THIS stage's linear;
                             // DGRAD: the same mask of the TARGET stage, applied to the stored dh (W-wgrad and dgrad operand)
+  // Gabor filters (reference mfn.py:96-131): envelope E = exp(-gamma/2 (|x|^2 + |mu|^2 - 2 x.mu)) as its own GEMM pass
+  const uint8_t* in_e;      // MFN_FWD: envelope image of this stage (null for Fourier filters)
+  uint8_t* out_q;           // MFN_DGRAD: q = dL/df * f image of the target stage (drives d mu, d gamma) or null
+  const float* xn;          // GABOR_E: |x|^2 per row, fp32
+  const float* gamma;       // GABOR_E: gamma_j [width]
+  const float* mn;          // GABOR_E: |mu_j|^2 [width]
   uint32_t feat_tile_bytes; // bytes of one 128-row image of the epilogue's feature images (MFN: 128 * width * 2)
   int dbg;                  // debug (INR_LGEMM_DBG): bit 0 skip MMAs, bit 1 skip operand copies (timing experiments only)
   unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)

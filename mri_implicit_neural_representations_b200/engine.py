@@ -33,7 +33,7 @@ class Plan:
         enc = encoder or {"embedding": "none"}
         if model not in L.MODEL:
             raise NotImplementedError(model)                      # src/train.py:69-70
-        if model in ("WIRE", "Fourier", "MultiscaleFourier", "BoundedFourier"):
+        if model in ("WIRE", "Fourier", "MultiscaleFourier", "BoundedFourier", "Gabor", "KGabor"):
             last = "linear"                                        # WIRE: real part of the final complex linear; MFN: plain heads
         elif model == "FFN":
             last = "sigmoid"                                       # src/models/networks.py:63
@@ -91,11 +91,12 @@ class Plan:
         return b.value
 
     def workspace_layout(self, bs: int) -> dict:
-        arr = (C.c_uint64 * 44)()
-        L.check(L.lib.inr_workspace_layout(self.handle, bs, arr, 44), "inr_workspace_layout")
+        arr = (C.c_uint64 * 60)()
+        L.check(L.lib.inr_workspace_layout(self.handle, bs, arr, 60), "inr_workspace_layout")
         v = list(arr)
         return {"h": v[0:12], "d": v[12:24], "dz": v[24:36], "dzlast": v[36], "g": v[37], "part": v[38],
-                "scal": v[39], "gpart": v[40], "n_tiles": int(v[41]), "n_split": int(v[42]), "total": v[43]}
+                "scal": v[39], "gpart": v[40], "n_tiles": int(v[41]), "n_split": int(v[42]), "total": v[43],
+                "q": v[44:56], "gfin": v[56], "gstride": int(v[57]), "aux0": int(v[58]), "e": v[59]}
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -130,6 +131,11 @@ class ChainEngine:
         self.loss_out = torch.zeros(1, **f32)
         self.encB = None
         self._graphs = {}
+        # WIRE / MFN backward passes store fp16 gradient images under per-layer power-of-two scales that lag one step
+        # (amax of the previous backward); the very first backward after construction runs twice so that the gradients
+        # it returns are already computed with calibrated scales
+        self._lagged_scales = plan.model not in ("SIREN", "FFN")
+        self._calibrated = False
 
     # ---- parameters -------------------------------------------------------------------------------
     def _views(self, flat):
@@ -188,11 +194,15 @@ class ChainEngine:
         dout = dout.to(self.device, torch.float32).contiguous()
         if dist is not None:
             dist = dist.to(self.device, torch.float32).contiguous()
-            L.check(L.lib.inr_backward_dist(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(dout), _ptr(dist), bs,
-                                            _ptr(self.workspace), _ptr(self.grads), _stream()), "inr_backward_dist")
+            for _ in range(2 if (self._lagged_scales and not self._calibrated) else 1):
+                L.check(L.lib.inr_backward_dist(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(dout), _ptr(dist), bs,
+                                                _ptr(self.workspace), _ptr(self.grads), _stream()), "inr_backward_dist")
+            self._calibrated = True
             return self.grads
-        L.check(L.lib.inr_backward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(dout), bs,
-                                   _ptr(self.workspace), _ptr(self.grads), _stream()), "inr_backward")
+        for _ in range(2 if (self._lagged_scales and not self._calibrated) else 1):
+            L.check(L.lib.inr_backward(self.plan.handle, _ptr(self.params), _ptr(self.wpack), _ptr(dout), bs,
+                                       _ptr(self.workspace), _ptr(self.grads), _stream()), "inr_backward")
+        self._calibrated = True
         return self.grads
 
     def adam_step(self):
@@ -210,10 +220,20 @@ class ChainEngine:
         o = loss_opts or {}
         ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
                         float(o.get("hdr_ff_factor", 0.0)))
+        if self._lagged_scales and not self._calibrated:
+            self._calibrate(ld, coords, x, gt, mask, bs)
         L.check(L.lib.inr_train_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                      _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords), _ptr(x), _ptr(self.encB),
                                      _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None, _ptr(self.workspace),
                                      _ptr(out), _ptr(self.loss_out), _stream()), "inr_train_step")
+
+    def _calibrate(self, ld, coords, x, gt, mask, bs):
+        """One gradients-only pass over rows [0, bs) (no optimiser step, cursor and step counter untouched) that leaves
+        the per-layer gradient scales of the WIRE / MFN backward calibrated for the step that follows."""
+        L.check(L.lib.inr_grad_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords), _ptr(x),
+                                    _ptr(self.encB), _ptr(gt), _ptr(mask), bs, None, _ptr(self.workspace), None,
+                                    _ptr(self.grads), _ptr(self.loss_out), _stream()), "inr_grad_step(calibration)")
+        self._calibrated = True
 
     def profile_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, reps: int = 20):
         """Average device time (ms) of the four kernels of one step: forward, dgrad, wgrad, optimiser."""
@@ -258,6 +278,8 @@ class ChainEngine:
         o = loss_opts or {}
         ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
                         float(o.get("hdr_ff_factor", 0.0)))
+        if self._lagged_scales and not self._calibrated:
+            self._calibrate(ld, coords, x, gt, mask, bs)
         L.check(L.lib.inr_grad_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords), _ptr(x),
                                     _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None,
                                     _ptr(self.workspace), _ptr(out), _ptr(self.grads), _ptr(self.loss_out), _stream()),
@@ -268,7 +290,7 @@ class ChainEngine:
         """MFN only (tests / debugging): 'z' (stage output), 'g' (sin p), 'dp' (S_stage * dL/dp) as [rows_pad, width]."""
         lay = self.plan.workspace_layout(bs)
         T, F = lay["n_tiles"], self.plan.desc.width
-        off = {"z": lay["h"], "g": lay["d"], "dp": lay["dz"]}[kind][stage]
+        off = {"z": lay["h"], "g": lay["d"], "dp": lay["dz"], "q": lay["q"]}[kind][stage]
         img = self.workspace[off:off + T * 128 * F * 2].view(torch.float16).view(T, F // 8, 128, 8)
         return img.permute(0, 2, 1, 3).reshape(T * 128, F).float()
 

@@ -59,10 +59,12 @@ def wire_tensors(net: dict):
     return out
 
 
-def mfn_tensors(model: str, net: dict, input_scale: float = 2.0, weight_scale: float = 1.0):
-    """[(name, tensor)] in reference state_dict order for FourierNet ('Fourier') and the multiscale variants
-    ('MultiscaleFourier', 'BoundedFourier'), same torch calls in the same order as reference src/models/mfn.py
-    (:15-30 MFNBase, :50-55 FourierLayer, :61-83, :216-251, :300-340)."""
+def mfn_tensors(model: str, net: dict, input_scale: float = 2.0, weight_scale: float = 1.0, alpha: float = 6.0,
+                beta: float = 1.0):
+    """[(name, tensor)] in reference state_dict order for FourierNet ('Fourier'), GaborNet / KGaborNet ('Gabor',
+    'KGabor') and the multiscale variants ('MultiscaleFourier', 'BoundedFourier'), same torch calls in the same order
+    as reference src/models/mfn.py (:15-30 MFNBase, :50-55 FourierLayer, :61-83, :102-113 GaborLayer, :134-162,
+    :216-251, :300-340)."""
     L, hid = net["network_depth"], net["network_width"]
     fin, fout = net["network_input_size"], net["network_output_size"]
     lins = [nn.Linear(hid, hid, True) for _ in range(L)]
@@ -70,6 +72,22 @@ def mfn_tensors(model: str, net: dict, input_scale: float = 2.0, weight_scale: f
     b = math.sqrt(weight_scale / hid)
     for lin in lins:
         lin.weight.data.uniform_(-b, b)
+    if model in ("Gabor", "KGabor"):
+        res = []
+        for i, l in enumerate(lins):
+            res += [(f"linear.{i}.weight", l.weight.detach().clone()), (f"linear.{i}.bias", l.bias.detach().clone())]
+        res += [("output_linear.weight", out_lin.weight.detach().clone()), ("output_linear.bias", out_lin.bias.detach().clone())]
+        ws = input_scale / math.sqrt(L + 1)
+        for i in range(L + 1):
+            lin = nn.Linear(fin, hid)                                               # GaborLayer.__init__, :104
+            mu = 2 * torch.rand(hid, fin) - 1                                       # :109
+            gamma = torch.distributions.gamma.Gamma(alpha / (L + 1), beta).sample((hid,))   # :110-112
+            lin.weight.data *= ws * torch.sqrt(gamma[:, None])                      # :113
+            lin.bias.data.uniform_(-math.pi, math.pi)                               # :114
+            res += [(f"filters.{i}.mu", mu), (f"filters.{i}.gamma", gamma),
+                    (f"filters.{i}.linear.weight", lin.weight.detach().clone()),
+                    (f"filters.{i}.linear.bias", lin.bias.detach().clone())]
+        return res
     multi = model != "Fourier"
     if model == "BoundedFourier":                       # BoundedLinear replaces the scaled-uniform linears (default init)
         lins = [nn.Linear(hid, hid, True) for _ in range(L)]

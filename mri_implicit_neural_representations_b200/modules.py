@@ -310,6 +310,56 @@ class FourierNet(FusedChain):
         return _ChainFn.apply(x, self, None, *self._params_in_order())
 
 
+class _GaborFilterHolder(nn.Module):
+    """Parameters of one reference GaborLayer (mfn.py:102-114) under its names: mu, gamma, linear.{weight,bias}."""
+
+    def __init__(self, mu, gamma, weight, bias):
+        super().__init__()
+        self.mu = nn.Parameter(mu)
+        self.gamma = nn.Parameter(gamma)
+        self.linear = _Leaf(weight, bias)
+
+
+class GaborNet(FourierNet):
+    """reference src/models/mfn.py:133-162 -- keys linear.<i>.*, output_linear.*, filters.<i>.{mu, gamma, linear.weight,
+    linear.bias}.  forward(x [bs, in]) -> [bs, out]."""
+    MODEL = "Gabor"
+
+    def __init__(self, params, input_scale=2, weight_scale=1.0, alpha=6.0, beta=1.0, bias=True, output_act=False):
+        if output_act or not bias:
+            raise L.InrError("output_act / bias=False variants of the MFNs are not built")
+        self._scales = (float(input_scale), float(weight_scale), float(alpha), float(beta))
+        FusedChain.__init__(self, params)
+
+    def _build_tree(self):
+        v = self._views(self._flat)
+        L_ = self.net["network_depth"]
+        self.linear = nn.ModuleList([_Leaf(v[2 * i], v[2 * i + 1]) for i in range(L_)])
+        o = 2 * L_
+        self.output_linear = _Leaf(v[o], v[o + 1])
+        o += 2
+        self.filters = nn.ModuleList([_GaborFilterHolder(v[o + 4 * i], v[o + 4 * i + 1], v[o + 4 * i + 2], v[o + 4 * i + 3])
+                                      for i in range(L_ + 1)])
+
+    def _params_in_order(self):
+        out = []
+        for m in self.linear:
+            out += [m.weight, m.bias]
+        out += [self.output_linear.weight, self.output_linear.bias]
+        for f in self.filters:
+            out += [f.mu, f.gamma, f.linear.weight, f.linear.bias]
+        return out
+
+
+class KGaborNet(GaborNet):
+    """reference src/models/mfn.py:164-204 -- forward(x, dist_to_center); the reference never enables
+    with_dist_filtering, so dist_to_center is accepted and ignored exactly as there (:184-198)."""
+    MODEL = "KGabor"
+
+    def forward(self, x, dist_to_center=None):
+        return GaborNet.forward(self, x)
+
+
 class MultiscaleKFourier(FourierNet):
     """reference src/models/mfn.py:206-267 -- heads output_linear.<i> at `output_layers`; forward(coords=x) returns the
     LIST of head outputs in stage order.  Parameters of dead stages / unused heads never receive gradients."""

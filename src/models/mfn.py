@@ -1,5 +1,5 @@
-"""Drop-in for the reference's src/models/mfn.py: FourierNet and MultiscaleKFourier run on the B200 engine (same
-constructor arguments and state_dict keys).  GaborNet / KGaborNet are not built yet."""
+"""Drop-in for the reference's src/models/mfn.py: FourierNet, GaborNet, KGaborNet, MultiscaleKFourier and
+MultiscaleBoundedFourier run on the B200 engine (same constructor arguments and state_dict keys)."""
 import os
 import sys
 
@@ -7,17 +7,5 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from mri_implicit_neural_representations_b200.modules import (FourierNet, MultiscaleBoundedFourier,  # noqa: E402,F401
-                                                                MultiscaleKFourier)
-
-
-def _not_built(name):
-    class _Stub:
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"{name}: kernels for this model are not built yet (see DESIGN.md section 1)")
-    _Stub.__name__ = name
-    return _Stub
-
-
-GaborNet = _not_built("GaborNet")
-KGaborNet = _not_built("KGaborNet")
+from mri_implicit_neural_representations_b200.modules import (FourierNet, GaborNet, KGaborNet,  # noqa: E402,F401
+                                                                MultiscaleBoundedFourier, MultiscaleKFourier)

@@ -188,3 +188,85 @@ def test_bounded_fourier_forward_and_gradients(inr):
             assert named[k].grad is None, k
         else:
             assert rel(named[k].grad, ref) <= 1.5e-3, (k, rel(named[k].grad, ref))
+
+
+def _gabor(inr, condition=False):
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup("gabor_tanh")
+    if condition:
+        # reference init: gamma ~ Gamma(6/9, 1) and |x|^2 + |mu|^2 ~ 430, so most envelopes underflow and only the few
+        # features with gamma < 0.02 carry signal.  For the gradient checks every feature is made to matter.
+        for i in range(net["network_depth"] + 1):
+            sd[f"filters.{i}.gamma"] = sd[f"filters.{i}.gamma"] * 0.01 + 1e-3
+            sd[f"filters.{i}.mu"] = sd[f"filters.{i}.mu"] * 0.5
+    plan = inr.Plan("Gabor", net, enc_cfg)
+    eng = inr.ChainEngine(plan, max_batch=coords.shape[0], lr=G.LR)
+    eng.load_tensors(list(sd.values()))
+    eng.set_encoder(encB)
+    return plan, eng, net, loss_kind, opts, sd, encB, coords, gt
+
+
+@pytest.mark.parametrize("condition", [False, True])
+def test_gabor_forward_per_stage(inr, condition):
+    """GaborNet (reference mfn.py:96-162): every stage's z_i and the output against the oracle, with the reference
+    initialisation (sparse live features) and with a conditioned state where all envelopes are O(1)."""
+    plan, eng, net, loss_kind, opts, sd, encB, coords, gt = _gabor(inr, condition)
+    L, bs = net["network_depth"], coords.shape[0]
+    x = O.encode(coords, encB, "gauss")
+    tr = []
+    out_ref = O.mfn_forward(sd, x, L, True, trace=tr)
+    out = eng.forward(coords.cuda(), train=True)
+    for i in range(L + 1):
+        assert rel(eng.read_mfn_image("z", i, bs)[:bs], tr[i]) <= 1.5e-3, f"z{i}"
+    assert rel(out, out_ref) <= 1.5e-3
+    # teacher-forced stage in fp64 from the engine's own z_{i-1}
+    x64 = x.double()
+    for i in (1, L):
+        zin = eng.read_mfn_image("z", i - 1, bs)[:bs].cpu().double()
+        sd64 = {k: v.double() for k, v in sd.items()}
+        f = O._filter(sd64, i, x64, True)
+        h = zin @ sd64[f"linear.{i-1}.weight"].t() + sd64[f"linear.{i-1}.bias"]
+        assert rel(eng.read_mfn_image("z", i, bs)[:bs], f * h) <= 1e-3, i
+
+
+def test_gabor_gradients_conditioned(inr):
+    """Every parameter gradient of GaborNet, incl. d mu and d gamma from the q-reductions, vs torch autograd on the oracle."""
+    plan, eng, net, loss_kind, opts, sd, encB, coords, gt = _gabor(inr, True)
+    L, bs = net["network_depth"], coords.shape[0]
+    x = O.encode(coords, encB, "gauss")
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.mfn_forward(P, x, L, True)
+    val, dout = loss_and_grad(loss_kind, opts, o.detach(), gt, coords)
+    gr = dict(zip(P.keys(), torch.autograd.grad(o, list(P.values()), grad_outputs=dout)))
+    eng.grad_step(loss_kind, coords.cuda(), gt.cuda(), bs, loss_opts=opts)
+    assert abs(float(eng.loss_out) - float(val)) <= 1e-4 * float(val)
+    gv = dict(zip(sd.keys(), eng._views(eng.grads)))
+    for k in sd:
+        assert rel(gv[k], gr[k]) <= 2e-3, (k, rel(gv[k], gr[k]))
+
+
+def test_gabor_fused_steps_vs_reference_golden(inr):
+    plan, eng, net, loss_kind, opts, sd, encB, coords, gt = _gabor(inr, False)
+    bs = coords.shape[0]
+    gold = G.load_golden("gabor_tanh")
+    for step in range(G.N_ADAM_STEPS):
+        eng.train_step(loss_kind, coords.cuda(), gt.cuda(), bs, loss_opts=opts)
+        assert abs(float(eng.loss_out) - gold["losses"][step]) <= 2e-4 * gold["losses"][step], step
+    for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
+        dg = G.tensor_digest(eng.params[off:off + rows * cols].cpu())
+        assert abs(dg["l2"] - gold["final"][k]["l2"]) <= 1e-4 * gold["final"][k]["l2"], k
+
+
+def test_kgabor_module_ignores_dist_like_the_reference(inr):
+    from mri_implicit_neural_representations_b200.modules import GaborNet, KGaborNet
+    torch.manual_seed(3)
+    a = KGaborNet(dict(G.NET_MFN)).to("cuda")
+    keys = list(a.state_dict().keys())
+    assert keys[-4:] == ["filters.8.mu", "filters.8.gamma", "filters.8.linear.weight", "filters.8.linear.bias"]
+    x = torch.rand(300, G.NET_MFN["network_input_size"], device="cuda") * 2 - 1
+    d = torch.rand(300, device="cuda")
+    with torch.no_grad():
+        assert torch.equal(a(x, d), a(x, None))
+    torch.manual_seed(3)
+    b = GaborNet(dict(G.NET_MFN)).to("cuda")
+    with torch.no_grad():
+        assert torch.equal(a(x, d), b(x))
