@@ -73,6 +73,11 @@ typedef struct inr_model_desc {
 typedef struct inr_loss_desc {
   int32_t kind;             /* INR_LOSS_* */
   float hdr_eps, hdr_sigma, hdr_factor;   /* loss_opts of src/metrics/losses.py:230-234 */
+  /* total-variation term of the per-coil loop (src/train.py:173-174, tv_loss of src/metrics/losses.py:326-343):
+   * tv_weight > 0 adds tv_weight * (L1mean(d/dw) + L1mean(d/dh)) of out.view(tv_h, tv_w, out) over ALL rows of the
+   * batch (bs must equal tv_h * tv_w, `out` must be given; not combinable with INR_LOSS_HDR in the fused step) */
+  float tv_weight;
+  int32_t tv_h, tv_w;
 } inr_loss_desc;
 
 typedef struct inr_tensor_info {

@@ -34,6 +34,7 @@ cudaError_t launch_mfn_scalars(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_top(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_gabor_prep(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_gabor_grad(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_tv(const TvArgs& a, int n_tiles, cudaStream_t st);
 }  // namespace inr
 
 using namespace inr;
@@ -75,6 +76,20 @@ extern "C" int inr_debug_set_trace(void* dev_u64_buffer_64) {
   g_trace_lgemm_count = 0;
   return INR_OK;
 }
+// TV term between the forward (which left the main loss pieces and `out`) and the backward (which reduces the partials)
+static int run_tv(const inr_loss_desc* loss, const float* out, int out_f, int64_t bs, uint8_t* ws, uint64_t g_off, uint64_t part_off,
+                  int n_tiles, cudaStream_t st) {
+  if (!(loss->tv_weight > 0.f)) return INR_OK;
+  if (loss->kind == INR_LOSS_HDR) return fail(INR_EUNSUPPORTED, "TV + HDR is not fused (use the autograd face)");
+  if (!out) return fail(INR_EINVAL, "the TV term needs the `out` buffer");
+  if (loss->tv_h < 1 || loss->tv_w < 1 || static_cast<int64_t>(loss->tv_h) * loss->tv_w != bs)
+    return fail(INR_EINVAL, "TV needs bs == tv_h * tv_w (one coil per batch, src/train.py:173-174)");
+  TvArgs t{out, reinterpret_cast<float*>(ws + g_off), reinterpret_cast<float*>(ws + part_off), static_cast<int>(bs), loss->tv_h,
+           loss->tv_w, out_f, loss->tv_weight};
+  cudaError_t e = launch_tv(t, n_tiles, st);
+  return e == cudaSuccess ? INR_OK : cuda_fail(e, "tv_kernel");
+}
+
 static int lgemm_dbg() { static int v = -1; if (v < 0) { const char* e = std::getenv("INR_LGEMM_DBG"); v = e ? std::atoi(e) : 0; } return v; }
 static unsigned long long* lgemm_trace_ptr() { return (g_trace && g_trace_lgemm_count++ == g_trace_lgemm_sel) ? g_trace : nullptr; }
 
@@ -989,10 +1004,12 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
       return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
     const MfnWorkspace mw = mfn_workspace(p, bs);
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
-    const LossDesc ML{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
+    const LossDesc ML{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w};
     if (ev) cudaEventRecord(ev[0], st);
     int rcm = mfn_forward_impl(p, mw, ML, params, wpack, coords, input_x, encB, gt, mask, nullptr, bs, workspace, out, 1,
                                row_cursor_dev, no_adam ? nullptr : step_dev, st);
+    if (rcm) return rcm;
+    rcm = run_tv(loss, out, p->mm.out_f, bs, wsb, mw.gl, mw.part, mw.n_tiles, st);
     if (rcm) return rcm;
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     rcm = mfn_backward_impl(p, mw, ML, params, wpack, nullptr, nullptr, bs, workspace, no_adam ? nullptr : hyper_dev,
@@ -1018,10 +1035,12 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
       return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
     const WireWorkspace ww = wire_workspace(p, bs);
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
-    const LossDesc WL{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
+    const LossDesc WL{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w};
     if (ev) cudaEventRecord(ev[0], st);
     int rcw = wire_forward_impl(p, ww, WL, params, wpack, coords, gt, mask, bs, workspace, out, 1, row_cursor_dev,
                                 no_adam ? nullptr : step_dev, st, ev ? ev + 5 : nullptr);
+    if (rcw) return rcw;
+    rcw = run_tv(loss, out, p->wm.out_f, bs, wsb, ww.g, ww.part, ww.n_tiles, st);
     if (rcw) return rcw;
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     rcw = wire_backward_impl(p, ww, WL, params, wpack, nullptr, bs, workspace, no_adam ? nullptr : hyper_dev,
@@ -1048,10 +1067,12 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   if (p->model.out_f > 2) return fail(INR_EUNSUPPORTED, "fused loss path packs at most 2 outputs");
   Workspace w = plan_workspace(p, bs);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  LossDesc L{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor};
+  LossDesc L{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w};
   if (ev) cudaEventRecord(ev[0], st);
   int rc = run_forward(p, w, L, params, wpack, coords, input_x, encB, gt, mask, bs, workspace, out, 1, row_cursor_dev,
                        no_adam ? nullptr : step_dev, st);
+  if (rc) return rc;
+  rc = run_tv(loss, out, p->model.out_f, bs, ws, w.g_off, w.part_off, w.n_tiles, st);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[1], st);
   rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st, ev ? ev[2] : nullptr,

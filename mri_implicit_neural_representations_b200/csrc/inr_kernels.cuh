@@ -55,6 +55,16 @@ struct ChainModel {
 struct LossDesc {
   int kind;
   float eps, sigma, factor;   // HDR / LSL options
+  float tv_weight;            // > 0: total-variation term of reference losses.py:326-343 on the batch viewed as [tv_h, tv_w, out]
+  int tv_h, tv_w;
+};
+
+struct TvArgs {               // tv_kernel (optim.cu): adds the TV gradient / loss to the per-row loss pieces of one batch
+  const float* out;           // [bs, out_f] network output of the batch (all rows, before the row mask)
+  float* g;                   // [rows_pad] float4 loss pieces; .zw receive the TV gradient (normaliser cB = 1)
+  float* part;                // [n_tiles][kPartialsPerTile] tile partials; slots 1 (loss B) and 5 (amax B) are written
+  int bs, h, w, out_f;
+  float weight;
 };
 
 // Workspace byte offsets for a batch of n_tiles tiles (computed on the host by plan_workspace()).

@@ -114,6 +114,7 @@ __device__ inline void reduce_step_scalars(const float* part_g, int n_tiles, con
         break;
       default: cA = 1.f; break;   // external dout: gA holds dL/dz_last already
     }
+    if (loss.tv_weight > 0.f && loss.kind != LOSS_HDR) { cB = 1.f; lossv += lB; }   // TV pieces arrive fully normalised
     const float amax = cA * amA + fabsf(cB) * amB;
     float S = 1.f;
     if (amax > 0.f && isfinite(amax)) {

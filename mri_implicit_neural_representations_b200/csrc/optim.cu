@@ -129,6 +129,47 @@ __global__ void __launch_bounds__(128) dout_amax_kernel(const float* dout, int b
   }
 }
 
+// Total-variation term of the per-coil training loop (reference src/train.py:173-174, losses.py:326-343):
+//   tv = weight * (L1mean(img[:, :-1] - img[:, 1:]) + L1mean(img[:-1] - img[1:])),  img = out.view(H, W, out_f)
+// evaluated on ALL rows of the batch (before the undersampling mask selects rows for the main loss).  One thread per
+// row writes d tv / d out into the B pieces of the row's loss record; every pair difference is counted by its
+// upper-left element, tile sums in fixed order (bit-reproducible).
+__global__ void __launch_bounds__(kTileM) tv_kernel(const TvArgs a) {
+  __shared__ float red[4][2];
+  const int tid = threadIdx.x, row = blockIdx.x * kTileM + tid;
+  float lossn = 0.f, am = 0.f, t[2] = {0.f, 0.f};
+  if (row < a.bs) {
+    const int h = row / a.w, w = row % a.w;
+    const float cw = a.w > 1 ? a.weight / (static_cast<float>(a.h) * (a.w - 1) * a.out_f) : 0.f;
+    const float ch = a.h > 1 ? a.weight / (static_cast<float>(a.h - 1) * a.w * a.out_f) : 0.f;
+    auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
+    for (int o = 0; o < a.out_f && o < 2; ++o) {
+      const float x = a.out[static_cast<size_t>(row) * a.out_f + o];
+      if (w < a.w - 1) { const float d = x - a.out[static_cast<size_t>(row + 1) * a.out_f + o]; lossn += cw * fabsf(d); t[o] += cw * sgn(d); }
+      if (w > 0) { const float d = a.out[static_cast<size_t>(row - 1) * a.out_f + o] - x; t[o] -= cw * sgn(d); }
+      if (h < a.h - 1) { const float d = x - a.out[static_cast<size_t>(row + a.w) * a.out_f + o]; lossn += ch * fabsf(d); t[o] += ch * sgn(d); }
+      if (h > 0) { const float d = a.out[static_cast<size_t>(row - a.w) * a.out_f + o] - x; t[o] -= ch * sgn(d); }
+    }
+    am = fmaxf(fabsf(t[0]), fabsf(t[1]));
+  }
+  float4* gr = reinterpret_cast<float4*>(a.g) + row;
+  float4 v = *gr; v.z = t[0]; v.w = t[1]; *gr = v;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { lossn += __shfl_xor_sync(0xffffffffu, lossn, off); am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off)); }
+  if ((tid & 31) == 0) { red[tid >> 5][0] = lossn; red[tid >> 5][1] = am; }
+  __syncthreads();
+  if (tid == 0) {
+    float* q = a.part + static_cast<size_t>(blockIdx.x) * kPartialsPerTile;
+    q[1] = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+    q[5] = fmaxf(fmaxf(red[0][1], red[1][1]), fmaxf(red[2][1], red[3][1]));
+  }
+}
+
+cudaError_t launch_tv(const TvArgs& a, int n_tiles, cudaStream_t st) {
+  tv_kernel<<<n_tiles, kTileM, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_adam(const AdamArgs& a, cudaStream_t stream) {
   const int grid = (a.n_params + 255) / 256;
   adam_kernel<<<grid, 256, 0, stream>>>(a);

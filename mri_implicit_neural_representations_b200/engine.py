@@ -20,6 +20,16 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _loss_desc(loss: str, loss_opts: Optional[dict]):
+    """inr_loss_desc from the reference's loss name + loss_opts; loss_opts['tv'] = (H, W[, weight]) switches the
+    total-variation term of the per-coil loop on (src/train.py:173-174; weight defaults to tv_loss's 1e-4)."""
+    o = loss_opts or {}
+    tv = o.get("tv")
+    tvw, tvh, tvww = (float(tv[2]) if len(tv) > 2 else 1e-4, int(tv[0]), int(tv[1])) if tv else (0.0, 0, 0)
+    return L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
+                      float(o.get("hdr_ff_factor", 0.0)), tvw, tvh, tvww)
+
+
 def selftest_umma(mode: int, variant: int = 0):
     err, ref = C.c_float(), C.c_float()
     L.check(L.lib.inr_selftest_umma(mode, variant, C.byref(err), C.byref(ref)), "inr_selftest_umma")
@@ -217,29 +227,25 @@ class ChainEngine:
                    out: Optional[torch.Tensor] = None):
         """One fused forward+loss+backward+Adam step on rows [cursor, cursor+bs) (or [0, bs)) of the resident
         arrays.  Asynchronous; the loss lands in self.loss_out."""
-        o = loss_opts or {}
-        ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
-                        float(o.get("hdr_ff_factor", 0.0)))
+        ld = _loss_desc(loss, loss_opts)
         if self._lagged_scales and not self._calibrated:
-            self._calibrate(ld, coords, x, gt, mask, bs)
+            self._calibrate(ld, coords, x, gt, mask, bs, out)
         L.check(L.lib.inr_train_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                      _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords), _ptr(x), _ptr(self.encB),
                                      _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None, _ptr(self.workspace),
                                      _ptr(out), _ptr(self.loss_out), _stream()), "inr_train_step")
 
-    def _calibrate(self, ld, coords, x, gt, mask, bs):
+    def _calibrate(self, ld, coords, x, gt, mask, bs, out=None):
         """One gradients-only pass over rows [0, bs) (no optimiser step, cursor and step counter untouched) that leaves
         the per-layer gradient scales of the WIRE / MFN backward calibrated for the step that follows."""
         L.check(L.lib.inr_grad_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords), _ptr(x),
-                                    _ptr(self.encB), _ptr(gt), _ptr(mask), bs, None, _ptr(self.workspace), None,
+                                    _ptr(self.encB), _ptr(gt), _ptr(mask), bs, None, _ptr(self.workspace), _ptr(out),
                                     _ptr(self.grads), _ptr(self.loss_out), _stream()), "inr_grad_step(calibration)")
         self._calibrated = True
 
     def profile_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, reps: int = 20):
         """Average device time (ms) of the four kernels of one step: forward, dgrad, wgrad, optimiser."""
-        o = loss_opts or {}
-        ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
-                        float(o.get("hdr_ff_factor", 0.0)))
+        ld = _loss_desc(loss, loss_opts)
         ms = (C.c_float * 8)()
         L.check(L.lib.inr_profile_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg),
                                        _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords),
@@ -275,11 +281,9 @@ class ChainEngine:
 
     def grad_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, use_cursor: bool = False, out=None):
         """forward + loss + backward only; gradients land in self.grads (data-parallel: all-reduce them, then adam_step)."""
-        o = loss_opts or {}
-        ld = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
-                        float(o.get("hdr_ff_factor", 0.0)))
+        ld = _loss_desc(loss, loss_opts)
         if self._lagged_scales and not self._calibrated:
-            self._calibrate(ld, coords, x, gt, mask, bs)
+            self._calibrate(ld, coords, x, gt, mask, bs, out)
         L.check(L.lib.inr_grad_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords), _ptr(x),
                                     _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None,
                                     _ptr(self.workspace), _ptr(out), _ptr(self.grads), _ptr(self.loss_out), _stream()),

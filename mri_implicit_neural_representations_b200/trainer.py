@@ -84,7 +84,9 @@ class FusedTrainer:
 
     def __init__(self, model: FusedChain, encoder: Positional_Encoder, optim: FusedAdam, loss: str, batch_size: int,
                  coords: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None, loss_opts: Optional[dict] = None,
-                 use_graph: bool = True):
+                 use_graph: bool = True, tv: Optional[tuple] = None):
+        """tv = (H, W[, weight]): per-coil batches (batch_size == H * W) with the total-variation term of
+        src/train.py:173-174 added on every batch (the reference only reaches it with an undersampling mask)."""
         if loss not in FUSABLE_LOSSES:
             raise L.InrError(f"loss '{loss}' is not fused; use the unfused model(x)/backward path")
         wire = getattr(model, "MODEL", None) == "WIRE"
@@ -94,7 +96,11 @@ class FusedTrainer:
             raise L.InrError("the fused step needs the gauss encoder (dense inputs go through the unfused path)")
         dev = model._flat.device
         self.model, self.encoder, self.optim = model, encoder, optim
-        self.loss, self.loss_opts, self.bs = loss, loss_opts, int(batch_size)
+        self.loss, self.loss_opts, self.bs = loss, dict(loss_opts or {}), int(batch_size)
+        if tv is not None:
+            if int(tv[0]) * int(tv[1]) != int(batch_size):
+                raise L.InrError("the TV term needs per-coil batches: batch_size == H * W")
+            self.loss_opts["tv"] = tuple(tv)
         self.coords = coords.to(dev, torch.float32).contiguous()
         self.gt = gt.to(dev, torch.float32).contiguous()
         self.mask = None if mask is None else mask.to(dev).to(torch.uint8).contiguous()
@@ -102,6 +108,8 @@ class FusedTrainer:
         self._enc_params = None if wire else encoder.params
         self.eng = model.engine(self._enc_params, self.bs)
         self.eng.set_encoder(encoder.B)
+        self._out = (torch.empty(self.bs, self.eng.plan.out_cols, dtype=torch.float32, device=dev)
+                     if "tv" in self.loss_opts else None)
         self.use_graph = use_graph
         self._graphs = {}
         self.pos = 0
@@ -112,7 +120,8 @@ class FusedTrainer:
         return (self.n + self.bs - 1) // self.bs
 
     def _launch(self, bs):
-        self.eng.train_step(self.loss, self.coords, self.gt, bs, mask=self.mask, loss_opts=self.loss_opts, use_cursor=True)
+        self.eng.train_step(self.loss, self.coords, self.gt, bs, mask=self.mask, loss_opts=self.loss_opts, use_cursor=True,
+                            out=self._out)
 
     def step(self) -> torch.Tensor:
         """One batch; returns the device scalar holding its loss (no host sync)."""

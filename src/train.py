@@ -121,13 +121,18 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
     gt_image = M.reconstruct(dataset.image.to(device), (C, H, W), in_image_space)
 
     enc_ok = config["encoder"]["embedding"] == ("none" if config["model"] == "WIRE" else "gauss")
-    fused = (config["loss"] in FUSABLE_LOSSES and enc_ok
-             and not config.get("use_tv", False) and not config.get("per_coil", False))
+    per_coil = bool(config.get("per_coil", False))
+    if per_coil:
+        bs = H * W                              # one coil per batch, grid order (reference per-coil loader)
+    has_mask = train_ds.coords_mask is not None
+    # the reference reaches tv_loss only inside `if len(mask_coords) != 0` (:172-174) and views the batch as (H, W, 2)
+    use_tv = bool(config.get("use_tv", False)) and has_mask
+    fused = (config["loss"] in FUSABLE_LOSSES and enc_ok and (not use_tv or (per_coil and config["loss"] != "HDR")))
     trainer = None
     if fused:
-        mask = train_ds.coords_mask[:, 0] if train_ds.coords_mask is not None else None
+        mask = train_ds.coords_mask[:, 0] if has_mask else None
         trainer = FusedTrainer(model, encoder, optim, config["loss"], bs, train_ds.coords, train_ds.image, mask,
-                               config.get("loss_opts"))
+                               config.get("loss_opts"), tv=(H, W) if use_tv else None)
     elif verbose:
         print("unfused path: model(x) -> loss -> backward -> optim.step through the engine's autograd face")
 

@@ -143,3 +143,35 @@ def test_end_to_end_short_horizon_quality_parity(src_path, tmp_path):
     # percent-level drift after 12 steps although the function (PSNR/SSIM above) agrees.
     for k in sd:
         assert rel(blob["net"][k], P[k]) <= 6e-2, k
+
+
+@pytest.mark.parametrize("model_name", ["FFN", "Gabor"])
+def test_config3_per_coil_tv_fused_equals_autograd_face(src_path, tmp_path, model_name):
+    """BASELINE config 3 shape: FFN / Gabor on k-space, tanh loss, per-coil batches, undersampling grid-2*1, use_tv.
+    The fused per-coil step (TV kernel between forward and backward) against the unfused loop of the same script
+    (model(x) -> tv_loss + TanhL2Loss in PyTorch -> backward -> optimiser), same seed, short horizon."""
+    import train
+    from data.slices import get_data_loader
+    shape, epochs = (3, 24, 32), 2
+    net = dict(NET)
+    if model_name == "Gabor":
+        net.update(network_depth=2, network_width=256)
+    cfg = _config(epochs, shape[1] * shape[2])
+    cfg.update(model=model_name, net=net, loss="tanh", transform=False, per_coil=True, use_tv=True, undersampling="grid-2*1")
+    hist = {}
+    for fused in (True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ds, tl, vl = get_data_loader("knee", "data", "train", cfg["batch_size"], transform=False, shape=shape,
+                                         undersampling="grid-2*1", per_coil=True)
+        torch.manual_seed(31)
+        saved = train.FUSABLE_LOSSES
+        if not fused:
+            train.FUSABLE_LOSSES = ()
+        try:
+            hist[fused] = train.training_script(cfg, ds, tl, vl, 0, 0, output_path=str(tmp_path / str(fused)), verbose=False)
+        finally:
+            train.FUSABLE_LOSSES = saved
+    (_, p1, s1), (_, p0, s0) = hist[True][-1], hist[False][-1]
+    assert abs(p1 - p0) <= 0.1, (p1, p0)
+    assert abs(s1 - s0) <= 0.002, (s1, s0)
