@@ -38,6 +38,14 @@ WORKLOADS = {
         net={"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256},
         encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
         flop_per_coord=1313792, fwd_flop_per_coord=525312),
+    # BASELINE.json configs[2] (Gabor arm): GaborNet depth 8 width 512 on gauss-512, k-space fit, tanh loss, per-coil
+    # batches (bs = H*W = 102400), undersampling grid-2*1, total-variation term on every batch
+    "gabor_kspace_tanh_tv_percoil": dict(
+        model="Gabor", loss="tanh", loss_opts={"tv": (320, 320)}, batch=102400, image_space=False, normalization="max",
+        undersampling="grid-2*1",
+        net={"network_input_size": 512, "network_output_size": 2, "network_depth": 8, "network_width": 512},
+        encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
+        flop_per_coord=31463424, fwd_flop_per_coord=(18 + 8) * 512 * 512 * 2 + 2 * 512 * 2),
 }
 DEFAULT_WORKLOAD = "wire_kspace_hdr_bs25000"
 SLICE = (15, 320, 320)                 # fastMRI-knee-shaped: 15 coils x 320 x 320 after the reference's crop
@@ -107,6 +115,8 @@ def build_engine(wl, device, seed):
     encB = pinit.encoder_matrix(wl["encoder"])
     if wl["model"] == "WIRE":
         tensors = [t for _, t in pinit.wire_tensors(wl["net"])]
+    elif wl["model"] in ("Gabor", "KGabor", "Fourier"):
+        tensors = [t for _, t in pinit.mfn_tensors(wl["model"], wl["net"])]
     else:
         tensors = [t for _, t in pinit.chain_tensors(wl["model"], wl["net"])]
     plan = inr.Plan(wl["model"], wl["net"], wl["encoder"])
@@ -162,16 +172,17 @@ def cpu_port_steps(wl, n_steps, warmup, rows_per_step, seed=1234):
         coords, gt = coords.repeat(reps, 1), gt.repeat(reps, 1)
         mask = None if mask is None else mask.repeat(reps)
     opts = None
-    if wl["loss_opts"]:
+    if wl["loss_opts"] and "hdr_eps" in wl["loss_opts"]:
         opts = {"sigma": wl["loss_opts"]["hdr_ff_sigma"], "eps": wl["loss_opts"]["hdr_eps"],
                 "factor": wl["loss_opts"]["hdr_ff_factor"]}
+    tv = (wl["loss_opts"] or {}).get("tv")          # only applies when a step is one whole coil (rows_per_step == H*W)
     if warmup:
         O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords, gt, warmup, rows_per_step, LR,
-                      wl["loss"], opts, mask=mask)
+                      wl["loss"], opts, mask=mask, tv=tv)
     o = warmup * rows_per_step
     t0 = time.perf_counter()
     O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords[o:], gt[o:], n_steps, rows_per_step, LR,
-                  wl["loss"], opts, mask=None if mask is None else mask[o:])
+                  wl["loss"], opts, mask=None if mask is None else mask[o:], tv=tv)
     dt = time.perf_counter() - t0
     return n_steps * rows_per_step / dt, dt
 
@@ -239,15 +250,17 @@ def main():
     coords, gt, mask = resident_arrays(wl, device, 1234 + 100 * rank, min_bytes=200 << 20)
     n_rows = coords.shape[0]
     wire = wl["model"] == "WIRE"
+    mfn = wl["model"] in ("Gabor", "KGabor", "Fourier")
     steps_per_pass = n_rows // bs
+    out_buf = torch.empty(bs, 2, device=device) if (wl["loss_opts"] or {}).get("tv") else None   # the TV term reads the output
 
     def one_step():
         if dp:      # forward+loss+backward -> all-reduce(mean) of the flat fp32 gradients -> Adam (+ fp16 re-pack)
-            eng.grad_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True)
+            eng.grad_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True, out=out_buf)
             allreduce_mean_(eng.grads)
             eng.adam_step()
         else:
-            eng.train_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True)
+            eng.train_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True, out=out_buf)
 
     # eager warm-up (also sets kernel attributes outside capture), then capture one step in a CUDA graph
     for _ in range(3):
@@ -312,8 +325,9 @@ def main():
 
     # ---- per-kernel device times (CUDA events between the four kernels of a step, same stream)
     reset_cursor()
-    prof = eng.profile_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], reps=100)
-    wire = wl["model"] == "WIRE"
+    prof = eng.profile_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], reps=100 if bs <= 25000 else 20,
+                            out=out_buf)
+    n_launch = 14 if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
     kern_ms = prof["forward_layer_gemms"] / wl["net"]["network_depth"] if wire else prof["forward"]
     kern_flop = (wl["fwd_flop_per_coord"] / wl["net"]["network_depth"] if wire else wl["fwd_flop_per_coord"]) * bs
     fwd_tflops = kern_flop / (kern_ms * 1e-3) / 1e12
@@ -335,11 +349,11 @@ def main():
         if d_m is not None:
             d_m.copy_(h_mask[j:j + bs], non_blocking=True)
         if dp:
-            eng.grad_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"])
+            eng.grad_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"], out=out_buf)
             allreduce_mean_(eng.grads)
             eng.adam_step()
         else:
-            eng.train_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"])
+            eng.train_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"], out=out_buf)
         h_loss.copy_(eng.loss_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(h_loss)
@@ -397,20 +411,23 @@ def main():
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
                    "step": ("14 kernels: first layer, 4 layer GEMMs (3-pass split fp16 + complex Gabor epilogue), final layer + HDR loss, "
                             "scalars, final-layer backward, 4 dgrad layer GEMMs, split-K wgrad, complex Adam + repack") if wire else
+                           (f"{n_launch} kernels: encoding, |mu|^2, 9 x (envelope GEMM + stage GEMM), head + loss, TV, scalars, top stage, "
+                            "8 dgrad stage GEMMs, split-K wgrad, d mu / d gamma, Adam + repack") if mfn else
                            "4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",
                    "loss": wl["loss"], "undersampling": wl["undersampling"],
                    "loss_last_step": loss_dev},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": bs * (21 if mask is not None else 20), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / n_e2e, "api": "ChainEngine.train_step (C ABI inr_train_step), pinned host batches"},
-        "gpu_launches": ((15 if dp else 14) if wire else (5 if dp else 4)) * args.steps,
+        "gpu_launches": (n_launch + (1 if dp else 0)) * args.steps,
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"],
                      # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture
                      "traffic": (44.3e6 if wire and bs == 25000 else None),
                      "traffic_source": ("profiles/r01_ncu_lgemm_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, cold L2)"
                                         if wire and bs == 25000 else None),
-                     "kernel": "lgemm_kernel (WIRE forward layer GEMM + Gabor epilogue; one of 4 launches/step)" if wire else "chain_fwd_kernel<SIN>",
+                     "kernel": ("lgemm_kernel (WIRE forward layer GEMM + Gabor epilogue; one of 4 launches/step)" if wire else
+                                ("forward phase (encoding + 18 lgemm launches + head/loss + TV)" if mfn else "chain_fwd_kernel<SIN>")),
                      "kernel_ms": kern_ms,
                      "issued_tflops": (wl["issued_fwd_flop_per_coord"] / wl["net"]["network_depth"] * bs / (kern_ms * 1e-3) / 1e12) if wire else None,
                      "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['source']})",

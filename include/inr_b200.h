@@ -174,7 +174,8 @@ int inr_grad_step(const inr_plan* plan, const inr_loss_desc* loss, const float* 
 int inr_profile_step(const inr_plan* plan, const inr_loss_desc* loss, float* params, float* exp_avg,
                      float* exp_avg_sq, void* wpack, const float* hyper_dev, int32_t* step_dev,
                      const float* coords, const float* input_x, const float* encB, const float* gt,
-                     const uint8_t* mask, int64_t bs, void* workspace, int32_t reps, float* ms_out4, void* stream);
+                     const uint8_t* mask, int64_t bs, void* workspace, float* out, int32_t reps, float* ms_out4,
+                     void* stream);
 
 /* debugging: CTA 0 of the forward kernel writes %globaltimer stamps of its phases into this device buffer of
  * 64 uint64 (NULL switches tracing off; off by default).  Process-global, not thread-safe. */

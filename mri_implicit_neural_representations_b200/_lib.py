@@ -70,7 +70,7 @@ def _load():
     lib.inr_train_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp,
                                    vp, vp, vp]
     lib.inr_grad_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
-    lib.inr_profile_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32,
+    lib.inr_profile_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32,
                                      C.POINTER(C.c_float), vp]
     lib.inr_debug_set_trace.argtypes = [vp]
     lib.inr_selftest_umma.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]

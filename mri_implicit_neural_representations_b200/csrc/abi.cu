@@ -1113,7 +1113,7 @@ extern "C" int inr_grad_step(const inr_plan* p, const inr_loss_desc* loss, const
 extern "C" int inr_profile_step(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
                                 const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
                                 const float* encB, const float* gt, const uint8_t* mask, int64_t bs, void* workspace,
-                                int32_t reps, float* ms_out4, void* stream) {
+                                float* out, int32_t reps, float* ms_out4, void* stream) {
   if (!ms_out4 || reps <= 0) return fail(INR_EINVAL, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaEvent_t ev[7];
@@ -1122,7 +1122,7 @@ extern "C" int inr_profile_step(const inr_plan* p, const inr_loss_desc* loss, fl
   int rc = INR_OK;
   for (int r = 0; r < reps && rc == INR_OK; ++r) {
     rc = train_step_impl(p, loss, params, m, v, wpack, hyper_dev, step_dev, coords, input_x, encB, gt, mask, bs, nullptr,
-                         workspace, nullptr, nullptr, st, ev);
+                         workspace, out, nullptr, st, ev);
     if (rc) break;
     cudaError_t e = cudaEventSynchronize(ev[4]);
     if (e != cudaSuccess) { rc = cuda_fail(e, "profile step"); break; }

@@ -243,16 +243,18 @@ class ChainEngine:
                                     _ptr(self.grads), _ptr(self.loss_out), _stream()), "inr_grad_step(calibration)")
         self._calibrated = True
 
-    def profile_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, reps: int = 20):
+    def profile_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, reps: int = 20, out=None):
         """Average device time (ms) of the four kernels of one step: forward, dgrad, wgrad, optimiser."""
         ld = _loss_desc(loss, loss_opts)
         ms = (C.c_float * 8)()
         L.check(L.lib.inr_profile_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg),
                                        _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords),
-                                       _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.workspace), reps, ms,
-                                       _stream()), "inr_profile_step")
+                                       _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.workspace), _ptr(out),
+                                       reps, ms, _stream()), "inr_profile_step")
         if self.plan.model == "WIRE":
             return {"forward": ms[0], "backward": ms[2], "optimiser": ms[3], "forward_layer_gemms": ms[4]}
+        if self.plan.model not in ("SIREN", "FFN"):      # MFN family: forward (+ TV) | backward (dgrad + wgrad) | optimiser
+            return {"forward": ms[0], "backward": ms[2], "optimiser": ms[3]}
         return {"forward": ms[0], "dgrad": ms[1], "wgrad": ms[2], "optimiser": ms[3]}
 
     def read_image(self, kind: str, layer: int, bs: int) -> torch.Tensor:

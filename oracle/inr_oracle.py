@@ -588,7 +588,7 @@ def model_forward(kind, sd, x, net, trace=None):
 
 
 def train_steps(kind, net, sd, encB, enc_kind, coords, gt, n_steps, batch, lr,
-                loss="L2", loss_opts=None, betas=(0.9, 0.999), mask=None):
+                loss="L2", loss_opts=None, betas=(0.9, 0.999), mask=None, tv=None):
     """Grid-order mini-batches (shuffle=False, src/models/utils.py:84-90) through
     forward -> loss -> autograd backward -> Adam, exactly the loop body of src/train.py:158-192
     restricted to fused-kernel territory.  Returns (losses, final sd)."""
@@ -608,6 +608,7 @@ def train_steps(kind, net, sd, encB, enc_kind, coords, gt, n_steps, batch, lr,
         c, y = coords[pos:pos + batch], gt[pos:pos + batch]
         pos += batch
         out = model_forward(kind, params, encode(c, encB, enc_kind), net)
+        out_full, mb = out, None
         if mask is not None:                      # src/train.py:172-177
             mb = mask[pos - batch:pos]
             out, y = out[mb], y[mb]
@@ -618,6 +619,12 @@ def train_steps(kind, net, sd, encB, enc_kind, coords, gt, n_steps, batch, lr,
         else:
             val, g = LOSS_TRAIN[loss](out.detach(), y)
         live = [p for k, p in params.items() if k not in frozen]
+        if tv is not None and mb is not None and out_full.shape[0] == tv[0] * tv[1]:     # per-coil TV, src/train.py:173-174
+            val_tv, g_full = loss_tv(out_full.detach(), tv[0], tv[1], tv[2] if len(tv) > 2 else 1e-4)
+            g_full = g_full.clone()
+            g_full[mb] += g
+            val = val + val_tv
+            out, g = out_full, g_full
         grads = torch.autograd.grad(out, live, grad_outputs=g)
         with torch.no_grad():
             for (k, p), gr in zip([(k, p) for k, p in params.items() if k not in frozen], grads):
