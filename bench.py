@@ -393,7 +393,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v1, dt1 = cpu_port_steps(wl, 1, 1, bs)
-        n_cpu = max(5, min(200, int(12.0 / max(dt1, 1e-3))))
+        n_cpu = max(2, min(200, int(12.0 / max(dt1, 1e-3))))
         v, dt = cpu_port_steps(wl, n_cpu, 1, bs)
         cpu = {"value": v, "unit": "coords/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": f"{n_cpu} steps x {bs} coords, oracle port (torch CPU fp32, autograd, Adam), {torch.get_num_threads()} threads, {dt:.1f} s"}
