@@ -47,6 +47,16 @@ WORKLOADS = {
         encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
         flop_per_coord=31463424, fwd_flop_per_coord=(18 + 8) * 512 * 512 * 2 + 2 * 512 * 2),
 }
+# BASELINE.json configs[3]: MultiscaleBoundedFourier depth 8 width 512 (4 ring heads), LSL loss per head + 0.1 *
+# ConsistencyLoss, batch 100000, non-per-coil.  Runs through the reference-named module's autograd face
+# (src/train_kspace_multiscale.py loop body): C-ABI forward -> composite loss in PyTorch on the [bs, 2] heads -> C-ABI
+# backward -> fused Adam.  Measured by run_multiscale() below (single GPU, eager launches).
+MULTISCALE_WORKLOAD = dict(
+    name="bounded_fourier_lsl_bs100000", model="BoundedFourier", batch=100000, image_space=False, normalization="max",
+    net={"network_input_size": 512, "network_output_size": 2, "network_depth": 8, "network_width": 512},
+    encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
+    loss_opts={"hdr_eps": 1e-2, "hdr_ff_sigma": 1.0, "hdr_ff_factor": 0.0}, radii=[0.35, 0.7, 1.05, 5.0],
+    flop_per_coord=19423232)
 DEFAULT_WORKLOAD = "wire_kspace_hdr_bs25000"
 SLICE = (15, 320, 320)                 # fastMRI-knee-shaped: 15 coils x 320 x 320 after the reference's crop
 LR = 5e-4
@@ -212,19 +222,146 @@ def run_reference(args, wl, name):
     print(json.dumps(line), flush=True)
 
 
+def run_multiscale(args):
+    """BASELINE config 4 through the drop-in module + composite loss (see MULTISCALE_WORKLOAD)."""
+    wl = MULTISCALE_WORKLOAD
+    sys.path.insert(0, os.path.join(ROOT, "src"))
+    from metrics.losses import ConsistencyLoss, LogSpaceLoss
+    from mri_implicit_neural_representations_b200.modules import MultiscaleBoundedFourier, Positional_Encoder
+    from mri_implicit_neural_representations_b200.trainer import FusedAdam
+    from mri_implicit_neural_representations_b200 import synthetic
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    bs = wl["batch"]
+    peaks = load_peaks()
+    torch.manual_seed(1234)
+    enc = Positional_Encoder(wl["encoder"], device=device)
+    pairs = [(0.0, r) for r in wl["radii"]]
+    model = MultiscaleBoundedFourier(dict(wl["net"]), boundaries=[p for p in pairs for _ in (0, 1)]).to(device)
+    optim = FusedAdam(model, lr=LR, betas=(0.9, 0.999), weight_decay=0.0)
+    lsl, cons = LogSpaceLoss(wl["loss_opts"]), ConsistencyLoss(pairs)
+    C, H, W = SLICE
+    coords, gt, _ = synthetic.make_fit_arrays(1234, C, H, W, image_space=False, normalization="max")
+    coords, gt = coords.to(device), gt.to(device)
+    dist = torch.sqrt(coords[:, 1] ** 2 + coords[:, 2] ** 2)
+    n_batches = coords.shape[0] // bs
+    h_c, h_g = coords[: bs * 8].cpu().pin_memory(), gt[: bs * 8].cpu().pin_memory()
+    d_c, d_g = torch.empty(bs, 3, device=device), torch.empty(bs, 2, device=device)
+
+    def step(c, y, d):
+        outs = model(coords=enc.embedding(c), dist_to_center=d)
+        optim.zero_grad()
+        loss = 0.1 * cons(outs, d)
+        for o in outs:
+            loss = loss + 0.5 * lsl(o.contiguous(), y)
+        loss.backward()
+        optim.step()
+        return loss
+
+    def run(n, i0=0):
+        for i in range(n):
+            j = ((i0 + i) % n_batches) * bs
+            last = step(coords[j:j + bs], gt[j:j + bs], dist[j:j + bs])
+        return last
+
+    run(max(args.warmup, 3))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clk:
+        e0.record()
+        last = run(args.steps, args.warmup)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = args.steps * bs / (ms * 1e-3)
+    loss_last = float(last.detach())
+    # end to end: host batches in, loss out, every step
+    h_loss = torch.empty(1).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        j = (i % 8) * bs
+        d_c.copy_(h_c[j:j + bs], non_blocking=True)
+        d_g.copy_(h_g[j:j + bs], non_blocking=True)
+        dd = torch.sqrt(d_c[:, 1] ** 2 + d_c[:, 2] ** 2)
+        h_loss.copy_(step(d_c, d_g, dd).detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    # CPU port: the oracle's multiscale forward + the same composite loss + torch autograd + Adam on the host cores
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import inr_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(1234)
+        encB = O.encoder_init(wl["encoder"])
+        sd = O.multiscale_init(dict(wl["net"]), bounded=True)
+        P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.Adam(list(P.values()), lr=LR)
+        rows = 20000
+        cc, yy = coords[:rows * 3].cpu(), gt[:rows * 3].cpu()
+        ddc = dist[:rows * 3].cpu()
+        bounds = [p for p in pairs for _ in (0, 1)]
+        n_cpu, t_cpu = 0, 0.0
+        for i in range(40):
+            if t_cpu > 12.0:
+                break
+            k = i % 3
+            c, y, d = cc[k * rows:(k + 1) * rows], yy[k * rows:(k + 1) * rows], ddc[k * rows:(k + 1) * rows]
+            t0 = time.perf_counter()
+            outs = O.multiscale_forward(P, O.encode(c, encB, "gauss"), wl["net"]["network_depth"], d, bounds)
+            opt.zero_grad()
+            loss = 0.1 * cons(outs, d)
+            for o in outs:
+                loss = loss + 0.5 * lsl(o.contiguous(), y)
+            loss.backward()
+            opt.step()
+            if i > 0:
+                n_cpu += 1
+                t_cpu += time.perf_counter() - t0
+        cpu = {"value": n_cpu * rows / t_cpu, "unit": "coords/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{n_cpu} steps x {rows} coords of the {bs}-coord batch, oracle port (torch CPU fp32, autograd, Adam), "
+                         f"{torch.get_num_threads()} threads, {t_cpu:.1f} s"}
+    step_tflops = wl["flop_per_coord"] * bs / (ms / args.steps * 1e-3) / 1e12
+    line = {
+        "metric": "train coords/sec (fwd+bwd+Adam)", "value": value, "unit": "coords/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
+        "config": {"workload": wl["name"], "model": wl["model"], "batch_per_gpu": bs, "slice": list(SLICE),
+                   "parallelism": "single GPU", "launch": "eager (module autograd face)",
+                   "inputs": f"resident coords+targets {coords.shape[0] * 20 / 2**20:.0f} MiB, walked in grid order; gauss encoding in torch "
+                             "(dense [bs,512] input to the engine)",
+                   "step": "src/train_kspace_multiscale.py loop body: inr_forward_dist -> 4 x LogSpaceLoss + 0.1 ConsistencyLoss in "
+                           "PyTorch -> inr_backward_dist -> fused Adam", "loss": "LSL + consistency", "loss_last_step": loss_last},
+        "clocks": clk.summary(),
+        "e2e": {"value": args.steps * bs / (ms_e2e * 1e-3), "unit": "coords/s", "h2d_bytes_per_step": bs * 20, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "api": "MultiscaleBoundedFourier module + FusedAdam, pinned host batches"},
+        "gpu_launches": (1 + 8 + 4 + 3 + 7 + 1 + 1) * args.steps,
+        "roofline": {"bound": "tensor", "achieved": step_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": step_tflops / peaks["tflops_sustained"], "traffic": None,
+                     "kernel": "whole step (live-graph algorithmic FLOP of SURVEY 8d / step time; includes the PyTorch loss ops)",
+                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['source']})"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + [MULTISCALE_WORKLOAD["name"]])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parallel", default="dp", choices=["dp", "independent"],
                     help="N>1: dp = one fit, per-GPU batch shard + NCCL gradient all-reduce; independent = one fit per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload == MULTISCALE_WORKLOAD["name"]:
+        if args.impl == "reference" or args.gpus != 1:
+            raise SystemExit("the multiscale workload is measured on one GPU through the module face only")
+        return run_multiscale(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl, args.workload)
