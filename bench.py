@@ -391,26 +391,69 @@ def main():
     steps_per_pass = n_rows // bs
     out_buf = torch.empty(bs, 2, device=device) if (wl["loss_opts"] or {}).get("tv") else None   # the TV term reads the output
 
-    def one_step():
-        if dp:      # forward+loss+backward -> all-reduce(mean) of the flat fp32 gradients -> Adam (+ fp16 re-pack)
-            eng.grad_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True, out=out_buf)
+    # dp gradient exchange: fused into the optimiser kernel over NVLink peer memory (symmetric memory, double-buffered
+    # by step parity); NCCL all-reduce only if symmetric memory cannot be set up on this box
+    peer, exchange = None, "none"
+    if dp:
+        try:
+            if os.environ.get("INR_DP_EXCHANGE", "peer") != "peer":
+                raise RuntimeError("disabled by INR_DP_EXCHANGE")
+            from mri_implicit_neural_representations_b200.parallel import PeerGradExchange
+            peer = PeerGradExchange(eng.plan.n_params, device)
+            exchange = "optimiser kernel reads all ranks' fp32 gradients over NVLink peer memory (flag barrier, no all-reduce kernel)"
+        except Exception as e:
+            ok = torch.tensor([0], device=device)
+            exchange = f"NCCL all-reduce(avg) ({type(e).__name__}: {e})"[:200]
+        if peer is not None:        # all ranks must agree on the mechanism
+            ok = torch.tensor([1], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0 and peer is not None:
+            peer, exchange = None, "NCCL all-reduce(avg) (symmetric memory unavailable on another rank)"
+    gstep = [0]                                 # host count of optimiser steps (same on every rank): exchange-buffer parity
+
+    def one_step(c=None, y=None, m=None, use_cursor=True):
+        c = coords if c is None else c
+        y = gt if y is None else y
+        m = mask if c is coords else m
+        if dp and peer is not None:
+            par = gstep[0] & 1
+            eng.grad_step(wl["loss"], c, y, bs, mask=m, loss_opts=wl["loss_opts"], use_cursor=use_cursor, out=out_buf,
+                          grads=peer.grads(par))
+            eng.adam_step_peers(peer, par)
+        elif dp:    # forward+loss+backward -> all-reduce(mean) of the flat fp32 gradients -> Adam (+ fp16 re-pack)
+            eng.grad_step(wl["loss"], c, y, bs, mask=m, loss_opts=wl["loss_opts"], use_cursor=use_cursor, out=out_buf)
             allreduce_mean_(eng.grads)
             eng.adam_step()
         else:
-            eng.train_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], use_cursor=True, out=out_buf)
+            eng.train_step(wl["loss"], c, y, bs, mask=m, loss_opts=wl["loss_opts"], use_cursor=use_cursor, out=out_buf)
+        gstep[0] += 1
 
-    # eager warm-up (also sets kernel attributes outside capture), then capture one step in a CUDA graph
-    for _ in range(3):
+    # eager warm-up (also sets kernel attributes outside capture), then capture the step in CUDA graphs
+    # (one per exchange-buffer parity)
+    for _ in range(4):
         one_step()
     torch.cuda.synchronize()
     graph_mode = "cuda graph"
+    n_graphs = 2 if peer is not None else 1
     try:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            one_step()
+        graphs = []
+        for par in range(n_graphs):
+            gstep[0] = par                      # capture records pointers only; nothing executes here
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                one_step()
+            graphs.append(gph)
+        gstep[0] = 0                            # 4 eager steps done: parity 0 is next
+
+        class _Replay:
+            def replay(self):
+                graphs[gstep[0] % n_graphs].replay()
+                gstep[0] += 1
+        graph = _Replay()
     except Exception as e:          # e.g. a collective that refuses capture: fall back to eager launches
         graph_mode = f"eager ({type(e).__name__})"
         torch.cuda.synchronize()
+        gstep[0] = 0
 
         class _Eager:
             def replay(self):
@@ -436,10 +479,15 @@ def main():
     # ---- device-resident throughput (`value`)
     # clocks ramp over tens of ms from idle: warm up for at least W steps AND ~1.5 s of continuous load
     run_steps(args.warmup)
-    t_end = time.perf_counter() + 1.5
-    while time.perf_counter() < t_end:
-        run_steps(50)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run_steps(50)
+    torch.cuda.synchronize()
+    n_ramp = torch.tensor([int(1.5 / max((time.perf_counter() - t0) / 50, 1e-6))], device=device)
+    if dist:                                     # every rank must run the same number of steps (collectives / flag epochs)
+        dist.all_reduce(n_ramp, op=dist.ReduceOp.MAX)
+    run_steps(min(int(n_ramp), 200000))
+    torch.cuda.synchronize()
     reset_cursor()
     run_steps(args.warmup % steps_per_pass)      # leave the cursor where a W-step warm-up would
     torch.cuda.synchronize()
@@ -485,12 +533,7 @@ def main():
         d_g.copy_(h_gt[j:j + bs], non_blocking=True)
         if d_m is not None:
             d_m.copy_(h_mask[j:j + bs], non_blocking=True)
-        if dp:
-            eng.grad_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"], out=out_buf)
-            allreduce_mean_(eng.grads)
-            eng.adam_step()
-        else:
-            eng.train_step(wl["loss"], d_c, d_g, bs, mask=d_m, loss_opts=wl["loss_opts"], out=out_buf)
+        one_step(d_c, d_g, d_m, use_cursor=False)
         h_loss.copy_(eng.loss_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(h_loss)
@@ -542,7 +585,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
         "config": {"workload": args.workload, "model": wl["model"], "batch_per_gpu": bs, "slice": list(SLICE),
                    "parallelism": ("single GPU" if world == 1 else
-                                   (f"dp{world}: replicated weights, per-GPU batch {bs}, NCCL all-reduce(avg) of {eng.plan.n_params * 4} B fp32 gradients per step"
+                                   (f"dp{world}: replicated weights, per-GPU batch {bs}, {eng.plan.n_params * 4} B fp32 gradients per step; exchange: {exchange}"
                                     if dp else f"independent fit per GPU x{world}, no collective")),
                    "launch": graph_mode,
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
@@ -556,7 +599,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": bs * (21 if mask is not None else 20), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / n_e2e, "api": "ChainEngine.train_step (C ABI inr_train_step), pinned host batches"},
-        "gpu_launches": (n_launch + (1 if dp else 0)) * args.steps,
+        "gpu_launches": (n_launch + (1 if dp else 0)) * args.steps,     # dp: gradient-reduce kernel + optimiser kernel instead of one
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"],
                      # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture

@@ -986,6 +986,31 @@ extern "C" int inr_adam_step(const inr_plan* p, float* params, const float* grad
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "adam_kernel");
 }
 
+extern "C" int inr_adam_step_peers(const inr_plan* p, float* params, const float* const* peer_grads, uint32_t* const* peer_flags,
+                                   int32_t n_ranks, int32_t rank, float* m, float* v, void* wpack, const float* hyper_dev,
+                                   const int32_t* step_dev, void* stream) {
+  if (!p || !params || !peer_grads || !peer_flags || !m || !v || !wpack || !hyper_dev || !step_dev) return fail(INR_EINVAL, "null argument");
+  if (n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) return fail(INR_EINVAL, "bad rank / world size (at most 8 ranks)");
+  PeerArgs P{};
+  P.n_ranks = n_ranks; P.rank = rank;
+  for (int q = 0; q < n_ranks; ++q) {
+    if (!peer_grads[q] || !peer_flags[q]) return fail(INR_EINVAL, "null peer pointer");
+    P.grads[q] = peer_grads[q]; P.flags[q] = peer_flags[q];
+  }
+  if (p->is_wire) {
+    WireAdamArgs wa; wire_adam_fill(p, wa);
+    wa.params = params; wa.mom = m; wa.var = v; wa.wpack = static_cast<uint8_t*>(wpack); wa.gpart = peer_grads[rank];
+    wa.hyper = hyper_dev; wa.step = step_dev; wa.do_adam = 1; wa.peer = P;
+    cudaError_t we = launch_wire_adam_flat(wa, static_cast<cudaStream_t>(stream));
+    return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_flat_kernel(peers)");
+  }
+  AdamArgs a; fill_adam(p, a);
+  a.n_split = 1; a.params = params; a.m = m; a.v = v; a.wpack = static_cast<uint8_t*>(wpack);
+  a.gpart = peer_grads[rank]; a.scal = nullptr; a.hyper = hyper_dev; a.step = step_dev; a.do_adam = 1; a.peer = P;
+  cudaError_t e = launch_adam(a, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? INR_OK : cuda_fail(e, "adam_kernel(peers)");
+}
+
 static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
                            const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
                            const float* encB, const float* gt, const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev,

@@ -139,6 +139,18 @@ struct WgradArgs {
   unsigned long long* trace;   // debug: 8 %globaltimer stamps per CTA starting at slot 64 (null in production)
 };
 
+// Data-parallel gradient exchange over NVLink peer memory, fused into the optimiser kernel: every rank's
+// reduced fp32 gradients live in symmetric memory; the optimiser of rank r waits until all ranks have published step
+// `epoch` (one flag per peer, release / acquire at system scope), then sums the n_ranks copies with plain peer loads in
+// rank order (bit-identical on every rank) -- no separate all-reduce kernel.  The gradient buffers are double-buffered
+// by step parity on the host side, which makes the single barrier per step sufficient.
+constexpr int kMaxRanks = 8;
+struct PeerArgs {
+  const float* grads[kMaxRanks];    // rank q's gradient buffer of this step (peer-mapped), [n_params]
+  unsigned int* flags[kMaxRanks];   // rank q's flag array uint32[kMaxRanks] (peer-mapped); flags[q][r] = last epoch r published to q
+  int n_ranks, rank;                // n_ranks == 0: no exchange
+};
+
 struct SegDesc {          // one parameter tensor for the optimiser / packer
   int off, rows, cols;    // flat float offset; weight [rows, cols] or bias (rows = n, cols = 1)
   int layer;              // chain layer index or -1 (not packed)
@@ -160,6 +172,7 @@ struct AdamArgs {
   float* params; float* m; float* v;
   float* grads;             // optional: unscaled fp32 gradients are written here when non-null
   uint8_t* wpack;
+  PeerArgs peer;            // n_ranks > 0: gradients = mean over ranks of peer.grads[q] (gpart ignored)
   const float* gfin;        // finalised gradients of the tensors with gfin_off >= 0 (Gabor mu / gamma) or null
   const float* gpart;       // [n_split][n_params] gradient partials (scaled by S), or plain gradients (n_split 1)
   const float* scal;        // step scalars written by the backward prologue, or null (scale 1, no loss)

@@ -3,6 +3,7 @@
 #pragma once
 #include <cmath>
 #include "inr_kernels.cuh"
+#include "inr_ptx.cuh"
 
 namespace inr {
 
@@ -68,6 +69,26 @@ __device__ __forceinline__ RowLoss loss_row(const LossDesc& L, int out_f, const 
   return r;
 }
 
+
+// Entry barrier of the peer-memory gradient exchange (see PeerArgs): CTA 0 publishes `epoch` to every rank, every CTA
+// waits until all ranks have published it.  Bounded wait (4 s) -> trap instead of a hung GPU.
+__device__ __forceinline__ void peer_barrier(const PeerArgs& P, unsigned int epoch) {
+  if (static_cast<int>(threadIdx.x) < P.n_ranks) {
+    if (blockIdx.x == 0) { __threadfence_system(); st_release_sys(P.flags[threadIdx.x] + P.rank, epoch); }
+    const unsigned int* mine = P.flags[P.rank] + threadIdx.x;
+    const uint64_t t0 = global_ns();
+    unsigned int spins = 0;
+    while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
+      if ((++spins & 0x3FF) == 0 && global_ns() - t0 > 4000000000ull) { asm volatile("trap;"); }
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float peer_mean(const PeerArgs& P, size_t p) {
+  float s = 0.f;
+  for (int q = 0; q < P.n_ranks; ++q) s += ld_relaxed_sys_f32(P.grads[q] + p);
+  return s * (1.f / static_cast<float>(P.n_ranks));
+}
 
 // Fixed-order block reduction of the tile partials -> step scalars sc[kScalars] in shared memory (all threads of the
 // block must call this; works for any blockDim.x that is a multiple of 32, up to 1024).  Bit-reproducible.

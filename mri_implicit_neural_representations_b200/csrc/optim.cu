@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include "inr_kernels.cuh"
+#include "inr_loss.cuh"
 
 namespace inr {
 
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
     }
   }
   __syncthreads();
+  if (a.peer.n_ranks > 0) peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.n_params) return;
   const int si = find_seg(a.seg, a.n_seg, p);
@@ -79,7 +81,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
   if (sg.frozen) { if (a.grads) a.grads[p] = 0.f; return; }
   const float* gp = a.gpart;
   float g = 0.f;
-  if (sg.gfin_off >= 0 && a.gfin) g = a.gfin[sg.gfin_off + (p - sg.off)];
+  if (a.peer.n_ranks > 0) g = peer_mean(a.peer, p);
+  else if (sg.gfin_off >= 0 && a.gfin) g = a.gfin[sg.gfin_off + (p - sg.off)];
   else
     for (int s = 0; s < a.n_split; ++s) g += gp[static_cast<size_t>(s) * a.gstride + p];
   g *= (sg.scale_slot >= 0 && a.scal) ? 1.f / a.scal[sg.scale_slot] : s_c[2];

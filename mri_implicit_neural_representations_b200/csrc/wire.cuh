@@ -126,6 +126,7 @@ struct WireAdamArgs {
   const float* gpart; const float* scal; const float* hyper; const int* step;
   float* loss_out; int* row_offset; int row_advance;
   int do_adam, scal_has_bc, pack_only;
+  PeerArgs peer;            // flat kernel only: n_ranks > 0 -> gradients = mean over ranks of peer.grads[q]
 };
 
 }  // namespace inr

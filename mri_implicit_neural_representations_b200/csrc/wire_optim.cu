@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include "wire.cuh"
+#include "inr_loss.cuh"
 
 namespace inr {
 
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_consta
     s_c[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.hyper[2]), t)));
   }
   __syncthreads();
+  if (a.peer.n_ranks > 0) peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= M.n_params) return;
   const int L = M.depth + 1;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_consta
     if (l >= 1 && l < L && p >= M.w_off[l] && p < M.w_off[l] + M.c * M.c * 2) { layer = l; idx = p - M.w_off[l]; break; }
   }
   if (frozen) return;
-  float g = a.gpart[p], w = a.params[p];
+  float g = a.peer.n_ranks > 0 ? peer_mean(a.peer, p) : a.gpart[p], w = a.params[p];
   const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
   if (wd != 0.f) g = fmaf(wd, w, g);
   const float m = b1 * a.mom[p] + (1.f - b1) * g;

@@ -221,6 +221,15 @@ class ChainEngine:
                                     _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _stream()),
                 "inr_adam_step")
 
+    def adam_step_peers(self, ex, parity=None):
+        """Data-parallel optimiser step with the gradient exchange fused into the kernel: gradients = mean over ranks
+        of the peer-mapped buffers of `ex` (a parallel.PeerGradExchange) for the given parity."""
+        self.step += 1
+        gp, fp = ex.pointers(parity)
+        L.check(L.lib.inr_adam_step_peers(self.plan.handle, _ptr(self.params), gp, fp, ex.world, ex.rank, _ptr(self.exp_avg),
+                                          _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _stream()),
+                "inr_adam_step_peers")
+
     # ---- fused step --------------------------------------------------------------------------------
     def train_step(self, loss: str, coords: Optional[torch.Tensor], gt: torch.Tensor, bs: int, x: Optional[torch.Tensor] = None,
                    mask: Optional[torch.Tensor] = None, loss_opts: Optional[dict] = None, use_cursor: bool = False,
@@ -281,16 +290,20 @@ class ChainEngine:
             mat = out
         return mat
 
-    def grad_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, use_cursor: bool = False, out=None):
-        """forward + loss + backward only; gradients land in self.grads (data-parallel: all-reduce them, then adam_step)."""
+    def grad_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, use_cursor: bool = False, out=None,
+                  grads: Optional[torch.Tensor] = None):
+        """forward + loss + backward only; gradients land in self.grads, or in `grads` (e.g. a PeerGradExchange buffer)
+        (data-parallel: all-reduce them, then adam_step -- or adam_step_peers)."""
+        gbuf = self.grads if grads is None else grads
+        assert gbuf.numel() >= self.plan.n_params and gbuf.dtype == torch.float32 and gbuf.is_cuda
         ld = _loss_desc(loss, loss_opts)
         if self._lagged_scales and not self._calibrated:
             self._calibrate(ld, coords, x, gt, mask, bs, out)
         L.check(L.lib.inr_grad_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords), _ptr(x),
                                     _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.cursor) if use_cursor else None,
-                                    _ptr(self.workspace), _ptr(out), _ptr(self.grads), _ptr(self.loss_out), _stream()),
+                                    _ptr(self.workspace), _ptr(out), _ptr(gbuf), _ptr(self.loss_out), _stream()),
                 "inr_grad_step")
-        return self.grads
+        return gbuf
 
     def read_mfn_image(self, kind: str, stage: int, bs: int) -> torch.Tensor:
         """MFN only (tests / debugging): 'z' (stage output), 'g' (sin p), 'dp' (S_stage * dL/dp) as [rows_pad, width]."""

@@ -37,3 +37,45 @@ def allreduce_mean_(flat: torch.Tensor, weight: float = 1.0, group=None) -> torc
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.div_(world)
     return flat
+
+
+class PeerGradExchange:
+    """Symmetric (peer-mapped) gradient buffers for the optimiser-fused data-parallel exchange (`inr_adam_step_peers`).
+
+    Every rank allocates 2 x [n_params] fp32 (double-buffered by step parity) plus a flag array in
+    torch.distributed symmetric memory; after the rendezvous each rank holds device pointers to all peers' copies.
+    `grads(parity)` is the local buffer `inr_grad_step` writes; `ChainEngine.adam_step_peers(ex)` runs the optimiser
+    kernel that waits for all ranks' flags, sums the peers' gradients over NVLink and applies Adam -- there is no
+    separate all-reduce kernel.  Raises if symmetric memory is unavailable (callers fall back to NCCL)."""
+
+    FLAG_WORDS = 64
+
+    def __init__(self, n_params: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("the fused exchange supports at most 8 ranks (one NVSwitch domain)")
+        self.n = (int(n_params) + 3) // 4 * 4
+        total = 2 * self.n + self.FLAG_WORDS
+        self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        dist.barrier(group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._grad_ptrs = [(C.c_void_p * self.world)(*[p + 4 * par * self.n for p in ptrs]) for par in (0, 1)]
+        self._flag_ptrs = (C.c_void_p * self.world)(*[p + 8 * self.n for p in ptrs])
+        self.parity = 0
+
+    def grads(self, parity=None) -> torch.Tensor:
+        par = self.parity if parity is None else parity
+        return self.buf[par * self.n:(par + 1) * self.n]
+
+    def pointers(self, parity=None):
+        par = self.parity if parity is None else parity
+        return self._grad_ptrs[par], self._flag_ptrs
+
+    def flip(self):
+        self.parity ^= 1
