@@ -84,10 +84,30 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& P, unsigned int epo
   }
   __syncthreads();
 }
-__device__ __forceinline__ float peer_mean(const PeerArgs& P, size_t p) {
-  float s = 0.f;
-  for (int q = 0; q < P.n_ranks; ++q) s += ld_relaxed_sys_f32(P.grads[q] + p);
-  return s * (1.f / static_cast<float>(P.n_ranks));
+// Gather phase: the CTA owns parameters [base, base + 4 * blockDim.x); thread t pulls one float4 from every rank (all
+// loads in flight together: the exchange is NVLink-latency bound), adds them in rank order and leaves the mean in
+// shared memory for the per-parameter optimiser code that follows.  `n` is a multiple of 4 (buffers are padded).
+__device__ __forceinline__ float4 ld_relaxed_sys_f32x4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_gather(const PeerArgs& P, size_t base, size_t n, float* s_g /*[4 * blockDim.x]*/) {
+  const size_t p4 = base + 4 * static_cast<size_t>(threadIdx.x);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p4 < n) {
+    float4 v[kMaxRanks];
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+      if (q < P.n_ranks) v[q] = ld_relaxed_sys_f32x4(P.grads[q] + p4);
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+      if (q < P.n_ranks) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+    const float inv = 1.f / static_cast<float>(P.n_ranks);
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+  }
+  reinterpret_cast<float4*>(s_g)[threadIdx.x] = acc;
+  __syncthreads();
 }
 
 // Fixed-order block reduction of the tile partials -> step scalars sc[kScalars] in shared memory (all threads of the

@@ -73,36 +73,46 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
     }
   }
   __syncthreads();
-  if (a.peer.n_ranks > 0) peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.n_params) return;
-  const int si = find_seg(a.seg, a.n_seg, p);
-  const SegDesc& sg = a.seg[si];
-  if (sg.frozen) { if (a.grads) a.grads[p] = 0.f; return; }
-  const float* gp = a.gpart;
-  float g = 0.f;
-  if (a.peer.n_ranks > 0) g = peer_mean(a.peer, p);
-  else if (sg.gfin_off >= 0 && a.gfin) g = a.gfin[sg.gfin_off + (p - sg.off)];
-  else
-    for (int s = 0; s < a.n_split; ++s) g += gp[static_cast<size_t>(s) * a.gstride + p];
-  g *= (sg.scale_slot >= 0 && a.scal) ? 1.f / a.scal[sg.scale_slot] : s_c[2];
-  float w = a.params[p];
-  if (a.do_adam) {
-    const float l1 = a.hyper[5], l2 = a.hyper[6];
-    if (l1 != 0.f) g += l1 * (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f));
-    if (l2 != 0.f) g += 2.f * l2 * w;
+  // peer mode (data-parallel exchange fused in): one CTA owns 1024 consecutive parameters -- gather, then 4 passes
+  __shared__ __align__(16) float s_g[4 * 256];
+  const bool peer = a.peer.n_ranks > 0;
+  const int reps = peer ? 4 : 1;
+  const size_t base = static_cast<size_t>(blockIdx.x) * 256 * reps;
+  if (peer) {
+    peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
+    peer_gather(a.peer, base, static_cast<size_t>((a.n_params + 3) & ~3), s_g);
   }
-  if (a.grads) a.grads[p] = g;
-  if (!a.do_adam) return;
-  const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
-  if (wd != 0.f) g = fmaf(wd, w, g);
-  const float m = b1 * a.m[p] + (1.f - b1) * g;
-  const float v = b2 * a.v[p] + (1.f - b2) * g * g;
-  a.m[p] = m; a.v[p] = v;
-  const float denom = sqrtf(v) / s_c[1] + eps;
-  w = w - s_c[0] * (m / denom);
-  a.params[p] = w;
-  if (sg.pack_fwd | sg.pack_bwd) pack_store(sg, a.wpack, p - sg.off, w);
+  for (int j = 0; j < reps; ++j) {
+    const int p = static_cast<int>(base) + j * 256 + threadIdx.x;
+    if (p >= a.n_params) return;
+    const int si = find_seg(a.seg, a.n_seg, p);
+    const SegDesc& sg = a.seg[si];
+    if (sg.frozen) { if (a.grads) a.grads[p] = 0.f; continue; }
+    const float* gp = a.gpart;
+    float g = 0.f;
+    if (peer) g = s_g[j * 256 + threadIdx.x];
+    else if (sg.gfin_off >= 0 && a.gfin) g = a.gfin[sg.gfin_off + (p - sg.off)];
+    else
+      for (int s = 0; s < a.n_split; ++s) g += gp[static_cast<size_t>(s) * a.gstride + p];
+    g *= (sg.scale_slot >= 0 && a.scal) ? 1.f / a.scal[sg.scale_slot] : s_c[2];
+    float w = a.params[p];
+    if (a.do_adam) {
+      const float l1 = a.hyper[5], l2 = a.hyper[6];
+      if (l1 != 0.f) g += l1 * (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f));
+      if (l2 != 0.f) g += 2.f * l2 * w;
+    }
+    if (a.grads) a.grads[p] = g;
+    if (!a.do_adam) continue;
+    const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
+    if (wd != 0.f) g = fmaf(wd, w, g);
+    const float m = b1 * a.m[p] + (1.f - b1) * g;
+    const float v = b2 * a.v[p] + (1.f - b2) * g * g;
+    a.m[p] = m; a.v[p] = v;
+    const float denom = sqrtf(v) / s_c[1] + eps;
+    w = w - s_c[0] * (m / denom);
+    a.params[p] = w;
+    if (sg.pack_fwd | sg.pack_bwd) pack_store(sg, a.wpack, p - sg.off, w);
+  }
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ AdamArgs a) {
@@ -174,7 +184,8 @@ cudaError_t launch_tv(const TvArgs& a, int n_tiles, cudaStream_t st) {
 }
 
 cudaError_t launch_adam(const AdamArgs& a, cudaStream_t stream) {
-  const int grid = (a.n_params + 255) / 256;
+  const int per_cta = a.peer.n_ranks > 0 ? 1024 : 256;
+  const int grid = (a.n_params + per_cta - 1) / per_cta;
   adam_kernel<<<grid, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }

@@ -135,26 +135,35 @@ __global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_consta
     s_c[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.hyper[2]), t)));
   }
   __syncthreads();
-  if (a.peer.n_ranks > 0) peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= M.n_params) return;
-  const int L = M.depth + 1;
-  int layer = -1, idx = 0;
-  bool frozen = false;
-  for (int l = 0; l <= L; ++l) {
-    if (l < L && (p == M.omega_off[l] || p == M.scale_off[l])) { frozen = true; break; }
-    if (l >= 1 && l < L && p >= M.w_off[l] && p < M.w_off[l] + M.c * M.c * 2) { layer = l; idx = p - M.w_off[l]; break; }
+  __shared__ __align__(16) float s_g[4 * 256];
+  const bool peer = a.peer.n_ranks > 0;
+  const int reps = peer ? 4 : 1;
+  const size_t base = static_cast<size_t>(blockIdx.x) * 256 * reps;
+  if (peer) {
+    peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
+    peer_gather(a.peer, base, static_cast<size_t>((M.n_params + 3) & ~3), s_g);
   }
-  if (frozen) return;
-  float g = a.peer.n_ranks > 0 ? peer_mean(a.peer, p) : a.gpart[p], w = a.params[p];
-  const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
-  if (wd != 0.f) g = fmaf(wd, w, g);
-  const float m = b1 * a.mom[p] + (1.f - b1) * g;
-  const float v = b2 * a.var[p] + (1.f - b2) * g * g;
-  a.mom[p] = m; a.var[p] = v;
-  w = w - s_c[0] * (m / (sqrtf(v) / s_c[1] + eps));
-  a.params[p] = w;
-  if (layer >= 1) { const int e = idx >> 1; wire_pack_hidden(M, a.wpack, layer, e / M.c, e % M.c, idx & 1, w); }
+  const int L = M.depth + 1;
+  for (int j = 0; j < reps; ++j) {
+    const int p = static_cast<int>(base) + j * 256 + threadIdx.x;
+    if (p >= M.n_params) return;
+    int layer = -1, idx = 0;
+    bool frozen = false;
+    for (int l = 0; l <= L; ++l) {
+      if (l < L && (p == M.omega_off[l] || p == M.scale_off[l])) { frozen = true; break; }
+      if (l >= 1 && l < L && p >= M.w_off[l] && p < M.w_off[l] + M.c * M.c * 2) { layer = l; idx = p - M.w_off[l]; break; }
+    }
+    if (frozen) continue;
+    float g = peer ? s_g[j * 256 + threadIdx.x] : a.gpart[p], w = a.params[p];
+    const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
+    if (wd != 0.f) g = fmaf(wd, w, g);
+    const float m = b1 * a.mom[p] + (1.f - b1) * g;
+    const float v = b2 * a.var[p] + (1.f - b2) * g * g;
+    a.mom[p] = m; a.var[p] = v;
+    w = w - s_c[0] * (m / (sqrtf(v) / s_c[1] + eps));
+    a.params[p] = w;
+    if (layer >= 1) { const int e = idx >> 1; wire_pack_hidden(M, a.wpack, layer, e / M.c, e % M.c, idx & 1, w); }
+  }
 }
 
 cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st) {
@@ -162,7 +171,8 @@ cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_wire_adam_flat(const WireAdamArgs& a, cudaStream_t st) {
-  wire_adam_flat_kernel<<<(a.m.n_params + 255) / 256, 256, 0, st>>>(a);
+  const int per_cta = a.peer.n_ranks > 0 ? 1024 : 256;
+  wire_adam_flat_kernel<<<(a.m.n_params + per_cta - 1) / per_cta, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
