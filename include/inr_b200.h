@@ -37,6 +37,7 @@ extern "C" {
 #define INR_MODEL_FOURIER 4  /* FourierNet, src/models/mfn.py:61-94 (one head after stage `depth`) */
 #define INR_MODEL_MS_FOURIER 5          /* MultiscaleKFourier, src/models/mfn.py:206-267 (heads at output_layers) */
 #define INR_MODEL_MS_BOUNDED_FOURIER 6  /* MultiscaleBoundedFourier, src/models/mfn.py:288-356 (BoundedLinear row masks) */
+#define INR_MODEL_WIRE2D 8              /* WIRE2D, src/models/wire2d.py:63-118 (linear + scale_orth per layer, width not reduced, in 3) */
 #define INR_MODEL_GABOR 7               /* GaborNet / KGaborNet, src/models/mfn.py:96-204 (mu, gamma, linear per filter; one head) */
 /* encoders (src/models/networks.py:7-35) */
 #define INR_ENC_NONE 0       /* x is the dense [bs, in] fp32 network input */

@@ -31,7 +31,7 @@ class TensorInfo(C.Structure):
                 ("layer", C.c_int32), ("is_bias", C.c_int32), ("is_complex", C.c_int32), ("frozen", C.c_int32)]
 
 
-MODEL = {"SIREN": 1, "FFN": 2, "WIRE": 3, "Fourier": 4, "MultiscaleFourier": 5, "BoundedFourier": 6, "Gabor": 7, "KGabor": 7}
+MODEL = {"SIREN": 1, "FFN": 2, "WIRE": 3, "Fourier": 4, "MultiscaleFourier": 5, "BoundedFourier": 6, "Gabor": 7, "KGabor": 7, "WIRE2D": 8}
 ENC = {"none": 0, "gauss": 1}
 LAST = {"linear": 0, "tanh": 1, "sigmoid": 2}
 LOSS = {"none": 0, "L2": 1, "L1": 2, "MSLE": 3, "tanh": 4, "LSL": 5, "HDR": 6}

@@ -35,6 +35,11 @@ cudaError_t launch_mfn_top(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_gabor_prep(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_gabor_grad(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_tv(const TvArgs& a, int n_tiles, cudaStream_t st);
+cudaError_t launch_w2d_first(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_w2d_last(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_w2d_blast(const WireAuxArgs& a, cudaStream_t st);
+cudaError_t launch_w2d_adam(const WireAdamArgs& a, cudaStream_t st);
+cudaError_t launch_w2d_adam_flat(const WireAdamArgs& a, cudaStream_t st);
 }  // namespace inr
 
 using namespace inr;
@@ -94,6 +99,7 @@ static int lgemm_dbg() { static int v = -1; if (v < 0) { const char* e = std::ge
 static unsigned long long* lgemm_trace_ptr() { return (g_trace && g_trace_lgemm_count++ == g_trace_lgemm_sel) ? g_trace : nullptr; }
 
 static int wire_plan_create(const inr_model_desc* d, inr_plan** out);
+static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out);
 static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs);
 static int mfn_plan_create(const inr_model_desc* d, inr_plan** out);
 static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs);
@@ -101,6 +107,7 @@ static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs);
 extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (!d || !out) return fail(INR_EINVAL, "null argument");
   if (d->model == INR_MODEL_WIRE) return wire_plan_create(d, out);
+  if (d->model == INR_MODEL_WIRE2D) return wire2d_plan_create(d, out);
   if (d->model == INR_MODEL_FOURIER || d->model == INR_MODEL_MS_FOURIER || d->model == INR_MODEL_MS_BOUNDED_FOURIER ||
       d->model == INR_MODEL_GABOR)
     return mfn_plan_create(d, out);
@@ -337,7 +344,7 @@ static int wire_plan_create(const inr_model_desc* d, inr_plan** out) {
   p->is_wire = true;
   WireModel& M = p->wm;
   std::memset(&M, 0, sizeof(M));
-  M.depth = d->depth; M.c = c; M.in_f = 3; M.out_f = d->out_features;
+  M.depth = d->depth; M.c = c; M.in_f = 3; M.out_f = d->out_features; M.nlin = 1; M.P = kWP;
   M.omega_first = d->w0; M.omega_hidden = d->hidden_omega_0; M.sigma = d->sigma0;
   int off = 0;
   const int L = M.depth + 1;
@@ -407,6 +414,103 @@ static int wire_plan_create(const inr_model_desc* d, inr_plan** out) {
   return INR_OK;
 }
 
+// WIRE2D (reference src/models/wire2d.py): two linears per layer, hidden width = network_width (not reduced)
+static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out) {
+  const int c = d->width;
+  if (d->in_features != 3) return fail(INR_EUNSUPPORTED, "WIRE2D kernels take raw (coil, kx, ky) coordinates: network_input_size 3");
+  if (d->encoder != INR_ENC_NONE) return fail(INR_EUNSUPPORTED, "WIRE2D is used without positional encoding");
+  if (c < 8 || c > kW2dMaxP) return fail(INR_EUNSUPPORTED, "WIRE2D kernels are built for network_width <= 256");
+  if (d->depth < 1 || d->depth > kWMaxDepth) return fail(INR_EINVAL, "network_depth out of range");
+  if (d->out_features < 1 || d->out_features > 2) return fail(INR_EUNSUPPORTED, "network_output_size must be 1 or 2");
+  if (d->last_act != INR_LAST_LINEAR) return fail(INR_EUNSUPPORTED, "WIRE2D last_tanh (complex tanh tail) is not built");
+  inr_plan* p = new (std::nothrow) inr_plan();
+  if (!p) return fail(INR_EINVAL, "out of host memory");
+  p->desc = *d;
+  p->is_wire = true;
+  WireModel& M = p->wm;
+  std::memset(&M, 0, sizeof(M));
+  const int P = (c + 63) / 64 * 64;
+  M.depth = d->depth; M.c = c; M.in_f = 3; M.out_f = d->out_features; M.nlin = 2; M.P = P;
+  M.omega_first = d->w0; M.omega_hidden = d->hidden_omega_0; M.sigma = d->sigma0;
+  int off = 0;
+  const int L = M.depth + 1;
+  for (int l = 0; l <= L; ++l) {      // state_dict order: omega_0, scale_0, linear.{weight,bias}, scale_orth.{weight,bias}
+    if (l < L) {
+      M.omega_off[l] = off; p->tensors.push_back({off, 1, 1, l, 0, 0, 1}); off += 1;
+      M.scale_off[l] = off; p->tensors.push_back({off, 1, 1, l, 0, 0, 1}); off += 1;
+    }
+    if (l == 0) {
+      M.w_off[l] = off; p->tensors.push_back({off, c, 3, l, 0, 0, 0}); off += c * 3;
+      M.b_off[l] = off; p->tensors.push_back({off, c, 1, l, 1, 0, 0}); off += c;
+      M.v_off[l] = off; p->tensors.push_back({off, c, 3, l, 0, 0, 0}); off += c * 3;
+      M.vb_off[l] = off; p->tensors.push_back({off, c, 1, l, 1, 0, 0}); off += c;
+    } else {
+      const int rows = l == L ? M.out_f : c;
+      M.w_off[l] = off; p->tensors.push_back({off, rows, c, l, 0, 1, 0}); off += rows * c * 2;
+      M.b_off[l] = off; p->tensors.push_back({off, rows, 1, l, 1, 1, 0}); off += rows * 2;
+      if (l < L) {
+        M.v_off[l] = off; p->tensors.push_back({off, c, c, l, 0, 1, 0}); off += c * c * 2;
+        M.vb_off[l] = off; p->tensors.push_back({off, c, 1, l, 1, 1, 0}); off += c * 2;
+      }
+    }
+  }
+  M.n_params = off;
+  const uint32_t fwd_bytes = static_cast<uint32_t>(P / kW2dFwdFeat) * (2 * P / 32) * (kW2dNT * 64);   // all forward N-blocks, K = 2P
+  const uint32_t bwd_bytes = static_cast<uint32_t>(P / kW2dBwdFeat) * (4 * P / 32) * (kW2dNT * 64);   // all dgrad N-blocks, K = 4P
+  uint32_t wo = 0;
+  for (int l = 1; l <= M.depth; ++l) {
+    M.wf_hi[l] = wo; wo += fwd_bytes;
+    M.wf_lo[l] = wo; wo += fwd_bytes;
+    M.wd_hi[l] = wo; wo += bwd_bytes;
+  }
+  M.wpack_bytes = wo;
+  const int K2 = 2 * P, Z4 = 4 * P;
+  int go = 0;
+  for (int l = 1; l <= M.depth; ++l) { M.gd_hidden[l] = go; go += Z4 * K2 + Z4; }
+  M.gd_final = go; go += 16 * K2 + 16;
+  M.gd_first = go; go += Z4 * 16;
+  M.gd_floats = go;
+  const uint32_t th = static_cast<uint32_t>(kTileM) * K2 * 2, tz = static_cast<uint32_t>(kTileM) * Z4 * 2;
+  const int hc = K2 / 128, zc = Z4 / 128;
+  for (int l = 1; l <= M.depth; ++l)
+    for (int mc = 0; mc < zc; ++mc)            // 128 rows of D = dZ^T [hr|hi]
+      for (int c0 = 0, per = chunk_group(hc); c0 < hc; c0 += per) {
+        const int nch = (hc - c0) < per ? (hc - c0) : per;
+        WgradUnit u{};
+        u.a_tile_stride = tz; u.a_sub = mc * 32768; u.a_bytes = 32768;
+        u.b_tile_stride = th; u.b_sub = c0 * 32768; u.b_bytes = 32768;
+        u.n = 128; u.n_chunks = nch; u.transposed = 0;
+        u.out_off = M.gd_hidden[l]; u.out_ld = K2; u.row0 = mc * 128; u.col0 = c0 * 128;
+        u.rows_valid = 128; u.cols_valid = 128 * nch;
+        u.bias_off = c0 == 0 ? M.gd_hidden[l] + Z4 * K2 : -1;
+        p->units.push_back(u); p->unit_layer.push_back(l);
+      }
+  for (int mc = 0; mc < hc; ++mc) {            // final layer, transposed
+    WgradUnit u{};
+    u.a_tile_stride = th; u.a_sub = mc * 32768; u.a_bytes = 32768;
+    u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+    u.n = kDzLastCols; u.transposed = 1;
+    u.out_off = M.gd_final; u.out_ld = K2; u.row0 = 0; u.col0 = mc * 128;
+    u.rows_valid = M.out_f; u.cols_valid = 128;
+    u.bias_off = mc == 0 ? M.gd_final + 16 * K2 : -1;
+    p->units.push_back(u); p->unit_layer.push_back(L);
+  }
+  for (int mc = 0; mc < zc; ++mc) {            // first layer: D0[row][col] = sum_rows dZ0[row] * ximg[col] (b / d rows stay zero)
+    WgradUnit u{};
+    u.a_tile_stride = tz; u.a_sub = mc * 32768; u.a_bytes = 32768;
+    u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+    u.n = kDzLastCols; u.transposed = 0;
+    u.out_off = M.gd_first; u.out_ld = 16; u.row0 = mc * 128; u.col0 = 0;
+    u.rows_valid = 128; u.cols_valid = 16;
+    u.bias_off = -1;
+    p->units.push_back(u); p->unit_layer.push_back(0);
+  }
+  if (static_cast<int>(p->units.size()) > kMaxUnits) { delete p; return fail(INR_EUNSUPPORTED, "WIRE2D model too deep for the static unit table"); }
+  p->n_sm = query_sm_count();
+  *out = p;
+  return INR_OK;
+}
+
 static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
   const WireModel& M = p->wm;
   WireWorkspace w{};
@@ -421,10 +525,11 @@ static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
   w.part = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
   w.g = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
   w.outacc = o;
-  const uint64_t img = static_cast<uint64_t>(T) * kWTileBytes;
+  const uint64_t img = static_cast<uint64_t>(T) * kTileM * 2 * M.P * 2;            // H images: [hr | hi]
+  const uint64_t zimg = img * M.nlin;                                              // pre-activation / gradient images
   for (int l = 1; l <= M.depth + 1; ++l) { w.hhi[l] = o; o += img; w.hlo[l] = o; o += img; }
-  for (int l = 0; l <= M.depth; ++l) { w.ab[l] = o; o += img; }
-  for (int l = 0; l <= M.depth; ++l) { w.dz[l] = o; o += img; }
+  for (int l = 0; l <= M.depth; ++l) { w.ab[l] = o; o += zimg; }
+  for (int l = 0; l <= M.depth; ++l) { w.dz[l] = o; o += zimg; }
   w.dzlast = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024);
   w.ximg = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024);
   w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * M.gd_floats * 4, 1024);
@@ -448,10 +553,22 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
   WireAuxArgs x; wire_aux_fill(p, w, x, params, ws, bs);
   x.loss = loss; x.coords = coords; x.gt = gt; x.mask = mask; x.out = out; x.train = train;
   x.row_offset = row_off; x.step_counter = step;
-  cudaError_t e = launch_wire_first(x, st);
+  cudaError_t e = M.nlin == 2 ? launch_w2d_first(x, st) : launch_wire_first(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "wire_first_kernel");
   if (gemm_ev) cudaEventRecord(gemm_ev[0], st);
-  for (int l = 1; l <= M.depth; ++l) {
+  for (int l = 1; l <= M.depth && M.nlin == 2; ++l) {
+    LGemmArgs g{};
+    g.seg[0].a_hi = W + w.hhi[l]; g.seg[0].a_lo = W + w.hlo[l];
+    g.seg[0].b_hi = wp + M.wf_hi[l]; g.seg[0].b_lo = wp + M.wf_lo[l];
+    g.seg[0].a_tile_bytes = static_cast<uint32_t>(kTileM) * 2 * M.P * 2; g.seg[0].k_stages = 2 * M.P / kStageK; g.seg[0].acc_col = 0;
+    g.n_seg = 1; g.nt = kW2dNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.P / kW2dFwdFeat; g.passes = 3; g.mode = LG_W2D_FWD;
+    g.bias = params + M.b_off[l]; g.bias2 = params + M.vb_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c;
+    g.p2 = M.P; g.train = train;
+    g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
+    e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(wire2d fwd)");
+  }
+  for (int l = 1; l <= M.depth && M.nlin == 1; ++l) {
     LGemmArgs g{};
     g.seg[0].a_hi = W + w.hhi[l]; g.seg[0].a_lo = W + w.hlo[l];
     g.seg[0].b_hi = wp + M.wf_hi[l]; g.seg[0].b_lo = wp + M.wf_lo[l];
@@ -464,7 +581,7 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
   }
   if (gemm_ev) cudaEventRecord(gemm_ev[1], st);
   x.step_counter = nullptr;
-  e = launch_wire_last(x, st);
+  e = M.nlin == 2 ? launch_w2d_last(x, st) : launch_wire_last(x, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wire_last_kernel");
 }
 
@@ -479,9 +596,21 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
   if (dout) { e = launch_wire_dout_amax(x, st); if (e != cudaSuccess) return cuda_fail(e, "wire_dout_amax_kernel"); }
   e = launch_wire_scalars(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "wire_scalars_kernel");
-  e = launch_wire_blast(x, st);
+  e = M.nlin == 2 ? launch_w2d_blast(x, st) : launch_wire_blast(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "wire_blast_kernel");
-  for (int l = M.depth; l >= 1; --l) {      // dL/dh_{l-1} = dZ_l * conj-block(W_l), then the Gabor derivative of layer l-1
+  for (int l = M.depth; l >= 1 && M.nlin == 2; --l) {
+    LGemmArgs g{};
+    g.seg[0].a_hi = W + w.dz[l]; g.seg[0].b_hi = wp + M.wd_hi[l];
+    g.seg[0].a_tile_bytes = static_cast<uint32_t>(kTileM) * 4 * M.P * 2; g.seg[0].k_stages = 4 * M.P / kStageK; g.seg[0].acc_col = 0;
+    g.n_seg = 1; g.nt = kW2dNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.P / kW2dBwdFeat; g.passes = 1; g.mode = LG_W2D_DGRAD;
+    g.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.p2 = M.P;
+    g.real_first = (l - 1 == 0) ? 1 : 0;
+    g.in_y = W + w.hhi[l]; g.in_ab = W + w.ab[l - 1]; g.out_dz = W + w.dz[l - 1];
+    g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = l; g.dst_layer = l - 1;
+    e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(wire2d dgrad)");
+  }
+  for (int l = M.depth; l >= 1 && M.nlin == 1; --l) {      // dL/dh_{l-1} = dZ_l * conj-block(W_l), then the Gabor derivative of layer l-1
     LGemmArgs g{};
     g.seg[0].a_hi = W + w.dz[l]; g.seg[0].b_hi = wp + M.wd_hi[l];
     g.seg[0].a_tile_bytes = kWTileBytes; g.seg[0].k_stages = kW2 / kStageK; g.seg[0].acc_col = 0; g.n_seg = 1; g.nt = kWNT;
@@ -828,7 +957,7 @@ extern "C" int inr_pack_weights(const inr_plan* p, const float* params, void* wp
   if (p->is_wire) {
     WireAdamArgs wa; wire_adam_fill(p, wa);
     wa.params = const_cast<float*>(params); wa.wpack = static_cast<uint8_t*>(wpack); wa.pack_only = 1;
-    cudaError_t we = launch_wire_adam(wa, static_cast<cudaStream_t>(stream));
+    cudaError_t we = (p->wm.nlin == 2 ? launch_w2d_adam(wa, static_cast<cudaStream_t>(stream)) : launch_wire_adam(wa, static_cast<cudaStream_t>(stream)));
     return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_kernel(pack)");
   }
   AdamArgs a; fill_adam(p, a);
@@ -949,7 +1078,7 @@ extern "C" int inr_backward(const inr_plan* p, const float* params, const void* 
     wa.n_split = ww.n_split; wa.params = const_cast<float*>(params); wa.grads = grads;
     wa.gpart = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + ww.gpart);
     wa.scal = reinterpret_cast<const float*>(static_cast<uint8_t*>(workspace) + ww.scal);
-    cudaError_t we = launch_wire_adam(wa, st);
+    cudaError_t we = p->wm.nlin == 2 ? launch_w2d_adam(wa, st) : launch_wire_adam(wa, st);
     return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_kernel(reduce)");
   }
   Workspace w = plan_workspace(p, bs);
@@ -976,7 +1105,7 @@ extern "C" int inr_adam_step(const inr_plan* p, float* params, const float* grad
     WireAdamArgs wa; wire_adam_fill(p, wa);
     wa.params = params; wa.mom = m; wa.var = v; wa.wpack = static_cast<uint8_t*>(wpack); wa.gpart = grads;
     wa.hyper = hyper_dev; wa.step = step_dev; wa.do_adam = 1;
-    cudaError_t we = launch_wire_adam_flat(wa, static_cast<cudaStream_t>(stream));
+    cudaError_t we = p->wm.nlin == 2 ? launch_w2d_adam_flat(wa, static_cast<cudaStream_t>(stream)) : launch_wire_adam_flat(wa, static_cast<cudaStream_t>(stream));
     return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_flat_kernel");
   }
   AdamArgs a; fill_adam(p, a);
@@ -1001,7 +1130,7 @@ extern "C" int inr_adam_step_peers(const inr_plan* p, float* params, const float
     WireAdamArgs wa; wire_adam_fill(p, wa);
     wa.params = params; wa.mom = m; wa.var = v; wa.wpack = static_cast<uint8_t*>(wpack); wa.gpart = peer_grads[rank];
     wa.hyper = hyper_dev; wa.step = step_dev; wa.do_adam = 1; wa.peer = P;
-    cudaError_t we = launch_wire_adam_flat(wa, static_cast<cudaStream_t>(stream));
+    cudaError_t we = p->wm.nlin == 2 ? launch_w2d_adam_flat(wa, static_cast<cudaStream_t>(stream)) : launch_wire_adam_flat(wa, static_cast<cudaStream_t>(stream));
     return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_flat_kernel(peers)");
   }
   AdamArgs a; fill_adam(p, a);
@@ -1078,7 +1207,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
     wa.hyper = hyper_dev; wa.step = step_dev; wa.loss_out = loss_out_dev;
     wa.row_offset = row_cursor_dev; wa.row_advance = static_cast<int>(bs);
     wa.do_adam = no_adam ? 0 : 1; wa.scal_has_bc = no_adam ? 0 : 1; wa.grads = grads_only;
-    cudaError_t we = launch_wire_adam(wa, st);
+    cudaError_t we = p->wm.nlin == 2 ? launch_w2d_adam(wa, st) : launch_wire_adam(wa, st);
     if (ev) cudaEventRecord(ev[4], st);
     return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_kernel");
   }

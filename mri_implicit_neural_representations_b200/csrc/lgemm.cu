@@ -14,6 +14,9 @@
 //                   (reference src/models/mfn.py:34-38,57-58; BoundedLinear :281-286 as a row mask on the linear term).
 //                   Two segments (filter GEMM, linear GEMM), nt = 128; stage 0 has the filter segment only.
 //   LG_MFN_DGRAD  : dz_{i-1} = dh_i W_i (+ head gradient), then dh_{i-1} = dz g, dp_{i-1} = dz h cos(p).
+//   LG_W2D_FWD / LG_W2D_DGRAD : WIRE2D layers (reference wire2d.py:38-60), two linears per layer: forward item = 64
+//                   features x (a, b, c, d) columns, y = exp(j w (a+jb)) exp(-s^2 (a^2+b^2+c^2+d^2)); dgrad item = 128 input
+//                   features x (re, im), the epilogue turns dL/dh into the four pre-activation gradients of the layer below.
 //   LG_GABOR_E    : Gabor envelope E = exp(-gamma/2 (|x|^2 + |mu|^2 - 2 x mu^T)) (reference mfn.py:117-131) as an fp16
 //                   image; MFN_FWD then stores f = sin(p) E and cos(p) E in place of sin / cos, which makes the
 //                   backward epilogue of a Gabor stage identical to the Fourier one plus the q = dL/df * f image.
@@ -84,6 +87,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     for (int j = tid; j < width; j += kLgThreads) {
       s_ba[j] = a.bias ? a.bias[j] : 0.f;
       s_bb[j] = a.phi[j];
+    }
+  } else if (MODE == LG_W2D_FWD) {
+    for (int j = tid; j < kW2dMaxP; j += kLgThreads) {
+      const bool ok = j < a.c_valid;
+      s_ba[j] = ok ? a.bias[2 * j] : 0.f;          s_bb[j] = ok ? a.bias[2 * j + 1] : 0.f;
+      s_ba[kW2dMaxP + j] = ok ? a.bias2[2 * j] : 0.f; s_bb[kW2dMaxP + j] = ok ? a.bias2[2 * j + 1] : 0.f;
     }
   } else if (MODE == LG_GABOR_E) {
     const int width = a.n_nblocks * a.nt;
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     const int q = warp & 3, sub = (warp - 4) >> 2, row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
     const float w = a.omega, s2 = a.sigma * a.sigma;
-    const bool dgrad = MODE == LG_WIRE_DGRAD || MODE == LG_MFN_DGRAD;
+    const bool dgrad = MODE == LG_WIRE_DGRAD || MODE == LG_MFN_DGRAD || MODE == LG_W2D_DGRAD;
     // per-layer power-of-two gradient scales (WIRE's gradient norm grows ~10x per layer towards the input; one global
     // loss scale would saturate the fp16 images of the lower layers)
     float ratio = 1.f, amax = 0.f, s_dst = 1.f;
@@ -191,7 +200,85 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
       const uint32_t ab = n_done & 1, use = n_done >> 1;
       const uint32_t acc = tmem + t_lane + ab * 256;
-      if (MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) {
+      if (MODE == LG_W2D_FWD) {
+        // ---------------- WIRE2D forward: 64 features per item, accumulator columns [a | b | c | d] (64 each)
+        const int P2 = a.p2, pg = P2 >> 3;
+        const size_t himg = static_cast<size_t>(tile) * (static_cast<size_t>(kTileM) * 2 * P2 * 2) + row * 16;
+        const size_t zimg = static_cast<size_t>(tile) * (static_cast<size_t>(kTileM) * 4 * P2 * 2) + row * 16;
+        mbar_wait(&acc_full[ab], use & 1);
+        tc_fence_after();
+        if (tid == 128) LG_TRACE(3 + 3 * n_done);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 16 * sub + 8 * i;               // feature inside the block
+          const int f0 = kW2dFwdFeat * nb + c0;          // complex feature index (multiple of 8)
+          float va[8], vb[8], vc[8], vd[8], yr[8], yi[8];
+          tmem_ld8(acc + c0, va); tmem_ld8(acc + 64 + c0, vb); tmem_ld8(acc + 128 + c0, vc); tmem_ld8(acc + 192 + c0, vd);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float za = va[e] + s_ba[f0 + e], zb = vb[e] + s_bb[f0 + e];
+            const float zc = vc[e] + s_ba[kW2dMaxP + f0 + e], zd = vd[e] + s_bb[kW2dMaxP + f0 + e];
+            va[e] = za; vb[e] = zb; vc[e] = zc; vd[e] = zd;
+            const float mag = __expf(-w * zb - s2 * (za * za + zb * zb + zc * zc + zd * zd));
+            const float ang = w * za;
+            const bool live = (f0 + e) < a.c_valid;
+            yr[e] = live ? mag * fast_cos(ang) : 0.f;
+            yi[e] = live ? mag * fast_sin(ang) : 0.f;
+          }
+          uint4 rh, rl, ih, il;
+          split_h2(yr[0], yr[1], rh.x, rl.x); split_h2(yr[2], yr[3], rh.y, rl.y);
+          split_h2(yr[4], yr[5], rh.z, rl.z); split_h2(yr[6], yr[7], rh.w, rl.w);
+          split_h2(yi[0], yi[1], ih.x, il.x); split_h2(yi[2], yi[3], ih.y, il.y);
+          split_h2(yi[4], yi[5], ih.z, il.z); split_h2(yi[6], yi[7], ih.w, il.w);
+          const size_t off_r = himg + static_cast<size_t>(f0 >> 3) * 2048, off_i = himg + static_cast<size_t>(pg + (f0 >> 3)) * 2048;
+          st_global_v4(a.out_hi + off_r, rh); st_global_v4(a.out_hi + off_i, ih);
+          st_global_v4(a.out_lo + off_r, rl); st_global_v4(a.out_lo + off_i, il);
+          if (a.train) {
+            const size_t z0 = zimg + static_cast<size_t>(f0 >> 3) * 2048, zs = static_cast<size_t>(pg) * 2048;
+            st_global_v4(a.out_ab + z0, pack8(va)); st_global_v4(a.out_ab + z0 + zs, pack8(vb));
+            st_global_v4(a.out_ab + z0 + 2 * zs, pack8(vc)); st_global_v4(a.out_ab + z0 + 3 * zs, pack8(vd));
+          }
+        }
+      } else if (MODE == LG_W2D_DGRAD) {
+        // ---------------- WIRE2D dgrad: 128 input features per item, accumulator columns [dL/dRe h | dL/dIm h] (128 each)
+        const int P2 = a.p2, pg = P2 >> 3;
+        const size_t himg = static_cast<size_t>(tile) * (static_cast<size_t>(kTileM) * 2 * P2 * 2) + row * 16;
+        const size_t zimg = static_cast<size_t>(tile) * (static_cast<size_t>(kTileM) * 4 * P2 * 2) + row * 16;
+        const size_t zs = static_cast<size_t>(pg) * 2048;
+        mbar_wait(&acc_full[ab], use & 1);
+        tc_fence_after();
+        if (tid == 128) LG_TRACE(3 + 3 * n_done);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 32 * sub + 8 * i;
+          const int f0 = kW2dBwdFeat * nb + c0;
+          const size_t z0 = zimg + static_cast<size_t>(f0 >> 3) * 2048;
+          const uint4 yr4 = ld_global_nc_v4(a.in_y + himg + static_cast<size_t>(f0 >> 3) * 2048);
+          const uint4 yi4 = ld_global_nc_v4(a.in_y + himg + static_cast<size_t>(pg + (f0 >> 3)) * 2048);
+          const uint4 a4 = ld_global_nc_v4(a.in_ab + z0), c4 = ld_global_nc_v4(a.in_ab + z0 + 2 * zs);
+          uint4 b4 = make_uint4(0u, 0u, 0u, 0u), d4 = make_uint4(0u, 0u, 0u, 0u);
+          if (!a.real_first) { b4 = ld_global_nc_v4(a.in_ab + z0 + zs); d4 = ld_global_nc_v4(a.in_ab + z0 + 3 * zs); }
+          float gr[8], gi[8];
+          tmem_ld8(acc + c0, gr);
+          tmem_ld8(acc + 128 + c0, gi);
+          tmem_ld_wait();
+          float yr[8], yi[8], za[8], zb[8], zc[8], zd[8], da[8], db[8], dc[8], dd[8];
+          unpack8(yr4, yr); unpack8(yi4, yi); unpack8(a4, za); unpack8(b4, zb); unpack8(c4, zc); unpack8(d4, zd);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float Pp = gr[e] * yr[e] + gi[e] * yi[e];
+            const float Q = gr[e] * yi[e] - gi[e] * yr[e];
+            da[e] = ratio * (-2.f * s2 * za[e] * Pp - w * Q);
+            db[e] = a.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * Pp);
+            dc[e] = ratio * (-2.f * s2 * zc[e] * Pp);
+            dd[e] = a.real_first ? 0.f : ratio * (-2.f * s2 * zd[e] * Pp);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(da[e]), fabsf(db[e])), fmaxf(fabsf(dc[e]), fabsf(dd[e]))));
+          }
+          st_global_v4(a.out_dz + z0, pack8(da)); st_global_v4(a.out_dz + z0 + zs, pack8(db));
+          st_global_v4(a.out_dz + z0 + 2 * zs, pack8(dc)); st_global_v4(a.out_dz + z0 + 3 * zs, pack8(dd));
+        }
+      } else if (MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) {
         const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16;
         // dgrad: the saved activations do not depend on the accumulator -- fetch all of them before waiting for the MMAs
         uint4 pre[3][4];
@@ -372,7 +459,7 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   const int items = a.n_tiles * a.n_nblocks;
   const int grid = items < n_sm ? items : n_sm;
   if (grid <= 0) return cudaSuccess;
-  const int expect_passes = a.mode == LG_WIRE_FWD ? 3 : 1;
+  const int expect_passes = (a.mode == LG_WIRE_FWD || a.mode == LG_W2D_FWD) ? 3 : 1;
   if (a.passes != expect_passes) return cudaErrorInvalidValue;
 #define LG_LAUNCH(P, M, K)                                                                                        \
   do {                                                                                                            \
@@ -392,6 +479,8 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
     case LG_MFN_FWD:    LG_LAUNCH(1, LG_MFN_FWD, 4); break;
     case LG_MFN_DGRAD:  LG_LAUNCH(1, LG_MFN_DGRAD, 4); break;
     case LG_GABOR_E:    LG_LAUNCH(1, LG_GABOR_E, 4); break;
+    case LG_W2D_FWD:    LG_LAUNCH(3, LG_W2D_FWD, 2); break;
+    case LG_W2D_DGRAD:  LG_LAUNCH(1, LG_W2D_DGRAD, 4); break;
     default: return cudaErrorInvalidValue;
   }
 #undef LG_LAUNCH

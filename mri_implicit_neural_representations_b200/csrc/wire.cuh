@@ -25,7 +25,14 @@ constexpr int kWStageBBytes = kWNT * kStageK * 2;     // 12288: B stage (192 row
 constexpr int kWStageABytes = kTileM * kStageK * 2;   // 8192:  A stage (128 rows x 32 K)
 constexpr int kWMaxDepth = 8;
 
-enum LGemmMode { LG_WIRE_FWD = 1, LG_WIRE_DGRAD = 2, LG_MFN_FWD = 3, LG_MFN_DGRAD = 4, LG_GABOR_E = 5 };
+// WIRE2D (reference src/models/wire2d.py): every layer has TWO linears (`linear`, `scale_orth`); the hidden width is not
+// reduced.  Complex features are padded to P2 (multiple of 64, <= 256); pre-activation / gradient images hold 4 P2 real
+// features [a | b | c | d] (a + jb = linear, c + jd = scale_orth), H images 2 P2 = [hr | hi].
+constexpr int kW2dMaxP = 256;
+constexpr int kW2dNT = 256;              // accumulator columns per item: forward 64 features x (a,b,c,d); dgrad 128 features x (re,im)
+constexpr int kW2dFwdFeat = 64, kW2dBwdFeat = 128;
+
+enum LGemmMode { LG_WIRE_FWD = 1, LG_WIRE_DGRAD = 2, LG_MFN_FWD = 3, LG_MFN_DGRAD = 4, LG_GABOR_E = 5, LG_W2D_FWD = 6, LG_W2D_DGRAD = 7 };
 
 // One GEMM segment of a work item: acc[:, acc_col : acc_col + nt] = A[128 x K] * B_block[nt x K]^T
 struct LGemmSeg {
@@ -48,6 +55,8 @@ struct LGemmArgs {
   const float* phi;         // MFN_FWD: filter bias phi_i [width]
   float omega, sigma;       // WIRE: Gabor constants of the layer whose activation / derivative is evaluated
   int c_valid;              // WIRE: real complex width (181)
+  int p2;                   // WIRE2D: padded complex width P2
+  const float* bias2;       // WIRE2D_FWD: complex bias of scale_orth, interleaved (re, im)
   int train;                // FWD: also store what backward needs
   int real_first;           // WIRE_DGRAD: target layer is the real first layer;  MFN: target stage is stage 0 (z_0 = sin p_0)
   uint8_t* out_hi;          // WIRE_FWD: H_hi / H_lo of the next layer, AB of this layer.  MFN_FWD: z_i image
@@ -84,6 +93,9 @@ struct WireModel {
   int depth;                // hidden complex layers
   int c;                    // complex width (181)
   int in_f, out_f;          // 3, 2
+  int nlin;                 // 1: WIRE, 2: WIRE2D (second linear `scale_orth` per layer)
+  int P;                    // padded complex width: 192 (WIRE) or a multiple of 64 up to 256 (WIRE2D)
+  int v_off[kWMaxDepth + 1], vb_off[kWMaxDepth + 1];          // WIRE2D: scale_orth weight / bias offsets, layers 0..depth
   float omega_first, omega_hidden, sigma;
   // float offsets in the flat parameter buffer (reference state_dict order)
   int omega_off[kWMaxDepth + 1], scale_off[kWMaxDepth + 1];   // frozen scalars

@@ -43,7 +43,9 @@ class Plan:
         enc = encoder or {"embedding": "none"}
         if model not in L.MODEL:
             raise NotImplementedError(model)                      # src/train.py:69-70
-        if model in ("WIRE", "Fourier", "MultiscaleFourier", "BoundedFourier", "Gabor", "KGabor"):
+        if model == "WIRE2D" and net.get("last_tanh", False):
+            raise L.InrError("WIRE2D with last_tanh (complex tanh tail, wire2d.py:106-107) is not built")
+        if model in ("WIRE", "WIRE2D", "Fourier", "MultiscaleFourier", "BoundedFourier", "Gabor", "KGabor"):
             last = "linear"                                        # WIRE: real part of the final complex linear; MFN: plain heads
         elif model == "FFN":
             last = "sigmoid"                                       # src/models/networks.py:63
@@ -59,7 +61,7 @@ class Plan:
         self.desc = L.ModelDesc(L.MODEL[model], int(net["network_input_size"]), int(net["network_output_size"]),
                                 int(net["network_depth"]), int(net["network_width"]), L.LAST[last],
                                 L.ENC[kind], int(enc.get("embedding_size", 0)) if kind == "gauss" else 0,
-                                float(net.get("first_omega_0", 30.0)) if model == "WIRE" else 30.0,
+                                float(net.get("first_omega_0", 30.0)) if model in ("WIRE", "WIRE2D") else 30.0,
                                 float(net.get("hidden_omega_0", 30.0)), float(net.get("scale", 10.0)))
         self.out_cols = int(net["network_output_size"])
         if model in ("MultiscaleFourier", "BoundedFourier"):
@@ -260,7 +262,7 @@ class ChainEngine:
                                        _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _ptr(coords),
                                        _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), bs, _ptr(self.workspace), _ptr(out),
                                        reps, ms, _stream()), "inr_profile_step")
-        if self.plan.model == "WIRE":
+        if self.plan.model in ("WIRE", "WIRE2D"):
             return {"forward": ms[0], "backward": ms[2], "optimiser": ms[3], "forward_layer_gemms": ms[4]}
         if self.plan.model not in ("SIREN", "FFN"):      # MFN family: forward (+ TV) | backward (dgrad + wgrad) | optimiser
             return {"forward": ms[0], "backward": ms[2], "optimiser": ms[3]}

@@ -59,6 +59,27 @@ def wire_tensors(net: dict):
     return out
 
 
+def wire2d_tensors(net: dict):
+    """[(name, tensor)] in reference state_dict order for WIRE2D (reference src/models/wire2d.py:62-104): per layer the
+    frozen omega_0 / scale_0, `linear` and `scale_orth` (real on the first layer, complex after; width NOT reduced), a
+    complex final linear.  Same nn.Linear calls in the same RNG order."""
+    depth, hid = net["network_depth"], net["network_width"]
+    fin, fout = net["network_input_size"], net["network_output_size"]
+    out = []
+    specs = [(fin, hid, torch.float, net["first_omega_0"])] + [(hid, hid, torch.cfloat, net["hidden_omega_0"])] * depth
+    for i, (a, b, dt, om) in enumerate(specs):
+        out.append((f"net.{i}.omega_0", om * torch.ones(1)))
+        out.append((f"net.{i}.scale_0", net["scale"] * torch.ones(1)))
+        for name in ("linear", "scale_orth"):
+            lin = nn.Linear(a, b, dtype=dt)
+            out.append((f"net.{i}.{name}.weight", lin.weight.detach().clone()))
+            out.append((f"net.{i}.{name}.bias", lin.bias.detach().clone()))
+    lin = nn.Linear(hid, fout, dtype=torch.cfloat)
+    out.append((f"net.{depth + 1}.weight", lin.weight.detach().clone()))
+    out.append((f"net.{depth + 1}.bias", lin.bias.detach().clone()))
+    return out
+
+
 def mfn_tensors(model: str, net: dict, input_scale: float = 2.0, weight_scale: float = 1.0, alpha: float = 6.0,
                 beta: float = 1.0):
     """[(name, tensor)] in reference state_dict order for FourierNet ('Fourier'), GaborNet / KGaborNet ('Gabor',

@@ -150,8 +150,8 @@ class FusedChain(nn.Module):
         eng = self._engines.get(key)
         if eng is None or eng.max_batch < max_batch:
             plan = Plan(self.MODEL, self.net, encoder if key == "gauss" else {"embedding": "none"})
-            if self.MODEL == "WIRE":
-                assert key == "none", "WIRE takes raw coordinates"
+            if self.MODEL in ("WIRE", "WIRE2D"):
+                assert key == "none", "WIRE / WIRE2D take raw coordinates"
             eng = ChainEngine(plan, max_batch=max(max_batch, 128), device=self._flat.device,
                               shared={"params": self._flat, **st})
             eng.packed_epoch = -1
@@ -265,6 +265,41 @@ class WIRE(FusedChain):
         res = nn.Module.load_state_dict(self, renamed, strict=strict)
         self._param_epoch += 1
         return res
+
+
+class _Gabor2DHolder(nn.Module):
+    """One ComplexGaborLayer2D's parameters (wire2d.py:35-46): omega_0, scale_0 (frozen), linear.*, scale_orth.*."""
+
+    def __init__(self, omega, scale, weight, bias, oweight, obias):
+        super().__init__()
+        self.omega_0 = nn.Parameter(omega, requires_grad=False)
+        self.scale_0 = nn.Parameter(scale, requires_grad=False)
+        self.linear = _Leaf(weight, bias)
+        self.scale_orth = _Leaf(oweight, obias)
+
+
+class WIRE2D(WIRE):
+    """reference src/models/wire2d.py:63-118 -- keys net.<i>.{omega_0,scale_0,linear.*,scale_orth.*}, net.<depth+1>.*;
+    hidden width = network_width (not reduced).  forward(coords [bs,3]) returns the real part of the final linear."""
+    MODEL = "WIRE2D"
+
+    def _init_tensors(self):
+        return pinit.wire2d_tensors(self.net)
+
+    def _build_tree(self):
+        v = self._views(self._flat)
+        depth = self.net["network_depth"]
+        mods = [_Gabor2DHolder(*v[6 * i:6 * i + 6]) for i in range(depth + 1)]
+        mods.append(_Leaf(v[6 * (depth + 1)], v[6 * (depth + 1) + 1]))
+        self.net_modules = mods
+        self.net_tree = nn.Sequential(*mods)
+
+    def _params_in_order(self):
+        out = []
+        for m in self.net_modules[:-1]:
+            out += [m.omega_0, m.scale_0, m.linear.weight, m.linear.bias, m.scale_orth.weight, m.scale_orth.bias]
+        out += [self.net_modules[-1].weight, self.net_modules[-1].bias]
+        return out
 
 
 class FourierNet(FusedChain):

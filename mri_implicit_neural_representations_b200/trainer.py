@@ -89,7 +89,7 @@ class FusedTrainer:
         src/train.py:173-174 added on every batch (the reference only reaches it with an undersampling mask)."""
         if loss not in FUSABLE_LOSSES:
             raise L.InrError(f"loss '{loss}' is not fused; use the unfused model(x)/backward path")
-        wire = getattr(model, "MODEL", None) == "WIRE"
+        wire = getattr(model, "MODEL", None) in ("WIRE", "WIRE2D")
         if wire and encoder.embedding_type != "none":
             raise L.InrError("WIRE is fitted on raw coordinates (encoder.embedding: none)")
         if not wire and encoder.embedding_type not in ("gauss",):

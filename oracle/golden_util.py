@@ -18,6 +18,8 @@ ENC_NONE = {"embedding": "none", "scale": 4, "embedding_size": 256, "coordinates
 NET_256 = {"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256}
 NET_WIRE = {"network_input_size": 3, "network_output_size": 2, "network_depth": 4, "network_width": 256,
             "first_omega_0": 30, "hidden_omega_0": 30, "scale": 15}
+NET_W2D = {"network_input_size": 3, "network_output_size": 2, "network_depth": 3, "network_width": 256,
+           "first_omega_0": 30, "hidden_omega_0": 30, "scale": 15}
 NET_MFN = {"network_input_size": 512, "network_output_size": 2, "network_depth": 8, "network_width": 512}
 HDR_OPTS = {"hdr_eps": 1e-2, "hdr_ff_sigma": 1.0, "hdr_ff_factor": 0.5}
 
@@ -32,6 +34,7 @@ CASES = {
     "wire_l2":    ("WIRE", NET_WIRE, ENC_NONE, "L2", None, 500, 17),
     "fourier_l2": ("Fourier", NET_MFN, ENC_GAUSS, "L2", None, 300, 18),
     "gabor_tanh": ("Gabor", NET_MFN, ENC_GAUSS, "tanh", None, 300, 19),
+    "wire2d_l2":  ("WIRE2D", NET_W2D, ENC_NONE, "L2", None, 400, 20),
 }
 N_ADAM_STEPS = 3
 LR = 5e-4

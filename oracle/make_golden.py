@@ -115,10 +115,14 @@ def run_reference_losses():
 
 
 def main():
+    """python -m oracle.make_golden [case ...]: regenerate everything, or only the named model cases."""
+    import sys
+    only = sys.argv[1:]
     os.makedirs(G.GOLDEN_DIR, exist_ok=True)
-    with open(os.path.join(G.GOLDEN_DIR, "losses.json"), "w") as f:
-        json.dump(run_reference_losses(), f, indent=1)
-    for name in G.CASES:
+    if not only:
+        with open(os.path.join(G.GOLDEN_DIR, "losses.json"), "w") as f:
+            json.dump(run_reference_losses(), f, indent=1)
+    for name in (only or G.CASES):
         d = run_reference_case(name)
         d["fp64"] = run_reference_case(name, torch.float64)
         with open(os.path.join(G.GOLDEN_DIR, name + ".json"), "w") as f:
