@@ -38,6 +38,14 @@ WORKLOADS = {
         net={"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256},
         encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
         flop_per_coord=1313792, fwd_flop_per_coord=525312),
+    # WIRE2D (reference config_wire2d_kspace.yaml: depth 8, width 256, omega 30, scale 15), k-space fit, L2
+    "wire2d_kspace_l2_bs25000": dict(
+        model="WIRE2D", loss="L2", loss_opts=None, batch=25000, image_space=False, normalization="max", undersampling=None,
+        net={"network_input_size": 3, "network_output_size": 2, "network_depth": 8, "network_width": 256,
+             "first_omega_0": 30, "hidden_omega_0": 30, "scale": 15},
+        encoder={"embedding": "none", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
+        flop_per_coord=6144 + 8 * 3145728 + 12288, fwd_flop_per_coord=8 * 2 * 256 * 256 * 8,
+        issued_fwd_flop_per_coord=8 * 3 * 2 * 512 * 1024),
     # BASELINE.json configs[2] (Gabor arm): GaborNet depth 8 width 512 on gauss-512, k-space fit, tanh loss, per-coil
     # batches (bs = H*W = 102400), undersampling grid-2*1, total-variation term on every batch
     "gabor_kspace_tanh_tv_percoil": dict(
@@ -125,6 +133,8 @@ def build_engine(wl, device, seed):
     encB = pinit.encoder_matrix(wl["encoder"])
     if wl["model"] == "WIRE":
         tensors = [t for _, t in pinit.wire_tensors(wl["net"])]
+    elif wl["model"] == "WIRE2D":
+        tensors = [t for _, t in pinit.wire2d_tensors(wl["net"])]
     elif wl["model"] in ("Gabor", "KGabor", "Fourier"):
         tensors = [t for _, t in pinit.mfn_tensors(wl["model"], wl["net"])]
     else:
@@ -386,7 +396,7 @@ def main():
     eng, tensors, encB = build_engine(wl, device, seed=1234 if dp else 1234 + rank)
     coords, gt, mask = resident_arrays(wl, device, 1234 + 100 * rank, min_bytes=200 << 20)
     n_rows = coords.shape[0]
-    wire = wl["model"] == "WIRE"
+    wire = wl["model"] in ("WIRE", "WIRE2D")
     mfn = wl["model"] in ("Gabor", "KGabor", "Fourier")
     steps_per_pass = n_rows // bs
     out_buf = torch.empty(bs, 2, device=device) if (wl["loss_opts"] or {}).get("tv") else None   # the TV term reads the output
@@ -512,7 +522,7 @@ def main():
     reset_cursor()
     prof = eng.profile_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], reps=100 if bs <= 25000 else 20,
                             out=out_buf)
-    n_launch = 14 if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
+    n_launch = (2 * wl["net"]["network_depth"] + 6) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
     kern_ms = prof["forward_layer_gemms"] / wl["net"]["network_depth"] if wire else prof["forward"]
     kern_flop = (wl["fwd_flop_per_coord"] / wl["net"]["network_depth"] if wire else wl["fwd_flop_per_coord"]) * bs
     fwd_tflops = kern_flop / (kern_ms * 1e-3) / 1e12
@@ -589,8 +599,9 @@ def main():
                                     if dp else f"independent fit per GPU x{world}, no collective")),
                    "launch": graph_mode,
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
-                   "step": ("14 kernels: first layer, 4 layer GEMMs (3-pass split fp16 + complex Gabor epilogue), final layer + HDR loss, "
-                            "scalars, final-layer backward, 4 dgrad layer GEMMs, split-K wgrad, complex Adam + repack") if wire else
+                   "step": (f"{n_launch} kernels: first layer, {wl['net']['network_depth']} layer GEMMs (3-pass split fp16 + complex Gabor epilogue), "
+                            f"final layer + loss, scalars, final-layer backward, {wl['net']['network_depth']} dgrad layer GEMMs, split-K wgrad, "
+                            "complex Adam + repack") if wire else
                            (f"{n_launch} kernels: encoding, |mu|^2, 9 x (envelope GEMM + stage GEMM), head + loss, TV, scalars, top stage, "
                             "8 dgrad stage GEMMs, split-K wgrad, d mu / d gamma, Adam + repack") if mfn else
                            "4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",
@@ -603,10 +614,10 @@ def main():
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"],
                      # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture
-                     "traffic": (44.3e6 if wire and bs == 25000 else None),
+                     "traffic": (44.3e6 if wl["model"] == "WIRE" and bs == 25000 else None),
                      "traffic_source": ("profiles/r01_ncu_lgemm_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, cold L2)"
-                                        if wire and bs == 25000 else None),
-                     "kernel": ("lgemm_kernel (WIRE forward layer GEMM + Gabor epilogue; one of 4 launches/step)" if wire else
+                                        if wl["model"] == "WIRE" and bs == 25000 else None),
+                     "kernel": (f"lgemm_kernel ({wl['model']} forward layer GEMM + Gabor epilogue; one of {wl['net']['network_depth']} launches/step)" if wire else
                                 ("forward phase (encoding + 18 lgemm launches + head/loss + TV)" if mfn else "chain_fwd_kernel<SIN>")),
                      "kernel_ms": kern_ms,
                      "issued_tflops": (wl["issued_fwd_flop_per_coord"] / wl["net"]["network_depth"] * bs / (kern_ms * 1e-3) / 1e12) if wire else None,
