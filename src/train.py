@@ -52,6 +52,9 @@ def build_model(config):
         return GaborNet(config["net"])
     if name == "KGabor":
         return KGaborNet(config["net"])
+    if name == "WIRE2D" and config.get("_allow_wire2d", False):      # only the HP-search trainer builds it (hp_model_training.py:55-56)
+        from models.wire2d import WIRE2D
+        return WIRE2D(config["net"])
     raise NotImplementedError(name)            # reference :69-70
 
 
@@ -90,7 +93,20 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
     if cfg_path and os.path.exists(cfg_path):
         shutil.copy(cfg_path, os.path.join(out_root, "outputs", model_name, "config.yaml"))
 
+    return fit(config, dataset, data_loader, val_loader, max_epoch, device, train_writer=train_writer,
+               checkpoint_directory=checkpoint_directory, verbose=verbose)["history"]
+
+
+def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_writer=None, checkpoint_directory=None,
+        verbose=True, model_seed=None):
+    """The training loop shared by training_script (reference src/train.py:52-252) and the HP-search trainer
+    (reference src/parameter_search/hp_model_training.py:13-228): encoder, model, optimiser, loss, regulariser, the
+    per-epoch LambdaLR decay, grid-order batches, validation every val_epoch.  Returns {'history': [(epoch, psnr,
+    ssim)], 'best_psnr', 'best_psnr_ep', 'best_ssim', 'best_ssim_ep', 'model', 'encoder', 'optim'}."""
+    in_image_space = config["transform"]
     encoder = Positional_Encoder(config["encoder"], device=device)
+    if model_seed is not None:
+        torch.manual_seed(model_seed)               # hp_model_training.py:50 seeds between encoder and model
     model = build_model(config)
     model.to(device=device)
     model.train()
@@ -138,6 +154,7 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
 
     scheduler = LambdaLR(optim, lambda x: 0.2 ** min(x / max_epoch, 1))
     history = []
+    best = {"best_psnr": -999999, "best_psnr_ep": 0, "best_ssim": -1, "best_ssim_ep": 0}
     log_iter = config["log_iter"]
     for epoch in range(max_epoch):
         model.train()
@@ -146,7 +163,7 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
                 loss_dev = trainer.step()
                 if it % log_iter == log_iter - 1:              # the only host sync of the training loop
                     train_loss = float(loss_dev)
-                    train_writer.log_train(train_loss, epoch * trainer.steps_per_epoch + it + 1)
+                    (train_writer.log_train if train_writer else (lambda *a, **k: None))(train_loss, epoch * trainer.steps_per_epoch + it + 1)
                     if verbose:
                         print("[Epoch: {}/{}, Iteration: {}] Train loss: {:.4g}".format(epoch + 1, max_epoch, it, train_loss))
         else:
@@ -176,7 +193,7 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
                 if regularization is not None:
                     optim.reg_l1, optim.reg_l2 = l1, l2
                 if it % log_iter == log_iter - 1:
-                    train_writer.log_train(float(train_loss), epoch * len(data_loader) + it + 1)
+                    (train_writer.log_train if train_writer else (lambda *a, **k: None))(float(train_loss), epoch * len(data_loader) + it + 1)
         if (epoch + 1) % config["val_epoch"] == 0:
             model.eval()
             with torch.no_grad():
@@ -188,14 +205,18 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
                 test_psnr = float(M.psnr(gt_image, recon))
                 test_ssim = float(M.ssim(gt_image, recon))
             history.append((epoch + 1, test_psnr, test_ssim))
-            train_writer.log_test(0.0, test_psnr, test_ssim, epoch + 1)
+            if test_psnr > best["best_psnr"]:
+                best["best_psnr"], best["best_psnr_ep"] = test_psnr, epoch
+            if test_ssim > best["best_ssim"]:
+                best["best_ssim"], best["best_ssim_ep"] = test_ssim, epoch
+            (train_writer.log_test if train_writer else (lambda *a, **k: None))(0.0, test_psnr, test_ssim, epoch + 1)
             if verbose:
                 print("[Validation Epoch: {}/{}] Test psnr: {:.4g} | Test ssim: {:.4g}".format(epoch + 1, max_epoch, test_psnr, test_ssim))
-        if (epoch + 1) % config["image_save_epoch"] == 0:
+        if checkpoint_directory and (epoch + 1) % config["image_save_epoch"] == 0:
             torch.save({"net": model.state_dict(), "enc": encoder.B, "opt": optim.state_dict()},
                        os.path.join(checkpoint_directory, "model_%06d.pt" % (epoch + 1)))
         scheduler.step()
-    return history
+    return {"history": history, **best, "model": model, "encoder": encoder, "optim": optim}
 
 
 if __name__ == "__main__":

@@ -97,3 +97,29 @@ def test_train_script_has_reference_cli(src_path):
     import inspect
     params = list(inspect.signature(train.training_script).parameters)
     assert params[:6] == ["config", "dataset", "data_loader", "val_loader", "sample", "slice_no"]
+
+
+def test_hp_search_space_expansion_matches_reference_semantics(src_path):
+    """Grid: itertools.product over the keys' insertion order of {'key': {'values': [...]}}; random: the reference's
+    log / int / float / item modes with the same `random` calls; dotted keys update one nesting level
+    (reference src/parameter_search/find_best_config.py:15-26,137-152,186-213)."""
+    import random
+    pytest.importorskip("yaml")
+    try:
+        from parameter_search import find_best_config as F
+    except Exception as e:          # importing the trainer needs the built library (no CPU fallback)
+        pytest.skip(f"engine library not importable here: {e}")
+    grid = F.grid_configs({"lr": {"values": [1e-4, 1e-3]}, "net.network_width": {"values": [128, 256, 512]}})
+    assert len(grid) == 6 and grid[0] == {"lr": 1e-4, "net.network_width": 128} and grid[1]["net.network_width"] == 256
+    cfg = F.update_model_config({"lr": 0.1, "net": {"network_width": 64, "network_depth": 4}}, grid[5])
+    assert cfg == {"lr": 1e-3, "net": {"network_width": 512, "network_depth": 4}}
+    random.seed(7)
+    a = F.random_search_spaces_to_config({"lr": ([1e-4, 1e-1], "log"), "w": ([100, 400], "int"), "f": ([0.0, 1.0], "float"),
+                                          "loss": (["L2", "tanh"], "item"), "bad": ([1, 2], "nope"), "neg": ([-1, 1], "log")})
+    random.seed(7)
+    from math import log10
+    exp_lr = 10 ** random.uniform(log10(1e-4), log10(1e-1))
+    exp_w = random.randint(100, 400)
+    exp_f = random.uniform(0.0, 1.0)
+    exp_loss = random.choice(["L2", "tanh"])
+    assert a == {"lr": exp_lr, "w": exp_w, "f": exp_f, "loss": exp_loss}

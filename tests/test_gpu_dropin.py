@@ -175,3 +175,25 @@ def test_config3_per_coil_tv_fused_equals_autograd_face(src_path, tmp_path, mode
     (_, p1, s1), (_, p0, s0) = hist[True][-1], hist[False][-1]
     assert abs(p1 - p0) <= 0.1, (p1, p0)
     assert abs(s1 - s0) <= 0.002, (s1, s0)
+
+
+def test_hp_grid_search_end_to_end(src_path, tmp_path):
+    """reference src/parameter_search/find_best_config.py:grid_search on a tiny synthetic slice: every candidate is
+    fitted by the engine, the best PSNR / SSIM configurations are the candidates with the best reported scores, and an
+    absurd learning rate loses against a sane one."""
+    from parameter_search.find_best_config import grid_search
+    cfg = _config(2, 1920)
+    cfg.update(data_root="data", set="train", sample=0, slice=0, full_norm=False, normalization="max", val_epoch=1,
+               _shape=(3, 32, 40), image_directory=str(tmp_path), output_directory=str(tmp_path))
+    space = {"lr": {"values": [5e-4, 1e-9]}, "net.network_depth": {"values": [3, 4]}}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = grid_search("SIREN", cfg, torch.device("cuda"), epochs=2, grid_search_spaces=space)
+    assert len(res["results"]) == 4
+    scores = [st["best_psnr"] for _, st in res["results"]]
+    hp_best = res["results"][max(range(4), key=lambda i: scores[i])][0]
+    assert res["PSNR"]["config"]["lr"] == hp_best["lr"] == 5e-4
+    assert res["PSNR"]["config"]["net"]["network_depth"] == hp_best["net.network_depth"]
+    assert os.path.exists(os.path.join(tmp_path, "hp_search_config_4.yaml"))
+    # the two lr = 1e-9 candidates did not learn anything
+    assert max(scores[0], scores[1]) > max(scores[2], scores[3])
