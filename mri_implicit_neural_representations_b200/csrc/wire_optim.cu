@@ -91,30 +91,43 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
     // ---- gradient gather (fixed split order); every layer's block carries that layer's own dZ scale
     float inv_scale = s_c[2];
     if (a.scal && layer < L) inv_scale = 1.f / a.scal[SC_LAYER_SCALE + layer];
-    float g = 0.f;
-    for (int s = 0; s < a.n_split; ++s) {
-      const float* G = a.gpart + static_cast<size_t>(s) * M.gd_floats;
-      if (layer == 0) {
-        const float* D0 = G + M.gd_first;
-        if (kind == 0) { const int oo = idx / M.in_f, cc = idx % M.in_f; g += D0[oo * 16 + cc] + D0[oo * 16 + 4 + cc]; }
-        else g += D0[idx * 16 + 3];
-      } else if (layer < L) {
-        const float* D = G + M.gd_hidden[layer];
-        if (kind == 0) {
-          g += comp == 0 ? D[o * kW2 + i] + D[(kWP + o) * kW2 + kWP + i] : D[(kWP + o) * kW2 + i] - D[o * kW2 + kWP + i];
-        } else {
-          const int oo = idx >> 1;
-          g += D[kW2 * kW2 + ((idx & 1) ? kWP + oo : oo)];
-        }
+    // the two D entries (or one) this parameter gathers are the same for every split: resolve them once, then walk the
+    // split copies four at a time so eight independent loads are in flight (summation order unchanged: split order)
+    int i0 = 0, i1 = -1;
+    float sg1 = 1.f, sg0 = 1.f;
+    if (layer == 0) {
+      if (kind == 0) { const int oo = idx / M.in_f, cc = idx % M.in_f; i0 = M.gd_first + oo * 16 + cc; i1 = i0 + 4; }
+      else i0 = M.gd_first + idx * 16 + 3;
+    } else if (layer < L) {
+      if (kind == 0) {
+        if (comp == 0) { i0 = M.gd_hidden[layer] + o * kW2 + i; i1 = M.gd_hidden[layer] + (kWP + o) * kW2 + kWP + i; }
+        else { i0 = M.gd_hidden[layer] + (kWP + o) * kW2 + i; i1 = M.gd_hidden[layer] + o * kW2 + kWP + i; sg1 = -1.f; }
       } else {
-        const float* DT = G + M.gd_final;
-        if (kind == 0) {
-          const int e = idx >> 1, oo = e / M.c, j = e % M.c;
-          g += (idx & 1) ? -DT[oo * kW2 + kWP + j] : DT[oo * kW2 + j];
-        } else {
-          g += (idx & 1) ? 0.f : DT[16 * kW2 + (idx >> 1)];
-        }
+        const int oo = idx >> 1;
+        i0 = M.gd_hidden[layer] + kW2 * kW2 + ((idx & 1) ? kWP + oo : oo);
       }
+    } else {
+      if (kind == 0) {
+        const int e = idx >> 1, oo = e / M.c, j = e % M.c;
+        if (idx & 1) { i0 = M.gd_final + oo * kW2 + kWP + j; sg0 = -1.f; } else i0 = M.gd_final + oo * kW2 + j;
+      } else {
+        if (idx & 1) sg0 = 0.f;      // Im(b) of the final layer never reaches the real output
+        i0 = M.gd_final + 16 * kW2 + (idx >> 1);
+      }
+    }
+    float g = 0.f;
+    {
+      const float* G = a.gpart;
+      const size_t st = M.gd_floats;
+      int sp = 0;
+      for (; sp + 4 <= a.n_split; sp += 4) {
+        float v[4], u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { v[q] = G[(sp + q) * st + i0]; u[q] = i1 >= 0 ? G[(sp + q) * st + i1] : 0.f; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g += sg0 * v[q] + sg1 * u[q];
+      }
+      for (; sp < a.n_split; ++sp) g += sg0 * G[sp * st + i0] + (i1 >= 0 ? sg1 * G[sp * st + i1] : 0.f);
     }
     g *= inv_scale;
     if (a.grads) a.grads[p] = g;
