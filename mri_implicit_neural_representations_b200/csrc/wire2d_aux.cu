@@ -12,6 +12,8 @@
 
 namespace inr {
 
+constexpr int kW2dAuxSplit = 4;     // CTAs per row tile in the first-layer / backward-entry kernels
+
 __device__ __forceinline__ void w2d_split8(const float (&y)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(256) w2d_first_kernel(const __grid_constant__ 
     sB[i] = i < M.c ? a.params[M.b_off[0] + i] : 0.f;
     sVB[i] = i < M.c ? a.params[M.vb_off[0] + i] : 0.f;
   }
-  if (tile == 0 && tid == 0 && a.step_counter) *a.step_counter += 1;
+  if (tile == 0 && tid == 0 && blockIdx.y == 0 && a.step_counter) *a.step_counter += 1;
   __syncthreads();
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const float w = M.omega_first, s2 = M.sigma * M.sigma;
@@ -56,8 +58,9 @@ __global__ void __launch_bounds__(256) w2d_first_kernel(const __grid_constant__ 
   uint8_t* hlo = a.ws + a.w.hlo[1] + tile * th;
   uint8_t* zimg = a.ws + a.w.ab[0] + tile * tz;
   const int pg = P / 8;
-  for (int idx = tid; idx < kTileM * pg; idx += 256) {
-    const int row = idx & (kTileM - 1), kg = idx >> 7;
+  const int kg_per = pg / kW2dAuxSplit, kg0 = blockIdx.y * kg_per;      // four CTAs per row tile (latency-bound otherwise)
+  for (int idx = tid; idx < kTileM * kg_per; idx += 256) {
+    const int row = idx & (kTileM - 1), kg = kg0 + (idx >> 7);
     const int grow = tile * kTileM + row;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     if (grow < a.bs) {
@@ -220,8 +223,9 @@ __global__ void __launch_bounds__(256) w2d_blast_kernel(const __grid_constant__ 
   const uint8_t* zimg = a.ws + a.w.ab[M.depth] + tile * tz;
   uint8_t* dzimg = a.ws + a.w.dz[M.depth] + tile * tz;
   const bool complex_layer = M.depth >= 1;
-  for (int idx = tid; idx < kTileM * pg; idx += 256) {
-    const int row = idx & (kTileM - 1), kg = idx >> 7;
+  const int kg_per = pg / kW2dAuxSplit, kg0 = blockIdx.y * kg_per;
+  for (int idx = tid; idx < kTileM * kg_per; idx += 256) {
+    const int row = idx & (kTileM - 1), kg = kg0 + (idx >> 7);
     const int grow = tile * kTileM + row;
     float dz[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
     if (grow < a.bs) {
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(256) w2d_blast_kernel(const __grid_constant__ 
 }
 
 cudaError_t launch_w2d_first(const WireAuxArgs& a, cudaStream_t st) {
-  w2d_first_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  w2d_first_kernel<<<dim3(a.w.n_tiles, kW2dAuxSplit), 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_w2d_last(const WireAuxArgs& a, cudaStream_t st) {
@@ -282,7 +286,7 @@ cudaError_t launch_w2d_last(const WireAuxArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_w2d_blast(const WireAuxArgs& a, cudaStream_t st) {
-  w2d_blast_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  w2d_blast_kernel<<<dim3(a.w.n_tiles, kW2dAuxSplit), 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -12,6 +12,8 @@
 
 namespace inr {
 
+constexpr int kWAuxSplit = 4;     // CTAs per row tile in the first-layer / backward-entry kernels
+
 __device__ __forceinline__ void wire_split8(const float (&y)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
@@ -38,15 +40,17 @@ __global__ void __launch_bounds__(256) wire_first_kernel(const __grid_constant__
   const int tile = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < kWP * 3; i += 256) sW[i] = (i / 3) < M.c ? a.params[M.w_off[0] + i] : 0.f;
   for (int i = tid; i < kWP; i += 256) sB[i] = i < M.c ? a.params[M.b_off[0] + i] : 0.f;
-  if (tile == 0 && tid == 0 && a.step_counter) *a.step_counter += 1;
+  if (tile == 0 && tid == 0 && blockIdx.y == 0 && a.step_counter) *a.step_counter += 1;
   __syncthreads();
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const float w = M.omega_first, s2 = M.sigma * M.sigma;
   uint8_t* hhi = a.ws + a.w.hhi[1] + static_cast<size_t>(tile) * kWTileBytes;
   uint8_t* hlo = a.ws + a.w.hlo[1] + static_cast<size_t>(tile) * kWTileBytes;
   uint8_t* ab = a.ws + a.w.ab[0] + static_cast<size_t>(tile) * kWTileBytes;
-  for (int idx = tid; idx < kTileM * (kWP / 8); idx += 256) {
-    const int row = idx & (kTileM - 1), kg = idx >> 7;
+  // four CTAs per row tile, each one quarter of the feature groups: these kernels are latency-bound at one CTA per tile
+  const int kg_per = (kWP / 8) / kWAuxSplit, kg0 = blockIdx.y * kg_per;
+  for (int idx = tid; idx < kTileM * kg_per; idx += 256) {
+    const int row = idx & (kTileM - 1), kg = kg0 + (idx >> 7);
     const int grow = tile * kTileM + row;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     if (grow < a.bs) {
@@ -249,8 +253,9 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
   const uint8_t* yimg = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes;
   const uint8_t* abimg = a.ws + a.w.ab[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
   uint8_t* dzimg = a.ws + a.w.dz[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
-  for (int idx = tid; idx < kTileM * (kWP / 8); idx += 256) {
-    const int row = idx & (kTileM - 1), kg = idx >> 7;
+  const int kg_per = (kWP / 8) / kWAuxSplit, kg0 = blockIdx.y * kg_per;
+  for (int idx = tid; idx < kTileM * kg_per; idx += 256) {
+    const int row = idx & (kTileM - 1), kg = kg0 + (idx >> 7);
     const int grow = tile * kTileM + row;
     float dz[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
     if (grow < a.bs) {
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
 }
 
 cudaError_t launch_wire_first(const WireAuxArgs& a, cudaStream_t st) {
-  wire_first_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  wire_first_kernel<<<dim3(a.w.n_tiles, kWAuxSplit), 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_wire_last(const WireAuxArgs& a, cudaStream_t st) {
@@ -317,7 +322,7 @@ cudaError_t launch_wire_dout_amax(const WireAuxArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_wire_blast(const WireAuxArgs& a, cudaStream_t st) {
-  wire_blast_kernel<<<a.w.n_tiles, 256, 0, st>>>(a);
+  wire_blast_kernel<<<dim3(a.w.n_tiles, kWAuxSplit), 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
