@@ -366,7 +366,8 @@ static int wire_plan_create(const inr_model_desc* d, inr_plan** out) {
   const uint32_t blk = 2u * (kW2 / kStageK) * kWStageBBytes;      // two N-blocks of one packed operand
   uint32_t wo = 0;
   for (int l = 1; l <= M.depth; ++l) {
-    M.wf_hi[l] = wo; M.wf_lo[l] = wo + kWStageBBytes; wo += 2 * blk;     // hi / lo interleaved per stage
+    M.wf_hi[l] = wo; wo += blk;
+    M.wf_lo[l] = wo; wo += blk;
     M.wd_hi[l] = wo; wo += blk;
   }
   M.wpack_bytes = wo;
@@ -458,7 +459,8 @@ static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out) {
   const uint32_t bwd_bytes = static_cast<uint32_t>(P / kW2dBwdFeat) * (4 * P / 32) * (kW2dNT * 64);   // all dgrad N-blocks, K = 4P
   uint32_t wo = 0;
   for (int l = 1; l <= M.depth; ++l) {
-    M.wf_hi[l] = wo; M.wf_lo[l] = wo + kW2dNT * 64; wo += 2 * fwd_bytes;  // hi / lo interleaved per stage
+    M.wf_hi[l] = wo; wo += fwd_bytes;
+    M.wf_lo[l] = wo; wo += fwd_bytes;
     M.wd_hi[l] = wo; wo += bwd_bytes;
   }
   M.wpack_bytes = wo;

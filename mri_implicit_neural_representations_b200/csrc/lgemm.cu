@@ -64,9 +64,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   // few steps per slot = deeper ring of smaller copies, many = fewer barrier round trips for the single producer / MMA threads
   const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 32 * KSTEPS;    // B part of a slot: KSTEPS x (nt rows x 16 K x 2 B)
   constexpr uint32_t a_bytes = (kWStageABytes / 2) * KSTEPS;
-  static_assert(PASSES == 1 || KSTEPS == 2, "3-pass operands are packed per K = 32 stage: a slot must be exactly one stage");
   const uint32_t a_lo_off = a_bytes;
   const uint32_t b_hi_off = PASSES == 3 ? 2 * a_bytes : a_bytes;
+  const uint32_t b_lo_off = b_hi_off + b_bytes;
   const uint32_t slot_bytes = PASSES == 3 ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes);
   int n_slots = kLgRingBytes / slot_bytes;
   if (n_slots > kLgMaxSlots) n_slots = kLgMaxSlots;
@@ -119,21 +119,21 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           const int n_it = S.k_stages * 2 / KSTEPS;
           const uint8_t* ah = S.a_hi + static_cast<size_t>(tile) * S.a_tile_bytes;
           const uint8_t* al = PASSES == 3 ? S.a_lo + static_cast<size_t>(tile) * S.a_tile_bytes : nullptr;
-          // 3-pass operands are packed [hi stage | lo stage] per K = 32 stage, so one bulk copy brings both parts
-          const uint32_t b_copy = PASSES == 3 ? 2 * b_bytes : b_bytes;
-          const uint8_t* bh = S.b_hi + static_cast<size_t>(nb) * n_it * b_copy;
+          const uint8_t* bh = S.b_hi + static_cast<size_t>(nb) * n_it * b_bytes;
+          const uint8_t* bl = PASSES == 3 ? S.b_lo + static_cast<size_t>(nb) * n_it * b_bytes : nullptr;
           for (int s = 0; s < n_it; ++s) {
             mbar_wait(&empty[slot], ph ^ 1);
             if (a.dbg & 2) { mbar_arrive(&full[slot]); if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; } continue; }
             mbar_arrive_expect_tx(&full[slot], slot_bytes);
             uint8_t* dst = smem + slot * slot_bytes;
             bulk_g2s(dst, ah, a_bytes, &full[slot]);
-            bulk_g2s(dst + b_hi_off, bh, b_copy, &full[slot]);
+            bulk_g2s(dst + b_hi_off, bh, b_bytes, &full[slot]);
             if (PASSES == 3) {
               bulk_g2s(dst + a_lo_off, al, a_bytes, &full[slot]);
-              al += a_bytes;
+              bulk_g2s(dst + b_lo_off, bl, b_bytes, &full[slot]);
+              al += a_bytes; bl += b_bytes;
             }
-            ah += a_bytes; bh += b_copy;
+            ah += a_bytes; bh += b_bytes;
             if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
           }
         }

@@ -17,10 +17,6 @@
 
 namespace inr {
 
-// forward operand: the same image with hi / lo parts interleaved per stage
-__device__ __forceinline__ uint32_t w2d_fwd_off(int n, int k) {
-  return static_cast<uint32_t>(k >> 5) * (2 * kW2dNT * 64) + ((k & 31) >> 3) * (kW2dNT * 16) + n * 16 + (k & 7) * 2;
-}
 // byte offset of element (n, k) inside one N-block image [K/32 stages][256 x 32]
 __device__ __forceinline__ uint32_t w2d_blk_off(int n, int k) {
   return static_cast<uint32_t>(k >> 5) * (kW2dNT * 64) + ((k & 31) >> 3) * (kW2dNT * 16) + n * 16 + (k & 7) * 2;
@@ -35,22 +31,22 @@ __device__ __forceinline__ void w2d_put(uint8_t* hi, uint8_t* lo, uint32_t off, 
 __device__ void w2d_pack_hidden(const WireModel& M, uint8_t* wpack, int l, int lin, int o, int i, int comp, float v) {
   const int P = M.P;
   uint8_t* fh = wpack + M.wf_hi[l];
-  uint8_t* fl = fh + kW2dNT * 64;              // [hi stage | lo stage] per K = 32 stage (one bulk copy per ring slot)
+  uint8_t* fl = wpack + M.wf_lo[l];
   uint8_t* dh = wpack + M.wd_hi[l];
-  const uint32_t fblk = static_cast<uint32_t>(2 * P / 32) * (2 * kW2dNT * 64);  // forward block bytes (K = 2P, hi + lo)
+  const uint32_t fblk = static_cast<uint32_t>(2 * P / 32) * (kW2dNT * 64);     // forward block bytes (K = 2P)
   const uint32_t dblk = static_cast<uint32_t>(4 * P / 32) * (kW2dNT * 64);     // dgrad block bytes (K = 4P)
   const int nbo = o / kW2dFwdFeat, no = o % kW2dFwdFeat;
   const int nbi = i / kW2dBwdFeat, ni = i % kW2dBwdFeat;
   const int ra = (2 * lin) * kW2dFwdFeat + no, rb = (2 * lin + 1) * kW2dFwdFeat + no;     // forward rows a/c and b/d
   const int kr = (2 * lin) * P + o, ki = (2 * lin + 1) * P + o;                          // dgrad K index of d(a|c)_o and d(b|d)_o
   if (comp == 0) {   // real part
-    w2d_put(fh, fl, nbo * fblk + w2d_fwd_off(ra, i), v);
-    w2d_put(fh, fl, nbo * fblk + w2d_fwd_off(rb, P + i), v);
+    w2d_put(fh, fl, nbo * fblk + w2d_blk_off(ra, i), v);
+    w2d_put(fh, fl, nbo * fblk + w2d_blk_off(rb, P + i), v);
     w2d_put(dh, nullptr, nbi * dblk + w2d_blk_off(ni, kr), v);
     w2d_put(dh, nullptr, nbi * dblk + w2d_blk_off(kW2dBwdFeat + ni, ki), v);
   } else {           // imaginary part
-    w2d_put(fh, fl, nbo * fblk + w2d_fwd_off(ra, P + i), -v);
-    w2d_put(fh, fl, nbo * fblk + w2d_fwd_off(rb, i), v);
+    w2d_put(fh, fl, nbo * fblk + w2d_blk_off(ra, P + i), -v);
+    w2d_put(fh, fl, nbo * fblk + w2d_blk_off(rb, i), v);
     w2d_put(dh, nullptr, nbi * dblk + w2d_blk_off(ni, ki), v);
     w2d_put(dh, nullptr, nbi * dblk + w2d_blk_off(kW2dBwdFeat + ni, kr), -v);
   }

@@ -21,11 +21,6 @@ __device__ __forceinline__ uint32_t wblk_off(int n, int k) {
   return static_cast<uint32_t>(s) * kWStageBBytes + (kk >> 3) * (kWNT * 16) + n * 16 + (kk & 7) * 2;
 }
 constexpr uint32_t kWBlockBytes = (kW2 / kStageK) * kWStageBBytes;   // 147456 per N-block
-// forward operand: hi and lo parts interleaved per K = 32 stage ([hi stage | lo stage], one bulk copy per ring slot)
-__device__ __forceinline__ uint32_t wfwd_off(int n, int k) {
-  const int s = k >> 5, kk = k & 31;
-  return static_cast<uint32_t>(s) * (2 * kWStageBBytes) + (kk >> 3) * (kWNT * 16) + n * 16 + (kk & 7) * 2;
-}
 
 __device__ __forceinline__ void put_hi_lo(uint8_t* hi, uint8_t* lo, uint32_t off, float v) {
   const __half h = __float2half_rn(v);
@@ -35,18 +30,18 @@ __device__ __forceinline__ void put_hi_lo(uint8_t* hi, uint8_t* lo, uint32_t off
 
 __device__ void wire_pack_hidden(const WireModel& M, uint8_t* wpack, int l, int o, int i, int comp, float v) {
   uint8_t* fh = wpack + M.wf_hi[l];
-  uint8_t* fl = fh + kWStageBBytes;
+  uint8_t* fl = wpack + M.wf_lo[l];
   uint8_t* dh = wpack + M.wd_hi[l];
   const int nbo = o / kWFeatPerBlock, no = o % kWFeatPerBlock;     // forward: N over output features
   const int nbi = i / kWFeatPerBlock, ni = i % kWFeatPerBlock;     // dgrad:   N over input features
   if (comp == 0) {   // Wr
-    put_hi_lo(fh, fl, nbo * 2 * kWBlockBytes + wfwd_off(no, i), v);
-    put_hi_lo(fh, fl, nbo * 2 * kWBlockBytes + wfwd_off(kWFeatPerBlock + no, kWP + i), v);
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(no, i), v);
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(kWFeatPerBlock + no, kWP + i), v);
     put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(ni, o), v);
     put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(kWFeatPerBlock + ni, kWP + o), v);
   } else {           // Wi
-    put_hi_lo(fh, fl, nbo * 2 * kWBlockBytes + wfwd_off(no, kWP + i), -v);
-    put_hi_lo(fh, fl, nbo * 2 * kWBlockBytes + wfwd_off(kWFeatPerBlock + no, i), v);
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(no, kWP + i), -v);
+    put_hi_lo(fh, fl, nbo * kWBlockBytes + wblk_off(kWFeatPerBlock + no, i), v);
     put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(ni, kWP + o), v);
     put_hi_lo(dh, nullptr, nbi * kWBlockBytes + wblk_off(kWFeatPerBlock + ni, o), -v);
   }
