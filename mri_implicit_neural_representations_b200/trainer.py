@@ -164,3 +164,122 @@ class FusedTrainer:
         eng.set_encoder(self.encoder.B)
         outs = [eng.forward(coords[i:i + chunk], train=False) for i in range(0, coords.shape[0], chunk)]
         return torch.cat(outs)
+
+
+class HostFedStepper:
+    """Fused steps fed from HOST batches -- the reference's DataLoader loop (src/train.py:158-192:
+    ``coords.to(device); gt.to(device); ... backward(); optim.step()``) for callers that keep their own loader.
+
+    A staging set is one pinned host block [coords | targets | row mask] and its device twin.  Per step: the block goes
+    host -> HBM as ONE copy on a copy stream (it overlaps the previous step's kernels), then one CUDA-graph launch on
+    the caller's stream runs the fused step's kernels and the D2H copy of the step's loss into pinned memory.
+    ``depth`` staging sets rotate, so the host fills and launches step i+1 while step i runs; ``loss(ticket)`` waits
+    for exactly that step and stays valid until the set is reused (``depth`` submits later).
+
+    ``step_fn(coords_dev, gt_dev, mask_dev, slot, bs)`` launches the step's kernels on the current stream and leaves
+    the loss in ``eng.loss_out`` (default: ``eng.train_step``)."""
+
+    def __init__(self, eng, loss: str, batch_size: int, masked: bool = False, loss_opts: Optional[dict] = None,
+                 depth: int = 2, step_fn=None, out: Optional[torch.Tensor] = None, use_graph: bool = True):
+        if loss not in FUSABLE_LOSSES:
+            raise L.InrError(f"loss '{loss}' is not fused; use the unfused model(x)/backward path")
+        dev = eng.params.device
+        self.eng, self.loss_name, self.loss_opts, self.bs, self.depth = eng, loss, loss_opts, int(batch_size), int(depth)
+        in_f, out_f, bs = 3, eng.plan.out_cols, self.bs
+        up = lambda n: (n + 255) // 256 * 256
+        o_gt = up(bs * in_f * 4)
+        o_mask = o_gt + up(bs * out_f * 4)
+        total = o_mask + (up(bs) if masked else 0)
+
+        def views(block):
+            c = block[:bs * in_f * 4].view(torch.float32).view(bs, in_f)
+            y = block[o_gt:o_gt + bs * out_f * 4].view(torch.float32).view(bs, out_f)
+            m = block[o_mask:o_mask + bs] if masked else None
+            return c, y, m
+        self.h_block = [torch.zeros(total, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.d_block = [torch.zeros(total, dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self._h = [views(b) for b in self.h_block]
+        self._d = [views(b) for b in self.d_block]
+        self.h_loss = [torch.zeros(1).pin_memory() for _ in range(depth)]
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._in = [torch.cuda.Event() for _ in range(depth)]     # staging set landed in HBM
+        self._done = [None] * depth                                # event recorded after the set's last step
+        self._graphs = {}
+        self._warm = set()
+        self._out = out
+        self.use_graph = use_graph
+        self.count = 0
+        self.h2d_bytes = total
+        self._step_fn = step_fn or self._default_step
+
+    def _default_step(self, c, y, m, slot, bs):
+        self.eng.train_step(self.loss_name, c, y, bs, mask=m, loss_opts=self.loss_opts, use_cursor=False, out=self._out)
+
+    def staging(self, slot: int):
+        """Pinned (coords, targets, mask) views of a staging set; valid to write once ``wait_slot(slot)`` returned."""
+        return self._h[slot]
+
+    def next_slot(self) -> int:
+        return self.count % self.depth
+
+    def wait_slot(self, slot: int):
+        ev = self._done[slot]
+        if ev is not None:
+            ev.synchronize()
+
+    def _body(self, slot, bs):
+        c, y, m = self._d[slot]
+        self._step_fn(c, y, m, slot, bs)
+        self.h_loss[slot].copy_(self.eng.loss_out.reshape(-1)[:1], non_blocking=True)
+
+    def launch(self, slot: Optional[int] = None, bs: Optional[int] = None) -> int:
+        """Run one step on the batch sitting in staging set ``slot`` (the caller has waited for the set and filled it);
+        returns the ticket (= slot)."""
+        slot = self.next_slot() if slot is None else slot
+        bs = self.bs if bs is None else int(bs)
+        main = torch.cuda.current_stream()
+        # the set's previous step has finished (wait_slot), so its device twin is free: no device-side wait needed
+        with torch.cuda.stream(self._copy_stream):
+            self.d_block[slot].copy_(self.h_block[slot], non_blocking=True)
+            self._in[slot].record(self._copy_stream)
+        main.wait_event(self._in[slot])
+        key = (slot, bs)
+        g = self._graphs.get(key) if self.use_graph else None
+        if g is not None:
+            g.replay()
+        else:
+            self._body(slot, bs)                       # eager: first uses of this (set, batch size), or graphs off
+            if self.use_graph and key in self._warm:
+                # second eager use done: calibration passes and kernel attributes are behind us -> record the graph
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):              # capture only records; nothing executes here
+                    self._body(slot, bs)
+                self._graphs[key] = g
+            self._warm.add(key)
+        ev = self._done[slot] or torch.cuda.Event()
+        ev.record(main)
+        self._done[slot] = ev
+        self.count += 1
+        return slot
+
+    def submit(self, coords: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None) -> int:
+        """Copy a host batch (CPU tensors, short last batch allowed) into the next staging set and launch its step."""
+        slot = self.next_slot()
+        bs = int(coords.shape[0])
+        if bs > self.bs:
+            raise L.InrError(f"batch of {bs} rows exceeds the stepper's batch size {self.bs}")
+        hc, hy, hm = self._h[slot]
+        if hm is not None and mask is None:
+            raise L.InrError("this stepper was built with masked=True: every batch needs its row mask")
+        self.wait_slot(slot)
+        hc[:bs].copy_(coords)
+        hy[:bs].copy_(gt)
+        if hm is not None:
+            hm[:bs].copy_(mask.reshape(-1)[:bs] if mask.dim() == 1 else mask[:, 0])
+        return self.launch(slot, bs)
+
+    def loss(self, ticket: int) -> float:
+        """Loss of the step launched with this ticket (blocks until that step's D2H copy has landed)."""
+        self.wait_slot(ticket)
+        return float(self.h_loss[ticket])
