@@ -79,3 +79,47 @@ class PeerGradExchange:
 
     def flip(self):
         self.parity ^= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Ring models, one per GPU (reference src/train_variations/train_clustering.py:57-59,
+# 173-189, 209-225): `no_models` independent networks, model i is fitted to the k-space samples whose distance to the
+# centre lies in [radii[i], radii[i+1]].  The rings share nothing while training -> ring index -> rank, no data-path
+# collective; validation assembles the slice from the per-ring predictions with ONE all-reduce(sum) of [N, out] rows.
+
+def owned_rings(no_models: int, rank: int, world: int):
+    """Rings fitted by `rank`: round-robin, so 4 rings on 4 (or 8) GPUs = one ring model per GPU, on 2 GPUs two each,
+    on one GPU all of them in turn."""
+    return [i for i in range(int(no_models)) if i % max(int(world), 1) == int(rank)]
+
+
+def ring_jitter(rng, radii, no_models: int):
+    """The training-time ring limits of one batch (reference :175-176): every ring is widened by |N(0, 0.05)| on both
+    sides, inner radius clipped at 0.  Draws for ALL rings in ring order -- every rank consumes the same stream, so
+    the limits of ring i do not depend on how the rings are spread over GPUs."""
+    out = []
+    for i in range(int(no_models)):
+        r0 = max(0.0, float(radii[i]) - abs(float(rng.normal(0, 0.05))))
+        r1 = float(radii[i + 1]) + abs(float(rng.normal(0, 0.05)))
+        out.append((r0, r1))
+    return out
+
+
+def ring_writer_masks(dist: torch.Tensor, radii, no_models: int):
+    """Validation (reference :218-232): ring i predicts the rows with radii[i] <= dist <= radii[i+1] and writes them
+    into the batch in ring order, so a row on a shared edge ends up with the OUTER ring's value.  Returns, per ring,
+    the bool mask of rows whose final value comes from that ring (disjoint; rows in no ring stay zero)."""
+    inside = [(dist >= float(radii[i])) & (dist <= float(radii[i + 1])) for i in range(int(no_models))]
+    masks = []
+    later = torch.zeros_like(inside[0])
+    for i in reversed(range(int(no_models))):
+        masks.append(inside[i] & ~later)
+        later = later | inside[i]
+    return masks[::-1]
+
+
+def combine_ring_outputs(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum over ranks of the per-rank partial reconstructions (each row non-zero on exactly one rank)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return partial

@@ -283,3 +283,65 @@ class HostFedStepper:
         """Loss of the step launched with this ticket (blocks until that step's D2H copy has landed)."""
         self.wait_slot(ticket)
         return float(self.h_loss[ticket])
+
+
+class RingTrainer:
+    """One ring model of the partitioned k-space fit (reference src/train_variations/train_clustering.py:171-189): the
+    model sees every grid-order batch but only the rows whose distance to the k-space centre lies in [r0, r1] enter the
+    loss -- exactly the reference's ``coords[ind]`` / ``gt[ind]`` gather, expressed as the fused step's row mask (masked-out
+    rows get zero gradient, the loss is the mean over the ring's rows).  Ring models are independent of each other:
+    one RingTrainer per ring, rings spread over GPUs by ``parallel.owned_rings`` with no collective while training."""
+
+    def __init__(self, model: FusedChain, encoder: Positional_Encoder, optim: FusedAdam, loss: str, batch_size: int,
+                 coords: torch.Tensor, gt: torch.Tensor, dist: torch.Tensor, loss_opts: Optional[dict] = None):
+        if loss not in ("L2", "L1", "MSLE", "tanh"):
+            # HDR: the reference hands the ENCODED batch to the loss as k-space coordinates (:184); LSL means CenterLoss
+            # there (:85-86, randperm based) -- neither is a fused-kernel target
+            raise NotImplementedError(f"ring models are fitted with L2 / L1 / MSLE / tanh on the fused path, not '{loss}'")
+        if encoder.embedding_type != "gauss":
+            raise L.InrError("the fused step needs the gauss encoder")
+        dev = model._flat.device
+        self.model, self.encoder, self.optim = model, encoder, optim
+        self.loss, self.loss_opts, self.bs = loss, dict(loss_opts or {}), int(batch_size)
+        self.coords = coords.to(dev, torch.float32).contiguous()
+        self.gt = gt.to(dev, torch.float32).contiguous()
+        self.dist = dist.to(dev, torch.float32).contiguous()
+        self._dist_host = dist.detach().to("cpu", torch.float32).numpy()
+        self.n = self.coords.shape[0]
+        self.eng = model.engine(encoder.params, self.bs)
+        self.eng.set_encoder(encoder.B)
+
+    @property
+    def steps_per_epoch(self):
+        return (self.n + self.bs - 1) // self.bs
+
+    def step(self, it: int, r0: float, r1: float):
+        """Batch `it` (grid order) restricted to the ring [r0, r1].  Returns the device scalar holding the loss, or None
+        when no row of the batch lies in the ring (reference :179: the model is not touched)."""
+        import numpy as np
+        i = it * self.bs
+        bs = min(self.bs, self.n - i)
+        dh = self._dist_host[i:i + bs]
+        if not bool(((dh >= np.float32(r0)) & (dh <= np.float32(r1))).any()):      # host copy: no device sync
+            return None
+        d = self.dist[i:i + bs]
+        mask = ((d >= r0) & (d <= r1)).to(torch.uint8)
+        self.optim.sync_hyper(self.eng)
+        self.model.engine(self.encoder.params, self.bs)
+        self.eng.train_step(self.loss, self.coords[i:i + bs], self.gt[i:i + bs], bs, mask=mask, loss_opts=self.loss_opts,
+                            use_cursor=False)
+        self.model.mark_params_updated_by_kernel(self.eng)
+        self.optim._fused_done = False
+        return self.eng.loss_out
+
+    @torch.no_grad()
+    def predict_rows(self, rows: torch.Tensor, coords: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Fused forward on the given row indices of `coords` (default: the resident training coordinates) -- the
+        validation of one ring (reference :218-232)."""
+        coords = self.coords if coords is None else coords
+        self.model.engine(self.encoder.params, self.bs)      # refreshes the fp16 operand copies after load_state_dict
+        out = torch.empty(rows.numel(), self.eng.plan.out_cols, dtype=torch.float32, device=self.coords.device)
+        for s in range(0, rows.numel(), self.bs):
+            c = coords[rows[s:s + self.bs]].contiguous()
+            out[s:s + c.shape[0]] = self.eng.forward(c, train=False)
+        return out

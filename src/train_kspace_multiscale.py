@@ -19,37 +19,16 @@ from models.networks import Positional_Encoder                               # n
 from models.mfn import MultiscaleKFourier, MultiscaleBoundedFourier           # noqa: E402
 from metrics.losses import ConsistencyLoss, HDRLoss_FF, LogSpaceLoss, MSLELoss, TanhL2Loss, tv_loss  # noqa: E402
 from data.slices import get_data_loader                                      # noqa: E402
+from clustering import partition_and_stats                                   # noqa: E402
 from utils import get_config, set_default_configs                            # noqa: E402
 from mri_implicit_neural_representations_b200 import metrics as M            # noqa: E402
 from mri_implicit_neural_representations_b200.trainer import FusedAdam       # noqa: E402
 
 
-def create_pairs(radii):
-    """reference :42-47 -- discs (0, r_i), the last one open to 5."""
-    pairs = [(0, float(r)) for r in radii[:-1]] + [(0, 5)]
-    return pairs
-
-
-def partition_radii(dist, magnitude, no_steps=40, no_models=4):
-    """Ring partition of k-space (reference src/clustering.py:19-92): `no_steps` equal-width rings, k-means of their
-    log mean magnitude into `no_models` contiguous groups; returns the outer radius of every group."""
-    import numpy as np
-    from sklearn.cluster import KMeans
-    edges = torch.linspace(0, float(dist.max()) + 1e-6, no_steps + 1)
-    means = []
-    for i in range(no_steps):
-        sel = (dist >= edges[i]) & (dist < edges[i + 1])
-        means.append(float(torch.log(magnitude[sel].mean() + 1e-12)) if sel.any() else -30.0)
-    km = KMeans(n_clusters=no_models, n_init=10, random_state=0).fit(np.array(means)[:, None])
-    labels = km.labels_
-    radii, cur = [], labels[0]
-    for i in range(1, no_steps):
-        if labels[i] != cur and len(radii) < no_models - 1:
-            radii.append(float(edges[i]))
-            cur = labels[i]
-    while len(radii) < no_models - 1:
-        radii.append(float(edges[(len(radii) + 1) * no_steps // no_models]))
-    return radii + [float(edges[-1])]
+def create_pairs(values, multiplication_factor=1):
+    """Discs (values[0], values[i+1]) of growing radius, each repeated (reference src/train_kspace_multiscale.py:42-47)."""
+    pairs = [(values[0], values[i + 1]) for i in range(len(values) - 1)]
+    return [(p[0], p[1]) for p in pairs for _ in range(multiplication_factor)]
 
 
 def training_multiscale(config, dataset, data_loader, val_loader, output_path=".", verbose=True):
@@ -58,15 +37,16 @@ def training_multiscale(config, dataset, data_loader, val_loader, output_path=".
     device = torch.device("cuda")
     max_epoch = config["max_epoch"]
     C, H, W, S = dataset.img_shape
-    train_ds = data_loader.ds
-    mag = train_ds.image.pow(2).sum(-1).sqrt()
-    radii = partition_radii(train_ds.dist_to_center, mag, config["partition"]["no_steps"], config["partition"]["no_models"])
-    pairs = create_pairs(radii)
+    # ring partition of the FULL slice (reference :72-86): k-means over per-ring max log|k| -> partition radii
+    part_config = config["partition"]
+    _, part_radii = partition_and_stats(dataset=dataset, no_steps=part_config["no_steps"], no_parts=part_config["no_models"],
+                                        stat="max", show=False)
+    pairs = [(float(a), float(b)) for a, b in create_pairs(part_radii, 1)]
     encoder = Positional_Encoder(config["encoder"], device=device)
     if config["model"] == "Fourier":
         model = MultiscaleKFourier(config["net"])
     elif config["model"] == "BoundedFourier":
-        pairs_model = [p_ for p_ in pairs for _ in (0, 1)]          # reference :85,:96 -- each disc twice -> 8 BoundedLinears
+        pairs_model = [(float(a), float(b)) for a, b in create_pairs(part_radii, 2)]     # reference :85,:96 -> 8 BoundedLinears
         model = MultiscaleBoundedFourier(config["net"], boundaries=pairs_model)
     else:
         raise NotImplementedError(config["model"])
@@ -116,7 +96,9 @@ def training_multiscale(config, dataset, data_loader, val_loader, output_path=".
         if (epoch + 1) % config["val_epoch"] == 0:
             model.eval()
             with torch.no_grad():
-                flat = torch.cat([model(coords=encoder.embedding(c.to(device)))[-1] for c, _, _, _ in val_loader])
+                flat = torch.cat([model(coords=encoder.embedding(c.to(device)),                 # reference :207-212
+                                        dist_to_center=(d.to(device) if len(d) != 0 else None))[-1]
+                                  for c, _, d, _ in val_loader])
                 recon = M.reconstruct(flat, (C, H, W), config["transform"])
                 history.append((epoch + 1, float(loss), float(M.psnr(gt_image, recon)), float(M.ssim(gt_image, recon))))
             if verbose:
