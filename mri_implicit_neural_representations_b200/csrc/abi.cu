@@ -1,6 +1,7 @@
 // extern "C" boundary of libinr_b200.so (declared in include/inr_b200.h): plan construction, workspace
 // layout, and the launch sequences of the fused kernels.  No exceptions leave this file.
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <cstdlib>
 #include <string>
@@ -56,11 +57,52 @@ struct inr_plan {
   std::vector<WgradUnit> units;   // offsets inside the workspace are filled per call (they depend on bs)
   std::vector<int> unit_layer;    // chain layer of each unit
   int n_sm;
+  // wgrad schedule (WgradArgs): heavy units first in `order`, `group` light (unit, split) items per CTA
+  std::vector<uint16_t> order;
+  int n_heavy = 0, n_light = 0, group = 1;
 };
 
 static thread_local std::string g_err;
 // wgrad units sweep up to three 128-feature B chunks per resident A sub-image: split `n` chunks into equal groups
 static int chunk_group(int n) { const int groups = (n + 2) / 3; return (n + groups - 1) / groups; }
+
+// What one row tile costs a wgrad unit, in operand bytes (what bounds the kernel): its A sub-image plus every B chunk --
+// but never less than 64 KB: a unit with tiny operands is bound by the ring's round trip (about 2.2 us over the three
+// 32 KB slots its A sub-images get), which is what half a three-chunk unit's tile takes (measured).
+static uint32_t unit_cost(const WgradUnit& u) {
+  return std::max<uint32_t>(65536u, u.a_bytes + static_cast<uint32_t>(u.n_chunks > 1 ? u.n_chunks : 1) * u.b_bytes);
+}
+
+// Two-class static schedule: units costing more than half of the dearest one are "heavy" (one CTA per (unit, split)
+// item), the others are "light" and `group` of their items share a CTA, group = dearest / dearest light cost.
+static void build_wgrad_sched(inr_plan* p) {
+  uint32_t cmax = 0, lmax = 0;
+  for (const WgradUnit& u : p->units) cmax = std::max(cmax, unit_cost(u));
+  p->order.clear();
+  std::vector<uint16_t> light;
+  for (size_t i = 0; i < p->units.size(); ++i) {
+    const uint32_t c = unit_cost(p->units[i]);
+    if (2 * c > cmax) p->order.push_back(static_cast<uint16_t>(i));
+    else { light.push_back(static_cast<uint16_t>(i)); lmax = std::max(lmax, c); }
+  }
+  p->n_heavy = static_cast<int>(p->order.size());
+  p->n_light = static_cast<int>(light.size());
+  p->group = lmax ? std::min<int>(8, std::max<int>(1, static_cast<int>(cmax / lmax))) : 1;
+  p->order.insert(p->order.end(), light.begin(), light.end());
+}
+
+// split-K factor: as many row-tile ranges as fit one wave of CTAs (heavy items 1 per CTA, light items `group` per CTA)
+static int wgrad_splits(const inr_plan* p, int T) {
+  int ns = 1;
+  while (p->n_heavy * (ns + 1) + (p->n_light * (ns + 1) + p->group - 1) / p->group <= p->n_sm) ++ns;
+  if (ns > T) ns = T > 0 ? T : 1;
+  return ns;
+}
+
+static void fill_wgrad_sched(const inr_plan* p, WgradArgs& g) {
+  g.n_heavy = p->n_heavy; g.n_light = p->n_light; g.group = p->group;
+  for (size_t i = 0; i < p->order.size(); ++i) g.order[i] = p->order[i];
+}
 
 // float stride between split-K partial copies: a multiple of 4 so every row the wgrad epilogue bulk-stores stays 16 B aligned
 static int gpart_stride(int n_params) { return (n_params + 3) & ~3; }
@@ -204,6 +246,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   } else {
     cudaGetLastError();
   }
+  build_wgrad_sched(p);
   *out = p;
   return INR_OK;
 }
@@ -231,9 +274,7 @@ static Workspace plan_workspace(const inr_plan* p, int64_t bs) {
   Workspace w{};
   const int T = static_cast<int>((bs + kTileM - 1) / kTileM);
   w.n_tiles = T;
-  int ns = p->n_sm / static_cast<int>(p->units.size());
-  if (ns < 1) ns = 1;
-  if (ns > T) ns = T > 0 ? T : 1;
+  const int ns = wgrad_splits(p, T);
   w.n_split = ns;
   uint64_t o = 0;
   w.scal_off = o; o += align_up(kScalars * 4, 1024);
@@ -312,6 +353,7 @@ static void fill_wgrad(const inr_plan* p, const Workspace& w, uint8_t* ws, Wgrad
     else { u.a_off = w.h_off[M.n_gemm]; u.b_off = w.dzlast_off; }
     g.u[i] = u;
   }
+  fill_wgrad_sched(p, g);
   g.n_split = w.n_split; g.n_tiles = w.n_tiles; g.n_params = gpart_stride(M.n_params);
   g.ws = ws; g.gpart_off = w.gpart_off;
 }
@@ -410,6 +452,7 @@ static int wire_plan_create(const inr_model_desc* d, inr_plan** out) {
   }
   if (static_cast<int>(p->units.size()) > kMaxUnits) { delete p; return fail(INR_EUNSUPPORTED, "WIRE model too deep for the static unit table"); }
   p->n_sm = query_sm_count();
+  build_wgrad_sched(p);
   *out = p;
   return INR_OK;
 }
@@ -507,6 +550,7 @@ static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out) {
   }
   if (static_cast<int>(p->units.size()) > kMaxUnits) { delete p; return fail(INR_EUNSUPPORTED, "WIRE2D model too deep for the static unit table"); }
   p->n_sm = query_sm_count();
+  build_wgrad_sched(p);
   *out = p;
   return INR_OK;
 }
@@ -516,9 +560,7 @@ static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
   WireWorkspace w{};
   const int T = static_cast<int>((bs + kTileM - 1) / kTileM);
   w.n_tiles = T;
-  int ns = p->n_sm / static_cast<int>(p->units.size());
-  if (ns < 1) ns = 1;
-  if (ns > T) ns = T > 0 ? T : 1;
+  const int ns = wgrad_splits(p, T);
   w.n_split = ns;
   uint64_t o = 0;
   w.scal = o; o += align_up(kScalars * 4, 1024);
@@ -633,6 +675,7 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
     else { u.a_off = w.dz[l]; u.b_off = w.hhi[l]; }
     wg.u[i] = u;
   }
+  fill_wgrad_sched(p, wg);
   wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = M.gd_floats; wg.ws = W; wg.gpart_off = w.gpart;
   e = launch_wgrad(wg, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel(wire)");
@@ -794,6 +837,7 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
     return fail(INR_EUNSUPPORTED, "MFN model too large for the static unit / segment tables");
   }
   p->n_sm = query_sm_count();
+  build_wgrad_sched(p);
   *out = p;
   return INR_OK;
 }
@@ -803,9 +847,7 @@ static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs) {
   MfnWorkspace w{};
   const int T = static_cast<int>((bs + kTileM - 1) / kTileM);
   w.n_tiles = T;
-  int ns = p->n_sm / static_cast<int>(p->units.size());
-  if (ns < 1) ns = 1;
-  if (ns > T) ns = T > 0 ? T : 1;
+  const int ns = wgrad_splits(p, T);
   w.n_split = ns;
   uint64_t o = 0;
   w.scal = o; o += align_up(kScalars * 4, 1024);
@@ -942,6 +984,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
     else { const int s = code - 100; u.a_off = w.dh[s]; u.b_off = w.z[s - 1]; }
     wg.u[i] = u;
   }
+  fill_wgrad_sched(p, wg);
   wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = gpart_stride(M.g_floats); wg.ws = W; wg.gpart_off = w.gpart;
   e = launch_wgrad(wg, st);
   if (e != cudaSuccess) return cuda_fail(e, "wgrad_kernel(mfn)");

@@ -130,9 +130,14 @@ struct WgradUnit {
   int n_chunks;                 // B chunks of 128 features swept against one resident A sub-image (0/1: single chunk)
 };
 
-constexpr int kMaxUnits = 320;      // by-value kernel parameter: 320 x 88 B < 32 KB
+constexpr int kMaxUnits = 320;      // by-value kernel parameter: 320 x (88 + 2) B < 32 KB
+// Static two-class schedule of the (unit, split) items over CTAs: a "heavy" item (three-chunk units of the hidden layers)
+// gets a CTA of its own, `group` "light" items (first / last layer, single-chunk units) share one, so every CTA streams
+// about the same number of operand bytes.  order[] lists the heavy units first, then the light ones.
 struct WgradArgs {
   WgradUnit u[kMaxUnits];
+  uint16_t order[kMaxUnits];
+  int n_heavy, n_light, group;
   int n_units, n_split, n_tiles, n_params;
   uint8_t* ws;
   uint64_t gpart_off;

@@ -33,7 +33,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int unit = blockIdx.x % a.n_units, split = blockIdx.x / a.n_units;
+  // items of this CTA: one heavy (unit, split) pair, or up to `group` light ones worked off one after the other
+  const int n_hi = a.n_heavy * a.n_split, n_lo = a.n_light * a.n_split;
+  int item0, n_my;
+  if (static_cast<int>(blockIdx.x) < n_hi) { item0 = blockIdx.x; n_my = 1; }
+  else {
+    item0 = (blockIdx.x - n_hi) * a.group;
+    n_my = n_lo - item0 < a.group ? n_lo - item0 : a.group;
+    item0 += n_hi;
+  }
+
+  for (int i = tid; i < kWgOnesBytes / 2; i += kWgThreads) ones[i] = __float2half(1.0f);
+  fence_proxy_async_smem();
+  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+  if (tid == 0) WG_TRACE(0);
+
+  for (int my = 0; my < n_my; ++my) {
+  const int item = item0 + my;
+  const int unit = item < n_hi ? a.order[item % a.n_heavy] : a.order[a.n_heavy + (item - n_hi) % a.n_light];
+  const int split = item < n_hi ? item / a.n_heavy : (item - n_hi) / a.n_light;
   const WgradUnit& U = a.u[unit];
   const int nch = U.n_chunks > 1 ? U.n_chunks : 1;
   const int bias_col = 128 * nch;               // accumulator columns of the bias MMA
@@ -41,20 +59,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int t0 = static_cast<int>((static_cast<long long>(a.n_tiles) * split) / a.n_split);
   const int t1 = static_cast<int>((static_cast<long long>(a.n_tiles) * (split + 1)) / a.n_split);
 
+  // every item starts from freshly initialised barriers: the previous item's MMAs, commits and bulk copies have all
+  // completed (its epilogue waited on acc_full, which is committed last), and the A / B sub-ring partition may change
   if (tid == 0) {
-    WG_TRACE(0);
     for (int i = 0; i < kWgSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&acc_full, 1);
     mbar_fence_init();
   }
-  for (int i = tid; i < kWgOnesBytes / 2; i += kWgThreads) ones[i] = __float2half(1.0f);
-  fence_proxy_async_smem();
-  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) WG_TRACE(1);
+  if (tid == 0 && my == 0) WG_TRACE(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: per tile  A, B_0 .. B_{nch-1}
@@ -219,13 +235,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   }
   if (tid == 64) WG_TRACE(5);
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem);
+  __syncthreads();            // item boundary: ring, barriers and accumulator are free again
+  tc_fence_after();
+  }  // items
+  if (warp == 2) tmem_dealloc<512>(tmem_base_s);
   if (tid == 0) WG_TRACE(6);
 }
 
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
-  const int grid = a.n_units * a.n_split;
+  if (a.n_heavy + a.n_light != a.n_units || a.group < 1) return cudaErrorInvalidValue;
+  const int grid = a.n_heavy * a.n_split + (a.n_light * a.n_split + a.group - 1) / a.group;
   if (grid <= 0) return cudaSuccess;
   static bool attr_done = false;
   if (!attr_done) {

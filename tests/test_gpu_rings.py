@@ -153,3 +153,62 @@ def test_training_multiscale_entry_uses_reference_partition(src_path):
     assert hist[1][1] < hist[0][1]                          # the loss goes down
     _, radii = partition_and_stats(dataset=ds, no_steps=16, no_parts=4, stat="max", show=False)
     assert TM.create_pairs(radii, 2) == [(radii[0], radii[i // 2 + 1]) for i in range(8)]
+
+
+def _ring_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sys.path.insert(0, SRC)
+    from train_variations import train_clustering as TC
+    from data.slices import get_data_loader
+    bs, epochs, no_models = 3000, 1, 4
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ds, tl, vl = get_data_loader("knee", "data", "train", bs, transform=False, normalization="max", shape=(3, 64, 64))
+    cfg = {"model": "SIREN", "net": dict(NET), "encoder": dict(ENC), "loss": "L2", "optimizer": "Adam", "lr": 5e-4,
+           "beta1": 0.9, "beta2": 0.999, "weight_decay": 0.0, "max_epoch": epochs, "batch_size": bs, "log_iter": 1000,
+           "val_epoch": 1, "image_save_epoch": 100, "transform": False, "data": "knee",
+           "partition": {"no_steps": 16, "no_models": no_models}}
+    torch.manual_seed(11)
+    res = TC.training_clustering(cfg, ds, tl, vl, verbose=False, jitter_seed=5, rank=rank, world=world)
+    torch.cuda.synchronize()
+    params = {i: m._flat.detach().cpu().clone() for i, m in res["models"].items()}
+    q.put((rank, params, res["history"]))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_rings_spread_over_two_gpus_equal_all_rings_on_one():
+    """Ring -> rank placement changes nothing: every ring model ends bit-identical to the single-GPU run, and both ranks
+    report the single-GPU validation numbers (the slice is assembled by one all-reduce)."""
+    import socket
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+
+    def run(world):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        q = ctx.SimpleQueue()
+        procs = [ctx.Process(target=_ring_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = [q.get() for _ in range(world)]
+        for p in procs:
+            p.join(300)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        return sorted(got, key=lambda t: t[0])
+    one = run(1)[0]
+    two = run(2)
+    assert sorted(two[0][1]) == [0, 2] and sorted(two[1][1]) == [1, 3]
+    for rank, params, hist in two:
+        for i, p in params.items():
+            assert torch.equal(p, one[1][i]), (rank, i)
+        assert hist == one[2] or all(abs(a - b) <= 1e-6 * max(abs(b), 1) for h, g in zip(hist, one[2]) for a, b in zip(h, g))
