@@ -566,7 +566,7 @@ static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
   w.scal = o; o += align_up(kScalars * 4, 1024);
   w.part = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
   w.g = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
-  w.outacc = o;
+  w.outacc = o; o += align_up(static_cast<uint64_t>(T) * kWOutParts * kTileM * 16, 1024);   // partial outputs of the final linear
   const uint64_t img = static_cast<uint64_t>(T) * kTileM * 2 * M.P * 2;            // H images: [hr | hi]
   const uint64_t zimg = img * M.nlin;                                              // pre-activation / gradient images
   for (int l = 1; l <= M.depth + 1; ++l) { w.hhi[l] = o; o += img; w.hlo[l] = o; o += img; }
@@ -588,7 +588,8 @@ static void wire_aux_fill(const inr_plan* p, const WireWorkspace& w, WireAuxArgs
 
 static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
                              const float* coords, const float* gt, const uint8_t* mask, int64_t bs, void* ws, float* out, int train,
-                             const int* row_off, int* step, cudaStream_t st, cudaEvent_t* gemm_ev = nullptr) {
+                             const int* row_off, int* step, cudaStream_t st, cudaEvent_t* gemm_ev = nullptr,
+                             bool fold_scalars = false, const float* hyper = nullptr) {
   const WireModel& M = p->wm;
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
@@ -618,17 +619,23 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 3; g.mode = LG_WIRE_FWD;
     g.bias = params + M.b_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.train = train;
     g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
+    if (l == M.depth && M.out_f <= 2) {       // the final linear rides in this layer's epilogue (partial sums per row)
+      g.last_w = params + M.w_off[M.depth + 1]; g.out_part = reinterpret_cast<float*>(W + w.outacc); g.out_f = M.out_f;
+      x.use_outacc = 1;
+    }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(fwd)");
   }
   if (gemm_ev) cudaEventRecord(gemm_ev[1], st);
   x.step_counter = nullptr;
+  if (fold_scalars && M.nlin == 1 && train) { x.fold_scalars = 1; x.hyper = hyper; x.step = step; }
   e = M.nlin == 2 ? launch_w2d_last(x, st) : launch_wire_last(x, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wire_last_kernel");
 }
 
 static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
-                              const float* dout, int64_t bs, void* ws, const float* hyper, const int* step, cudaStream_t st) {
+                              const float* dout, int64_t bs, void* ws, const float* hyper, const int* step, cudaStream_t st,
+                              bool scalars_done = false) {
   const WireModel& M = p->wm;
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
@@ -636,8 +643,10 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
   x.loss = loss; x.dout = dout; x.hyper = hyper; x.step = step;
   cudaError_t e;
   if (dout) { e = launch_wire_dout_amax(x, st); if (e != cudaSuccess) return cuda_fail(e, "wire_dout_amax_kernel"); }
-  e = launch_wire_scalars(x, st);
-  if (e != cudaSuccess) return cuda_fail(e, "wire_scalars_kernel");
+  if (!scalars_done) {      // the fused step computed them in wire_last's last CTA
+    e = launch_wire_scalars(x, st);
+    if (e != cudaSuccess) return cuda_fail(e, "wire_scalars_kernel");
+  }
   e = M.nlin == 2 ? launch_w2d_blast(x, st) : launch_wire_blast(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "wire_blast_kernel");
   for (int l = M.depth; l >= 1 && M.nlin == 2; --l) {
@@ -1234,14 +1243,16 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
     const LossDesc WL{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w};
     if (ev) cudaEventRecord(ev[0], st);
+    // without a TV pass between forward and backward the step scalars are reduced by the last CTA of wire_last
+    const bool fold = p->wm.nlin == 1 && !(loss->tv_weight > 0.f);
     int rcw = wire_forward_impl(p, ww, WL, params, wpack, coords, gt, mask, bs, workspace, out, 1, row_cursor_dev,
-                                no_adam ? nullptr : step_dev, st, ev ? ev + 5 : nullptr);
+                                no_adam ? nullptr : step_dev, st, ev ? ev + 5 : nullptr, fold, no_adam ? nullptr : hyper_dev);
     if (rcw) return rcw;
     rcw = run_tv(loss, out, p->wm.out_f, bs, wsb, ww.g, ww.part, ww.n_tiles, st);
     if (rcw) return rcw;
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     rcw = wire_backward_impl(p, ww, WL, params, wpack, nullptr, bs, workspace, no_adam ? nullptr : hyper_dev,
-                             no_adam ? nullptr : step_dev, st);
+                             no_adam ? nullptr : step_dev, st, fold);
     if (rcw) return rcw;
     if (ev) cudaEventRecord(ev[3], st);
     WireAdamArgs wa; wire_adam_fill(p, wa);

@@ -33,7 +33,8 @@ enum LossKind { LOSS_NONE = 0, LOSS_L2 = 1, LOSS_L1 = 2, LOSS_MSLE = 3, LOSS_TAN
 enum Scalar { SC_LOSS = 0, SC_SCALE = 1, SC_CA = 2, SC_CB = 3, SC_COUNT = 4, SC_FMEAN = 5, SC_REG = 6, SC_INV_SCALE = 7,
               SC_STEP_SIZE = 8, SC_BC2_SQRT = 9,
               SC_LAYER_SCALE = 16,   // [16 .. 16+depth]: power-of-two scale of the dZ image of layer l (WIRE)
-              SC_LAYER_AMAX = 40 };  // [40 .. 40+depth]: amax (float bits, atomicMax) of the scaled dZ of layer l, this step   // Adam bias corrections, computed once per step (fp64) by the backward prologue
+              SC_LAYER_AMAX = 40,
+              SC_DONE_COUNT = 63 };  // uint32 count of finished CTAs (last-CTA reduction of wire_last), self-resetting  // [40 .. 40+depth]: amax (float bits, atomicMax) of the scaled dZ of layer l, this step   // Adam bias corrections, computed once per step (fp64) by the backward prologue
 
 struct ChainModel {
   int n_gemm;        // tensor-core layers (reference depth - 1)

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_ba[512], s_bb[512];     // WIRE: bias re / im (192 used);  MFN: b_i / phi_i (width <= 512)
+  __shared__ float4 s_lw[MODE == LG_WIRE_FWD ? kWP : 1];   // WIRE_FWD: final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_items = a.n_tiles * a.n_nblocks;
@@ -81,6 +82,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     for (int j = tid; j < kWP; j += kLgThreads) {
       s_ba[j] = j < a.c_valid ? a.bias[2 * j] : 0.f;
       s_bb[j] = j < a.c_valid ? a.bias[2 * j + 1] : 0.f;
+      float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.last_w && j < a.c_valid) {
+        lw.x = a.last_w[2 * j]; lw.y = a.last_w[2 * j + 1];
+        if (a.out_f > 1) { lw.z = a.last_w[2 * (a.c_valid + j)]; lw.w = a.last_w[2 * (a.c_valid + j) + 1]; }
+      }
+      s_lw[j] = lw;
     }
   } else if (MODE == LG_MFN_FWD) {
     const int width = a.n_nblocks * a.nt;
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         mbar_wait(&acc_full[ab], use & 1);
         tc_fence_after();
         if (tid == 128) LG_TRACE(3 + 3 * n_done);
+        float o0 = 0.f, o1 = 0.f;                           // this thread's share of the final linear (last hidden layer only)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int c0 = 24 * sub + 8 * i;                 // feature inside the N-block
@@ -317,6 +325,14 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               const bool live = (f0 + e) < a.c_valid;
               yr[e] = live ? mag * fast_cos(ang) : 0.f;
               yi[e] = live ? mag * fast_sin(ang) : 0.f;
+            }
+            if (MODE == LG_WIRE_FWD && a.out_part) {       // features in ascending order: fixed summation order
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 lw = s_lw[f0 + e];            // same address in every lane: broadcast
+                o0 = fmaf(yr[e], lw.x, fmaf(-yi[e], lw.y, o0));
+                o1 = fmaf(yr[e], lw.z, fmaf(-yi[e], lw.w, o1));
+              }
             }
             uint4 rh, rl, ih, il;
             split_h2(yr[0], yr[1], rh.x, rl.x); split_h2(yr[2], yr[3], rh.y, rl.y);
@@ -348,6 +364,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             st_global_v4(a.out_dz + off_i, pack8(db));
           }
         }
+        if (MODE == LG_WIRE_FWD && a.out_part)
+          reinterpret_cast<float4*>(a.out_part)[(static_cast<size_t>(tile) * kWOutParts + nb * 4 + sub) * kTileM + row] =
+              make_float4(o0, o1, 0.f, 0.f);
       } else {
         // ---------------- MFN stages: nt = 128 columns per N-block, this warp owns 32 of them (4 steps of 8)
         const size_t img = static_cast<size_t>(tile) * a.feat_tile_bytes + row * 16;

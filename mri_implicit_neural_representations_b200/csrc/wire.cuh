@@ -85,6 +85,10 @@ struct LGemmArgs {
   const float* gamma;       // GABOR_E: gamma_j [width]
   const float* mn;          // GABOR_E: |mu_j|^2 [width]
   uint32_t feat_tile_bytes; // bytes of one 128-row image of the epilogue's feature images (MFN: 128 * width * 2)
+  // WIRE_FWD of the last hidden layer: the final complex linear (reference networks.py:247-258, real part) rides along --
+  // every epilogue thread adds its 24 features' share of out[row][o] = sum_f Re(y_f W[o][f]) and stores the partial sum
+  const float* last_w;      // final-layer weight [out_f][c] complex, interleaved (re, im), or null
+  float* out_part;          // [tile][kWOutParts][128 rows] float4 partial outputs (fixed slots: no atomics), or null
   int dbg;                  // debug (INR_LGEMM_DBG): bit 0 skip MMAs, bit 1 skip operand copies (timing experiments only)
   unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)
 };
@@ -116,6 +120,8 @@ struct WireWorkspace {
   int n_tiles, n_split;
 };
 
+constexpr int kWOutParts = 8;   // partial sums of the final linear per row: 2 N-blocks x 4 epilogue column groups
+
 struct WireAuxArgs {
   WireModel m;
   WireWorkspace w;
@@ -128,6 +134,8 @@ struct WireAuxArgs {
   const float* hyper; const int* step;
   const float* dout;
   int bs, train, bs_k;
+  int use_outacc;           // wire_last: sum the layer GEMM's partial outputs (w.outacc) instead of re-reading the H images
+  int fold_scalars;         // wire_last: the last CTA to finish also computes the step scalars (no wire_scalars launch)
 };
 
 struct WireAdamArgs {

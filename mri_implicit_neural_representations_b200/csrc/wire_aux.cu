@@ -94,6 +94,37 @@ __global__ void __launch_bounds__(256) wire_first_kernel(const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ step scalars
+// One block: tile partials -> loss, normalisers, global gradient scale, Adam bias corrections, per-layer dZ scales.
+__device__ inline void wire_step_scalars(const WireAuxArgs& a) {
+  __shared__ float sc[kScalars];
+  float* g = reinterpret_cast<float*>(a.ws + a.w.scal);
+  reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step, g, sc);
+  if (threadIdx.x == 0) {
+    // per-layer dZ scales for this step from the previous step's amax (lagged dynamic scaling, 2^10 headroom below
+    // the fp16 maximum); uncalibrated layers start 16x below the layer above (gradients grow ~10x per layer downwards)
+    unsigned int* am = reinterpret_cast<unsigned int*>(g) + SC_LAYER_AMAX;
+    float above = sc[SC_SCALE];
+    for (int l = a.m.depth; l >= 0; --l) {
+      const float old = g[SC_LAYER_SCALE + l];
+      const float seen = __uint_as_float(am[l]);
+      float S;
+      if (old > 0.f && seen > 0.f && isfinite(seen) && isfinite(old)) {
+        int e = static_cast<int>(floorf(log2f(64.f * old / seen)));
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        S = exp2f(static_cast<float>(e));
+      } else {
+        S = above * 0.0625f;
+      }
+      g[SC_LAYER_SCALE + l] = S;
+      am[l] = 0u;
+      above = S;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) wire_scalars_kernel(const __grid_constant__ WireAuxArgs a) { wire_step_scalars(a); }
+
 // ------------------------------------------------------------------------------------------------ final layer + loss
 __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ WireAuxArgs a) {
   __shared__ float sWr[kMaxOut][kWP], sWi[kMaxOut][kWP];
@@ -117,6 +148,13 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
   const uint8_t* hhi = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
   const uint8_t* hlo = a.ws + a.w.hlo[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
   float acc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+  if (a.use_outacc) {
+    // the last hidden layer's GEMM epilogue left kWOutParts partial sums per row (lgemm.cu, LG_WIRE_FWD): 2 of them per
+    // thread here, combined below in the same fixed order as the image path
+    const float4* op = reinterpret_cast<const float4*>(a.ws + a.w.outacc) + static_cast<size_t>(tile) * kWOutParts * kTileM + row;
+    const float4 p0 = op[(2 * part) * kTileM], p1 = op[(2 * part + 1) * kTileM];
+    acc[0] = p0.x + p1.x; acc[1] = p0.y + p1.y;
+  } else {
 #pragma unroll 2
   for (int kg = part * (kWP / 32); kg < (part + 1) * (kWP / 32); ++kg) {
     float rh[8], rl[8], ih[8], il[8];
@@ -132,12 +170,13 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
         if (o < M.out_f) acc[o] = fmaf(hr, sWr[o][kg * 8 + e], fmaf(-hi, sWi[o][kg * 8 + e], acc[o]));
     }
   }
+  }
   if (part > 0) {
 #pragma unroll
     for (int o = 0; o < kMaxOut; ++o) s_part[part - 1][row][o] = acc[o];
   }
   __syncthreads();
-  if (part > 0) return;
+  if (part == 0) {
   float y[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, t[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o)
@@ -145,7 +184,7 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
       y[o] = ((acc[o] + s_part[0][row][o]) + (s_part[1][row][o] + s_part[2][row][o])) + a.params[M.b_off[L] + 2 * o];
   if (valid && a.out)
     for (int o = 0; o < M.out_f; ++o) a.out[static_cast<size_t>(grow) * M.out_f + o] = y[o];
-  if (!a.train) return;
+  if (a.train) {
   float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
   float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
   if (valid && a.gt && a.loss.kind != LOSS_NONE) {
@@ -184,34 +223,21 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
     pdst[5] = fmaxf(fmaxf(red[0][5], red[1][5]), fmaxf(red[2][5], red[3][5]));
     pdst[6] = 0.f; pdst[7] = 0.f;
   }
-}
-
-// ------------------------------------------------------------------------------------------------ step scalars
-__global__ void __launch_bounds__(256) wire_scalars_kernel(const __grid_constant__ WireAuxArgs a) {
-  __shared__ float sc[kScalars];
-  float* g = reinterpret_cast<float*>(a.ws + a.w.scal);
-  reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step, g, sc);
-  if (threadIdx.x == 0) {
-    // per-layer dZ scales for this step from the previous step's amax (lagged dynamic scaling, 2^10 headroom below
-    // the fp16 maximum); uncalibrated layers start 16x below the layer above (gradients grow ~10x per layer downwards)
-    unsigned int* am = reinterpret_cast<unsigned int*>(g) + SC_LAYER_AMAX;
-    float above = sc[SC_SCALE];
-    for (int l = a.m.depth; l >= 0; --l) {
-      const float old = g[SC_LAYER_SCALE + l];
-      const float seen = __uint_as_float(am[l]);
-      float S;
-      if (old > 0.f && seen > 0.f && isfinite(seen) && isfinite(old)) {
-        int e = static_cast<int>(floorf(log2f(64.f * old / seen)));
-        e = e < -100 ? -100 : (e > 100 ? 100 : e);
-        S = exp2f(static_cast<float>(e));
-      } else {
-        S = above * 0.0625f;
-      }
-      g[SC_LAYER_SCALE + l] = S;
-      am[l] = 0u;
-      above = S;
-    }
-  }
+  }  // train
+  }  // part == 0
+  if (!(a.train && a.fold_scalars)) return;
+  // The last CTA to finish reduces all tile partials to the step scalars (what wire_scalars_kernel does as a launch
+  // of its own): every CTA publishes its partials (fence) before it counts itself in.
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  unsigned int* done = reinterpret_cast<unsigned int*>(a.ws + a.w.scal) + SC_DONE_COUNT;
+  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  wire_step_scalars(a);
+  if (threadIdx.x == 0) *done = 0u;
 }
 
 // amax partials for an externally supplied dL/dout (autograd path)
