@@ -41,7 +41,8 @@ class SliceDataset:
     """coords [N,3], image [N,2], optional coords_mask [N,3] bool, dist_to_center [N]; img_shape (C,H,W,2)."""
 
     def __init__(self, data="knee", data_root="data", set="train", transform=True, sample=0, slice=0, full_norm=False,
-                 normalization="max", undersampling: Optional[str] = None, use_dists=False, shape=(15, 320, 320), seed=None):
+                 normalization="max", undersampling: Optional[str] = None, use_dists=False, shape=(15, 320, 320), seed=None,
+                 device=None):
         loaded = _load_h5_slice(data, data_root, set, sample, slice)
         if loaded is not None:
             kspace, self.file = loaded
@@ -54,6 +55,10 @@ class SliceDataset:
             seed = 1234 + 17 * int(sample) + int(slice) if seed is None else seed
             img = synthetic.phantom_slice(seed, *shape)
             self.file = f"synthetic://knee/sample{sample}/slice{slice}"
+        if device is not None:
+            # the whole preparation below (FFT, normalisation, masks, coordinate grid, distances) is plain tensor
+            # arithmetic: on `device` it runs on the GPU and the arrays are born resident
+            img = img.to(device)
         C, H, W = img.shape
         if transform:
             t = torch.view_as_real(img) / img.abs().max()         # normalize_image; `normalization` ignored (reference :64-68)
@@ -75,16 +80,15 @@ class SliceDataset:
             t = k
         self.img_shape = (C, H, W, 2)
         self.shape = t.shape
-        self.coords = synthetic.coords_grid(C, H, W).float().contiguous()
+        self.coords = synthetic.coords_grid(C, H, W, device=img.device).float().contiguous()
         self.coords_mask = None
         if undersampling is not None and str(undersampling).lower() != "none":
-            kind, param = undersampling.split("-")
-            if kind != "grid":
-                raise NotImplementedError(f"undersampling '{kind}' is CPU preprocessing outside this engine's scope")
-            gx, gy = (int(v) for v in param.split("*"))
-            m = grid_mask(H, W, gx, gy)
-            t = t * m[None, :, :, None]                          # masked-out samples are zeroed (undersampler.py:59-61)
-            self.coords_mask = m[None].expand(C, H, W).reshape(-1, 1).expand(-1, 3).contiguous()
+            # reference data/nerp_datasets.py:256-334: 'grid-x*y' | 'random_line-p' | 'radial-acc' -> Undersampler.apply;
+            # masked-out samples are zeroed (undersampler.py:59-61), coords_mask = the image mask per coil and column
+            from undersampling.undersampler import Undersampler, parse_undersampling_argument
+            kind, params = parse_undersampling_argument(undersampling)
+            self.undersampler = Undersampler(kind)
+            t, _, self.coords_mask = self.undersampler.apply(t, params)
         self.image = t.reshape(C * H * W, 2).float().contiguous()
         self.dist_to_center = None
         if use_dists:
@@ -115,14 +119,16 @@ class GridOrderLoader:
 
 def get_data_loader(data, data_root, set, batch_size, transform=True, num_workers=0, sample=0, slice=0,
                     challenge="multicoil", shuffle=True, full_norm=False, normalization="max", use_dists="no",
-                    undersampling=None, per_coil=False, shape=(15, 320, 320)):
+                    undersampling=None, per_coil=False, shape=(15, 320, 320), device=None):
     """Same signature / return triple as reference src/models/utils.py:57-141 (`shuffle` is ignored there too)."""
     assert data in ["brain", "knee"], "Unsupported parameter is provided in the get_data_loader() function"
     use_d = use_dists in ("yes", True)
-    full = SliceDataset(data, data_root, set, transform, sample, slice, full_norm, normalization, None, use_d, shape)
+    full = SliceDataset(data, data_root, set, transform, sample, slice, full_norm, normalization, None, use_d, shape,
+                        device=device)
     train = full
     if undersampling is not None and str(undersampling).lower() != "none":
-        train = SliceDataset(data, data_root, set, transform, sample, slice, full_norm, normalization, undersampling, use_d, shape)
+        train = SliceDataset(data, data_root, set, transform, sample, slice, full_norm, normalization, undersampling, use_d, shape,
+                             device=device)
     C, H, W, _ = full.img_shape
     train_bs = H * W if per_coil else batch_size
     return full, GridOrderLoader(train, train_bs), GridOrderLoader(full, batch_size)
