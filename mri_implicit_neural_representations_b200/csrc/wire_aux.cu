@@ -98,16 +98,23 @@ __global__ void __launch_bounds__(256) wire_first_kernel(const __grid_constant__
 // One block: tile partials -> loss, normalisers, global gradient scale, Adam bias corrections, per-layer dZ scales.
 __device__ inline void wire_step_scalars(const WireAuxArgs& a) {
   __shared__ float sc[kScalars];
+  __shared__ float s_old[kWMaxDepth + 1], s_seen[kWMaxDepth + 1];
   float* g = reinterpret_cast<float*>(a.ws + a.w.scal);
+  unsigned int* am = reinterpret_cast<unsigned int*>(g) + SC_LAYER_AMAX;
+  // one thread per layer fetches last step's scale / amax while the block reduces the tile partials: the recurrence
+  // below then runs out of shared memory instead of through 2 x (depth + 1) dependent global loads on one thread
+  if (static_cast<int>(threadIdx.x) <= a.m.depth) {
+    s_old[threadIdx.x] = g[SC_LAYER_SCALE + threadIdx.x];
+    s_seen[threadIdx.x] = __uint_as_float(am[threadIdx.x]);
+  }
   reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step, g, sc);
   if (threadIdx.x == 0) {
     // per-layer dZ scales for this step from the previous step's amax (lagged dynamic scaling, 2^10 headroom below
     // the fp16 maximum); uncalibrated layers start 16x below the layer above (gradients grow ~10x per layer downwards)
-    unsigned int* am = reinterpret_cast<unsigned int*>(g) + SC_LAYER_AMAX;
     float above = sc[SC_SCALE];
     for (int l = a.m.depth; l >= 0; --l) {
-      const float old = g[SC_LAYER_SCALE + l];
-      const float seen = __uint_as_float(am[l]);
+      const float old = s_old[l];
+      const float seen = s_seen[l];
       float S;
       if (old > 0.f && seen > 0.f && isfinite(seen) && isfinite(old)) {
         int e = static_cast<int>(floorf(log2f(64.f * old / seen)));
@@ -134,13 +141,15 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
   // 4 threads per row, each reduces 6 of the 24 feature groups (independent 16-byte loads in flight), then one combines
   const int tile = blockIdx.x, row = threadIdx.x & (kTileM - 1), part = threadIdx.x >> 7, lane = row & 31, q = row >> 5;
   const int L = M.depth + 1;
-  for (int i = threadIdx.x; i < kMaxOut * kWP; i += 512) {
-    const int o = i / kWP, j = i % kWP;
-    const bool ok = o < M.out_f && j < M.c;
-    sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
-    sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
+  if (!a.use_outacc) {          // the image path applies the final linear here
+    for (int i = threadIdx.x; i < kMaxOut * kWP; i += 512) {
+      const int o = i / kWP, j = i % kWP;
+      const bool ok = o < M.out_f && j < M.c;
+      sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
+      sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const int grow = tile * kTileM + row;
   const bool valid = grow < a.bs;
