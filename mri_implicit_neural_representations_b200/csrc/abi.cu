@@ -619,9 +619,9 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 3; g.mode = LG_WIRE_FWD;
     g.bias = params + M.b_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.train = train;
     g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
-    if (l == M.depth && M.out_f <= 2) {       // the final linear rides in this layer's epilogue (partial sums per row)
+    if (l == M.depth) {       // the final linear rides in this layer's epilogue (partial sums per row; out_f <= 2, depth >= 1)
       g.last_w = params + M.w_off[M.depth + 1]; g.out_part = reinterpret_cast<float*>(W + w.outacc); g.out_f = M.out_f;
-      x.use_outacc = 1;
+      g.out_lo = nullptr;     // H_lo of the last hidden layer had one reader, the final linear
     }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(fwd)");

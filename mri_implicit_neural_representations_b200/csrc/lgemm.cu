@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             split_h2(yi[0], yi[1], ih.x, il.x); split_h2(yi[2], yi[3], ih.y, il.y);
             split_h2(yi[4], yi[5], ih.z, il.z); split_h2(yi[6], yi[7], ih.w, il.w);
             st_global_v4(a.out_hi + off_r, rh); st_global_v4(a.out_hi + off_i, ih);
-            st_global_v4(a.out_lo + off_r, rl); st_global_v4(a.out_lo + off_i, il);
+            if (a.out_lo) {       // null for the last hidden layer: nothing reads its lo image (the final linear rode along above)
+              st_global_v4(a.out_lo + off_r, rl); st_global_v4(a.out_lo + off_i, il);
+            }
             if (a.train) {
               st_global_v4(a.out_ab + off_r, pack8(va));
               st_global_v4(a.out_ab + off_i, pack8(vb));

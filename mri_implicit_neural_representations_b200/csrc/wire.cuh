@@ -134,7 +134,6 @@ struct WireAuxArgs {
   const float* hyper; const int* step;
   const float* dout;
   int bs, train, bs_k;
-  int use_outacc;           // wire_last: sum the layer GEMM's partial outputs (w.outacc) instead of re-reading the H images
   int fold_scalars;         // wire_last: the last CTA to finish also computes the step scalars (no wire_scalars launch)
 };
 

@@ -2,7 +2,8 @@
 //   wire_first_kernel   : real first layer 3 -> C + Gabor wavelet (reference networks.py:185-204 with is_first), writes the
 //                         hi/lo operand images of hidden layer 1, the (a) image for backward and the coordinate image
 //                         used by the first layer's wgrad
-//   wire_last_kernel    : final complex linear C -> out, real part (networks.py:247-258) + per-row loss pieces
+//   wire_last_kernel    : final complex linear C -> out, real part (networks.py:247-258): adds up the partial sums the last
+//                         hidden layer's GEMM epilogue left per row, + per-row loss pieces (+ step scalars in its last CTA)
 //   wire_scalars_kernel : step scalars from the tile partials (one block)
 //   wire_blast_kernel   : backward of the final layer + Gabor derivative of the last hidden layer
 #include <cuda_runtime.h>
@@ -134,51 +135,23 @@ __global__ void __launch_bounds__(256) wire_scalars_kernel(const __grid_constant
 
 // ------------------------------------------------------------------------------------------------ final layer + loss
 __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ WireAuxArgs a) {
-  __shared__ float sWr[kMaxOut][kWP], sWi[kMaxOut][kWP];
   __shared__ float red[4][8];
   __shared__ float s_part[3][kTileM][kMaxOut];
   const WireModel& M = a.m;
   // 4 threads per row, each reduces 6 of the 24 feature groups (independent 16-byte loads in flight), then one combines
   const int tile = blockIdx.x, row = threadIdx.x & (kTileM - 1), part = threadIdx.x >> 7, lane = row & 31, q = row >> 5;
   const int L = M.depth + 1;
-  if (!a.use_outacc) {          // the image path applies the final linear here
-    for (int i = threadIdx.x; i < kMaxOut * kWP; i += 512) {
-      const int o = i / kWP, j = i % kWP;
-      const bool ok = o < M.out_f && j < M.c;
-      sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
-      sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
-    }
-    __syncthreads();
-  }
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const int grow = tile * kTileM + row;
   const bool valid = grow < a.bs;
   const size_t srow = static_cast<size_t>(row_base) + grow;
-  const uint8_t* hhi = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
-  const uint8_t* hlo = a.ws + a.w.hlo[L] + static_cast<size_t>(tile) * kWTileBytes + row * 16;
   float acc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
-  if (a.use_outacc) {
+  {
     // the last hidden layer's GEMM epilogue left kWOutParts partial sums per row (lgemm.cu, LG_WIRE_FWD): 2 of them per
-    // thread here, combined below in the same fixed order as the image path
+    // thread here, combined below in a fixed order
     const float4* op = reinterpret_cast<const float4*>(a.ws + a.w.outacc) + static_cast<size_t>(tile) * kWOutParts * kTileM + row;
     const float4 p0 = op[(2 * part) * kTileM], p1 = op[(2 * part + 1) * kTileM];
     acc[0] = p0.x + p1.x; acc[1] = p0.y + p1.y;
-  } else {
-#pragma unroll 2
-  for (int kg = part * (kWP / 32); kg < (part + 1) * (kWP / 32); ++kg) {
-    float rh[8], rl[8], ih[8], il[8];
-    wire_unpack8(ld_global_nc_v4(hhi + static_cast<size_t>(kg) * 2048), rh);
-    wire_unpack8(ld_global_nc_v4(hlo + static_cast<size_t>(kg) * 2048), rl);
-    wire_unpack8(ld_global_nc_v4(hhi + static_cast<size_t>(kWP / 8 + kg) * 2048), ih);
-    wire_unpack8(ld_global_nc_v4(hlo + static_cast<size_t>(kWP / 8 + kg) * 2048), il);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float hr = rh[e] + rl[e], hi = ih[e] + il[e];
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o)
-        if (o < M.out_f) acc[o] = fmaf(hr, sWr[o][kg * 8 + e], fmaf(-hi, sWi[o][kg * 8 + e], acc[o]));
-    }
-  }
   }
   if (part > 0) {
 #pragma unroll

@@ -330,7 +330,9 @@ class ChainEngine:
         if kind == "h":
             hi = dec(lay["h"][layer])
             lo = dec(lay["h"][layer] + nbytes)          # H_lo[l] is laid out right after H_hi[l]
-            m = hi + lo
+            # WIRE: the lo image of the last hidden layer's output is never written (nothing reads it)
+            last = self.plan.model == "WIRE" and layer == int(self.plan.net["network_depth"]) + 1
+            m = hi if last else hi + lo
         elif kind == "ab":
             m = dec(lay["d"][layer])
         else:
