@@ -67,10 +67,11 @@ static thread_local std::string g_err;
 static int chunk_group(int n) { const int groups = (n + 2) / 3; return (n + groups - 1) / groups; }
 
 // What one row tile costs a wgrad unit, in operand bytes (what bounds the kernel): its A sub-image plus every B chunk --
-// but never less than 64 KB: a unit with tiny operands is bound by the ring's round trip (about 2.2 us over the three
-// 32 KB slots its A sub-images get), which is what half a three-chunk unit's tile takes (measured).
+// but never less than 48 KB: a unit with tiny operands is bound by the ring's round trip (about 2.2 us over the three
+// 32 KB slots its A sub-images get), not by its bytes.  With this floor two light items share a CTA on every model
+// measured (WIRE: 54.5 -> 47 us against 57 us with three per CTA; SIREN: 20.7 us either way).
 static uint32_t unit_cost(const WgradUnit& u) {
-  return std::max<uint32_t>(65536u, u.a_bytes + static_cast<uint32_t>(u.n_chunks > 1 ? u.n_chunks : 1) * u.b_bytes);
+  return std::max<uint32_t>(49152u, u.a_bytes + static_cast<uint32_t>(u.n_chunks > 1 ? u.n_chunks : 1) * u.b_bytes);
 }
 
 // Two-class static schedule: units costing more than half of the dearest one are "heavy" (one CTA per (unit, split)

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
   const int n_tiles = a.w.n_tiles;
   const float zscale = (M.act == ACT_SIN) ? M.w0 : 1.f;   // act' images hold cos(w0 z); w0 rides in the weights
 
+  griddep_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < kBwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&act_full[i], kBwdComputeThreads); }
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
   }
   for (int i = tid; i < M.out_f * kWidth; i += kBwdThreads) c_wlast[i] = zscale * a.params[M.w_off[M.n_gemm] + i];
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+  griddep_wait();            // forward kernel complete: tile partials, loss pieces and act' images are final
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -219,8 +221,7 @@ cudaError_t launch_chain_bwd(const BwdArgs& a, int n_sm, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  chain_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, stream>>>(a);
-  return cudaGetLastError();
+  return launch_dependent(chain_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmem, stream, a);
 }
 
 }  // namespace inr

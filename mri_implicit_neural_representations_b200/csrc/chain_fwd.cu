@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const float zscale = (ACT == ACT_SIN) ? M.w0 : 1.f;     // packed weights carry the same factor (optim.cu)
   if (tid == 0) INR_TRACE(a, 0);
+  griddep_launch_dependents();      // the backward kernel may set up (barriers, TMEM, constants) on SMs this grid leaves idle
 
   if (tid == 0) {
     for (int i = 0; i < kFwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }

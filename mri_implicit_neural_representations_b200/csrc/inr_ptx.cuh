@@ -198,6 +198,11 @@ __device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
 __device__ __forceinline__ void st_global_v4(void* p, uint4 v) {
   asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization): the next kernel
+// of the stream may be scheduled once every CTA of this grid has executed launch_dependents (or exited); it must execute
+// griddep_wait() -- this grid complete, its writes visible -- before touching anything an earlier kernel of the step wrote.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float fast_sin(float x) {
   float r;
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -207,6 +212,21 @@ __device__ __forceinline__ float fast_cos(float x) {
   float r;
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+// Host side of programmatic dependent launch: launch `kern` so that it may be scheduled as soon as every CTA of the
+// previous kernel in the stream has executed griddep_launch_dependents() (or exited).  The kernel must call griddep_wait()
+// before it reads or writes anything an earlier kernel of the step touches.  INR_PDL=0 gives plain stream-ordered launches.
+bool pdl_enabled();   // lgemm.cu
+template <typename Arg>
+inline cudaError_t launch_dependent(void (*kern)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Arg& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 }  // namespace inr

@@ -20,6 +20,7 @@
 //   LG_GABOR_E    : Gabor envelope E = exp(-gamma/2 (|x|^2 + |mu|^2 - 2 x mu^T)) (reference mfn.py:117-131) as an fp16
 //                   image; MFN_FWD then stores f = sin(p) E and cos(p) E in place of sin / cos, which makes the
 //                   backward epilogue of a Gabor stage identical to the Fourier one plus the q = dL/df * f image.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "inr_ptx.cuh"
 #include "wire.cuh"
@@ -72,12 +73,18 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   int n_slots = kLgRingBytes / slot_bytes;
   if (n_slots > kLgMaxSlots) n_slots = kLgMaxSlots;
 
+  // The next layer GEMM of the stream may be scheduled onto SMs this grid has already left; what runs before
+  // griddep_wait() (barrier init, TMEM allocation) touches no global memory, everything after it sees the previous
+  // kernel -- and with it every earlier kernel of the step -- complete.
+  griddep_launch_dependents();
   if (tid == 0) {
     LG_TRACE(0);
     for (int i = 0; i < kLgMaxSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads); }
     mbar_fence_init();
   }
+  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+  griddep_wait();
   if (MODE == LG_WIRE_FWD) {
     for (int j = tid; j < kWP; j += kLgThreads) {
       s_ba[j] = j < a.c_valid ? a.bias[2 * j] : 0.f;
@@ -108,7 +115,6 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       s_bb[j] = a.mn[j];
     }
   }
-  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -476,6 +482,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   if (tid == 0) LG_TRACE(15);
 }
 
+// INR_PDL=0 launches the GEMM kernels without the programmatic-serialization attribute (plain stream order)
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("INR_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   const int items = a.n_tiles * a.n_nblocks;
   const int grid = items < n_sm ? items : n_sm;
@@ -490,7 +503,14 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
       if (e != cudaSuccess) return e;                                                                             \
       attr = true;                                                                                                \
     }                                                                                                             \
-    lgemm_kernel<P, M, K><<<grid, kLgThreads, kLgSmem, stream>>>(a);                                              \
+    cudaLaunchConfig_t cfg = {};                                                                                  \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kLgThreads); cfg.dynamicSmemBytes = kLgSmem; cfg.stream = stream;  \
+    cudaLaunchAttribute at[1];                                                                                    \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                               \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                                         \
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;                                                         \
+    cudaError_t le = cudaLaunchKernelEx(&cfg, lgemm_kernel<P, M, K>, a);                                          \
+    if (le != cudaSuccess) return le;                                                                             \
   } while (0)
   switch (a.mode) {
     case LG_WIRE_FWD:

@@ -54,6 +54,7 @@ __device__ __forceinline__ void pack_store(const SegDesc& s, uint8_t* wpack, int
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
   __shared__ float s_c[4];   // step_size, sqrt(bc2), inv_scale, -
+  griddep_wait();            // split-K partials of wgrad (or the exchanged gradients) complete
   if (threadIdx.x == 0) {
     const float* sc = a.scal;
     s_c[2] = sc ? sc[SC_INV_SCALE] : 1.f;
@@ -194,8 +195,7 @@ cudaError_t launch_tv(const TvArgs& a, int n_tiles, cudaStream_t st) {
 cudaError_t launch_adam(const AdamArgs& a, cudaStream_t stream) {
   const int per_cta = a.peer.n_ranks > 0 ? 1024 : 256;
   const int grid = (a.n_params + per_cta - 1) / per_cta;
-  adam_kernel<<<grid, 256, 0, stream>>>(a);
-  return cudaGetLastError();
+  return launch_dependent(adam_kernel, dim3(grid), dim3(256), 0, stream, a);
 }
 cudaError_t launch_pack(const AdamArgs& a, cudaStream_t stream) {
   const int grid = (a.n_params + 255) / 256;

@@ -43,10 +43,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     item0 += n_hi;
   }
 
+  griddep_launch_dependents();      // nothing here is launched as a programmatic dependent of wgrad; harmless
   for (int i = tid; i < kWgOnesBytes / 2; i += kWgThreads) ones[i] = __float2half(1.0f);
   fence_proxy_async_smem();
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) WG_TRACE(0);
+  griddep_wait();                   // the last dgrad GEMM (and every kernel before it) complete: the images are final
 
   for (int my = 0; my < n_my; ++my) {
   const int item = item0 + my;
@@ -252,8 +254,7 @@ cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  wgrad_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(a);
-  return cudaGetLastError();
+  return launch_dependent(wgrad_kernel, dim3(grid), dim3(kWgThreads), kWgSmem, stream, a);
 }
 
 }  // namespace inr

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) wire_first_kernel(const __grid_constant__
   __shared__ float sW[kWP * 3], sB[kWP];
   const WireModel& M = a.m;
   const int tile = blockIdx.x, tid = threadIdx.x;
+  griddep_launch_dependents();       // the first layer GEMM may set up (barriers, TMEM) while this kernel runs
   for (int i = tid; i < kWP * 3; i += 256) sW[i] = (i / 3) < M.c ? a.params[M.w_off[0] + i] : 0.f;
   for (int i = tid; i < kWP; i += 256) sB[i] = i < M.c ? a.params[M.b_off[0] + i] : 0.f;
   if (tile == 0 && tid == 0 && blockIdx.y == 0 && a.step_counter) *a.step_counter += 1;
@@ -141,6 +142,8 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
   // 4 threads per row, each reduces 6 of the 24 feature groups (independent 16-byte loads in flight), then one combines
   const int tile = blockIdx.x, row = threadIdx.x & (kTileM - 1), part = threadIdx.x >> 7, lane = row & 31, q = row >> 5;
   const int L = M.depth + 1;
+  griddep_launch_dependents();
+  griddep_wait();                    // the last layer GEMM's partial sums are complete
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const int grow = tile * kTileM + row;
   const bool valid = grow < a.bs;
@@ -246,12 +249,14 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
   const WireModel& M = a.m;
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int L = M.depth + 1;
+  griddep_launch_dependents();
   for (int i = tid; i < kMaxOut * kWP; i += 256) {
     const int o = i / kWP, j = i % kWP;
     const bool ok = o < M.out_f && j < M.c;
     sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
     sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
   }
+  griddep_wait();                    // weights above do not change inside a step; scalars and images below do
   __syncthreads();
   const float* sc = reinterpret_cast<const float*>(a.ws + a.w.scal);
   const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
@@ -318,8 +323,7 @@ cudaError_t launch_wire_first(const WireAuxArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_wire_last(const WireAuxArgs& a, cudaStream_t st) {
-  wire_last_kernel<<<a.w.n_tiles, 512, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_dependent(wire_last_kernel, dim3(a.w.n_tiles), dim3(512), 0, st, a);
 }
 cudaError_t launch_wire_scalars(const WireAuxArgs& a, cudaStream_t st) {
   wire_scalars_kernel<<<1, 256, 0, st>>>(a);
@@ -330,8 +334,7 @@ cudaError_t launch_wire_dout_amax(const WireAuxArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_wire_blast(const WireAuxArgs& a, cudaStream_t st) {
-  wire_blast_kernel<<<dim3(a.w.n_tiles, kWAuxSplit), 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_dependent(wire_blast_kernel, dim3(a.w.n_tiles, kWAuxSplit), dim3(256), 0, st, a);
 }
 
 }  // namespace inr

@@ -50,6 +50,7 @@ __device__ void wire_pack_hidden(const WireModel& M, uint8_t* wpack, int l, int 
 __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ WireAdamArgs a) {
   __shared__ float s_c[4];
   const WireModel& M = a.m;
+  griddep_wait();                    // split-K partials of wgrad complete
   if (threadIdx.x == 0) {
     const float* sc = a.scal;
     s_c[2] = sc ? sc[SC_INV_SCALE] : 1.f;
@@ -180,8 +181,7 @@ __global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_consta
 }
 
 cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st) {
-  wire_adam_kernel<<<(a.m.n_params + 255) / 256, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_dependent(wire_adam_kernel, dim3((a.m.n_params + 255) / 256), dim3(256), 0, st, a);
 }
 cudaError_t launch_wire_adam_flat(const WireAdamArgs& a, cudaStream_t st) {
   const int per_cta = a.peer.n_ranks > 0 ? 1024 : 256;
