@@ -522,9 +522,9 @@ def main():
     reset_cursor()
     prof = eng.profile_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], reps=100 if bs <= 25000 else 20,
                             out=out_buf)
-    # WIRE: first, depth fwd GEMMs, last (+ step scalars in its last CTA), blast, depth dgrad GEMMs, wgrad, Adam;
-    # WIRE2D keeps the separate scalars launch
-    n_launch = (2 * wl["net"]["network_depth"] + (5 if wl["model"] == "WIRE" else 6)) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
+    # WIRE: first, ONE chained launch of the depth forward GEMMs, last (+ step scalars in its last CTA), blast, ONE chained
+    # launch of the depth dgrad GEMMs, wgrad, Adam = 7; WIRE2D launches its layers one by one and keeps the scalars kernel
+    n_launch = (7 if wl["model"] == "WIRE" else 2 * wl["net"]["network_depth"] + 6) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
     kern_ms = prof["forward_layer_gemms"] / wl["net"]["network_depth"] if wire else prof["forward"]
     kern_flop = (wl["fwd_flop_per_coord"] / wl["net"]["network_depth"] if wire else wl["fwd_flop_per_coord"]) * bs
     fwd_tflops = kern_flop / (kern_ms * 1e-3) / 1e12
@@ -611,9 +611,11 @@ def main():
                                     if dp else f"independent fit per GPU x{world}, no collective")),
                    "launch": graph_mode,
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
-                   "step": (f"{n_launch} kernels: first layer, {wl['net']['network_depth']} layer GEMMs (3-pass split fp16 + complex Gabor epilogue), "
+                   "step": (f"{n_launch} kernels: first layer, {wl['net']['network_depth']} layer GEMMs (3-pass split fp16 + complex Gabor epilogue"
+                            f"{'; one chained persistent launch, tiles handed from layer to layer' if wl['model'] == 'WIRE' else ''}), "
                             f"final layer + loss{' + step scalars (last CTA)' if wl['model'] == 'WIRE' else ', scalars'}, final-layer backward, "
-                            f"{wl['net']['network_depth']} dgrad layer GEMMs, split-K wgrad, complex Adam + repack") if wire else
+                            f"{wl['net']['network_depth']} dgrad layer GEMMs{' (one chained launch)' if wl['model'] == 'WIRE' else ''}, split-K wgrad, "
+                            "complex Adam + repack") if wire else
                            (f"{n_launch} kernels: encoding, |mu|^2, 9 x (envelope GEMM + stage GEMM), head + loss, TV, scalars, top stage, "
                             "8 dgrad stage GEMMs, split-K wgrad, d mu / d gamma, Adam + repack") if mfn else
                            "4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",

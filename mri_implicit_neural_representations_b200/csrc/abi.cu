@@ -568,6 +568,8 @@ static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
   w.part = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
   w.g = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
   w.outacc = o; o += align_up(static_cast<uint64_t>(T) * kWOutParts * kTileM * 16, 1024);   // partial outputs of the final linear
+  w.flags_fwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * T * 4, 1024);          // layer-chain hand-over counters
+  w.flags_bwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * T * 4, 1024);
   const uint64_t img = static_cast<uint64_t>(T) * kTileM * 2 * M.P * 2;            // H images: [hr | hi]
   const uint64_t zimg = img * M.nlin;                                              // pre-activation / gradient images
   for (int l = 1; l <= M.depth + 1; ++l) { w.hhi[l] = o; o += img; w.hlo[l] = o; o += img; }
@@ -612,17 +614,22 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(wire2d fwd)");
   }
-  for (int l = 1; l <= M.depth && M.nlin == 1; ++l) {
+  if (M.nlin == 1) {       // all hidden layers as ONE chained launch (tile hand-over through w.flags_fwd, zeroed by wire_first)
     LGemmArgs g{};
-    g.seg[0].a_hi = W + w.hhi[l]; g.seg[0].a_lo = W + w.hlo[l];
-    g.seg[0].b_hi = wp + M.wf_hi[l]; g.seg[0].b_lo = wp + M.wf_lo[l];
     g.seg[0].a_tile_bytes = kWTileBytes; g.seg[0].k_stages = kW2 / kStageK; g.seg[0].acc_col = 0; g.n_seg = 1; g.nt = kWNT;
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 3; g.mode = LG_WIRE_FWD;
-    g.bias = params + M.b_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.train = train;
-    g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
-    if (l == M.depth) {       // the final linear rides in this layer's epilogue (partial sums per row; out_f <= 2, depth >= 1)
-      g.last_w = params + M.w_off[M.depth + 1]; g.out_part = reinterpret_cast<float*>(W + w.outacc); g.out_f = M.out_f;
-      g.out_lo = nullptr;     // H_lo of the last hidden layer had one reader, the final linear
+    g.sigma = M.sigma; g.c_valid = M.c; g.train = train; g.out_f = M.out_f;
+    g.chain_len = M.depth; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_fwd);
+    for (int l = 1; l <= M.depth; ++l) {
+      LGemmLayer& c = g.chain[l - 1];
+      c.a_hi = W + w.hhi[l]; c.a_lo = W + w.hlo[l];
+      c.b_hi = wp + M.wf_hi[l]; c.b_lo = wp + M.wf_lo[l];
+      c.bias = params + M.b_off[l]; c.omega = M.omega_hidden;
+      c.out_hi = W + w.hhi[l + 1]; c.out_lo = W + w.hlo[l + 1]; c.out_ab = W + w.ab[l];
+      if (l == M.depth) {     // the final linear rides in this layer's epilogue (partial sums per row; out_f <= 2, depth >= 1)
+        c.last_w = params + M.w_off[M.depth + 1]; c.out_part = reinterpret_cast<float*>(W + w.outacc);
+        c.out_lo = nullptr;   // H_lo of the last hidden layer had one reader, the final linear
+      }
     }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(fwd)");
@@ -662,15 +669,21 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(wire2d dgrad)");
   }
-  for (int l = M.depth; l >= 1 && M.nlin == 1; --l) {      // dL/dh_{l-1} = dZ_l * conj-block(W_l), then the Gabor derivative of layer l-1
-    LGemmArgs g{};
-    g.seg[0].a_hi = W + w.dz[l]; g.seg[0].b_hi = wp + M.wd_hi[l];
+  if (M.nlin == 1) {      // dL/dh_{l-1} = dZ_l * conj-block(W_l), then the Gabor derivative of layer l-1: layers depth .. 1 as ONE
+    LGemmArgs g{};        // chained launch (tile hand-over through w.flags_bwd, zeroed by wire_blast)
     g.seg[0].a_tile_bytes = kWTileBytes; g.seg[0].k_stages = kW2 / kStageK; g.seg[0].acc_col = 0; g.n_seg = 1; g.nt = kWNT;
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 1; g.mode = LG_WIRE_DGRAD;
-    g.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c;
-    g.real_first = (l - 1 == 0) ? 1 : 0;
-    g.in_y = W + w.hhi[l]; g.in_ab = W + w.ab[l - 1]; g.out_dz = W + w.dz[l - 1];
-    g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = l; g.dst_layer = l - 1;
+    g.sigma = M.sigma; g.c_valid = M.c;
+    g.scal = reinterpret_cast<const float*>(W + w.scal);
+    g.chain_len = M.depth; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_bwd);
+    for (int l = M.depth; l >= 1; --l) {
+      LGemmLayer& c = g.chain[M.depth - l];
+      c.a_hi = W + w.dz[l]; c.b_hi = wp + M.wd_hi[l];
+      c.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden;
+      c.real_first = (l - 1 == 0) ? 1 : 0;
+      c.in_y = W + w.hhi[l]; c.in_ab = W + w.ab[l - 1]; c.out_dz = W + w.dz[l - 1];
+      c.src_layer = l; c.dst_layer = l - 1;
+    }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(dgrad)");
   }

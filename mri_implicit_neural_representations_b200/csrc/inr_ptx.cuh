@@ -70,6 +70,26 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {     // nev
   return v;
 }
 
+// ---------------------------------------------------------------- device-scope flags (tile hand-over between CTAs of one grid)
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded like mbar_wait: a broken dependency traps after ~4 s instead of hanging the box.
+__device__ __forceinline__ void flag_wait_ge(const unsigned int* p, unsigned int want) {
+  if (ld_acquire_gpu(p) >= want) return;
+  const uint64_t t0 = global_ns();
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(p) < want) {
+    __nanosleep(64);
+    if ((++spins & 0xFF) == 0 && global_ns() - t0 > 4000000000ull) { asm volatile("trap;"); }
+  }
+}
+// generic-proxy accesses (here: the acquire above, after another SM's global stores) -> this thread's later async-proxy
+// operations (bulk TMA reads of that data)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {   // generic-proxy smem writes -> async proxy (UMMA/TMA) readers
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

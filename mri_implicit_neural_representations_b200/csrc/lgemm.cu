@@ -4,6 +4,10 @@
 // accumulators ping-pong between work items so the epilogue of item i overlaps the MMAs of item i+1.  Persistent
 // CTAs (one per SM) walk the items.
 //
+// The WIRE modes run the GEMMs of all hidden layers as one launch (LGemmArgs::chain): items are ordered layer-major,
+// dealt round-robin to the CTAs, and item (layer, tile, *) starts once both N-blocks of (layer - 1, tile) have been
+// stored (per-(layer, tile) counters in global memory).
+//
 // Epilogues:
 //   LG_WIRE_FWD   : complex Gabor wavelet  y = exp(j w z - |s z|^2),  z = a + jb = acc + bias
 //                   (reference src/models/networks.py:199-204) -> fp16 hi/lo operand images of the next layer plus
@@ -55,13 +59,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 template <int PASSES, int MODE, int KSTEPS>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_ba[512], s_bb[512];     // WIRE: bias re / im (192 used);  MFN: b_i / phi_i (width <= 512)
+  constexpr bool kChain = MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD;
+  constexpr int kBiasFloats = MODE == LG_WIRE_FWD ? kWMaxDepth * kWP : 512;
+  __shared__ float s_ba[kBiasFloats], s_bb[kBiasFloats];   // WIRE_FWD: bias re / im per chain layer;  MFN: b_i / phi_i (width <= 512)
   __shared__ float4 s_lw[MODE == LG_WIRE_FWD ? kWP : 1];   // WIRE_FWD: final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_items = a.n_tiles * a.n_nblocks;
+  const int per_layer = a.n_tiles * a.n_nblocks;           // items of one layer
+  const int n_layers = kChain ? a.chain_len : 1;
+  const int n_items = per_layer * n_layers;
   // A ring slot holds KSTEPS consecutive K=16 steps of every operand (a K=32 stage image is two contiguous halves):
   // few steps per slot = deeper ring of smaller copies, many = fewer barrier round trips for the single producer / MMA threads
   const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 32 * KSTEPS;    // B part of a slot: KSTEPS x (nt rows x 16 K x 2 B)
@@ -80,19 +88,24 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   if (tid == 0) {
     LG_TRACE(0);
     for (int i = 0; i < kLgMaxSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads); mbar_init(&stored[i], kLgComputeThreads); }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   griddep_wait();
   if (MODE == LG_WIRE_FWD) {
+    for (int i = tid; i < n_layers * kWP; i += kLgThreads) {
+      const int j = i % kWP;
+      const float* bias = a.chain[i / kWP].bias;
+      s_ba[i] = j < a.c_valid ? bias[2 * j] : 0.f;
+      s_bb[i] = j < a.c_valid ? bias[2 * j + 1] : 0.f;
+    }
+    const float* last_w = a.chain[n_layers - 1].last_w;
     for (int j = tid; j < kWP; j += kLgThreads) {
-      s_ba[j] = j < a.c_valid ? a.bias[2 * j] : 0.f;
-      s_bb[j] = j < a.c_valid ? a.bias[2 * j + 1] : 0.f;
       float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.last_w && j < a.c_valid) {
-        lw.x = a.last_w[2 * j]; lw.y = a.last_w[2 * j + 1];
-        if (a.out_f > 1) { lw.z = a.last_w[2 * (a.c_valid + j)]; lw.w = a.last_w[2 * (a.c_valid + j) + 1]; }
+      if (last_w && j < a.c_valid) {
+        lw.x = last_w[2 * j]; lw.y = last_w[2 * j + 1];
+        if (a.out_f > 1) { lw.z = last_w[2 * (a.c_valid + j)]; lw.w = last_w[2 * (a.c_valid + j) + 1]; }
       }
       s_lw[j] = lw;
     }
@@ -126,14 +139,24 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     if (lane == 0) {
       uint32_t slot = 0, ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
+        const int layer = item / per_layer, rem = item - layer * per_layer;
+        const int tile = rem / a.n_nblocks, nb = rem % a.n_nblocks;
+        if (kChain && layer > 0) {
+          // the A images of this tile are what the previous layer's items (tile, 0 .. n_nblocks-1) stored
+          if (!(a.dbg & 8)) flag_wait_ge(a.chain_flags + static_cast<size_t>(layer - 1) * a.n_tiles + tile, static_cast<unsigned int>(a.n_nblocks));
+          if (!(a.dbg & 4)) fence_proxy_async_global();
+        }
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
           const int n_it = S.k_stages * 2 / KSTEPS;
-          const uint8_t* ah = S.a_hi + static_cast<size_t>(tile) * S.a_tile_bytes;
-          const uint8_t* al = PASSES == 3 ? S.a_lo + static_cast<size_t>(tile) * S.a_tile_bytes : nullptr;
-          const uint8_t* bh = S.b_hi + static_cast<size_t>(nb) * n_it * b_bytes;
-          const uint8_t* bl = PASSES == 3 ? S.b_lo + static_cast<size_t>(nb) * n_it * b_bytes : nullptr;
+          const uint8_t* a_hi = kChain ? a.chain[layer].a_hi : S.a_hi;
+          const uint8_t* a_lo = kChain ? a.chain[layer].a_lo : S.a_lo;
+          const uint8_t* b_hi = kChain ? a.chain[layer].b_hi : S.b_hi;
+          const uint8_t* b_lo = kChain ? a.chain[layer].b_lo : S.b_lo;
+          const uint8_t* ah = a_hi + static_cast<size_t>(tile) * S.a_tile_bytes;
+          const uint8_t* al = PASSES == 3 ? a_lo + static_cast<size_t>(tile) * S.a_tile_bytes : nullptr;
+          const uint8_t* bh = b_hi + static_cast<size_t>(nb) * n_it * b_bytes;
+          const uint8_t* bl = PASSES == 3 ? b_lo + static_cast<size_t>(nb) * n_it * b_bytes : nullptr;
           for (int s = 0; s < n_it; ++s) {
             mbar_wait(&empty[slot], ph ^ 1);
             if (a.dbg & 2) { mbar_arrive(&full[slot]); if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; } continue; }
@@ -195,22 +218,56 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         LG_TRACE(2 + 3 * n_done);
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ publisher (layer chains): hands finished tiles to the next layer
+    // The epilogue threads arrive on stored[ab] once their stores of an item are issued (release at CTA scope); this one
+    // thread then makes them visible device-wide (fence, cumulative over what it acquired) and bumps the (layer, tile)
+    // counter the next layer's producers poll -- the store drain is waited out here, off the epilogue's critical path.
+    if (kChain && n_layers > 1 && lane == 0) {
+      uint32_t n_done = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        const int layer = item / per_layer, rem = item - layer * per_layer;
+        mbar_wait(&stored[n_done & 1], (n_done >> 1) & 1);
+        if (layer + 1 < n_layers) {
+          __threadfence();
+          atomicAdd(a.chain_flags + static_cast<size_t>(layer) * a.n_tiles + rem / a.n_nblocks, 1u);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue warps (16)
     const int q = warp & 3, sub = (warp - 4) >> 2, row = q * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
-    const float w = a.omega, s2 = a.sigma * a.sigma;
+    const float s2 = a.sigma * a.sigma;
     const bool dgrad = MODE == LG_WIRE_DGRAD || MODE == LG_MFN_DGRAD || MODE == LG_W2D_DGRAD;
     // per-layer power-of-two gradient scales (WIRE's gradient norm grows ~10x per layer towards the input; one global
     // loss scale would saturate the fp16 images of the lower layers)
     float ratio = 1.f, amax = 0.f, s_dst = 1.f;
-    if (dgrad) {
+    if (dgrad && !kChain) {
       s_dst = a.scal[SC_LAYER_SCALE + a.dst_layer];
       ratio = s_dst / a.scal[SC_LAYER_SCALE + a.src_layer];
     }
+    // amax of the stored (scaled) values -> next step's scale of that layer; order-independent
+    auto flush_amax = [&](int dst_layer) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+      if (lane == 0 && amax > 0.f && isfinite(amax))
+        atomicMax(reinterpret_cast<unsigned int*>(const_cast<float*>(a.scal)) + SC_LAYER_AMAX + dst_layer, __float_as_uint(amax));
+      amax = 0.f;
+    };
+    int cur_layer = -1;
     uint32_t n_done = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-      const int tile = item / a.n_nblocks, nb = item % a.n_nblocks;
+      const int layer = item / per_layer, rem = item - layer * per_layer;
+      const int tile = rem / a.n_nblocks, nb = rem % a.n_nblocks;
+      const LGemmLayer& Ly = a.chain[kChain ? layer : 0];
+      if (MODE == LG_WIRE_DGRAD && layer != cur_layer) {     // a CTA's items are layer-major: one flush per layer
+        if (cur_layer >= 0) flush_amax(a.chain[cur_layer].dst_layer);
+        cur_layer = layer;
+        s_dst = a.scal[SC_LAYER_SCALE + Ly.dst_layer];
+        ratio = s_dst / a.scal[SC_LAYER_SCALE + Ly.src_layer];
+      }
+      const float w = kChain ? Ly.omega : a.omega;
       const uint32_t ab = n_done & 1, use = n_done >> 1;
       const uint32_t acc = tmem + t_lane + ab * 256;
       if (MODE == LG_W2D_FWD) {
@@ -301,9 +358,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             const int f0 = kWFeatPerBlock * nb + 24 * sub + 8 * i;
             const size_t off_r = img + static_cast<size_t>(f0 >> 3) * 2048;
             const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;
-            pre[i][0] = ld_global_nc_v4(a.in_y + off_r); pre[i][1] = ld_global_nc_v4(a.in_y + off_i);
-            pre[i][2] = ld_global_nc_v4(a.in_ab + off_r);
-            pre[i][3] = a.real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(a.in_ab + off_i);
+            pre[i][0] = ld_global_nc_v4(Ly.in_y + off_r); pre[i][1] = ld_global_nc_v4(Ly.in_y + off_i);
+            pre[i][2] = ld_global_nc_v4(Ly.in_ab + off_r);
+            pre[i][3] = Ly.real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(Ly.in_ab + off_i);
           }
         }
         mbar_wait(&acc_full[ab], use & 1);
@@ -324,7 +381,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             float yr[8], yi[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float za = va[e] + s_ba[f0 + e], zb = vb[e] + s_bb[f0 + e];
+              const float za = va[e] + s_ba[layer * kWP + f0 + e], zb = vb[e] + s_bb[layer * kWP + f0 + e];
               va[e] = za; vb[e] = zb;
               const float mag = __expf(-w * zb - s2 * (za * za + zb * zb));
               const float ang = w * za;
@@ -332,7 +389,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               yr[e] = live ? mag * fast_cos(ang) : 0.f;
               yi[e] = live ? mag * fast_sin(ang) : 0.f;
             }
-            if (MODE == LG_WIRE_FWD && a.out_part) {       // features in ascending order: fixed summation order
+            if (MODE == LG_WIRE_FWD && Ly.out_part) {       // features in ascending order: fixed summation order
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float4 lw = s_lw[f0 + e];            // same address in every lane: broadcast
@@ -345,13 +402,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             split_h2(yr[4], yr[5], rh.z, rl.z); split_h2(yr[6], yr[7], rh.w, rl.w);
             split_h2(yi[0], yi[1], ih.x, il.x); split_h2(yi[2], yi[3], ih.y, il.y);
             split_h2(yi[4], yi[5], ih.z, il.z); split_h2(yi[6], yi[7], ih.w, il.w);
-            st_global_v4(a.out_hi + off_r, rh); st_global_v4(a.out_hi + off_i, ih);
-            if (a.out_lo) {       // null for the last hidden layer: nothing reads its lo image (the final linear rode along above)
-              st_global_v4(a.out_lo + off_r, rl); st_global_v4(a.out_lo + off_i, il);
+            st_global_v4(Ly.out_hi + off_r, rh); st_global_v4(Ly.out_hi + off_i, ih);
+            if (Ly.out_lo) {       // null for the last hidden layer: nothing reads its lo image (the final linear rode along above)
+              st_global_v4(Ly.out_lo + off_r, rl); st_global_v4(Ly.out_lo + off_i, il);
             }
             if (a.train) {
-              st_global_v4(a.out_ab + off_r, pack8(va));
-              st_global_v4(a.out_ab + off_i, pack8(vb));
+              st_global_v4(Ly.out_ab + off_r, pack8(va));
+              st_global_v4(Ly.out_ab + off_i, pack8(vb));
             }
           } else {
             const uint4 yr4 = pre[i][0], yi4 = pre[i][1], a4 = pre[i][2], b4 = pre[i][3];
@@ -365,15 +422,15 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               const float P = va[e] * yr[e] + vb[e] * yi[e];
               const float Q = va[e] * yi[e] - vb[e] * yr[e];
               da[e] = ratio * (-2.f * s2 * za[e] * P - w * Q);
-              db[e] = a.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * P);
+              db[e] = Ly.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * P);
               amax = fmaxf(amax, fmaxf(fabsf(da[e]), fabsf(db[e])));
             }
-            st_global_v4(a.out_dz + off_r, pack8(da));
-            st_global_v4(a.out_dz + off_i, pack8(db));
+            st_global_v4(Ly.out_dz + off_r, pack8(da));
+            st_global_v4(Ly.out_dz + off_i, pack8(db));
           }
         }
-        if (MODE == LG_WIRE_FWD && a.out_part)
-          reinterpret_cast<float4*>(a.out_part)[(static_cast<size_t>(tile) * kWOutParts + nb * 4 + sub) * kTileM + row] =
+        if (MODE == LG_WIRE_FWD && Ly.out_part)
+          reinterpret_cast<float4*>(Ly.out_part)[(static_cast<size_t>(tile) * kWOutParts + nb * 4 + sub) * kTileM + row] =
               make_float4(o0, o1, 0.f, 0.f);
       } else {
         // ---------------- MFN stages: nt = 128 columns per N-block, this warp owns 32 of them (4 steps of 8)
@@ -468,12 +525,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       if (tid == 128) LG_TRACE(4 + 3 * n_done);
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
+      if (kChain && n_layers > 1) mbar_arrive(&stored[ab]);     // this thread's stores of the item are issued (publisher warp below)
     }
-    if (dgrad) {      // amax of the stored (scaled) values -> next step's scale; order-independent
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
-      if (lane == 0 && amax > 0.f && isfinite(amax))
-        atomicMax(reinterpret_cast<unsigned int*>(const_cast<float*>(a.scal)) + SC_LAYER_AMAX + a.dst_layer, __float_as_uint(amax));
+    if (MODE == LG_WIRE_DGRAD) {
+      if (cur_layer >= 0) flush_amax(a.chain[cur_layer].dst_layer);
+    } else if (dgrad) {
+      flush_amax(a.dst_layer);
     }
   }
   tc_fence_before();
@@ -490,7 +547,10 @@ bool pdl_enabled() {
 }
 
 cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
-  const int items = a.n_tiles * a.n_nblocks;
+  const bool chain = a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD;
+  if (chain && (a.chain_len < 1 || a.chain_len > kWMaxDepth || (a.chain_len > 1 && !a.chain_flags))) return cudaErrorInvalidValue;
+  const int items = a.n_tiles * a.n_nblocks * (chain ? a.chain_len : 1);
+  // chained layers wait on each other's tiles: every CTA must be resident, i.e. never more CTAs than SMs
   const int grid = items < n_sm ? items : n_sm;
   if (grid <= 0) return cudaSuccess;
   const int expect_passes = (a.mode == LG_WIRE_FWD || a.mode == LG_W2D_FWD) ? 3 : 1;

@@ -45,7 +45,27 @@ struct LGemmSeg {
   int acc_col;              // column offset inside the item's accumulator
 };
 
+// WIRE layer chains: the forward (or dgrad) GEMMs of ALL hidden layers run as ONE persistent launch.  Items are ordered
+// layer-major and dealt round-robin to the CTAs; item (layer, tile, *) needs the images both N-blocks of (layer - 1, tile)
+// wrote, which is tracked per (layer, tile) by a counter in global memory (release by the writing epilogue, acquire by
+// the reading producer thread).  A layer's tail no longer idles a third of the SMs: they move on to the next layer.
+struct LGemmLayer {
+  const uint8_t* a_hi; const uint8_t* a_lo;     // A operand images of this layer (forward: H_hi / H_lo; dgrad: dZ)
+  const uint8_t* b_hi; const uint8_t* b_lo;     // packed weights
+  const float* bias;                            // forward: complex bias, interleaved
+  uint8_t* out_hi; uint8_t* out_lo; uint8_t* out_ab;   // forward outputs (out_lo null: not stored)
+  const uint8_t* in_y; const uint8_t* in_ab;    // dgrad epilogue inputs
+  uint8_t* out_dz;                              // dgrad output
+  float omega;                                  // Gabor constant of the layer whose activation / derivative is evaluated
+  int real_first;                               // dgrad: the target layer is the real first layer
+  int src_layer, dst_layer;                     // dgrad: scale indices
+  const float* last_w; float* out_part;         // forward, last layer of the chain: final-linear partial sums (or null)
+};
+
 struct LGemmArgs {
+  LGemmLayer chain[kWMaxDepth];   // WIRE_FWD / WIRE_DGRAD only
+  int chain_len;                  // layers in the chain (>= 1 for the WIRE modes)
+  unsigned int* chain_flags;      // [chain_len][n_tiles] finished N-blocks per (layer, tile), zeroed before the launch
   LGemmSeg seg[2];
   int n_seg;                // 1 (WIRE) or 2 (MFN stage: filter GEMM + linear GEMM)
   int nt;                   // UMMA N of every segment; n_seg * nt <= 256 (two 256-column accumulators ping-pong)
@@ -117,6 +137,7 @@ struct WireModel {
 struct WireWorkspace {
   uint64_t hhi[kWMaxDepth + 2], hlo[kWMaxDepth + 2], ab[kWMaxDepth + 1], dz[kWMaxDepth + 1];
   uint64_t dzlast, ximg, outacc, g, part, scal, gpart, total;
+  uint64_t flags_fwd, flags_bwd;      // uint32 [kWMaxDepth][n_tiles] each: layer-chain hand-over counters
   int n_tiles, n_split;
 };
 
