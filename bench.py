@@ -66,6 +66,9 @@ MULTISCALE_WORKLOAD = dict(
     loss_opts={"hdr_eps": 1e-2, "hdr_ff_sigma": 1.0, "hdr_ff_factor": 0.0}, radii=[0.35, 0.7, 1.05, 5.0],
     flop_per_coord=19423232)
 DEFAULT_WORKLOAD = "wire_kspace_hdr_bs25000"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE chained forward GEMM launch (4 layers) at bs 25000, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_lgemm_chain_summary.md)
+WIRE_CHAIN_DRAM_BYTES = 199.6e6
 SLICE = (15, 320, 320)                 # fastMRI-knee-shaped: 15 coils x 320 x 320 after the reference's crop
 LR = 5e-4
 
@@ -525,8 +528,12 @@ def main():
     # WIRE: first, ONE chained launch of the depth forward GEMMs, last (+ step scalars in its last CTA), blast, ONE chained
     # launch of the depth dgrad GEMMs, wgrad, Adam = 7; WIRE2D launches its layers one by one and keeps the scalars kernel
     n_launch = (7 if wl["model"] == "WIRE" else 2 * wl["net"]["network_depth"] + 6) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
-    kern_ms = prof["forward_layer_gemms"] / wl["net"]["network_depth"] if wire else prof["forward"]
-    kern_flop = (wl["fwd_flop_per_coord"] / wl["net"]["network_depth"] if wire else wl["fwd_flop_per_coord"]) * bs
+    # roofline kernel.  WIRE: the chained forward GEMM launch (all hidden layers in one persistent launch), timed by the
+    # events around it; WIRE2D: the average of its per-layer forward GEMM launches; SIREN / FFN: the fused forward kernel
+    chained = wl["model"] == "WIRE"
+    n_gemm_launches = 1 if chained else wl["net"]["network_depth"]
+    kern_ms = prof["forward_layer_gemms"] / n_gemm_launches if wire else prof["forward"]
+    kern_flop = (wl["fwd_flop_per_coord"] / n_gemm_launches if wire else wl["fwd_flop_per_coord"]) * bs
     fwd_tflops = kern_flop / (kern_ms * 1e-3) / 1e12
     step_tflops = wl["flop_per_coord"] * bs / (ms / args.steps * 1e-3) / 1e12
 
@@ -629,13 +636,15 @@ def main():
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"],
                      # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture
-                     "traffic": (44.3e6 if wl["model"] == "WIRE" and bs == 25000 else None),
-                     "traffic_source": ("profiles/r01_ncu_lgemm_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, cold L2)"
-                                        if wl["model"] == "WIRE" and bs == 25000 else None),
-                     "kernel": (f"lgemm_kernel ({wl['model']} forward layer GEMM + Gabor epilogue; one of {wl['net']['network_depth']} launches/step)" if wire else
+                     "traffic": (WIRE_CHAIN_DRAM_BYTES if chained and bs == 25000 else None),
+                     "traffic_source": ("profiles/r01_ncu_lgemm_chain_summary.md (dram__bytes_read.sum + dram__bytes_write.sum of the chained launch, cold L2)"
+                                        if chained and bs == 25000 else None),
+                     "kernel": ((f"lgemm_kernel<3,1,2> (WIRE forward: the {wl['net']['network_depth']} hidden-layer GEMMs + Gabor epilogues as one chained persistent launch)"
+                                 if chained else
+                                 f"lgemm_kernel ({wl['model']} forward layer GEMM + Gabor epilogue; one of {wl['net']['network_depth']} launches/step)") if wire else
                                 ("forward phase (encoding + 18 lgemm launches + head/loss + TV)" if mfn else "chain_fwd_kernel<SIN>")),
                      "kernel_ms": kern_ms,
-                     "issued_tflops": (wl["issued_fwd_flop_per_coord"] / wl["net"]["network_depth"] * bs / (kern_ms * 1e-3) / 1e12) if wire else None,
+                     "issued_tflops": (wl["issued_fwd_flop_per_coord"] / n_gemm_launches * bs / (kern_ms * 1e-3) / 1e12) if wire else None,
                      "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['source']})",
                      "step_tflops": step_tflops, "step_frac_of_sustained": step_tflops / peaks["tflops_sustained"],
                      "kernels_ms": prof},

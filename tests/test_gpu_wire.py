@@ -211,3 +211,40 @@ def test_wire_unsupported_shapes_fail_loudly(inr):
     for bad in ({"network_output_size": 3}, {"network_depth": 0}, {"network_input_size": 2}, {"network_width": 512}):
         with pytest.raises(Exception):
             inr.Plan("WIRE", dict(base, **bad), enc)
+
+
+def test_wire_full_size_batch_chained_layers(inr):
+    """BASELINE config 2 size (bs 25 000 = 196 row tiles, more items than SMs): the hidden layers run as one chained launch
+    in which tiles are handed from layer to layer between CTAs.  (a) rows sampled from all over the batch match the fp64
+    oracle as well as the fp32 oracle does, (b) the fused loss matches the oracle's, (c) two engines fed the same three
+    steps end bit-identical (a tile read before it was complete would show up here)."""
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup("wire_hdr")
+    bs = 25000
+    g = torch.Generator().manual_seed(9)
+    c = torch.rand(bs, 3, generator=g) * 2 - 1
+    y = torch.randn(bs, 2, generator=g) * 0.05
+    m = (torch.arange(bs) % 2 == 0)
+    engs = []
+    for _ in range(2):
+        plan = inr.Plan(model_kind, net, enc_cfg)
+        eng = inr.ChainEngine(plan, max_batch=bs, lr=G.LR)
+        eng.load_tensors(list(sd.values()))
+        engs.append(eng)
+    out = engs[0].forward(c.cuda(), train=False).cpu()
+    rows = torch.cat([torch.arange(0, 300), torch.randint(300, bs - 300, (400,), generator=g), torch.arange(bs - 300, bs)])
+    sd64 = to64(sd)
+    o32 = O.model_forward(model_kind, sd, c[rows], net)
+    o64 = O.model_forward(model_kind, sd64, c[rows].double(), net)
+    assert rel(out[rows], o64) <= 4 * rel(o32, o64) + 1e-4
+    val, _ = loss_and_grad(loss_kind, opts, out[m], y[m], c)      # HDR is ill-conditioned: teacher-forced on the engine's output
+    cd, yd, md = c.cuda(), y.cuda(), m.to(torch.uint8).cuda()
+    for eng in engs:
+        for _ in range(3):
+            eng.train_step(loss_kind, cd, yd, bs, mask=md, loss_opts=opts)
+    torch.cuda.synchronize()
+    assert torch.equal(engs[0].params, engs[1].params)
+    assert torch.isfinite(engs[0].params).all()
+    eng = inr.ChainEngine(inr.Plan(model_kind, net, enc_cfg), max_batch=bs, lr=G.LR)
+    eng.load_tensors(list(sd.values()))
+    eng.train_step(loss_kind, cd, yd, bs, mask=md, loss_opts=opts)
+    assert abs(float(eng.loss_out) - float(val)) <= 2e-3 * abs(float(val)), (float(eng.loss_out), float(val))
