@@ -109,7 +109,8 @@ struct LGemmArgs {
   // every epilogue thread adds its 24 features' share of out[row][o] = sum_f Re(y_f W[o][f]) and stores the partial sum
   const float* last_w;      // final-layer weight [out_f][c] complex, interleaved (re, im), or null
   float* out_part;          // [tile][kWOutParts][128 rows] float4 partial outputs (fixed slots: no atomics), or null
-  int dbg;                  // debug (INR_LGEMM_DBG): bit 0 skip MMAs, bit 1 skip operand copies (timing experiments only)
+  int dbg;                  // debug (INR_LGEMM_DBG), timing experiments only, results are wrong: bit 0 skip MMAs, bit 1 skip operand copies,
+                            // bit 2 skip the proxy fence and bit 3 the hand-over wait of chained layers
   unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)
 };
 
