@@ -59,7 +59,10 @@ struct LGemmLayer {
   float omega;                                  // Gabor constant of the layer whose activation / derivative is evaluated
   int real_first;                               // dgrad: the target layer is the real first layer
   int src_layer, dst_layer;                     // dgrad: scale indices
-  const float* last_w; float* out_part;         // forward, last layer of the chain: final-linear partial sums (or null)
+  // forward, last layer of the chain: the final complex linear (reference networks.py:247-258, real part) rides along --
+  // every epilogue thread adds its 24 features' share of out[row][o] = sum_f Re(y_f W[o][f]) into a fixed slot
+  const float* last_w;      // final-layer weight [out_f][c] complex, interleaved (re, im), or null
+  float* out_part;          // [tile][kWOutParts][128 rows] float4 partial outputs (no atomics), or null
 };
 
 struct LGemmArgs {
@@ -105,10 +108,6 @@ struct LGemmArgs {
   const float* gamma;       // GABOR_E: gamma_j [width]
   const float* mn;          // GABOR_E: |mu_j|^2 [width]
   uint32_t feat_tile_bytes; // bytes of one 128-row image of the epilogue's feature images (MFN: 128 * width * 2)
-  // WIRE_FWD of the last hidden layer: the final complex linear (reference networks.py:247-258, real part) rides along --
-  // every epilogue thread adds its 24 features' share of out[row][o] = sum_f Re(y_f W[o][f]) and stores the partial sum
-  const float* last_w;      // final-layer weight [out_f][c] complex, interleaved (re, im), or null
-  float* out_part;          // [tile][kWOutParts][128 rows] float4 partial outputs (fixed slots: no atomics), or null
   int dbg;                  // debug (INR_LGEMM_DBG), timing experiments only, results are wrong: bit 0 skip MMAs, bit 1 skip operand copies,
                             // bit 2 skip the proxy fence and bit 3 the hand-over wait of chained layers
   unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)
