@@ -526,11 +526,11 @@ def main():
     prof = eng.profile_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"], reps=100 if bs <= 25000 else 20,
                             out=out_buf)
     # WIRE: first, ONE chained launch of the depth forward GEMMs, last (+ step scalars in its last CTA), blast, ONE chained
-    # launch of the depth dgrad GEMMs, wgrad, Adam = 7; WIRE2D launches its layers one by one and keeps the scalars kernel
-    n_launch = (7 if wl["model"] == "WIRE" else 2 * wl["net"]["network_depth"] + 6) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
+    # launch of the depth dgrad GEMMs, wgrad, Adam = 7; WIRE2D the same plus its separate scalars kernel = 8
+    n_launch = (7 if wl["model"] == "WIRE" else 8) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
     # roofline kernel.  WIRE: the chained forward GEMM launch (all hidden layers in one persistent launch), timed by the
     # events around it; WIRE2D: the average of its per-layer forward GEMM launches; SIREN / FFN: the fused forward kernel
-    chained = wl["model"] == "WIRE"
+    chained = wire
     n_gemm_launches = 1 if chained else wl["net"]["network_depth"]
     kern_ms = prof["forward_layer_gemms"] / n_gemm_launches if wire else prof["forward"]
     kern_flop = (wl["fwd_flop_per_coord"] / n_gemm_launches if wire else wl["fwd_flop_per_coord"]) * bs
@@ -619,9 +619,9 @@ def main():
                    "launch": graph_mode,
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
                    "step": (f"{n_launch} kernels: first layer, {wl['net']['network_depth']} layer GEMMs (3-pass split fp16 + complex Gabor epilogue"
-                            f"{'; one chained persistent launch, tiles handed from layer to layer' if wl['model'] == 'WIRE' else ''}), "
+                            "; one chained persistent launch, tiles handed from layer to layer), "
                             f"final layer + loss{' + step scalars (last CTA)' if wl['model'] == 'WIRE' else ', scalars'}, final-layer backward, "
-                            f"{wl['net']['network_depth']} dgrad layer GEMMs{' (one chained launch)' if wl['model'] == 'WIRE' else ''}, split-K wgrad, "
+                            f"{wl['net']['network_depth']} dgrad layer GEMMs (one chained launch), split-K wgrad, "
                             "complex Adam + repack") if wire else
                            (f"{n_launch} kernels: encoding, |mu|^2, 9 x (envelope GEMM + stage GEMM), head + loss, TV, scalars, top stage, "
                             "8 dgrad stage GEMMs, split-K wgrad, d mu / d gamma, Adam + repack") if mfn else
@@ -636,12 +636,10 @@ def main():
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"],
                      # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture
-                     "traffic": (WIRE_CHAIN_DRAM_BYTES if chained and bs == 25000 else None),
+                     "traffic": (WIRE_CHAIN_DRAM_BYTES if wl["model"] == "WIRE" and bs == 25000 else None),
                      "traffic_source": ("profiles/r01_ncu_lgemm_chain_summary.md (dram__bytes_read.sum + dram__bytes_write.sum of the chained launch, cold L2)"
-                                        if chained and bs == 25000 else None),
-                     "kernel": ((f"lgemm_kernel<3,1,2> (WIRE forward: the {wl['net']['network_depth']} hidden-layer GEMMs + Gabor epilogues as one chained persistent launch)"
-                                 if chained else
-                                 f"lgemm_kernel ({wl['model']} forward layer GEMM + Gabor epilogue; one of {wl['net']['network_depth']} launches/step)") if wire else
+                                        if wl["model"] == "WIRE" and bs == 25000 else None),
+                     "kernel": (f"lgemm_kernel ({wl['model']} forward: the {wl['net']['network_depth']} hidden-layer GEMMs + Gabor epilogues as one chained persistent launch)" if wire else
                                 ("forward phase (encoding + 18 lgemm launches + head/loss + TV)" if mfn else "chain_fwd_kernel<SIN>")),
                      "kernel_ms": kern_ms,
                      "issued_tflops": (wl["issued_fwd_flop_per_coord"] / n_gemm_launches * bs / (kern_ms * 1e-3) / 1e12) if wire else None,

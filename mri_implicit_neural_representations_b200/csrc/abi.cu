@@ -602,15 +602,19 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
   cudaError_t e = M.nlin == 2 ? launch_w2d_first(x, st) : launch_wire_first(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "wire_first_kernel");
   if (gemm_ev) cudaEventRecord(gemm_ev[0], st);
-  for (int l = 1; l <= M.depth && M.nlin == 2; ++l) {
+  if (M.nlin == 2) {       // WIRE2D: all hidden layers as ONE chained launch (hand-over through w.flags_fwd, zeroed by w2d_first)
     LGemmArgs g{};
-    g.seg[0].a_hi = W + w.hhi[l]; g.seg[0].a_lo = W + w.hlo[l];
-    g.seg[0].b_hi = wp + M.wf_hi[l]; g.seg[0].b_lo = wp + M.wf_lo[l];
     g.seg[0].a_tile_bytes = static_cast<uint32_t>(kTileM) * 2 * M.P * 2; g.seg[0].k_stages = 2 * M.P / kStageK; g.seg[0].acc_col = 0;
     g.n_seg = 1; g.nt = kW2dNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.P / kW2dFwdFeat; g.passes = 3; g.mode = LG_W2D_FWD;
-    g.bias = params + M.b_off[l]; g.bias2 = params + M.vb_off[l]; g.omega = M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c;
-    g.p2 = M.P; g.train = train;
-    g.out_hi = W + w.hhi[l + 1]; g.out_lo = W + w.hlo[l + 1]; g.out_ab = W + w.ab[l];
+    g.sigma = M.sigma; g.c_valid = M.c; g.p2 = M.P; g.train = train;
+    g.chain_len = M.depth; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_fwd);
+    for (int l = 1; l <= M.depth; ++l) {
+      LGemmLayer& c = g.chain[l - 1];
+      c.a_hi = W + w.hhi[l]; c.a_lo = W + w.hlo[l];
+      c.b_hi = wp + M.wf_hi[l]; c.b_lo = wp + M.wf_lo[l];
+      c.bias = params + M.b_off[l]; c.bias2 = params + M.vb_off[l]; c.omega = M.omega_hidden;
+      c.out_hi = W + w.hhi[l + 1]; c.out_lo = W + w.hlo[l + 1]; c.out_ab = W + w.ab[l];
+    }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(wire2d fwd)");
   }
@@ -657,15 +661,21 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
   }
   e = M.nlin == 2 ? launch_w2d_blast(x, st) : launch_wire_blast(x, st);
   if (e != cudaSuccess) return cuda_fail(e, "wire_blast_kernel");
-  for (int l = M.depth; l >= 1 && M.nlin == 2; --l) {
+  if (M.nlin == 2) {      // WIRE2D dgrad, layers depth .. 1 as ONE chained launch (hand-over through w.flags_bwd, zeroed by w2d_blast)
     LGemmArgs g{};
-    g.seg[0].a_hi = W + w.dz[l]; g.seg[0].b_hi = wp + M.wd_hi[l];
     g.seg[0].a_tile_bytes = static_cast<uint32_t>(kTileM) * 4 * M.P * 2; g.seg[0].k_stages = 4 * M.P / kStageK; g.seg[0].acc_col = 0;
     g.n_seg = 1; g.nt = kW2dNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.P / kW2dBwdFeat; g.passes = 1; g.mode = LG_W2D_DGRAD;
-    g.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden; g.sigma = M.sigma; g.c_valid = M.c; g.p2 = M.P;
-    g.real_first = (l - 1 == 0) ? 1 : 0;
-    g.in_y = W + w.hhi[l]; g.in_ab = W + w.ab[l - 1]; g.out_dz = W + w.dz[l - 1];
-    g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = l; g.dst_layer = l - 1;
+    g.sigma = M.sigma; g.c_valid = M.c; g.p2 = M.P;
+    g.scal = reinterpret_cast<const float*>(W + w.scal);
+    g.chain_len = M.depth; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_bwd);
+    for (int l = M.depth; l >= 1; --l) {
+      LGemmLayer& c = g.chain[M.depth - l];
+      c.a_hi = W + w.dz[l]; c.b_hi = wp + M.wd_hi[l];
+      c.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden;
+      c.real_first = (l - 1 == 0) ? 1 : 0;
+      c.in_y = W + w.hhi[l]; c.in_ab = W + w.ab[l - 1]; c.out_dz = W + w.dz[l - 1];
+      c.src_layer = l; c.dst_layer = l - 1;
+    }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(wire2d dgrad)");
   }

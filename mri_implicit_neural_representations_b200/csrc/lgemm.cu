@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2];
   __shared__ uint32_t tmem_base_s;
-  constexpr bool kChain = MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD;
+  constexpr bool kChain = MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD || MODE == LG_W2D_FWD || MODE == LG_W2D_DGRAD;
   constexpr int kBiasFloats = MODE == LG_WIRE_FWD ? kWMaxDepth * kWP : 512;
   __shared__ float s_ba[kBiasFloats], s_bb[kBiasFloats];   // WIRE_FWD: bias re / im per chain layer;  MFN: b_i / phi_i (width <= 512)
   __shared__ float4 s_lw[MODE == LG_WIRE_FWD ? kWP : 1];   // WIRE_FWD: final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
@@ -114,12 +114,6 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     for (int j = tid; j < width; j += kLgThreads) {
       s_ba[j] = a.bias ? a.bias[j] : 0.f;
       s_bb[j] = a.phi[j];
-    }
-  } else if (MODE == LG_W2D_FWD) {
-    for (int j = tid; j < kW2dMaxP; j += kLgThreads) {
-      const bool ok = j < a.c_valid;
-      s_ba[j] = ok ? a.bias[2 * j] : 0.f;          s_bb[j] = ok ? a.bias[2 * j + 1] : 0.f;
-      s_ba[kW2dMaxP + j] = ok ? a.bias2[2 * j] : 0.f; s_bb[kW2dMaxP + j] = ok ? a.bias2[2 * j + 1] : 0.f;
     }
   } else if (MODE == LG_GABOR_E) {
     const int width = a.n_nblocks * a.nt;
@@ -261,7 +255,19 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       const int layer = item / per_layer, rem = item - layer * per_layer;
       const int tile = rem / a.n_nblocks, nb = rem % a.n_nblocks;
       const LGemmLayer& Ly = a.chain[kChain ? layer : 0];
-      if (MODE == LG_WIRE_DGRAD && layer != cur_layer) {     // a CTA's items are layer-major: one flush per layer
+      if (MODE == LG_W2D_FWD && layer != cur_layer) {
+        // WIRE2D: both complex biases of a layer fill the staging arrays, so they are re-staged when the CTA moves on to
+        // the next layer (its items are layer-major); the barriers keep slower epilogue warps off the old values
+        named_bar_sync(2, kLgComputeThreads);
+        for (int j = tid - 128; j < kW2dMaxP; j += kLgComputeThreads) {
+          const bool ok = j < a.c_valid;
+          s_ba[j] = ok ? Ly.bias[2 * j] : 0.f;             s_bb[j] = ok ? Ly.bias[2 * j + 1] : 0.f;
+          s_ba[kW2dMaxP + j] = ok ? Ly.bias2[2 * j] : 0.f; s_bb[kW2dMaxP + j] = ok ? Ly.bias2[2 * j + 1] : 0.f;
+        }
+        named_bar_sync(2, kLgComputeThreads);
+        cur_layer = layer;
+      }
+      if ((MODE == LG_WIRE_DGRAD || MODE == LG_W2D_DGRAD) && layer != cur_layer) {     // a CTA's items are layer-major: one flush per layer
         if (cur_layer >= 0) flush_amax(a.chain[cur_layer].dst_layer);
         cur_layer = layer;
         s_dst = a.scal[SC_LAYER_SCALE + Ly.dst_layer];
@@ -302,12 +308,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           split_h2(yi[0], yi[1], ih.x, il.x); split_h2(yi[2], yi[3], ih.y, il.y);
           split_h2(yi[4], yi[5], ih.z, il.z); split_h2(yi[6], yi[7], ih.w, il.w);
           const size_t off_r = himg + static_cast<size_t>(f0 >> 3) * 2048, off_i = himg + static_cast<size_t>(pg + (f0 >> 3)) * 2048;
-          st_global_v4(a.out_hi + off_r, rh); st_global_v4(a.out_hi + off_i, ih);
-          st_global_v4(a.out_lo + off_r, rl); st_global_v4(a.out_lo + off_i, il);
+          st_global_v4(Ly.out_hi + off_r, rh); st_global_v4(Ly.out_hi + off_i, ih);
+          st_global_v4(Ly.out_lo + off_r, rl); st_global_v4(Ly.out_lo + off_i, il);
           if (a.train) {
             const size_t z0 = zimg + static_cast<size_t>(f0 >> 3) * 2048, zs = static_cast<size_t>(pg) * 2048;
-            st_global_v4(a.out_ab + z0, pack8(va)); st_global_v4(a.out_ab + z0 + zs, pack8(vb));
-            st_global_v4(a.out_ab + z0 + 2 * zs, pack8(vc)); st_global_v4(a.out_ab + z0 + 3 * zs, pack8(vd));
+            st_global_v4(Ly.out_ab + z0, pack8(va)); st_global_v4(Ly.out_ab + z0 + zs, pack8(vb));
+            st_global_v4(Ly.out_ab + z0 + 2 * zs, pack8(vc)); st_global_v4(Ly.out_ab + z0 + 3 * zs, pack8(vd));
           }
         }
       } else if (MODE == LG_W2D_DGRAD) {
@@ -324,11 +330,11 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           const int c0 = 32 * sub + 8 * i;
           const int f0 = kW2dBwdFeat * nb + c0;
           const size_t z0 = zimg + static_cast<size_t>(f0 >> 3) * 2048;
-          const uint4 yr4 = ld_global_nc_v4(a.in_y + himg + static_cast<size_t>(f0 >> 3) * 2048);
-          const uint4 yi4 = ld_global_nc_v4(a.in_y + himg + static_cast<size_t>(pg + (f0 >> 3)) * 2048);
-          const uint4 a4 = ld_global_nc_v4(a.in_ab + z0), c4 = ld_global_nc_v4(a.in_ab + z0 + 2 * zs);
+          const uint4 yr4 = ld_global_nc_v4(Ly.in_y + himg + static_cast<size_t>(f0 >> 3) * 2048);
+          const uint4 yi4 = ld_global_nc_v4(Ly.in_y + himg + static_cast<size_t>(pg + (f0 >> 3)) * 2048);
+          const uint4 a4 = ld_global_nc_v4(Ly.in_ab + z0), c4 = ld_global_nc_v4(Ly.in_ab + z0 + 2 * zs);
           uint4 b4 = make_uint4(0u, 0u, 0u, 0u), d4 = make_uint4(0u, 0u, 0u, 0u);
-          if (!a.real_first) { b4 = ld_global_nc_v4(a.in_ab + z0 + zs); d4 = ld_global_nc_v4(a.in_ab + z0 + 3 * zs); }
+          if (!Ly.real_first) { b4 = ld_global_nc_v4(Ly.in_ab + z0 + zs); d4 = ld_global_nc_v4(Ly.in_ab + z0 + 3 * zs); }
           float gr[8], gi[8];
           tmem_ld8(acc + c0, gr);
           tmem_ld8(acc + 128 + c0, gi);
@@ -340,13 +346,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             const float Pp = gr[e] * yr[e] + gi[e] * yi[e];
             const float Q = gr[e] * yi[e] - gi[e] * yr[e];
             da[e] = ratio * (-2.f * s2 * za[e] * Pp - w * Q);
-            db[e] = a.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * Pp);
+            db[e] = Ly.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * Pp);
             dc[e] = ratio * (-2.f * s2 * zc[e] * Pp);
-            dd[e] = a.real_first ? 0.f : ratio * (-2.f * s2 * zd[e] * Pp);
+            dd[e] = Ly.real_first ? 0.f : ratio * (-2.f * s2 * zd[e] * Pp);
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(da[e]), fabsf(db[e])), fmaxf(fabsf(dc[e]), fabsf(dd[e]))));
           }
-          st_global_v4(a.out_dz + z0, pack8(da)); st_global_v4(a.out_dz + z0 + zs, pack8(db));
-          st_global_v4(a.out_dz + z0 + 2 * zs, pack8(dc)); st_global_v4(a.out_dz + z0 + 3 * zs, pack8(dd));
+          st_global_v4(Ly.out_dz + z0, pack8(da)); st_global_v4(Ly.out_dz + z0 + zs, pack8(db));
+          st_global_v4(Ly.out_dz + z0 + 2 * zs, pack8(dc)); st_global_v4(Ly.out_dz + z0 + 3 * zs, pack8(dd));
         }
       } else if (MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) {
         const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16;
@@ -527,7 +533,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       mbar_arrive(&acc_empty[ab]);
       if (kChain && n_layers > 1) mbar_arrive(&stored[ab]);     // this thread's stores of the item are issued (publisher warp below)
     }
-    if (MODE == LG_WIRE_DGRAD) {
+    if (MODE == LG_WIRE_DGRAD || MODE == LG_W2D_DGRAD) {
       if (cur_layer >= 0) flush_amax(a.chain[cur_layer].dst_layer);
     } else if (dgrad) {
       flush_amax(a.dst_layer);
@@ -547,7 +553,7 @@ bool pdl_enabled() {
 }
 
 cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
-  const bool chain = a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD;
+  const bool chain = a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD || a.mode == LG_W2D_FWD || a.mode == LG_W2D_DGRAD;
   if (chain && (a.chain_len < 1 || a.chain_len > kWMaxDepth || (a.chain_len > 1 && !a.chain_flags))) return cudaErrorInvalidValue;
   const int items = a.n_tiles * a.n_nblocks * (chain ? a.chain_len : 1);
   // chained layers wait on each other's tiles: every CTA must be resident, i.e. never more CTAs than SMs

@@ -53,6 +53,7 @@ struct LGemmLayer {
   const uint8_t* a_hi; const uint8_t* a_lo;     // A operand images of this layer (forward: H_hi / H_lo; dgrad: dZ)
   const uint8_t* b_hi; const uint8_t* b_lo;     // packed weights
   const float* bias;                            // forward: complex bias, interleaved
+  const float* bias2;                           // WIRE2D forward: complex bias of scale_orth, interleaved
   uint8_t* out_hi; uint8_t* out_lo; uint8_t* out_ab;   // forward outputs (out_lo null: not stored)
   const uint8_t* in_y; const uint8_t* in_ab;    // dgrad epilogue inputs
   uint8_t* out_dz;                              // dgrad output
@@ -66,7 +67,7 @@ struct LGemmLayer {
 };
 
 struct LGemmArgs {
-  LGemmLayer chain[kWMaxDepth];   // WIRE_FWD / WIRE_DGRAD only
+  LGemmLayer chain[kWMaxDepth];   // WIRE / WIRE2D forward and dgrad only
   int chain_len;                  // layers in the chain (>= 1 for the WIRE modes)
   unsigned int* chain_flags;      // [chain_len][n_tiles] finished N-blocks per (layer, tile), zeroed before the launch
   LGemmSeg seg[2];

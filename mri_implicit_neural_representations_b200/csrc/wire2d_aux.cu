@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(256) w2d_first_kernel(const __grid_constant__ 
     sVB[i] = i < M.c ? a.params[M.vb_off[0] + i] : 0.f;
   }
   if (tile == 0 && tid == 0 && blockIdx.y == 0 && a.step_counter) *a.step_counter += 1;
+  if (blockIdx.y == 0 && tid < kWMaxDepth)      // hand-over counters of the chained forward GEMMs (lgemm.cu) start at zero
+    reinterpret_cast<unsigned int*>(a.ws + a.w.flags_fwd)[tid * a.w.n_tiles + tile] = 0u;
   __syncthreads();
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const float w = M.omega_first, s2 = M.sigma * M.sigma;
@@ -213,6 +215,8 @@ __global__ void __launch_bounds__(256) w2d_blast_kernel(const __grid_constant__ 
     sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
   }
   __syncthreads();
+  if (blockIdx.y == 0 && tid < kWMaxDepth)      // hand-over counters of the chained dgrad GEMMs start at zero
+    reinterpret_cast<unsigned int*>(a.ws + a.w.flags_bwd)[tid * a.w.n_tiles + tile] = 0u;
   const float* sc = reinterpret_cast<const float*>(a.ws + a.w.scal);
   const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
   const float ratio = sc[SC_LAYER_SCALE + M.depth] / S;
