@@ -111,7 +111,7 @@ __device__ __forceinline__ void peer_gather(const PeerArgs& P, size_t base, size
 }
 
 // Fixed-order block reduction of the tile partials -> step scalars sc[kScalars] in shared memory (all threads of the
-// block must call this; works for any blockDim.x that is a multiple of 32, up to 1024).  Bit-reproducible.
+// block must call this; works for any blockDim.x that is a multiple of 32 from 64 up to 1024).  Bit-reproducible.
 //   loss value, masked row count m, HDR filter mean, normalisers cA / cB (training-loop weights of
 //   src/train.py:178-182 folded in), power-of-two gradient scale S = 2^floor(log2(256 / amax)), Adam bias corrections.
 __device__ inline void reduce_step_scalars(const float* part_g, int n_tiles, const LossDesc& loss, int out_f, int bs_k,
@@ -131,6 +131,18 @@ __device__ inline void reduce_step_scalars(const float* part_g, int n_tiles, con
     m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, off)); m5 = fmaxf(m5, __shfl_xor_sync(0xffffffffu, m5, off));
   }
   if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; part[warp][3] = s3; part[warp][4] = m4; part[warp][5] = m5; }
+  if (tid == 32) {
+    // Adam bias corrections (fp64 pow, a microsecond on this machine): nobody in this kernel needs them, so a thread of
+    // its own computes them next to the reduction instead of at the end of thread 0's serial path (blockDim.x >= 64)
+    float step_size = 0.f, bc2_sqrt = 1.f;
+    if (scal_global && hyper && step) {     // torch.optim.Adam: step_size = lr / (1 - b1^t), denom uses sqrt(1 - b2^t)
+      const double t = static_cast<double>(*step);
+      step_size = static_cast<float>(static_cast<double>(hyper[0]) / (1.0 - pow(static_cast<double>(hyper[1]), t)));
+      bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(hyper[2]), t)));
+    }
+    sc[SC_STEP_SIZE] = step_size; sc[SC_BC2_SQRT] = bc2_sqrt;
+    if (scal_global) { scal_global[SC_STEP_SIZE] = step_size; scal_global[SC_BC2_SQRT] = bc2_sqrt; }
+  }
   __syncthreads();
   if (tid == 0) {
     float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
@@ -165,15 +177,8 @@ __device__ inline void reduce_step_scalars(const float* part_g, int n_tiles, con
     }
     sc[SC_LOSS] = lossv; sc[SC_SCALE] = S; sc[SC_CA] = cA; sc[SC_CB] = cB; sc[SC_COUNT] = cnt; sc[SC_FMEAN] = fmean;
     sc[SC_REG] = reg; sc[SC_INV_SCALE] = 1.f / S;
-    sc[SC_STEP_SIZE] = 0.f; sc[SC_BC2_SQRT] = 1.f;
-    if (scal_global) {
-      if (hyper && step) {     // torch.optim.Adam: step_size = lr / (1 - b1^t), denom uses sqrt(1 - b2^t)
-        const double t = static_cast<double>(*step);
-        sc[SC_STEP_SIZE] = static_cast<float>(static_cast<double>(hyper[0]) / (1.0 - pow(static_cast<double>(hyper[1]), t)));
-        sc[SC_BC2_SQRT] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(hyper[2]), t)));
-      }
-      for (int i = 0; i < 10; ++i) scal_global[i] = sc[i];
-    }
+    if (scal_global)
+      for (int i = 0; i < 8; ++i) scal_global[i] = sc[i];
   }
   __syncthreads();
 }
