@@ -89,6 +89,10 @@ static void build_wgrad_sched(inr_plan* p) {
   p->n_heavy = static_cast<int>(p->order.size());
   p->n_light = static_cast<int>(light.size());
   p->group = lmax ? std::min<int>(8, std::max<int>(1, static_cast<int>(cmax / lmax))) : 1;
+  // More units than SMs (the MFN models: split factor 1, several waves of CTAs): the hardware's CTA scheduler already
+  // balances the waves, and a CTA that works off several whole-batch items in turn would only lengthen the tail
+  // (GaborNet config 3: 5.42 -> 5.90 ms per step with grouping).  Group only when everything fits one wave.
+  if (static_cast<int>(p->units.size()) > p->n_sm) p->group = 1;
   p->order.insert(p->order.end(), light.begin(), light.end());
 }
 
