@@ -90,12 +90,24 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
     const SegDesc& sg = a.seg[si];
     if (sg.frozen) { if (a.grads) a.grads[p] = 0.f; continue; }
     const float* gp = a.gpart;
+    // everything this parameter needs is requested up front, so the latencies of the master weight, the two moments,
+    // the layer scale and the split partials overlap instead of queueing behind each other
+    float w = a.params[p];
+    const float m_old = a.do_adam ? a.m[p] : 0.f, v_old = a.do_adam ? a.v[p] : 0.f;
+    const float gscale = (sg.scale_slot >= 0 && a.scal) ? 1.f / a.scal[sg.scale_slot] : s_c[2];
     float g = 0.f;
     if (peer) g = s_g[j * 256 + threadIdx.x];
     else if (sg.gfin_off >= 0 && a.gfin) g = a.gfin[sg.gfin_off + (p - sg.off)];
     else
-    {   // split partials in split order (bit-reproducible); four loads in flight per thread instead of one
+    {   // split partials in split order (bit-reproducible); eight loads in flight per thread
       int sp = 0;
+      for (; sp + 8 <= a.n_split; sp += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = gp[static_cast<size_t>(sp + q) * a.gstride + p];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g += v[q];
+      }
       for (; sp + 4 <= a.n_split; sp += 4) {
         const float v0 = gp[static_cast<size_t>(sp) * a.gstride + p], v1 = gp[static_cast<size_t>(sp + 1) * a.gstride + p];
         const float v2 = gp[static_cast<size_t>(sp + 2) * a.gstride + p], v3 = gp[static_cast<size_t>(sp + 3) * a.gstride + p];
@@ -103,8 +115,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
       }
       for (; sp < a.n_split; ++sp) g += gp[static_cast<size_t>(sp) * a.gstride + p];
     }
-    g *= (sg.scale_slot >= 0 && a.scal) ? 1.f / a.scal[sg.scale_slot] : s_c[2];
-    float w = a.params[p];
+    g *= gscale;
     if (a.do_adam) {
       const float l1 = a.hyper[5], l2 = a.hyper[6];
       if (l1 != 0.f) g += l1 * (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f));
@@ -114,8 +125,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
     if (!a.do_adam) continue;
     const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
     if (wd != 0.f) g = fmaf(wd, w, g);
-    const float m = b1 * a.m[p] + (1.f - b1) * g;
-    const float v = b2 * a.v[p] + (1.f - b2) * g * g;
+    const float m = b1 * m_old + (1.f - b1) * g;
+    const float v = b2 * v_old + (1.f - b2) * g * g;
     a.m[p] = m; a.v[p] = v;
     const float denom = sqrtf(v) / s_c[1] + eps;
     w = w - s_c[0] * (m / denom);

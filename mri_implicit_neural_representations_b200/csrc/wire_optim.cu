@@ -80,7 +80,10 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
     if (p >= M.b_off[l] && p < M.b_off[l] + bn) { layer = l; kind = 1; idx = p - M.b_off[l]; break; }
   }
   if (kind == 2 || kind < 0) { if (a.grads && !a.pack_only) a.grads[p] = 0.f; return; }
+  // master weight, moments and the layer's gradient scale are requested before the gather so that their latencies overlap it
   float w = a.params[p];
+  const bool upd = !a.pack_only && a.do_adam;
+  const float m_old = upd ? a.mom[p] : 0.f, v_old = upd ? a.var[p] : 0.f;
   int o = 0, i = 0, comp = 0;
   if (layer >= 1 && layer < L && kind == 0) { const int e = idx >> 1; comp = idx & 1; o = e / M.c; i = e % M.c; }
   if (!a.pack_only) {
@@ -116,6 +119,13 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
       const float* G = a.gpart;
       const size_t st = M.gd_floats;
       int sp = 0;
+      for (; sp + 8 <= a.n_split; sp += 8) {      // 16 independent loads in flight
+        float v[8], u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { v[q] = G[(sp + q) * st + i0]; u[q] = i1 >= 0 ? G[(sp + q) * st + i1] : 0.f; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g += sg0 * v[q] + sg1 * u[q];
+      }
       for (; sp + 4 <= a.n_split; sp += 4) {
         float v[4], u[4];
 #pragma unroll
@@ -130,8 +140,8 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
     if (!a.do_adam) return;
     const float b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], wd = a.hyper[4];
     if (wd != 0.f) g = fmaf(wd, w, g);
-    const float m = b1 * a.mom[p] + (1.f - b1) * g;
-    const float v = b2 * a.var[p] + (1.f - b2) * g * g;
+    const float m = b1 * m_old + (1.f - b1) * g;
+    const float v = b2 * v_old + (1.f - b2) * g * g;
     a.mom[p] = m; a.var[p] = v;
     w = w - s_c[0] * (m / (sqrtf(v) / s_c[1] + eps));
     a.params[p] = w;
