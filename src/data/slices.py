@@ -7,6 +7,7 @@ fastMRI .h5 files are read when h5py and the file exist; otherwise a synthetic f
 from __future__ import annotations
 
 import glob
+import math
 import os
 import warnings
 from typing import Optional
@@ -69,8 +70,26 @@ class SliceDataset:
                 k = k / mx[:, None, None, None]
             elif normalization == "abs_max":
                 k = k / torch.view_as_complex(k.contiguous()).abs().max()
-            elif normalization in ("max", "gaussian_blur"):
+            elif normalization == "max":
                 k = k / k.abs().max()
+            elif normalization == "gaussian_blur":
+                # reference nerp_datasets.py:117-123 + data/utils.py:11-28: max-normalise, then a separable Gaussian
+                # (sigma 0.1, support +-ceil(10 sigma)) over (H, W) of the real and the imaginary plane of every coil
+                k = k / k.abs().max()
+                sigma = 0.1
+                radius = math.ceil(10.0 * sigma)
+                support = torch.arange(-radius, radius + 1, dtype=torch.float, device=k.device)
+                kern = torch.distributions.Normal(loc=0, scale=sigma).log_prob(support).exp_()
+                kern = kern.mul_(1 / kern.sum())
+                planes = k.permute(0, 3, 1, 2).reshape(-1, 1, H, W)            # [C*2, 1, H, W]
+                planes = torch.nn.functional.conv2d(planes, kern.view(1, 1, -1, 1), padding=(radius, 0))
+                planes = torch.nn.functional.conv2d(planes, kern.view(1, 1, 1, -1), padding=(0, radius))
+                k = planes.reshape(C, 2, H, W).permute(0, 2, 3, 1).contiguous()
+            elif normalization == "tonemap":
+                # reference nerp_datasets.py:129-133
+                k = k / (k + 1)
+                k = k / k.max()
+                k = k - k.mean(dim=(1, 2, 3), keepdim=True)
             elif normalization == "max_std":
                 k = k / k.abs().max()
                 k = (k - k.mean()) / k.std()
@@ -100,10 +119,13 @@ class SliceDataset:
 
 class GridOrderLoader:
     """Yields (coords, gt, dist, mask) batches in grid order like the reference's DataLoader(shuffle=False) +
-    collate_inr (src/models/utils.py:47-53,84-99), by slicing -- no per-sample __getitem__."""
+    collate_inr (src/models/utils.py:47-53,84-99), by slicing -- no per-sample __getitem__.
+    `with_mask=False` reproduces MRIDatasetWithDistances.__getitem__ (nerp_datasets.py:391-396), which hands out an
+    empty mask even for an undersampled slice: with distances and per-sample batches the reference's loops therefore run
+    over ALL points (the masked-out ones hold zeros); the per-coil wrapper (:428-441) does pass the mask."""
 
-    def __init__(self, ds: SliceDataset, batch_size: int):
-        self.ds, self.bs = ds, int(batch_size)
+    def __init__(self, ds: SliceDataset, batch_size: int, with_mask: bool = True):
+        self.ds, self.bs, self.with_mask = ds, int(batch_size), bool(with_mask)
 
     def __len__(self):
         return (len(self.ds) + self.bs - 1) // self.bs
@@ -113,7 +135,7 @@ class GridOrderLoader:
         for i in range(0, len(ds), self.bs):
             j = i + self.bs
             dist = ds.dist_to_center[i:j] if ds.dist_to_center is not None else []
-            mask = ds.coords_mask[i:j] if ds.coords_mask is not None else []
+            mask = ds.coords_mask[i:j] if (ds.coords_mask is not None and self.with_mask) else []
             yield ds.coords[i:j], ds.image[i:j], dist, mask
 
 
@@ -131,4 +153,4 @@ def get_data_loader(data, data_root, set, batch_size, transform=True, num_worker
                              device=device)
     C, H, W, _ = full.img_shape
     train_bs = H * W if per_coil else batch_size
-    return full, GridOrderLoader(train, train_bs), GridOrderLoader(full, batch_size)
+    return full, GridOrderLoader(train, train_bs, with_mask=per_coil or not use_d), GridOrderLoader(full, batch_size)

@@ -64,7 +64,7 @@ def _quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
-@pytest.mark.parametrize("norm", ["max", "coil", "abs_max", "max_std", "stand"])
+@pytest.mark.parametrize("norm", ["max", "coil", "abs_max", "max_std", "stand", "gaussian_blur", "tonemap"])
 def test_kspace_normalisations(ref_nd, ours, norm):
     r = _quiet(ref_nd.MRIDataset, data_class="knee", transform=False, sample=0, slice=0, normalization=norm)
     o = _quiet(ours.SliceDataset, "knee", "data", "train", False, 0, 0, False, norm, None, False, (C, H, W))
