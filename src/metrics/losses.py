@@ -82,3 +82,81 @@ def tv_loss(img, weight=0.0001):            # reference :326-343
     w_variance = torch.nn.functional.l1_loss(img[:, :-1, :], img[:, 1:, :])
     h_variance = torch.nn.functional.l1_loss(img[:-1, :, :], img[1:, :, :])
     return weight * (h_variance + w_variance)
+
+
+# ---- losses that stay plain PyTorch on the engine's autograd face: selectable by config like in the
+# ---- reference (`T`, `LSL` in src/train.py, `FFL`), not fused-kernel targets
+class TLoss(torch.nn.Module):               # reference :30-55
+    """Phase-aware complex loss: the cross-product distance |x × y| / |x| where the phases agree to within 90 degrees,
+    a reflected magnitude term where they do not, plus the MSE of the magnitudes."""
+
+    def forward(self, X, Y):
+        x, y = _cplx(X), _cplx(Y)
+        assert x.is_complex() and y.is_complex()
+        mag_x, mag_y = x.abs(), y.abs()
+        ploss = (x.real * y.imag - x.imag * y.real).abs() / (mag_x + 1e-8)
+        opposed = torch.cos(torch.atan2(x.imag, x.real) - torch.atan2(y.imag, y.real)) < 0
+        term = torch.where(opposed, mag_y + (mag_y - ploss), ploss)
+        return (term + torch.nn.functional.mse_loss(mag_x, mag_y)).mean()
+
+
+class CenterLoss(torch.nn.Module):          # reference :141-201 (what `loss: LSL` means in src/train.py:87-88)
+    """0.1 * log-space error + 0.9 * (the same error + the HDR filter regulariser, evaluated per point here, not as the
+    [bs, m] outer product of HDRLoss_FF) + 0.1 * a ranking term that compares magnitude differences between two radial
+    bands on `min_sample` randomly paired points (torch.randperm: the value depends on the global RNG state)."""
+    N_BANDS = 2
+
+    def __init__(self, config):
+        super().__init__()
+        self.sigma, self.eps, self.factor = float(config["hdr_ff_sigma"]), float(config["hdr_eps"]), float(config["hdr_ff_factor"])
+        self.min_sample = int(config["min_sample"])
+
+    def forward(self, input, target, kcoords):
+        d2 = kcoords[..., 1] ** 2 + kcoords[..., 2] ** 2
+        filt = torch.exp(-d2 / (2 * self.sigma ** 2)).unsqueeze(-1)
+        # the reference views (re, im) pairs as complex [m]; the [m, 1] filter then broadcasts the regulariser to [m, m]
+        x, y = _cplx(input), _cplx(target)
+        denom = x.detach().abs() + self.eps
+        err = ((x - y).abs() / denom) ** 2
+        reg = self.factor * ((x - x * filt).abs() / denom) ** 2
+        x_abs, y_abs = x.abs(), y.abs()
+        center = torch.zeros(1, device=x.device)
+        for band in range(1, self.N_BANDS + 1):
+            r_in = (band - 1) / self.N_BANDS or 0.1
+            inner = d2 <= r_in
+            outer = (d2 <= band / self.N_BANDS) & ~inner
+            xi, xo = x_abs[inner], x_abs[outer]
+            n = min(self.min_sample, min(len(xi), len(xo)))
+            if n == 0:
+                continue
+            a = torch.randperm(xi.size(0))[:n]
+            b = torch.randperm(xo.size(0))[:n]
+            center = center + (((y_abs[inner][a] - y_abs[outer][b]) - (xi[a] - xo[b])) ** 2).mean()
+        return 0.1 * err.mean() + 0.9 * (err.mean() + reg.mean()) + 0.1 * center, 0
+
+
+class FocalFrequencyLoss(torch.nn.Module):  # reference :57-119
+    """Squared distance of (re, im) pairs weighted by its own normalised (log-)magnitude.  Returns a 0-d tensor, so the
+    reference's `loss, _ = loss_fn(...)` (src/train.py:179) cannot unpack it -- `loss: FFL` fails there and fails here."""
+
+    def __init__(self, loss_weight=1.0, alpha=1.0, log_matrix=True, batch_matrix=False):
+        super().__init__()
+        self.loss_weight, self.alpha, self.log_matrix, self.batch_matrix = loss_weight, alpha, log_matrix, batch_matrix
+
+    def loss_formulation(self, recon_freq, real_freq, matrix=None):
+        dist = ((recon_freq - real_freq) ** 2)
+        dist = dist[..., 0] + dist[..., 1]
+        if matrix is not None:
+            weight = matrix.detach()
+        else:
+            w = torch.sqrt(dist) ** self.alpha
+            if self.log_matrix:
+                w = torch.log(w + 1.0)
+            w = w / w.max()
+            w = torch.where(torch.isnan(w), torch.zeros_like(w), w)
+            weight = torch.clamp(w, min=0.0, max=1.0).clone().detach()
+        assert weight.min().item() >= 0 and weight.max().item() <= 1, "spectrum weights must lie in [0, 1]"
+        return torch.mean(weight * dist)
+
+    def forward(self, pred, target, matrix=None, **kwargs):
+        return self.loss_formulation(pred, target, matrix) * self.loss_weight

@@ -22,7 +22,8 @@ if _SRC not in sys.path:
 from models.networks import FFN, SIREN, WIRE, Positional_Encoder            # noqa: E402
 from models.mfn import FourierNet, GaborNet, KGaborNet                       # noqa: E402
 from models.regularization import Regularization_L1, Regularization_L2       # noqa: E402
-from metrics.losses import HDRLoss_FF, MSLELoss, TanhL2Loss, tv_loss          # noqa: E402
+from metrics.losses import (CenterLoss, FocalFrequencyLoss, HDRLoss_FF, MSLELoss, TanhL2Loss, TLoss,    # noqa: E402
+                            tv_loss)
 from data.slices import get_data_loader                                      # noqa: E402
 from log_handler.logger import INRLogger                                     # noqa: E402
 from utils import get_config, set_default_configs                            # noqa: E402
@@ -70,6 +71,12 @@ def build_loss(config):
         return HDRLoss_FF(config["loss_opts"])
     if loss == "tanh":
         return TanhL2Loss()
+    if loss == "T":
+        return TLoss()
+    if loss == "LSL":
+        return CenterLoss(config["loss_opts"])     # src/train.py maps LSL to CenterLoss (:87-88), not to LogSpaceLoss
+    if loss == "FFL":
+        return FocalFrequencyLoss()
     return None                                # reference falls through silently (:97-98)
 
 
@@ -143,7 +150,11 @@ def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_write
     has_mask = train_ds.coords_mask is not None
     # the reference reaches tv_loss only inside `if len(mask_coords) != 0` (:172-174) and views the batch as (H, W, 2)
     use_tv = bool(config.get("use_tv", False)) and has_mask
-    fused = (config["loss"] in FUSABLE_LOSSES and enc_ok and (not use_tv or (per_coil and config["loss"] != "HDR")))
+    # `LSL` means CenterLoss in this entry point and in the HP-search trainer (reference src/train.py:87-88,
+    # hp_model_training.py:81-82) -- randperm-based, not a fused-kernel target; the engine's fused log-space loss is what
+    # train_kspace_multiscale.py calls LSL (:113-114)
+    fused = (config["loss"] in FUSABLE_LOSSES and config["loss"] != "LSL" and enc_ok
+             and (not use_tv or (per_coil and config["loss"] != "HDR")))
     trainer = None
     if fused:
         mask = train_ds.coords_mask[:, 0] if has_mask else None
@@ -179,7 +190,7 @@ def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_write
                         train_loss = train_loss + tv_loss(out.view((H, W, 2)))
                     sel = mask_coords.to(device)[:, 0]
                     out, gt = out[sel], gt[sel]
-                if config["loss"] in ["HDR", "tanh"]:
+                if config["loss"] in ["HDR", "LSL", "FFL", "tanh"]:      # reference :178-182 (FFL cannot be unpacked there either)
                     loss, _ = loss_fn(out, gt, kcoords)
                     train_loss = train_loss + loss
                 else:
