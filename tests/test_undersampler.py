@@ -107,3 +107,17 @@ def test_reference_unit_test_properties(ours):
     assert ours.parse_undersampling_argument("none") == ("none", [])
     with pytest.raises(ValueError):
         ours.parse_undersampling_argument("spiral-3")
+
+
+def test_masks_match_golden_from_reference(ours):
+    """tests/golden/undersampler.json was generated from the unmodified reference (oracle/make_golden_undersampler.py);
+    this pin also holds where the reference tree is absent."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_golden_undersampler as MG
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "undersampler.json")))
+
+    def set_rng(u):
+        u.rng = np.random.RandomState(MG.NP_SEED)
+    got = MG.run(ours.Undersampler, set_rng)
+    assert got == gold
