@@ -12,7 +12,12 @@
  *    owns only the immutable plan; nothing allocates or synchronises inside a call except
  *    inr_plan_create / inr_selftest_umma;
  *  - every call is asynchronous on the cudaStream_t passed as `void* stream` (0 = default stream);
- *  - one in-flight step per (plan, workspace).
+ *  - one in-flight step per (plan, workspace);
+ *  - WIRE / WIRE2D: the layer GEMMs of a step run as chained persistent launches whose CTAs hand tiles to each other
+ *    and therefore must all be resident (grid <= SM count).  Steps of DIFFERENT engines must not run concurrently on
+ *    one device (issue them on one stream, or on streams that are ordered against each other): two chained launches
+ *    sharing the SMs could starve each other's unscheduled CTAs.  A dependency that is not met within ~4 s traps
+ *    (CUDA launch error) instead of hanging.
  *
  * Flat parameter buffer: fp32, tensors in reference state_dict order (e.g. model.0.linear.weight [256,512]
  * row-major, model.0.linear.bias [256], ...), see inr_plan_tensor().
