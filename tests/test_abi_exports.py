@@ -56,6 +56,23 @@ def test_workspace_layout_is_consistent(inr):
         assert 1 <= lay["n_split"] <= lay["n_tiles"]
 
 
+def test_wgrad_split_schedule(inr):
+    """The split-K factor comes from the two-class wgrad schedule (abi.cu: build_wgrad_sched / wgrad_splits): heavy
+    (unit, split) items one per CTA, light items two per CTA, everything inside one wave of the device's SMs; models with
+    more units than SMs keep split factor 1.  Pinned for the BASELINE shapes on a 148-SM device (the default without a GPU)."""
+    import torch
+    if torch.cuda.is_available() and torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip("schedule figures are for 148 SMs")
+    wire = inr.Plan("WIRE", {"network_input_size": 3, "network_output_size": 2, "network_depth": 4, "network_width": 256,
+                             "first_omega_0": 30, "hidden_omega_0": 30, "scale": 15}, {"embedding": "none"})
+    assert wire.workspace_layout(25000)["n_split"] == 10        # 12 heavy x 10 + ceil(5 light x 10 / 2) = 145 CTAs
+    assert wire.workspace_layout(300)["n_split"] == 3           # never more splits than row tiles
+    siren = inr.Plan("SIREN", NET, ENC)
+    assert siren.workspace_layout(10000)["n_split"] == 16       # 8 heavy x 16 + ceil(2 light x 16 / 2) = 144 CTAs
+    gabor = inr.Plan("Gabor", {"network_input_size": 512, "network_output_size": 2, "network_depth": 8, "network_width": 512}, ENC)
+    assert gabor.workspace_layout(102400)["n_split"] == 1
+
+
 def test_unsupported_shapes_fail_loudly(inr):
     with pytest.raises(inr.InrError):
         inr.Plan("SIREN", dict(NET, network_width=192), ENC)
