@@ -11,6 +11,11 @@ imported from /root/reference (``oracle/ref_shims.py``) by ``tests/test_oracle_v
 (runs wherever /root/reference exists) and against the committed digests under
 ``tests/golden/`` that ``oracle/make_golden.py`` produced from those reference modules.
 
+Third-party pieces the reference calls (fastmri 0.3.0 fft2c / ifft2c / complex_abs / rss, scikit-image 0.18.1
+structural_similarity) are restated here from the libraries' published definitions; the libraries are not in this
+image, so parity with them is UNPINNED (checked against independent constructions in
+tests/test_third_party_restatements.py).
+
 Reference citations are relative to /root/reference/.
 All functions are dtype-generic (float32 mirrors the reference, float64 is used as a
 tighter yardstick in some tests).
