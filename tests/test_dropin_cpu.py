@@ -123,3 +123,24 @@ def test_hp_search_space_expansion_matches_reference_semantics(src_path):
     exp_f = random.uniform(0.0, 1.0)
     exp_loss = random.choice(["L2", "tanh"])
     assert a == {"lr": exp_lr, "w": exp_w, "f": exp_f, "loss": exp_loss}
+
+
+def test_loss_selection_matches_reference_entry_point(src_path):
+    """src/train.py:81-98 of the reference: L2 / MSLE / T / LSL (-> CenterLoss!) / FFL / L1 / HDR / tanh, anything else
+    falls through silently."""
+    import train
+    opts = {"hdr_ff_sigma": 1, "hdr_eps": 1e-2, "hdr_ff_factor": 0, "min_sample": 10}
+    names = {k: type(train.build_loss({"loss": k, "loss_opts": opts})).__name__
+             for k in ("L2", "MSLE", "T", "LSL", "FFL", "L1", "HDR", "tanh", "nonsense")}
+    assert names == {"L2": "MSELoss", "MSLE": "MSLELoss", "T": "TLoss", "LSL": "CenterLoss", "FFL": "FocalFrequencyLoss",
+                     "L1": "L1Loss", "HDR": "HDRLoss_FF", "tanh": "TanhL2Loss", "nonsense": "NoneType"}
+
+
+def test_ring_entry_point_imports_and_fails_loudly_without_cuda(src_path):
+    import torch
+    from train_variations import train_clustering as T
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        T.training_clustering({"max_epoch": 1, "transform": False, "partition": {"no_models": 2, "no_steps": 8},
+                               "model": "SIREN"}, None, None, None)
