@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: dH_{l-1} = dZ_l * W_l
-    if (lane == 0) {
+    // convergent warp, one elected lane issues (warp-uniform descriptors; see chain_fwd.cu)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, kWidth, false, false);
       uint32_t it = 0, act_use = 0;
       const uint32_t act_s = smem_u32(act), wring_s = smem_u32(wring);
@@ -104,17 +105,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) chain_bwd_kernel(const __grid_
               const uint32_t slot = it % kBwdStages;
               mbar_wait(&w_full[slot], (it / kBwdStages) & 1);
               tc_fence_after();
+              __syncwarp();
               const uint32_t b_base = wring_s + slot * kStageBytes;
+              if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t da = umma_smem_desc(a_base + (s2 * 2 + kk) * 4096, 2048, 128);
-                const uint64_t db = umma_smem_desc(b_base + kk * 8192, 4096, 128);
-                umma_f16(acc, da, db, idesc, (c | s2 | kk) != 0);
+                for (int kk = 0; kk < 2; ++kk) {
+                  const uint64_t da = umma_smem_desc(a_base + (s2 * 2 + kk) * 4096, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_base + kk * 8192, 4096, 128);
+                  umma_f16(acc, da, db, idesc, (c | s2 | kk) != 0);
+                }
+                umma_commit(&w_empty[slot]);
+                if (c == 3 && s2 == 1) umma_commit(&acc_full[l & 1]);
               }
-              umma_commit(&w_empty[slot]);
+              __syncwarp();
             }
           }
-          umma_commit(&acc_full[l & 1]);
         }
       }
     }

@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the pipeline (all lanes poll the barriers) and one elected lane issues, so the descriptors stay
+    // warp-uniform: a single divergent thread paid ~280 cycles per stage + ~50 per MMA (tools/umma_commit2.cu), more than
+    // the 256 tensor cycles of a K = 32 weight stage.
+    {
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, kWidth, false, false);
       uint32_t it = 0, inq = 0, act_use = 0;
       const uint32_t act_s = smem_u32(act), wring_s = smem_u32(wring);
@@ -114,21 +117,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) chain_fwd_kernel(const __grid_
             for (int s2 = 0; s2 < 2; ++s2, ++it) {
               const uint32_t slot = it % kFwdStages;
               mbar_wait(&w_full[slot], (it / kFwdStages) & 1);
-              if (it < 8) INR_TRACE(a, 48 + it);         // MMA thread: first eight weight stages landed
+              if (it < 8 && lane == 0) INR_TRACE(a, 48 + it);         // MMA warp: first eight weight stages landed
               tc_fence_after();
+              __syncwarp();
               const uint32_t b_base = wring_s + slot * kStageBytes;
+              if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t da = umma_smem_desc(a_base + (s2 * 2 + kk) * 4096, 2048, 128);
-                const uint64_t db = umma_smem_desc(b_base + kk * 8192, 4096, 128);
-                umma_f16(acc, da, db, idesc, (c | s2 | kk) != 0);
+                for (int kk = 0; kk < 2; ++kk) {
+                  const uint64_t da = umma_smem_desc(a_base + (s2 * 2 + kk) * 4096, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_base + kk * 8192, 4096, 128);
+                  umma_f16(acc, da, db, idesc, (c | s2 | kk) != 0);
+                }
+                umma_commit(&w_empty[slot]);
+                if (l == 0 && s2 == 1) umma_commit(&in_empty[in_slot]);
+                if (s2 == 1 && c == nchunks - 1) umma_commit(&acc_full[l & 1]);
               }
-              umma_commit(&w_empty[slot]);
+              __syncwarp();
             }
-            if (l == 0) { umma_commit(&in_empty[in_slot]); ++inq; }
+            if (l == 0) ++inq;
           }
-          umma_commit(&acc_full[l & 1]);
-          if (tile == 0) INR_TRACE(a, 40 + l);          // MMA thread: layer l fully issued
+          if (tile == 0 && lane == 0) INR_TRACE(a, 40 + l);          // MMA warp: layer l fully issued
           if (l > 0) ++act_use;
         }
       }

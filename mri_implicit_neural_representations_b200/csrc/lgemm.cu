@@ -56,7 +56,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
 }
 
-template <int PASSES, int MODE, int KSTEPS>
+// PAIR = 1: the CTAs of a cluster of two work on two neighbouring row tiles of the same (layer, N-block) with ONE
+// tcgen05.mma.cta_group::2 stream (M = 256): each CTA streams its own A tile but only HALF of the weight rows, which cuts the
+// operand bytes an SM ingests per flop by 30 % (WIRE: 28 KB instead of 40 KB per ring slot, 7 slots deep instead of 5).
+template <int PASSES, int MODE, int KSTEPS, int PAIR>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2];
@@ -67,12 +70,17 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   __shared__ float4 s_lw[MODE == LG_WIRE_FWD ? kWP : 1];   // WIRE_FWD: final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int per_layer = a.n_tiles * a.n_nblocks;           // items of one layer
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
+  const int cta0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);     // work-item walker of this CTA (pair)
+  const int n_walk = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int n_rowgroups = PAIR ? (a.n_tiles + 1) >> 1 : a.n_tiles;    // a pair item covers tiles 2g and 2g + 1
+  const int per_layer = n_rowgroups * a.n_nblocks;         // items of one layer
   const int n_layers = kChain ? a.chain_len : 1;
   const int n_items = per_layer * n_layers;
   // A ring slot holds KSTEPS consecutive K=16 steps of every operand (a K=32 stage image is two contiguous halves):
   // few steps per slot = deeper ring of smaller copies, many = fewer barrier round trips for the single producer / MMA threads
-  const uint32_t b_bytes = static_cast<uint32_t>(a.nt) * 32 * KSTEPS;    // B part of a slot: KSTEPS x (nt rows x 16 K x 2 B)
+  const uint32_t b_rows = static_cast<uint32_t>(a.nt) >> PAIR;           // weight rows this CTA holds (pair: half of them)
+  const uint32_t b_bytes = b_rows * 32 * KSTEPS;                         // B part of a slot: KSTEPS x (rows x 16 K x 2 B)
   constexpr uint32_t a_bytes = (kWStageABytes / 2) * KSTEPS;
   const uint32_t a_lo_off = a_bytes;
   const uint32_t b_hi_off = PASSES == 3 ? 2 * a_bytes : a_bytes;
@@ -87,11 +95,15 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   griddep_launch_dependents();
   if (tid == 0) {
     LG_TRACE(0);
-    for (int i = 0; i < kLgMaxSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads); mbar_init(&stored[i], kLgComputeThreads); }
+    // pair: the leader's full barrier also takes the peer's "my half of the slot has landed" arrival, its acc_empty the
+    // arrivals of both CTAs' epilogue threads
+    for (int i = 0; i < kLgMaxSlots; ++i) { mbar_init(&full[i], (PAIR && rank == 0) ? 2 : 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads << PAIR); mbar_init(&stored[i], kLgComputeThreads);
+    }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+  if (warp == 2) { if (PAIR) tmem_alloc_pair<512>(&tmem_base_s); else tmem_alloc<512>(&tmem_base_s); }
   griddep_wait();
   if (MODE == LG_WIRE_FWD) {
     for (int i = tid; i < n_layers * kWP; i += kLgThreads) {
@@ -123,22 +135,33 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: the peer's barriers must be initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   if (tid == 0) LG_TRACE(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    if (lane == 0) {
+    // The whole warp walks the ring (all lanes poll the barriers, so the warp stays convergent); lane 0 arms the slot's
+    // barrier, lanes 0 .. 3 issue one bulk copy each.  A single divergent thread spent ~110 cycles per copy and, with four
+    // copies and the waits, more than the 576 tensor cycles of a slot (tools/umma_commit2.cu, in-kernel cycle counters).
+    {
       uint32_t slot = 0, ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const bool tr = a.trace != nullptr;
+      long long c_flag = 0, c_empty = 0, c_issue = 0, tq = 0;
+      const long long tr_c0 = tr ? clock64() : 0;
+      const unsigned long long tr_n0 = tr ? global_ns() : 0;
+      for (int item = cta0; item < n_items; item += n_walk) {
         const int layer = item / per_layer, rem = item - layer * per_layer;
-        const int tile = rem / a.n_nblocks, nb = rem % a.n_nblocks;
-        if (kChain && layer > 0) {
-          // the A images of this tile are what the previous layer's items (tile, 0 .. n_nblocks-1) stored
+        const int tile = PAIR ? 2 * (rem / a.n_nblocks) + static_cast<int>(rank) : rem / a.n_nblocks, nb = rem % a.n_nblocks;
+        const bool phantom = PAIR && tile >= a.n_tiles;       // odd tile count: the last pair's second CTA only lends its B half
+        if (kChain && layer > 0 && !phantom) {
+          // the A images of this tile are what the previous layer's items (tile, 0 .. n_nblocks-1) stored; every lane that
+          // issues copies acquires the counter itself and orders its own async-proxy reads behind it
+          if (tr) tq = clock64();
           if (!(a.dbg & 8)) flag_wait_ge(a.chain_flags + static_cast<size_t>(layer - 1) * a.n_tiles + tile, static_cast<unsigned int>(a.n_nblocks));
           if (!(a.dbg & 4)) fence_proxy_async_global();
+          if (tr) c_flag += clock64() - tq;
         }
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
@@ -147,69 +170,116 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           const uint8_t* a_lo = kChain ? a.chain[layer].a_lo : S.a_lo;
           const uint8_t* b_hi = kChain ? a.chain[layer].b_hi : S.b_hi;
           const uint8_t* b_lo = kChain ? a.chain[layer].b_lo : S.b_lo;
-          const uint8_t* ah = a_hi + static_cast<size_t>(tile) * S.a_tile_bytes;
-          const uint8_t* al = PASSES == 3 ? a_lo + static_cast<size_t>(tile) * S.a_tile_bytes : nullptr;
-          const uint8_t* bh = b_hi + static_cast<size_t>(nb) * n_it * b_bytes;
-          const uint8_t* bl = PASSES == 3 ? b_lo + static_cast<size_t>(nb) * n_it * b_bytes : nullptr;
-          for (int s = 0; s < n_it; ++s) {
-            mbar_wait(&empty[slot], ph ^ 1);
-            if (a.dbg & 2) { mbar_arrive(&full[slot]); if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; } continue; }
-            mbar_arrive_expect_tx(&full[slot], slot_bytes);
-            uint8_t* dst = smem + slot * slot_bytes;
-            bulk_g2s(dst, ah, a_bytes, &full[slot]);
-            bulk_g2s(dst + b_hi_off, bh, b_bytes, &full[slot]);
-            if (PASSES == 3) {
-              bulk_g2s(dst + a_lo_off, al, a_bytes, &full[slot]);
-              bulk_g2s(dst + b_lo_off, bl, b_bytes, &full[slot]);
-              al += a_bytes; bl += b_bytes;
+          // this lane's copy of every slot: lane 0 A_hi, 1 B_hi, 2 A_lo, 3 B_lo  (pair layout of a packed N-block:
+          // [half][K16 step][k-group][nt / 2 rows][8 K] -- each CTA's half is contiguous)
+          const bool is_b = lane & 1, is_lo = (lane & 2) != 0;
+          const uint8_t* src = nullptr;
+          uint32_t bytes = 0, dst_off = 0;
+          if (lane < (PASSES == 3 ? 4 : 2)) {
+            if (is_b) {
+              src = (is_lo ? b_lo : b_hi) + (static_cast<size_t>(nb << PAIR) + rank) * n_it * b_bytes;
+              bytes = b_bytes; dst_off = is_lo ? b_lo_off : b_hi_off;
+            } else if (!phantom) {
+              src = (is_lo ? a_lo : a_hi) + static_cast<size_t>(tile) * S.a_tile_bytes;
+              bytes = a_bytes; dst_off = is_lo ? a_lo_off : 0;
             }
-            ah += a_bytes; bh += b_bytes;
+          }
+          for (int s = 0; s < n_it; ++s) {
+            if (tr) tq = clock64();
+            mbar_wait(&empty[slot], ph ^ 1);
+            if (tr) { const long long t1 = clock64(); c_empty += t1 - tq; tq = t1; }
+            if (a.dbg & 2) {
+              if (lane == 0) mbar_arrive(&full[slot]);
+            } else {
+              if (lane == 0) mbar_arrive_expect_tx(&full[slot], phantom ? slot_bytes - (PASSES == 3 ? 2 : 1) * a_bytes : slot_bytes);
+              __syncwarp();
+              if (src) { bulk_g2s(smem + slot * slot_bytes + dst_off, src, bytes, &full[slot]); src += bytes; }
+            }
+            __syncwarp();
             if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
+            if (tr) c_issue += clock64() - tq;
           }
         }
+      }
+      if (tr && lane == 0) {   // cycles of the producer warp: waiting for tiles of the previous layer | for free slots | issuing copies
+        a.trace[64 + blockIdx.x * 32 + 16] = c_flag; a.trace[64 + blockIdx.x * 32 + 17] = c_empty; a.trace[64 + blockIdx.x * 32 + 18] = c_issue;
+        a.trace[64 + blockIdx.x * 32 + 24] = clock64() - tr_c0; a.trace[64 + blockIdx.x * 32 + 25] = global_ns() - tr_n0;   // SM clock = ratio
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kTileM, a.nt, false, false);
-      const uint32_t b_lbo = static_cast<uint32_t>(a.nt) * 16;
+    if (PAIR && rank != 0) {
+      // ---------------------------------------------------------------- peer CTA: no MMAs to issue; relay "slot landed" to the leader
+      if (lane == 0) {
+        uint32_t slot = 0, ph = 0;
+        for (int item = cta0; item < n_items; item += n_walk)
+          for (int sg = 0; sg < a.n_seg; ++sg) {
+            const int n_it = a.seg[sg].k_stages * 2 / KSTEPS;
+            for (int s = 0; s < n_it; ++s) {
+              mbar_wait(&full[slot], ph);
+              mbar_arrive_cluster(&full[slot], 0);
+              if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
+            }
+          }
+      }
+    } else {
+      // the whole warp walks the ring and one elected lane issues: descriptors stay warp-uniform (uniform registers), which
+      // takes the per-slot issue cost from ~280 + 50 per MMA cycles (single divergent thread) to ~40 (tools/umma_commit2.cu)
+      const uint32_t idesc = umma_idesc_f16(kTileM << PAIR, a.nt, false, false);
+      const uint32_t b_lbo = b_rows * 16;
       // descriptors differ only in their 14-bit start-address field (bytes >> 4): build once, add offsets
       const uint64_t da0 = umma_smem_desc(smem_u32(smem), 2048, 128);
       const uint64_t db0 = umma_smem_desc(smem_u32(smem), b_lbo, 128);
       const uint32_t bk16 = (2 * b_lbo) >> 4;                            // one K=16 step of B: two k-groups of nt x 16 B
       uint32_t slot = 0, ph = 0, n_done = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+      const bool tr = a.trace != nullptr;
+      long long c_acc = 0, c_full = 0, c_mma = 0, tq = 0;
+      for (int item = cta0; item < n_items; item += n_walk, ++n_done) {
         const uint32_t ab = n_done & 1, use = n_done >> 1;
+        if (tr) tq = clock64();
         mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
+        if (tr) c_acc += clock64() - tq;
         tc_fence_after();
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
           const uint32_t acc = tmem + ab * 256 + S.acc_col;
           const int n_it = S.k_stages * 2 / KSTEPS;
           for (int s = 0; s < n_it; ++s) {
+            if (tr) tq = clock64();
             mbar_wait(&full[slot], ph);
+            if (tr) { const long long t1 = clock64(); c_full += t1 - tq; tq = t1; }
             tc_fence_after();
+            __syncwarp();
             const uint32_t so = (slot * slot_bytes) >> 4;
+            if (elect_one()) {
             if (!(a.dbg & 1))
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k) {          // K = 16 steps inside the slot
               const uint64_t dah = da0 + so + k * 256;                                            // 4096 B per step
               const uint64_t dbh = db0 + so + (b_hi_off >> 4) + k * bk16;
-              umma_f16(acc, dah, dbh, idesc, (s | k) != 0);
+              if (PAIR) umma_f16_pair(acc, dah, dbh, idesc, (s | k) != 0); else umma_f16(acc, dah, dbh, idesc, (s | k) != 0);
               if (PASSES == 3) {
                 const uint64_t dal = dah + (a_lo_off >> 4);
                 const uint64_t dbl = dbh + (b_bytes >> 4);
-                umma_f16(acc, dal, dbh, idesc, 1);
-                umma_f16(acc, dah, dbl, idesc, 1);
+                if (PAIR) { umma_f16_pair(acc, dal, dbh, idesc, 1); umma_f16_pair(acc, dah, dbl, idesc, 1); }
+                else { umma_f16(acc, dal, dbh, idesc, 1); umma_f16(acc, dah, dbl, idesc, 1); }
               }
             }
-            umma_commit(&empty[slot]);
+            if (PAIR) umma_commit_pair(&empty[slot]); else umma_commit(&empty[slot]);
+            }
+            __syncwarp();
             if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
+            if (tr) c_mma += clock64() - tq;
           }
         }
-        umma_commit(&acc_full[ab]);
-        LG_TRACE(2 + 3 * n_done);
+        __syncwarp();
+        if (elect_one()) { if (PAIR) umma_commit_pair(&acc_full[ab]); else umma_commit(&acc_full[ab]); }
+        __syncwarp();
+        if (lane == 0) LG_TRACE(2 + 3 * n_done);
+      }
+      if (tr && lane == 0) {      // cycles of the MMA thread: waiting for a drained accumulator | for landed slots | issuing MMAs + commits
+        a.trace[64 + blockIdx.x * 32 + 20] = c_acc; a.trace[64 + blockIdx.x * 32 + 21] = c_full; a.trace[64 + blockIdx.x * 32 + 22] = c_mma;
+        a.trace[64 + blockIdx.x * 32 + 23] = n_done;
       }
     }
   } else if (warp == 3) {
@@ -219,12 +289,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     // counter the next layer's producers poll -- the store drain is waited out here, off the epilogue's critical path.
     if (kChain && n_layers > 1 && lane == 0) {
       uint32_t n_done = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+      for (int item = cta0; item < n_items; item += n_walk, ++n_done) {
         const int layer = item / per_layer, rem = item - layer * per_layer;
+        const int tile = PAIR ? 2 * (rem / a.n_nblocks) + static_cast<int>(rank) : rem / a.n_nblocks;
         mbar_wait(&stored[n_done & 1], (n_done >> 1) & 1);
-        if (layer + 1 < n_layers) {
+        if (layer + 1 < n_layers && tile < a.n_tiles) {
           __threadfence();
-          atomicAdd(a.chain_flags + static_cast<size_t>(layer) * a.n_tiles + rem / a.n_nblocks, 1u);
+          atomicAdd(a.chain_flags + static_cast<size_t>(layer) * a.n_tiles + tile, 1u);
         }
       }
     }
@@ -251,10 +322,17 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     };
     int cur_layer = -1;
     uint32_t n_done = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+    for (int item = cta0; item < n_items; item += n_walk, ++n_done) {
       const int layer = item / per_layer, rem = item - layer * per_layer;
-      const int tile = rem / a.n_nblocks, nb = rem % a.n_nblocks;
+      const int tile = PAIR ? 2 * (rem / a.n_nblocks) + static_cast<int>(rank) : rem / a.n_nblocks, nb = rem % a.n_nblocks;
       const LGemmLayer& Ly = a.chain[kChain ? layer : 0];
+      if (PAIR && tile >= a.n_tiles) {      // phantom tile of an odd tile count: nothing to store, just hand the accumulator back
+        mbar_wait(&acc_full[n_done & 1], (n_done >> 1) & 1);
+        tc_fence_before();
+        mbar_arrive_cluster(&acc_empty[n_done & 1], 0);
+        if (kChain && n_layers > 1) mbar_arrive(&stored[n_done & 1]);
+        continue;
+      }
       if (MODE == LG_W2D_FWD && layer != cur_layer) {
         // WIRE2D: both complex biases of a layer fill the staging arrays, so they are re-staged when the CTA moves on to
         // the next layer (its items are layer-major); the barriers keep slower epilogue warps off the old values
@@ -530,7 +608,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       }
       if (tid == 128) LG_TRACE(4 + 3 * n_done);
       tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
+      if (PAIR) mbar_arrive_cluster(&acc_empty[ab], 0); else mbar_arrive(&acc_empty[ab]);
       if (kChain && n_layers > 1) mbar_arrive(&stored[ab]);     // this thread's stores of the item are issued (publisher warp below)
     }
     if (MODE == LG_WIRE_DGRAD || MODE == LG_W2D_DGRAD) {
@@ -540,8 +618,8 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem);
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // pair: the peer's shared memory and barriers stay alive until both are done
+  if (warp == 2) { if (PAIR) tmem_dealloc_pair<512>(tmem); else tmem_dealloc<512>(tmem); }
   if (tid == 0) LG_TRACE(15);
 }
 
@@ -552,45 +630,91 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+// WIRE layer chains run on CTA pairs (INR_LGEMM_PAIR=0 keeps single CTAs with the same pair-packed weights: debugging only)
+static bool lgemm_pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("INR_LGEMM_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+template <int P, int M, int K, int PAIR>
+static cudaError_t lgemm_launch_one(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
+  static bool attr = false;
+  static int max_clusters = 0;
+  auto kern = lgemm_kernel<P, M, K, PAIR>;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
+    if (e != cudaSuccess) return e;
+    if (PAIR) {
+      // chained items wait on tiles other CTAs produce: every cluster of the grid must be resident at once
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(2 * (n_sm / 2)); q.blockDim = dim3(kLgThreads); q.dynamicSmemBytes = kLgSmem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q);
+      if (e != cudaSuccess) return e;
+      if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+    }
+    attr = true;
+  }
+  const bool chain = a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD || a.mode == LG_W2D_FWD || a.mode == LG_W2D_DGRAD;
+  const int rowgroups = PAIR ? (a.n_tiles + 1) / 2 : a.n_tiles;
+  const int items = rowgroups * a.n_nblocks * (chain ? a.chain_len : 1);
+  int walkers = PAIR ? n_sm / 2 : n_sm;                    // never more CTAs than SMs
+  if (PAIR && walkers > max_clusters) walkers = max_clusters;
+  if (items < walkers) walkers = items;
+  if (walkers <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(walkers << PAIR); cfg.blockDim = dim3(kLgThreads); cfg.dynamicSmemBytes = kLgSmem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  if (PAIR) {
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = 2; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
+    ++n_at;
+  }
+  if (pdl_enabled()) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
+  }
+  cfg.attrs = at; cfg.numAttrs = n_at;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   const bool chain = a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD || a.mode == LG_W2D_FWD || a.mode == LG_W2D_DGRAD;
   if (chain && (a.chain_len < 1 || a.chain_len > kWMaxDepth || (a.chain_len > 1 && !a.chain_flags))) return cudaErrorInvalidValue;
-  const int items = a.n_tiles * a.n_nblocks * (chain ? a.chain_len : 1);
-  // chained layers wait on each other's tiles: every CTA must be resident, i.e. never more CTAs than SMs
-  const int grid = items < n_sm ? items : n_sm;
-  if (grid <= 0) return cudaSuccess;
+  if (a.n_tiles <= 0) return cudaSuccess;
   const int expect_passes = (a.mode == LG_WIRE_FWD || a.mode == LG_W2D_FWD) ? 3 : 1;
   if (a.passes != expect_passes) return cudaErrorInvalidValue;
-#define LG_LAUNCH(P, M, K)                                                                                        \
-  do {                                                                                                            \
-    static bool attr = false;                                                                                     \
-    if (!attr) {                                                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(lgemm_kernel<P, M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem); \
-      if (e != cudaSuccess) return e;                                                                             \
-      attr = true;                                                                                                \
-    }                                                                                                             \
-    cudaLaunchConfig_t cfg = {};                                                                                  \
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kLgThreads); cfg.dynamicSmemBytes = kLgSmem; cfg.stream = stream;  \
-    cudaLaunchAttribute at[1];                                                                                    \
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                               \
-    at[0].val.programmaticStreamSerializationAllowed = 1;                                                         \
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;                                                         \
-    cudaError_t le = cudaLaunchKernelEx(&cfg, lgemm_kernel<P, M, K>, a);                                          \
-    if (le != cudaSuccess) return le;                                                                             \
-  } while (0)
+  cudaError_t e;
   switch (a.mode) {
-    case LG_WIRE_FWD:
-      LG_LAUNCH(3, LG_WIRE_FWD, 2);
+    case LG_WIRE_FWD: {
+      static int kf = -1;
+      if (kf < 0) { const char* e2 = std::getenv("INR_LG_KF"); kf = e2 ? std::atoi(e2) : 3; }
+      if (!lgemm_pair_enabled()) return cudaErrorNotSupported;
+      e = kf == 4 ? lgemm_launch_one<3, LG_WIRE_FWD, 4, 1>(a, n_sm, stream)
+        : kf == 3 ? lgemm_launch_one<3, LG_WIRE_FWD, 3, 1>(a, n_sm, stream) : lgemm_launch_one<3, LG_WIRE_FWD, 2, 1>(a, n_sm, stream);
       break;
-    case LG_WIRE_DGRAD: LG_LAUNCH(1, LG_WIRE_DGRAD, 4); break;
-    case LG_MFN_FWD:    LG_LAUNCH(1, LG_MFN_FWD, 4); break;
-    case LG_MFN_DGRAD:  LG_LAUNCH(1, LG_MFN_DGRAD, 4); break;
-    case LG_GABOR_E:    LG_LAUNCH(1, LG_GABOR_E, 4); break;
-    case LG_W2D_FWD:    LG_LAUNCH(3, LG_W2D_FWD, 2); break;
-    case LG_W2D_DGRAD:  LG_LAUNCH(1, LG_W2D_DGRAD, 4); break;
+    }
+    case LG_WIRE_DGRAD: {
+      static int kd = -1;
+      if (kd < 0) { const char* e2 = std::getenv("INR_LG_KD"); kd = e2 ? std::atoi(e2) : 4; }
+      if (!lgemm_pair_enabled()) return cudaErrorNotSupported;
+      e = kd == 8 ? lgemm_launch_one<1, LG_WIRE_DGRAD, 8, 1>(a, n_sm, stream)
+        : kd == 6 ? lgemm_launch_one<1, LG_WIRE_DGRAD, 6, 1>(a, n_sm, stream) : lgemm_launch_one<1, LG_WIRE_DGRAD, 4, 1>(a, n_sm, stream);
+      break;
+    }
+    case LG_MFN_FWD:    e = lgemm_launch_one<1, LG_MFN_FWD, 4, 0>(a, n_sm, stream); break;
+    case LG_MFN_DGRAD:  e = lgemm_launch_one<1, LG_MFN_DGRAD, 4, 0>(a, n_sm, stream); break;
+    case LG_GABOR_E:    e = lgemm_launch_one<1, LG_GABOR_E, 4, 0>(a, n_sm, stream); break;
+    case LG_W2D_FWD:    e = lgemm_launch_one<3, LG_W2D_FWD, 2, 0>(a, n_sm, stream); break;
+    case LG_W2D_DGRAD:  e = lgemm_launch_one<1, LG_W2D_DGRAD, 4, 0>(a, n_sm, stream); break;
     default: return cudaErrorInvalidValue;
   }
-#undef LG_LAUNCH
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

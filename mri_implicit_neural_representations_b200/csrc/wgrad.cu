@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp walks the ring and one elected lane issues: the descriptors stay warp-uniform (uniform registers).  A
+    // single divergent thread paid ~280 cycles per slot + ~50 per MMA (tools/umma_commit2.cu), more than the 512 tensor
+    // cycles of the eight N = 128 MMAs of a chunk.
+    {
       const uint32_t idesc = umma_idesc_f16(kTileM, U.n, true, true);
       constexpr uint32_t idesc_bias = umma_idesc_f16(kTileM, 16, true, true);
       const uint64_t d_ones = umma_smem_desc(smem_u32(ones), 128, 128);
@@ -105,35 +108,41 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&full[as], aph);
         tc_fence_after();
-        if (t == t0) WG_TRACE(2);
+        if (t == t0 && lane == 0) WG_TRACE(2);
         const uint64_t da0 = d0 + ((as * kWgSlotBytes) >> 4);
         for (int c = 0; c < nch; ++c) {
           const uint32_t slot = nA + bs;
           mbar_wait(&full[slot], bph);
           tc_fence_after();
+          __syncwarp();
           const uint64_t db0 = d0 + ((slot * kWgSlotBytes) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kTileM / 16; ++k)          // K = 16 batch rows per MMA: 256 B of every 2 KB feature group
-            umma_f16(tmem + 128 * c, da0 + k * 16, db0 + k * 16, idesc, (first ^ 1) | (k != 0));
-          if (U.bias_off >= 0 && c == nch - 1) {
-            // normal unit: bias[o] = sum_rows dZ[row,o] * 1  -> A = dZ image, B = ones
-            // transposed unit: bias[o] = sum_rows 1 * dZ_last[row,o] -> A = ones, B = dZ_last image
+            for (int k = 0; k < kTileM / 16; ++k)          // K = 16 batch rows per MMA: 256 B of every 2 KB feature group
+              umma_f16(tmem + 128 * c, da0 + k * 16, db0 + k * 16, idesc, (first ^ 1) | (k != 0));
+            if (U.bias_off >= 0 && c == nch - 1) {
+              // normal unit: bias[o] = sum_rows dZ[row,o] * 1  -> A = dZ image, B = ones
+              // transposed unit: bias[o] = sum_rows 1 * dZ_last[row,o] -> A = ones, B = dZ_last image
 #pragma unroll
-            for (int k = 0; k < kTileM / 16; ++k) {
-              const uint64_t da = U.transposed ? d_ones : da0 + k * 16;
-              const uint64_t db = U.transposed ? db0 + k * 16 : d_ones;
-              umma_f16(tmem + bias_col, da, db, idesc_bias, (first ^ 1) | (k != 0));
+              for (int k = 0; k < kTileM / 16; ++k) {
+                const uint64_t da = U.transposed ? d_ones : da0 + k * 16;
+                const uint64_t db = U.transposed ? db0 + k * 16 : d_ones;
+                umma_f16(tmem + bias_col, da, db, idesc_bias, (first ^ 1) | (k != 0));
+              }
             }
+            umma_commit(&empty[slot]);                       // commits cover every MMA issued so far
+            if (c == nch - 1) umma_commit(&empty[as]);
           }
-          umma_commit(&empty[slot]);                       // commits cover every MMA issued so far
+          __syncwarp();
           if (++bs == nB) { bs = 0; bph ^= 1; }
         }
-        umma_commit(&empty[as]);
         if (++as == nA) { as = 0; aph ^= 1; }
         first = 0;
       }
-      umma_commit(&acc_full);
-      WG_TRACE(3);
+      __syncwarp();
+      if (elect_one()) umma_commit(&acc_full);
+      __syncwarp();
+      if (lane == 0) WG_TRACE(3);
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> gpart[split]

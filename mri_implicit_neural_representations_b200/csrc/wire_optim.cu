@@ -15,10 +15,12 @@
 
 namespace inr {
 
-// byte offset of element (n, k) inside one N-block image [12 stages][192 x 32]
+constexpr uint32_t kWBlockBytesC = (kW2 / kStageK) * kWStageBBytes;   // 147456 per N-block
+// byte offset of element (n, k) inside one N-block image, pair layout: [half n / 96][k-group k / 8][96 rows][8 K] -- the CTA
+// pair of lgemm_kernel<.., PAIR = 1> streams one contiguous half each (rows 0..95 = the "a" rows, 96..191 = the "b" rows)
 __device__ __forceinline__ uint32_t wblk_off(int n, int k) {
-  const int s = k >> 5, kk = k & 31;
-  return static_cast<uint32_t>(s) * kWStageBBytes + (kk >> 3) * (kWNT * 16) + n * 16 + (kk & 7) * 2;
+  const int h = n / kWFeatPerBlock, nl = n - h * kWFeatPerBlock;
+  return static_cast<uint32_t>(h) * (kWBlockBytesC / 2) + (k >> 3) * (kWFeatPerBlock * 16) + nl * 16 + (k & 7) * 2;
 }
 constexpr uint32_t kWBlockBytes = (kW2 / kStageK) * kWStageBBytes;   // 147456 per N-block
 

@@ -162,9 +162,12 @@ class FusedChain(nn.Module):
         return eng
 
     def _epoch_token(self):
-        # in-place edits through torch (optimiser steps, load_state_dict, manual writes) bump _version;
-        # fused steps edit through raw pointers and bump _param_epoch instead
-        return (self._param_epoch, self._flat._version)
+        # In-place edits through torch bump a version counter: writes to the flat buffer bump _flat._version, but
+        # an optimiser step (torch.optim.Adam: p.addcdiv_) or any edit through a Parameter bumps THAT Parameter's
+        # counter only -- after _rebind's `p.data = view` every Parameter counts on its own.  Version counters only
+        # grow, so their sum changes whenever any of them does.  Fused steps edit through raw pointers and bump
+        # _param_epoch instead.
+        return (self._param_epoch, self._flat._version, sum(p._version for p in self._params_in_order()))
 
     def mark_params_updated_by_kernel(self, eng: ChainEngine):
         self._param_epoch += 1

@@ -20,9 +20,12 @@ def step_fn():
     eng.train_step(wl["loss"], coords, gt, bs, mask=mask, loss_opts=wl["loss_opts"])
 
 
-for _ in range(50):
-    step_fn()
-torch.cuda.synchronize()
+import time
+t_end = time.time() + float(os.environ.get("INR_TRACE_WARM_S", "2.0"))      # SM clocks ramp over ~1.5 s of continuous load
+while time.time() < t_end:
+    for _ in range(50):
+        step_fn()
+    torch.cuda.synchronize()
 buf = torch.zeros(64 + 32 * 1024, dtype=torch.int64, device=dev)
 for sel in os.environ.get("INR_TRACE_LGEMMS", os.environ.get("INR_TRACE_LGEMM", "0")).split(","):
     os.environ["INR_TRACE_LGEMM"] = sel
@@ -35,11 +38,15 @@ for sel in os.environ.get("INR_TRACE_LGEMMS", os.environ.get("INR_TRACE_LGEMM", 
     t = t[t[:, 0] > 0]
     t0 = int(t[:, 0].min())
     print(f"--- lgemm launch {sel}: {t.shape[0]} CTAs; ns since first CTA start: start, prologue | per item: mma issued, acc ready, epilogue done | exit")
-    for i in list(range(0, t.shape[0], max(1, t.shape[0] // 16))):
+    for i in list(range(0, t.shape[0], max(1, t.shape[0] // 8))) + [1, 75]:
         v = t[i].tolist()
         f = lambda x: f"{int(x) - t0:7d}" if x else "      -"
         items = " | ".join(" ".join(f(v[2 + 3 * j + k]) for k in range(3)) for j in range(4))
         print(f"cta {i:4d} {f(v[0])} {f(v[1])} | {items} | {f(v[15])}")
-        if any(v[16:]):
-            print("          item 1 slots (full seen, committed): " + " ".join(f(x) for x in v[16:32] if x))
+        if any(v[16:24]):
+            print(f"          producer cycles: flag wait {v[16]}, empty wait {v[17]}, copy issue {v[18]} | mma thread cycles: acc wait {v[20]}, "
+                  f"full wait {v[21]}, issue+commit {v[22]} over {v[23]} items")
     print("max exit", int(t[:, 15].max()) - t0)
+    v = t[t.shape[0] // 2].tolist()
+    if v[25]:
+        print(f"producer warp of cta {t.shape[0] // 2}: {v[24]} cycles in {v[25]} ns -> SM clock {v[24] / v[25] * 1e3:.0f} MHz")
