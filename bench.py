@@ -66,9 +66,18 @@ MULTISCALE_WORKLOAD = dict(
     loss_opts={"hdr_eps": 1e-2, "hdr_ff_sigma": 1.0, "hdr_ff_factor": 0.0}, radii=[0.35, 0.7, 1.05, 5.0],
     flop_per_coord=19423232)
 DEFAULT_WORKLOAD = "wire_kspace_hdr_bs25000"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE chained forward GEMM launch (4 layers) at bs 25000, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_lgemm_chain_summary.md)
-WIRE_CHAIN_DRAM_BYTES = 199.6e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel, read from the committed artefact of
+# the latest `ncu --set full` capture (profiles/roofline_traffic.json: {workload: {bytes, source, commit}}); absent -> null
+
+
+def load_traffic(workload):
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f).get(workload)
+        return (float(t["bytes"]), f"{t['source']} (kernel as of commit {t['commit']})") if t else (None, None)
+    except Exception:
+        return None, None
 SLICE = (15, 320, 320)                 # fastMRI-knee-shaped: 15 coils x 320 x 320 after the reference's crop
 LR = 5e-4
 
@@ -229,7 +238,9 @@ def run_reference(args, wl, name):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "batch": bs, "slice": list(SLICE)},
-            "cpu_baseline": {"value": value, "unit": "coords/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "coords/s", "cores": cores, "kind": "port",
+                             "port": "oracle restatement of the reference modules (separable HDR: faster than the reference's [bs, m] outer product)",
+                             "sample": sample},
             "e2e": {"value": value, "unit": "coords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -366,6 +377,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + [MULTISCALE_WORKLOAD["name"]])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-this-GPU context measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="default run: skip the SIREN configs[0] measurement")
     ap.add_argument("--parallel", default="dp", choices=["dp", "independent"],
                     help="N>1: dp = one fit, per-GPU batch shard + NCCL gradient all-reduce; independent = one fit per GPU")
     args = ap.parse_args()
@@ -389,6 +402,57 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=device)
+    line = run_workload(args, args.workload, dist, rank, world, local, device, cpu_baseline=not args.no_cpu_baseline)
+    # BASELINE.json's metric is quoted on "SIREN/WIRE": the default single-GPU run also measures configs[0] (SIREN d4 w256,
+    # image space, L2, batch 10000) and carries its numbers in the same line
+    if rank == 0 and world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_secondary:
+        sec = run_workload(args, "siren_image_l2_bs10000", None, 0, 1, local, device, cpu_baseline=False)
+        line["workloads"] = {"siren_image_l2_bs10000": {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "roofline",
+                                                                             "gpu_launches", "config", "gpu_eager_baseline")}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    # a CUDA graph that captured NCCL kernels can wedge destroy_process_group(); results are out, leave hard
+    if dist:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
+
+
+def gpu_eager_steps(wl, device, seconds=2.0):
+    """The reference's own arithmetic on THIS GPU ("the real bar"): the oracle port -- plain torch forward,
+    autograd backward, explicit Adam, fp32 / complex64, cuBLAS -- with its tensors on the B200, same batch.  Context for
+    the headline only; bounded to a couple of seconds."""
+    from oracle import inr_oracle as O
+    bs = wl["batch"]
+    torch.manual_seed(1234)
+    encB = O.encoder_init(wl["encoder"])
+    sd = {k: v.to(device) for k, v in O.MODEL_INIT[wl["model"]](dict(wl["net"])).items()}
+    encB = None if encB is None else encB.to(device)
+    n = 6
+    coords = torch.rand(bs * n, 3, device=device) * 2 - 1
+    gt = (torch.randn(bs * n, 2, device=device) * 0.05) if not wl["image_space"] else torch.rand(bs * n, 2, device=device)
+    mask = (torch.arange(bs * n, device=device) % 2 == 0) if wl["undersampling"] else None
+    opts = None
+    if wl["loss_opts"] and "hdr_eps" in wl["loss_opts"]:
+        opts = {"sigma": wl["loss_opts"]["hdr_ff_sigma"], "eps": wl["loss_opts"]["hdr_eps"], "factor": wl["loss_opts"]["hdr_ff_factor"]}
+    run = lambda k: O.train_steps(wl["model"], wl["net"], sd, encB, wl["encoder"]["embedding"], coords, gt, k, bs, LR, wl["loss"],
+                                  opts, mask=mask)
+    run(2)
+    torch.cuda.synchronize()
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds and done < 200:
+        run(n)
+        torch.cuda.synchronize()
+        done += n
+    dt = time.perf_counter() - t0
+    return {"value": done * bs / dt, "unit": "coords/s", "ms_per_step": dt / done * 1e3, "kind": "oracle port in PyTorch eager on the same B200 (fp32 / complex64, autograd, explicit Adam; separable HDR)",
+            "sample": f"{done} steps x {bs} coords"}
+
+
+def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=True):
+    """Measures one workload on this rank's GPU; returns the JSON line (rank 0) or None."""
+    wl = WORKLOADS[workload]
     from mri_implicit_neural_representations_b200.parallel import allreduce_mean_
     bs = wl["batch"]
     peaks = load_peaks()
@@ -504,10 +568,12 @@ def main():
     reset_cursor()
     run_steps(args.warmup % steps_per_pass)      # leave the cursor where a W-step warm-up would
     torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # NVML initialisation (tens of ms, different on every rank) happens BEFORE the barrier: nothing but the barrier's own
+    # exit skew sits between the ranks' synchronisation point and e0.record()
     with ClockSampler(local) as clk:
+        if dist:
+            dist.barrier()
         torch.cuda.synchronize()
         e0.record()
         run_steps(args.steps)        # graph replays; one 4-byte memset when the walk wraps around the resident rows
@@ -520,6 +586,18 @@ def main():
         ms = float(t)
     value = world * args.steps * bs / (ms * 1e-3)
     loss_dev = float(eng.loss_out)
+
+    # data-parallel replicas must be bit-identical after the warm-up, ramp and timed steps (checked BEFORE profile_step below,
+    # whose instrumented steps update every replica with its local gradients only): min / max over ranks of an fp64 parameter checksum
+    dp_check = None
+    if dist and dp:
+        torch.cuda.synchronize()
+        cs = eng.params.double().sum().reshape(1)
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dp_check = {"param_checksum_min": float(lo), "param_checksum_max": float(hi), "identical": float(lo) == float(hi),
+                    "steps_taken": int(eng.step)}
 
     # ---- per-kernel device times (CUDA events between the four kernels of a step, same stream)
     reset_cursor()
@@ -587,24 +665,23 @@ def main():
         ms_e2e = float(t)
     e2e_value = world * n_e2e * bs / (ms_e2e * 1e-3)
 
-    def finish():
-        # a CUDA graph that captured NCCL kernels can wedge destroy_process_group(); results are out, leave hard
-        if dist:
-            torch.cuda.synchronize()
-            dist.barrier()
-            sys.stdout.flush()
-            os._exit(0)
-
     if rank != 0:
-        finish()
-        return
+        return None
+
+    eager = None
+    if world == 1 and not args.no_gpu_eager and wl["model"] in ("WIRE", "SIREN", "FFN"):
+        try:
+            eager = gpu_eager_steps(wl, device)
+        except Exception as e:      # context only: never fail the bench over it
+            eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if cpu_baseline and world == 1:
         v1, dt1 = cpu_port_steps(wl, 1, 1, bs)
         n_cpu = max(2, min(200, int(12.0 / max(dt1, 1e-3))))
         v, dt = cpu_port_steps(wl, n_cpu, 1, bs)
         cpu = {"value": v, "unit": "coords/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "port": "oracle restatement of the reference modules (separable HDR: faster than the reference's [bs, m] outer product)",
                "sample": f"{n_cpu} steps x {bs} coords, oracle port (torch CPU fp32, autograd, Adam), {torch.get_num_threads()} threads, {dt:.1f} s"}
 
     clocks = clk.summary()
@@ -612,7 +689,7 @@ def main():
         "metric": "train coords/sec (fwd+bwd+Adam)", "value": value, "unit": "coords/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
-        "config": {"workload": args.workload, "model": wl["model"], "batch_per_gpu": bs, "slice": list(SLICE),
+        "config": {"workload": workload, "model": wl["model"], "batch_per_gpu": bs, "slice": list(SLICE),
                    "parallelism": ("single GPU" if world == 1 else
                                    (f"dp{world}: replicated weights, per-GPU batch {bs}, {eng.plan.n_params * 4} B fp32 gradients per step; exchange: {exchange}"
                                     if dp else f"independent fit per GPU x{world}, no collective")),
@@ -636,9 +713,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fwd_tflops / peaks["tflops_burst"],
                      # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture
-                     "traffic": (WIRE_CHAIN_DRAM_BYTES if wl["model"] == "WIRE" and bs == 25000 else None),
-                     "traffic_source": ("profiles/r01_ncu_lgemm_chain_summary.md (dram__bytes_read.sum + dram__bytes_write.sum of the chained launch, cold L2)"
-                                        if wl["model"] == "WIRE" and bs == 25000 else None),
+                     "traffic": load_traffic(workload)[0], "traffic_source": load_traffic(workload)[1],
                      "kernel": (f"lgemm_kernel ({wl['model']} forward: the {wl['net']['network_depth']} hidden-layer GEMMs + Gabor epilogues as one chained persistent launch)" if wire else
                                 ("forward phase (encoding + 18 lgemm launches + head/loss + TV)" if mfn else "chain_fwd_kernel<SIN>")),
                      "kernel_ms": kern_ms,
@@ -647,9 +722,11 @@ def main():
                      "step_tflops": step_tflops, "step_frac_of_sustained": step_tflops / peaks["tflops_sustained"],
                      "kernels_ms": prof},
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
     }
-    print(json.dumps(line), flush=True)
-    finish()
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    return line
 
 
 if __name__ == "__main__":

@@ -84,6 +84,14 @@ typedef struct inr_loss_desc {
    * batch (bs must equal tv_h * tv_w, `out` must be given; not combinable with INR_LOSS_HDR in the fused step) */
   float tv_weight;
   int32_t tv_h, tv_w;
+  /* data-parallel fits (one process per GPU, every rank a contiguous shard of each global grid-order batch): the
+   * reference's loss means run over the WHOLE batch (src/train.py:172-182; HDR: src/metrics/losses.py:241-262), so the
+   * normalisers are read from a DEVICE table built from the inputs alone: dp_norm[2 * b] = rows of global batch b that
+   * enter the loss / world size, dp_norm[2 * b + 1] = HDR filter mean of global batch b; b = *row_cursor_dev / dp_rows
+   * (b = 0 without a cursor).  The mean over ranks of the per-rank gradients is then the global-batch gradient.
+   * NULL: single-process semantics (the batch's own count and filter mean). */
+  const float* dp_norm;
+  int32_t dp_rows;
 } inr_loss_desc;
 
 typedef struct inr_tensor_info {

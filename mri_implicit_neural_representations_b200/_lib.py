@@ -23,7 +23,8 @@ class ModelDesc(C.Structure):
 
 class LossDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("hdr_eps", C.c_float), ("hdr_sigma", C.c_float), ("hdr_factor", C.c_float),
-                ("tv_weight", C.c_float), ("tv_h", C.c_int32), ("tv_w", C.c_int32)]
+                ("tv_weight", C.c_float), ("tv_h", C.c_int32), ("tv_w", C.c_int32),
+                ("dp_norm", C.c_void_p), ("dp_rows", C.c_int32)]
 
 
 class TensorInfo(C.Structure):

@@ -1202,6 +1202,11 @@ extern "C" int inr_adam_step_peers(const inr_plan* p, float* params, const float
   if (n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) return fail(INR_EINVAL, "bad rank / world size (at most 8 ranks)");
   PeerArgs P{};
   P.n_ranks = n_ranks; P.rank = rank;
+  {
+    static unsigned long long tmo = 0;
+    if (!tmo) { const char* e = std::getenv("INR_PEER_TIMEOUT_S"); const double s = e ? std::atof(e) : 120.0; tmo = static_cast<unsigned long long>((s > 0 ? s : 120.0) * 1e9); }
+    P.timeout_ns = tmo;
+  }
   for (int q = 0; q < n_ranks; ++q) {
     if (!peer_grads[q] || !peer_flags[q]) return fail(INR_EINVAL, "null peer pointer");
     P.grads[q] = peer_grads[q]; P.flags[q] = peer_flags[q];
@@ -1238,7 +1243,8 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
       return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
     const MfnWorkspace mw = mfn_workspace(p, bs);
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
-    const LossDesc ML{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w};
+    const LossDesc ML{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w,
+                      loss->dp_norm, loss->dp_rows, row_cursor_dev};
     if (ev) cudaEventRecord(ev[0], st);
     int rcm = mfn_forward_impl(p, mw, ML, params, wpack, coords, input_x, encB, gt, mask, nullptr, bs, workspace, out, 1,
                                row_cursor_dev, no_adam ? nullptr : step_dev, st);
@@ -1269,7 +1275,8 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
       return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
     const WireWorkspace ww = wire_workspace(p, bs);
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
-    const LossDesc WL{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w};
+    const LossDesc WL{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w,
+                      loss->dp_norm, loss->dp_rows, row_cursor_dev};
     if (ev) cudaEventRecord(ev[0], st);
     // without a TV pass between forward and backward the step scalars are reduced by the last CTA of wire_last
     const bool fold = p->wm.nlin == 1 && !(loss->tv_weight > 0.f);
@@ -1303,7 +1310,8 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   if (p->model.out_f > 2) return fail(INR_EUNSUPPORTED, "fused loss path packs at most 2 outputs");
   Workspace w = plan_workspace(p, bs);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  LossDesc L{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w};
+  LossDesc L{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w,
+             loss->dp_norm, loss->dp_rows, row_cursor_dev};
   if (ev) cudaEventRecord(ev[0], st);
   int rc = run_forward(p, w, L, params, wpack, coords, input_x, encB, gt, mask, bs, workspace, out, 1, row_cursor_dev,
                        no_adam ? nullptr : step_dev, st);

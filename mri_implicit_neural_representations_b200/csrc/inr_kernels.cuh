@@ -58,6 +58,14 @@ struct LossDesc {
   float eps, sigma, factor;   // HDR / LSL options
   float tv_weight;            // > 0: total-variation term of reference losses.py:326-343 on the batch viewed as [tv_h, tv_w, out]
   int tv_h, tv_w;
+  // data-parallel fits: this rank holds a shard of every GLOBAL grid-order batch; the loss means run over the global batch
+  // (reference src/train.py:172-182), so the normalisers come from a table that depends on the inputs only:
+  // dp_norm[2 * b] = (rows of global batch b that enter the loss) / world, dp_norm[2 * b + 1] = HDR filter mean of global
+  // batch b; b = *dp_cursor / dp_rows (0 without a cursor).  The mean over ranks of the per-rank gradients / loss values
+  // is then exactly the global-batch gradient / loss.  Null: the batch's own count / mean (single-process semantics).
+  const float* dp_norm;
+  int dp_rows;
+  const int* dp_cursor;
 };
 
 struct TvArgs {               // tv_kernel (optim.cu): adds the TV gradient / loss to the per-row loss pieces of one batch
@@ -155,6 +163,7 @@ struct PeerArgs {
   const float* grads[kMaxRanks];    // rank q's gradient buffer of this step (peer-mapped), [n_params]
   unsigned int* flags[kMaxRanks];   // rank q's flag array uint32[kMaxRanks] (peer-mapped); flags[q][r] = last epoch r published to q
   int n_ranks, rank;                // n_ranks == 0: no exchange
+  unsigned long long timeout_ns;    // entry barrier: trap after this long without the other ranks (0: 120 s)
 };
 
 struct SegDesc {          // one parameter tensor for the optimiser / packer

@@ -71,7 +71,8 @@ __device__ __forceinline__ RowLoss loss_row(const LossDesc& L, int out_f, const 
 
 
 // Entry barrier of the peer-memory gradient exchange (see PeerArgs): CTA 0 publishes `epoch` to every rank, every CTA
-// waits until all ranks have published it.  Bounded wait (4 s) -> trap instead of a hung GPU.
+// waits until all ranks have published it.  Bounded wait (PeerArgs::timeout_ns, 120 s unless INR_PEER_TIMEOUT_S says
+// otherwise: long enough for a straggler that validates or saves a checkpoint) -> trap instead of a hung GPU.
 __device__ __forceinline__ void peer_barrier(const PeerArgs& P, unsigned int epoch) {
   if (static_cast<int>(threadIdx.x) < P.n_ranks) {
     if (blockIdx.x == 0) { __threadfence_system(); st_release_sys(P.flags[threadIdx.x] + P.rank, epoch); }
@@ -79,7 +80,7 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& P, unsigned int epo
     const uint64_t t0 = global_ns();
     unsigned int spins = 0;
     while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
-      if ((++spins & 0x3FF) == 0 && global_ns() - t0 > 4000000000ull) { asm volatile("trap;"); }
+      if ((++spins & 0x3FF) == 0 && global_ns() - t0 > (P.timeout_ns ? P.timeout_ns : 120000000000ull)) { asm volatile("trap;"); }
     }
   }
   __syncthreads();
@@ -150,9 +151,14 @@ __device__ inline void reduce_step_scalars(const float* part_g, int n_tiles, con
       lA += part[w][0]; lB += part[w][1]; fs += part[w][2]; cnt += part[w][3];
       amA = fmaxf(amA, part[w][4]); amB = fmaxf(amB, part[w][5]);
     }
-    const float m = fmaxf(cnt, 1.f);
+    float m = fmaxf(cnt, 1.f);
     const float of = static_cast<float>(out_f);
     float cA = 0.f, cB = 0.f, lossv = 0.f, fmean = 0.f, reg = 0.f;
+    const float* dpn = nullptr;       // data-parallel shard: normalisers of the GLOBAL batch (see LossDesc)
+    if (loss.dp_norm) {
+      dpn = loss.dp_norm + 2 * static_cast<size_t>(loss.dp_cursor && loss.dp_rows > 0 ? *loss.dp_cursor / loss.dp_rows : 0);
+      m = dpn[0] > 0.f ? dpn[0] : 1.f;
+    }
     switch (loss.kind) {
       case LOSS_L2:   cA = 1.f / (m * of);  lossv = lA * 0.5f / (m * of); break;
       case LOSS_L1:   cA = 0.5f / (m * of); lossv = lA * 0.5f / (m * of); break;
@@ -160,7 +166,7 @@ __device__ inline void reduce_step_scalars(const float* part_g, int n_tiles, con
       case LOSS_TANH: cA = 2.f / (m * of);  lossv = lA / (m * of); break;
       case LOSS_LSL:  cA = 1.f / m;         lossv = lA * 0.5f / m; break;
       case LOSS_HDR:
-        fmean = fs / static_cast<float>(bs_k > 0 ? bs_k : 1);
+        fmean = dpn ? dpn[1] : fs / static_cast<float>(bs_k > 0 ? bs_k : 1);
         cA = 1.f / m; cB = loss.factor * fmean / m;
         reg = loss.factor * fmean * lB / m;
         lossv = lA / m + reg;

@@ -26,8 +26,10 @@ def _loss_desc(loss: str, loss_opts: Optional[dict]):
     o = loss_opts or {}
     tv = o.get("tv")
     tvw, tvh, tvww = (float(tv[2]) if len(tv) > 2 else 1e-4, int(tv[0]), int(tv[1])) if tv else (0.0, 0, 0)
+    dp = o.get("dp_norm")            # (device float table [n_batches, 2], rows per local batch): see inr_loss_desc.dp_norm
+    dp_ptr, dp_rows = (dp[0].data_ptr(), int(dp[1])) if dp is not None else (None, 0)
     return L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
-                      float(o.get("hdr_ff_factor", 0.0)), tvw, tvh, tvww)
+                      float(o.get("hdr_ff_factor", 0.0)), tvw, tvh, tvww, dp_ptr, dp_rows)
 
 
 def selftest_umma(mode: int, variant: int = 0):
@@ -223,9 +225,12 @@ class ChainEngine:
                                     _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _stream()),
                 "inr_adam_step")
 
-    def adam_step_peers(self, ex, parity=None):
+    def adam_step_peers(self, ex, parity: int):
         """Data-parallel optimiser step with the gradient exchange fused into the kernel: gradients = mean over ranks
-        of the peer-mapped buffers of `ex` (a parallel.PeerGradExchange) for the given parity."""
+        of the peer-mapped buffers of `ex` (a parallel.PeerGradExchange) for the given parity, which must alternate with
+        every optimiser step (step & 1: the same buffer `grad_step` of this step wrote) -- see PeerGradExchange.
+        No rank may do long host-only work between the steps of a fit without the others: the entry barrier of the
+        exchange waits for every rank (INR_PEER_TIMEOUT_S, default 120 s, then the kernel traps)."""
         self.step += 1
         gp, fp = ex.pointers(parity)
         L.check(L.lib.inr_adam_step_peers(self.plan.handle, _ptr(self.params), gp, fp, ex.world, ex.rank, _ptr(self.exp_avg),

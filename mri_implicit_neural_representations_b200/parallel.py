@@ -67,18 +67,18 @@ class PeerGradExchange:
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self._grad_ptrs = [(C.c_void_p * self.world)(*[p + 4 * par * self.n for p in ptrs]) for par in (0, 1)]
         self._flag_ptrs = (C.c_void_p * self.world)(*[p + 8 * self.n for p in ptrs])
-        self.parity = 0
 
-    def grads(self, parity=None) -> torch.Tensor:
-        par = self.parity if parity is None else parity
-        return self.buf[par * self.n:(par + 1) * self.n]
+    # The exchange has ONE barrier per step (entry of the optimiser kernel) and no exit barrier: a fast rank's next
+    # backward pass may start while a slow rank still gathers.  That is safe only because consecutive steps use
+    # different buffers -- the parity MUST alternate with every optimiser step (parity = step & 1), which is why it is an
+    # explicit argument everywhere and never a default.
 
-    def pointers(self, parity=None):
-        par = self.parity if parity is None else parity
-        return self._grad_ptrs[par], self._flag_ptrs
+    def grads(self, parity: int) -> torch.Tensor:
+        """This rank's gradient buffer for the optimiser step of the given parity (step & 1)."""
+        return self.buf[(parity & 1) * self.n:((parity & 1) + 1) * self.n]
 
-    def flip(self):
-        self.parity ^= 1
+    def pointers(self, parity: int):
+        return self._grad_ptrs[parity & 1], self._flag_ptrs
 
 
 # ---------------------------------------------------------------------------------------------------------------

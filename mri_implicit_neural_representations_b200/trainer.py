@@ -79,12 +79,78 @@ class FusedAdam(torch.optim.Optimizer):
                 st["step"].fill_(int(s["step"]))
 
 
+def dp_batch_table(coords: torch.Tensor, mask: Optional[torch.Tensor], batch_size: int, world: int, loss: str,
+                   loss_opts: Optional[dict]) -> torch.Tensor:
+    """Loss normalisers of every GLOBAL grid-order batch of a slice, [n_batches, 2] fp32 (inr_loss_desc.dp_norm):
+    column 0 = rows of the batch that enter the loss / world, column 1 = the HDR filter mean
+    mean_i (1 - exp(-(k_i1^2 + k_i2^2) / (2 sigma^2)))^2 over ALL rows of the batch (reference src/metrics/losses.py:241-259).
+    Both depend on the inputs only, so every rank computes the same table without communication."""
+    n = coords.shape[0]
+    nb = (n + batch_size - 1) // batch_size
+    pad = nb * batch_size - n
+    ones = torch.ones(n, dtype=torch.float32, device=coords.device) if mask is None else (mask.reshape(-1) != 0).float()
+    cnt = torch.nn.functional.pad(ones, (0, pad)).view(nb, batch_size).sum(1)
+    fmean = torch.zeros(nb, dtype=torch.float32, device=coords.device)
+    if loss == "HDR":
+        sigma = float((loss_opts or {}).get("hdr_ff_sigma", 1.0))
+        f = torch.exp(-(coords[:, 1] ** 2 + coords[:, 2] ** 2) / (2.0 * sigma * sigma))
+        w = (1.0 - f) ** 2
+        rows = torch.nn.functional.pad(torch.ones_like(w), (0, pad)).view(nb, batch_size).sum(1)
+        fmean = torch.nn.functional.pad(w, (0, pad)).view(nb, batch_size).sum(1) / rows
+    return torch.stack([cnt / float(world), fmean], dim=1).contiguous()
+
+
+class DataParallel:
+    """Coordinate data-parallel context of one fit (nothing like it exists in the reference, whose loop is
+    single-device): one process per GPU, replicated weights, every rank takes a contiguous share of each global grid-order
+    batch, gradients are exchanged once per step and every rank applies the same Adam update.
+
+    The exchange is the optimiser-fused peer gather over NVLink (`parallel.PeerGradExchange`) when symmetric memory can
+    be set up on every rank, else one NCCL all-reduce(avg) of the flat fp32 gradient buffer."""
+
+    def __init__(self, group=None, exchange: Optional[str] = None):
+        import os
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise L.InrError("DataParallel needs an initialised torch.distributed process group (launch with torchrun)")
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.exchange = exchange or os.environ.get("INR_DP_EXCHANGE", "peer")
+        self.peer = None
+
+    def setup(self, n_params: int, device):
+        """Collective: all ranks agree on the exchange mechanism."""
+        dist = self.dist
+        if self.world == 1:
+            return
+        ok = 0
+        if self.exchange == "peer" and dist.get_backend(self.group) == "nccl":
+            try:
+                from .parallel import PeerGradExchange
+                self.peer = PeerGradExchange(n_params, device, self.group)
+                ok = 1
+            except Exception:
+                self.peer = None
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag) == 0:
+            self.peer = None
+
+    def describe(self) -> str:
+        return "peer gather fused into the optimiser kernel (NVLink symmetric memory)" if self.peer is not None else "NCCL all-reduce(avg)"
+
+
 class FusedTrainer:
-    """Owns the resident arrays of one slice and walks them in grid order, one fused step per batch."""
+    """Owns the resident arrays of one slice and walks them in grid order, one fused step per batch.
+
+    With ``dp`` (a `DataParallel`) the SAME global batches are walked by all ranks together: rank r processes its
+    contiguous share of every global batch (`parallel.shard_rows`), the loss means run over the global batch
+    (`dp_batch_table`), gradients are averaged over ranks and every rank applies the same update -- so a world-size-R
+    fit follows the single-process trajectory up to summation order."""
 
     def __init__(self, model: FusedChain, encoder: Positional_Encoder, optim: FusedAdam, loss: str, batch_size: int,
                  coords: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None, loss_opts: Optional[dict] = None,
-                 use_graph: bool = True, tv: Optional[tuple] = None):
+                 use_graph: bool = True, tv: Optional[tuple] = None, dp: Optional[DataParallel] = None):
         """tv = (H, W[, weight]): per-coil batches (batch_size == H * W) with the total-variation term of
         src/train.py:173-174 added on every batch (the reference only reaches it with an undersampling mask)."""
         if loss not in FUSABLE_LOSSES:
@@ -105,6 +171,11 @@ class FusedTrainer:
         self.gt = gt.to(dev, torch.float32).contiguous()
         self.mask = None if mask is None else mask.to(dev).to(torch.uint8).contiguous()
         self.n = self.coords.shape[0]
+        self.dp = dp if (dp is not None and dp.world > 1) else None
+        self.global_bs, self.n_global = self.bs, self.n
+        self._full_coords = self.coords               # validation predicts the whole grid on every rank
+        if self.dp is not None:
+            self._shard_rows(tv)
         self._enc_params = None if wire else encoder.params
         self.eng = model.engine(self._enc_params, self.bs)
         self.eng.set_encoder(encoder.B)
@@ -113,40 +184,111 @@ class FusedTrainer:
         self.use_graph = use_graph
         self._graphs = {}
         self.pos = 0
+        self._gstep = 0                               # optimiser steps taken: parity of the peer exchange buffers
+        self._batch = 0                               # index of the next batch inside the epoch
         self.eng.cursor.zero_()
+        if self.dp is not None:
+            self.dp.setup(self.eng.plan.n_params, dev)
+
+    def _shard_rows(self, tv):
+        """Data-parallel: keep this rank's share of every global batch, contiguous and in batch order, so the local walk is
+        again a plain grid-order walk with batch size global_bs / world (the short last batch is split to within a row)."""
+        from .parallel import shard_rows
+        dp = self.dp
+        if tv is not None:
+            raise L.InrError("per-coil TV batches are not sharded over ranks (the TV term couples neighbouring rows); "
+                             "run per-coil fits as independent fits, one per GPU")
+        if self.global_bs % dp.world != 0:
+            raise L.InrError(f"data-parallel fits need batch_size ({self.global_bs}) divisible by the world size ({dp.world})")
+        self._dp_table = dp_batch_table(self.coords, self.mask, self.global_bs, dp.world, self.loss, self.loss_opts)
+        idx, self._local_counts = [], []
+        for start in range(0, self.n, self.global_bs):
+            s, c = shard_rows(start, self.global_bs, self.n, dp.rank, dp.world)
+            idx.append(torch.arange(s, s + c, device=self.coords.device))
+            self._local_counts.append(c)
+        idx = torch.cat(idx)
+        self.coords = self.coords[idx].contiguous()
+        self.gt = self.gt[idx].contiguous()
+        self.mask = None if self.mask is None else self.mask[idx].contiguous()
+        self.bs = self.global_bs // dp.world
+        self.n = int(idx.numel())
+        self.loss_opts["dp_norm"] = (self._dp_table, self.bs)
 
     @property
     def steps_per_epoch(self):
-        return (self.n + self.bs - 1) // self.bs
+        return (self.n_global + self.global_bs - 1) // self.global_bs
 
-    def _launch(self, bs):
-        self.eng.train_step(self.loss, self.coords, self.gt, bs, mask=self.mask, loss_opts=self.loss_opts, use_cursor=True,
-                            out=self._out)
+    def _launch(self, bs, par=0):
+        if self.dp is None:
+            self.eng.train_step(self.loss, self.coords, self.gt, bs, mask=self.mask, loss_opts=self.loss_opts, use_cursor=True,
+                                out=self._out)
+        elif self.dp.peer is not None:
+            # forward + loss + backward into this rank's peer-mapped buffer of parity `par`; the optimiser kernel waits for
+            # every rank's flag, gathers all ranks' gradients over NVLink and applies Adam (no all-reduce kernel)
+            self.eng.grad_step(self.loss, self.coords, self.gt, bs, mask=self.mask, loss_opts=self.loss_opts, use_cursor=True,
+                               out=self._out, grads=self.dp.peer.grads(par))
+            self.eng.adam_step_peers(self.dp.peer, par)
+        else:
+            from .parallel import allreduce_mean_
+            self.eng.grad_step(self.loss, self.coords, self.gt, bs, mask=self.mask, loss_opts=self.loss_opts, use_cursor=True,
+                               out=self._out)
+            allreduce_mean_(self.eng.grads, group=self.dp.group)
+            self.eng.adam_step()
 
     def step(self) -> torch.Tensor:
-        """One batch; returns the device scalar holding its loss (no host sync)."""
+        """One batch; returns the device scalar holding its loss (no host sync).  Data-parallel: the scalar is this rank's
+        share, normalised so that the mean over ranks is the global-batch loss (`global_loss`)."""
         if self.pos >= self.n:
             self.pos = 0
+            self._batch = 0
             self.eng.cursor.zero_()
-        bs = min(self.bs, self.n - self.pos)
+        if self.dp is None:
+            bs = min(self.bs, self.n - self.pos)
+        else:
+            bs = self._local_counts[self._batch]
+            if bs == 0:
+                raise L.InrError("a rank received no rows of the last global batch; use a batch size the slice does not "
+                                 "leave a remainder smaller than the world size for")
         self.optim.sync_hyper(self.eng)
         # engines of this module share the parameters: make sure this one's fp16 copies are current
         self.model.engine(self._enc_params, self.bs)
-        g = self._graphs.get(bs) if self.use_graph else None
+        par = self._gstep & 1 if (self.dp is not None and self.dp.peer is not None) else 0
+        key = (bs, par)
+        g = self._graphs.get(key) if self.use_graph else None
         if g is not None:
             g.replay()
         else:
-            self._launch(bs)                          # eager (first step of this batch size, or graphs off)
-            if self.use_graph:
+            self._launch(bs, par)                     # eager (first step of this batch size / parity, or graphs off)
+            if self.use_graph and self._gstep >= 1:   # calibration passes and kernel attributes are behind us
                 torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):             # capture records the same four launches; nothing executes here
-                    self._launch(bs)
-                self._graphs[bs] = g
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):         # capture only records the launches; nothing executes here
+                        self._launch(bs, par)
+                    self._graphs[key] = g
+                except Exception:
+                    if self.dp is None:
+                        raise
+                    self.use_graph = False            # a collective that refuses capture: stay eager
+                    torch.cuda.synchronize()
         self.pos += bs
+        self._batch += 1
+        self._gstep += 1
         self.model.mark_params_updated_by_kernel(self.eng)
         self.optim._fused_done = False
         return self.eng.loss_out
+
+    def global_loss(self, loss_dev: torch.Tensor) -> float:
+        """Host value of a step's loss; data-parallel: mean over ranks (one tiny all-reduce -- call it at log_iter only)."""
+        if self.dp is None:
+            return float(loss_dev)
+        t = loss_dev.detach().clone().reshape(1)
+        self.dp.dist.all_reduce(t, op=self.dp.dist.ReduceOp.SUM, group=self.dp.group)
+        return float(t) / self.dp.world
+
+    def param_checksum(self) -> float:
+        """Sum of all parameters as fp64 (data-parallel replicas must agree bit for bit)."""
+        return float(self.model._flat.double().sum())
 
     def epoch(self):
         """All batches of one pass in grid order; returns the summed loss as a device tensor."""
@@ -158,8 +300,8 @@ class FusedTrainer:
     @torch.no_grad()
     def predict(self, coords: Optional[torch.Tensor] = None, chunk: Optional[int] = None) -> torch.Tensor:
         """Full-grid inference (validation, src/train.py:199-220) through the fused forward, chunked."""
-        coords = self.coords if coords is None else coords.to(self.coords.device, torch.float32).contiguous()
-        chunk = chunk or self.bs
+        coords = self._full_coords if coords is None else coords.to(self.coords.device, torch.float32).contiguous()
+        chunk = chunk or self.global_bs
         eng = self.model.engine(self._enc_params, chunk)
         eng.set_encoder(self.encoder.B)
         outs = [eng.forward(coords[i:i + chunk], train=False) for i in range(0, coords.shape[0], chunk)]

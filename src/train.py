@@ -28,7 +28,8 @@ from data.slices import get_data_loader                                      # n
 from log_handler.logger import INRLogger                                     # noqa: E402
 from utils import get_config, set_default_configs                            # noqa: E402
 from mri_implicit_neural_representations_b200 import metrics as M            # noqa: E402
-from mri_implicit_neural_representations_b200.trainer import FUSABLE_LOSSES, FusedAdam, FusedTrainer  # noqa: E402
+from mri_implicit_neural_representations_b200.trainer import (FUSABLE_LOSSES, DataParallel, FusedAdam,   # noqa: E402
+                                                              FusedTrainer)
 
 opts = None      # the reference reads a module-global `opts` (src/train.py:35,45-48); kept for callers that set it
 
@@ -36,7 +37,41 @@ opts = None      # the reference reads a module-global `opts` (src/train.py:35,4
 def get_device(net_name=None):
     if not torch.cuda.is_available():
         raise RuntimeError("this engine has no CPU fallback: a CUDA device (B200) is required")
-    return torch.device("cuda")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def init_distributed():
+    """One process per GPU under torchrun (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment): binds the
+    process to its GPU and joins the NCCL group.  Returns (rank, world); (0, 1) for a plain `python src/train.py` run.
+    The reference has no multi-GPU path (its loop is single-device, src/train.py:27-252); see `run_fits` below for how
+    the work is spread."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo",
+                                device_id=torch.device("cuda", local) if torch.cuda.is_available() else None)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def plan_fits(fits, rank, world, parallel="auto"):
+    """How a list of (sample, slice) fits is spread over `world` ranks:
+      * 'independent' (auto when there are at least as many fits as ranks): fit i runs on rank i % world, whole and on its
+        own -- no data-path collective, exactly the reference's sequential loop (src/train.py:292-318) cut into `world` lanes;
+      * 'dp' (auto otherwise, i.e. a single slice): every rank works on every fit, coordinate data-parallel.
+    Returns (mode, fits of this rank)."""
+    fits = list(fits)
+    if world <= 1:
+        return "single", fits
+    if parallel == "auto":
+        parallel = "independent" if len(fits) >= world else "dp"
+    if parallel == "independent":
+        return "independent", fits[rank::world]
+    return "dp", fits
 
 
 def build_model(config):
@@ -53,7 +88,7 @@ def build_model(config):
         return GaborNet(config["net"])
     if name == "KGabor":
         return KGaborNet(config["net"])
-    if name == "WIRE2D" and config.get("_allow_wire2d", False):      # only the HP-search trainer builds it (hp_model_training.py:55-56)
+    if name == "WIRE2D":                       # reference src/train.py:59-60, hp_model_training.py:55-56
         from models.wire2d import WIRE2D
         return WIRE2D(config["net"])
     raise NotImplementedError(name)            # reference :69-70
@@ -81,8 +116,9 @@ def build_loss(config):
 
 
 def training_script(config, dataset, data_loader, val_loader, sample, slice_no, output_path=None, config_path=None,
-                    verbose=True):
-    """Same positional signature as the reference.  Returns the list of (epoch, psnr, ssim) validations."""
+                    verbose=True, dp=None):
+    """Same positional signature as the reference.  Returns the list of (epoch, psnr, ssim) validations.
+    dp: a trainer.DataParallel context -> this fit runs coordinate data-parallel over its ranks (rank 0 logs and saves)."""
     max_epoch = config["max_epoch"]
     in_image_space = config["transform"]
     device = get_device(config["model"])
@@ -93,19 +129,23 @@ def training_script(config, dataset, data_loader, val_loader, sample, slice_no, 
         config["data"], sample, slice_no, config["model"], config["net"]["network_input_size"],
         config["net"]["network_width"], config["net"]["network_depth"], config["loss"], config["lr"],
         config["encoder"]["embedding"]))
+    if config["encoder"]["embedding"] != "none":            # reference :40-41
+        model_name += "_scale{}_size{}".format(config["encoder"]["scale"], config["encoder"]["embedding_size"])
     model_name += datetime.now().strftime("%Y-%m-%d_%H-%M-%S")
-    train_writer = INRLogger(os.path.join(out_root, "logs", model_name))
-    checkpoint_directory = os.path.join(out_root, "outputs", model_name, "checkpoints")
-    os.makedirs(checkpoint_directory, exist_ok=True)
-    if cfg_path and os.path.exists(cfg_path):
-        shutil.copy(cfg_path, os.path.join(out_root, "outputs", model_name, "config.yaml"))
+    writes = dp is None or dp.rank == 0                      # data-parallel replicas are identical: one rank logs and saves
+    train_writer = INRLogger(os.path.join(out_root, "logs", model_name)) if writes else None
+    checkpoint_directory = os.path.join(out_root, "outputs", model_name, "checkpoints") if writes else None
+    if writes:
+        os.makedirs(checkpoint_directory, exist_ok=True)
+        if cfg_path and os.path.exists(cfg_path):
+            shutil.copy(cfg_path, os.path.join(out_root, "outputs", model_name, "config.yaml"))
 
     return fit(config, dataset, data_loader, val_loader, max_epoch, device, train_writer=train_writer,
-               checkpoint_directory=checkpoint_directory, verbose=verbose)["history"]
+               checkpoint_directory=checkpoint_directory, verbose=verbose and writes, dp=dp)["history"]
 
 
 def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_writer=None, checkpoint_directory=None,
-        verbose=True, model_seed=None):
+        verbose=True, model_seed=None, dp=None):
     """The training loop shared by training_script (reference src/train.py:52-252) and the HP-search trainer
     (reference src/parameter_search/hp_model_training.py:13-228): encoder, model, optimiser, loss, regulariser, the
     per-epoch LambdaLR decay, grid-order batches, validation every val_epoch.  Returns {'history': [(epoch, psnr,
@@ -143,7 +183,8 @@ def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_write
     train_ds = data_loader.ds
     gt_image = M.reconstruct(dataset.image.to(device), (C, H, W), in_image_space)
 
-    enc_ok = config["encoder"]["embedding"] == ("none" if config["model"] == "WIRE" else "gauss")
+    wire = config["model"] in ("WIRE", "WIRE2D")           # both take raw coordinates (reference networks.py:234, wire2d.py:92)
+    enc_ok = config["encoder"]["embedding"] == ("none" if wire else "gauss")
     per_coil = bool(config.get("per_coil", False))
     if per_coil:
         bs = H * W                              # one coil per batch, grid order (reference per-coil loader)
@@ -153,15 +194,22 @@ def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_write
     # `LSL` means CenterLoss in this entry point and in the HP-search trainer (reference src/train.py:87-88,
     # hp_model_training.py:81-82) -- randperm-based, not a fused-kernel target; the engine's fused log-space loss is what
     # train_kspace_multiscale.py calls LSL (:113-114)
+    # the complex-parameter optimiser kernels of WIRE / WIRE2D carry no regulariser term (the reference's penalty on
+    # complex tensors goes through abs / complex pow, regularization.py:27,35): those fits keep the autograd path
     fused = (config["loss"] in FUSABLE_LOSSES and config["loss"] != "LSL" and enc_ok
-             and (not use_tv or (per_coil and config["loss"] != "HDR")))
+             and (not use_tv or (per_coil and config["loss"] != "HDR"))
+             and (regularization is None or not wire))
     trainer = None
     if fused:
         mask = train_ds.coords_mask[:, 0] if has_mask else None
         trainer = FusedTrainer(model, encoder, optim, config["loss"], bs, train_ds.coords, train_ds.image, mask,
-                               config.get("loss_opts"), tv=(H, W) if use_tv else None)
-    elif verbose:
-        print("unfused path: model(x) -> loss -> backward -> optim.step through the engine's autograd face")
+                               config.get("loss_opts"), tv=(H, W) if use_tv else None, dp=dp)
+    else:
+        if dp is not None and dp.world > 1:
+            raise NotImplementedError("data-parallel fits need the fused step (fusable model + loss); run unfused "
+                                      "configurations as independent fits, one per GPU")
+        if verbose:
+            print("unfused path: model(x) -> loss -> backward -> optim.step through the engine's autograd face")
 
     scheduler = LambdaLR(optim, lambda x: 0.2 ** min(x / max_epoch, 1))
     history = []
@@ -173,7 +221,7 @@ def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_write
             for it in range(trainer.steps_per_epoch):
                 loss_dev = trainer.step()
                 if it % log_iter == log_iter - 1:              # the only host sync of the training loop
-                    train_loss = float(loss_dev)
+                    train_loss = trainer.global_loss(loss_dev)
                     (train_writer.log_train if train_writer else (lambda *a, **k: None))(train_loss, epoch * trainer.steps_per_epoch + it + 1)
                     if verbose:
                         print("[Epoch: {}/{}, Iteration: {}] Train loss: {:.4g}".format(epoch + 1, max_epoch, it, train_loss))
@@ -235,9 +283,12 @@ if __name__ == "__main__":
     parser.add_argument("--config", type=str, default="src/config/config_image.yaml", help="Path to the config file.")
     parser.add_argument("--data_samples", type=str, default="", help="Path to the config file.")
     parser.add_argument("--output_path", type=str, default=".", help="outputs path")
+    parser.add_argument("--parallel", type=str, default="auto", choices=["auto", "dp", "independent"],
+                        help="under torchrun: coordinate data-parallel fits, or one independent fit per GPU")
     opts = parser.parse_args()
     config = set_default_configs(get_config(opts.config))
     data_samples = get_config(opts.data_samples)
+    rank, world = init_distributed()
 
     def loaders(sample, slice_no):
         return get_data_loader(data=config["data"], data_root=config["data_root"], set=config["set"],
@@ -246,12 +297,19 @@ if __name__ == "__main__":
                                normalization=config["normalization"], undersampling=config["undersampling"],
                                use_dists="no", per_coil=config["per_coil"])
 
+    # (name, file sample, slice): the reference always loads config["sample"] in the multi-sample loop (:304); kept
     if not data_samples:
-        dataset, data_loader, val_loader = loaders(config["sample"], config["slice"])
-        training_script(config, dataset, data_loader, val_loader, config["sample"], config["slice"])
+        fits = [(config["sample"], config["sample"], config["slice"])]
     else:
-        for sample, slices in data_samples["samples"].items():
-            for _slice in slices:
-                # the reference always loads config["sample"] here (src/train.py:304); kept
-                dataset, data_loader, val_loader = loaders(config["sample"], _slice)
-                training_script(config, dataset, data_loader, val_loader, sample, _slice)
+        fits = [(sample, config["sample"], _slice) for sample, slices in data_samples["samples"].items() for _slice in slices]
+    mode, mine = plan_fits(fits, rank, world, opts.parallel)
+    dp = DataParallel() if mode == "dp" else None
+    if world > 1 and rank == 0:
+        print(f"{world} ranks, {len(fits)} fit(s): {mode}")
+    for name, file_sample, _slice in mine:
+        dataset, data_loader, val_loader = loaders(file_sample, _slice)
+        training_script(config, dataset, data_loader, val_loader, name, _slice, dp=dp)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
