@@ -51,6 +51,7 @@ extern "C" {
 #define INR_LAST_LINEAR 0
 #define INR_LAST_TANH 1      /* SIREN last_tanh, src/models/networks.py:94-95 */
 #define INR_LAST_SIGMOID 2   /* FFN, src/models/networks.py:63 */
+#define INR_LAST_SIN 3       /* SIREN with network_last_linear False: sine output layer, src/models/networks.py:107-117 */
 /* losses as weighted by the training loop (src/train.py:81-98,178-182) */
 #define INR_LOSS_NONE 0
 #define INR_LOSS_L2 1        /* 0.5 * torch.nn.MSELoss */

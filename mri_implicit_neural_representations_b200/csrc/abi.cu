@@ -149,6 +149,7 @@ static int wire_plan_create(const inr_model_desc* d, inr_plan** out);
 static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out);
 static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs);
 static int mfn_plan_create(const inr_model_desc* d, inr_plan** out);
+static int wide_plan_create(const inr_model_desc* d, inr_plan** out);
 static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs);
 
 extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
@@ -159,7 +160,9 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
       d->model == INR_MODEL_GABOR)
     return mfn_plan_create(d, out);
   if (d->model != INR_MODEL_SIREN && d->model != INR_MODEL_FFN) return fail(INR_EUNSUPPORTED, "model kind not built yet");
-  if (d->width != kWidth) return fail(INR_EUNSUPPORTED, "tensor-core chain kernels are built for network_width 256");
+  // the on-chip chain kernels hold one 128 x 256 activation tile per SM; other widths (8 shipped SIREN configs use 512), a
+  // single sine layer (network_depth 1 or 2) and the sine output layer run layer by layer on the streaming stage GEMMs
+  if (d->width != kWidth || d->depth < 3 || d->last_act == INR_LAST_SIN) return wide_plan_create(d, out);
   if (d->depth < 2 || d->depth - 1 > kMaxLayers - 1) return fail(INR_EINVAL, "network_depth out of range");
   if (d->out_features < 1 || d->out_features > kMaxOut) return fail(INR_EUNSUPPORTED, "network_output_size must be 1..4");
   if (d->encoder == INR_ENC_GAUSS) {
@@ -879,6 +882,99 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
   return INR_OK;
 }
 
+// SIREN / FFN as a chain of plain layers on the MFN stage GEMMs (MfnModel::chain): reference src/models/networks.py:48-124.
+// Sine layers: first (in -> W) + max(depth - 2, 0) hidden (W -> W); then the output layer (W -> out) with its activation.
+static int wide_plan_create(const inr_model_desc* d, inr_plan** out) {
+  const int W = d->width, IN = d->in_features, OF = d->out_features;
+  const int n_sine = d->depth >= 2 ? d->depth - 1 : 1;      // reference: depth 1 and depth 2 both build [first, last]
+  if (W % kMfnNT != 0 || W < kMfnNT || W > 512) return fail(INR_EUNSUPPORTED, "SIREN / FFN kernels need network_width in {128, 256, 384, 512}");
+  if (IN % 128 != 0 || IN < 128 || IN > 2048) return fail(INR_EUNSUPPORTED, "this network_width runs on the streaming layer GEMMs: network_input_size must be a multiple of 128");
+  if (d->depth < 1 || n_sine > kMfnMaxStages) return fail(INR_EINVAL, "network_depth out of range");
+  if (OF < 1 || OF > kMaxOut) return fail(INR_EUNSUPPORTED, "network_output_size must be 1..4");
+  if (d->encoder == INR_ENC_GAUSS) {
+    if (IN != 2 * d->enc_size) return fail(INR_EINVAL, "gauss encoder needs network_input_size == 2*embedding_size");
+  } else if (d->encoder != INR_ENC_NONE) {
+    return fail(INR_EUNSUPPORTED, "encoder kind not built yet");
+  }
+  inr_plan* p = new (std::nothrow) inr_plan();
+  if (!p) return fail(INR_EINVAL, "out of host memory");
+  p->desc = *d;
+  p->is_mfn = true;
+  MfnModel& M = p->mm;
+  std::memset(&M, 0, sizeof(M));
+  const int L = n_sine - 1;
+  M.L = L; M.width = W; M.in_f = IN; M.out_f = OF;
+  M.input_kind = d->encoder == INR_ENC_GAUSS ? INPUT_GAUSS : INPUT_DENSE;
+  M.enc_size = d->enc_size;
+  M.chain = 1; M.act = d->model == INR_MODEL_SIREN ? ACT_SIN : ACT_RELU; M.last_act = d->last_act;
+  M.w0 = d->model == INR_MODEL_SIREN ? d->w0 : 1.f;
+  for (int i = 0; i < kMfnMaxStages; ++i) { M.stage_head[i] = -1; M.bound_lo[i] = 0.f; M.bound_hi[i] = 3.0e38f; }
+  M.n_heads = 1; M.head_stage[0] = L; M.head_live[0] = 1; M.stage_head[L] = 0; M.top = L; M.n_out = 1;
+  // parameter layout = reference state_dict order: model.<l>.linear.{weight,bias}, l = 0 .. n_sine (FFN: model.<2l>.*)
+  int off = 0;
+  uint32_t wo = 0;
+  auto add_seg = [&](int o, int rows, int cols, int stage, bool is_bias, int scale_slot, int pf, int pb, uint32_t wf, uint32_t wd) {
+    p->tensors.push_back({o, rows, cols, stage, is_bias ? 1 : 0, 0, 0});
+    SegDesc s{};
+    s.off = o; s.rows = rows; s.cols = cols; s.layer = stage; s.pack_fwd = pf; s.pack_bwd = pb; s.wf_off = wf; s.wd_off = wd;
+    s.fwd_scale = M.w0; s.bwd_scale = 1.f;      // forward operand carries w0 (accumulator = w0 W z); dgrad uses W itself
+    s.layout = 1; s.nt = kMfnNT; s.scale_slot = scale_slot; s.frozen = 0; s.gfin_off = -1;
+    p->segs.push_back(s);
+  };
+  for (int i = 0; i <= L; ++i) {
+    const int cols = i == 0 ? IN : W;
+    const uint32_t bytes = static_cast<uint32_t>(W) * cols * 2;
+    if (i == 0) {
+      M.filt_w[0] = off; M.pk_filt[0] = wo; wo += bytes;
+      add_seg(off, W, IN, 0, false, SC_LAYER_SCALE + 0, 1, 0, M.pk_filt[0], 0); off += W * IN;
+      M.filt_b[0] = off; add_seg(off, W, 1, 0, true, SC_LAYER_SCALE + 0, 0, 0, 0, 0); off += W;
+    } else {
+      M.lin_w[i] = off; M.pk_lin[i] = wo; wo += bytes; M.pk_lin_t[i] = wo; wo += bytes;
+      add_seg(off, W, W, i, false, SC_LAYER_SCALE + i, 1, 1, M.pk_lin[i], M.pk_lin_t[i]); off += W * W;
+      M.lin_b[i] = off; add_seg(off, W, 1, i, true, SC_LAYER_SCALE + i, 0, 0, 0, 0); off += W;
+    }
+  }
+  M.head_w[0] = off; add_seg(off, OF, W, L, false, -1, 0, 0, 0, 0); off += OF * W;
+  M.head_b[0] = off; add_seg(off, OF, 1, L, true, -1, 0, 0, 0, 0); off += OF;
+  M.n_params = off;
+  M.wpack_bytes = wo;
+  M.gfin_floats = 0;
+  M.g_floats = gpart_stride(off);
+  // ---- wgrad units: dW_s = DP[s]^T (X | Z[s-1]), db_s = sum DP[s]; head as in the MFNs
+  const int wc = W / 128;
+  const uint32_t wtile = static_cast<uint32_t>(kTileM) * W * 2;
+  for (int i = 0; i <= L; ++i) {
+    const int K = i == 0 ? IN : W, kc = K / 128;
+    const uint32_t btile = static_cast<uint32_t>(kTileM) * K * 2;
+    for (int mc = 0; mc < wc; ++mc)
+      for (int c0 = 0, per = chunk_group(kc); c0 < kc; c0 += per) {
+        const int nch = (kc - c0) < per ? (kc - c0) : per;
+        WgradUnit u{};
+        u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+        u.b_tile_stride = btile; u.b_sub = c0 * 32768; u.b_bytes = 32768;
+        u.n = 128; u.n_chunks = nch; u.out_off = i == 0 ? M.filt_w[0] : M.lin_w[i]; u.out_ld = K; u.row0 = mc * 128; u.col0 = c0 * 128;
+        u.rows_valid = 128; u.cols_valid = 128 * nch; u.bias_off = c0 == 0 ? (i == 0 ? M.filt_b[0] : M.lin_b[i]) : -1;
+        p->units.push_back(u); p->unit_layer.push_back(i == 0 ? 200 : 700 + i);
+      }
+  }
+  for (int mc = 0; mc < wc; ++mc) {          // dV^T[o][f] = sum_rows dy[o] z_L[f]
+    WgradUnit u{};
+    u.a_tile_stride = wtile; u.a_sub = mc * 32768; u.a_bytes = 32768;
+    u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
+    u.n = kDzLastCols; u.transposed = 1; u.out_off = M.head_w[0]; u.out_ld = W; u.row0 = 0; u.col0 = mc * 128;
+    u.rows_valid = OF; u.cols_valid = 128; u.bias_off = mc == 0 ? M.head_b[0] : -1;
+    p->units.push_back(u); p->unit_layer.push_back(300);
+  }
+  if (static_cast<int>(p->units.size()) > kMaxUnits || static_cast<int>(p->segs.size()) > kMaxSegs) {
+    delete p;
+    return fail(INR_EUNSUPPORTED, "model too large for the static unit / segment tables");
+  }
+  p->n_sm = query_sm_count();
+  build_wgrad_sched(p);
+  *out = p;
+  return INR_OK;
+}
+
 static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs) {
   const MfnModel& M = p->mm;
   MfnWorkspace w{};
@@ -953,14 +1049,17 @@ static int mfn_forward_impl(const inr_plan* p, const MfnWorkspace& w, const Loss
     if (M.gabor) g.in_e = W + w.e;
     g.seg[0].a_hi = W + w.x; g.seg[0].b_hi = wp + M.pk_filt[i]; g.seg[0].a_tile_bytes = xtile; g.seg[0].k_stages = M.in_f / 32; g.seg[0].acc_col = 0;
     g.n_seg = 1;
-    if (i >= 1) {
+    if (M.chain) {          // plain layer of a wide SIREN / FFN: ONE segment, z_i = act(w0 (W_i z_{i-1} + b_i))
+      if (i >= 1) { g.seg[0].a_hi = W + w.z[i - 1]; g.seg[0].b_hi = wp + M.pk_lin[i]; g.seg[0].a_tile_bytes = wtile; g.seg[0].k_stages = M.width / 32; }
+      g.act_w0 = M.w0; g.act_kind = M.act;
+    } else if (i >= 1) {
       g.seg[1].a_hi = W + w.z[i - 1]; g.seg[1].b_hi = wp + M.pk_lin[i]; g.seg[1].a_tile_bytes = wtile; g.seg[1].k_stages = M.width / 32;
       g.seg[1].acc_col = kMfnNT; g.n_seg = 2;
       g.bias = params + M.lin_b[i];
     }
     g.nt = kMfnNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.width / kMfnNT; g.passes = 1; g.mode = LG_MFN_FWD;
-    g.phi = params + M.filt_b[i]; g.train = train;
-    g.out_hi = W + w.z[i]; g.out_lo = W + w.g[i]; g.out_ab = W + w.cp[i]; g.out_h = i >= 1 ? W + w.h[i] : nullptr;
+    g.phi = params + ((M.chain && i >= 1) ? M.lin_b[i] : M.filt_b[i]); g.train = train;
+    g.out_hi = W + w.z[i]; g.out_lo = M.chain ? nullptr : W + w.g[i]; g.out_ab = W + w.cp[i]; g.out_h = (i >= 1 && !M.chain) ? W + w.h[i] : nullptr;
     g.feat_tile_bytes = wtile; g.bs = static_cast<int>(bs);
     if (M.bounded && i >= 1) { g.dist = dist; g.bound_lo = M.bound_lo[i]; g.bound_hi = M.bound_hi[i]; }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
@@ -989,12 +1088,13 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
   const uint32_t wtile = static_cast<uint32_t>(kTileM) * M.width * 2;
   for (int i = M.top; i >= 1; --i) {        // dz_{i-1} = dh_i W_i (+ head gradient of stage i-1), then (dh, dp) of stage i-1
     LGemmArgs g{};
-    g.seg[0].a_hi = W + w.dh[i]; g.seg[0].b_hi = wp + M.pk_lin_t[i]; g.seg[0].a_tile_bytes = wtile; g.seg[0].k_stages = M.width / 32;
+    // wide chain: dL/d(pre-activation of layer i-1) = (DP[i] W_i) * CP[i-1] -- the stage-0 epilogue for every layer
+    g.seg[0].a_hi = W + (M.chain ? w.dp[i] : w.dh[i]); g.seg[0].b_hi = wp + M.pk_lin_t[i]; g.seg[0].a_tile_bytes = wtile; g.seg[0].k_stages = M.width / 32;
     g.seg[0].acc_col = 0; g.n_seg = 1;
     g.nt = kMfnNT; g.n_tiles = w.n_tiles; g.n_nblocks = M.width / kMfnNT; g.passes = 1; g.mode = LG_MFN_DGRAD;
-    g.real_first = (i - 1 == 0) ? 1 : 0;
-    g.in_y = W + w.g[i - 1]; g.in_ab = W + w.cp[i - 1]; g.in_h = i - 1 >= 1 ? W + w.h[i - 1] : nullptr;
-    g.out_dz = i - 1 >= 1 ? W + w.dh[i - 1] : nullptr; g.out_dp = W + w.dp[i - 1];
+    g.real_first = (i - 1 == 0 || M.chain) ? 1 : 0;
+    g.in_y = M.chain ? nullptr : W + w.g[i - 1]; g.in_ab = W + w.cp[i - 1]; g.in_h = (i - 1 >= 1 && !M.chain) ? W + w.h[i - 1] : nullptr;
+    g.out_dz = (i - 1 >= 1 && !M.chain) ? W + w.dh[i - 1] : nullptr; g.out_dp = W + w.dp[i - 1];
     g.out_dzu = (M.bounded && i - 1 >= 1) ? W + w.dhu[i - 1] : nullptr;
     g.out_q = M.gabor ? W + w.q[i - 1] : nullptr;
     g.scal = reinterpret_cast<const float*>(W + w.scal); g.src_layer = i; g.dst_layer = i - 1;
@@ -1013,7 +1113,8 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
   for (int i = 0; i < wg.n_units; ++i) {
     WgradUnit u = p->units[i];
     const int code = p->unit_layer[i];
-    if (code >= 600) { u.a_off = w.q[code - 600]; u.b_off = w.xa; }
+    if (code >= 700) { u.a_off = w.dp[code - 700]; u.b_off = w.z[code - 700 - 1]; }      // wide chain: dW_s = DP[s]^T Z[s-1]
+    else if (code >= 600) { u.a_off = w.q[code - 600]; u.b_off = w.xa; }
     else if (code >= 500) { u.a_off = w.q[code - 500]; u.b_off = w.x; }
     else if (code >= 400) { u.a_off = w.dhu[code - 400]; u.b_off = w.ones; }
     else if (code >= 300) { const int k = code - 300; u.a_off = w.z[M.head_stage[k]]; u.b_off = w.dout[M.stage_head[M.head_stage[k]]]; }

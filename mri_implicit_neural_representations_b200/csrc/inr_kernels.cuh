@@ -26,7 +26,7 @@ constexpr int kPartialsPerTile = 8;  // lossA, lossB, fsum, count, amaxA, amaxB,
 constexpr int kScalars = 64;          // step scalars + per-layer gradient scales + amax accumulators (WIRE)
 
 enum Act { ACT_SIN = 0, ACT_RELU = 1 };
-enum LastAct { LAST_LINEAR = 0, LAST_TANH = 1, LAST_SIGMOID = 2 };
+enum LastAct { LAST_LINEAR = 0, LAST_TANH = 1, LAST_SIGMOID = 2, LAST_SIN = 3 };
 enum InputKind { INPUT_GAUSS = 0, INPUT_DENSE = 1 };
 enum LossKind { LOSS_NONE = 0, LOSS_L2 = 1, LOSS_L1 = 2, LOSS_MSLE = 3, LOSS_TANH = 4, LOSS_LSL = 5, LOSS_HDR = 6 };
 // scalar slots written by the backward prologue (device memory, fp32)

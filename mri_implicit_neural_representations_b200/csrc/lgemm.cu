@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     const int width = a.n_nblocks * a.nt;
     for (int j = tid; j < width; j += kLgThreads) {
       s_ba[j] = a.bias ? a.bias[j] : 0.f;
-      s_bb[j] = a.phi[j];
+      s_bb[j] = a.act_w0 != 0.f ? a.act_w0 * a.phi[j] : a.phi[j];
     }
   } else if (MODE == LG_GABOR_E) {
     const int width = a.n_nblocks * a.nt;
@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const size_t off = img + static_cast<size_t>((a.nt * nb + 32 * sub + 8 * i) >> 3) * 2048;
-            pre[i][0] = ld_global_nc_v4(a.in_y + off); pre[i][1] = ld_global_nc_v4(a.in_ab + off);
+            pre[i][0] = a.in_y ? ld_global_nc_v4(a.in_y + off) : make_uint4(0u, 0u, 0u, 0u);
+            pre[i][1] = ld_global_nc_v4(a.in_ab + off);
             pre[i][2] = a.real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(a.in_h + off);
           }
         }
@@ -555,14 +556,19 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float p = vp[e] + s_bb[f0 + e];
-              g[e] = fast_sin(p); c[e] = fast_cos(p);
+              if (a.act_w0 != 0.f) {      // wide SIREN / FFN layer: z = act(w0 (W z + b)), c = d z / d(W z + b)
+                if (a.act_kind == ACT_RELU) { g[e] = fmaxf(p, 0.f); c[e] = p > 0.f ? 1.f : 0.f; }
+                else { g[e] = fast_sin(p); c[e] = a.act_w0 * fast_cos(p); }
+              } else {
+                g[e] = fast_sin(p); c[e] = fast_cos(p);
+              }
               if (a.in_e) { g[e] *= env[e]; c[e] *= env[e]; }     // Gabor: f = sin(p) E, d f / d p = cos(p) E
               h[e] = a.n_seg == 2 ? ((masked ? 0.f : vh[e]) + s_ba[f0 + e]) : 1.f;
               z[e] = g[e] * h[e];
             }
             st_global_v4(a.out_hi + off, pack8(z));
             if (a.train) {
-              st_global_v4(a.out_lo + off, pack8(g));
+              if (a.out_lo) st_global_v4(a.out_lo + off, pack8(g));
               st_global_v4(a.out_ab + off, pack8(c));
               if (a.n_seg == 2) st_global_v4(a.out_h + off, pack8(h));
             }

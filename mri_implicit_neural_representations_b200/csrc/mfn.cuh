@@ -32,6 +32,15 @@ struct MfnModel {
   int head_w[kMfnMaxStages], head_b[kMfnMaxStages];
   int filt_w[kMfnMaxStages], filt_b[kMfnMaxStages];     // stage i = 0..L
   int n_params;
+  // "wide chain": SIREN / FFN at widths the on-chip chain kernels are not built for (reference networks.py:48-124 takes any
+  // width; 8 shipped configs use 512) run on the same stage GEMMs as plain layers  z_s = act(w0 (W_s z_{s-1} + b_s)):
+  // stage 0 reads the X image through filt_w[0] / filt_b[0], stage s >= 1 reads Z[s-1] through lin_w[s] / lin_b[s]; there
+  // are no filters above stage 0, CP[s] holds d act / d(pre-activation) = w0 cos(p) (or the ReLU mask), DP[s] the gradient
+  // with respect to the pre-activation W z + b, and the single head applies `last_act`.
+  int chain;             // 1: wide chain
+  int act;               // chain: ACT_SIN / ACT_RELU
+  int last_act;          // chain: LAST_LINEAR / LAST_TANH / LAST_SIGMOID / LAST_SIN (sine output layer, network_last_linear False)
+  float w0;              // chain: 30 for SIREN, 1 for FFN
   // Gabor filters (GaborNet / KGaborNet, reference mfn.py:96-204): per stage mu [width, in_f] and gamma [width] precede
   // linear.{weight,bias} in the state_dict.  Their gradients come from three split-K reductions of q = dL/df * f:
   //   Qx = q^T x (written at mu's own offset), s = sum_rows q, u = sum_rows q |x|^2 (aux block [width][16], cols 0 / 1)

@@ -151,12 +151,25 @@ __global__ void __launch_bounds__(128) mfn_head_kernel(const __grid_constant__ M
         if (o < M.out_f) acc[o] = fmaf(z[e], sW[o][kg * 8 + e], acc[o]);
   }
   float y[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, t[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+  float dact[kMaxOut] = {1.f, 1.f, 1.f, 1.f};      // d y / d(V z + c) of the wide chain's output activation
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o)
-    if (o < M.out_f) y[o] = acc[o] + a.params[M.head_b[k] + o];
+    if (o < M.out_f) {
+      y[o] = acc[o] + a.params[M.head_b[k] + o];
+      if (M.chain) {      // reference networks.py:94-96 (tanh), :63 (sigmoid), :107-117 (sine output layer)
+        if (M.last_act == LAST_TANH) { y[o] = tanhf(y[o]); dact[o] = 1.f - y[o] * y[o]; }
+        else if (M.last_act == LAST_SIGMOID) { y[o] = 1.f / (1.f + expf(-y[o])); dact[o] = y[o] * (1.f - y[o]); }
+        else if (M.last_act == LAST_SIN) { const float pz = M.w0 * y[o]; y[o] = sinf(pz); dact[o] = M.w0 * cosf(pz); }
+      }
+    }
   const int out_ld = M.n_out * M.out_f, col = static_cast<int>(blockIdx.y) * M.out_f;
   if (valid && a.out)
     for (int o = 0; o < M.out_f; ++o) a.out[static_cast<size_t>(grow) * out_ld + col + o] = y[o];
+  if (a.train && M.chain && a.loss.kind == LOSS_NONE) {
+    // unfused path of a wide chain: the backward entry multiplies the caller's dL/dy by the output activation's derivative
+    float* ddst = reinterpret_cast<float*>(a.ws + a.w.gl) + (static_cast<size_t>(tile) * kTileM + row) * 4;
+    *reinterpret_cast<float4*>(ddst) = make_float4(dact[0], dact[1], dact[2], dact[3]);
+  }
   if (!a.train || a.loss.kind == LOSS_NONE || M.n_out != 1) return;
   // ---- fused loss pieces (single-head models)
   float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
@@ -173,7 +186,10 @@ __global__ void __launch_bounds__(128) mfn_head_kernel(const __grid_constant__ M
       RowLoss r = loss_row(a.loss, M.out_f, y, t);
       lA = r.lossA; lB = r.lossB; cnt = 1.f;
 #pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) { amA = fmaxf(amA, fabsf(r.gA[o])); amB = fmaxf(amB, fabsf(r.gB[o])); }
+      for (int o = 0; o < kMaxOut; ++o) {       // the stored pieces are gradients with respect to the head's linear output
+        r.gA[o] *= dact[o]; r.gB[o] *= dact[o];
+        amA = fmaxf(amA, fabsf(r.gA[o])); amB = fmaxf(amB, fabsf(r.gB[o]));
+      }
       gq = make_float4(r.gA[0], r.gA[1], r.gB[0], r.gB[1]);
     }
   }
@@ -275,6 +291,11 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
       if (grow < a.bs) {
         if (a.dout) {
           for (int o = 0; o < M.out_f; ++o) d[o] = S * a.dout[static_cast<size_t>(grow) * out_ld + kg * M.out_f + o];
+          if (M.chain) {      // output activation of the wide chain: derivative left by mfn_head_kernel
+            const float4 da = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.gl) +
+                                                                (static_cast<size_t>(tile) * kTileM + row) * 4);
+            d[0] *= da.x; d[1] *= da.y; d[2] *= da.z; d[3] *= da.w;
+          }
         } else {
           const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.gl) +
                                                              (static_cast<size_t>(tile) * kTileM + row) * 4);
@@ -289,6 +310,11 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
     if (grow < a.bs) {
       if (a.dout) {
         for (int o = 0; o < M.out_f; ++o) dy[o] = St * a.dout[static_cast<size_t>(grow) * out_ld + hk * M.out_f + o];
+        if (M.chain) {
+          const float4 da = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.gl) +
+                                                              (static_cast<size_t>(tile) * kTileM + row) * 4);
+          dy[0] *= da.x; dy[1] *= da.y; dy[2] *= da.z; dy[3] *= da.w;
+        }
       } else {
         const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.gl) +
                                                            (static_cast<size_t>(tile) * kTileM + row) * 4);
@@ -296,23 +322,24 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
       }
     }
     const size_t off = static_cast<size_t>(kg) * 2048 + row * 16;
-    float g[8], c[8], h[8], dh[8], dp[8], q[8];
-    mfn_unpack8(ld_global_nc_v4(gimg + off), g);
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, c[8], h[8], dh[8], dp[8], q[8];
+    const bool filt_only = M.chain || top == 0;      // z_top = act(p_top): no multiplicative linear term
+    if (!M.chain) mfn_unpack8(ld_global_nc_v4(gimg + off), g);
     mfn_unpack8(ld_global_nc_v4(cimg + off), c);
-    if (top >= 1) mfn_unpack8(ld_global_nc_v4(himg + off), h);
+    if (!filt_only) mfn_unpack8(ld_global_nc_v4(himg + off), h);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float dz = 0.f;
 #pragma unroll
       for (int o = 0; o < kMaxOut; ++o)
         if (o < M.out_f) dz = fmaf(dy[o], __ldg(Wt + o * M.width + kg * 8 + e), dz);
-      if (top >= 1) { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; q[e] = dh[e] * h[e]; }
+      if (!filt_only) { dh[e] = dz * g[e]; dp[e] = dz * h[e] * c[e]; q[e] = dh[e] * h[e]; }
       else { dh[e] = 0.f; dp[e] = dz * c[e]; q[e] = dz * g[e]; }
       amax = fmaxf(amax, fmaxf(fabsf(dh[e]), fabsf(dp[e])));
       if (M.gabor) amax = fmaxf(amax, fabsf(q[e]));
     }
     if (M.gabor) st_global_v4(a.ws + a.w.q[top] + static_cast<size_t>(tile) * tile_bytes + off, mfn_pack8(q));
-    if (top >= 1) {
+    if (!filt_only) {
       if (M.bounded) {
         st_global_v4(a.ws + a.w.dhu[top] + static_cast<size_t>(tile) * tile_bytes + off, mfn_pack8(dh));
         bool masked = false;

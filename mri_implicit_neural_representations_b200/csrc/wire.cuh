@@ -77,6 +77,9 @@ struct LGemmArgs {
   // ---- epilogue operands
   const float* bias;        // WIRE_FWD: complex bias, interleaved (re, im); MFN_FWD: linear bias b_i [width]
   const float* phi;         // MFN_FWD: filter bias phi_i [width]
+  float act_w0;             // MFN_FWD, != 0: plain layer of a wide SIREN / FFN chain: z = act(acc + w0 * phi) from ONE segment
+                            // (B packed with w0 folded in), CP image = d act / d(W z + b) = w0 cos(p) or the ReLU mask
+  int act_kind;             // wide chain: ACT_SIN / ACT_RELU
   float omega, sigma;       // WIRE: Gabor constants of the layer whose activation / derivative is evaluated
   int c_valid;              // WIRE: real complex width (181)
   int p2;                   // WIRE2D: padded complex width P2

@@ -54,7 +54,7 @@ class Plan:
         elif net.get("last_tanh", False):
             last = "tanh"                                          # src/models/networks.py:94-95
         elif not net.get("network_last_linear", True):
-            raise L.InrError("SIREN with a sine output layer is not built")
+            last = "sin"                                           # src/models/networks.py:107-117: sine output layer
         else:
             last = "linear"
         kind = enc.get("embedding", "none")
@@ -66,6 +66,9 @@ class Plan:
                                 float(net.get("first_omega_0", 30.0)) if model in ("WIRE", "WIRE2D") else 30.0,
                                 float(net.get("hidden_omega_0", 30.0)), float(net.get("scale", 10.0)))
         self.out_cols = int(net["network_output_size"])
+        # SIREN / FFN outside the on-chip chain kernels' shape (width 256, >= 2 sine layers, linear / tanh / sigmoid output)
+        # run layer by layer on the streaming stage GEMMs ("wide chain", csrc/abi.cu wide_plan_create)
+        self.wide = model in ("SIREN", "FFN") and (int(net["network_width"]) != 256 or int(net["network_depth"]) < 3 or last == "sin")
         if model in ("MultiscaleFourier", "BoundedFourier"):
             layers = list(net.get("output_layers", [1, 3, 5, 7]))
             mask = 0
@@ -148,7 +151,7 @@ class ChainEngine:
         # WIRE / MFN backward passes store fp16 gradient images under per-layer power-of-two scales that lag one step
         # (amax of the previous backward); the very first backward after construction runs twice so that the gradients
         # it returns are already computed with calibrated scales
-        self._lagged_scales = plan.model not in ("SIREN", "FFN")
+        self._lagged_scales = plan.model not in ("SIREN", "FFN") or plan.wide
         self._calibrated = False
 
     # ---- parameters -------------------------------------------------------------------------------
@@ -269,7 +272,7 @@ class ChainEngine:
                                        reps, ms, _stream()), "inr_profile_step")
         if self.plan.model in ("WIRE", "WIRE2D"):
             return {"forward": ms[0], "backward": ms[2], "optimiser": ms[3], "forward_layer_gemms": ms[4]}
-        if self.plan.model not in ("SIREN", "FFN"):      # MFN family: forward (+ TV) | backward (dgrad + wgrad) | optimiser
+        if self.plan.model not in ("SIREN", "FFN") or self.plan.wide:      # MFN family / wide chains: forward (+ TV) | backward (dgrad + wgrad) | optimiser
             return {"forward": ms[0], "backward": ms[2], "optimiser": ms[3]}
         return {"forward": ms[0], "dgrad": ms[1], "wgrad": ms[2], "optimiser": ms[3]}
 

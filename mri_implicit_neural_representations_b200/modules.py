@@ -50,7 +50,9 @@ class _ChainFn(torch.autograd.Function):
         (out,) = ctx.saved_tensors
         m = ctx.module
         dz = dout
-        if m._last_act == "tanh":
+        if m._act_in_kernel():
+            pass          # wide chains: the backward entry kernel applies the output activation's derivative itself
+        elif m._last_act == "tanh":
             dz = dout * (1 - out * out)
         elif m._last_act == "sigmoid":
             dz = dout * out * (1 - out)
@@ -81,6 +83,8 @@ class FusedChain(nn.Module):
             off += r.numel()
         self._flat = flat
         self._last_act = "sigmoid" if self.MODEL == "FFN" else ("tanh" if self.net.get("last_tanh", False) else "linear")
+        if self.MODEL == "SIREN" and not self.net.get("last_tanh", False) and not self.net.get("network_last_linear", True):
+            self._last_act = "sin"
         self._build_tree()
         self._engines = {}
         self._state = None
@@ -172,6 +176,10 @@ class FusedChain(nn.Module):
     def mark_params_updated_by_kernel(self, eng: ChainEngine):
         self._param_epoch += 1
         eng.packed_epoch = self._epoch_token()      # the fused optimiser re-packed this engine's copies itself
+
+    def _act_in_kernel(self):
+        eng = next(iter(self._engines.values()))
+        return bool(getattr(eng.plan, "wide", False))
 
     def _dead_param_flags(self):
         """True for parameters no gradient ever reaches (reference autograd leaves their .grad None)."""

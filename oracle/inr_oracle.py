@@ -219,8 +219,10 @@ def _affine(x, w, b=None):
 
 
 def siren_forward(sd, x, depth, last_tanh=False, last_linear=True, w0=30.0, trace=None):
-    """src/models/networks.py:91-96,121-124.  ``trace`` (list) receives (z, h) per layer."""
+    """src/models/networks.py:91-96,121-124.  ``trace`` (list) receives (z, h) per layer.
+    The reference builds first + (depth - 2) hidden + last layers (:111-115), i.e. TWO layers for depth 1 as for depth 2."""
     h = x
+    depth = max(int(depth), 2)
     for i in range(depth):
         z = h @ sd[f"model.{i}.linear.weight"].t() + sd[f"model.{i}.linear.bias"]
         if i == depth - 1:
