@@ -56,9 +56,8 @@ WORKLOADS = {
         flop_per_coord=31463424, fwd_flop_per_coord=(18 + 8) * 512 * 512 * 2 + 2 * 512 * 2),
 }
 # BASELINE.json configs[3]: MultiscaleBoundedFourier depth 8 width 512 (4 ring heads), LSL loss per head + 0.1 *
-# ConsistencyLoss, batch 100000, non-per-coil.  Runs through the reference-named module's autograd face
-# (src/train_kspace_multiscale.py loop body): C-ABI forward -> composite loss in PyTorch on the [bs, 2] heads -> C-ABI
-# backward -> fused Adam.  Measured by run_multiscale() below (single GPU, eager launches).
+# ConsistencyLoss, batch 100000, non-per-coil: the loop body of src/train_kspace_multiscale.py as one fused CUDA-graph step
+# (inr_train_step_dist).  Measured by run_multiscale() below (single GPU).
 MULTISCALE_WORKLOAD = dict(
     name="bounded_fourier_lsl_bs100000", model="BoundedFourier", batch=100000, image_space=False, normalization="max",
     net={"network_input_size": 512, "network_output_size": 2, "network_depth": 8, "network_width": 512},
@@ -247,12 +246,13 @@ def run_reference(args, wl, name):
 
 
 def run_multiscale(args):
-    """BASELINE config 4 through the drop-in module + composite loss (see MULTISCALE_WORKLOAD)."""
+    """BASELINE config 4 (see MULTISCALE_WORKLOAD): the loop body of src/train_kspace_multiscale.py:164-192 as ONE fused
+    CUDA-graph step (FusedTrainer -> inr_train_step_dist): model(coords, dist) -> 4 x LogSpaceLoss + 0.1 ConsistencyLoss ->
+    backward -> Adam."""
     wl = MULTISCALE_WORKLOAD
     sys.path.insert(0, os.path.join(ROOT, "src"))
-    from metrics.losses import ConsistencyLoss, LogSpaceLoss
     from mri_implicit_neural_representations_b200.modules import MultiscaleBoundedFourier, Positional_Encoder
-    from mri_implicit_neural_representations_b200.trainer import FusedAdam
+    from mri_implicit_neural_representations_b200.trainer import FusedAdam, FusedTrainer, HostFedStepper
     from mri_implicit_neural_representations_b200 import synthetic
     torch.cuda.set_device(0)
     device = torch.device("cuda", 0)
@@ -263,58 +263,73 @@ def run_multiscale(args):
     pairs = [(0.0, r) for r in wl["radii"]]
     model = MultiscaleBoundedFourier(dict(wl["net"]), boundaries=[p for p in pairs for _ in (0, 1)]).to(device)
     optim = FusedAdam(model, lr=LR, betas=(0.9, 0.999), weight_decay=0.0)
-    lsl, cons = LogSpaceLoss(wl["loss_opts"]), ConsistencyLoss(pairs)
     C, H, W = SLICE
     coords, gt, _ = synthetic.make_fit_arrays(1234, C, H, W, image_space=False, normalization="max")
     coords, gt = coords.to(device), gt.to(device)
     dist = torch.sqrt(coords[:, 1] ** 2 + coords[:, 2] ** 2)
-    n_batches = coords.shape[0] // bs
-    h_c, h_g = coords[: bs * 8].cpu().pin_memory(), gt[: bs * 8].cpu().pin_memory()
-    d_c, d_g = torch.empty(bs, 3, device=device), torch.empty(bs, 2, device=device)
+    n_fit = (coords.shape[0] // bs) * bs                      # whole batches only: one graph
+    trainer = FusedTrainer(model, enc, optim, "LSL", bs, coords[:n_fit], gt[:n_fit], None, wl["loss_opts"], dist=dist[:n_fit],
+                           consistency=(pairs, 0.1))
 
-    def step(c, y, d):
-        outs = model(coords=enc.embedding(c), dist_to_center=d)
-        optim.zero_grad()
-        loss = 0.1 * cons(outs, d)
-        for o in outs:
-            loss = loss + 0.5 * lsl(o.contiguous(), y)
-        loss.backward()
-        optim.step()
-        return loss
-
-    def run(n, i0=0):
-        for i in range(n):
-            j = ((i0 + i) % n_batches) * bs
-            last = step(coords[j:j + bs], gt[j:j + bs], dist[j:j + bs])
+    def run(n):
+        for _ in range(n):
+            last = trainer.step()
         return last
 
     run(max(args.warmup, 3))
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(20)
+    torch.cuda.synchronize()
+    run(min(int(1.5 / max((time.perf_counter() - t0) / 20, 1e-6)), 2000))      # clocks ramp over ~1.5 s of load
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(0) as clk:
+        torch.cuda.synchronize()
         e0.record()
-        last = run(args.steps, args.warmup)
+        last = run(args.steps)
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     value = args.steps * bs / (ms * 1e-3)
-    loss_last = float(last.detach())
-    # end to end: host batches in, loss out, every step
-    h_loss = torch.empty(1).pin_memory()
+    loss_last = float(last)
+    # end to end: host batches in (pinned staging block -> one H2D copy), the distances are derived from the coordinates on
+    # the device, one graph launch per step, every loss read on the host
+    eng = trainer.eng
+    dbuf = [torch.empty(bs, device=device) for _ in range(2)]
+    opts = dict(trainer.loss_opts)
+
+    def host_step(c, y, m, slot, b):
+        torch.sqrt(c[:, 1] ** 2 + c[:, 2] ** 2, out=dbuf[slot])
+        eng.train_step("LSL", c, y, b, loss_opts=opts, use_cursor=False, dist=dbuf[slot])
+
+    stepper = HostFedStepper(eng, "LSL", bs, masked=False, loss_opts=opts, depth=2, step_fn=host_step)
+    h_c, h_g = coords[: bs * 8].cpu(), gt[: bs * 8].cpu()
+    losses = []
+
+    def e2e_run(n, i0=0):
+        prev = None
+        for i in range(i0, i0 + n):
+            j = (i % 8) * bs
+            t = stepper.submit(h_c[j:j + bs], h_g[j:j + bs])
+            if prev is not None:
+                losses.append(stepper.loss(prev))
+            prev = t
+        losses.append(stepper.loss(prev))
+
+    e2e_run(6)
     torch.cuda.synchronize()
+    losses.clear()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        j = (i % 8) * bs
-        d_c.copy_(h_c[j:j + bs], non_blocking=True)
-        d_g.copy_(h_g[j:j + bs], non_blocking=True)
-        dd = torch.sqrt(d_c[:, 1] ** 2 + d_c[:, 2] ** 2)
-        h_loss.copy_(step(d_c, d_g, dd).detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    e2e_run(args.steps, 6)
+    torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     # CPU port: the oracle's multiscale forward + the same composite loss + torch autograd + Adam on the host cores
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import inr_oracle as O
+        from metrics.losses import ConsistencyLoss, LogSpaceLoss
+        lsl, cons = LogSpaceLoss(wl["loss_opts"]), ConsistencyLoss(pairs)
         torch.set_num_threads(os.cpu_count() or 1)
         torch.manual_seed(1234)
         encB = O.encoder_init(wl["encoder"])
@@ -346,23 +361,27 @@ def run_multiscale(args):
                "sample": f"{n_cpu} steps x {rows} coords of the {bs}-coord batch, oracle port (torch CPU fp32, autograd, Adam), "
                          f"{torch.get_num_threads()} threads, {t_cpu:.1f} s"}
     step_tflops = wl["flop_per_coord"] * bs / (ms / args.steps * 1e-3) / 1e12
+    n_launch = 1 + 9 + 3 + 3 + 8 + 1 + 1          # encode, 9 stage GEMMs, ms head / scalars / dout, dout amax / scalars / top, 8 dgrad GEMMs, wgrad, Adam
     line = {
         "metric": "train coords/sec (fwd+bwd+Adam)", "value": value, "unit": "coords/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
         "config": {"workload": wl["name"], "model": wl["model"], "batch_per_gpu": bs, "slice": list(SLICE),
-                   "parallelism": "single GPU", "launch": "eager (module autograd face)",
-                   "inputs": f"resident coords+targets {coords.shape[0] * 20 / 2**20:.0f} MiB, walked in grid order; gauss encoding in torch "
-                             "(dense [bs,512] input to the engine)",
-                   "step": "src/train_kspace_multiscale.py loop body: inr_forward_dist -> 4 x LogSpaceLoss + 0.1 ConsistencyLoss in "
-                           "PyTorch -> inr_backward_dist -> fused Adam", "loss": "LSL + consistency", "loss_last_step": loss_last},
+                   "parallelism": "single GPU", "launch": "cuda graph" if trainer.use_graph else "eager",
+                   "inputs": f"resident coords+targets+distances {n_fit * 24 / 2**20:.0f} MiB, walked in grid order (device cursor); "
+                             "gauss encoding in-kernel",
+                   "step": f"{n_launch} kernels: src/train_kspace_multiscale.py loop body fused -- encoding, 9 stage GEMMs (BoundedLinear row "
+                           "masks in the epilogues), 4 heads + 4 x LogSpaceLoss + 0.1 ConsistencyLoss, backward entry, 8 dgrad stage GEMMs, "
+                           "split-K wgrad, Adam + repack", "loss": "LSL + consistency", "loss_last_step": loss_last},
         "clocks": clk.summary(),
-        "e2e": {"value": args.steps * bs / (ms_e2e * 1e-3), "unit": "coords/s", "h2d_bytes_per_step": bs * 20, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps, "api": "MultiscaleBoundedFourier module + FusedAdam, pinned host batches"},
-        "gpu_launches": (1 + 8 + 4 + 3 + 7 + 1 + 1) * args.steps,
+        "e2e": {"value": args.steps * bs / (ms_e2e * 1e-3), "unit": "coords/s", "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "api": "trainer.HostFedStepper over ChainEngine.train_step(dist=...) (C ABI inr_train_step_dist): "
+                "host batch -> pinned staging -> H2D -> one graph launch per step [distances, kernels, D2H loss], every loss read on the host",
+                "loss_last_step": losses[-1]},
+        "gpu_launches": n_launch * args.steps,
         "roofline": {"bound": "tensor", "achieved": step_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": step_tflops / peaks["tflops_sustained"], "traffic": None,
-                     "kernel": "whole step (live-graph algorithmic FLOP of SURVEY 8d / step time; includes the PyTorch loss ops)",
+                     "kernel": "whole step (live-graph algorithmic FLOP of SURVEY 8d / step time)",
                      "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['source']})"},
         "cpu_baseline": cpu,
     }

@@ -93,6 +93,12 @@ typedef struct inr_loss_desc {
    * NULL: single-process semantics (the batch's own count and filter mean). */
   const float* dp_norm;
   int32_t dp_rows;
+  /* multi-scale fits (src/train_kspace_multiscale.py:173-190): every head k is supervised with `kind` on the full target
+   * and, for k >= 1, pulled towards the detached output of head k-1 on the rows whose dist_to_center lies outside
+   * [cons_bounds[2(k-1)], cons_bounds[2(k-1)+1]] -- cons_weight * ConsistencyLoss(bounds), src/metrics/losses.py:292-324
+   * (weight 0.1 in the reference loop).  Used by inr_train_step_dist only. */
+  float cons_weight;
+  float cons_bounds[16];
 } inr_loss_desc;
 
 typedef struct inr_tensor_info {
@@ -187,6 +193,23 @@ int inr_train_step(const inr_plan* plan, const inr_loss_desc* loss, float* param
                    const float* coords, const float* input_x, const float* encB, const float* gt,
                    const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev, void* workspace,
                    float* out, float* loss_out_dev, void* stream);
+
+/* inr_train_step for the multi-scale models (MultiscaleKFourier / MultiscaleBoundedFourier): replaces the loop body of
+ * src/train_kspace_multiscale.py:164-192 -- model(coords, dist_to_center) -> per-head loss + 0.1 * ConsistencyLoss ->
+ * backward -> Adam.  dist: fp32 [rows] distance of every row to the k-space centre, indexed like coords / gt (from
+ * *row_cursor_dev when a cursor is given).  The row mask applies to the per-head loss, not to the consistency term (:176-183).
+ * L2 / L1 / MSLE / LSL, up to 4 heads of 2 outputs, no TV term (those configurations use the autograd face). */
+int inr_train_step_dist(const inr_plan* plan, const inr_loss_desc* loss, float* params, float* exp_avg,
+                        float* exp_avg_sq, void* wpack, const float* hyper_dev, int32_t* step_dev,
+                        const float* coords, const float* input_x, const float* encB, const float* gt,
+                        const uint8_t* mask, const float* dist, int64_t bs, int32_t* row_cursor_dev, void* workspace,
+                        float* out, float* loss_out_dev, void* stream);
+
+/* inr_train_step_dist without the optimiser (gradients only; see inr_grad_step) */
+int inr_grad_step_dist(const inr_plan* plan, const inr_loss_desc* loss, const float* params, const void* wpack,
+                       const float* coords, const float* input_x, const float* encB, const float* gt,
+                       const uint8_t* mask, const float* dist, int64_t bs, int32_t* row_cursor_dev, void* workspace,
+                       float* out, float* grads, float* loss_out_dev, void* stream);
 
 /* inr_train_step without the optimiser: forward + loss + backward, gradients (unscaled fp32, flat, reference
  * parameter order) into `grads`.  For data-parallel training: all-reduce `grads` across ranks, then

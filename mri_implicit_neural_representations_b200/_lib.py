@@ -24,7 +24,7 @@ class ModelDesc(C.Structure):
 class LossDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("hdr_eps", C.c_float), ("hdr_sigma", C.c_float), ("hdr_factor", C.c_float),
                 ("tv_weight", C.c_float), ("tv_h", C.c_int32), ("tv_w", C.c_int32),
-                ("dp_norm", C.c_void_p), ("dp_rows", C.c_int32)]
+                ("dp_norm", C.c_void_p), ("dp_rows", C.c_int32), ("cons_weight", C.c_float), ("cons_bounds", C.c_float * 16)]
 
 
 class TensorInfo(C.Structure):
@@ -42,7 +42,7 @@ EXPORTS = ["inr_last_error", "inr_plan_create", "inr_plan_destroy", "inr_plan_pa
            "inr_plan_tensor_count", "inr_plan_tensor", "inr_wpack_bytes", "inr_workspace_bytes",
            "inr_scalars_offset", "inr_workspace_layout", "inr_pack_weights", "inr_forward", "inr_backward",
            "inr_forward_dist", "inr_backward_dist", "inr_adam_step", "inr_adam_step_peers",
-           "inr_train_step", "inr_grad_step", "inr_profile_step", "inr_debug_set_trace", "inr_selftest_umma"]
+           "inr_train_step", "inr_train_step_dist", "inr_grad_step", "inr_grad_step_dist", "inr_profile_step", "inr_debug_set_trace", "inr_selftest_umma"]
 
 
 def _load():
@@ -70,6 +70,9 @@ def _load():
     lib.inr_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.inr_train_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp,
                                    vp, vp, vp]
+    lib.inr_train_step_dist.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp,
+                                        vp, vp, vp]
+    lib.inr_grad_step_dist.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.inr_grad_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.inr_profile_step.argtypes = [vp, C.POINTER(LossDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32,
                                      C.POINTER(C.c_float), vp]

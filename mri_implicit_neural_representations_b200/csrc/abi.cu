@@ -33,6 +33,7 @@ cudaError_t launch_mfn_head(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_dout_amax(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_scalars(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_top(const MfnAuxArgs& a, cudaStream_t st);
+cudaError_t launch_mfn_ms_loss(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_gabor_prep(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_mfn_gabor_grad(const MfnAuxArgs& a, cudaStream_t st);
 cudaError_t launch_tv(const TvArgs& a, int n_tiles, cudaStream_t st);
@@ -1003,6 +1004,11 @@ static MfnWorkspace mfn_workspace(const inr_plan* p, int64_t bs) {
     w.mn = o; o += align_up(static_cast<uint64_t>(M.top + 1) * M.width * 4, 1024);
     w.gfin = o; o += align_up(static_cast<uint64_t>(M.gfin_floats) * 4, 1024);
   }
+  if (M.n_out > 1) {       // fused multi-head loss (inr_train_step_dist)
+    w.msg = o; o += align_up(static_cast<uint64_t>(M.n_out) * T * kTileM * 16, 1024);
+    w.msp = o; o += align_up(static_cast<uint64_t>(T) * M.n_out * kPartialsPerTile * 4, 1024);
+    w.dyf = o; o += align_up(static_cast<uint64_t>(T) * kTileM * M.n_out * M.out_f * 4, 1024);
+  }
   w.gpart = o; o += align_up(static_cast<uint64_t>(ns) * gpart_stride(M.g_floats) * 4, 1024);
   w.total = o;
   return w;
@@ -1061,24 +1067,29 @@ static int mfn_forward_impl(const inr_plan* p, const MfnWorkspace& w, const Loss
     g.phi = params + ((M.chain && i >= 1) ? M.lin_b[i] : M.filt_b[i]); g.train = train;
     g.out_hi = W + w.z[i]; g.out_lo = M.chain ? nullptr : W + w.g[i]; g.out_ab = W + w.cp[i]; g.out_h = (i >= 1 && !M.chain) ? W + w.h[i] : nullptr;
     g.feat_tile_bytes = wtile; g.bs = static_cast<int>(bs);
-    if (M.bounded && i >= 1) { g.dist = dist; g.bound_lo = M.bound_lo[i]; g.bound_hi = M.bound_hi[i]; }
+    if (M.bounded && i >= 1) { g.dist = dist; g.dist_row_offset = row_off; g.bound_lo = M.bound_lo[i]; g.bound_hi = M.bound_hi[i]; }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn fwd)");
   }
   x.step_counter = nullptr;
+  if (train && M.n_out > 1 && loss.kind != LOSS_NONE) {     // fused multi-head step: heads + per-head loss + consistency term
+    e = launch_mfn_ms_loss(x, st);
+    return e == cudaSuccess ? INR_OK : cuda_fail(e, "mfn_ms_head_kernel");
+  }
   e = launch_mfn_head(x, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "mfn_head_kernel");
 }
 
 static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
                              const float* dout, const float* dist, int64_t bs, void* ws, const float* hyper, const int* step,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int* row_off = nullptr, bool keep_ms_loss = false) {
   const MfnModel& M = p->mm;
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
   if (M.bounded && !dist) return fail(INR_EINVAL, "BoundedFourier needs dist_to_center");
   MfnAuxArgs x; mfn_aux_fill(p, w, x, params, ws, bs);
-  x.loss = loss; x.dout = dout; x.dist = dist; x.hyper = hyper; x.step = step;
+  x.loss = loss; x.dout = dout; x.dist = dist; x.hyper = hyper; x.step = step; x.row_offset = row_off;
+  if (keep_ms_loss) x.train = 2;       // the composite loss value was reduced by mfn_ms_scalars_kernel
   cudaError_t e;
   if (dout) { e = launch_mfn_dout_amax(x, st); if (e != cudaSuccess) return cuda_fail(e, "mfn_dout_amax_kernel"); }
   e = launch_mfn_scalars(x, st);
@@ -1104,7 +1115,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
       for (int k = 0; k < M.n_heads; ++k) if (M.head_live[k]) { if (seen == M.stage_head[i - 1]) { kk = k; break; } ++seen; }
       g.head_dout = dout; g.head_w = params + M.head_w[kk]; g.head_col = M.stage_head[i - 1] * M.out_f; g.head_ld = M.n_out * M.out_f;
     }
-    if (M.bounded && i - 1 >= 1) { g.dist = dist; g.bound_lo = M.bound_lo[i - 1]; g.bound_hi = M.bound_hi[i - 1]; }
+    if (M.bounded && i - 1 >= 1) { g.dist = dist; g.dist_row_offset = row_off; g.bound_lo = M.bound_lo[i - 1]; g.bound_hi = M.bound_hi[i - 1]; }
     e = launch_lgemm((g.trace = lgemm_trace_ptr(), g.dbg = lgemm_dbg(), g), p->n_sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "lgemm_kernel(mfn dgrad)");
   }
@@ -1330,7 +1341,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
                            const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
                            const float* encB, const float* gt, const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev,
                            void* workspace, float* out, float* loss_out_dev, cudaStream_t st, cudaEvent_t* ev,
-                           float* grads_only = nullptr) {
+                           float* grads_only = nullptr, const float* dist = nullptr) {
   const bool no_adam = grads_only != nullptr;
   if (!p || !loss || !params || !wpack || !gt || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (!no_adam && (!m || !v || !hyper_dev || !step_dev)) return fail(INR_EINVAL, "bad argument");
@@ -1338,23 +1349,39 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
     const bool mg = p->mm.input_kind == INPUT_GAUSS;
     if (mg && (!coords || !encB)) return fail(INR_EINVAL, "gauss encoder needs coords and encB");
     if (!mg && !input_x) return fail(INR_EINVAL, "dense input needs input_x");
-    if (p->mm.n_out != 1) return fail(INR_EUNSUPPORTED, "multi-head MFN losses run through the autograd face (inr_forward / inr_backward)");
+    const bool multi = p->mm.n_out != 1;
+    if (multi) {      // fused multi-scale step (reference src/train_kspace_multiscale.py:173-190)
+      if (p->mm.n_out > 4 || p->mm.out_f != 2) return fail(INR_EUNSUPPORTED, "the fused multi-head loss handles up to 4 heads of 2 outputs");
+      if (loss->kind != INR_LOSS_L2 && loss->kind != INR_LOSS_L1 && loss->kind != INR_LOSS_MSLE && loss->kind != INR_LOSS_LSL)
+        return fail(INR_EUNSUPPORTED, "fused multi-head losses: L2, L1, MSLE, LSL (+ consistency); others run through the autograd face");
+      if (loss->tv_weight > 0.f) return fail(INR_EUNSUPPORTED, "the TV term of the multi-scale loop runs through the autograd face");
+      if (loss->dp_norm) return fail(INR_EUNSUPPORTED, "data-parallel normalisers are not wired into the multi-head loss");
+      if ((loss->cons_weight != 0.f || p->mm.bounded) && !dist) return fail(INR_EINVAL, "the multi-scale step needs dist_to_center");
+    }
     if (loss->kind < INR_LOSS_L2 || loss->kind > INR_LOSS_HDR) return fail(INR_EINVAL, "unknown loss kind");
     if ((loss->kind == INR_LOSS_HDR || loss->kind == INR_LOSS_LSL) && p->mm.out_f != 2)
       return fail(INR_EINVAL, "complex-valued losses need network_output_size == 2");
     const MfnWorkspace mw = mfn_workspace(p, bs);
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
-    const LossDesc ML{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w,
-                      loss->dp_norm, loss->dp_rows, row_cursor_dev};
+    LossDesc ML{loss->kind, loss->hdr_eps, loss->hdr_sigma, loss->hdr_factor, loss->tv_weight, loss->tv_h, loss->tv_w,
+                loss->dp_norm, loss->dp_rows, row_cursor_dev};
+    if (multi) {
+      ML.cons_weight = loss->cons_weight;
+      for (int i = 0; i < 8; ++i) { ML.cons_lo[i] = loss->cons_bounds[2 * i]; ML.cons_hi[i] = loss->cons_bounds[2 * i + 1]; }
+    }
     if (ev) cudaEventRecord(ev[0], st);
-    int rcm = mfn_forward_impl(p, mw, ML, params, wpack, coords, input_x, encB, gt, mask, nullptr, bs, workspace, out, 1,
+    int rcm = mfn_forward_impl(p, mw, ML, params, wpack, coords, input_x, encB, gt, mask, dist, bs, workspace, out, 1,
                                row_cursor_dev, no_adam ? nullptr : step_dev, st);
     if (rcm) return rcm;
     rcm = run_tv(loss, out, p->mm.out_f, bs, wsb, mw.gl, mw.part, mw.n_tiles, st);
     if (rcm) return rcm;
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
-    rcm = mfn_backward_impl(p, mw, ML, params, wpack, nullptr, nullptr, bs, workspace, no_adam ? nullptr : hyper_dev,
-                            no_adam ? nullptr : step_dev, st);
+    if (multi)        // the fused loss left fp32 dL/dy of every head: from here on the path of an external dL/dout
+      rcm = mfn_backward_impl(p, mw, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, reinterpret_cast<const float*>(wsb + mw.dyf), dist, bs,
+                              workspace, no_adam ? nullptr : hyper_dev, no_adam ? nullptr : step_dev, st, row_cursor_dev, true);
+    else
+      rcm = mfn_backward_impl(p, mw, ML, params, wpack, nullptr, dist, bs, workspace, no_adam ? nullptr : hyper_dev,
+                              no_adam ? nullptr : step_dev, st, row_cursor_dev);
     if (rcm) return rcm;
     if (ev) cudaEventRecord(ev[3], st);
     AdamArgs ma; fill_adam(p, ma);
@@ -1445,6 +1472,15 @@ extern "C" int inr_train_step(const inr_plan* p, const inr_loss_desc* loss, floa
                          row_cursor_dev, workspace, out, loss_out_dev, static_cast<cudaStream_t>(stream), nullptr);
 }
 
+extern "C" int inr_train_step_dist(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,
+                                   const float* hyper_dev, int32_t* step_dev, const float* coords, const float* input_x,
+                                   const float* encB, const float* gt, const uint8_t* mask, const float* dist, int64_t bs,
+                                   int32_t* row_cursor_dev, void* workspace, float* out, float* loss_out_dev, void* stream) {
+  if (p && !p->is_mfn) return fail(INR_EINVAL, "inr_train_step_dist is for the multiscale MFN models");
+  return train_step_impl(p, loss, params, m, v, wpack, hyper_dev, step_dev, coords, input_x, encB, gt, mask, bs,
+                         row_cursor_dev, workspace, out, loss_out_dev, static_cast<cudaStream_t>(stream), nullptr, nullptr, dist);
+}
+
 extern "C" int inr_grad_step(const inr_plan* p, const inr_loss_desc* loss, const float* params, const void* wpack,
                              const float* coords, const float* input_x, const float* encB, const float* gt,
                              const uint8_t* mask, int64_t bs, int32_t* row_cursor_dev, void* workspace, float* out,
@@ -1453,6 +1489,17 @@ extern "C" int inr_grad_step(const inr_plan* p, const inr_loss_desc* loss, const
   return train_step_impl(p, loss, const_cast<float*>(params), nullptr, nullptr, const_cast<void*>(wpack), nullptr, nullptr,
                          coords, input_x, encB, gt, mask, bs, row_cursor_dev, workspace, out, loss_out_dev,
                          static_cast<cudaStream_t>(stream), nullptr, grads);
+}
+
+extern "C" int inr_grad_step_dist(const inr_plan* p, const inr_loss_desc* loss, const float* params, const void* wpack,
+                                  const float* coords, const float* input_x, const float* encB, const float* gt,
+                                  const uint8_t* mask, const float* dist, int64_t bs, int32_t* row_cursor_dev, void* workspace,
+                                  float* out, float* grads, float* loss_out_dev, void* stream) {
+  if (!grads) return fail(INR_EINVAL, "grads must not be null");
+  if (p && !p->is_mfn) return fail(INR_EINVAL, "inr_grad_step_dist is for the multiscale MFN models");
+  return train_step_impl(p, loss, const_cast<float*>(params), nullptr, nullptr, const_cast<void*>(wpack), nullptr, nullptr,
+                         coords, input_x, encB, gt, mask, bs, row_cursor_dev, workspace, out, loss_out_dev,
+                         static_cast<cudaStream_t>(stream), nullptr, grads, dist);
 }
 
 extern "C" int inr_profile_step(const inr_plan* p, const inr_loss_desc* loss, float* params, float* m, float* v, void* wpack,

@@ -34,6 +34,9 @@ enum Scalar { SC_LOSS = 0, SC_SCALE = 1, SC_CA = 2, SC_CB = 3, SC_COUNT = 4, SC_
               SC_STEP_SIZE = 8, SC_BC2_SQRT = 9,
               SC_LAYER_SCALE = 16,   // [16 .. 16+depth]: power-of-two scale of the dZ image of layer l (WIRE)
               SC_LAYER_AMAX = 40,
+              SC_HEAD_NORM = 50,     // [50 .. 57]: (cA_k, cB_k) of head k, k < 4 (fused multi-head loss)
+              SC_MS_LOSS = 58,       // composite loss of the fused multi-head step
+
               SC_DONE_COUNT = 63 };  // uint32 count of finished CTAs (last-CTA reduction of wire_last), self-resetting  // [40 .. 40+depth]: amax (float bits, atomicMax) of the scaled dZ of layer l, this step   // Adam bias corrections, computed once per step (fp64) by the backward prologue
 
 struct ChainModel {
@@ -66,6 +69,11 @@ struct LossDesc {
   const float* dp_norm;
   int dp_rows;
   const int* dp_cursor;
+  // multi-head (multi-scale) fits, reference src/train_kspace_multiscale.py:173-190: every head k gets the per-head loss
+  // `kind` on the full target plus cons_weight * ConsistencyLoss (src/metrics/losses.py:292-324): for k >= 1 the rows with
+  // dist < cons_lo[k-1] or dist > cons_hi[k-1] pull head k towards the (detached) output of head k-1
+  float cons_weight;
+  float cons_lo[8], cons_hi[8];
 };
 
 struct TvArgs {               // tv_kernel (optim.cu): adds the TV gradient / loss to the per-row loss pieces of one batch

@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         if (tid == 128) LG_TRACE(3 + 3 * n_done);
         const int grow = tile * kTileM + row;
         bool masked = false;            // BoundedLinear: this row's input to the linear was zeroed
-        if (a.dist && grow < a.bs) { const float d = a.dist[grow]; masked = (d < a.bound_lo) || (d > a.bound_hi); }
+        if (a.dist && grow < a.bs) { const float d = a.dist[(a.dist_row_offset ? *a.dist_row_offset : 0) + grow]; masked = (d < a.bound_lo) || (d > a.bound_hi); }
         float hd[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
         if (MODE == LG_MFN_DGRAD && a.head_dout && grow < a.bs) {
 #pragma unroll

@@ -68,6 +68,7 @@ struct MfnWorkspace {
   uint64_t mn;                       // Gabor: |mu_j|^2 per stage and feature, fp32 [top + 1][width]
   uint64_t gfin;                     // Gabor: finalised (still scaled) d mu / d gamma, fp32
   uint64_t gl, part, scal, gpart, total;
+  uint64_t msg, msp, dyf;            // fused multi-head loss: per-head float4 loss pieces, per (tile, head) partials, fp32 dL/dy
   int n_tiles, n_split;
 };
 

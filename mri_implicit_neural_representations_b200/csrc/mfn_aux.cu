@@ -215,6 +215,145 @@ __global__ void __launch_bounds__(128) mfn_head_kernel(const __grid_constant__ M
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused multi-head loss
+// Reference src/train_kspace_multiscale.py:173-190: loss = sum_k w_kind * loss_kind(out_k[mask], gt[mask]) + cons_weight *
+// sum_{k >= 1} mse(out_{k-1}[S_{k-1}].detach(), out_k[S_{k-1}]), S_i = rows with dist outside [cons_lo[i], cons_hi[i]]
+// (ConsistencyLoss over ALL rows of the batch, src/metrics/losses.py:317-323).  One block per row tile evaluates every live
+// head for its 128 rows, so a thread holds all head outputs of its row: per head it leaves the unnormalised gradient pieces
+// (loss part, consistency part) and the tile partials; the normalisers (masked row count, |S_i|) are applied after the
+// fixed-order reduction in mfn_ms_scalars_kernel.  out_f == 2, at most 4 live heads.
+__global__ void __launch_bounds__(128) mfn_ms_head_kernel(const __grid_constant__ MfnAuxArgs a) {
+  __shared__ float sW[2][512];
+  __shared__ float red[4][4][8];      // [head][warp][slot]
+  const MfnModel& M = a.m;
+  const int tile = blockIdx.x, row = threadIdx.x, lane = row & 31, q = row >> 5;
+  const int row_base = a.row_offset ? *a.row_offset : 0;
+  const int grow = tile * kTileM + row;
+  const bool valid = grow < a.bs;
+  const size_t srow = static_cast<size_t>(row_base) + grow;
+  const uint32_t tile_bytes = kTileM * M.width * 2;
+  float y[4][2];
+  int hk = 0;
+  for (int k = 0; k < M.n_heads; ++k) {
+    if (!M.head_live[k]) continue;
+    __syncthreads();
+    for (int i = row; i < 2 * M.width; i += 128) sW[i / M.width][i % M.width] = a.params[M.head_w[k] + i];
+    __syncthreads();
+    const uint8_t* zimg = a.ws + a.w.z[M.head_stage[k]] + static_cast<size_t>(tile) * tile_bytes + row * 16;
+    float a0 = 0.f, a1 = 0.f;
+    for (int kg = 0; kg < M.width / 8; ++kg) {
+      float z[8];
+      mfn_unpack8(ld_global_nc_v4(zimg + static_cast<size_t>(kg) * 2048), z);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a0 = fmaf(z[e], sW[0][kg * 8 + e], a0); a1 = fmaf(z[e], sW[1][kg * 8 + e], a1); }
+    }
+    y[hk][0] = a0 + a.params[M.head_b[k]]; y[hk][1] = a1 + a.params[M.head_b[k] + 1];
+    if (valid && a.out) {
+      float* o = a.out + static_cast<size_t>(grow) * (M.n_out * 2) + hk * 2;
+      o[0] = y[hk][0]; o[1] = y[hk][1];
+    }
+    ++hk;
+  }
+  float t[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+  bool in_loss = false;
+  float dist = 0.f;
+  if (valid) {
+    in_loss = a.mask ? (a.mask[srow] != 0) : true;
+    t[0] = a.gt[srow * 2]; t[1] = a.gt[srow * 2 + 1];
+    dist = a.dist ? a.dist[srow] : 0.f;
+  }
+  for (int h = 0; h < M.n_out; ++h) {
+    float lA = 0.f, lC = 0.f, cnt = 0.f, cntS = 0.f, amA = 0.f, amB = 0.f;
+    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && in_loss) {
+      float yy[kMaxOut] = {y[h][0], y[h][1], 0.f, 0.f};
+      RowLoss r = loss_row(a.loss, 2, yy, t);
+      lA = r.lossA; cnt = 1.f;
+      gq.x = r.gA[0]; gq.y = r.gA[1];
+      amA = fmaxf(fabsf(r.gA[0]), fabsf(r.gA[1]));
+    }
+    if (valid && h >= 1 && a.loss.cons_weight != 0.f && (dist < a.loss.cons_lo[h - 1] || dist > a.loss.cons_hi[h - 1])) {
+      const float d0 = y[h][0] - y[h - 1][0], d1 = y[h][1] - y[h - 1][1];
+      gq.z = d0; gq.w = d1; lC = d0 * d0 + d1 * d1; cntS = 1.f;
+      amB = fmaxf(fabsf(d0), fabsf(d1));
+    }
+    reinterpret_cast<float4*>(a.ws + a.w.msg)[(static_cast<size_t>(h) * a.w.n_tiles + tile) * kTileM + row] = gq;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lA += __shfl_xor_sync(0xffffffffu, lA, off); lC += __shfl_xor_sync(0xffffffffu, lC, off);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, off); cntS += __shfl_xor_sync(0xffffffffu, cntS, off);
+      amA = fmaxf(amA, __shfl_xor_sync(0xffffffffu, amA, off)); amB = fmaxf(amB, __shfl_xor_sync(0xffffffffu, amB, off));
+    }
+    if (lane == 0) { red[h][q][0] = lA; red[h][q][1] = lC; red[h][q][2] = cnt; red[h][q][3] = cntS; red[h][q][4] = amA; red[h][q][5] = amB; }
+  }
+  __syncthreads();
+  if (row < M.n_out) {
+    const int h = row;
+    float* pdst = reinterpret_cast<float*>(a.ws + a.w.msp) + (static_cast<size_t>(tile) * M.n_out + h) * kPartialsPerTile;
+    for (int s = 0; s < 4; ++s) pdst[s] = (red[h][0][s] + red[h][1][s]) + (red[h][2][s] + red[h][3][s]);
+    pdst[4] = fmaxf(fmaxf(red[h][0][4], red[h][1][4]), fmaxf(red[h][2][4], red[h][3][4]));
+    pdst[5] = fmaxf(fmaxf(red[h][0][5], red[h][1][5]), fmaxf(red[h][2][5], red[h][3][5]));
+    pdst[6] = 0.f; pdst[7] = 0.f;
+  }
+}
+
+// Fixed-order reduction of the (tile, head) partials -> per-head normalisers and the composite loss.
+__global__ void __launch_bounds__(256) mfn_ms_scalars_kernel(const __grid_constant__ MfnAuxArgs a) {
+  __shared__ float part[8][4];
+  const MfnModel& M = a.m;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* g = reinterpret_cast<float*>(a.ws + a.w.scal);
+  const float* src = reinterpret_cast<const float*>(a.ws + a.w.msp);
+  float total = 0.f;
+  for (int h = 0; h < M.n_out; ++h) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int t = tid; t < a.w.n_tiles; t += 256) {
+      const float* qd = src + (static_cast<size_t>(t) * M.n_out + h) * kPartialsPerTile;
+      s0 += qd[0]; s1 += qd[1]; s2 += qd[2]; s3 += qd[3];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, off); s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+    }
+    __syncthreads();
+    if (lane == 0) { part[warp][0] = s0; part[warp][1] = s1; part[warp][2] = s2; part[warp][3] = s3; }
+    __syncthreads();
+    if (tid == 0) {
+      float lA = 0.f, lC = 0.f, cnt = 0.f, cntS = 0.f;
+      for (int w = 0; w < 8; ++w) { lA += part[w][0]; lC += part[w][1]; cnt += part[w][2]; cntS += part[w][3]; }
+      const float m = fmaxf(cnt, 1.f);
+      float cA = 0.f, lv = 0.f;
+      switch (a.loss.kind) {       // weights of the training loop, as in reduce_step_scalars
+        case LOSS_L2:   cA = 1.f / (m * 2.f);  lv = lA * 0.5f / (m * 2.f); break;
+        case LOSS_L1:   cA = 0.5f / (m * 2.f); lv = lA * 0.5f / (m * 2.f); break;
+        case LOSS_MSLE: cA = 1.f / (m * 2.f);  lv = lA * 0.5f / (m * 2.f); break;
+        case LOSS_LSL:  cA = 1.f / m;          lv = lA * 0.5f / m; break;
+        default: break;
+      }
+      float cB = 0.f;
+      if (cntS > 0.f) { cB = a.loss.cons_weight / cntS; lv += a.loss.cons_weight * lC / (2.f * cntS); }
+      g[SC_HEAD_NORM + 2 * h] = cA; g[SC_HEAD_NORM + 2 * h + 1] = cB;
+      total += lv;
+    }
+  }
+  if (tid == 0) g[SC_MS_LOSS] = total;
+}
+
+// dL/dy [rows, n_out * 2] fp32 (normalised, unscaled) for the backward entry, which then proceeds as for an external dL/dout.
+__global__ void __launch_bounds__(128) mfn_ms_dout_kernel(const __grid_constant__ MfnAuxArgs a) {
+  const MfnModel& M = a.m;
+  const int tile = blockIdx.x, row = threadIdx.x;
+  const int grow = tile * kTileM + row;
+  const float* g = reinterpret_cast<const float*>(a.ws + a.w.scal);
+  float* dy = reinterpret_cast<float*>(a.ws + a.w.dyf) + static_cast<size_t>(grow) * (M.n_out * 2);
+  for (int h = 0; h < M.n_out; ++h) {
+    const float4 gq = reinterpret_cast<const float4*>(a.ws + a.w.msg)[(static_cast<size_t>(h) * a.w.n_tiles + tile) * kTileM + row];
+    const float cA = g[SC_HEAD_NORM + 2 * h], cB = g[SC_HEAD_NORM + 2 * h + 1];
+    dy[2 * h] = cA * gq.x + cB * gq.z; dy[2 * h + 1] = cA * gq.y + cB * gq.w;
+  }
+}
+
 // amax partials of an external dL/dout [bs, n_out*out_f]
 __global__ void __launch_bounds__(128) mfn_dout_amax_kernel(const float* dout, int bs, int ld, float* partials) {
   __shared__ float red[4];
@@ -238,6 +377,7 @@ __global__ void __launch_bounds__(256) mfn_scalars_kernel(const __grid_constant_
   __shared__ float sc[kScalars];
   float* g = reinterpret_cast<float*>(a.ws + a.w.scal);
   reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step, g, sc);
+  if (threadIdx.x == 0 && a.train == 2) g[SC_LOSS] = g[SC_MS_LOSS];      // fused multi-head step: the loss was reduced by mfn_ms_scalars_kernel
   if (threadIdx.x == 0) {
     // per-stage scales from the previous step's amax (lagged dynamic scaling, 2^10 headroom below the fp16 maximum);
     // uncalibrated stages start at the loss scale divided by 16
@@ -343,7 +483,7 @@ __global__ void __launch_bounds__(256) mfn_top_kernel(const __grid_constant__ Mf
       if (M.bounded) {
         st_global_v4(a.ws + a.w.dhu[top] + static_cast<size_t>(tile) * tile_bytes + off, mfn_pack8(dh));
         bool masked = false;
-        if (grow < a.bs) { const float dd = a.dist[grow]; masked = (dd < M.bound_lo[top]) || (dd > M.bound_hi[top]); }
+        if (grow < a.bs) { const float dd = a.dist[(a.row_offset ? *a.row_offset : 0) + grow]; masked = (dd < M.bound_lo[top]) || (dd > M.bound_hi[top]); }
         if (masked) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) dh[e] = 0.f;
@@ -388,6 +528,12 @@ cudaError_t launch_mfn_dout_amax(const MfnAuxArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_mfn_scalars(const MfnAuxArgs& a, cudaStream_t st) {
   mfn_scalars_kernel<<<1, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_mfn_ms_loss(const MfnAuxArgs& a, cudaStream_t st) {
+  mfn_ms_head_kernel<<<a.w.n_tiles, 128, 0, st>>>(a);
+  mfn_ms_scalars_kernel<<<1, 256, 0, st>>>(a);
+  mfn_ms_dout_kernel<<<a.w.n_tiles, 128, 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_mfn_top(const MfnAuxArgs& a, cudaStream_t st) {

@@ -102,7 +102,8 @@ struct LGemmArgs {
   const float* head_dout;   // [rows, head_ld] fp32 dL/dout (unscaled) or null
   const float* head_w;      // [out_f, width] weight of the head attached to the target stage
   int head_col, head_ld, out_f, bs;
-  const float* dist;        // BoundedLinear: per-row distance [rows] or null
+  const float* dist;        // BoundedLinear: per-row distance [rows] or null (indexed from *dist_row_offset when that is given)
+  const int* dist_row_offset;
   float bound_lo, bound_hi; // FWD: rows with dist outside [lo, hi] are zeroed before THIS stage's linear;
                             // DGRAD: the same mask of the TARGET stage, applied to the stored dh (W-wgrad and dgrad operand)
   // Gabor filters (reference mfn.py:96-131): envelope E = exp(-gamma/2 (|x|^2 + |mu|^2 - 2 x.mu)) as its own GEMM pass

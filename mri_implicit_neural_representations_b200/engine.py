@@ -28,8 +28,17 @@ def _loss_desc(loss: str, loss_opts: Optional[dict]):
     tvw, tvh, tvww = (float(tv[2]) if len(tv) > 2 else 1e-4, int(tv[0]), int(tv[1])) if tv else (0.0, 0, 0)
     dp = o.get("dp_norm")            # (device float table [n_batches, 2], rows per local batch): see inr_loss_desc.dp_norm
     dp_ptr, dp_rows = (dp[0].data_ptr(), int(dp[1])) if dp is not None else (None, 0)
-    return L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
-                      float(o.get("hdr_ff_factor", 0.0)), tvw, tvh, tvww, dp_ptr, dp_rows)
+    d = L.LossDesc(L.LOSS[loss], float(o.get("hdr_eps", 0.0)), float(o.get("hdr_ff_sigma", 1.0)),
+                   float(o.get("hdr_ff_factor", 0.0)), tvw, tvh, tvww, dp_ptr, dp_rows)
+    cons = o.get("consistency")      # (bounds [(lo, hi), ...], weight): ConsistencyLoss of the multi-scale loop
+    if cons is not None:
+        bounds, weight = cons
+        if len(bounds) > 8:
+            raise L.InrError("at most 8 consistency bounds")
+        d.cons_weight = float(weight)
+        for i, (lo, hi) in enumerate(bounds):
+            d.cons_bounds[2 * i], d.cons_bounds[2 * i + 1] = float(lo), float(hi)
+    return d
 
 
 def selftest_umma(mode: int, variant: int = 0):
@@ -243,10 +252,24 @@ class ChainEngine:
     # ---- fused step --------------------------------------------------------------------------------
     def train_step(self, loss: str, coords: Optional[torch.Tensor], gt: torch.Tensor, bs: int, x: Optional[torch.Tensor] = None,
                    mask: Optional[torch.Tensor] = None, loss_opts: Optional[dict] = None, use_cursor: bool = False,
-                   out: Optional[torch.Tensor] = None):
+                   out: Optional[torch.Tensor] = None, dist: Optional[torch.Tensor] = None):
         """One fused forward+loss+backward+Adam step on rows [cursor, cursor+bs) (or [0, bs)) of the resident
-        arrays.  Asynchronous; the loss lands in self.loss_out."""
+        arrays.  Asynchronous; the loss lands in self.loss_out.  dist (multi-scale models): fp32 [rows] distance to the
+        k-space centre, indexed like coords; loss_opts['consistency'] = (bounds, weight) adds the ConsistencyLoss term."""
         ld = _loss_desc(loss, loss_opts)
+        if dist is not None or self.plan.model in ("MultiscaleFourier", "BoundedFourier"):
+            if not self._calibrated:        # gradients-only pass: calibrates the lagged per-stage gradient scales
+                L.check(L.lib.inr_grad_step_dist(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords),
+                                                 _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), _ptr(dist), bs, None,
+                                                 _ptr(self.workspace), _ptr(out), _ptr(self.grads), _ptr(self.loss_out), _stream()),
+                        "inr_grad_step_dist(calibration)")
+            L.check(L.lib.inr_train_step_dist(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg),
+                                              _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step),
+                                              _ptr(coords), _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), _ptr(dist), bs,
+                                              _ptr(self.cursor) if use_cursor else None, _ptr(self.workspace), _ptr(out),
+                                              _ptr(self.loss_out), _stream()), "inr_train_step_dist")
+            self._calibrated = True
+            return
         if self._lagged_scales and not self._calibrated:
             self._calibrate(ld, coords, x, gt, mask, bs, out)
         L.check(L.lib.inr_train_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
@@ -301,12 +324,20 @@ class ChainEngine:
         return mat
 
     def grad_step(self, loss: str, coords, gt, bs: int, x=None, mask=None, loss_opts=None, use_cursor: bool = False, out=None,
-                  grads: Optional[torch.Tensor] = None):
+                  grads: Optional[torch.Tensor] = None, dist: Optional[torch.Tensor] = None):
         """forward + loss + backward only; gradients land in self.grads, or in `grads` (e.g. a PeerGradExchange buffer)
         (data-parallel: all-reduce them, then adam_step -- or adam_step_peers)."""
         gbuf = self.grads if grads is None else grads
         assert gbuf.numel() >= self.plan.n_params and gbuf.dtype == torch.float32 and gbuf.is_cuda
         ld = _loss_desc(loss, loss_opts)
+        if dist is not None or self.plan.model in ("MultiscaleFourier", "BoundedFourier"):
+            for _ in range(1 if self._calibrated else 2):
+                L.check(L.lib.inr_grad_step_dist(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords),
+                                                 _ptr(x), _ptr(self.encB), _ptr(gt), _ptr(mask), _ptr(dist), bs,
+                                                 _ptr(self.cursor) if use_cursor else None, _ptr(self.workspace), _ptr(out),
+                                                 _ptr(gbuf), _ptr(self.loss_out), _stream()), "inr_grad_step_dist")
+            self._calibrated = True
+            return gbuf
         if self._lagged_scales and not self._calibrated:
             self._calibrate(ld, coords, x, gt, mask, bs, out)
         L.check(L.lib.inr_grad_step(self.plan.handle, C.byref(ld), _ptr(self.params), _ptr(self.wpack), _ptr(coords), _ptr(x),

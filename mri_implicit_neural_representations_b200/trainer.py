@@ -150,9 +150,12 @@ class FusedTrainer:
 
     def __init__(self, model: FusedChain, encoder: Positional_Encoder, optim: FusedAdam, loss: str, batch_size: int,
                  coords: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None, loss_opts: Optional[dict] = None,
-                 use_graph: bool = True, tv: Optional[tuple] = None, dp: Optional[DataParallel] = None):
+                 use_graph: bool = True, tv: Optional[tuple] = None, dp: Optional[DataParallel] = None,
+                 dist: Optional[torch.Tensor] = None, consistency: Optional[tuple] = None):
         """tv = (H, W[, weight]): per-coil batches (batch_size == H * W) with the total-variation term of
-        src/train.py:173-174 added on every batch (the reference only reaches it with an undersampling mask)."""
+        src/train.py:173-174 added on every batch (the reference only reaches it with an undersampling mask).
+        dist / consistency = (bounds, weight): the multi-scale loop of src/train_kspace_multiscale.py:164-192 -- the model is
+        called with dist_to_center, every head gets `loss` on the full target plus weight * ConsistencyLoss(bounds)."""
         if loss not in FUSABLE_LOSSES:
             raise L.InrError(f"loss '{loss}' is not fused; use the unfused model(x)/backward path")
         wire = getattr(model, "MODEL", None) in ("WIRE", "WIRE2D")
@@ -171,6 +174,18 @@ class FusedTrainer:
         self.gt = gt.to(dev, torch.float32).contiguous()
         self.mask = None if mask is None else mask.to(dev).to(torch.uint8).contiguous()
         self.n = self.coords.shape[0]
+        self.dist = None if dist is None else dist.to(dev, torch.float32).reshape(-1).contiguous()
+        multi = getattr(model, "MODEL", None) in ("MultiscaleFourier", "BoundedFourier")
+        if multi:
+            if self.dist is None or self.dist.numel() != self.n:
+                raise L.InrError("multi-scale models need dist_to_center for every row")
+            if loss not in ("L2", "L1", "MSLE", "LSL") or tv is not None:
+                raise L.InrError(f"the fused multi-scale step handles L2 / L1 / MSLE / LSL without TV, not '{loss}'"
+                                 + (" + TV" if tv is not None else ""))
+            if dp is not None and dp.world > 1:
+                raise L.InrError("multi-scale fits are not coordinate data-parallel; place whole fits (or ring models) on GPUs")
+            if consistency is not None:
+                self.loss_opts["consistency"] = (list(consistency[0]), float(consistency[1]))
         self.dp = dp if (dp is not None and dp.world > 1) else None
         self.global_bs, self.n_global = self.bs, self.n
         self._full_coords = self.coords               # validation predicts the whole grid on every rank
@@ -221,7 +236,7 @@ class FusedTrainer:
     def _launch(self, bs, par=0):
         if self.dp is None:
             self.eng.train_step(self.loss, self.coords, self.gt, bs, mask=self.mask, loss_opts=self.loss_opts, use_cursor=True,
-                                out=self._out)
+                                out=self._out, dist=self.dist)
         elif self.dp.peer is not None:
             # forward + loss + backward into this rank's peer-mapped buffer of parity `par`; the optimiser kernel waits for
             # every rank's flag, gathers all ranks' gradients over NVLink and applies Adam (no all-reduce kernel)
@@ -300,11 +315,16 @@ class FusedTrainer:
     @torch.no_grad()
     def predict(self, coords: Optional[torch.Tensor] = None, chunk: Optional[int] = None) -> torch.Tensor:
         """Full-grid inference (validation, src/train.py:199-220) through the fused forward, chunked."""
-        coords = self._full_coords if coords is None else coords.to(self.coords.device, torch.float32).contiguous()
+        own = coords is None
+        coords = self._full_coords if own else coords.to(self.coords.device, torch.float32).contiguous()
         chunk = chunk or self.global_bs
         eng = self.model.engine(self._enc_params, chunk)
         eng.set_encoder(self.encoder.B)
-        outs = [eng.forward(coords[i:i + chunk], train=False) for i in range(0, coords.shape[0], chunk)]
+        dist = None
+        if self.dist is not None:        # multi-scale models: every head of every row, [N, n_heads * out]
+            dist = self.dist if own else torch.sqrt(coords[:, 1] ** 2 + coords[:, 2] ** 2)
+        outs = [eng.forward(coords[i:i + chunk], train=False, dist=None if dist is None else dist[i:i + chunk])
+                for i in range(0, coords.shape[0], chunk)]
         return torch.cat(outs)
 
 
@@ -327,7 +347,7 @@ class HostFedStepper:
             raise L.InrError(f"loss '{loss}' is not fused; use the unfused model(x)/backward path")
         dev = eng.params.device
         self.eng, self.loss_name, self.loss_opts, self.bs, self.depth = eng, loss, loss_opts, int(batch_size), int(depth)
-        in_f, out_f, bs = 3, eng.plan.out_cols, self.bs
+        in_f, out_f, bs = 3, int(eng.plan.net["network_output_size"]), self.bs     # targets: one [bs, out] block (multi-head models too)
         up = lambda n: (n + 255) // 256 * 256
         o_gt = up(bs * in_f * 4)
         o_mask = o_gt + up(bs * out_f * 4)

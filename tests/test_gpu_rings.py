@@ -130,7 +130,7 @@ def test_ring_trainer_rejects_unfusable_losses(src_path):
     assert tr.step(0, 0.0, 1.0) is not None
 
 
-def test_training_multiscale_entry_uses_reference_partition(src_path):
+def test_training_multiscale_entry_uses_reference_partition(src_path, tmp_path):
     """train_kspace_multiscale.training_multiscale end to end on a small slice: the ring partition comes from
     clustering.partition_and_stats (reference :72-86), the 8 BoundedLinears get the doubled disc list, training runs."""
     import train_kspace_multiscale as TM
@@ -148,7 +148,7 @@ def test_training_multiscale_entry_uses_reference_partition(src_path):
            "batch_size": bs, "log_iter": 1000, "val_epoch": 1, "image_save_epoch": 100, "transform": False, "data": "knee",
            "use_tv": False, "per_coil": False, "partition": {"no_steps": 16, "no_models": 4}}
     torch.manual_seed(3)
-    hist = TM.training_multiscale(cfg, ds, tl, vl, verbose=False)
+    hist = TM.training_multiscale(cfg, ds, tl, vl, output_path=str(tmp_path), verbose=False)
     assert len(hist) == 2 and all(np.isfinite(h[1]) and np.isfinite(h[2]) for h in hist)
     assert hist[1][1] < hist[0][1]                          # the loss goes down
     _, radii = partition_and_stats(dataset=ds, no_steps=16, no_parts=4, stat="max", show=False)
