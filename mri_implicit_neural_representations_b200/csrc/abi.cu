@@ -8,6 +8,7 @@
 #include <vector>
 #include <new>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/inr_b200.h"
 #include "inr_kernels.cuh"
 #include "wire.cuh"
@@ -64,6 +65,19 @@ struct inr_plan {
 };
 
 static thread_local std::string g_err;
+
+// NVTX ranges around the kernel groups of a step (header-only nvtx3: a no-op unless a profiler injects itself); INR_NVTX=0
+// switches them off
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) {
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("INR_NVTX"); v = (e && e[0] == '0') ? 0 : 1; }
+    on = v != 0;
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 // wgrad units sweep up to three 128-feature B chunks per resident A sub-image: split `n` chunks into equal groups
 static int chunk_group(int n) { const int groups = (n + 2) / 3; return (n + groups - 1) / groups; }
 
@@ -601,6 +615,7 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
                              const float* coords, const float* gt, const uint8_t* mask, int64_t bs, void* ws, float* out, int train,
                              const int* row_off, int* step, cudaStream_t st, cudaEvent_t* gemm_ev = nullptr,
                              bool fold_scalars = false, const float* hyper = nullptr) {
+  NvtxRange nv("inr.wire.forward+loss");
   const WireModel& M = p->wm;
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
@@ -656,6 +671,7 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
 static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const LossDesc& loss, const float* params, const void* wpack,
                               const float* dout, int64_t bs, void* ws, const float* hyper, const int* step, cudaStream_t st,
                               bool scalars_done = false) {
+  NvtxRange nv("inr.wire.backward(dgrad+wgrad)");
   const WireModel& M = p->wm;
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
@@ -1029,6 +1045,7 @@ static int mfn_forward_impl(const inr_plan* p, const MfnWorkspace& w, const Loss
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
   if (M.bounded && !dist) return fail(INR_EINVAL, "BoundedFourier needs dist_to_center");
+  NvtxRange nv("inr.mfn.forward+loss");
   MfnAuxArgs x; mfn_aux_fill(p, w, x, params, ws, bs);
   x.loss = loss; x.coords = coords; x.x = xin; x.encB = encB; x.gt = gt; x.mask = mask; x.dist = dist; x.out = out; x.train = train;
   x.row_offset = row_off; x.step_counter = step;
@@ -1087,6 +1104,7 @@ static int mfn_backward_impl(const inr_plan* p, const MfnWorkspace& w, const Los
   uint8_t* W = static_cast<uint8_t*>(ws);
   const uint8_t* wp = static_cast<const uint8_t*>(wpack);
   if (M.bounded && !dist) return fail(INR_EINVAL, "BoundedFourier needs dist_to_center");
+  NvtxRange nv("inr.mfn.backward(dgrad+wgrad)");
   MfnAuxArgs x; mfn_aux_fill(p, w, x, params, ws, bs);
   x.loss = loss; x.dout = dout; x.dist = dist; x.hyper = hyper; x.step = step; x.row_offset = row_off;
   if (keep_ms_loss) x.train = 2;       // the composite loss value was reduced by mfn_ms_scalars_kernel
@@ -1161,6 +1179,7 @@ extern "C" int inr_pack_weights(const inr_plan* p, const float* params, void* wp
 static int run_forward(const inr_plan* p, const Workspace& w, const LossDesc& loss, const float* params, const void* wpack,
                        const float* coords, const float* x, const float* encB, const float* gt, const uint8_t* mask,
                        int64_t bs, void* ws, float* out, int train, const int* row_off, int* step, cudaStream_t st) {
+  NvtxRange nv("inr.chain.forward+loss");
   FwdArgs f{};
   f.m = p->model; f.w = w; f.loss = loss;
   f.params = params; f.wpack = static_cast<const uint8_t*>(wpack);
@@ -1230,6 +1249,7 @@ extern "C" int inr_backward_dist(const inr_plan* p, const float* params, const v
 static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& loss, const float* params, const void* wpack,
                         const float* dout, int64_t bs, void* ws, cudaStream_t st, cudaEvent_t mid = nullptr,
                         const float* hyper = nullptr, const int* step = nullptr) {
+  NvtxRange nv("inr.chain.backward(dgrad+wgrad)");
   BwdArgs b{};
   b.hyper = hyper; b.step = step;
   b.m = p->model; b.w = w; b.loss = loss;
@@ -1343,6 +1363,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
                            void* workspace, float* out, float* loss_out_dev, cudaStream_t st, cudaEvent_t* ev,
                            float* grads_only = nullptr, const float* dist = nullptr) {
   const bool no_adam = grads_only != nullptr;
+  NvtxRange nv_step(no_adam ? "inr.grad_step" : "inr.train_step");
   if (!p || !loss || !params || !wpack || !gt || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (!no_adam && (!m || !v || !hyper_dev || !step_dev)) return fail(INR_EINVAL, "bad argument");
   if (p->is_mfn) {

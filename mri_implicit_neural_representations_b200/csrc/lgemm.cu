@@ -163,6 +163,15 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           if (!(a.dbg & 4)) fence_proxy_async_global();
           if (tr) c_flag += clock64() - tq;
         }
+        if (MODE == LG_WIRE_DGRAD && !phantom && lane < 4 && !(a.dbg & 16)) {
+          // the epilogue of this item reads 96 KB the forward pass wrote long ago (activation y and pre-activation (a, b) of
+          // the layer below: four contiguous 24 KB runs, HBM by now): pull them into L2 while the item's MMAs run, so the
+          // epilogue's loads see L2 latency instead of an exposed DRAM round trip per item
+          const LGemmLayer& Lq = a.chain[layer];
+          const uint8_t* base = (lane < 2 ? Lq.in_y : Lq.in_ab) + static_cast<size_t>(tile) * kWTileBytes +
+                                static_cast<size_t>(((lane & 1) ? kWP / 8 : 0) + (kWFeatPerBlock / 8) * nb) * 2048;
+          if (!(lane == 3 && Lq.real_first)) bulk_prefetch_l2(base, (kWFeatPerBlock / 8) * 2048);
+        }
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
           const int n_it = S.k_stages * 2 / KSTEPS;

@@ -197,3 +197,36 @@ def test_hp_grid_search_end_to_end(src_path, tmp_path):
     assert os.path.exists(os.path.join(tmp_path, "hp_search_config_4.yaml"))
     # the two lr = 1e-9 candidates did not learn anything
     assert max(scores[0], scores[1]) > max(scores[2], scores[3])
+
+
+def test_torch_adam_on_model_parameters_keeps_the_fp16_operands_current(src_path):
+    """`torch.optim.Adam(model.parameters())` edits the Parameters in place -- after `.to('cuda')` each
+    Parameter counts its own version, so the engine's fp16 operand copies must be re-packed from a token that includes every
+    Parameter's version.  Three plain torch.optim.Adam steps through the autograd face against the oracle's loop: with stale
+    fp16 weights the tensor-core layers would keep computing with the initial weights and steps 2-3 would not follow."""
+    from models.networks import SIREN, Positional_Encoder
+    torch.manual_seed(13)
+    enc = Positional_Encoder(ENC, device="cuda")
+    model = SIREN(dict(NET)).to("cuda")
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    coords = torch.rand(600, 3, generator=g) * 2 - 1
+    gt = torch.rand(600, 2, generator=g)
+    lr = 1e-4
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    losses = []
+    for _ in range(3):
+        out = model(enc.embedding(coords.cuda()))
+        loss = 0.5 * torch.nn.MSELoss()(out, gt.cuda())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    ref_losses, ref_sd = O.train_steps("SIREN", NET, sd, enc.B.cpu(), "gauss", coords, gt, 3, 600, lr, "L2")
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 2e-3 * b, (losses, ref_losses)
+    assert losses[2] < losses[0]                    # and it actually trains
+    # the hidden (tensor-core) weights moved and the engine sees them: forward equals the oracle on the updated weights
+    new_sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    out2 = model(enc.embedding(coords.cuda()))
+    assert rel(out2, O.siren_forward(new_sd, O.encode(coords, enc.B.cpu(), "gauss"), 4)) <= 1e-3

@@ -114,16 +114,22 @@ def test_wire_backward_teacher_forced_and_gradients(inr, name):
     dzl = torch.complex(dout, torch.zeros_like(dout))
     assert rel(gv[f"net.{L}.weight"], dzl.t() @ h[L].conj()) <= TOL
     assert rel(gv[f"net.{L}.bias"].real, dout.sum(0)) <= TOL
-    # end to end against fp64 autograd: within the chaotic drift band (fp32 reference vs fp64: 1e-2 .. 8e-2)
+    # end to end against fp64 autograd (NOT teacher-forced): the network is ill-conditioned, the fp32 reference's own gradients
+    # sit 1e-2 .. 8e-2 from fp64 -- so the engine is held to a multiple of the fp32 reference's distance, tensor by tensor
     P = {k: v.clone().requires_grad_(not (k.endswith("omega_0") or k.endswith("scale_0"))) for k, v in sd64.items()}
     o64 = O.wire_forward(P, x64, depth)
     s64, g64 = (o64, gt.double()) if mask is None else (o64[mask], gt.double()[mask])
     _, d64 = loss_and_grad(loss_kind, opts, s64.detach(), g64, x64)
     live = [k for k in P if P[k].requires_grad]
     ref = dict(zip(live, torch.autograd.grad(s64, [P[k] for k in live], grad_outputs=d64)))
-    band = 2e-2 if name == "wire_l2" else 3e-1
+    P32 = {k: v.clone().requires_grad_(k in live) for k, v in sd.items()}
+    o32 = O.wire_forward(P32, coords, depth)
+    s32, g32 = (o32, gt) if mask is None else (o32[mask], gt[mask])
+    _, d32 = loss_and_grad(loss_kind, opts, s32.detach(), g32, coords)
+    ref32 = dict(zip(live, torch.autograd.grad(s32, [P32[k] for k in live], grad_outputs=d32)))
     for k in live:
-        assert rel(gv[k], ref[k]) <= band, (k, rel(gv[k], ref[k]))
+        own = rel(ref32[k], ref[k])                      # the fp32 reference arithmetic against fp64
+        assert rel(gv[k], ref[k]) <= 4 * own + 5e-3, (k, rel(gv[k], ref[k]), own)
 
 
 def test_wire_fused_steps_and_frozen_parameters(inr):
