@@ -228,6 +228,13 @@ int inr_profile_step(const inr_plan* plan, const inr_loss_desc* loss, float* par
                      const uint8_t* mask, int64_t bs, void* workspace, float* out, int32_t reps, float* ms_out4,
                      void* stream);
 
+/* Concurrent fits on ONE device (HP search, src/parameter_search: many small fits per GPU on separate streams).  The chained
+ * layer-GEMM launches of WIRE / WIRE2D hand tiles from CTA to CTA and need all their CTAs resident; two such launches of
+ * different fits that each want the whole chip can starve each other (bounded wait -> trap).  inr_set_sm_budget(n) caps every
+ * chained launch of this process at n SMs: give concurrent fits budgets that sum to at most the SM count (e.g. 74 + 74) and
+ * they run side by side.  0 (default) = the whole chip, one fit per device at a time.  Process-global. */
+int inr_set_sm_budget(int32_t n_sm);
+
 /* debugging: CTA 0 of the forward kernel writes %globaltimer stamps of its phases into this device buffer of
  * 64 uint64 (NULL switches tracing off; off by default).  Process-global, not thread-safe. */
 int inr_debug_set_trace(void* dev_u64_buffer_64);

@@ -5,7 +5,7 @@ There is no fallback path: touching any engine symbol without the built CUDA lib
 (`build` is importable on its own so the library can be (re)built before it is loaded.)"""
 
 _ENGINE_SYMBOLS = {"InrError": "_lib", "lib": "_lib", "LIB_PATH": "_lib",
-                   "ChainEngine": "engine", "Plan": "engine", "selftest_umma": "engine"}
+                   "ChainEngine": "engine", "Plan": "engine", "selftest_umma": "engine", "set_sm_budget": "engine"}
 
 
 def __getattr__(name):

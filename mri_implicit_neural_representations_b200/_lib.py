@@ -42,7 +42,7 @@ EXPORTS = ["inr_last_error", "inr_plan_create", "inr_plan_destroy", "inr_plan_pa
            "inr_plan_tensor_count", "inr_plan_tensor", "inr_wpack_bytes", "inr_workspace_bytes",
            "inr_scalars_offset", "inr_workspace_layout", "inr_pack_weights", "inr_forward", "inr_backward",
            "inr_forward_dist", "inr_backward_dist", "inr_adam_step", "inr_adam_step_peers",
-           "inr_train_step", "inr_train_step_dist", "inr_grad_step", "inr_grad_step_dist", "inr_profile_step", "inr_debug_set_trace", "inr_selftest_umma"]
+           "inr_train_step", "inr_train_step_dist", "inr_grad_step", "inr_grad_step_dist", "inr_profile_step", "inr_debug_set_trace", "inr_selftest_umma", "inr_set_sm_budget"]
 
 
 def _load():
@@ -78,6 +78,7 @@ def _load():
                                      C.POINTER(C.c_float), vp]
     lib.inr_adam_step_peers.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), i32, i32, vp, vp, vp, vp, vp, vp]
     lib.inr_debug_set_trace.argtypes = [vp]
+    lib.inr_set_sm_budget.argtypes = [i32]
     lib.inr_selftest_umma.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name != "inr_last_error":

@@ -22,6 +22,8 @@ cudaError_t launch_adam(const AdamArgs& a, cudaStream_t stream);
 cudaError_t launch_pack(const AdamArgs& a, cudaStream_t stream);
 cudaError_t launch_dout_amax(const float* dout, int bs, int out_f, float* partials, int n_tiles, cudaStream_t stream);
 cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream);
+void lgemm_set_sm_budget(int n);
+int lgemm_sm_budget();
 cudaError_t launch_wire_first(const WireAuxArgs& a, cudaStream_t st);
 cudaError_t launch_wire_last(const WireAuxArgs& a, cudaStream_t st);
 cudaError_t launch_wire_scalars(const WireAuxArgs& a, cudaStream_t st);
@@ -135,6 +137,11 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 extern "C" const char* inr_last_error(void) { return g_err.c_str(); }
+extern "C" int inr_set_sm_budget(int32_t n_sm) {
+  if (n_sm < 0) return fail(INR_EINVAL, "SM budget must be >= 0 (0 = whole chip)");
+  inr::lgemm_set_sm_budget(n_sm);
+  return INR_OK;
+}
 static int g_trace_lgemm_sel = -1, g_trace_lgemm_count = 0;   // debug: which layer-GEMM launch after set_trace gets the buffer
 extern "C" int inr_debug_set_trace(void* dev_u64_buffer_64) {
   g_trace = static_cast<unsigned long long*>(dev_u64_buffer_64);

@@ -645,6 +645,14 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+// Chained launches need every CTA resident.  Two fits stepping concurrently on one device (HP search: many small fits per GPU
+// on separate streams) must therefore share the SMs explicitly: inr_set_sm_budget(n) caps the grid of every chained launch of
+// this process at n SMs, so that the chained kernels of all concurrent fits fit on the chip together (budgets summing to at
+// most the SM count); non-chained kernels never wait on other CTAs and simply drain.  0 = the whole chip (one fit at a time).
+static int g_sm_budget = 0;
+void lgemm_set_sm_budget(int n) { g_sm_budget = n > 0 ? n : 0; }
+int lgemm_sm_budget() { return g_sm_budget; }
+
 // WIRE layer chains run on CTA pairs (INR_LGEMM_PAIR=0 keeps single CTAs with the same pair-packed weights: debugging only)
 static bool lgemm_pair_enabled() {
   static int v = -1;
@@ -676,6 +684,7 @@ static cudaError_t lgemm_launch_one(const LGemmArgs& a, int n_sm, cudaStream_t s
   const bool chain = a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD || a.mode == LG_W2D_FWD || a.mode == LG_W2D_DGRAD;
   const int rowgroups = PAIR ? (a.n_tiles + 1) / 2 : a.n_tiles;
   const int items = rowgroups * a.n_nblocks * (chain ? a.chain_len : 1);
+  if (chain && g_sm_budget > 0 && g_sm_budget < n_sm) n_sm = g_sm_budget < 2 ? 2 : g_sm_budget;
   int walkers = PAIR ? n_sm / 2 : n_sm;                    // never more CTAs than SMs
   if (PAIR && walkers > max_clusters) walkers = max_clusters;
   if (items < walkers) walkers = items;

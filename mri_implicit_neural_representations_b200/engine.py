@@ -47,6 +47,12 @@ def selftest_umma(mode: int, variant: int = 0):
     return err.value, ref.value
 
 
+def set_sm_budget(n_sm: int):
+    """Cap every chained (WIRE / WIRE2D layer-chain) launch of this process at `n_sm` SMs so that several fits can step
+    concurrently on one device without starving each other (inr_set_sm_budget); 0 = the whole chip."""
+    L.check(L.lib.inr_set_sm_budget(int(n_sm)), "inr_set_sm_budget")
+
+
 class Plan:
     """Immutable description of one model (inr_plan): layer table, parameter layout, work units."""
 

@@ -76,8 +76,7 @@ def test_all_false_mask_gives_zero_gradient_and_no_nan_in_parameters(inr):
 
 def test_unsupported_requests_fail_loudly(inr):
     net = dict(G.NET_256)
-    with pytest.raises(Exception):
-        inr.Plan("SIREN", dict(net, network_last_linear=False), G.ENC_GAUSS)          # sine output layer: not built
+    assert inr.Plan("SIREN", dict(net, network_last_linear=False), G.ENC_GAUSS).wide  # sine output layer: built since round 2 (wide chain)
     with pytest.raises(Exception):
         inr.Plan("SIREN", net, {"embedding": "LogF", "scale": 4, "embedding_size": 256, "coordinates_size": 3})
     with pytest.raises(Exception):
@@ -89,3 +88,47 @@ def test_unsupported_requests_fail_loudly(inr):
     with pytest.raises(Exception):                                                      # TV needs bs == H * W and `out`
         eng.train_step("L2", torch.zeros(100, 3, device="cuda"), torch.zeros(100, 2, device="cuda"), 100,
                        loss_opts={"tv": (8, 8)})
+
+
+def test_two_wire_fits_step_concurrently_under_an_sm_budget():
+    """chained launches need all their CTAs resident, so two fits stepping at the same time on one device
+    used to be able to starve each other (bounded wait -> trap).  With inr_set_sm_budget(74) each chained launch takes half
+    the chip: two WIRE fits on two streams run side by side and end exactly where the same fits end when run one after the
+    other (the grid size does not enter the arithmetic: every reduction has a fixed order)."""
+    import mri_implicit_neural_representations_b200 as inr
+    from mri_implicit_neural_representations_b200 import init as pinit
+    net = {"network_input_size": 3, "network_output_size": 2, "network_depth": 3, "network_width": 256, "first_omega_0": 30,
+           "hidden_omega_0": 30, "scale": 15}
+    bs = 6000
+
+    def make(seed):
+        torch.manual_seed(seed)
+        eng = inr.ChainEngine(inr.Plan("WIRE", net, {"embedding": "none"}), max_batch=bs, lr=1e-4)
+        eng.load_tensors([t for _, t in pinit.wire_tensors(net)])
+        g = torch.Generator().manual_seed(seed)
+        return eng, (torch.rand(bs, 3, generator=g) * 2 - 1).cuda(), (torch.randn(bs, 2, generator=g) * 0.05).cuda()
+
+    def run(concurrent):
+        fits = [make(1), make(2)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        for eng, c, y in fits:                       # calibration pass + kernel attributes on the default stream
+            eng.train_step("L2", c, y, bs)
+        torch.cuda.synchronize()
+        for _ in range(20):
+            for (eng, c, y), st in zip(fits, streams):
+                with torch.cuda.stream(st if concurrent else torch.cuda.current_stream()):
+                    eng.train_step("L2", c, y, bs)
+            if not concurrent:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return [eng.params.clone() for eng, _, _ in fits]
+
+    inr.set_sm_budget(74)
+    try:
+        together = run(True)
+        apart = run(False)
+    finally:
+        inr.set_sm_budget(0)
+    for a, b in zip(together, apart):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b)
