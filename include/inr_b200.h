@@ -175,12 +175,15 @@ int inr_adam_step(const inr_plan* plan, float* params, const float* grads, float
 /* inr_adam_step with the data-parallel gradient exchange fused into the optimiser kernel (replaces the
  * all-reduce a DistributedDataParallel wrapper of src/train.py:189-190 would issue).  peer_grads / peer_flags are HOST
  * arrays of n_ranks DEVICE pointers into symmetric (peer-mapped, NVLink) memory: rank q's reduced fp32 gradients of this
- * step [param_count] (as written by inr_grad_step) and rank q's flag array uint32[8] (zero-initialised, same array every
- * step).  The kernel publishes *step_dev to every rank's flags, waits (bounded) until every rank has published it, and
- * uses mean_q(peer_grads[q]) in rank order as the gradient.  The caller alternates two gradient buffers by step parity. */
+ * step [param_count] (as written by inr_grad_step) and rank q's flag block uint32[64] (zero-initialised, same block every
+ * step; words 0..7 = last step each rank published, word 32 = finished-CTA counter).  Like inr_train_step, the kernel advances
+ * the device step counter itself: every CTA works with t = *step_dev + 1, publishes t to every rank's flags, waits (bounded,
+ * INR_PEER_TIMEOUT_S) until every rank has published it, uses mean_q(peer_grads[q]) in rank order as the gradient, and the
+ * last CTA to finish stores t -- no host-enqueued increment sits between the kernels of a step.  The caller alternates two
+ * gradient buffers by step parity. */
 int inr_adam_step_peers(const inr_plan* plan, float* params, const float* const* peer_grads, uint32_t* const* peer_flags,
                         int32_t n_ranks, int32_t rank, float* exp_avg, float* exp_avg_sq, void* wpack,
-                        const float* hyper_dev, const int32_t* step_dev, void* stream);
+                        const float* hyper_dev, int32_t* step_dev, void* stream);
 
 /* replaces: the whole loop body src/train.py:160-192 for fusable model+loss combinations:
  * forward, loss (+ row mask, src/train.py:172-177), backward, Adam, fp16 re-pack.

@@ -1336,7 +1336,7 @@ extern "C" int inr_adam_step(const inr_plan* p, float* params, const float* grad
 
 extern "C" int inr_adam_step_peers(const inr_plan* p, float* params, const float* const* peer_grads, uint32_t* const* peer_flags,
                                    int32_t n_ranks, int32_t rank, float* m, float* v, void* wpack, const float* hyper_dev,
-                                   const int32_t* step_dev, void* stream) {
+                                   int32_t* step_dev, void* stream) {
   if (!p || !params || !peer_grads || !peer_flags || !m || !v || !wpack || !hyper_dev || !step_dev) return fail(INR_EINVAL, "null argument");
   if (n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) return fail(INR_EINVAL, "bad rank / world size (at most 8 ranks)");
   PeerArgs P{};
@@ -1350,6 +1350,7 @@ extern "C" int inr_adam_step_peers(const inr_plan* p, float* params, const float
     if (!peer_grads[q] || !peer_flags[q]) return fail(INR_EINVAL, "null peer pointer");
     P.grads[q] = peer_grads[q]; P.flags[q] = peer_flags[q];
   }
+  P.done = peer_flags[rank] + 32;      // word 32 of this rank's own flag block: finished-CTA counter of the optimiser kernel
   if (p->is_wire) {
     WireAdamArgs wa; wire_adam_fill(p, wa);
     wa.params = params; wa.mom = m; wa.var = v; wa.wpack = static_cast<uint8_t*>(wpack); wa.gpart = peer_grads[rank];

@@ -172,6 +172,9 @@ struct PeerArgs {
   unsigned int* flags[kMaxRanks];   // rank q's flag array uint32[kMaxRanks] (peer-mapped); flags[q][r] = last epoch r published to q
   int n_ranks, rank;                // n_ranks == 0: no exchange
   unsigned long long timeout_ns;    // entry barrier: trap after this long without the other ranks (0: 120 s)
+  // the optimiser kernel itself advances the device step counter (no host-enqueued increment between the kernels of a step):
+  // every CTA uses t = *step + 1; the LAST CTA to finish (counter `done`, self-resetting) stores t
+  unsigned int* done;
 };
 
 struct SegDesc {          // one parameter tensor for the optimiser / packer

@@ -85,6 +85,15 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& P, unsigned int epo
   }
   __syncthreads();
 }
+// Exit of a peer-mode optimiser kernel: the last CTA to get here publishes the new step count (all CTAs worked with
+// t = old + 1, which they read before any CTA could have stored it: the store happens after EVERY CTA has arrived).
+__device__ __forceinline__ void peer_finish_step(const PeerArgs& P, const int* step, int t) {
+  __syncthreads();
+  if (threadIdx.x == 0 && P.done) {
+    __threadfence();
+    if (atomicAdd(P.done, 1u) == gridDim.x - 1) { *const_cast<int*>(step) = t; *P.done = 0u; __threadfence(); }
+  }
+}
 // Gather phase: the CTA owns parameters [base, base + 4 * blockDim.x); thread t pulls one float4 from every rank (all
 // loads in flight together: the exchange is NVLink-latency bound), adds them in rank order and leaves the mean in
 // shared memory for the per-parameter optimiser code that follows.  `n` is a multiple of 4 (buffers are padded).

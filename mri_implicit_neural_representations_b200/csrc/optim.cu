@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
     if (a.do_adam && a.scal_has_bc && sc) {
       s_c[0] = sc[SC_STEP_SIZE]; s_c[1] = sc[SC_BC2_SQRT];
     } else if (a.do_adam) {
-      const int t = *a.step;
+      const int t = *a.step + (a.peer.n_ranks > 0 && a.peer.done ? 1 : 0);
       const double b1 = a.hyper[1], b2 = a.hyper[2];
       const double bc1 = 1.0 - pow(b1, static_cast<double>(t));
       const double bc2 = 1.0 - pow(b2, static_cast<double>(t));
@@ -79,13 +79,14 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
   const bool peer = a.peer.n_ranks > 0;
   const int reps = peer ? 4 : 1;
   const size_t base = static_cast<size_t>(blockIdx.x) * 256 * reps;
+  const int t_new = peer ? *a.step + (a.peer.done ? 1 : 0) : 0;
   if (peer) {
-    peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
+    peer_barrier(a.peer, static_cast<unsigned int>(t_new));
     peer_gather(a.peer, base, static_cast<size_t>((a.n_params + 3) & ~3), s_g);
   }
   for (int j = 0; j < reps; ++j) {
     const int p = static_cast<int>(base) + j * 256 + threadIdx.x;
-    if (p >= a.n_params) return;
+    if (p >= a.n_params) break;
     const int si = find_seg(a.seg, a.n_seg, p);
     const SegDesc& sg = a.seg[si];
     if (sg.frozen) { if (a.grads) a.grads[p] = 0.f; continue; }
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
     a.params[p] = w;
     if (sg.pack_fwd | sg.pack_bwd) pack_store(sg, a.wpack, p - sg.off, w);
   }
+  if (peer) peer_finish_step(a.peer, a.step, t_new);
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ AdamArgs a) {

@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
 __global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_constant__ WireAdamArgs a) {
   __shared__ float s_c[2];
   const WireModel& M = a.m;
+  griddep_wait();            // launched as a programmatic dependent of the kernel that reduced this rank's gradients
+  const int t_new = *a.step + ((a.peer.n_ranks > 0 && a.peer.done) ? 1 : 0);
   if (threadIdx.x == 0) {
-    const double t = static_cast<double>(*a.step);
+    const double t = static_cast<double>(t_new);
     s_c[0] = static_cast<float>(static_cast<double>(a.hyper[0]) / (1.0 - pow(static_cast<double>(a.hyper[1]), t)));
     s_c[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.hyper[2]), t)));
   }
@@ -166,13 +168,13 @@ __global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_consta
   const int reps = peer ? 4 : 1;
   const size_t base = static_cast<size_t>(blockIdx.x) * 256 * reps;
   if (peer) {
-    peer_barrier(a.peer, static_cast<unsigned int>(*a.step));
+    peer_barrier(a.peer, static_cast<unsigned int>(t_new));
     peer_gather(a.peer, base, static_cast<size_t>((M.n_params + 3) & ~3), s_g);
   }
   const int L = M.depth + 1;
   for (int j = 0; j < reps; ++j) {
     const int p = static_cast<int>(base) + j * 256 + threadIdx.x;
-    if (p >= M.n_params) return;
+    if (p >= M.n_params) break;
     int layer = -1, idx = 0;
     bool frozen = false;
     for (int l = 0; l <= L; ++l) {
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(256) wire_adam_flat_kernel(const __grid_consta
     a.params[p] = w;
     if (layer >= 1) { const int e = idx >> 1; wire_pack_hidden(M, a.wpack, layer, e / M.c, e % M.c, idx & 1, w); }
   }
+  if (peer) peer_finish_step(a.peer, a.step, t_new);
 }
 
 cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st) {
@@ -197,8 +200,7 @@ cudaError_t launch_wire_adam(const WireAdamArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_wire_adam_flat(const WireAdamArgs& a, cudaStream_t st) {
   const int per_cta = a.peer.n_ranks > 0 ? 1024 : 256;
-  wire_adam_flat_kernel<<<(a.m.n_params + per_cta - 1) / per_cta, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_dependent(wire_adam_flat_kernel, dim3((a.m.n_params + per_cta - 1) / per_cta), dim3(256), 0, st, a);
 }
 
 }  // namespace inr

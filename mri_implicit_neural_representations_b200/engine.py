@@ -248,8 +248,8 @@ class ChainEngine:
         of the peer-mapped buffers of `ex` (a parallel.PeerGradExchange) for the given parity, which must alternate with
         every optimiser step (step & 1: the same buffer `grad_step` of this step wrote) -- see PeerGradExchange.
         No rank may do long host-only work between the steps of a fit without the others: the entry barrier of the
-        exchange waits for every rank (INR_PEER_TIMEOUT_S, default 120 s, then the kernel traps)."""
-        self.step += 1
+        exchange waits for every rank (INR_PEER_TIMEOUT_S, default 120 s, then the kernel traps).  The kernel advances the
+        device step counter itself."""
         gp, fp = ex.pointers(parity)
         L.check(L.lib.inr_adam_step_peers(self.plan.handle, _ptr(self.params), gp, fp, ex.world, ex.rank, _ptr(self.exp_avg),
                                           _ptr(self.exp_avg_sq), _ptr(self.wpack), _ptr(self.hyper), _ptr(self.step), _stream()),
