@@ -38,6 +38,18 @@ WORKLOADS = {
         net={"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256},
         encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
         flop_per_coord=1313792, fwd_flop_per_coord=525312),
+    # batch sweep of configs[0] (the reference's config_siren_image.yaml fits with batch_size 300000)
+    **{f"siren_image_l2_bs{b}": dict(
+        model="SIREN", loss="L2", loss_opts=None, batch=b, image_space=True, normalization="max", undersampling=None,
+        net={"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256},
+        encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
+        flop_per_coord=1313792, fwd_flop_per_coord=525312) for b in (25000, 100000, 300000)},
+    # the reference's SIREN k-space configs (config_siren_kspace*.yaml): width 512, depth 8, last_tanh, L2, batch 100000
+    "siren_w512_d8_kspace_l2_bs100000": dict(
+        model="SIREN", loss="L2", loss_opts=None, batch=100000, image_space=False, normalization="max", undersampling=None,
+        net={"network_input_size": 512, "network_output_size": 2, "network_depth": 8, "network_width": 512, "last_tanh": True},
+        encoder={"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3},
+        flop_per_coord=3 * 2 * (512 * 512 + 6 * 512 * 512 + 512 * 2) - 2 * 512 * 512, fwd_flop_per_coord=2 * (512 * 512 + 6 * 512 * 512 + 512 * 2)),
     # WIRE2D (reference config_wire2d_kspace.yaml: depth 8, width 256, omega 30, scale 15), k-space fit, L2
     "wire2d_kspace_l2_bs25000": dict(
         model="WIRE2D", loss="L2", loss_opts=None, batch=25000, image_space=False, normalization="max", undersampling=None,
@@ -529,6 +541,7 @@ def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=
     for _ in range(4):
         one_step()
     torch.cuda.synchronize()
+    eng.cursor.zero_()          # the eager steps advanced the device cursor: the host mirror `pos` below starts at 0 as well
     graph_mode = "cuda graph"
     n_graphs = 2 if peer is not None else 1
     try:
@@ -624,7 +637,11 @@ def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=
                             out=out_buf)
     # WIRE: first, ONE chained launch of the depth forward GEMMs, last (+ step scalars in its last CTA), blast, ONE chained
     # launch of the depth dgrad GEMMs, wgrad, Adam = 7; WIRE2D the same plus its separate scalars kernel = 8
+    wide = bool(getattr(eng.plan, "wide", False))
+    n_sine = max(wl["net"]["network_depth"] - 1, 1)
     n_launch = (7 if wl["model"] == "WIRE" else 8) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
+    if wide:          # encoding, n_sine layer GEMMs, head + loss, scalars, backward entry, n_sine - 1 dgrad GEMMs, wgrad, Adam
+        n_launch = 1 + n_sine + 1 + 1 + 1 + (n_sine - 1) + 1 + 1
     # roofline kernel.  WIRE: the chained forward GEMM launch (all hidden layers in one persistent launch), timed by the
     # events around it; WIRE2D: the average of its per-layer forward GEMM launches; SIREN / FFN: the fused forward kernel
     chained = wire
@@ -721,6 +738,8 @@ def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=
                             "complex Adam + repack") if wire else
                            (f"{n_launch} kernels: encoding, |mu|^2, 9 x (envelope GEMM + stage GEMM), head + loss, TV, scalars, top stage, "
                             "8 dgrad stage GEMMs, split-K wgrad, d mu / d gamma, Adam + repack") if mfn else
+                           (f"{n_launch} kernels: encoding, {n_sine} streamed layer GEMMs (sine epilogue), head + loss, scalars, backward entry, "
+                            f"{n_sine - 1} dgrad layer GEMMs, split-K wgrad, Adam + repack (wide chain: width {wl['net']['network_width']})") if wide else
                            "4 kernels: fused forward+loss, dgrad chain, split-K wgrad, Adam+repack",
                    "loss": wl["loss"], "undersampling": wl["undersampling"],
                    "loss_last_step": loss_dev},
@@ -734,7 +753,8 @@ def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=
                      # DRAM read+write bytes of ONE launch of this kernel from the committed `ncu --set full` capture
                      "traffic": load_traffic(workload)[0], "traffic_source": load_traffic(workload)[1],
                      "kernel": (f"lgemm_kernel ({wl['model']} forward: the {wl['net']['network_depth']} hidden-layer GEMMs + Gabor epilogues as one chained persistent launch)" if wire else
-                                ("forward phase (encoding + 18 lgemm launches + head/loss + TV)" if mfn else "chain_fwd_kernel<SIN>")),
+                                ("forward phase (encoding + 18 lgemm launches + head/loss + TV)" if mfn else
+                                 ("forward phase (encoding + layer GEMMs + head/loss)" if wide else "chain_fwd_kernel<SIN>"))),
                      "kernel_ms": kern_ms,
                      "issued_tflops": (wl["issued_fwd_flop_per_coord"] / n_gemm_launches * bs / (kern_ms * 1e-3) / 1e12) if wire else None,
                      "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peaks['source']})",
