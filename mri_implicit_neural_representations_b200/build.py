@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libinr_b200.so")
-SOURCES = ["abi.cu", "chain_fwd.cu", "chain_bwd.cu", "wgrad.cu", "optim.cu", "selftest.cu", "lgemm.cu", "wire_aux.cu",
+SOURCES = ["abi.cu", "chain_fwd.cu", "chain_bwd.cu", "chain_t.cu", "wgrad.cu", "optim.cu", "selftest.cu", "lgemm.cu", "wire_aux.cu",
            "wire_optim.cu", "wire2d_aux.cu", "wire2d_optim.cu", "mfn_aux.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]

@@ -17,6 +17,8 @@
 namespace inr {
 cudaError_t launch_chain_fwd(const FwdArgs& a, int n_sm, cudaStream_t stream);
 cudaError_t launch_chain_bwd(const BwdArgs& a, int n_sm, cudaStream_t stream);
+cudaError_t launch_chain_fwd_t(const FwdArgs& a, int n_sm, cudaStream_t stream);
+cudaError_t launch_chain_bwd_t(const BwdArgs& a, int n_sm, cudaStream_t stream);
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream);
 cudaError_t launch_adam(const AdamArgs& a, cudaStream_t stream);
 cudaError_t launch_pack(const AdamArgs& a, cudaStream_t stream);
@@ -299,32 +301,60 @@ extern "C" int inr_wpack_bytes(const inr_plan* p, size_t* b) {
   *b = p->is_wire ? p->wm.wpack_bytes : (p->is_mfn ? p->mm.wpack_bytes : p->model.wpack_bytes); return INR_OK;
 }
 
+// Rows per tile of the width-256 chain.  A batch that fills the chip with 128-row tiles runs the row-tile kernels
+// (chain_fwd.cu / chain_bwd.cu); a smaller one (BASELINE configs[0]: 10 000 rows = 79 such tiles on 148 SMs) is cut into
+// one tile of NR <= 80 rows per SM for the transposed kernels of chain_t.cu.  INR_CHAIN_T=0 keeps the 128-row tiles.
+static int chain_tile_rows(const inr_plan* p, int64_t bs) {
+  const char* e = std::getenv("INR_CHAIN_T");          // read per call: the parity tests run both tilings in one process
+  const int on = e ? std::atoi(e) : 0;
+  const int kTMaxRows = 80, kTMaxK0 = 512;
+  if (!on || p->model.k0 > kTMaxK0 || bs > static_cast<int64_t>(p->n_sm) * kTMaxRows) return kTileM;
+  const int nr = 16 * static_cast<int>((bs + 16ll * p->n_sm - 1) / (16ll * p->n_sm));
+  return nr < 16 ? 16 : nr;
+}
+
 static Workspace plan_workspace(const inr_plan* p, int64_t bs) {
   const ChainModel& M = p->model;
   Workspace w{};
-  const int T = static_cast<int>((bs + kTileM - 1) / kTileM);
+  w.tile_rows = chain_tile_rows(p, bs);
+  w.lb = w.tile_rows == kTileM ? 2048 : w.tile_rows * 16 + 16;
+  const int T = static_cast<int>((bs + w.tile_rows - 1) / w.tile_rows);
   w.n_tiles = T;
   const int ns = wgrad_splits(p, T);
   w.n_split = ns;
+  const uint64_t lb = static_cast<uint64_t>(w.lb);
   uint64_t o = 0;
   w.scal_off = o; o += align_up(kScalars * 4, 1024);
   w.part_off = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
-  w.g_off = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
+  // loss records, indexed by batch row; the TV kernel walks them in 128-row blocks whatever the tile height
+  const uint64_t g_rows = std::max<uint64_t>(static_cast<uint64_t>(T) * w.tile_rows, (static_cast<uint64_t>(bs) + 127) / 128 * 128);
+  w.g_off = o; o += align_up(g_rows * 16, 1024);
   for (int l = 0; l <= M.n_gemm; ++l) {
     const int K = l == 0 ? M.k0 : kWidth;
-    w.h_off[l] = o; o += static_cast<uint64_t>(T) * kTileM * K * 2;
+    w.h_off[l] = o; o += align_up(static_cast<uint64_t>(T) * (K / 8) * lb, 1024);
   }
-  for (int l = 0; l < M.n_gemm; ++l) { w.d_off[l] = o; o += static_cast<uint64_t>(T) * kActBytes; }
-  for (int l = 0; l < M.n_gemm; ++l) { w.dz_off[l] = o; o += static_cast<uint64_t>(T) * kActBytes; }
-  w.dzlast_off = o; o += align_up(static_cast<uint64_t>(T) * kDzLastBytes, 1024);
+  for (int l = 0; l < M.n_gemm; ++l) { w.d_off[l] = o; o += align_up(static_cast<uint64_t>(T) * (kWidth / 8) * lb, 1024); }
+  for (int l = 0; l < M.n_gemm; ++l) { w.dz_off[l] = o; o += align_up(static_cast<uint64_t>(T) * (kWidth / 8) * lb, 1024); }
+  w.dzlast_off = o; o += align_up(static_cast<uint64_t>(T) * 2 * lb, 1024);
   w.gpart_off = o; o += align_up(static_cast<uint64_t>(ns) * gpart_stride(M.n_params) * 4, 1024);
   w.total = o;
   return w;
 }
 
+// A workspace sized for `bs` rows serves every smaller batch too.  The chain's tile height steps with the batch (short tiles
+// carry 16 padding bytes per k-group), so its footprint is not monotone across a step: take the largest one up to bs.
+static uint64_t chain_workspace_bytes(const inr_plan* p, int64_t bs) {
+  uint64_t t = plan_workspace(p, bs).total;
+  for (int k = 1; k <= 5; ++k) {
+    const int64_t edge = static_cast<int64_t>(p->n_sm) * 16 * k;
+    if (edge < bs) t = std::max<uint64_t>(t, plan_workspace(p, edge).total);
+  }
+  return t;
+}
+
 extern "C" int inr_workspace_bytes(const inr_plan* p, int64_t bs, size_t* bytes) {
   if (!p || !bytes || bs <= 0) return fail(INR_EINVAL, "bad argument");
-  *bytes = p->is_wire ? wire_workspace(p, bs).total : (p->is_mfn ? mfn_workspace(p, bs).total : plan_workspace(p, bs).total); return INR_OK;
+  *bytes = p->is_wire ? wire_workspace(p, bs).total : (p->is_mfn ? mfn_workspace(p, bs).total : chain_workspace_bytes(p, bs)); return INR_OK;
 }
 extern "C" int inr_scalars_offset(const inr_plan* p, int64_t bs, size_t* off) {
   if (!p || !off || bs <= 0) return fail(INR_EINVAL, "bad argument");
@@ -361,6 +391,7 @@ extern "C" int inr_workspace_layout(const inr_plan* p, int64_t bs, uint64_t* out
   for (int l = 0; l < kMaxLayers; ++l) { out[l] = w.h_off[l]; out[12 + l] = w.d_off[l]; out[24 + l] = w.dz_off[l]; }
   out[36] = w.dzlast_off; out[37] = w.g_off; out[38] = w.part_off; out[39] = w.scal_off; out[40] = w.gpart_off;
   out[41] = static_cast<uint64_t>(w.n_tiles); out[42] = static_cast<uint64_t>(w.n_split); out[43] = w.total;
+  if (n >= 46) { out[44] = static_cast<uint64_t>(w.tile_rows); out[45] = static_cast<uint64_t>(w.lb); }
   return INR_OK;
 }
 
@@ -381,9 +412,16 @@ static void fill_wgrad(const inr_plan* p, const Workspace& w, uint8_t* ws, Wgrad
     const int l = p->unit_layer[i];
     if (l < M.n_gemm) { u.a_off = w.dz_off[l]; u.b_off = w.h_off[l]; }
     else { u.a_off = w.h_off[M.n_gemm]; u.b_off = w.dzlast_off; }
+    if (w.lb != 2048) {      // the plan's units are written for 2048-byte k-groups (128-row tiles): rescale to this batch's tiles
+      const uint32_t lb = static_cast<uint32_t>(w.lb);
+      u.a_tile_stride = u.a_tile_stride / 2048 * lb; u.b_tile_stride = u.b_tile_stride / 2048 * lb;
+      u.a_sub = u.a_sub / 2048 * lb; u.b_sub = u.b_sub / 2048 * lb;
+      u.a_bytes = u.a_bytes / 2048 * lb; u.b_bytes = u.b_bytes / 2048 * lb;
+    }
     g.u[i] = u;
   }
   fill_wgrad_sched(p, g);
+  g.tile_rows = w.tile_rows; g.lb = w.lb;
   g.n_split = w.n_split; g.n_tiles = w.n_tiles; g.n_params = gpart_stride(M.n_params);
   g.ws = ws; g.gpart_off = w.gpart_off;
 }
@@ -1193,7 +1231,7 @@ static int run_forward(const inr_plan* p, const Workspace& w, const LossDesc& lo
   f.coords = coords; f.x = x; f.encB = encB; f.gt = gt; f.mask = mask; f.out = out;
   f.ws = static_cast<uint8_t*>(ws); f.row_offset = row_off; f.step_counter = step;
   f.bs = static_cast<int>(bs); f.train = train; f.trace = g_trace;
-  cudaError_t e = launch_chain_fwd(f, p->n_sm, st);
+  cudaError_t e = w.tile_rows == kTileM ? launch_chain_fwd(f, p->n_sm, st) : launch_chain_fwd_t(f, p->n_sm, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "chain_fwd_kernel");
 }
 
@@ -1262,7 +1300,7 @@ static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& l
   b.m = p->model; b.w = w; b.loss = loss;
   b.params = params; b.wpack = static_cast<const uint8_t*>(wpack); b.dout = dout;
   b.ws = static_cast<uint8_t*>(ws); b.bs = static_cast<int>(bs); b.bs_k = static_cast<int>(bs);
-  cudaError_t e = launch_chain_bwd(b, p->n_sm, st);
+  cudaError_t e = w.tile_rows == kTileM ? launch_chain_bwd(b, p->n_sm, st) : launch_chain_bwd_t(b, p->n_sm, st);
   if (e != cudaSuccess) return cuda_fail(e, "chain_bwd_kernel");
   if (mid) cudaEventRecord(mid, st);
   WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g); g.trace = g_trace;
@@ -1473,7 +1511,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   int rc = run_forward(p, w, L, params, wpack, coords, input_x, encB, gt, mask, bs, workspace, out, 1, row_cursor_dev,
                        no_adam ? nullptr : step_dev, st);
   if (rc) return rc;
-  rc = run_tv(loss, out, p->model.out_f, bs, ws, w.g_off, w.part_off, w.n_tiles, st);
+  rc = run_tv(loss, out, p->model.out_f, bs, ws, w.g_off, w.part_off, static_cast<int>((bs + kTileM - 1) / kTileM), st);
   if (rc) return rc;
   if (ev) cudaEventRecord(ev[1], st);
   rc = run_backward(p, w, L, params, wpack, nullptr, bs, workspace, st, ev ? ev[2] : nullptr,

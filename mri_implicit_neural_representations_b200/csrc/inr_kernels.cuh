@@ -96,6 +96,9 @@ struct Workspace {
   uint64_t gpart_off;            // [n_split][n_params rounded up to 4] fp32 split-K gradient partials (scaled)
   uint64_t total;
   int n_tiles, n_split;
+  // Row-tile geometry of every image: 128 rows with k-group stride 2048 B (chain_fwd.cu / chain_bwd.cu), or the transposed
+  // small-batch kernels' NR <= 80 rows with the padded stride NR*16 + 16 (chain_t.cu).  elem(r, f) at (f/8)*lb + r*16 + (f%8)*2.
+  int tile_rows, lb;
 };
 
 struct FwdArgs {
@@ -156,6 +159,7 @@ struct WgradArgs {
   uint16_t order[kMaxUnits];
   int n_heavy, n_light, group;
   int n_units, n_split, n_tiles, n_params;
+  int tile_rows, lb;            // rows per tile / k-group stride of the operand images (0: 128 rows, 2048 B)
   uint8_t* ws;
   uint64_t gpart_off;
   unsigned long long* trace;   // debug: 8 %globaltimer stamps per CTA starting at slot 64 (null in production)

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           mbar_wait(&empty[slot], bph ^ 1);
           mbar_arrive_expect_tx(&full[slot], U.b_bytes);
           bulk_g2s(ring + slot * kWgSlotBytes,
-                   a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub + static_cast<size_t>(c) * kWgSlotBytes, U.b_bytes, &full[slot]);
+                   a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub + static_cast<size_t>(c) * U.b_bytes, U.b_bytes, &full[slot]);
           if (++bs == nB) { bs = 0; bph ^= 1; }
         }
       }
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       const uint32_t idesc = umma_idesc_f16(kTileM, U.n, true, true);
       constexpr uint32_t idesc_bias = umma_idesc_f16(kTileM, 16, true, true);
       const uint64_t d_ones = umma_smem_desc(smem_u32(ones), 128, 128);
-      const uint64_t d0 = umma_smem_desc(smem_u32(ring), 128, 2048);     // MN-major image: LBO 128 (K groups), SBO 2048
+      const int ksteps = a.tile_rows ? a.tile_rows / 16 : kTileM / 16;   // K = 16 batch rows per MMA
+      const uint64_t d0 = umma_smem_desc(smem_u32(ring), 128, a.lb ? a.lb : 2048);   // MN-major image: LBO 128 (K groups), SBO = k-group stride
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, first = 1;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&full[as], aph);
@@ -117,14 +118,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           __syncwarp();
           const uint64_t db0 = d0 + ((slot * kWgSlotBytes) >> 4);
           if (elect_one()) {
+            if (ksteps == kTileM / 16) {
 #pragma unroll
-            for (int k = 0; k < kTileM / 16; ++k)          // K = 16 batch rows per MMA: 256 B of every 2 KB feature group
-              umma_f16(tmem + 128 * c, da0 + k * 16, db0 + k * 16, idesc, (first ^ 1) | (k != 0));
+              for (int k = 0; k < kTileM / 16; ++k)        // K = 16 batch rows per MMA: 256 B of every feature group
+                umma_f16(tmem + 128 * c, da0 + k * 16, db0 + k * 16, idesc, (first ^ 1) | (k != 0));
+            } else {
+              for (int k = 0; k < ksteps; ++k)
+                umma_f16(tmem + 128 * c, da0 + k * 16, db0 + k * 16, idesc, (first ^ 1) | (k != 0));
+            }
             if (U.bias_off >= 0 && c == nch - 1) {
               // normal unit: bias[o] = sum_rows dZ[row,o] * 1  -> A = dZ image, B = ones
               // transposed unit: bias[o] = sum_rows 1 * dZ_last[row,o] -> A = ones, B = dZ_last image
-#pragma unroll
-              for (int k = 0; k < kTileM / 16; ++k) {
+              for (int k = 0; k < ksteps; ++k) {
                 const uint64_t da = U.transposed ? d_ones : da0 + k * 16;
                 const uint64_t db = U.transposed ? db0 + k * 16 : d_ones;
                 umma_f16(tmem + bias_col, da, db, idesc_bias, (first ^ 1) | (k != 0));

@@ -128,7 +128,10 @@ class Plan:
         v = list(arr)
         return {"h": v[0:12], "d": v[12:24], "dz": v[24:36], "dzlast": v[36], "g": v[37], "part": v[38],
                 "scal": v[39], "gpart": v[40], "n_tiles": int(v[41]), "n_split": int(v[42]), "total": v[43],
-                "q": v[44:56], "gfin": v[56], "gstride": int(v[57]), "aux0": int(v[58]), "e": v[59]}
+                "q": v[44:56], "gfin": v[56], "gstride": int(v[57]), "aux0": int(v[58]), "e": v[59],
+                # width-256 chains: rows per tile and k-group stride of the operand images (chain_t.cu below one wave of rows)
+                "tile_rows": int(v[44]) if self.model in ("SIREN", "FFN") and not self.wide else 128,
+                "lb": int(v[45]) if self.model in ("SIREN", "FFN") and not self.wide else 2048}
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -316,9 +319,10 @@ class ChainEngine:
         else:
             F = self.plan.desc.in_features if (kind == "h" and layer == 0) else self.plan.desc.width
             off = lay[kind][layer]
-        nbytes = T * 128 * F * 2
-        img = self.workspace[off:off + nbytes].view(torch.float16).view(T, F // 8, 128, 8)
-        mat = img.permute(0, 2, 1, 3).reshape(T * 128, F).float()
+        R, lb = lay["tile_rows"], lay["lb"]           # elem(r, f) of a tile at (f/8)*lb + r*16 + (f%8)*2
+        nbytes = T * (F // 8) * lb
+        img = self.workspace[off:off + nbytes].view(torch.float16).view(T, F // 8, lb // 16, 8)[:, :, :R]
+        mat = img.permute(0, 2, 1, 3).reshape(T * R, F).float()
         if kind == "h" and layer == 0 and self.plan.desc.encoder == L.ENC["gauss"]:
             E = self.plan.desc.enc_size           # undo the sin/cos chunk interleave of the in-kernel encoder
             kp = torch.arange(F, device=mat.device)

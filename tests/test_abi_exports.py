@@ -44,12 +44,20 @@ def test_plan_layout_matches_reference_state_dict_order(inr):
         off += v.numel()
 
 
-def test_workspace_layout_is_consistent(inr):
+@pytest.mark.parametrize("short_tiles", [0, 1])
+def test_workspace_layout_is_consistent(inr, monkeypatch, short_tiles):
+    monkeypatch.setenv("INR_CHAIN_T", str(short_tiles))
     plan = inr.Plan("SIREN", NET, ENC)
-    for bs in (1, 128, 129, 10000, 102400):
+    prev = 0
+    for bs in (1, 128, 129, 2368, 2369, 10000, 11840, 11841, 102400):
         lay = plan.workspace_layout(bs)
-        assert lay["n_tiles"] == (bs + 127) // 128
-        assert lay["total"] == plan.workspace_bytes(bs)
+        # below one wave of 80-row tiles (148 SMs without a GPU) the chain is cut into one short tile per SM (chain_t.cu)
+        rows = 128 if (bs > 148 * 80 or not short_tiles) else max(16, 16 * -(-bs // (148 * 16)))
+        assert lay["tile_rows"] == rows and lay["lb"] == (2048 if rows == 128 else rows * 16 + 16)
+        assert lay["n_tiles"] == -(-bs // rows)
+        # a workspace sized for bs rows serves every smaller batch: never smaller than the layout, and monotone
+        assert plan.workspace_bytes(bs) >= lay["total"] and plan.workspace_bytes(bs) >= prev
+        prev = plan.workspace_bytes(bs)
         regions = sorted([lay["scal"], lay["part"], lay["g"], *lay["h"][:4], *lay["d"][:3], *lay["dz"][:3],
                           lay["dzlast"], lay["gpart"]])
         assert len(set(regions)) == len(regions) and regions[-1] < lay["total"]

@@ -24,6 +24,14 @@ def inr():
     return m
 
 
+@pytest.fixture(autouse=True, params=["rows128", "transposed"])
+def tiling(request, monkeypatch):
+    """Every test of this file runs on both tilings of the width-256 chain: 128-row tiles (chain_fwd.cu / chain_bwd.cu) and
+    the transposed short tiles the library picks below one wave of rows (chain_t.cu; these cases: 16-row tiles)."""
+    monkeypatch.setenv("INR_CHAIN_T", "0" if request.param == "rows128" else "1")
+    return request.param
+
+
 def _engine(inr, name, bs=None):
     model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup(name)
     plan = inr.Plan(model_kind, net, enc_cfg)

@@ -7,7 +7,7 @@ import mri_implicit_neural_representations_b200 as inr
 from mri_implicit_neural_representations_b200 import _lib as L
 
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-wl = dict(bench.WORKLOADS[bench.DEFAULT_WORKLOAD], batch=bs)
+wl = dict(bench.WORKLOADS[sys.argv[2] if len(sys.argv) > 2 else "siren_image_l2_bs10000"], batch=bs)
 dev = torch.device("cuda", 0)
 eng, _, _ = bench.build_engine(wl, dev, 1234)
 coords = torch.rand(bs, 3, device=dev) * 2 - 1

@@ -62,6 +62,15 @@ int main(int argc, char** argv) {
     {"Kmaj  none  N=192 (lgemm)",      192, 0, 0, 2048, 128, 3072, 128, 0, 4096, 6144, 4, 65536},
     {"Kmaj  none  N=128",              128, 0, 0, 2048, 128, 2048, 128, 0, 4096, 4096, 4, 65536},
     {"Kmaj  none  N=64",                64, 0, 0, 2048, 128, 1024, 128, 0, 4096, 2048, 4, 65536},
+    // transposed chain (chain_t.cu): A = packed weight stage (k-group stride 4096), B = NR-row image, k-group stride NR*16 (+16)
+    {"T: A w-stage, B N=80 LB=1296",    80, 0, 0, 4096, 128, 1296, 128, 0, 8192, 2592, 4, 65536},
+    {"T: A w-stage, B N=80 LB=1280",    80, 0, 0, 4096, 128, 1280, 128, 0, 8192, 2560, 4, 65536},
+    {"T: A w-stage, B N=80 LB=1408",    80, 0, 0, 4096, 128, 1408, 128, 0, 8192, 2816, 4, 65536},
+    {"T: A 2048,    B N=80 LB=1280",    80, 0, 0, 2048, 128, 1280, 128, 0, 4096, 2560, 4, 65536},
+    {"T: A w-stage, B N=64 LB=1024",    64, 0, 0, 4096, 128, 1024, 128, 0, 8192, 2048, 4, 65536},
+    {"T: A w-stage, B N=128 LB=2048",  128, 0, 0, 4096, 128, 2048, 128, 0, 8192, 4096, 4, 65536},
+    {"T: A w-stage, B N=32 LB=528",     32, 0, 0, 4096, 128, 528, 128, 0, 8192, 1056, 4, 65536},
+    {"T: A w-stage, B N=16 LB=272",     16, 0, 0, 4096, 128, 272, 128, 0, 8192, 544, 4, 65536},
     // MN-major no swizzle over the 128-row image (the wgrad layout): LBO 128 (k groups), SBO 2048 (mn groups)
     {"MNmaj none  N=128 (wgrad)",      128, 1, 1, 128, 2048, 128, 2048, 0, 256, 256, 8, 32768},
     {"MNmaj none  N=256",              256, 1, 1, 128, 2048, 128, 2048, 0, 256, 256, 8, 32768},
