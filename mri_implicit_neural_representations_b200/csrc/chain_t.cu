@@ -15,9 +15,17 @@
 // stores (a warp = 32 consecutive features of one row = 4 k-groups) free of bank conflicts: NR*16 alone is a multiple of 256.
 // A whole image of a tile is one contiguous run, so it leaves and enters by ONE bulk copy.
 //
+// Weight stages are shared inside a thread-block cluster: every tile needs all of the layer's weights, and 125 CTAs pulling
+// 640 KB each out of L2 is 80 MB per forward pass -- more than 10 us of L2 -> SM bandwidth on its own.  The CTAs of a cluster
+// (4, or 2 where the device cannot co-schedule 4) walk the stages in lockstep; CTA c fetches 1/C of every stage and multicasts
+// it into the same ring slot of all C CTAs, and a slot is refilled once the MMAs of all C CTAs have released it (commit
+// multicast to every CTA's `empty` barrier).  A grid rounded up to whole clusters recomputes the last tile in its spare CTAs
+// (identical bytes to identical addresses) instead of special-casing the ring protocol.
+//
 // Mirrors (results, not code): src/models/networks.py:23-35 (encoder), :74-124 (SIREN), :48-69 (FFN).
 #include <cuda_runtime.h>
 #include <cmath>
+#include <cstdlib>
 #include "inr_ptx.cuh"
 #include "inr_kernels.cuh"
 #include "inr_loss.cuh"
@@ -51,17 +59,22 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
   __shared__ uint64_t w_full[kTFwdStages], w_empty[kTFwdStages], img_full, acc_full[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[16][8];
+  __shared__ float s_xyz[kTMaxRows * 3];                    // coordinates of the tile's rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ChainModel& M = a.m;
   const int NR = a.w.tile_rows, LB = a.w.lb;
   const int n_tiles = a.w.n_tiles;
+  const int n_rounds = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctas();
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+  const uint32_t slice = kStageBytes / csize;               // this CTA's share of every weight stage
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const float zscale = (ACT == ACT_SIN) ? M.w0 : 1.f;
   if (tid == 0) INR_TRACE(a, 0);
   griddep_launch_dependents();
   if (tid == 0) {
-    for (int i = 0; i < kTFwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < kTFwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], csize); }
     mbar_init(&img_full, kTCompute);
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_fence_init();
@@ -73,7 +86,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
     for (int i = tid; i < M.enc_size * 3; i += kTThreads) c_encB[i] = 6.283185307179586f * a.encB[i];
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();        // (also the CTA barrier) nobody multicasts into a peer whose barriers are not initialised yet
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   if (tid == 0) INR_TRACE(a, 1);
@@ -82,15 +95,15 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
     // ------------------------------------------------------------------ weight-stage producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int rd = 0; rd < n_rounds; ++rd)
         for (int l = 0; l < M.n_gemm; ++l) {
           const int nst = (l == 0 ? M.k0 : kWidth) / kStageK;
-          const uint8_t* src = a.wpack + M.wf_off[l];
+          const uint8_t* src = a.wpack + M.wf_off[l] + crank * slice;
           for (int s = 0; s < nst; ++s, ++it) {
             const uint32_t slot = it % kTFwdStages, ph = (it / kTFwdStages) & 1;
-            mbar_wait(&w_empty[slot], ph ^ 1);
+            mbar_wait(&w_empty[slot], ph ^ 1);              // released by the MMAs of every CTA of the cluster
             mbar_arrive_expect_tx(&w_full[slot], kStageBytes);
-            bulk_g2s(wring + slot * kStageBytes, src + static_cast<size_t>(s) * kStageBytes, kStageBytes, &w_full[slot]);
+            bulk_g2s_mc(wring + slot * kStageBytes + crank * slice, src + static_cast<size_t>(s) * kStageBytes, slice, &w_full[slot], cmask);
           }
         }
     }
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
     const uint32_t idesc = umma_idesc_f16(kTileM, NR, false, false);
     const uint32_t x_s = smem_u32(X), y_s = smem_u32(Y), wring_s = smem_u32(wring);
     uint32_t it = 0, iq = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    for (int rd = 0; rd < n_rounds; ++rd)
       for (int l = 0; l < M.n_gemm; ++l) {
         mbar_wait(&img_full, iq & 1); ++iq;                 // input image of layer l complete
         tc_fence_after();
@@ -121,12 +134,12 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
                 const uint64_t db = umma_smem_desc(img + (s * 4 + kk * 2) * LB, LB, 128);
                 umma_f16(tmem + ((l & 1) * 2 + h) * kTAccStride, da, db, idesc, (s | kk) != 0);
               }
-            umma_commit(&w_empty[slot]);
+            umma_commit_mc(&w_empty[slot], cmask);
             if (s == nst - 1) umma_commit(&acc_full[l & 1]);
           }
           __syncwarp();
         }
-        if (tile == 0 && lane == 0) INR_TRACE(a, 40 + l);
+        if (rd == 0 && lane == 0) INR_TRACE(a, 40 + l);
       }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ compute warps (16)
@@ -137,8 +150,24 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
     const int c_lo = ch * (NR >> 1), c_hi = c_lo + (NR >> 1);
     uint8_t* DST = X + 32 * LB;                     // act' staging: upper half of X, free once layer 0's MMAs are done
     uint32_t acc_ph[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const int tile = min(static_cast<int>(blockIdx.x) + rd * static_cast<int>(gridDim.x), n_tiles - 1);
       const int r0g = tile * NR;                            // first batch row of the tile
+      if (rd > 0) named_bar_sync(1, kTCompute);             // the previous tile's last readers of s_xyz are done
+      // everything the tile reads from global memory row by row is fetched now, in one round trip: coordinates into shared
+      // memory (the encoder reads a different row per item), targets and mask into the registers of the row's loss thread
+      if (a.coords && ct < 3 * NR) {
+        const int idx = r0g * 3 + ct;
+        s_xyz[ct] = idx < a.bs * 3 ? a.coords[static_cast<size_t>(row_base) * 3 + idx] : 0.f;
+      }
+      float t_pref[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+      bool in_loss_pref = false;
+      if (a.train && (ct & 3) == 0 && ct < 4 * NR && r0g + (ct >> 2) < a.bs && a.gt && a.loss.kind != LOSS_NONE) {
+        const size_t srow = static_cast<size_t>(row_base) + r0g + (ct >> 2);
+        in_loss_pref = a.mask ? (a.mask[srow] != 0) : true;
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) if (o < M.out_f) t_pref[o] = a.gt[srow * M.out_f + o];
+      }
       // every bulk store issued so far has finished READING shared memory before anybody overwrites an image
       if (ct == 0) bulk_wait_read0();
       named_bar_sync(1, kTCompute);
@@ -151,8 +180,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
           const int grow = r0g + r;
           float s[8], co[8];
           if (grow < a.bs) {
-            const float* c = a.coords + (static_cast<size_t>(row_base) + grow) * 3;
-            const float cx = c[0], cy = c[1], cz = c[2];
+            const float cx = s_xyz[3 * r], cy = s_xyz[3 * r + 1], cz = s_xyz[3 * r + 2];
             const float* b = c_encB + fg * 24;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -184,7 +212,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
       }
       fence_proxy_async_smem();
       mbar_arrive(&img_full);
-      if (ct == 0 && tile == 0) INR_TRACE(a, 2);
+      if (ct == 0 && rd == 0) INR_TRACE(a, 2);
       named_bar_sync(1, kTCompute);
       if (ct == 0 && a.train) {
         bulk_s2g(a.ws + a.w.h_off[0] + static_cast<size_t>(tile) * ((M.k0 >> 3) * LB), X, (M.k0 >> 3) * LB);
@@ -195,10 +223,10 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
         mbar_wait(&acc_full[l & 1], acc_ph[l & 1]);
         acc_ph[l & 1] ^= 1;
         tc_fence_after();
-        if (ct == 0 && tile == 0) INR_TRACE(a, 12 + 5 * l);
+        if (ct == 0 && rd == 0) INR_TRACE(a, 12 + 5 * l);
         if (ct == 0) bulk_wait_read0();
         named_bar_sync(1, kTCompute);
-        if (ct == 0 && tile == 0) INR_TRACE(a, 13 + 5 * l);
+        if (ct == 0 && rd == 0) INR_TRACE(a, 13 + 5 * l);
         uint8_t* OUT = (l & 1) ? X : Y;
         const float bias = c_bias[l * kWidth + f];
         const uint32_t acc = tmem + t_lane + ((l & 1) * 2 + h) * kTAccStride;
@@ -221,14 +249,15 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
         fence_proxy_async_smem();
         tc_fence_before();
         if (l < M.n_gemm - 1) mbar_arrive(&img_full);
-        if (ct == 0 && tile == 0) INR_TRACE(a, 14 + 5 * l);
+        if (ct == 0 && rd == 0) INR_TRACE(a, 14 + 5 * l);
         named_bar_sync(1, kTCompute);
-        if (ct == 0 && tile == 0) INR_TRACE(a, 15 + 5 * l);
+        if (ct == 0 && rd == 0) INR_TRACE(a, 15 + 5 * l);
         if (ct == 0 && a.train) {
           bulk_s2g(a.ws + a.w.h_off[l + 1] + static_cast<size_t>(tile) * (32 * LB), OUT, 32 * LB);
           bulk_s2g(a.ws + a.w.d_off[l] + static_cast<size_t>(tile) * (32 * LB), DST, 32 * LB);
           bulk_commit();
         }
+        if (ct == 0 && rd == 0 && l == M.n_gemm - 1) INR_TRACE(a, 30);
       }
       // ---------------- final linear (CUDA cores, four threads per row) + last activation + loss pieces
       const uint8_t* HL = ((M.n_gemm - 1) & 1) ? X : Y;
@@ -236,9 +265,12 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
       if (ct < 4 * NR) {
         const int r = ct >> 2, part = ct & 3, grow = r0g + r;
         const bool valid = part == 0 && grow < a.bs;        // lane `part == 0` of a row's quad owns the row's output and loss
-        const size_t srow = static_cast<size_t>(row_base) + grow;
         float po[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
-        for (int kg = part * 8; kg < part * 8 + 8; ++kg) {  // 64 of the 256 hidden features
+        // 64 of the 256 hidden features: k-groups part, part + 4, ... (neighbouring lanes 1296 B apart: no bank conflict).
+        // Not unrolled on purpose: code that runs once per CTA is paced by cold instruction fetches, not by its arithmetic
+        // (the unrolled loop took 3.7 us here).
+#pragma unroll 1
+        for (int kg = part; kg < kWidth / 8; kg += 4) {
           const uint4 hv = *reinterpret_cast<const uint4*>(HL + kg * LB + r * 16);
           const __half2* hh = reinterpret_cast<const __half2*>(&hv);
           float hf[8];
@@ -254,6 +286,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
               po[o] += s0 + s1;                             // short chains, then a tree over the quad: fp32 error stays ~1e-7
             }
         }
+        if (ct == 0 && rd == 0) INR_TRACE(a, 31);
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) {
           po[o] += __shfl_xor_sync(0xffffffffu, po[o], 1);
@@ -277,14 +310,15 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
           float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
           float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid && a.gt && a.loss.kind != LOSS_NONE) {
-            const bool in_loss = a.mask ? (a.mask[srow] != 0) : true;
-            if (a.loss.kind == LOSS_HDR) {
-              const float kx = a.coords[srow * 3 + 1], ky = a.coords[srow * 3 + 2];
+            const bool in_loss = in_loss_pref;
+            if (a.loss.kind == LOSS_HDR) {   // filter term runs over ALL batch rows (unmasked kcoords)
+              const float kx = s_xyz[3 * r + 1], ky = s_xyz[3 * r + 2];
               const float ff = expf(-(kx * kx + ky * ky) / (2.f * a.loss.sigma * a.loss.sigma));
               fs = (1.f - ff) * (1.f - ff);
             }
             if (in_loss) {
-              for (int o = 0; o < M.out_f; ++o) t[o] = a.gt[srow * M.out_f + o];
+#pragma unroll
+              for (int o = 0; o < kMaxOut; ++o) t[o] = t_pref[o];
               RowLoss rl = loss_row(a.loss, M.out_f, y, t);
               lA = rl.lossA; lB = rl.lossB; cnt = 1.f;
               float ga[kMaxOut], gb[kMaxOut];
@@ -305,9 +339,11 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
             amA = fmaxf(amA, __shfl_xor_sync(0xffffffffu, amA, off));
             amB = fmaxf(amB, __shfl_xor_sync(0xffffffffu, amB, off));
           }
+          if (ct == 0 && rd == 0) INR_TRACE(a, 32);
           const int wq = ct >> 5;
           if (lane == 0) { red[wq][0] = lA; red[wq][1] = lB; red[wq][2] = fs; red[wq][3] = cnt; red[wq][4] = amA; red[wq][5] = amB; }
           named_bar_sync(2, 32 * nw);
+          if (ct == 0 && rd == 0) INR_TRACE(a, 33);
           if (ct == 0) {
             float* pdst = reinterpret_cast<float*>(a.ws + a.w.part_off) + static_cast<size_t>(tile) * kPartialsPerTile;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, m4 = 0.f, m5 = 0.f;
@@ -326,7 +362,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_fwd_t_kernel(const __grid_
     if (ct == 0) INR_TRACE(a, 38);
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();        // no CTA leaves while a peer may still multicast into its ring or arrive on its barriers
   if (tid == 0) INR_TRACE(a, 39);
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
@@ -354,11 +390,15 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_bwd_t_kernel(const __grid_
   const int NR = a.w.tile_rows, LB = a.w.lb;
   const int n_tiles = a.w.n_tiles;
   const uint32_t img_bytes = 32u * LB;
+  const int n_rounds = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctas();
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+  const uint32_t slice = kStageBytes / csize;
   const float zscale = (M.act == ACT_SIN) ? M.w0 : 1.f;
 
   griddep_launch_dependents();
   if (tid == 0) {
-    for (int i = 0; i < kTBwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < kTBwdStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], csize); }
     for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], kTCompute); mbar_init(&acc_full[i], 1); }
     mbar_init(&img_full, kTCompute);
     mbar_fence_init();
@@ -367,7 +407,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_bwd_t_kernel(const __grid_
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   griddep_wait();            // forward kernel complete: tile partials, loss pieces and act' images are final
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();        // (also the CTA barrier) peers' barriers are initialised before anybody multicasts
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   reduce_step_scalars(reinterpret_cast<const float*>(a.ws + a.w.part_off), a.w.n_tiles, a.loss, a.m.out_f, a.bs_k, a.hyper, a.step,
@@ -384,16 +424,17 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_bwd_t_kernel(const __grid_
         mbar_arrive_expect_tx(&d_full[slot], img_bytes);
         bulk_g2s(Db + slot * kTYBytes, a.ws + a.w.d_off[l] + static_cast<size_t>(tile) * img_bytes, img_bytes, &d_full[slot]);
       };
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int rd = 0; rd < n_rounds; ++rd) {
+        const int tile = min(static_cast<int>(blockIdx.x) + rd * static_cast<int>(gridDim.x), n_tiles - 1);
         load_d(M.n_gemm - 1, tile);
         for (int l = M.n_gemm - 1; l >= 1; --l) {
           load_d(l - 1, tile);                              // ahead of the weight stages: ready when the epilogue needs it
-          const uint8_t* src = a.wpack + M.wd_off[l];
+          const uint8_t* src = a.wpack + M.wd_off[l] + crank * slice;
           for (int s = 0; s < kWidth / kStageK; ++s, ++it) {
             const uint32_t slot = it % kTBwdStages, ph = (it / kTBwdStages) & 1;
-            mbar_wait(&w_empty[slot], ph ^ 1);
+            mbar_wait(&w_empty[slot], ph ^ 1);              // released by the MMAs of every CTA of the cluster
             mbar_arrive_expect_tx(&w_full[slot], kStageBytes);
-            bulk_g2s(wring + slot * kStageBytes, src + static_cast<size_t>(s) * kStageBytes, kStageBytes, &w_full[slot]);
+            bulk_g2s_mc(wring + slot * kStageBytes + crank * slice, src + static_cast<size_t>(s) * kStageBytes, slice, &w_full[slot], cmask);
           }
         }
       }
@@ -403,7 +444,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_bwd_t_kernel(const __grid_
     const uint32_t idesc = umma_idesc_f16(kTileM, NR, false, false);
     const uint32_t z_s = smem_u32(Zb), wring_s = smem_u32(wring);
     uint32_t it = 0, iq = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int rd = 0; rd < n_rounds; ++rd) {
       uint32_t zi = 0;                                      // dZ of the top layer lives in Z[0]
       for (int l = M.n_gemm - 1; l >= 1; --l, zi ^= 1) {
         mbar_wait(&img_full, iq & 1); ++iq;
@@ -422,7 +463,7 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_bwd_t_kernel(const __grid_
                 const uint64_t db = umma_smem_desc(z_s + zi * kTYBytes + (s * 4 + kk * 2) * LB, LB, 128);
                 umma_f16(tmem + ((l & 1) * 2 + h) * kTAccStride, da, db, idesc, (s | kk) != 0);
               }
-            umma_commit(&w_empty[slot]);
+            umma_commit_mc(&w_empty[slot], cmask);
             if (s == kWidth / kStageK - 1) umma_commit(&acc_full[l & 1]);
           }
           __syncwarp();
@@ -439,7 +480,8 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_bwd_t_kernel(const __grid_
     const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
     const size_t f_off = static_cast<size_t>(f >> 3) * LB + (f & 7) * 2;
     uint32_t dq = 0, acc_ph[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const int tile = min(static_cast<int>(blockIdx.x) + rd * static_cast<int>(gridDim.x), n_tiles - 1);
       const int r0g = tile * NR;
       if (ct == 0) bulk_wait_read0();
       named_bar_sync(1, kTCompute);
@@ -515,14 +557,44 @@ __global__ void __launch_bounds__(kTThreads, 1) chain_bwd_t_kernel(const __grid_
     if (ct == 0) bulk_wait0();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();        // no CTA leaves while a peer may still multicast into its ring or arrive on its barriers
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
+// Cluster size of the weight multicast: 4 where the device can co-schedule the whole grid as clusters of 4 (148 SMs in GPCs of
+// uneven size: some cannot), else 2, else single CTAs.  INR_CHAIN_T_CLUSTER overrides.  Cached per grid size: the occupancy
+// query stays out of the step (and out of graph capture).
+template <typename Kern>
+static int pick_cluster(Kern kern, int smem, int ctas, int* cache) {
+  if (ctas < 1 || ctas > 1023) return 1;
+  if (cache[ctas]) return cache[ctas];
+  int pick = 1;
+  const char* e = std::getenv("INR_CHAIN_T_CLUSTER");
+  if (e) {
+    const int v = std::atoi(e);
+    pick = (v == 4 || v == 2) ? v : 1;
+  } else {
+    for (int c = 4; c >= 2 && pick == 1; c >>= 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((ctas + c - 1) / c * c); cfg.blockDim = dim3(kTThreads); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n * c >= static_cast<int>(cfg.gridDim.x)) pick = c;
+      else cudaGetLastError();
+    }
+  }
+  cache[ctas] = pick;
+  return pick;
+}
+
 cudaError_t launch_chain_fwd_t(const FwdArgs& a, int n_sm, cudaStream_t stream) {
-  const int grid = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
-  if (grid <= 0) return cudaSuccess;
+  const int ctas = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
+  if (ctas <= 0) return cudaSuccess;
   static bool attr_done = false;
+  static int cache[2][1024];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(chain_fwd_t_kernel<ACT_SIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTFwdSmem);
     if (e != cudaSuccess) return e;
@@ -530,21 +602,26 @@ cudaError_t launch_chain_fwd_t(const FwdArgs& a, int n_sm, cudaStream_t stream) 
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  if (a.m.act == ACT_SIN) chain_fwd_t_kernel<ACT_SIN><<<grid, kTThreads, kTFwdSmem, stream>>>(a);
-  else chain_fwd_t_kernel<ACT_RELU><<<grid, kTThreads, kTFwdSmem, stream>>>(a);
-  return cudaGetLastError();
+  const bool sine = a.m.act == ACT_SIN;
+  auto kern = sine ? chain_fwd_t_kernel<ACT_SIN> : chain_fwd_t_kernel<ACT_RELU>;
+  const int c = pick_cluster(kern, kTFwdSmem, ctas, cache[sine ? 0 : 1]);
+  const int grid = (ctas + c - 1) / c * c;
+  return launch_clustered(kern, dim3(grid), dim3(kTThreads), kTFwdSmem, stream, a, c, false);
 }
 
 cudaError_t launch_chain_bwd_t(const BwdArgs& a, int n_sm, cudaStream_t stream) {
-  const int grid = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
-  if (grid <= 0) return cudaSuccess;
+  const int ctas = a.w.n_tiles < n_sm ? a.w.n_tiles : n_sm;
+  if (ctas <= 0) return cudaSuccess;
   static bool attr_done = false;
+  static int cache[1024];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(chain_bwd_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTBwdSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  return launch_dependent(chain_bwd_t_kernel, dim3(grid), dim3(kTThreads), kTBwdSmem, stream, a);
+  const int c = pick_cluster(chain_bwd_t_kernel, kTBwdSmem, ctas, cache);
+  const int grid = (ctas + c - 1) / c * c;
+  return launch_clustered(chain_bwd_t_kernel, dim3(grid), dim3(kTThreads), kTBwdSmem, stream, a, c, true);
 }
 
 }  // namespace inr

