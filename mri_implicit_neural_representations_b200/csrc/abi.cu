@@ -301,9 +301,10 @@ extern "C" int inr_wpack_bytes(const inr_plan* p, size_t* b) {
   *b = p->is_wire ? p->wm.wpack_bytes : (p->is_mfn ? p->mm.wpack_bytes : p->model.wpack_bytes); return INR_OK;
 }
 
-// Rows per tile of the width-256 chain.  A batch that fills the chip with 128-row tiles runs the row-tile kernels
-// (chain_fwd.cu / chain_bwd.cu); a smaller one (BASELINE configs[0]: 10 000 rows = 79 such tiles on 148 SMs) is cut into
-// one tile of NR <= 80 rows per SM for the transposed kernels of chain_t.cu.  INR_CHAIN_T=0 keeps the 128-row tiles.
+// Rows per tile of the width-256 chain: 128 (chain_fwd.cu / chain_bwd.cu).  With INR_CHAIN_T=1 a batch below one wave of
+// 80-row tiles (BASELINE configs[0]: 10 000 rows = 79 128-row tiles on 148 SMs) is cut into one tile of NR <= 80 rows per SM
+// for the transposed kernels of chain_t.cu instead.  Opt-in: measured on B200 they halve the epilogue but expose the MMA phases
+// (71.9 us against 59.7 us per step at 10 000 rows).
 static int chain_tile_rows(const inr_plan* p, int64_t bs) {
   const char* e = std::getenv("INR_CHAIN_T");          // read per call: the parity tests run both tilings in one process
   const int on = e ? std::atoi(e) : 0;
