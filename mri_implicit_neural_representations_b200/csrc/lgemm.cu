@@ -38,6 +38,15 @@ constexpr int kLgRingBytes = 5 * 40960;                                // 204800
 constexpr int kLgComputeThreads = 512;
 constexpr int kLgThreads = 128 + kLgComputeThreads;
 constexpr int kLgSmem = kLgRingBytes + 1024;
+// BRES kernels (weights resident, see lgemm_kernel): 208 KB, as much as fits next to the static bias / barrier arrays
+constexpr int kLgRingBytesBres = 212992;
+constexpr int kLgSmemBres = kLgRingBytesBres + 1024;
+// (A fifth K = 48 slot for the forward chain -- 210 KB of ring, all an SM has next to the static arrays -- was measured and
+// changes nothing: 78.9 us against 78.6 us.)
+template <int MODE, int PAIR, int BRES> struct LgRing {
+  static constexpr int bytes = BRES ? kLgRingBytesBres : kLgRingBytes;
+  static constexpr int smem = BRES ? kLgSmemBres : kLgSmem;
+};
 
 
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -59,10 +68,19 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // PAIR = 1: the CTAs of a cluster of two work on two neighbouring row tiles of the same (layer, N-block) with ONE
 // tcgen05.mma.cta_group::2 stream (M = 256): each CTA streams its own A tile but only HALF of the weight rows, which cuts the
 // operand bytes an SM ingests per flop by 30 % (WIRE: 28 KB instead of 40 KB per ring slot, 7 slots deep instead of 5).
-template <int PASSES, int MODE, int KSTEPS, int PAIR>
+//
+// BRES = 1 (WIRE chains on CTA pairs): the weight block of the (layer, N-block) a pair is working on stays RESIDENT in shared
+// memory and only the A tiles stream through the ring.  The chains are bound by the chip's L2 -> SM bandwidth (measured: MMA
+// warp waiting for operands 50 % of the time at 8.2 TB/s of bulk-copy traffic), and a pair's items of one layer all use
+// the same N-block (items are dealt with an even stride), so the 147 KB (forward, hi + lo) / 74 KB (dgrad) of weights
+// that every item used to pull again are now fetched once per layer: L2 -> SM bytes per item 343 -> 196 KB forward, 170 -> 96 KB
+// dgrad.  b_full / b_empty hand the resident block between producer and MMA warp exactly like a ring slot.
+// BRES = 2 (3-pass forward): only the hi image is resident, the lo image keeps streaming with the A tiles -- 270 KB per item, but
+// 139 KB of ring instead of 65 KB (the ring depth is what covers the L2 round trip of the A tiles).
+template <int PASSES, int MODE, int KSTEPS, int PAIR, int BRES = 0>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2];
+  __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2], b_full, b_empty;
   __shared__ uint32_t tmem_base_s;
   constexpr bool kChain = MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD || MODE == LG_W2D_FWD || MODE == LG_W2D_DGRAD;
   constexpr int kBiasFloats = MODE == LG_WIRE_FWD ? kWMaxDepth * kWP : 512;
@@ -85,8 +103,15 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   const uint32_t a_lo_off = a_bytes;
   const uint32_t b_hi_off = PASSES == 3 ? 2 * a_bytes : a_bytes;
   const uint32_t b_lo_off = b_hi_off + b_bytes;
-  const uint32_t slot_bytes = PASSES == 3 ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes);
-  int n_slots = kLgRingBytes / slot_bytes;
+  constexpr bool kLoStreams = BRES == 2 && PASSES == 3;     // B lo image in the ring slots
+  const uint32_t slot_bytes = BRES ? (PASSES == 3 ? 2 * a_bytes : a_bytes) + (kLoStreams ? b_bytes : 0u)
+                                   : (PASSES == 3 ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes));
+  const uint32_t b_lo_ring = 2 * a_bytes;                    // kLoStreams: B lo part of a slot behind A hi / A lo
+  // resident weights: this CTA's half of the N-block over the whole K, hi image then (3-pass forward) lo image; ring behind it
+  const uint32_t bres_half = BRES ? b_rows * 64 * static_cast<uint32_t>(a.seg[0].k_stages) : 0u;
+  const uint32_t bres_bytes = BRES ? ((PASSES == 3 && !kLoStreams) ? 2 : 1) * bres_half : 0u;
+  uint8_t* ring = smem + bres_bytes;
+  int n_slots = (LgRing<MODE, PAIR, BRES>::bytes - bres_bytes) / slot_bytes;
   if (n_slots > kLgMaxSlots) n_slots = kLgMaxSlots;
 
   // The next layer GEMM of the stream may be scheduled onto SMs this grid has already left; what runs before
@@ -98,6 +123,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     // pair: the leader's full barrier also takes the peer's "my half of the slot has landed" arrival, its acc_empty the
     // arrivals of both CTAs' epilogue threads
     for (int i = 0; i < kLgMaxSlots; ++i) { mbar_init(&full[i], (PAIR && rank == 0) ? 2 : 1); mbar_init(&empty[i], 1); }
+    mbar_init(&b_full, (PAIR && rank == 0) ? 2 : 1); mbar_init(&b_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLgComputeThreads << PAIR); mbar_init(&stored[i], kLgComputeThreads);
     }
@@ -147,6 +173,8 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     // copies and the waits, more than the 576 tensor cycles of a slot (tools/umma_commit2.cu, in-kernel cycle counters).
     {
       uint32_t slot = 0, ph = 0;
+      int cur_b = -1;                  // BRES: (layer, N-block) of the resident weights
+      uint32_t bph = 0;
       const bool tr = a.trace != nullptr;
       long long c_flag = 0, c_empty = 0, c_issue = 0, tq = 0;
       const long long tr_c0 = tr ? clock64() : 0;
@@ -172,6 +200,20 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
                                 static_cast<size_t>(((lane & 1) ? kWP / 8 : 0) + (kWFeatPerBlock / 8) * nb) * 2048;
           if (!(lane == 3 && Lq.real_first)) bulk_prefetch_l2(base, (kWFeatPerBlock / 8) * 2048);
         }
+        if (BRES && layer * a.n_nblocks + nb != cur_b) {
+          // new weight block: wait until the MMAs that read the old one are done (commit of the last item that used it), then
+          // fetch this CTA's half -- lanes 0-3 a quarter of the hi image each, lanes 4-7 of the lo image
+          if (cur_b >= 0) { mbar_wait(&b_empty, bph); bph ^= 1; }
+          cur_b = layer * a.n_nblocks + nb;
+          if (lane == 0) mbar_arrive_expect_tx(&b_full, bres_bytes);
+          __syncwarp();
+          if (lane < ((PASSES == 3 && !kLoStreams) ? 8 : 4)) {
+            const uint8_t* bsrc = ((lane >> 2) ? a.chain[layer].b_lo : a.chain[layer].b_hi) + (static_cast<size_t>(nb << PAIR) + rank) * bres_half;
+            const uint32_t q = bres_half >> 2, off = (lane & 3) * q;
+            bulk_g2s(smem + (lane >> 2) * bres_half + off, bsrc + off, q, &b_full);
+          }
+          __syncwarp();
+        }
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
           const int n_it = S.k_stages * 2 / KSTEPS;
@@ -186,8 +228,10 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           uint32_t bytes = 0, dst_off = 0;
           if (lane < (PASSES == 3 ? 4 : 2)) {
             if (is_b) {
-              src = (is_lo ? b_lo : b_hi) + (static_cast<size_t>(nb << PAIR) + rank) * n_it * b_bytes;
-              bytes = b_bytes; dst_off = is_lo ? b_lo_off : b_hi_off;
+              if (!BRES || (kLoStreams && is_lo)) {
+                src = (is_lo ? b_lo : b_hi) + (static_cast<size_t>(nb << PAIR) + rank) * n_it * b_bytes;
+                bytes = b_bytes; dst_off = BRES ? b_lo_ring : (is_lo ? b_lo_off : b_hi_off);
+              }
             } else if (!phantom) {
               src = (is_lo ? a_lo : a_hi) + static_cast<size_t>(tile) * S.a_tile_bytes;
               bytes = a_bytes; dst_off = is_lo ? a_lo_off : 0;
@@ -202,7 +246,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             } else {
               if (lane == 0) mbar_arrive_expect_tx(&full[slot], phantom ? slot_bytes - (PASSES == 3 ? 2 : 1) * a_bytes : slot_bytes);
               __syncwarp();
-              if (src) { bulk_g2s(smem + slot * slot_bytes + dst_off, src, bytes, &full[slot]); src += bytes; }
+              if (src) { bulk_g2s(ring + slot * slot_bytes + dst_off, src, bytes, &full[slot]); src += bytes; }
             }
             __syncwarp();
             if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
@@ -220,8 +264,17 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     if (PAIR && rank != 0) {
       // ---------------------------------------------------------------- peer CTA: no MMAs to issue; relay "slot landed" to the leader
       if (lane == 0) {
-        uint32_t slot = 0, ph = 0;
-        for (int item = cta0; item < n_items; item += n_walk)
+        uint32_t slot = 0, ph = 0, bph = 0;
+        int cur_b = -1;
+        for (int item = cta0; item < n_items; item += n_walk) {
+          if (BRES) {
+            const int layer = item / per_layer, nb = (item - layer * per_layer) % a.n_nblocks;
+            if (layer * a.n_nblocks + nb != cur_b) {        // my half of the new weight block has landed: tell the leader
+              cur_b = layer * a.n_nblocks + nb;
+              mbar_wait(&b_full, bph); bph ^= 1;
+              mbar_arrive_cluster(&b_full, 0);
+            }
+          }
           for (int sg = 0; sg < a.n_seg; ++sg) {
             const int n_it = a.seg[sg].k_stages * 2 / KSTEPS;
             for (int s = 0; s < n_it; ++s) {
@@ -230,6 +283,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
             }
           }
+        }
       }
     } else {
       // the whole warp walks the ring and one elected lane issues: descriptors stay warp-uniform (uniform registers), which
@@ -237,10 +291,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       const uint32_t idesc = umma_idesc_f16(kTileM << PAIR, a.nt, false, false);
       const uint32_t b_lbo = b_rows * 16;
       // descriptors differ only in their 14-bit start-address field (bytes >> 4): build once, add offsets
-      const uint64_t da0 = umma_smem_desc(smem_u32(smem), 2048, 128);
-      const uint64_t db0 = umma_smem_desc(smem_u32(smem), b_lbo, 128);
+      const uint64_t da0 = umma_smem_desc(smem_u32(ring), 2048, 128);
+      const uint64_t db0 = umma_smem_desc(BRES ? smem_u32(smem) : smem_u32(ring), b_lbo, 128);
+      const uint64_t db0r = umma_smem_desc(smem_u32(ring), b_lbo, 128);      // kLoStreams: B lo inside the ring slot
       const uint32_t bk16 = (2 * b_lbo) >> 4;                            // one K=16 step of B: two k-groups of nt x 16 B
-      uint32_t slot = 0, ph = 0, n_done = 0;
+      uint32_t slot = 0, ph = 0, n_done = 0, bph = 0;
+      int cur_b = -1;
       const bool tr = a.trace != nullptr;
       long long c_acc = 0, c_full = 0, c_mma = 0, tq = 0;
       for (int item = cta0; item < n_items; item += n_walk, ++n_done) {
@@ -248,6 +304,21 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         if (tr) tq = clock64();
         mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
         if (tr) c_acc += clock64() - tq;
+        int key = 0, next_key = -1;
+        if (BRES) {
+          const int layer = item / per_layer, nb = (item - layer * per_layer) % a.n_nblocks;
+          key = layer * a.n_nblocks + nb;
+          if (item + n_walk < n_items) {
+            const int nl = (item + n_walk) / per_layer;
+            next_key = nl * a.n_nblocks + ((item + n_walk) - nl * per_layer) % a.n_nblocks;
+          }
+          if (key != cur_b) {                               // both halves of the new weight block have landed
+            cur_b = key;
+            if (tr) tq = clock64();
+            mbar_wait(&b_full, bph); bph ^= 1;
+            if (tr) c_full += clock64() - tq;
+          }
+        }
         tc_fence_after();
         for (int sg = 0; sg < a.n_seg; ++sg) {
           const LGemmSeg& S = a.seg[sg];
@@ -265,11 +336,11 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k) {          // K = 16 steps inside the slot
               const uint64_t dah = da0 + so + k * 256;                                            // 4096 B per step
-              const uint64_t dbh = db0 + so + (b_hi_off >> 4) + k * bk16;
+              const uint64_t dbh = BRES ? db0 + static_cast<uint32_t>(s * KSTEPS + k) * bk16 : db0 + so + (b_hi_off >> 4) + k * bk16;
               if (PAIR) umma_f16_pair(acc, dah, dbh, idesc, (s | k) != 0); else umma_f16(acc, dah, dbh, idesc, (s | k) != 0);
               if (PASSES == 3) {
                 const uint64_t dal = dah + (a_lo_off >> 4);
-                const uint64_t dbl = dbh + (b_bytes >> 4);
+                const uint64_t dbl = kLoStreams ? db0r + so + (b_lo_ring >> 4) + k * bk16 : dbh + ((BRES ? bres_half : b_bytes) >> 4);
                 if (PAIR) { umma_f16_pair(acc, dal, dbh, idesc, 1); umma_f16_pair(acc, dah, dbl, idesc, 1); }
                 else { umma_f16(acc, dal, dbh, idesc, 1); umma_f16(acc, dah, dbl, idesc, 1); }
               }
@@ -282,7 +353,11 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           }
         }
         __syncwarp();
-        if (elect_one()) { if (PAIR) umma_commit_pair(&acc_full[ab]); else umma_commit(&acc_full[ab]); }
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(&acc_full[ab]); else umma_commit(&acc_full[ab]);
+          // last item on this weight block: its MMAs release the resident weights to both producers
+          if (BRES && next_key >= 0 && next_key != key) { if (PAIR) umma_commit_pair(&b_empty); else umma_commit(&b_empty); }
+        }
         __syncwarp();
         if (lane == 0) LG_TRACE(2 + 3 * n_done);
       }
@@ -660,11 +735,25 @@ static bool lgemm_pair_enabled() {
   return v != 0;
 }
 
-template <int P, int M, int K, int PAIR>
+// Which WIRE chains keep the weight block of a pair's current (layer, N-block) resident in shared memory: INR_LGEMM_BRES bit 0 =
+// dgrad chain (default on; in-process A/B, tools/ab_variants.py: backward kernels of the bs 25 000 step 117.4 -> 113.5-114.0 us
+// with 24 / 32 / 48 KB slots, no gain with 16 KB slots, +15 us with 8 KB slots: fewer, larger copies), bit 1 = forward chain
+// (default off: 88.3 us against 79.5 us streaming with everything resident, equal with the hi image resident.  Neither fewer
+// L2 -> SM bytes nor a deeper ring -- a fifth slot was tried too -- move the 3-pass forward; what is left as a suspect is the
+// shared memory itself: per K = 16 step the MMAs read 21-30 KB of operands in 288 tensor cycles while the bulk copies
+// write 14 KB, i.e. 120-150 B per cycle against the 128 B per cycle an SM's shared memory moves).  Read per launch.
+static int lgemm_bres_mask() {
+  const char* e = std::getenv("INR_LGEMM_BRES");
+  return e ? std::atoi(e) : 1;
+}
+
+template <int P, int M, int K, int PAIR, int BRES = 0>
 static cudaError_t lgemm_launch_one(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   static bool attr = false;
   static int max_clusters = 0;
-  auto kern = lgemm_kernel<P, M, K, PAIR>;
+  auto kern = lgemm_kernel<P, M, K, PAIR, BRES>;
+  constexpr int kLgSmem = LgRing<M, PAIR, BRES>::smem;
+  if (BRES && (a.n_seg != 1 || !PAIR)) return cudaErrorInvalidValue;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem);
     if (e != cudaSuccess) return e;
@@ -688,6 +777,7 @@ static cudaError_t lgemm_launch_one(const LGemmArgs& a, int n_sm, cudaStream_t s
   int walkers = PAIR ? n_sm / 2 : n_sm;                    // never more CTAs than SMs
   if (PAIR && walkers > max_clusters) walkers = max_clusters;
   if (items < walkers) walkers = items;
+  if (BRES && walkers > 2) walkers &= ~1;                  // an even item stride keeps a pair on one N-block for a whole layer
   if (walkers <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(walkers << PAIR); cfg.blockDim = dim3(kLgThreads); cfg.dynamicSmemBytes = kLgSmem; cfg.stream = stream;
@@ -716,10 +806,20 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   cudaError_t e;
   switch (a.mode) {
     case LG_WIRE_FWD: {
-      static int kf = -1;
-      if (kf < 0) { const char* e2 = std::getenv("INR_LG_KF"); kf = e2 ? std::atoi(e2) : 3; }
+      const char* ekf = std::getenv("INR_LG_KF");          // K = 16 steps per ring slot (read per launch)
+      const int kf = ekf ? std::atoi(ekf) : 3;
       if (!lgemm_pair_enabled()) return cudaErrorNotSupported;
-      e = kf == 4 ? lgemm_launch_one<3, LG_WIRE_FWD, 4, 1>(a, n_sm, stream)
+      if (lgemm_bres_mask() & 2) {
+        static int kfb = -1;
+        if (kfb < 0) { const char* e2 = std::getenv("INR_LG_KFB"); kfb = e2 ? std::atoi(e2) : 2; }
+        static int lo = -1;      // INR_LG_LO=1: the weights' lo image streams (BRES = 2)
+        if (lo < 0) { const char* e2 = std::getenv("INR_LG_LO"); lo = e2 ? std::atoi(e2) : 1; }
+        if (lo) e = kfb == 3 ? lgemm_launch_one<3, LG_WIRE_FWD, 3, 1, 2>(a, n_sm, stream) : lgemm_launch_one<3, LG_WIRE_FWD, 2, 1, 2>(a, n_sm, stream);
+        else e = kfb == 1 ? lgemm_launch_one<3, LG_WIRE_FWD, 1, 1, 1>(a, n_sm, stream) : lgemm_launch_one<3, LG_WIRE_FWD, 2, 1, 1>(a, n_sm, stream);
+        break;
+      }
+      e = kf == 6 ? lgemm_launch_one<3, LG_WIRE_FWD, 6, 1>(a, n_sm, stream)
+        : kf == 4 ? lgemm_launch_one<3, LG_WIRE_FWD, 4, 1>(a, n_sm, stream)
         : kf == 3 ? lgemm_launch_one<3, LG_WIRE_FWD, 3, 1>(a, n_sm, stream) : lgemm_launch_one<3, LG_WIRE_FWD, 2, 1>(a, n_sm, stream);
       break;
     }
@@ -727,6 +827,14 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
       static int kd = -1;
       if (kd < 0) { const char* e2 = std::getenv("INR_LG_KD"); kd = e2 ? std::atoi(e2) : 4; }
       if (!lgemm_pair_enabled()) return cudaErrorNotSupported;
+      if (lgemm_bres_mask() & 1) {
+        const char* e2 = std::getenv("INR_LG_KDB");        // K = 16 steps per ring slot (read per launch)
+        const int kdb = e2 ? std::atoi(e2) : 8;
+        e = kdb == 12 ? lgemm_launch_one<1, LG_WIRE_DGRAD, 12, 1, 1>(a, n_sm, stream)
+          : kdb == 6 ? lgemm_launch_one<1, LG_WIRE_DGRAD, 6, 1, 1>(a, n_sm, stream)
+          : kdb == 4 ? lgemm_launch_one<1, LG_WIRE_DGRAD, 4, 1, 1>(a, n_sm, stream) : lgemm_launch_one<1, LG_WIRE_DGRAD, 8, 1, 1>(a, n_sm, stream);
+        break;
+      }
       e = kd == 8 ? lgemm_launch_one<1, LG_WIRE_DGRAD, 8, 1>(a, n_sm, stream)
         : kd == 6 ? lgemm_launch_one<1, LG_WIRE_DGRAD, 6, 1>(a, n_sm, stream) : lgemm_launch_one<1, LG_WIRE_DGRAD, 4, 1>(a, n_sm, stream);
       break;
