@@ -166,7 +166,7 @@ static int run_tv(const inr_loss_desc* loss, const float* out, int out_f, int64_
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "tv_kernel");
 }
 
-static int lgemm_dbg() { static int v = -1; if (v < 0) { const char* e = std::getenv("INR_LGEMM_DBG"); v = e ? std::atoi(e) : 0; } return v; }
+static int lgemm_dbg() { const char* e = std::getenv("INR_LGEMM_DBG"); return e ? std::atoi(e) : 0; }     // timing experiments; read per launch
 static unsigned long long* lgemm_trace_ptr() { return (g_trace && g_trace_lgemm_count++ == g_trace_lgemm_sel) ? g_trace : nullptr; }
 
 static int wire_plan_create(const inr_model_desc* d, inr_plan** out);
