@@ -534,7 +534,8 @@ static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (c < 8 || c > kW2dMaxP) return fail(INR_EUNSUPPORTED, "WIRE2D kernels are built for network_width <= 256");
   if (d->depth < 1 || d->depth > kWMaxDepth) return fail(INR_EINVAL, "network_depth out of range");
   if (d->out_features < 1 || d->out_features > 2) return fail(INR_EUNSUPPORTED, "network_output_size must be 1 or 2");
-  if (d->last_act != INR_LAST_LINEAR) return fail(INR_EUNSUPPORTED, "WIRE2D last_tanh (complex tanh tail) is not built");
+  if (d->last_act != INR_LAST_LINEAR && d->last_act != INR_LAST_TANH)
+    return fail(INR_EUNSUPPORTED, "WIRE2D output: linear (real part) or last_tanh (real part of the complex tanh)");
   inr_plan* p = new (std::nothrow) inr_plan();
   if (!p) return fail(INR_EINVAL, "out of host memory");
   p->desc = *d;
@@ -543,6 +544,7 @@ static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out) {
   std::memset(&M, 0, sizeof(M));
   const int P = (c + 63) / 64 * 64;
   M.depth = d->depth; M.c = c; M.in_f = 3; M.out_f = d->out_features; M.nlin = 2; M.P = P;
+  M.last_tanh = d->last_act == INR_LAST_TANH ? 1 : 0;
   M.omega_first = d->w0; M.omega_hidden = d->hidden_omega_0; M.sigma = d->sigma0;
   int off = 0;
   const int L = M.depth + 1;
@@ -603,7 +605,7 @@ static int wire2d_plan_create(const inr_model_desc* d, inr_plan** out) {
     u.b_tile_stride = kDzLastBytes; u.b_sub = 0; u.b_bytes = kDzLastBytes;
     u.n = kDzLastCols; u.transposed = 1;
     u.out_off = M.gd_final; u.out_ld = K2; u.row0 = 0; u.col0 = mc * 128;
-    u.rows_valid = M.out_f; u.cols_valid = 128;
+    u.rows_valid = M.last_tanh ? 4 : M.out_f; u.cols_valid = 128;     // tanh tail: dz_last = [gx0 gx1 | gy0 gy1] (w2d_blast_kernel)
     u.bias_off = mc == 0 ? M.gd_final + 16 * K2 : -1;
     p->units.push_back(u); p->unit_layer.push_back(L);
   }

@@ -123,6 +123,7 @@ struct WireModel {
   int c;                    // complex width (181)
   int in_f, out_f;          // 3, 2
   int nlin;                 // 1: WIRE, 2: WIRE2D (second linear `scale_orth` per layer)
+  int last_tanh;            // WIRE2D: complex tanh after the final linear (reference wire2d.py:106-107), output = Re(tanh(z))
   int P;                    // padded complex width: 192 (WIRE) or a multiple of 64 up to 256 (WIRE2D)
   int v_off[kWMaxDepth + 1], vb_off[kWMaxDepth + 1];          // WIRE2D: scale_orth weight / bias offsets, layers 0..depth
   float omega_first, omega_hidden, sigma;

@@ -3,7 +3,9 @@
 // scale_orth(h)  (:50-60).  With P = Re(conj(g) y), Q = Im(conj(g) y) for the upstream gradient g = dL/dy:
 //   dL/da = -2 s^2 a P - w Q,   dL/db = -(w + 2 s^2 b) P,   dL/dc = -2 s^2 c P,   dL/dd = -2 s^2 d P.
 //   w2d_first_kernel : real first layer (both linears real, :27-30) -> H images of layer 1, Z image [a|0|c|0], coordinate image
-//   w2d_last_kernel  : final complex linear, real part (:98-117) + per-row loss pieces
+//   w2d_last_kernel  : final complex linear, real part (:98-117) + per-row loss pieces; with `last_tanh` (:106-107) the output is
+//                      Re(tanh(z)), z = x + jy the complex linear:  out = sinh 2x / (cosh 2x + cos 2y), and the row's
+//                      d out / dx, d out / dy are left in the workspace for the backward entry kernel
 //   w2d_blast_kernel : backward of the final layer + derivative of the last Gabor layer
 #include <cuda_runtime.h>
 #include "inr_ptx.cuh"
@@ -110,15 +112,29 @@ __global__ void __launch_bounds__(256) w2d_first_kernel(const __grid_constant__ 
   }
 }
 
+// Real part of the complex tanh and its two partial derivatives, written with e = exp(-2|x|) so that nothing overflows:
+//   Re tanh(x + jy) = sgn(x) (1 - e^2) / D,  D = 1 + e^2 + 2 e cos 2y
+//   d/dx = (8 e^2 + 4 e (1 + e^2) cos 2y) / D^2,   d/dy = sgn(x) 4 e (1 - e^2) sin 2y / D^2
+__device__ __forceinline__ void w2d_re_tanh(float x, float y, float& out, float& tx, float& ty) {
+  const float e = expf(-2.f * fabsf(x)), e2 = e * e;
+  float s, c;
+  sincosf(2.f * y, &s, &c);
+  const float D = 1.f + e2 + 2.f * e * c, sg = x < 0.f ? -1.f : 1.f;
+  out = sg * (1.f - e2) / D;
+  tx = (8.f * e2 + 4.f * e * (1.f + e2) * c) / (D * D);
+  ty = sg * 4.f * e * (1.f - e2) * s / (D * D);
+}
+
 // ------------------------------------------------------------------------------------------------ final layer + loss
 __global__ void __launch_bounds__(512) w2d_last_kernel(const __grid_constant__ WireAuxArgs a) {
   __shared__ float sWr[kMaxOut][kW2dMaxP], sWi[kMaxOut][kW2dMaxP];
   __shared__ float red[4][8];
-  __shared__ float s_part[3][kTileM][kMaxOut];
+  __shared__ float s_part[3][kTileM][kMaxOut];     // out_f <= 2: columns 0..1 real parts, 2..3 imaginary parts (tanh tail)
   const WireModel& M = a.m;
   const int P = M.P, pg = P / 8;
   const int tile = blockIdx.x, row = threadIdx.x & (kTileM - 1), part = threadIdx.x >> 7, lane = row & 31, q = row >> 5;
   const int L = M.depth + 1;
+  const bool ctanh = M.last_tanh != 0;
   for (int i = threadIdx.x; i < kMaxOut * P; i += 512) {
     const int o = i / P, j = i % P;
     const bool ok = o < M.out_f && j < M.c;
@@ -144,8 +160,11 @@ __global__ void __launch_bounds__(512) w2d_last_kernel(const __grid_constant__ W
     for (int e = 0; e < 8; ++e) {
       const float hr = rh[e] + rl[e], hi = ih[e] + il[e];
 #pragma unroll
-      for (int o = 0; o < kMaxOut; ++o)
-        if (o < M.out_f) acc[o] = fmaf(hr, sWr[o][kg * 8 + e], fmaf(-hi, sWi[o][kg * 8 + e], acc[o]));
+      for (int o = 0; o < 2; ++o)
+        if (o < M.out_f) {
+          acc[o] = fmaf(hr, sWr[o][kg * 8 + e], fmaf(-hi, sWi[o][kg * 8 + e], acc[o]));
+          if (ctanh) acc[2 + o] = fmaf(hr, sWi[o][kg * 8 + e], fmaf(hi, sWr[o][kg * 8 + e], acc[2 + o]));
+        }
     }
   }
   if (part > 0) {
@@ -156,9 +175,21 @@ __global__ void __launch_bounds__(512) w2d_last_kernel(const __grid_constant__ W
   if (part > 0) return;
   float y[kMaxOut] = {0.f, 0.f, 0.f, 0.f}, t[kMaxOut] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int o = 0; o < kMaxOut; ++o)
+  for (int o = 0; o < 2; ++o)
     if (o < M.out_f)
       y[o] = ((acc[o] + s_part[0][row][o]) + (s_part[1][row][o] + s_part[2][row][o])) + a.params[M.b_off[L] + 2 * o];
+  if (ctanh) {
+    float fac[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+      if (o < M.out_f) {
+        const float zi = ((acc[2 + o] + s_part[0][row][2 + o]) + (s_part[1][row][2 + o] + s_part[2][row][2 + o])) +
+                         a.params[M.b_off[L] + 2 * o + 1];
+        w2d_re_tanh(y[o], zi, y[o], fac[2 * o], fac[2 * o + 1]);
+      }
+    if (a.train)      // (d out_0 / dx, d out_0 / dy, d out_1 / dx, d out_1 / dy) per row; WIRE2D does not use this slot otherwise
+      reinterpret_cast<float4*>(a.ws + a.w.outacc)[static_cast<size_t>(tile) * kTileM + row] = make_float4(fac[0], fac[1], fac[2], fac[3]);
+  }
   if (valid && a.out)
     for (int o = 0; o < M.out_f; ++o) a.out[static_cast<size_t>(grow) * M.out_f + o] = y[o];
   if (!a.train) return;
@@ -242,6 +273,13 @@ __global__ void __launch_bounds__(256) w2d_blast_kernel(const __grid_constant__ 
         dz[1] = S * (cA * g.y + cB * g.w);
       }
     }
+    // gradient of the final linear's pre-activation z = x + jy: (gx, gy) = dL/dout * (d out/dx, d out/dy); without the
+    // tanh tail out = x, i.e. (dz, 0).  dz[0..1] = gx, dz[2..3] = gy from here on.
+    if (M.last_tanh) {
+      const float4 f = reinterpret_cast<const float4*>(a.ws + a.w.outacc)[static_cast<size_t>(tile) * kTileM + row];
+      dz[2] = dz[0] * f.y; dz[3] = dz[1] * f.w;
+      dz[0] *= f.x; dz[1] *= f.z;
+    }
     const size_t ro = static_cast<size_t>(row) * 16;
     if (kg == 0) {
       uint8_t* zl = a.ws + a.w.dzlast + static_cast<size_t>(tile) * kDzLastBytes;
@@ -258,10 +296,13 @@ __global__ void __launch_bounds__(256) w2d_blast_kernel(const __grid_constant__ 
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int j = kg * 8 + e;
-      float gr = 0.f, gi = 0.f;     // dL/d Re(h_j), dL/d Im(h_j) for out = Re(h W^T + b)
+      float gr = 0.f, gi = 0.f;     // dL/d Re(h_j), dL/d Im(h_j) for z = h W^T + b, dL/dz = gx + j gy
 #pragma unroll
-      for (int o = 0; o < kMaxOut; ++o)
-        if (o < M.out_f) { gr = fmaf(dz[o], sWr[o][j], gr); gi = fmaf(-dz[o], sWi[o][j], gi); }
+      for (int o = 0; o < 2; ++o)
+        if (o < M.out_f) {
+          gr = fmaf(dz[o], sWr[o][j], fmaf(dz[2 + o], sWi[o][j], gr));
+          gi = fmaf(-dz[o], sWi[o][j], fmaf(dz[2 + o], sWr[o][j], gi));
+        }
       const float Pp = gr * yr[e] + gi * yi[e];
       const float Q = gr * yi[e] - gi * yr[e];
       da[e] = ratio * (-2.f * s2 * za[e] * Pp - w * Q);

@@ -5,7 +5,8 @@
 //     dWr[o,i] = D[o,i] + D[P+o,P+i]      dWi[o,i] = D[P+o,i] - D[o,P+i]        (linear)
 //     dVr[o,i] = D[2P+o,i] + D[3P+o,P+i]  dVi[o,i] = D[3P+o,i] - D[2P+o,P+i]    (scale_orth)
 //   first layer (real): D0 [4P][16] against the coordinate image [x_hi(3), 1, x_lo(3), 0]: dW[o,c] = D0[o,c] + D0[o,4+c],
-//     db[o] = D0[o,3]; scale_orth from the rows 2P+o.   final layer: as WIRE (DT [16][2P] + bias).
+//     db[o] = D0[o,3]; scale_orth from the rows 2P+o.   final layer: as WIRE (DT [16][2P] + bias); with the complex tanh tail
+//     rows 2 + o of DT hold the gradient of Im z_o:  dWr[o,j] = DT[o,j] + DT[2+o,P+j],  dWi[o,j] = -DT[o,P+j] + DT[2+o,j].
 //   packed operands (fp16): forward blocks of 64 output features, rows [a | b | c | d] x K = 2P with
 //     a_o = [Wr_o | -Wi_o], b_o = [Wi_o | Wr_o], c_o = [Vr_o | -Vi_o], d_o = [Vi_o | Vr_o]  (hi + lo copies);
 //   dgrad blocks of 128 input features, rows [dhr | dhi] x K = 4P with
@@ -122,8 +123,10 @@ __global__ void __launch_bounds__(256) w2d_adam_kernel(const __grid_constant__ W
         if (loc.kind == 0) {
           const int e = idx >> 1, oo = e / M.c, j = e % M.c;
           g += (idx & 1) ? -DT[oo * K2 + P + j] : DT[oo * K2 + j];
+          // tanh tail: rows 2 + o of DT carry gy (gradient of Im z):  dWr += gy . hi,  dWi += gy . hr
+          if (M.last_tanh) g += (idx & 1) ? DT[(2 + oo) * K2 + j] : DT[(2 + oo) * K2 + P + j];
         } else {
-          g += (idx & 1) ? 0.f : DT[16 * K2 + (idx >> 1)];
+          g += (idx & 1) ? (M.last_tanh ? DT[16 * K2 + 2 + (idx >> 1)] : 0.f) : DT[16 * K2 + (idx >> 1)];
         }
       }
     }

@@ -61,8 +61,8 @@ class Plan:
         if model not in L.MODEL:
             raise NotImplementedError(model)                      # src/train.py:69-70
         if model == "WIRE2D" and net.get("last_tanh", False):
-            raise L.InrError("WIRE2D with last_tanh (complex tanh tail, wire2d.py:106-107) is not built")
-        if model in ("WIRE", "WIRE2D", "Fourier", "MultiscaleFourier", "BoundedFourier", "Gabor", "KGabor"):
+            last = "tanh"                                          # src/models/wire2d.py:106-107: complex tanh, then .real
+        elif model in ("WIRE", "WIRE2D", "Fourier", "MultiscaleFourier", "BoundedFourier", "Gabor", "KGabor"):
             last = "linear"                                        # WIRE: real part of the final complex linear; MFN: plain heads
         elif model == "FFN":
             last = "sigmoid"                                       # src/models/networks.py:63

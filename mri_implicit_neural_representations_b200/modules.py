@@ -51,7 +51,7 @@ class _ChainFn(torch.autograd.Function):
         m = ctx.module
         dz = dout
         if m._act_in_kernel():
-            pass          # wide chains: the backward entry kernel applies the output activation's derivative itself
+            pass          # wide chains / WIRE2D: the backward entry kernel applies the output activation's derivative itself
         elif m._last_act == "tanh":
             dz = dout * (1 - out * out)
         elif m._last_act == "sigmoid":
@@ -179,7 +179,8 @@ class FusedChain(nn.Module):
 
     def _act_in_kernel(self):
         eng = next(iter(self._engines.values()))
-        return bool(getattr(eng.plan, "wide", False))
+        # wide chains, and WIRE2D's complex tanh tail (the derivative needs the imaginary part of the final linear as well)
+        return bool(getattr(eng.plan, "wide", False)) or eng.plan.model == "WIRE2D"
 
     def _dead_param_flags(self):
         """True for parameters no gradient ever reaches (reference autograd leaves their .grad None)."""

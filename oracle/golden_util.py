@@ -35,6 +35,7 @@ CASES = {
     "fourier_l2": ("Fourier", NET_MFN, ENC_GAUSS, "L2", None, 300, 18),
     "gabor_tanh": ("Gabor", NET_MFN, ENC_GAUSS, "tanh", None, 300, 19),
     "wire2d_l2":  ("WIRE2D", NET_W2D, ENC_NONE, "L2", None, 400, 20),
+    "wire2d_tanh": ("WIRE2D", dict(NET_W2D, last_tanh=True), ENC_NONE, "tanh", None, 384, 21),
 }
 N_ADAM_STEPS = 3
 LR = 5e-4

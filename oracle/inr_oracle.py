@@ -276,8 +276,8 @@ def wire_forward(sd, x, depth, trace=None):
     return out.real
 
 
-def wire2d_forward(sd, x, depth, trace=None):
-    """src/models/wire2d.py:49-60,112-118 (no complex tanh tail: last_tanh handled by caller)."""
+def wire2d_forward(sd, x, depth, trace=None, last_tanh=False):
+    """src/models/wire2d.py:49-60,112-118; last_tanh (:106-107): torch.nn.Tanh on the complex output, then .real."""
     h = x
     for i in range(depth + 1):
         l = h @ sd[f"net.{i}.linear.weight"].t() + sd[f"net.{i}.linear.bias"]
@@ -291,6 +291,8 @@ def wire2d_forward(sd, x, depth, trace=None):
         if trace is not None:
             trace.append((l, s, h))
     out = h @ sd[f"net.{depth + 1}.weight"].t() + sd[f"net.{depth + 1}.bias"]
+    if last_tanh:
+        out = torch.tanh(out)
     return out.real
 
 
@@ -586,7 +588,7 @@ def model_forward(kind, sd, x, net, trace=None):
     if kind == "WIRE":
         return wire_forward(sd, x, d, trace=trace)
     if kind == "WIRE2D":
-        return wire2d_forward(sd, x, d, trace=trace)
+        return wire2d_forward(sd, x, d, trace=trace, last_tanh=net.get("last_tanh", False))
     if kind == "Fourier":
         return mfn_forward(sd, x, d, False, trace=trace)
     if kind in ("Gabor", "KGabor"):

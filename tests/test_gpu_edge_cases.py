@@ -79,8 +79,7 @@ def test_unsupported_requests_fail_loudly(inr):
     assert inr.Plan("SIREN", dict(net, network_last_linear=False), G.ENC_GAUSS).wide  # sine output layer: built since round 2 (wide chain)
     with pytest.raises(Exception):
         inr.Plan("SIREN", net, {"embedding": "LogF", "scale": 4, "embedding_size": 256, "coordinates_size": 3})
-    with pytest.raises(Exception):
-        inr.Plan("WIRE2D", dict(G.NET_W2D, last_tanh=True), G.ENC_NONE)
+    inr.Plan("WIRE2D", dict(G.NET_W2D, last_tanh=True), G.ENC_NONE)      # complex tanh tail: built (tests/test_gpu_wire2d.py)
     with pytest.raises(NotImplementedError):
         inr.Plan("NoSuchModel", net, G.ENC_GAUSS)
     plan = inr.Plan("SIREN", net, G.ENC_GAUSS)

@@ -181,3 +181,97 @@ def test_wire2d_fused_steps_module_and_frozen_parameters(inr):
     with torch.no_grad():
         o = m(coords.cuda())
     assert rel(o, O.wire2d_forward(to64(sd), coords.double(), net["network_depth"])) <= 5e-2
+
+
+# ------------------------------------------------------------------------------------------------ complex tanh tail
+def _act_grad(sd, dh, y, zl, l):
+    w_, s2 = float(sd[f"net.{l}.omega_0"]), float(sd[f"net.{l}.scale_0"]) ** 2
+    pq = dh.conj() * y
+    za, zb, zc, zd = zl
+    da = -2 * s2 * za * pq.real - w_ * pq.imag
+    dc = -2 * s2 * zc * pq.real
+    if l == 0:
+        return [da, torch.zeros_like(da), dc, torch.zeros_like(da)]
+    return [da, -(w_ + 2 * s2 * zb) * pq.real, dc, -2 * s2 * zd * pq.real]
+
+
+def _engine_tanh(inr):
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup("wire2d_tanh")
+    plan = inr.Plan(model_kind, net, enc_cfg)
+    eng = inr.ChainEngine(plan, max_batch=coords.shape[0], lr=G.LR)
+    eng.load_tensors(list(sd.values()))
+    return plan, eng, net, loss_kind, opts, sd, coords, gt
+
+
+def test_wire2d_tanh_tail_forward_backward_teacher_forced(inr):
+    """reference wire2d.py:106-107,115-116: torch.nn.Tanh on the complex final linear, then `.real`.  The final stage is judged
+    teacher-forced on the engine's own last-layer activations (fp64): output, the gradient handed to the last hidden layer,
+    and the COMPLEX gradients of the final weight / bias (the imaginary parts exist only because of the tail)."""
+    plan, eng, net, loss_kind, opts, sd, coords, gt = _engine_tanh(inr)
+    depth, bs, C = net["network_depth"], coords.shape[0], net["network_width"]
+    P = (C + 63) // 64 * 64
+    L = depth + 1
+    sd64 = to64(sd)
+    out_dev = torch.zeros(bs, 2, device="cuda")
+    eng.grad_step(loss_kind, coords.cuda(), gt.cuda(), bs, loss_opts=opts, out=out_dev)
+    torch.cuda.synchronize()
+    Sl = eng.scalars(bs)[16:16 + depth + 1].tolist()
+    hr, hi = _img(eng, "h", L, bs, P, 2)
+    hL = torch.complex(hr, hi)[:, :C]
+    z = (hL @ sd64[f"net.{L}.weight"].t() + sd64[f"net.{L}.bias"]).requires_grad_(True)
+    o_tf = torch.tanh(z).real
+    assert rel(out_dev, o_tf.detach()) <= 1e-5
+    val, dout = loss_and_grad(loss_kind, opts, out_dev.cpu().double(), gt.double(), coords.double())
+    assert abs(float(eng.loss_out) - float(val)) <= TOL * abs(float(val))
+    gz = torch.autograd.grad(o_tf, z, grad_outputs=dout)[0]          # dL/dx + j dL/dy
+    assert float(gz.imag.abs().max()) > 1e-3 * float(gz.real.abs().max())      # the tail does feed the imaginary part
+    dh = gz @ sd64[f"net.{L}.weight"].conj()
+    zl = [m[:, :C] for m in _img(eng, "z", depth, bs, P, 4)]
+    dzl = [m[:, :C] / Sl[depth] for m in _img(eng, "dz", depth, bs, P, 4)]
+    assert rel(torch.cat(dzl, 1), torch.cat(_act_grad(sd, dh, hL, zl, depth), 1)) <= TOL
+    gv = dict(zip(sd.keys(), eng._views(eng.grads)))
+    assert rel(gv[f"net.{L}.weight"], gz.t() @ hL.conj()) <= TOL
+    assert rel(gv[f"net.{L}.bias"], gz.sum(0)) <= TOL
+    # end to end against fp64 autograd on the oracle: inside the drift band of the fp32 reference itself
+    x64 = coords.double()
+    Pm = {k: v.clone().requires_grad_(not (k.endswith("omega_0") or k.endswith("scale_0"))) for k, v in sd64.items()}
+    o64 = O.model_forward("WIRE2D", Pm, x64, net)
+    o32 = O.model_forward("WIRE2D", sd, coords, net)
+    assert rel(out_dev, o64.detach()) <= 4 * rel(o32, o64.detach()) + 1e-4
+    _, d64 = loss_and_grad(loss_kind, opts, o64.detach(), gt.double(), x64)
+    live = [k for k in Pm if Pm[k].requires_grad]
+    ref = dict(zip(live, torch.autograd.grad(o64, [Pm[k] for k in live], grad_outputs=d64)))
+    for k in live:
+        assert rel(gv[k], ref[k]) <= 5e-2, (k, rel(gv[k], ref[k]))
+
+
+def test_wire2d_tanh_tail_fused_steps_and_module(inr):
+    plan, eng, net, loss_kind, opts, sd, coords, gt = _engine_tanh(inr)
+    bs = coords.shape[0]
+    gold = G.load_golden("wire2d_tanh")
+    losses = []
+    for step in range(G.N_ADAM_STEPS):
+        eng.train_step(loss_kind, coords.cuda(), gt.cuda(), bs, loss_opts=opts)
+        losses.append(float(eng.loss_out))
+    assert abs(losses[0] - gold["fp64"]["losses"][0]) <= 5e-4 * gold["fp64"]["losses"][0]
+    lo = min(gold["losses"][-1], gold["fp64"]["losses"][-1])
+    hi = max(gold["losses"][-1], gold["fp64"]["losses"][-1])
+    assert 0.9 * lo <= losses[-1] <= 1.1 * hi
+    # drop-in module (autograd face): output and parameter .grad against torch autograd on the fp64 oracle
+    from mri_implicit_neural_representations_b200.modules import WIRE2D
+    torch.manual_seed(3)
+    m = WIRE2D(dict(net)).to("cuda")
+    m.load_state_dict({k: v for k, v in sd.items()})
+    o = m(coords.cuda())
+    sd64 = to64(sd)
+    Pm = {k: v.clone().requires_grad_(not (k.endswith("omega_0") or k.endswith("scale_0"))) for k, v in sd64.items()}
+    o64 = O.model_forward("WIRE2D", Pm, coords.double(), net)
+    assert rel(o.detach(), o64.detach()) <= 5e-2
+    w = torch.linspace(0.5, 1.5, bs * 2).view(bs, 2)
+    (o * w.cuda()).sum().backward()
+    (o64 * w.double()).sum().backward()
+    for k, p in m.state_dict(keep_vars=True).items():
+        if Pm[k].requires_grad:
+            assert rel(p.grad, Pm[k].grad) <= 5e-2, k
+        else:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k

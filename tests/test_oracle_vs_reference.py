@@ -41,6 +41,22 @@ def test_init_and_forward_all_models():
         assert float((m(x) - fwd(sd)).abs().max()) <= tol, cls.__name__
 
 
+def test_wire2d_complex_tanh_tail():
+    """wire2d.py:106-107: torch.nn.Tanh on the complex output of the final linear, `.real` afterwards (:115-116)."""
+    W2 = ref_shims.load("models.wire2d")
+    x = torch.randn(40, 24)
+    net = dict(NET, last_tanh=True)
+    torch.manual_seed(7)
+    m = W2.WIRE2D(dict(net))
+    torch.manual_seed(7)
+    sd = O.wire2d_init(dict(net))
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    ref = m(x)
+    got = O.model_forward("WIRE2D", sd, x, net)
+    assert float((ref - got).abs().max()) <= 1e-4
+    assert float((ref - O.wire2d_forward(sd, x, 3)).abs().max()) > 1e-3      # the tail is not a no-op on this input
+
+
 def test_multiscale_models_and_bounded_quirk():
     M = ref_shims.load("models.mfn")
     net = dict(NET, network_depth=8)
