@@ -166,6 +166,8 @@ static int run_tv(const inr_loss_desc* loss, const float* out, int out_f, int64_
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "tv_kernel");
 }
 
+// read per launch (tools/ab_variants.py switches it between launches of one process)
+static bool wire_fold_blast() { const char* e = std::getenv("INR_WIRE_FOLD_BLAST"); return !(e && e[0] == '0'); }
 static int lgemm_dbg() { const char* e = std::getenv("INR_LGEMM_DBG"); return e ? std::atoi(e) : 0; }     // timing experiments; read per launch
 static unsigned long long* lgemm_trace_ptr() { return (g_trace && g_trace_lgemm_count++ == g_trace_lgemm_sel) ? g_trace : nullptr; }
 
@@ -731,8 +733,13 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
     e = launch_wire_scalars(x, st);
     if (e != cudaSuccess) return cuda_fail(e, "wire_scalars_kernel");
   }
-  e = M.nlin == 2 ? launch_w2d_blast(x, st) : launch_wire_blast(x, st);
-  if (e != cudaSuccess) return cuda_fail(e, "wire_blast_kernel");
+  // WIRE: the backward of the final linear rides in the dgrad chain as its first ("top") items -- one launch less, and the
+  // chain's CTAs start on it while wire_last's tail is still draining (INR_WIRE_FOLD_BLAST=0: separate wire_blast_kernel)
+  const bool fold_blast = M.nlin == 1 && M.depth + 1 <= kWMaxDepth && wire_fold_blast();
+  if (!fold_blast) {
+    e = M.nlin == 2 ? launch_w2d_blast(x, st) : launch_wire_blast(x, st);
+    if (e != cudaSuccess) return cuda_fail(e, "wire_blast_kernel");
+  }
   if (M.nlin == 2) {      // WIRE2D dgrad, layers depth .. 1 as ONE chained launch (hand-over through w.flags_bwd, zeroed by w2d_blast)
     LGemmArgs g{};
     g.seg[0].a_tile_bytes = static_cast<uint32_t>(kTileM) * 4 * M.P * 2; g.seg[0].k_stages = 4 * M.P / kStageK; g.seg[0].acc_col = 0;
@@ -757,9 +764,21 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 1; g.mode = LG_WIRE_DGRAD;
     g.sigma = M.sigma; g.c_valid = M.c;
     g.scal = reinterpret_cast<const float*>(W + w.scal);
-    g.chain_len = M.depth; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_bwd);
+    const int top = fold_blast ? 1 : 0;
+    g.chain_len = M.depth + top; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_bwd);
+    if (fold_blast) {       // chain[0]: dL/dh_L from dL/dout * W_last, Gabor derivative of the last hidden layer, dz_last image
+      LGemmLayer& c = g.chain[0];
+      c.omega = M.omega_hidden; c.real_first = 0;
+      c.in_y = W + w.hhi[M.depth + 1]; c.in_ab = W + w.ab[M.depth]; c.out_dz = W + w.dz[M.depth];
+      c.src_layer = -1; c.dst_layer = M.depth;
+      g.top_w = params + M.w_off[M.depth + 1];
+      g.top_g = reinterpret_cast<const float*>(W + w.g);
+      g.top_dout = dout;
+      g.top_dzlast = W + w.dzlast;
+      g.bs = static_cast<int>(bs); g.out_f = M.out_f;
+    }
     for (int l = M.depth; l >= 1; --l) {
-      LGemmLayer& c = g.chain[M.depth - l];
+      LGemmLayer& c = g.chain[M.depth - l + top];
       c.a_hi = W + w.dz[l]; c.b_hi = wp + M.wd_hi[l];
       c.omega = (l - 1 == 0) ? M.omega_first : M.omega_hidden;
       c.real_first = (l - 1 == 0) ? 1 : 0;

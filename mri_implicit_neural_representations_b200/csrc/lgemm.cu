@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   constexpr bool kChain = MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD || MODE == LG_W2D_FWD || MODE == LG_W2D_DGRAD;
   constexpr int kBiasFloats = MODE == LG_WIRE_FWD ? kWMaxDepth * kWP : 512;
   __shared__ float s_ba[kBiasFloats], s_bb[kBiasFloats];   // WIRE_FWD: bias re / im per chain layer;  MFN: b_i / phi_i (width <= 512)
-  __shared__ float4 s_lw[MODE == LG_WIRE_FWD ? kWP : 1];   // WIRE_FWD: final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
+  // WIRE_FWD / WIRE_DGRAD (top items): final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
+  __shared__ float4 s_lw[(MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) ? kWP : 1];
+  const bool has_top = MODE == LG_WIRE_DGRAD && a.top_w != nullptr;      // chain[0] = backward of the final linear, no GEMM
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
@@ -150,6 +152,16 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       }
       s_lw[j] = lw;
     }
+  } else if (MODE == LG_WIRE_DGRAD) {
+    if (has_top)
+      for (int j = tid; j < kWP; j += kLgThreads) {
+        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < a.c_valid) {
+          lw.x = a.top_w[2 * j]; lw.y = a.top_w[2 * j + 1];
+          if (a.out_f > 1) { lw.z = a.top_w[2 * (a.c_valid + j)]; lw.w = a.top_w[2 * (a.c_valid + j) + 1]; }
+        }
+        s_lw[j] = lw;
+      }
   } else if (MODE == LG_MFN_FWD) {
     const int width = a.n_nblocks * a.nt;
     for (int j = tid; j < width; j += kLgThreads) {
@@ -203,6 +215,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
                                 static_cast<size_t>(((lane & 1) ? kWP / 8 : 0) + (kWFeatPerBlock / 8) * nb) * 2048;
           if (!(lane == 3 && Lq.real_first)) bulk_prefetch_l2(base, (kWFeatPerBlock / 8) * 2048);
         }
+        if (has_top && layer == 0) continue;      // top items have no operands: nothing to stream, no ring slots used
         if (BRES && layer * a.n_nblocks + nb != cur_b) {
           // new weight block: wait until the MMAs that read the old one are done (commit of the last item that used it), then
           // fetch this CTA's half -- lanes 0-3 a quarter of the hi image each, lanes 4-7 of the lo image
@@ -270,6 +283,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         uint32_t slot = 0, ph = 0, bph = 0;
         int cur_b = -1;
         for (int item = cta0; item < n_items; item += n_walk) {
+          if (has_top && item < per_layer) continue;
           if (BRES) {
             const int layer = item / per_layer, nb = (item - layer * per_layer) % a.n_nblocks;
             if (layer * a.n_nblocks + nb != cur_b) {        // my half of the new weight block has landed: tell the leader
@@ -307,6 +321,15 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         if (tr) tq = clock64();
         mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
         if (tr) c_acc += clock64() - tq;
+        if (has_top && item < per_layer) {
+          // top item: no MMAs; the commit (nothing outstanding for this accumulator) keeps the accumulator barriers of both
+          // CTAs in step with the epilogue warps
+          tc_fence_after();
+          __syncwarp();
+          if (elect_one()) { if (PAIR) umma_commit_pair(&acc_full[ab]); else umma_commit(&acc_full[ab]); }
+          __syncwarp();
+          continue;
+        }
         int key = 0, next_key = -1;
         if (BRES) {
           const int layer = item / per_layer, nb = (item - layer * per_layer) % a.n_nblocks;
@@ -439,7 +462,8 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         if (cur_layer >= 0) flush_amax(a.chain[cur_layer].dst_layer);
         cur_layer = layer;
         s_dst = a.scal[SC_LAYER_SCALE + Ly.dst_layer];
-        ratio = s_dst / a.scal[SC_LAYER_SCALE + Ly.src_layer];
+        // top items: dL/dh is built from dz_last, which carries the global scale S
+        ratio = s_dst / a.scal[(has_top && layer == 0) ? SC_SCALE : SC_LAYER_SCALE + Ly.src_layer];
       }
       const float w = kChain ? Ly.omega : a.omega;
       const uint32_t ab = n_done & 1, use = n_done >> 1;
@@ -537,6 +561,28 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             pre[i][3] = Ly.real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(Ly.in_ab + off_i);
           }
         }
+        const bool top = MODE == LG_WIRE_DGRAD && has_top && layer == 0;
+        float dzo0 = 0.f, dzo1 = 0.f;                       // top items: S * dL/dout of this thread's row
+        if (top) {
+          const int grow = tile * kTileM + row;
+          const float S = a.scal[SC_SCALE];
+          if (grow < a.bs) {
+            if (a.top_dout) {
+              dzo0 = S * a.top_dout[static_cast<size_t>(grow) * a.out_f];
+              if (a.out_f > 1) dzo1 = S * a.top_dout[static_cast<size_t>(grow) * a.out_f + 1];
+            } else {
+              const float cA = a.scal[SC_CA], cB = a.scal[SC_CB];
+              const float4 g = *reinterpret_cast<const float4*>(a.top_g + static_cast<size_t>(grow) * 4);
+              dzo0 = S * (cA * g.x + cB * g.z);
+              dzo1 = S * (cA * g.y + cB * g.w);
+            }
+          }
+          if (nb == 0 && sub == 0) {                        // padded dz_last image for the final layer's wgrad
+            uint8_t* zl = a.top_dzlast + static_cast<size_t>(tile) * kDzLastBytes;
+            st_global_v4(zl + row * 16, make_uint4(pack_h2(dzo0, dzo1), 0u, 0u, 0u));
+            st_global_v4(zl + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
+          }
+        }
         mbar_wait(&acc_full[ab], use & 1);
         tc_fence_after();
         if (tid == 128) LG_TRACE(3 + 3 * n_done);
@@ -594,9 +640,18 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             }
           } else {
             const uint4 yr4 = pre[i][0], yi4 = pre[i][1], a4 = pre[i][2], b4 = pre[i][3];
-            tmem_ld8(acc + c0, va);                       // dL/d Re(h)
-            tmem_ld8(acc + kWFeatPerBlock + c0, vb);      // dL/d Im(h)
-            tmem_ld_wait();
+            if (top) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {                 // out = Re(h W^T + b):  dL/d Re(h_j) = dz . Wr_j,  dL/d Im(h_j) = -dz . Wi_j
+                const float4 lw = s_lw[f0 + e];
+                va[e] = fmaf(dzo1, lw.z, fmaf(dzo0, lw.x, 0.f));
+                vb[e] = fmaf(-dzo1, lw.w, fmaf(-dzo0, lw.y, 0.f));
+              }
+            } else {
+              tmem_ld8(acc + c0, va);                       // dL/d Re(h)
+              tmem_ld8(acc + kWFeatPerBlock + c0, vb);      // dL/d Im(h)
+              tmem_ld_wait();
+            }
             float yr[8], yi[8], za[8], zb[8], da[8], db[8];
             unpack8(yr4, yr); unpack8(yi4, yi); unpack8(a4, za); unpack8(b4, zb);
 #pragma unroll

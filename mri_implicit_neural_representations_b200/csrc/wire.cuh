@@ -113,6 +113,14 @@ struct LGemmArgs {
   const float* gamma;       // GABOR_E: gamma_j [width]
   const float* mn;          // GABOR_E: |mu_j|^2 [width]
   uint32_t feat_tile_bytes; // bytes of one 128-row image of the epilogue's feature images (MFN: 128 * width * 2)
+  // WIRE_DGRAD chain with the backward of the final complex linear folded in (what wire_blast_kernel does as a launch of its
+  // own): top_w != null makes chain[0] a "top" pseudo-layer without a GEMM -- its items' epilogues take dL/dh from
+  // dL/dout * W_last instead of an accumulator (out = Re(h W^T + b), reference networks.py:247-258) and also write the
+  // padded dz_last image the final layer's wgrad reads.  Uses bs / out_f above.
+  const float* top_w;       // final-layer weight [out_f][c] complex, interleaved (re, im)
+  const float* top_g;       // per-row loss-gradient pieces [rows][4] fp32 (gA0, gA1, gB0, gB1) of wire_last_kernel
+  const float* top_dout;    // external dL/dout [bs][out_f] (autograd face) or null
+  uint8_t* top_dzlast;      // dz_last image [tile][2][128 rows][8] fp16
   int dbg;                  // debug (INR_LGEMM_DBG), timing experiments only, results are wrong: bit 0 skip MMAs, bit 1 skip operand copies,
                             // bit 2 skip the proxy fence and bit 3 the hand-over wait of chained layers
   unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)

@@ -134,7 +134,13 @@ __device__ inline void wire_step_scalars(const WireAuxArgs& a) {
   }
 }
 
-__global__ void __launch_bounds__(256) wire_scalars_kernel(const __grid_constant__ WireAuxArgs a) { wire_step_scalars(a); }
+__global__ void __launch_bounds__(256) wire_scalars_kernel(const __grid_constant__ WireAuxArgs a) {
+  // hand-over counters of the chained dgrad GEMMs start at zero (this kernel precedes every backward that wire_last's folded
+  // scalars do not: autograd face, TV pass, calibration re-runs)
+  unsigned int* fb = reinterpret_cast<unsigned int*>(a.ws + a.w.flags_bwd);
+  for (int i = threadIdx.x; i < kWMaxDepth * a.w.n_tiles; i += blockDim.x) fb[i] = 0u;
+  wire_step_scalars(a);
+}
 
 // ------------------------------------------------------------------------------------------------ final layer + loss
 __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ WireAuxArgs a) {
@@ -163,6 +169,9 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
     }
   }
   griddep_wait();                    // the last layer GEMM's partial sums are complete
+  // hand-over counters of the chained dgrad GEMMs start at zero (the chain may follow this kernel directly: the backward of
+  // the final linear rides in it, lgemm.cu "top" items)
+  if (a.train && threadIdx.x < kWMaxDepth) reinterpret_cast<unsigned int*>(a.ws + a.w.flags_bwd)[threadIdx.x * a.w.n_tiles + tile] = 0u;
   // Dependents (the backward entry kernel) are released only now: whatever they read ahead of their own wait -- the saved
   // activations of the last hidden layer -- is final once this kernel is past the chain.
   griddep_launch_dependents();
