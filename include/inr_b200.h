@@ -129,10 +129,13 @@ int inr_plan_tensor_count(const inr_plan* plan, int32_t* n);
 int inr_plan_tensor(const inr_plan* plan, int32_t index, inr_tensor_info* out);
 /* bytes of the fp16 operand copies of the weights (caller allocates, 1024-aligned) */
 int inr_wpack_bytes(const inr_plan* plan, size_t* bytes);
-/* bytes of activation/gradient workspace for batches of up to `bs` coordinates.  The first INR_SCALAR_FLOATS floats of
- * the workspace (the scalar block) must be ZERO before the first call and belong to the library afterwards: they carry
- * state across steps (WIRE / MFN per-layer gradient scales and amax accumulators, and the finished-CTA counter of the
- * last-CTA reduction in wire_last_kernel, which resets itself).  The rest of the workspace needs no initialisation. */
+/* bytes of activation/gradient workspace for batches of up to `bs` coordinates.  The first INR_WS_ZERO_BYTES bytes of
+ * the workspace must be ZERO before the first call and belong to the library afterwards: the scalar block
+ * (INR_SCALAR_FLOATS floats) carries state across steps (WIRE / MFN per-layer gradient scales and amax accumulators, and
+ * the finished-CTA counter of the last-CTA reduction in wire_last_kernel, which resets itself); behind it sit the tile
+ * hand-over counters of the WIRE forward layer chain, which every forward pass leaves at zero again (the chain is the first
+ * kernel of a step, so no kernel before it could clear them).  The rest of the workspace needs no initialisation. */
+#define INR_WS_ZERO_BYTES (1024 + 8 * 4096 * 4)
 int inr_workspace_bytes(const inr_plan* plan, int64_t bs, size_t* bytes);
 /* byte offset of the INR_SCALAR_FLOATS step scalars inside a workspace sized for `bs` */
 int inr_scalars_offset(const inr_plan* plan, int64_t bs, size_t* offset);

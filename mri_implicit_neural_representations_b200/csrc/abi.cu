@@ -167,6 +167,10 @@ static int run_tv(const inr_loss_desc* loss, const float* out, int out_f, int64_
 }
 
 // read per launch (tools/ab_variants.py switches it between launches of one process)
+// (default off: measured on B200 at bs 25 000, the chain grows by 9.6 us -- 2.65 rounds of store-bound items during which the
+// tensor pipe idles -- while wire_first_kernel takes 13 us next to it: forward phase 117.2 -> 113.3 us with eager launches, but
+// 228.1 -> 230.4 us per step in the CUDA graph, where the separate kernel's launch is already hidden.  INR_WIRE_FOLD_FIRST=1.)
+static bool wire_fold_first() { const char* e = std::getenv("INR_WIRE_FOLD_FIRST"); return e && e[0] == '1'; }
 static bool wire_fold_blast() { const char* e = std::getenv("INR_WIRE_FOLD_BLAST"); return !(e && e[0] == '0'); }
 static int lgemm_dbg() { const char* e = std::getenv("INR_LGEMM_DBG"); return e ? std::atoi(e) : 0; }     // timing experiments; read per launch
 static unsigned long long* lgemm_trace_ptr() { return (g_trace && g_trace_lgemm_count++ == g_trace_lgemm_sel) ? g_trace : nullptr; }
@@ -637,11 +641,13 @@ static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
   w.n_split = ns;
   uint64_t o = 0;
   w.scal = o; o += align_up(kScalars * 4, 1024);
+  // forward hand-over counters: same place for every batch size (a chain that starts the step cannot have them zeroed by a
+  // kernel before it: wire_last zeroes what the chain used, and the block starts out zero -- include/inr_b200.h)
+  w.flags_fwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * kWFlagTiles * 4, 1024);
   w.part = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
   w.g = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
   w.outacc = o; o += align_up(static_cast<uint64_t>(T) * kWOutParts * kTileM * 16, 1024);   // partial outputs of the final linear
-  w.flags_fwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * T * 4, 1024);          // layer-chain hand-over counters
-  w.flags_bwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * T * 4, 1024);
+  w.flags_bwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * T * 4, 1024);          // dgrad hand-over counters
   const uint64_t img = static_cast<uint64_t>(T) * kTileM * 2 * M.P * 2;            // H images: [hr | hi]
   const uint64_t zimg = img * M.nlin;                                              // pre-activation / gradient images
   for (int l = 1; l <= M.depth + 1; ++l) { w.hhi[l] = o; o += img; w.hlo[l] = o; o += img; }
@@ -672,8 +678,13 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
   WireAuxArgs x; wire_aux_fill(p, w, x, params, ws, bs);
   x.loss = loss; x.coords = coords; x.gt = gt; x.mask = mask; x.out = out; x.train = train;
   x.row_offset = row_off; x.step_counter = step;
-  cudaError_t e = M.nlin == 2 ? launch_w2d_first(x, st) : launch_wire_first(x, st);
-  if (e != cudaSuccess) return cuda_fail(e, "wire_first_kernel");
+  // WIRE, opt-in (INR_WIRE_FOLD_FIRST=1): the real first layer rides in the forward chain as its first items -- one launch less
+  const bool fold_first = M.nlin == 1 && M.depth + 1 <= kWMaxDepth && w.n_tiles <= kWFlagTiles && wire_fold_first();
+  cudaError_t e = cudaSuccess;
+  if (!fold_first) {
+    e = M.nlin == 2 ? launch_w2d_first(x, st) : launch_wire_first(x, st);
+    if (e != cudaSuccess) return cuda_fail(e, "wire_first_kernel");
+  }
   if (gemm_ev) cudaEventRecord(gemm_ev[0], st);
   if (M.nlin == 2) {       // WIRE2D: all hidden layers as ONE chained launch (hand-over through w.flags_fwd, zeroed by w2d_first)
     LGemmArgs g{};
@@ -696,9 +707,17 @@ static int wire_forward_impl(const inr_plan* p, const WireWorkspace& w, const Lo
     g.seg[0].a_tile_bytes = kWTileBytes; g.seg[0].k_stages = kW2 / kStageK; g.seg[0].acc_col = 0; g.n_seg = 1; g.nt = kWNT;
     g.n_tiles = w.n_tiles; g.n_nblocks = 2; g.passes = 3; g.mode = LG_WIRE_FWD;
     g.sigma = M.sigma; g.c_valid = M.c; g.train = train; g.out_f = M.out_f;
-    g.chain_len = M.depth; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_fwd);
+    const int f0 = fold_first ? 1 : 0;
+    g.chain_len = M.depth + f0; g.chain_flags = reinterpret_cast<unsigned int*>(W + w.flags_fwd);
+    if (fold_first) {       // chain[0]: z = x W0^T + b0 from the coordinates, Gabor wavelet, H images of layer 1 + (a) image + coordinate image
+      LGemmLayer& c = g.chain[0];
+      c.bias = params + M.b_off[0]; c.omega = M.omega_first;
+      c.out_hi = W + w.hhi[1]; c.out_lo = W + w.hlo[1]; c.out_ab = W + w.ab[0];
+      g.first_w = params + M.w_off[0]; g.coords = coords; g.row_offset = row_off; g.step_counter = step;
+      g.ximg = W + w.ximg; g.bs = static_cast<int>(bs);
+    }
     for (int l = 1; l <= M.depth; ++l) {
-      LGemmLayer& c = g.chain[l - 1];
+      LGemmLayer& c = g.chain[l - 1 + f0];
       c.a_hi = W + w.hhi[l]; c.a_lo = W + w.hlo[l];
       c.b_hi = wp + M.wf_hi[l]; c.b_lo = wp + M.wf_lo[l];
       c.bias = params + M.b_off[l]; c.omega = M.omega_hidden;

@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   // WIRE_FWD / WIRE_DGRAD (top items): final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
   __shared__ float4 s_lw[(MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) ? kWP : 1];
   const bool has_top = MODE == LG_WIRE_DGRAD && a.top_w != nullptr;      // chain[0] = backward of the final linear, no GEMM
+  __shared__ float s_w0[MODE == LG_WIRE_FWD ? kWP * 3 : 1];               // WIRE_FWD with the first layer folded in: W0 [c][3]
+  const bool has_first = MODE == LG_WIRE_FWD && a.first_w != nullptr;    // chain[0] = real first layer, no GEMM
+  const bool has_nogemm = has_top || has_first;                          // items of chain[0] use no operands and issue no MMAs
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
@@ -140,8 +143,17 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     for (int i = tid; i < n_layers * kWP; i += kLgThreads) {
       const int j = i % kWP;
       const float* bias = a.chain[i / kWP].bias;
-      s_ba[i] = j < a.c_valid ? bias[2 * j] : 0.f;
-      s_bb[i] = j < a.c_valid ? bias[2 * j + 1] : 0.f;
+      if (has_first && i < kWP) {      // real first layer: real bias
+        s_ba[i] = j < a.c_valid ? bias[j] : 0.f;
+        s_bb[i] = 0.f;
+      } else {
+        s_ba[i] = j < a.c_valid ? bias[2 * j] : 0.f;
+        s_bb[i] = j < a.c_valid ? bias[2 * j + 1] : 0.f;
+      }
+    }
+    if (has_first) {
+      for (int i = tid; i < kWP * 3; i += kLgThreads) s_w0[i] = (i / 3) < a.c_valid ? a.first_w[i] : 0.f;
+      if (blockIdx.x == 0 && tid == 0 && a.step_counter) *a.step_counter += 1;
     }
     const float* last_w = a.chain[n_layers - 1].last_w;
     for (int j = tid; j < kWP; j += kLgThreads) {
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
                                 static_cast<size_t>(((lane & 1) ? kWP / 8 : 0) + (kWFeatPerBlock / 8) * nb) * 2048;
           if (!(lane == 3 && Lq.real_first)) bulk_prefetch_l2(base, (kWFeatPerBlock / 8) * 2048);
         }
-        if (has_top && layer == 0) continue;      // top items have no operands: nothing to stream, no ring slots used
+        if (has_nogemm && layer == 0) continue;   // top / first-layer items have no operands: nothing to stream, no ring slots used
         if (BRES && layer * a.n_nblocks + nb != cur_b) {
           // new weight block: wait until the MMAs that read the old one are done (commit of the last item that used it), then
           // fetch this CTA's half -- lanes 0-3 a quarter of the hi image each, lanes 4-7 of the lo image
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         uint32_t slot = 0, ph = 0, bph = 0;
         int cur_b = -1;
         for (int item = cta0; item < n_items; item += n_walk) {
-          if (has_top && item < per_layer) continue;
+          if (has_nogemm && item < per_layer) continue;
           if (BRES) {
             const int layer = item / per_layer, nb = (item - layer * per_layer) % a.n_nblocks;
             if (layer * a.n_nblocks + nb != cur_b) {        // my half of the new weight block has landed: tell the leader
@@ -321,8 +333,8 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         if (tr) tq = clock64();
         mbar_wait(&acc_empty[ab], (use & 1) ^ 1);
         if (tr) c_acc += clock64() - tq;
-        if (has_top && item < per_layer) {
-          // top item: no MMAs; the commit (nothing outstanding for this accumulator) keeps the accumulator barriers of both
+        if (has_nogemm && item < per_layer) {
+          // top / first-layer item: no MMAs; the commit (nothing outstanding for this accumulator) keeps the accumulator barriers of both
           // CTAs in step with the epilogue warps
           tc_fence_after();
           __syncwarp();
@@ -587,6 +599,28 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         tc_fence_after();
         if (tid == 128) LG_TRACE(3 + 3 * n_done);
         float o0 = 0.f, o1 = 0.f;                           // this thread's share of the final linear (last hidden layer only)
+        const bool first = MODE == LG_WIRE_FWD && has_first && layer == 0;
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;                 // first-layer items: this row's coordinates
+        if (first) {
+          const int grow = tile * kTileM + row;
+          if (grow < a.bs) {
+            const float* c = a.coords + (static_cast<size_t>(a.row_offset ? *a.row_offset : 0) + grow) * 3;
+            x0 = c[0]; x1 = c[1]; x2 = c[2];
+          }
+          if (a.train && nb == 0 && sub == 0) {             // coordinate image for the first layer's wgrad
+            const float xs[3] = {x0, x1, x2};
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float h = __half2float(__float2half_rn(xs[c]));
+              v[c] = h; v[4 + c] = xs[c] - h;
+            }
+            v[3] = grow < a.bs ? 1.f : 0.f; v[7] = 0.f;
+            uint8_t* xi = a.ximg + static_cast<size_t>(tile) * kDzLastBytes;
+            st_global_v4(xi + row * 16, pack8(v));
+            st_global_v4(xi + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int c0 = 24 * sub + 8 * i;                 // feature inside the N-block
@@ -595,17 +629,27 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;       // imaginary-part k-group
           float va[8], vb[8];
           if (MODE == LG_WIRE_FWD) {
-            tmem_ld8(acc + c0, va);
-            tmem_ld8(acc + kWFeatPerBlock + c0, vb);
-            tmem_ld_wait();
+            if (first) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {                 // z = x W0^T + b0 (real; the bias sits in s_ba of chain layer 0)
+                const int f = f0 + e;
+                va[e] = fmaf(x0, s_w0[3 * f], fmaf(x1, s_w0[3 * f + 1], fmaf(x2, s_w0[3 * f + 2], s_ba[f])));
+                vb[e] = 0.f;
+              }
+            } else {
+              tmem_ld8(acc + c0, va);
+              tmem_ld8(acc + kWFeatPerBlock + c0, vb);
+              tmem_ld_wait();
+            }
             float yr[8], yi[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float za = va[e] + s_ba[layer * kWP + f0 + e], zb = vb[e] + s_bb[layer * kWP + f0 + e];
+              const float za = first ? va[e] : va[e] + s_ba[layer * kWP + f0 + e], zb = first ? 0.f : vb[e] + s_bb[layer * kWP + f0 + e];
               va[e] = za; vb[e] = zb;
               const bool live = (f0 + e) < a.c_valid;
               if (a.dbg & 64) { yr[e] = live ? za * zb : 0.f; yi[e] = live ? za + zb : 0.f; continue; }   // timing experiment: no MUFU
-              const float mag = __expf(-w * zb - s2 * (za * za + zb * zb));
+              // (first-layer items: the expression wire_first_kernel evaluates, so that both ways give the same bits)
+              const float mag = first ? __expf(-s2 * za * za) : __expf(-w * zb - s2 * (za * za + zb * zb));
               const float ang = w * za;
               yr[e] = live ? mag * fast_cos(ang) : 0.f;
               yi[e] = live ? mag * fast_sin(ang) : 0.f;
@@ -636,7 +680,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             }
             if (a.train) {
               st_global_v4(Ly.out_ab + off_r, pack8(va));
-              st_global_v4(Ly.out_ab + off_i, pack8(vb));
+              if (!first) st_global_v4(Ly.out_ab + off_i, pack8(vb));      // the real first layer has no b part (dgrad: real_first)
             }
           } else {
             const uint4 yr4 = pre[i][0], yi4 = pre[i][1], a4 = pre[i][2], b4 = pre[i][3];

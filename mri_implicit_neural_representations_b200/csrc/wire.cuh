@@ -24,6 +24,7 @@ constexpr int kWTileBytes = kTileM * kW2 * 2;         // 98304: one 128-row imag
 constexpr int kWStageBBytes = kWNT * kStageK * 2;     // 12288: B stage (192 rows x 32 K)
 constexpr int kWStageABytes = kTileM * kStageK * 2;   // 8192:  A stage (128 rows x 32 K)
 constexpr int kWMaxDepth = 8;
+constexpr int kWFlagTiles = 4096;        // forward hand-over counters live at a fixed workspace offset for up to this many row tiles
 
 // WIRE2D (reference src/models/wire2d.py): every layer has TWO linears (`linear`, `scale_orth`); the hidden width is not
 // reduced.  Complex features are padded to P2 (multiple of 64, <= 256); pre-activation / gradient images hold 4 P2 real
@@ -121,6 +122,15 @@ struct LGemmArgs {
   const float* top_g;       // per-row loss-gradient pieces [rows][4] fp32 (gA0, gA1, gB0, gB1) of wire_last_kernel
   const float* top_dout;    // external dL/dout [bs][out_f] (autograd face) or null
   uint8_t* top_dzlast;      // dz_last image [tile][2][128 rows][8] fp16
+  // WIRE_FWD chain with the real first layer folded in (what wire_first_kernel does as a launch of its own): first_w != null
+  // makes chain[0] the first layer 3 -> C (reference networks.py:185-204 with is_first) -- items without a GEMM whose
+  // epilogues evaluate z = x W0^T + b0 from the coordinates and write the same images as every other layer (H_hi / H_lo of
+  // layer 1, the (a) image, and the coordinate image the first layer's wgrad reads).  Uses bs above; chain[0].bias is the REAL bias.
+  const float* first_w;     // first-layer weight [c][3] fp32
+  const float* coords;      // [rows][3] fp32, indexed from *row_offset when that is given
+  const int* row_offset;
+  int* step_counter;        // incremented once per launch (by one thread) or null
+  uint8_t* ximg;            // coordinate image [tile][2][128 rows][8] fp16: [x_hi(3), 1, x_lo(3), 0 | 0 x 8]
   int dbg;                  // debug (INR_LGEMM_DBG), timing experiments only, results are wrong: bit 0 skip MMAs, bit 1 skip operand copies,
                             // bit 2 skip the proxy fence and bit 3 the hand-over wait of chained layers
   unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)
@@ -151,7 +161,8 @@ struct WireModel {
 struct WireWorkspace {
   uint64_t hhi[kWMaxDepth + 2], hlo[kWMaxDepth + 2], ab[kWMaxDepth + 1], dz[kWMaxDepth + 1];
   uint64_t dzlast, ximg, outacc, g, part, scal, gpart, total;
-  uint64_t flags_fwd, flags_bwd;      // uint32 [kWMaxDepth][n_tiles] each: layer-chain hand-over counters
+  uint64_t flags_fwd, flags_bwd;      // uint32 [kWMaxDepth][n_tiles] each: layer-chain hand-over counters (flags_fwd at a FIXED
+                                      // offset with room for kWFlagTiles tiles, whatever the batch: zeroed after use)
   int n_tiles, n_split;
 };
 

@@ -172,6 +172,10 @@ __global__ void __launch_bounds__(512) wire_last_kernel(const __grid_constant__ 
   // hand-over counters of the chained dgrad GEMMs start at zero (the chain may follow this kernel directly: the backward of
   // the final linear rides in it, lgemm.cu "top" items)
   if (a.train && threadIdx.x < kWMaxDepth) reinterpret_cast<unsigned int*>(a.ws + a.w.flags_bwd)[threadIdx.x * a.w.n_tiles + tile] = 0u;
+  // ... and the forward chain's own counters go back to zero for the next launch, which may start a step (first layer folded
+  // in) and then has no kernel before it that could do this
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kWMaxDepth)
+    reinterpret_cast<unsigned int*>(a.ws + a.w.flags_fwd)[(threadIdx.x - 32) * a.w.n_tiles + tile] = 0u;
   // Dependents (the backward entry kernel) are released only now: whatever they read ahead of their own wait -- the saved
   // activations of the last hidden layer -- is final once this kernel is past the chain.
   griddep_launch_dependents();

@@ -254,3 +254,43 @@ def test_wire_full_size_batch_chained_layers(inr):
     eng.load_tensors(list(sd.values()))
     eng.train_step(loss_kind, cd, yd, bs, mask=md, loss_opts=opts)
     assert abs(float(eng.loss_out) - float(val)) <= 2e-3 * abs(float(val)), (float(eng.loss_out), float(val))
+
+
+@pytest.mark.parametrize("name", ["wire_l2", "wire_hdr"])
+def test_wire_folded_first_and_last_layer_items_equal_the_separate_kernels(inr, name, monkeypatch):
+    """The backward of the final linear rides in the dgrad chain (default) and, opt-in, the real first layer in the forward
+    chain (csrc/lgemm.cu "top" / "first" items).  Both restate wire_blast_kernel / wire_first_kernel operation by operation, so
+    every variant must give the same output, loss and gradients (reference networks.py:185-204, :247-258)."""
+    import os
+    res = {}
+    for first, blast in (("0", "0"), ("0", "1"), ("1", "1"), ("1", "0")):
+        monkeypatch.setenv("INR_WIRE_FOLD_FIRST", first)       # read per launch
+        monkeypatch.setenv("INR_WIRE_FOLD_BLAST", blast)
+        plan, eng, net, loss_kind, opts, sd, coords, gt, mask = _engine(inr, name)
+        bs = coords.shape[0]
+        out = torch.zeros(bs, 2, device="cuda")
+        m = None if mask is None else mask.to(torch.uint8).cuda()
+        for _ in range(2):                                       # second pass: lagged per-layer scales calibrated
+            eng.grad_step(loss_kind, coords.cuda(), gt.cuda(), bs, mask=m, loss_opts=opts, out=out)
+        torch.cuda.synchronize()
+        res[(first, blast)] = (out.clone(), float(eng.loss_out), eng.grads.clone())
+    ref = res[("0", "0")]
+    for k, (o, l, g) in res.items():
+        assert torch.equal(o, ref[0]), (k, float((o - ref[0]).abs().max()))
+        assert l == ref[1], (k, l, ref[1])
+        assert float((g - ref[2]).norm()) <= 1e-6 * float(ref[2].norm()), k
+    # three fused steps with both folds on: same losses as with the separate kernels
+    losses = {}
+    for v in ("0", "1"):
+        monkeypatch.setenv("INR_WIRE_FOLD_FIRST", v)
+        monkeypatch.setenv("INR_WIRE_FOLD_BLAST", v)
+        plan, eng, net, loss_kind, opts, sd, coords, gt, mask = _engine(inr, name)
+        bs = coords.shape[0]
+        m = None if mask is None else mask.to(torch.uint8).cuda()
+        ls = []
+        for _ in range(3):
+            eng.train_step(loss_kind, coords.cuda(), gt.cuda(), bs, mask=m, loss_opts=opts)
+            ls.append(float(eng.loss_out))
+        losses[v] = ls
+    for a, b in zip(losses["0"], losses["1"]):
+        assert abs(a - b) <= 1e-6 * abs(a), losses
