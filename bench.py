@@ -639,7 +639,7 @@ def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=
     # launch of the depth dgrad GEMMs, wgrad, Adam = 7; WIRE2D the same plus its separate scalars kernel = 8
     wide = bool(getattr(eng.plan, "wide", False))
     n_sine = max(wl["net"]["network_depth"] - 1, 1)
-    n_launch = (7 if wl["model"] == "WIRE" else 8) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
+    n_launch = (6 if wl["model"] == "WIRE" else 8) if wire else (4 if not mfn else (36 if wl["model"] != "Fourier" else 23))
     if wide:          # encoding, n_sine layer GEMMs, head + loss, scalars, backward entry, n_sine - 1 dgrad GEMMs, wgrad, Adam
         n_launch = 1 + n_sine + 1 + 1 + 1 + (n_sine - 1) + 1 + 1
     # roofline kernel.  WIRE: the chained forward GEMM launch (all hidden layers in one persistent launch), timed by the
@@ -733,7 +733,8 @@ def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=
                    "inputs": f"resident coords+targets {n_rows * 20 / 2**20:.0f} MiB > 126 MB L2, walked in grid order (cold each step)",
                    "step": (f"{n_launch} kernels: first layer, {wl['net']['network_depth']} layer GEMMs (3-pass split fp16 + complex Gabor epilogue"
                             "; one chained persistent launch, tiles handed from layer to layer), "
-                            f"final layer + loss{' + step scalars (last CTA)' if wl['model'] == 'WIRE' else ', scalars'}, final-layer backward, "
+                            f"final layer + loss{' + step scalars (last CTA)' if wl['model'] == 'WIRE' else ', scalars'}, "
+                            f"{'final-layer backward as the first items of the dgrad chain + ' if wl['model'] == 'WIRE' else 'final-layer backward, '}"
                             f"{wl['net']['network_depth']} dgrad layer GEMMs (one chained launch), split-K wgrad, "
                             "complex Adam + repack") if wire else
                            (f"{n_launch} kernels: encoding, |mu|^2, 9 x (envelope GEMM + stage GEMM), head + loss, TV, scalars, top stage, "

@@ -319,6 +319,11 @@ __device__ __forceinline__ float fast_sin(float x) {
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float fast_cos(float x) {
   float r;
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -77,19 +77,19 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // dgrad.  b_full / b_empty hand the resident block between producer and MMA warp exactly like a ring slot.
 // BRES = 2 (3-pass forward): only the hi image is resident, the lo image keeps streaming with the A tiles -- 270 KB per item, but
 // 139 KB of ring instead of 65 KB (the ring depth is what covers the L2 round trip of the A tiles).
-template <int PASSES, int MODE, int KSTEPS, int PAIR, int BRES = 0>
+template <int PASSES, int MODE, int KSTEPS, int PAIR, int BRES = 0, int FIRST = 0>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2], b_full, b_empty;
   __shared__ uint32_t tmem_base_s;
   constexpr bool kChain = MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD || MODE == LG_W2D_FWD || MODE == LG_W2D_DGRAD;
   constexpr int kBiasFloats = MODE == LG_WIRE_FWD ? kWMaxDepth * kWP : 512;
-  __shared__ float s_ba[kBiasFloats], s_bb[kBiasFloats];   // WIRE_FWD: bias re / im per chain layer;  MFN: b_i / phi_i (width <= 512)
+  __shared__ __align__(16) float s_ba[kBiasFloats], s_bb[kBiasFloats];   // WIRE_FWD: bias re / im per chain layer;  MFN: b_i / phi_i (width <= 512)
   // WIRE_FWD / WIRE_DGRAD (top items): final-layer weights (Wr[0], Wi[0], Wr[1], Wi[1]) per feature
   __shared__ float4 s_lw[(MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) ? kWP : 1];
   const bool has_top = MODE == LG_WIRE_DGRAD && a.top_w != nullptr;      // chain[0] = backward of the final linear, no GEMM
-  __shared__ float s_w0[MODE == LG_WIRE_FWD ? kWP * 3 : 1];               // WIRE_FWD with the first layer folded in: W0 [c][3]
-  const bool has_first = MODE == LG_WIRE_FWD && a.first_w != nullptr;    // chain[0] = real first layer, no GEMM
+  __shared__ float s_w0[(FIRST && MODE == LG_WIRE_FWD) ? kWP * 3 : 1];    // WIRE_FWD with the first layer folded in: W0 [c][3]
+  const bool has_first = FIRST && MODE == LG_WIRE_FWD && a.first_w != nullptr;   // chain[0] = real first layer, no GEMM
   const bool has_nogemm = has_top || has_first;                          // items of chain[0] use no operands and issue no MMAs
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -559,18 +559,31 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           st_global_v4(Ly.out_dz + z0 + 2 * zs, pack8(dc)); st_global_v4(Ly.out_dz + z0 + 3 * zs, pack8(dd));
         }
       } else if (MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD) {
-        const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16;
+        // The epilogue is bound by instruction issue (ncu: issue slots busy 57 % of the forward chain's cycles, ~1800 warp
+        // instructions per item and warp before this was trimmed), so the per-feature code is kept minimal: image pointers and
+        // constants hoisted to the item, biases by 16-byte shared loads, exp as one ex2 with log2(e) folded into the
+        // constants, the live-feature mask only in the one group that straddles c_valid.
+        // this thread's three k-groups: real part at group 12 nb + 3 sub + i, imaginary part 24 groups further
+        const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16 + static_cast<size_t>(12 * nb + 3 * sub) * 2048;
+        constexpr size_t kImOff = static_cast<size_t>(kWP / 8) * 2048;
+        const int fb = kWFeatPerBlock * nb + 24 * sub;      // first complex feature of this thread (multiple of 8)
         // dgrad: the saved activations do not depend on the accumulator -- fetch all of them before waiting for the MMAs
         uint4 pre[3][4];
+        const bool real_first = MODE == LG_WIRE_DGRAD && Ly.real_first != 0;
         if (MODE == LG_WIRE_DGRAD) {
+          const uint8_t* const py = Ly.in_y + img;
+          const uint8_t* const pab = Ly.in_ab + img;
+#ifdef INR_LGEMM_EXPERIMENTS
+          if (a.dbg & 256) {      // timing experiment: no saved-activation loads (results are wrong)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pre[i][0] = pre[i][1] = pre[i][2] = pre[i][3] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+          } else
+#endif
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            const int f0 = kWFeatPerBlock * nb + 24 * sub + 8 * i;
-            const size_t off_r = img + static_cast<size_t>(f0 >> 3) * 2048;
-            const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;
-            pre[i][0] = ld_global_nc_v4(Ly.in_y + off_r); pre[i][1] = ld_global_nc_v4(Ly.in_y + off_i);
-            pre[i][2] = ld_global_nc_v4(Ly.in_ab + off_r);
-            pre[i][3] = Ly.real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(Ly.in_ab + off_i);
+            pre[i][0] = ld_global_nc_v4(py + i * 2048); pre[i][1] = ld_global_nc_v4(py + kImOff + i * 2048);
+            pre[i][2] = ld_global_nc_v4(pab + i * 2048);
+            pre[i][3] = real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4(pab + kImOff + i * 2048);
           }
         }
         const bool top = MODE == LG_WIRE_DGRAD && has_top && layer == 0;
@@ -599,9 +612,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         tc_fence_after();
         if (tid == 128) LG_TRACE(3 + 3 * n_done);
         float o0 = 0.f, o1 = 0.f;                           // this thread's share of the final linear (last hidden layer only)
-        const bool first = MODE == LG_WIRE_FWD && has_first && layer == 0;
+        const bool first = FIRST && MODE == LG_WIRE_FWD && has_first && layer == 0;
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;                 // first-layer items: this row's coordinates
-        if (first) {
+        if (FIRST && first) {
           const int grow = tile * kTileM + row;
           if (grow < a.bs) {
             const float* c = a.coords + (static_cast<size_t>(a.row_offset ? *a.row_offset : 0) + grow) * 3;
@@ -621,43 +634,61 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             st_global_v4(xi + 2048 + row * 16, make_uint4(0u, 0u, 0u, 0u));
           }
         }
+        if (MODE == LG_WIRE_FWD) {
+          uint8_t* const p_hi = Ly.out_hi + img;
+          uint8_t* const p_lo = Ly.out_lo ? Ly.out_lo + img : nullptr;      // null for the last hidden layer: nothing reads its lo
+          uint8_t* const p_ab = a.train ? Ly.out_ab + img : nullptr;        // image (the final linear rides along below)
+          const bool ride = Ly.out_part != nullptr;
+          constexpr float kLog2e = 1.4426950408889634f;
+          const float ncb = -w * kLog2e, ncs = -s2 * kLog2e;                // exp(-w zb - s^2 |z|^2) = 2^(ncb zb + ncs |z|^2)
+          const float* const bias_a = s_ba + layer * kWP + fb;
+          const float* const bias_b = s_bb + layer * kWP + fb;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int c0 = 24 * sub + 8 * i;                 // feature inside the N-block
-          const int f0 = kWFeatPerBlock * nb + c0;         // complex feature index (multiple of 8)
-          const size_t off_r = img + static_cast<size_t>(f0 >> 3) * 2048;               // real-part k-group
-          const size_t off_i = img + static_cast<size_t>((kWP + f0) >> 3) * 2048;       // imaginary-part k-group
-          float va[8], vb[8];
-          if (MODE == LG_WIRE_FWD) {
-            if (first) {
+          for (int i = 0; i < 3; ++i) {
+            const int c0 = 24 * sub + 8 * i;               // feature inside the N-block
+            float va[8], vb[8], yr[8], yi[8];
+            const int n_live = a.c_valid - (fb + 8 * i);    // < 8 only in the group that straddles the real width (and beyond it)
+            if (FIRST && first) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {                 // z = x W0^T + b0 (real; the bias sits in s_ba of chain layer 0)
-                const int f = f0 + e;
-                va[e] = fmaf(x0, s_w0[3 * f], fmaf(x1, s_w0[3 * f + 1], fmaf(x2, s_w0[3 * f + 2], s_ba[f])));
-                vb[e] = 0.f;
+                const int f = fb + 8 * i + e;
+                const float za = fmaf(x0, s_w0[3 * f], fmaf(x1, s_w0[3 * f + 1], fmaf(x2, s_w0[3 * f + 2], s_ba[f])));
+                va[e] = za; vb[e] = 0.f;
+                // the expressions wire_first_kernel evaluates, so that both ways give the same bits
+                const float mag = __expf(-s2 * za * za);
+                yr[e] = mag * fast_cos(w * za);
+                yi[e] = mag * fast_sin(w * za);
               }
             } else {
               tmem_ld8(acc + c0, va);
               tmem_ld8(acc + kWFeatPerBlock + c0, vb);
+              const float4 a0 = *reinterpret_cast<const float4*>(bias_a + 8 * i), a1 = *reinterpret_cast<const float4*>(bias_a + 8 * i + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_b + 8 * i), b1 = *reinterpret_cast<const float4*>(bias_b + 8 * i + 4);
+              const float ba[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               tmem_ld_wait();
-            }
-            float yr[8], yi[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float za = first ? va[e] : va[e] + s_ba[layer * kWP + f0 + e], zb = first ? 0.f : vb[e] + s_bb[layer * kWP + f0 + e];
-              va[e] = za; vb[e] = zb;
-              const bool live = (f0 + e) < a.c_valid;
-              if (a.dbg & 64) { yr[e] = live ? za * zb : 0.f; yi[e] = live ? za + zb : 0.f; continue; }   // timing experiment: no MUFU
-              // (first-layer items: the expression wire_first_kernel evaluates, so that both ways give the same bits)
-              const float mag = first ? __expf(-s2 * za * za) : __expf(-w * zb - s2 * (za * za + zb * zb));
-              const float ang = w * za;
-              yr[e] = live ? mag * fast_cos(ang) : 0.f;
-              yi[e] = live ? mag * fast_sin(ang) : 0.f;
-            }
-            if (MODE == LG_WIRE_FWD && Ly.out_part) {       // features in ascending order: fixed summation order
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float4 lw = s_lw[f0 + e];            // same address in every lane: broadcast
+                const float za = va[e] + ba[e], zb = vb[e] + bb[e];
+                va[e] = za; vb[e] = zb;
+#ifdef INR_LGEMM_EXPERIMENTS
+                if (a.dbg & 64) { yr[e] = za * zb; yi[e] = za + zb; continue; }   // timing experiment: no MUFU
+#endif
+                const float mag = fast_ex2(fmaf(ncb, zb, ncs * fmaf(za, za, zb * zb)));
+                const float ang = w * za;
+                yr[e] = mag * fast_cos(ang);
+                yi[e] = mag * fast_sin(ang);
+              }
+            }
+            if (n_live < 8) {                               // padded features stay exactly zero in every image
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (e >= n_live) { yr[e] = 0.f; yi[e] = 0.f; }
+            }
+            if (ride) {                                     // features in ascending order: fixed summation order
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 lw = s_lw[fb + 8 * i + e];    // same address in every lane: broadcast
                 o0 = fmaf(yr[e], lw.x, fmaf(-yi[e], lw.y, o0));
                 o1 = fmaf(yr[e], lw.z, fmaf(-yi[e], lw.w, o1));
               }
@@ -667,27 +698,37 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             split_h2(yr[4], yr[5], rh.z, rl.z); split_h2(yr[6], yr[7], rh.w, rl.w);
             split_h2(yi[0], yi[1], ih.x, il.x); split_h2(yi[2], yi[3], ih.y, il.y);
             split_h2(yi[4], yi[5], ih.z, il.z); split_h2(yi[6], yi[7], ih.w, il.w);
+#ifdef INR_LGEMM_EXPERIMENTS
             if (a.dbg & 32) {      // timing experiment: one store instead of six
               rh.x ^= rl.x ^ ih.x ^ il.x; rh.y ^= rl.y ^ ih.y ^ il.y; rh.z ^= rl.z ^ ih.z ^ il.z; rh.w ^= rl.w ^ ih.w ^ il.w;
               const uint4 pa = pack8(va), pb = pack8(vb);
               rh.x ^= pa.x ^ pb.x; rh.y ^= pa.y ^ pb.y; rh.z ^= pa.z ^ pb.z; rh.w ^= pa.w ^ pb.w;
-              st_global_v4(Ly.out_hi + off_r, rh);
+              st_global_v4(p_hi + i * 2048, rh);
               continue;
             }
-            st_global_v4(Ly.out_hi + off_r, rh); st_global_v4(Ly.out_hi + off_i, ih);
-            if (Ly.out_lo) {       // null for the last hidden layer: nothing reads its lo image (the final linear rode along above)
-              st_global_v4(Ly.out_lo + off_r, rl); st_global_v4(Ly.out_lo + off_i, il);
+#endif
+            st_global_v4(p_hi + i * 2048, rh); st_global_v4(p_hi + kImOff + i * 2048, ih);
+            if (p_lo) { st_global_v4(p_lo + i * 2048, rl); st_global_v4(p_lo + kImOff + i * 2048, il); }
+            if (p_ab) {
+              st_global_v4(p_ab + i * 2048, pack8(va));
+              if (!(FIRST && first)) st_global_v4(p_ab + kImOff + i * 2048, pack8(vb));   // the real first layer has no b part (dgrad: real_first)
             }
-            if (a.train) {
-              st_global_v4(Ly.out_ab + off_r, pack8(va));
-              if (!first) st_global_v4(Ly.out_ab + off_i, pack8(vb));      // the real first layer has no b part (dgrad: real_first)
-            }
-          } else {
-            const uint4 yr4 = pre[i][0], yi4 = pre[i][1], a4 = pre[i][2], b4 = pre[i][3];
+          }
+          if (ride)
+            reinterpret_cast<float4*>(Ly.out_part)[(static_cast<size_t>(tile) * kWOutParts + nb * 4 + sub) * kTileM + row] =
+                make_float4(o0, o1, 0.f, 0.f);
+        } else {
+          uint8_t* const p_dz = Ly.out_dz + img;
+          // da = ratio (-2 s^2 za P - w Q),  db = ratio (-(w + 2 s^2 zb) P)  with P = Re(conj(g) y), Q = Im(conj(g) y)
+          const float c1 = -2.f * s2 * ratio, c2 = -w * ratio;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int c0 = 24 * sub + 8 * i;
+            float va[8], vb[8];
             if (top) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {                 // out = Re(h W^T + b):  dL/d Re(h_j) = dz . Wr_j,  dL/d Im(h_j) = -dz . Wi_j
-                const float4 lw = s_lw[f0 + e];
+                const float4 lw = s_lw[fb + 8 * i + e];
                 va[e] = fmaf(dzo1, lw.z, fmaf(dzo0, lw.x, 0.f));
                 vb[e] = fmaf(-dzo1, lw.w, fmaf(-dzo0, lw.y, 0.f));
               }
@@ -697,22 +738,24 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               tmem_ld_wait();
             }
             float yr[8], yi[8], za[8], zb[8], da[8], db[8];
-            unpack8(yr4, yr); unpack8(yi4, yi); unpack8(a4, za); unpack8(b4, zb);
+            unpack8(pre[i][0], yr); unpack8(pre[i][1], yi); unpack8(pre[i][2], za); unpack8(pre[i][3], zb);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float P = va[e] * yr[e] + vb[e] * yi[e];
-              const float Q = va[e] * yi[e] - vb[e] * yr[e];
-              da[e] = ratio * (-2.f * s2 * za[e] * P - w * Q);
-              db[e] = Ly.real_first ? 0.f : ratio * (-(w + 2.f * s2 * zb[e]) * P);
-              amax = fmaxf(amax, fmaxf(fabsf(da[e]), fabsf(db[e])));
+              const float P = fmaf(va[e], yr[e], vb[e] * yi[e]);
+              const float Q = fmaf(va[e], yi[e], -(vb[e] * yr[e]));
+              da[e] = fmaf(c1 * za[e], P, c2 * Q);
+              db[e] = fmaf(c1, zb[e], c2) * P;
             }
-            st_global_v4(Ly.out_dz + off_r, pack8(da));
-            st_global_v4(Ly.out_dz + off_i, pack8(db));
+            if (real_first) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) db[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fmaxf(fabsf(da[e]), fabsf(db[e])));
+            st_global_v4(p_dz + i * 2048, pack8(da));
+            st_global_v4(p_dz + kImOff + i * 2048, pack8(db));
           }
         }
-        if (MODE == LG_WIRE_FWD && Ly.out_part)
-          reinterpret_cast<float4*>(Ly.out_part)[(static_cast<size_t>(tile) * kWOutParts + nb * 4 + sub) * kTileM + row] =
-              make_float4(o0, o1, 0.f, 0.f);
       } else {
         // ---------------- MFN stages: nt = 128 columns per N-block, this warp owns 32 of them (4 steps of 8)
         const size_t img = static_cast<size_t>(tile) * a.feat_tile_bytes + row * 16;
@@ -863,11 +906,11 @@ static int lgemm_bres_mask() {
   return e ? std::atoi(e) : 1;
 }
 
-template <int P, int M, int K, int PAIR, int BRES = 0>
+template <int P, int M, int K, int PAIR, int BRES = 0, int FIRST = 0>
 static cudaError_t lgemm_launch_one(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   static bool attr = false;
   static int max_clusters = 0;
-  auto kern = lgemm_kernel<P, M, K, PAIR, BRES>;
+  auto kern = lgemm_kernel<P, M, K, PAIR, BRES, FIRST>;
   constexpr int kLgSmem = LgRing<M, PAIR, BRES>::smem;
   if (BRES && (a.n_seg != 1 || !PAIR)) return cudaErrorInvalidValue;
   if (!attr) {
@@ -925,6 +968,10 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
       const char* ekf = std::getenv("INR_LG_KF");          // K = 16 steps per ring slot (read per launch)
       const int kf = ekf ? std::atoi(ekf) : 3;
       if (!lgemm_pair_enabled()) return cudaErrorNotSupported;
+      if (a.first_w) {       // first layer folded in (opt-in): one instantiation, K = 48 slots
+        e = lgemm_launch_one<3, LG_WIRE_FWD, 3, 1, 0, 1>(a, n_sm, stream);
+        break;
+      }
       if (lgemm_bres_mask() & 2) {
         static int kfb = -1;
         if (kfb < 0) { const char* e2 = std::getenv("INR_LG_KFB"); kfb = e2 ? std::atoi(e2) : 2; }
