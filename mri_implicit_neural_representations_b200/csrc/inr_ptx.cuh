@@ -114,6 +114,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 
 // ---------------------------------------------------------------- TMEM
 template <int NCOLS>
@@ -308,6 +309,9 @@ __device__ __forceinline__ uint4 ld_global_nc_v4(const void* p) {
 }
 __device__ __forceinline__ void st_global_v4(void* p, uint4 v) {
   asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(void* p, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization): the next kernel
 // of the stream may be scheduled once every CTA of this grid has executed launch_dependents (or exited); it must execute

@@ -77,10 +77,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // dgrad.  b_full / b_empty hand the resident block between producer and MMA warp exactly like a ring slot.
 // BRES = 2 (3-pass forward): only the hi image is resident, the lo image keeps streaming with the A tiles -- 270 KB per item, but
 // 139 KB of ring instead of 65 KB (the ring depth is what covers the L2 round trip of the A tiles).
-template <int PASSES, int MODE, int KSTEPS, int PAIR, int BRES = 0, int FIRST = 0>
+// BULK = 1 (WIRE forward chain, opt-in: see launch_lgemm for the measurement): the epilogue leaves its H_hi / H_lo images (last hidden layer: H_hi and the (a | b) image)
+// through a 32 KB staging block behind the ring and 8 KB bulk stores issued by the otherwise idle TMEM-allocator warp, instead
+// of 16-byte st.global from 512 threads: global stores from the SM's threads throttle the SM's own bulk loads
+// (profiles/r01_microbench_summary.md: 67.9 -> 47.8 B/cycle of TMA ingest next to st.global, 59.1 next to bulk stores).
+// The thread -> feature mapping becomes c0 = 32 i + 8 sub, so that the four column groups of an iteration form one
+// contiguous 8 KB run per image.
+constexpr int kLgStageBytes = 32768;
+template <int PASSES, int MODE, int KSTEPS, int PAIR, int BRES = 0, int FIRST = 0, int BULK = 0>
 __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_constant__ LGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2], b_full, b_empty;
+  __shared__ uint64_t full[kLgMaxSlots], empty[kLgMaxSlots], acc_full[2], acc_empty[2], stored[2], b_full, b_empty, stg_full, stg_empty;
   __shared__ uint32_t tmem_base_s;
   constexpr bool kChain = MODE == LG_WIRE_FWD || MODE == LG_WIRE_DGRAD || MODE == LG_W2D_FWD || MODE == LG_W2D_DGRAD;
   constexpr int kBiasFloats = MODE == LG_WIRE_FWD ? kWMaxDepth * kWP : 512;
@@ -133,8 +140,9 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
     // across the cluster for the peer CTA's acc_empty.  (Timing-neutral on B200: 76.3 against 76.2 us for the forward chain.)
     const uint32_t n_arr = kLgComputeThreads / 32;
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], n_arr << PAIR); mbar_init(&stored[i], n_arr);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], n_arr << PAIR); mbar_init(&stored[i], n_arr + (BULK ? 1 : 0));
     }
+    mbar_init(&stg_full, n_arr); mbar_init(&stg_empty, 1);
     mbar_fence_init();
   }
   if (warp == 2) { if (PAIR) tmem_alloc_pair<512>(&tmem_base_s); else tmem_alloc<512>(&tmem_base_s); }
@@ -192,6 +200,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   if (tid == 0) LG_TRACE(1);
+  uint8_t* const stage = ring + n_slots * slot_bytes;      // BULK: 32 KB behind the last ring slot (checked at launch)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -404,6 +413,46 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         a.trace[64 + blockIdx.x * 32 + 23] = n_done;
       }
     }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ BULK: store thread (the TMEM allocator warp is idle here)
+    if (BULK && MODE == LG_WIRE_FWD && lane == 0) {
+      uint32_t it = 0, n_done = 0;
+      int pending = -1;                  // accumulator index of the item whose stores are issued but not yet known complete
+      const bool publish = kChain && n_layers > 1;
+      for (int item = cta0; item < n_items; item += n_walk, ++n_done) {
+        const int layer = item / per_layer, rem = item - layer * per_layer;
+        const int tile = PAIR ? 2 * (rem / a.n_nblocks) + static_cast<int>(rank) : rem / a.n_nblocks, nb = rem % a.n_nblocks;
+        const int ab = static_cast<int>(n_done & 1);
+        if (PAIR && tile >= a.n_tiles) {               // phantom tile: nothing staged
+          if (pending >= 0) { bulk_wait0(); if (publish) mbar_arrive(&stored[pending]); pending = -1; }
+          if (publish) mbar_arrive(&stored[ab]);
+          continue;
+        }
+        const LGemmLayer& Ly = a.chain[layer];
+        const size_t base = static_cast<size_t>(tile) * kWTileBytes + static_cast<size_t>(12 * nb) * 2048;
+        constexpr size_t kIm = static_cast<size_t>(kWP / 8) * 2048;
+        uint8_t* const d0 = Ly.out_hi + base;
+        uint8_t* const d1 = Ly.out_lo ? Ly.out_lo + base : ((a.train && Ly.out_ab) ? Ly.out_ab + base : nullptr);
+        for (int i = 0; i < 3; ++i) {
+          mbar_wait(&stg_full, it & 1);
+          bulk_s2g(d0 + i * 8192, stage, 8192);
+          bulk_s2g(d0 + kIm + i * 8192, stage + 8192, 8192);
+          if (d1) { bulk_s2g(d1 + i * 8192, stage + 16384, 8192); bulk_s2g(d1 + kIm + i * 8192, stage + 24576, 8192); }
+          bulk_commit();
+          if (i == 0 && pending >= 0) {                 // every group but the one just committed is complete: the previous item is out
+            bulk_wait1();
+            if (publish) mbar_arrive(&stored[pending]);
+            pending = -1;
+          }
+          bulk_wait_read0();                            // the staging block has been read
+          mbar_arrive(&stg_empty);
+          ++it;
+        }
+        pending = ab;
+      }
+      bulk_wait0();
+      if (pending >= 0 && publish) mbar_arrive(&stored[pending]);
+    }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ publisher (layer chains): hands finished tiles to the next layer
     // The epilogue threads arrive on stored[ab] once their stores of an item are issued (release at CTA scope); this one
@@ -443,7 +492,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       amax = 0.f;
     };
     int cur_layer = -1;
-    uint32_t n_done = 0;
+    uint32_t n_done = 0, stg_it = 0;
     for (int item = cta0; item < n_items; item += n_walk, ++n_done) {
       const int layer = item / per_layer, rem = item - layer * per_layer;
       const int tile = PAIR ? 2 * (rem / a.n_nblocks) + static_cast<int>(rank) : rem / a.n_nblocks, nb = rem % a.n_nblocks;
@@ -564,9 +613,12 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
         // constants hoisted to the item, biases by 16-byte shared loads, exp as one ex2 with log2(e) folded into the
         // constants, the live-feature mask only in the one group that straddles c_valid.
         // this thread's three k-groups: real part at group 12 nb + 3 sub + i, imaginary part 24 groups further
-        const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16 + static_cast<size_t>(12 * nb + 3 * sub) * 2048;
+        // (BULK: k-groups 12 nb + 4 i + sub, features 96 nb + 32 i + 8 sub + e)
+        constexpr int kGi = BULK ? 4 : 1, kGs = BULK ? 1 : 3;           // k-group stride of the iteration index / of sub
+        const size_t img = static_cast<size_t>(tile) * kWTileBytes + row * 16 + static_cast<size_t>(12 * nb + kGs * sub) * 2048;
         constexpr size_t kImOff = static_cast<size_t>(kWP / 8) * 2048;
-        const int fb = kWFeatPerBlock * nb + 24 * sub;      // first complex feature of this thread (multiple of 8)
+        constexpr size_t kIt = static_cast<size_t>(kGi) * 2048;         // image bytes between this thread's iterations
+        const int fb = kWFeatPerBlock * nb + 8 * kGs * sub;  // first complex feature of this thread (multiple of 8)
         // dgrad: the saved activations do not depend on the accumulator -- fetch all of them before waiting for the MMAs
         uint4 pre[3][4];
         const bool real_first = MODE == LG_WIRE_DGRAD && Ly.real_first != 0;
@@ -638,6 +690,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           uint8_t* const p_hi = Ly.out_hi + img;
           uint8_t* const p_lo = Ly.out_lo ? Ly.out_lo + img : nullptr;      // null for the last hidden layer: nothing reads its lo
           uint8_t* const p_ab = a.train ? Ly.out_ab + img : nullptr;        // image (the final linear rides along below)
+          uint8_t* const stg = stage + sub * 2048 + row * 16;               // BULK: this thread's 16 bytes in each staged 8 KB run
           const bool ride = Ly.out_part != nullptr;
           constexpr float kLog2e = 1.4426950408889634f;
           const float ncb = -w * kLog2e, ncs = -s2 * kLog2e;                // exp(-w zb - s^2 |z|^2) = 2^(ncb zb + ncs |z|^2)
@@ -645,13 +698,13 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           const float* const bias_b = s_bb + layer * kWP + fb;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            const int c0 = 24 * sub + 8 * i;               // feature inside the N-block
+            const int c0 = 8 * kGs * sub + 8 * kGi * i;    // feature inside the N-block
             float va[8], vb[8], yr[8], yi[8];
-            const int n_live = a.c_valid - (fb + 8 * i);    // < 8 only in the group that straddles the real width (and beyond it)
+            const int n_live = a.c_valid - (fb + 8 * kGi * i);   // < 8 only in the group that straddles the real width (and beyond it)
             if (FIRST && first) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {                 // z = x W0^T + b0 (real; the bias sits in s_ba of chain layer 0)
-                const int f = fb + 8 * i + e;
+                const int f = fb + 8 * kGi * i + e;
                 const float za = fmaf(x0, s_w0[3 * f], fmaf(x1, s_w0[3 * f + 1], fmaf(x2, s_w0[3 * f + 2], s_ba[f])));
                 va[e] = za; vb[e] = 0.f;
                 // the expressions wire_first_kernel evaluates, so that both ways give the same bits
@@ -662,8 +715,8 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             } else {
               tmem_ld8(acc + c0, va);
               tmem_ld8(acc + kWFeatPerBlock + c0, vb);
-              const float4 a0 = *reinterpret_cast<const float4*>(bias_a + 8 * i), a1 = *reinterpret_cast<const float4*>(bias_a + 8 * i + 4);
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_b + 8 * i), b1 = *reinterpret_cast<const float4*>(bias_b + 8 * i + 4);
+              const float4 a0 = *reinterpret_cast<const float4*>(bias_a + 8 * kGi * i), a1 = *reinterpret_cast<const float4*>(bias_a + 8 * kGi * i + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_b + 8 * kGi * i), b1 = *reinterpret_cast<const float4*>(bias_b + 8 * kGi * i + 4);
               const float ba[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               tmem_ld_wait();
@@ -688,7 +741,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             if (ride) {                                     // features in ascending order: fixed summation order
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float4 lw = s_lw[fb + 8 * i + e];    // same address in every lane: broadcast
+                const float4 lw = s_lw[fb + 8 * kGi * i + e];    // same address in every lane: broadcast
                 o0 = fmaf(yr[e], lw.x, fmaf(-yi[e], lw.y, o0));
                 o1 = fmaf(yr[e], lw.z, fmaf(-yi[e], lw.w, o1));
               }
@@ -703,15 +756,28 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               rh.x ^= rl.x ^ ih.x ^ il.x; rh.y ^= rl.y ^ ih.y ^ il.y; rh.z ^= rl.z ^ ih.z ^ il.z; rh.w ^= rl.w ^ ih.w ^ il.w;
               const uint4 pa = pack8(va), pb = pack8(vb);
               rh.x ^= pa.x ^ pb.x; rh.y ^= pa.y ^ pb.y; rh.z ^= pa.z ^ pb.z; rh.w ^= pa.w ^ pb.w;
-              st_global_v4(p_hi + i * 2048, rh);
+              st_global_v4(p_hi + i * kIt, rh);
               continue;
             }
 #endif
-            st_global_v4(p_hi + i * 2048, rh); st_global_v4(p_hi + kImOff + i * 2048, ih);
-            if (p_lo) { st_global_v4(p_lo + i * 2048, rl); st_global_v4(p_lo + kImOff + i * 2048, il); }
-            if (p_ab) {
-              st_global_v4(p_ab + i * 2048, pack8(va));
-              if (!(FIRST && first)) st_global_v4(p_ab + kImOff + i * 2048, pack8(vb));   // the real first layer has no b part (dgrad: real_first)
+            if (BULK) {
+              // staged: [H_hi re | H_hi im | H_lo re | H_lo im], or with no lo image (last hidden layer) [.. | a | b]
+              mbar_wait(&stg_empty, (stg_it & 1) ^ 1);
+              ++stg_it;
+              st_shared_v4(stg, rh); st_shared_v4(stg + 8192, ih);
+              if (p_lo) { st_shared_v4(stg + 16384, rl); st_shared_v4(stg + 24576, il); }
+              else if (p_ab) { st_shared_v4(stg + 16384, pack8(va)); st_shared_v4(stg + 24576, pack8(vb)); }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&stg_full);
+              if (p_lo && p_ab) { st_global_v4(p_ab + i * kIt, pack8(va)); st_global_v4(p_ab + kImOff + i * kIt, pack8(vb)); }
+            } else {
+              st_global_v4(p_hi + i * kIt, rh); st_global_v4(p_hi + kImOff + i * kIt, ih);
+              if (p_lo) { st_global_v4(p_lo + i * kIt, rl); st_global_v4(p_lo + kImOff + i * kIt, il); }
+              if (p_ab) {
+                st_global_v4(p_ab + i * kIt, pack8(va));
+                if (!(FIRST && first)) st_global_v4(p_ab + kImOff + i * kIt, pack8(vb));   // the real first layer has no b part (dgrad: real_first)
+              }
             }
           }
           if (ride)
@@ -906,11 +972,14 @@ static int lgemm_bres_mask() {
   return e ? std::atoi(e) : 1;
 }
 
-template <int P, int M, int K, int PAIR, int BRES = 0, int FIRST = 0>
+template <int P, int M, int K, int PAIR, int BRES = 0, int FIRST = 0, int BULK = 0>
 static cudaError_t lgemm_launch_one(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
   static bool attr = false;
   static int max_clusters = 0;
-  auto kern = lgemm_kernel<P, M, K, PAIR, BRES, FIRST>;
+  auto kern = lgemm_kernel<P, M, K, PAIR, BRES, FIRST, BULK>;
+  // BULK: the staging block sits behind the last slot of the WIRE forward ring (K = 48 slots of 43 008 B: four of them leave 32 KB)
+  static_assert(!BULK || (M == LG_WIRE_FWD && P == 3 && K == 3 && PAIR == 1 && BRES == 0 &&
+                          kLgRingBytes - (kLgRingBytes / 43008) * 43008 >= kLgStageBytes), "staging block does not fit");
   constexpr int kLgSmem = LgRing<M, PAIR, BRES>::smem;
   if (BRES && (a.n_seg != 1 || !PAIR)) return cudaErrorInvalidValue;
   if (!attr) {
@@ -971,6 +1040,16 @@ cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
       if (a.first_w) {       // first layer folded in (opt-in): one instantiation, K = 48 slots
         e = lgemm_launch_one<3, LG_WIRE_FWD, 3, 1, 0, 1>(a, n_sm, stream);
         break;
+      }
+      {                      // opt-in (INR_LG_BULK=1, read per launch): epilogue images through shared memory + bulk stores.
+        // Measured on B200, in-process A/B at bs 25 000: 85.2 us against 84.1 us with plain st.global -- the microbenchmark's
+        // gain (stores that no longer throttle the bulk loads) is eaten by twelve more copies per item on a copy engine the
+        // producer already waits on for 46 % of its time.  Not the default.
+        const char* eb = std::getenv("INR_LG_BULK");
+        if (kf == 3 && !(lgemm_bres_mask() & 2) && eb && eb[0] == '1') {
+          e = lgemm_launch_one<3, LG_WIRE_FWD, 3, 1, 0, 0, 1>(a, n_sm, stream);
+          break;
+        }
       }
       if (lgemm_bres_mask() & 2) {
         static int kfb = -1;

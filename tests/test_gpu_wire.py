@@ -294,3 +294,28 @@ def test_wire_folded_first_and_last_layer_items_equal_the_separate_kernels(inr, 
         losses[v] = ls
     for a, b in zip(losses["0"], losses["1"]):
         assert abs(a - b) <= 1e-6 * abs(a), losses
+
+
+@pytest.mark.parametrize("name", ["wire_l2", "wire_hdr"])
+def test_wire_forward_chain_bulk_store_epilogue_equals_direct_stores(inr, name, monkeypatch):
+    """The forward chain's epilogue leaves H_hi / H_lo by 16-byte global stores (default) or, opt-in, through a shared-memory
+    staging block and 8 KB bulk stores issued by a store thread (INR_LG_BULK=1).  Same arithmetic per feature: every saved image must be bit-identical; the
+    output differs only by the grouping of the final linear's eight partial sums."""
+    res = {}
+    for bulk in ("0", "1"):
+        monkeypatch.setenv("INR_LG_BULK", bulk)                 # read per launch
+        plan, eng, net, loss_kind, opts, sd, coords, gt, mask = _engine(inr, name)
+        bs, depth = coords.shape[0], net["network_depth"]
+        out = torch.zeros(bs, 2, device="cuda")
+        m = None if mask is None else mask.to(torch.uint8).cuda()
+        for _ in range(2):
+            eng.grad_step(loss_kind, coords.cuda(), gt.cuda(), bs, mask=m, loss_opts=opts, out=out)
+        torch.cuda.synchronize()
+        imgs = [eng.read_wire_image("h", l, bs).clone() for l in range(1, depth + 2)]
+        res[bulk] = (out.clone(), float(eng.loss_out), eng.grads.clone(), imgs)
+    for a, b in zip(res["0"][3], res["1"][3]):
+        assert torch.equal(a, b)
+    assert float((res["0"][0] - res["1"][0]).abs().max()) <= 1e-6 * float(res["0"][0].abs().max())
+    assert abs(res["0"][1] - res["1"][1]) <= 1e-6 * abs(res["0"][1])
+    # (1e-7 in the output moves a few fp16 roundings of the dZ images)
+    assert float((res["0"][2] - res["1"][2]).norm()) <= 1e-4 * float(res["0"][2].norm())
