@@ -52,6 +52,27 @@ __device__ void wire_pack_hidden(const WireModel& M, uint8_t* wpack, int l, int 
 __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ WireAdamArgs a) {
   __shared__ float s_c[4];
   const WireModel& M = a.m;
+  // Ahead of the wait on wgrad: everything that no kernel of this step writes -- the tensor this thread's parameter belongs
+  // to, the master weight and the Adam moments (last written by the previous step's optimiser, which completed before this
+  // step's first kernel started).  Scalars, step counter and split-K partials are read behind the wait.
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int layer = -1, kind = -1, idx = 0;     // kind: 0 weight, 1 bias, 2 frozen
+  const int L = M.depth + 1;
+  const bool upd = !a.pack_only && a.do_adam;
+  float w = 0.f, m_old = 0.f, v_old = 0.f;
+  if (p < M.n_params) {
+    for (int l = 0; l <= L; ++l) {
+      const int wn = (l == 0) ? M.c * M.in_f : (l == L ? M.out_f * M.c * 2 : M.c * M.c * 2);
+      const int bn = (l == 0) ? M.c : (l == L ? M.out_f * 2 : M.c * 2);
+      if (l < L && (p == M.omega_off[l] || p == M.scale_off[l])) { layer = l; kind = 2; break; }
+      if (p >= M.w_off[l] && p < M.w_off[l] + wn) { layer = l; kind = 0; idx = p - M.w_off[l]; break; }
+      if (p >= M.b_off[l] && p < M.b_off[l] + bn) { layer = l; kind = 1; idx = p - M.b_off[l]; break; }
+    }
+    if (kind == 0 || kind == 1) {
+      w = a.params[p];
+      if (upd) { m_old = a.mom[p]; v_old = a.var[p]; }
+    }
+  }
   griddep_wait();                    // split-K partials of wgrad complete
   if (threadIdx.x == 0) {
     const float* sc = a.scal;
@@ -69,23 +90,8 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
     }
   }
   __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= M.n_params) return;
-  // ---- locate the tensor
-  int layer = -1, kind = -1, idx = 0;     // kind: 0 weight, 1 bias, 2 frozen
-  const int L = M.depth + 1;
-  for (int l = 0; l <= L; ++l) {
-    const int wn = (l == 0) ? M.c * M.in_f : (l == L ? M.out_f * M.c * 2 : M.c * M.c * 2);
-    const int bn = (l == 0) ? M.c : (l == L ? M.out_f * 2 : M.c * 2);
-    if (l < L && (p == M.omega_off[l] || p == M.scale_off[l])) { layer = l; kind = 2; break; }
-    if (p >= M.w_off[l] && p < M.w_off[l] + wn) { layer = l; kind = 0; idx = p - M.w_off[l]; break; }
-    if (p >= M.b_off[l] && p < M.b_off[l] + bn) { layer = l; kind = 1; idx = p - M.b_off[l]; break; }
-  }
   if (kind == 2 || kind < 0) { if (a.grads && !a.pack_only) a.grads[p] = 0.f; return; }
-  // master weight, moments and the layer's gradient scale are requested before the gather so that their latencies overlap it
-  float w = a.params[p];
-  const bool upd = !a.pack_only && a.do_adam;
-  const float m_old = upd ? a.mom[p] : 0.f, v_old = upd ? a.var[p] : 0.f;
   int o = 0, i = 0, comp = 0;
   if (layer >= 1 && layer < L && kind == 0) { const int e = idx >> 1; comp = idx & 1; o = e / M.c; i = e % M.c; }
   if (!a.pack_only) {
