@@ -118,19 +118,26 @@ class ClockSampler:
             self.nv = None
         self.t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def sample(self):
+        """One reading; also called by the timing thread right after the last step has been enqueued, so that even a
+        timed region of a few milliseconds holds a sample taken while the GPU is inside it."""
         nv = self.nv
+        if not nv:
+            return
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake": 0x80}
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
+            self.sample()
             time.sleep(0.005)
 
     def __enter__(self):
@@ -301,6 +308,7 @@ def run_multiscale(args):
         e0.record()
         last = run(args.steps)
         e1.record()
+        clk.sample()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     value = args.steps * bs / (ms * 1e-3)
@@ -610,6 +618,7 @@ def run_workload(args, workload, dist, rank, world, local, device, cpu_baseline=
         e0.record()
         run_steps(args.steps)        # graph replays; one 4-byte memset when the walk wraps around the resident rows
         e1.record()
+        clk.sample()                 # the steps are still running: a reading from inside the timed region
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if dist:
