@@ -47,6 +47,9 @@ extern "C" {
 /* encoders (src/models/networks.py:7-35) */
 #define INR_ENC_NONE 0       /* x is the dense [bs, in] fp32 network input */
 #define INR_ENC_GAUSS 1      /* gamma(x) = [sin(2 pi x B^T), cos(2 pi x B^T)] computed in-kernel from coords */
+#define INR_ENC_LOGF 2       /* per coordinate c: [sin(2 pi x_c B), cos(2 pi x_c B)], B = 2^linspace(0, scale, n), n = embedding_size / 6
+                              * (src/models/networks.py:14-16,24-29), computed in-kernel from coords; encB = B [n] fp32;
+                              * network_input_size = 6 n.  SIREN / FFN only (they then run on the streaming layer GEMMs) */
 /* last-layer activation */
 #define INR_LAST_LINEAR 0
 #define INR_LAST_TANH 1      /* SIREN last_tanh, src/models/networks.py:94-95 */

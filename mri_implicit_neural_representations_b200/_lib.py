@@ -33,7 +33,7 @@ class TensorInfo(C.Structure):
 
 
 MODEL = {"SIREN": 1, "FFN": 2, "WIRE": 3, "Fourier": 4, "MultiscaleFourier": 5, "BoundedFourier": 6, "Gabor": 7, "KGabor": 7, "WIRE2D": 8}
-ENC = {"none": 0, "gauss": 1}
+ENC = {"none": 0, "gauss": 1, "LogF": 2}
 LAST = {"linear": 0, "tanh": 1, "sigmoid": 2, "sin": 3}
 LOSS = {"none": 0, "L2": 1, "L1": 2, "MSLE": 3, "tanh": 4, "LSL": 5, "HDR": 6}
 

@@ -192,7 +192,7 @@ extern "C" int inr_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (d->model != INR_MODEL_SIREN && d->model != INR_MODEL_FFN) return fail(INR_EUNSUPPORTED, "model kind not built yet");
   // the on-chip chain kernels hold one 128 x 256 activation tile per SM; other widths (8 shipped SIREN configs use 512), a
   // single sine layer (network_depth 1 or 2) and the sine output layer run layer by layer on the streaming stage GEMMs
-  if (d->width != kWidth || d->depth < 3 || d->last_act == INR_LAST_SIN) return wide_plan_create(d, out);
+  if (d->width != kWidth || d->depth < 3 || d->last_act == INR_LAST_SIN || d->encoder == INR_ENC_LOGF) return wide_plan_create(d, out);
   if (d->depth < 2 || d->depth - 1 > kMaxLayers - 1) return fail(INR_EINVAL, "network_depth out of range");
   if (d->out_features < 1 || d->out_features > kMaxOut) return fail(INR_EUNSUPPORTED, "network_output_size must be 1..4");
   if (d->encoder == INR_ENC_GAUSS) {
@@ -838,6 +838,7 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
   if (d->depth < 1 || d->depth + 1 > kMfnMaxStages) return fail(INR_EINVAL, "network_depth out of range");
   if (d->out_features < 1 || d->out_features > 2) return fail(INR_EUNSUPPORTED, "network_output_size must be 1 or 2");
   if (d->encoder == INR_ENC_GAUSS && d->in_features != 2 * d->enc_size) return fail(INR_EINVAL, "gauss encoder needs network_input_size == 2*embedding_size");
+  if (d->encoder != INR_ENC_GAUSS && d->encoder != INR_ENC_NONE) return fail(INR_EUNSUPPORTED, "the MFN kernels take the gauss encoder or dense input");
   inr_plan* p = new (std::nothrow) inr_plan();
   if (!p) return fail(INR_EINVAL, "out of host memory");
   p->desc = *d;
@@ -988,15 +989,22 @@ static int mfn_plan_create(const inr_model_desc* d, inr_plan** out) {
 // SIREN / FFN as a chain of plain layers on the MFN stage GEMMs (MfnModel::chain): reference src/models/networks.py:48-124.
 // Sine layers: first (in -> W) + max(depth - 2, 0) hidden (W -> W); then the output layer (W -> out) with its activation.
 static int wide_plan_create(const inr_model_desc* d, inr_plan** out) {
-  const int W = d->width, IN = d->in_features, OF = d->out_features;
+  const int W = d->width, OF = d->out_features;
+  // LogF encoder (reference networks.py:14-16,24-29): n = int(embedding_size / 6) frequencies per coordinate, 6 n input
+  // features; the operand image (and the packed first-layer weights) are zero-padded to the next multiple of 128
+  const bool logf = d->encoder == INR_ENC_LOGF;
+  const int enc_n = logf ? d->enc_size / 6 : 0;
+  const int IN_LD = d->in_features;                          // columns of the first-layer weight in the parameter buffer
+  const int IN = logf ? (IN_LD + 127) / 128 * 128 : IN_LD;   // K of the first-layer GEMM
   const int n_sine = d->depth >= 2 ? d->depth - 1 : 1;      // reference: depth 1 and depth 2 both build [first, last]
   if (W % kMfnNT != 0 || W < kMfnNT || W > 512) return fail(INR_EUNSUPPORTED, "SIREN / FFN kernels need network_width in {128, 256, 384, 512}");
+  if (logf && (enc_n < 1 || IN_LD != 6 * enc_n)) return fail(INR_EINVAL, "LogF encoder needs network_input_size == 6 * int(embedding_size / 6)");
   if (IN % 128 != 0 || IN < 128 || IN > 2048) return fail(INR_EUNSUPPORTED, "this network_width runs on the streaming layer GEMMs: network_input_size must be a multiple of 128");
   if (d->depth < 1 || n_sine > kMfnMaxStages) return fail(INR_EINVAL, "network_depth out of range");
   if (OF < 1 || OF > kMaxOut) return fail(INR_EUNSUPPORTED, "network_output_size must be 1..4");
   if (d->encoder == INR_ENC_GAUSS) {
     if (IN != 2 * d->enc_size) return fail(INR_EINVAL, "gauss encoder needs network_input_size == 2*embedding_size");
-  } else if (d->encoder != INR_ENC_NONE) {
+  } else if (d->encoder != INR_ENC_NONE && !logf) {
     return fail(INR_EUNSUPPORTED, "encoder kind not built yet");
   }
   inr_plan* p = new (std::nothrow) inr_plan();
@@ -1007,8 +1015,8 @@ static int wide_plan_create(const inr_model_desc* d, inr_plan** out) {
   std::memset(&M, 0, sizeof(M));
   const int L = n_sine - 1;
   M.L = L; M.width = W; M.in_f = IN; M.out_f = OF;
-  M.input_kind = d->encoder == INR_ENC_GAUSS ? INPUT_GAUSS : INPUT_DENSE;
-  M.enc_size = d->enc_size;
+  M.input_kind = d->encoder == INR_ENC_GAUSS ? INPUT_GAUSS : (logf ? INPUT_LOGF : INPUT_DENSE);
+  M.enc_size = d->enc_size; M.enc_n = enc_n;
   M.chain = 1; M.act = d->model == INR_MODEL_SIREN ? ACT_SIN : ACT_RELU; M.last_act = d->last_act;
   M.w0 = d->model == INR_MODEL_SIREN ? d->w0 : 1.f;
   for (int i = 0; i < kMfnMaxStages; ++i) { M.stage_head[i] = -1; M.bound_lo[i] = 0.f; M.bound_hi[i] = 3.0e38f; }
@@ -1029,7 +1037,8 @@ static int wide_plan_create(const inr_model_desc* d, inr_plan** out) {
     const uint32_t bytes = static_cast<uint32_t>(W) * cols * 2;
     if (i == 0) {
       M.filt_w[0] = off; M.pk_filt[0] = wo; wo += bytes;
-      add_seg(off, W, IN, 0, false, SC_LAYER_SCALE + 0, 1, 0, M.pk_filt[0], 0); off += W * IN;
+      add_seg(off, W, IN_LD, 0, false, SC_LAYER_SCALE + 0, 1, 0, M.pk_filt[0], 0); off += W * IN_LD;
+      p->segs.back().kpad = IN;      // LogF: 6 n columns packed into K = IN (the padding stays zero: the buffer starts out zero)
       M.filt_b[0] = off; add_seg(off, W, 1, 0, true, SC_LAYER_SCALE + 0, 0, 0, 0, 0); off += W;
     } else {
       M.lin_w[i] = off; M.pk_lin[i] = wo; wo += bytes; M.pk_lin_t[i] = wo; wo += bytes;
@@ -1057,6 +1066,11 @@ static int wide_plan_create(const inr_model_desc* d, inr_plan** out) {
         u.b_tile_stride = btile; u.b_sub = c0 * 32768; u.b_bytes = 32768;
         u.n = 128; u.n_chunks = nch; u.out_off = i == 0 ? M.filt_w[0] : M.lin_w[i]; u.out_ld = K; u.row0 = mc * 128; u.col0 = c0 * 128;
         u.rows_valid = 128; u.cols_valid = 128 * nch; u.bias_off = c0 == 0 ? (i == 0 ? M.filt_b[0] : M.lin_b[i]) : -1;
+        if (i == 0 && IN_LD != IN) {       // LogF: the parameter tensor has 6 n columns, the padded ones are dropped on store
+          u.out_ld = IN_LD;
+          const int left = IN_LD - c0 * 128;
+          u.cols_valid = left < 128 * nch ? (left > 0 ? left : 0) : 128 * nch;
+        }
         p->units.push_back(u); p->unit_layer.push_back(i == 0 ? 200 : 700 + i);
       }
   }
@@ -1282,8 +1296,8 @@ extern "C" int inr_forward(const inr_plan* p, const float* params, const void* w
   if (train && !workspace) return fail(INR_EINVAL, "training forward needs a workspace");
   if (p->is_mfn) {
     if (!workspace) return fail(INR_EINVAL, "MFN forward streams its activations through the workspace");
-    const bool mg = p->mm.input_kind == INPUT_GAUSS;
-    if (mg && !encB) return fail(INR_EINVAL, "gauss encoder needs encB");
+    const bool mg = p->mm.input_kind != INPUT_DENSE;       // gauss / LogF: `input` = coords, encoded in-kernel
+    if (mg && !encB) return fail(INR_EINVAL, "gauss / LogF encoder needs encB");
     const MfnWorkspace mw = mfn_workspace(p, bs);
     return mfn_forward_impl(p, mw, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, mg ? input : nullptr, mg ? nullptr : input, encB,
                             nullptr, nullptr, nullptr, bs, workspace, out, train ? 1 : 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
@@ -1306,7 +1320,7 @@ extern "C" int inr_forward_dist(const inr_plan* p, const float* params, const vo
                                 const float* dist, int64_t bs, void* workspace, float* out, int32_t train, void* stream) {
   if (!p || !params || !wpack || !input || !out || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (!p->is_mfn) return fail(INR_EINVAL, "inr_forward_dist is for the multiscale MFN models");
-  const bool mg = p->mm.input_kind == INPUT_GAUSS;
+  const bool mg = p->mm.input_kind != INPUT_DENSE;
   if (mg && !encB) return fail(INR_EINVAL, "gauss encoder needs encB");
   const MfnWorkspace mw = mfn_workspace(p, bs);
   return mfn_forward_impl(p, mw, LossDesc{LOSS_NONE, 0.f, 0.f, 0.f}, params, wpack, mg ? input : nullptr, mg ? nullptr : input, encB,
@@ -1454,8 +1468,8 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
   if (!p || !loss || !params || !wpack || !gt || !workspace || bs <= 0) return fail(INR_EINVAL, "bad argument");
   if (!no_adam && (!m || !v || !hyper_dev || !step_dev)) return fail(INR_EINVAL, "bad argument");
   if (p->is_mfn) {
-    const bool mg = p->mm.input_kind == INPUT_GAUSS;
-    if (mg && (!coords || !encB)) return fail(INR_EINVAL, "gauss encoder needs coords and encB");
+    const bool mg = p->mm.input_kind != INPUT_DENSE;
+    if (mg && (!coords || !encB)) return fail(INR_EINVAL, "gauss / LogF encoder needs coords and encB");
     if (!mg && !input_x) return fail(INR_EINVAL, "dense input needs input_x");
     const bool multi = p->mm.n_out != 1;
     if (multi) {      // fused multi-scale step (reference src/train_kspace_multiscale.py:173-190)

@@ -27,7 +27,7 @@ constexpr int kScalars = 64;          // step scalars + per-layer gradient scale
 
 enum Act { ACT_SIN = 0, ACT_RELU = 1 };
 enum LastAct { LAST_LINEAR = 0, LAST_TANH = 1, LAST_SIGMOID = 2, LAST_SIN = 3 };
-enum InputKind { INPUT_GAUSS = 0, INPUT_DENSE = 1 };
+enum InputKind { INPUT_GAUSS = 0, INPUT_DENSE = 1, INPUT_LOGF = 2 };
 enum LossKind { LOSS_NONE = 0, LOSS_L2 = 1, LOSS_L1 = 2, LOSS_MSLE = 3, LOSS_TANH = 4, LOSS_LSL = 5, LOSS_HDR = 6 };
 // scalar slots written by the backward prologue (device memory, fp32)
 enum Scalar { SC_LOSS = 0, SC_SCALE = 1, SC_CA = 2, SC_CB = 3, SC_COUNT = 4, SC_FMEAN = 5, SC_REG = 6, SC_INV_SCALE = 7,
@@ -186,6 +186,7 @@ struct SegDesc {          // one parameter tensor for the optimiser / packer
   int layer;              // chain layer index or -1 (not packed)
   int pack_fwd, pack_bwd; // 1: write fp16 copies
   int perm_e;             // forward K permutation (gauss input layer)
+  int kpad;               // layout 1: K the packed operand is padded to (0: cols) -- LogF input layer, 6 n features padded to 128s
   uint32_t wf_off, wd_off;
   float fwd_scale, bwd_scale;   // factor folded into the fp16 copies (SIREN: w0, so the accumulators hold w0*z)
   int layout;             // 0: chain stages (256 rows x 32 K); 1: lgemm N-blocks of `nt` rows x 32 K

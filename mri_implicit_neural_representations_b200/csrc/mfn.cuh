@@ -25,7 +25,8 @@ struct MfnModel {
   int n_out;             // number of live heads (columns of `out` = n_out * out_f, in stage order)
   int bounded;           // MultiscaleBoundedFourier: rows with dist outside [lo, hi] are zeroed before linear i
   float bound_lo[kMfnMaxStages], bound_hi[kMfnMaxStages];   // indexed by stage (stage i uses reference linear[i-1])
-  int input_kind;        // INPUT_GAUSS / INPUT_DENSE
+  int input_kind;        // INPUT_GAUSS / INPUT_DENSE / INPUT_LOGF
+  int enc_n;             // LogF: frequencies per coordinate (the X image holds 6 n features, zero-padded to in_f)
   int enc_size;
   // float offsets in the flat parameter buffer
   int lin_w[kMfnMaxStages], lin_b[kMfnMaxStages];       // stage i = 1..L

@@ -47,6 +47,25 @@ __global__ void __launch_bounds__(256) mfn_encode_kernel(const __grid_constant__
         const float ang = 6.283185307179586f * fmaf(x0, __ldg(b), fmaf(x1, __ldg(b + 1), x2 * __ldg(b + 2)));
         v[e] = is_cos ? fast_cos(ang) : fast_sin(ang);
       }
+    } else if (M.input_kind == INPUT_LOGF) {
+      // reference networks.py:24-29: per coordinate c the block [sin(2 pi x_c B_0..n-1) | cos(2 pi x_c B_0..n-1)], B = a.encB [n];
+      // features beyond 6 n are the zero padding of the operand image
+      float xc[3] = {0.f, 0.f, 0.f};
+      if (grow < a.bs) { const float* c = a.coords + srow * 3; xc[0] = c[0]; xc[1] = c[1]; xc[2] = c[2]; }
+      const int n = M.enc_n;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int f = kg * 8 + e;
+        float val = 0.f;
+        if (f < 6 * n) {
+          const int c = f / (2 * n), r = f - c * 2 * n;
+          const bool is_cos = r >= n;
+          // full-precision sine: B reaches 2^scale, so the angle spans thousands of radians where sin.approx loses its digits
+          const float ang = (6.283185307179586f * xc[c]) * __ldg(a.encB + (is_cos ? r - n : r));
+          val = is_cos ? cosf(ang) : sinf(ang);
+        }
+        v[e] = val;
+      }
     } else {
       const float* xr = a.x + srow * M.in_f + kg * 8;
 #pragma unroll

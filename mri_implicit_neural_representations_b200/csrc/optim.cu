@@ -25,7 +25,7 @@ __device__ __forceinline__ void pack_store(const SegDesc& s, uint8_t* wpack, int
     const uint32_t stage_b = static_cast<uint32_t>(s.nt) * 64;
     if (s.pack_fwd) {       // B[n = out, k = in]
       const int nb = o / s.nt, n = o % s.nt, st = i >> 5, kk = i & 31;
-      *reinterpret_cast<__half*>(wpack + s.wf_off + (static_cast<size_t>(nb) * (s.cols >> 5) + st) * stage_b + (kk >> 3) * (s.nt * 16) +
+      *reinterpret_cast<__half*>(wpack + s.wf_off + (static_cast<size_t>(nb) * ((s.kpad ? s.kpad : s.cols) >> 5) + st) * stage_b + (kk >> 3) * (s.nt * 16) +
                                  n * 16 + (kk & 7) * 2) = __float2half_rn(val * s.fwd_scale);
     }
     if (s.pack_bwd) {       // B^T[n = in, k = out]

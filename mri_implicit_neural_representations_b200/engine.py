@@ -75,15 +75,19 @@ class Plan:
         kind = enc.get("embedding", "none")
         if kind not in L.ENC:
             raise L.InrError(f"encoder '{kind}' is not built into the fused kernels")
+        if kind == "LogF" and model not in ("SIREN", "FFN"):
+            raise L.InrError("the LogF encoder is fused for SIREN / FFN only (src/models/networks.py:24-29)")
         self.desc = L.ModelDesc(L.MODEL[model], int(net["network_input_size"]), int(net["network_output_size"]),
                                 int(net["network_depth"]), int(net["network_width"]), L.LAST[last],
-                                L.ENC[kind], int(enc.get("embedding_size", 0)) if kind == "gauss" else 0,
+                                L.ENC[kind], int(enc.get("embedding_size", 0)) if kind in ("gauss", "LogF") else 0,
                                 float(net.get("first_omega_0", 30.0)) if model in ("WIRE", "WIRE2D") else 30.0,
                                 float(net.get("hidden_omega_0", 30.0)), float(net.get("scale", 10.0)))
         self.out_cols = int(net["network_output_size"])
         # SIREN / FFN outside the on-chip chain kernels' shape (width 256, >= 2 sine layers, linear / tanh / sigmoid output)
         # run layer by layer on the streaming stage GEMMs ("wide chain", csrc/abi.cu wide_plan_create)
-        self.wide = model in ("SIREN", "FFN") and (int(net["network_width"]) != 256 or int(net["network_depth"]) < 3 or last == "sin")
+        # (and so does every LogF-encoded model: its 6 n input features are padded to the operand chunks there)
+        self.wide = model in ("SIREN", "FFN") and (int(net["network_width"]) != 256 or int(net["network_depth"]) < 3 or last == "sin"
+                                                    or kind == "LogF")
         if model in ("MultiscaleFourier", "BoundedFourier"):
             layers = list(net.get("output_layers", [1, 3, 5, 7]))
             mask = 0
@@ -360,7 +364,11 @@ class ChainEngine:
         """MFN only (tests / debugging): 'z' (stage output), 'g' (sin p), 'dp' (S_stage * dL/dp) as [rows_pad, width]."""
         lay = self.plan.workspace_layout(bs)
         T, F = lay["n_tiles"], self.plan.desc.width
-        off = {"z": lay["h"], "g": lay["d"], "dp": lay["dz"], "q": lay["q"]}[kind][stage]
+        if kind == "x":         # the encoded input image [rows_pad, in_features padded to 128s] (slot 36 of the MFN layout)
+            F = (self.plan.desc.in_features + 127) // 128 * 128
+            off = lay["dzlast"]
+        else:
+            off = {"z": lay["h"], "g": lay["d"], "dp": lay["dz"], "q": lay["q"]}[kind][stage]
         img = self.workspace[off:off + T * 128 * F * 2].view(torch.float16).view(T, F // 8, 128, 8)
         return img.permute(0, 2, 1, 3).reshape(T * 128, F).float()
 

@@ -149,11 +149,11 @@ class FusedChain(nn.Module):
     def engine(self, encoder: Optional[dict], max_batch: int) -> ChainEngine:
         """Engine for this model with the given input mode (None/'none': dense [bs,in] input; gauss: in-kernel
         encoding of coords).  All engines of a module share its parameters, gradients and Adam state."""
-        key = "gauss" if (encoder and encoder.get("embedding") == "gauss") else "none"
+        key = encoder.get("embedding") if (encoder and encoder.get("embedding") in ("gauss", "LogF")) else "none"
         st = self._shared_state(max_batch)
         eng = self._engines.get(key)
         if eng is None or eng.max_batch < max_batch:
-            plan = Plan(self.MODEL, self.net, encoder if key == "gauss" else {"embedding": "none"})
+            plan = Plan(self.MODEL, self.net, encoder if key != "none" else {"embedding": "none"})
             if self.MODEL in ("WIRE", "WIRE2D"):
                 assert key == "none", "WIRE / WIRE2D take raw coordinates"
             eng = ChainEngine(plan, max_batch=max(max_batch, 128), device=self._flat.device,

@@ -161,8 +161,9 @@ class FusedTrainer:
         wire = getattr(model, "MODEL", None) in ("WIRE", "WIRE2D")
         if wire and encoder.embedding_type != "none":
             raise L.InrError("WIRE is fitted on raw coordinates (encoder.embedding: none)")
-        if not wire and encoder.embedding_type not in ("gauss",):
-            raise L.InrError("the fused step needs the gauss encoder (dense inputs go through the unfused path)")
+        logf_ok = encoder.embedding_type == "LogF" and getattr(model, "MODEL", None) in ("SIREN", "FFN")
+        if not wire and encoder.embedding_type != "gauss" and not logf_ok:
+            raise L.InrError("the fused step needs the gauss encoder, or LogF with SIREN / FFN (dense inputs go through the unfused path)")
         dev = model._flat.device
         self.model, self.encoder, self.optim = model, encoder, optim
         self.loss, self.loss_opts, self.bs = loss, dict(loss_opts or {}), int(batch_size)

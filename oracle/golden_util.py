@@ -15,6 +15,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 
 ENC_GAUSS = {"embedding": "gauss", "scale": 4, "embedding_size": 256, "coordinates_size": 3}
 ENC_NONE = {"embedding": "none", "scale": 4, "embedding_size": 256, "coordinates_size": 3}
+ENC_LOGF = {"embedding": "LogF", "scale": 4, "embedding_size": 256, "coordinates_size": 3}     # 42 frequencies x 3 coords x (sin, cos) = 252
 NET_256 = {"network_input_size": 512, "network_output_size": 2, "network_depth": 4, "network_width": 256}
 NET_WIRE = {"network_input_size": 3, "network_output_size": 2, "network_depth": 4, "network_width": 256,
             "first_omega_0": 30, "hidden_omega_0": 30, "scale": 15}
@@ -36,6 +37,7 @@ CASES = {
     "gabor_tanh": ("Gabor", NET_MFN, ENC_GAUSS, "tanh", None, 300, 19),
     "wire2d_l2":  ("WIRE2D", NET_W2D, ENC_NONE, "L2", None, 400, 20),
     "wire2d_tanh": ("WIRE2D", dict(NET_W2D, last_tanh=True), ENC_NONE, "tanh", None, 384, 21),
+    "siren_logf": ("SIREN", dict(NET_256, network_input_size=252), ENC_LOGF, "L2", None, 600, 22),
 }
 N_ADAM_STEPS = 3
 LR = 5e-4

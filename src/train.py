@@ -184,7 +184,8 @@ def fit(config, dataset, data_loader, val_loader, max_epoch, device, train_write
     gt_image = M.reconstruct(dataset.image.to(device), (C, H, W), in_image_space)
 
     wire = config["model"] in ("WIRE", "WIRE2D")           # both take raw coordinates (reference networks.py:234, wire2d.py:92)
-    enc_ok = config["encoder"]["embedding"] == ("none" if wire else "gauss")
+    enc_ok = (config["encoder"]["embedding"] == ("none" if wire else "gauss")
+              or (config["encoder"]["embedding"] == "LogF" and config["model"] in ("SIREN", "FFN")))
     per_coil = bool(config.get("per_coil", False))
     if per_coil:
         bs = H * W                              # one coil per batch, grid order (reference per-coil loader)
