@@ -643,7 +643,8 @@ static WireWorkspace wire_workspace(const inr_plan* p, int64_t bs) {
   w.scal = o; o += align_up(kScalars * 4, 1024);
   // forward hand-over counters: same place for every batch size (a chain that starts the step cannot have them zeroed by a
   // kernel before it: wire_last zeroes what the chain used, and the block starts out zero -- include/inr_b200.h)
-  w.flags_fwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * kWFlagTiles * 4, 1024);
+  // (batches above kWFlagTiles row tiles get a larger block; the first-layer fold is off for them and wire_first zeroes it)
+  w.flags_fwd = o; o += align_up(static_cast<uint64_t>(kWMaxDepth) * (T > kWFlagTiles ? T : kWFlagTiles) * 4, 1024);
   w.part = o; o += align_up(static_cast<uint64_t>(T) * kPartialsPerTile * 4, 1024);
   w.g = o; o += align_up(static_cast<uint64_t>(T) * kTileM * 16, 1024);
   w.outacc = o; o += align_up(static_cast<uint64_t>(T) * kWOutParts * kTileM * 16, 1024);   // partial outputs of the final linear
