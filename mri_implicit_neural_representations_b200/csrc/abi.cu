@@ -1547,6 +1547,7 @@ static int train_step_impl(const inr_plan* p, const inr_loss_desc* loss, float* 
     wa.hyper = hyper_dev; wa.step = step_dev; wa.loss_out = loss_out_dev;
     wa.row_offset = row_cursor_dev; wa.row_advance = static_cast<int>(bs);
     wa.do_adam = no_adam ? 0 : 1; wa.scal_has_bc = no_adam ? 0 : 1; wa.grads = grads_only;
+    wa.params_stable = 1;     // the forward pass of this very call read them: complete since before the step's first kernel
     cudaError_t we = p->wm.nlin == 2 ? launch_w2d_adam(wa, st) : launch_wire_adam(wa, st);
     if (ev) cudaEventRecord(ev[4], st);
     return we == cudaSuccess ? INR_OK : cuda_fail(we, "wire_adam_kernel");

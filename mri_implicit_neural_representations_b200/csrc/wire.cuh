@@ -191,6 +191,8 @@ struct WireAdamArgs {
   const float* gpart; const float* scal; const float* hyper; const int* step;
   float* loss_out; int* row_offset; int row_advance;
   int do_adam, scal_has_bc, pack_only;
+  int params_stable;        // fused step only: nothing since the step's first kernel wrote params / moments, so the optimiser
+                            // kernel may fetch them ahead of its programmatic-dependent wait on wgrad
   PeerArgs peer;            // flat kernel only: n_ranks > 0 -> gradients = mean over ranks of peer.grads[q]
 };
 

@@ -68,12 +68,16 @@ __global__ void __launch_bounds__(256) wire_adam_kernel(const __grid_constant__ 
       if (p >= M.w_off[l] && p < M.w_off[l] + wn) { layer = l; kind = 0; idx = p - M.w_off[l]; break; }
       if (p >= M.b_off[l] && p < M.b_off[l] + bn) { layer = l; kind = 1; idx = p - M.b_off[l]; break; }
     }
-    if (kind == 0 || kind == 1) {
+    if (a.params_stable && (kind == 0 || kind == 1)) {
       w = a.params[p];
       if (upd) { m_old = a.mom[p]; v_old = a.var[p]; }
     }
   }
   griddep_wait();                    // split-K partials of wgrad complete
+  if (!a.params_stable && p < M.n_params && (kind == 0 || kind == 1)) {     // stand-alone calls: whatever precedes may have written them
+    w = a.params[p];
+    if (upd) { m_old = a.mom[p]; v_old = a.var[p]; }
+  }
   if (threadIdx.x == 0) {
     const float* sc = a.scal;
     s_c[2] = sc ? sc[SC_INV_SCALE] : 1.f;
