@@ -155,3 +155,50 @@ def test_ragged_batch_and_mask(inr):
     for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
         gv = eng.exp_avg[off:off + rows * cols].view(grads_ref[k].shape) / 0.1
         assert rel(gv, grads_ref[k]) <= TOL, k
+
+
+def test_siren_full_size_batch_config0(inr, tiling):
+    """BASELINE configs[0] size (SIREN d4 w256, gauss encoder, L2, batch 10 000 = 79 row tiles / 125 transposed tiles, last
+    one ragged) through the fused step (reference src/train.py:158-192).  (a) every output row, the loss and every
+    gradient against the oracle on the whole batch, (b) size-independent properties: a row permutation of the batch leaves
+    loss and gradients unchanged up to the order of the fixed-order reductions, and two engines fed the same three steps
+    end bit-identical (a tile read before it was complete would show up here)."""
+    name = "siren_l2"
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, _, _, _ = case_setup(name)
+    bs = 10000
+    g = torch.Generator().manual_seed(17)
+    coords = torch.rand(bs, 3, generator=g) * 2 - 1
+    gt = torch.randn(bs, 2, generator=g) * 0.1
+    x = O.encode(coords, encB, "gauss")
+    tr = []
+    out_ref = O.model_forward(model_kind, sd, x, net, trace=tr)
+    val, dout = O.loss_l2(out_ref, gt)
+    grads_ref, _ = O.siren_backward(sd, x, tr, dout, net["network_depth"])
+
+    def one_step(c, y):
+        plan, eng = _engine(inr, name, bs=bs)
+        eng.hyper[0:1].fill_(0.0)                                  # lr 0: the first Adam moment is (1 - beta1) * g
+        out = torch.empty(bs, 2, device="cuda")
+        eng.train_step("L2", c.cuda(), y.cuda(), bs, out=out)
+        torch.cuda.synchronize()
+        return plan, eng, out.cpu()
+
+    plan, eng, out = one_step(coords, gt)
+    assert rel(out, out_ref) <= TOL
+    assert abs(float(eng.loss_out) - float(val)) <= 1e-3 * float(val)
+    for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
+        gv = eng.exp_avg[off:off + rows * cols].view(grads_ref[k].shape) / 0.1
+        assert rel(gv, grads_ref[k]) <= TOL, k
+    perm = torch.randperm(bs, generator=g)
+    _, eng_p, out_p = one_step(coords[perm], gt[perm])
+    assert torch.equal(out_p, out[perm])                           # a row's output does not depend on its tile or lane
+    assert abs(float(eng_p.loss_out) - float(eng.loss_out)) <= 1e-5 * abs(float(eng.loss_out))
+    assert rel(eng_p.exp_avg, eng.exp_avg) <= 1e-4
+    engs = [_engine(inr, name, bs=bs)[1] for _ in range(2)]
+    cd, yd = coords.cuda(), gt.cuda()
+    for e in engs:
+        for _ in range(3):
+            e.train_step("L2", cd, yd, bs)
+    torch.cuda.synchronize()
+    assert torch.equal(engs[0].params, engs[1].params)
+    assert torch.isfinite(engs[0].params).all()
