@@ -120,3 +120,55 @@ def test_fused_multiscale_steps_follow_the_oracle_loop(inr):
     for (off, rows, cols, layer, is_bias), k in zip(plan.tensors, sd.keys()):
         got = eng.params[off:off + rows * cols].cpu()
         assert abs(float(got.norm()) - float(P[k].norm())) <= 1e-3 * float(P[k].norm()), k
+
+
+def test_fused_multiscale_full_size_batch_config4(inr):
+    """BASELINE configs[3] size (MultiscaleBoundedFourier w512, 8 stages, 4 heads, LSL + 0.1 * consistency, batch 100 000 =
+    782 row tiles, last one ragged; reference src/train_kspace_multiscale.py:164-192).  (a) every head, the loss and every
+    gradient against the oracle composite on the whole batch, (b) size-independent properties: a row permutation of the
+    batch (coordinates, targets, distances together) leaves every row's heads bit-identical and loss / gradients unchanged
+    up to the order of the fixed-order reductions; the same step twice gives the same bits."""
+    net = dict(G.NET_MFN)
+    torch.manual_seed(31)
+    encB = O.encoder_init(G.ENC_GAUSS)
+    sd = O.multiscale_init(dict(net), bounded=True)
+    bs = 100000
+    g = torch.Generator().manual_seed(8)
+    coords = torch.rand(bs, 3, generator=g) * 2 - 1
+    gt = torch.randn(bs, 2, generator=g) * 0.05
+    dist = torch.sqrt(coords[:, 1] ** 2 + coords[:, 2] ** 2)
+    pnet = dict(net)
+    pnet["boundaries"] = [p for p in PAIRS for _ in (0, 1)]
+    opts = dict(OPTS)
+    opts["consistency"] = (PAIRS, 0.1)
+
+    def grad_step(c, y, d):
+        plan = inr.Plan("BoundedFourier", pnet, G.ENC_GAUSS)
+        eng = inr.ChainEngine(plan, max_batch=bs, lr=G.LR)
+        eng.load_tensors(list(sd.values()))
+        eng.set_encoder(encB)
+        out = torch.empty(bs, 8, device="cuda")
+        eng.grad_step("LSL", c.cuda(), y.cuda(), bs, loss_opts=opts, out=out, dist=d.cuda())
+        torch.cuda.synchronize()
+        return eng, out.cpu(), eng.grads.clone(), float(eng.loss_out)
+
+    eng, out, grads, loss = grad_step(coords, gt, dist)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    outs, val, douts = _oracle_composite(P, O.encode(coords, encB, "gauss"), dist, gt, None, "LSL", True)
+    grs = torch.autograd.grad(outs, list(P.values()), grad_outputs=douts, allow_unused=True)
+    for k, o in enumerate(outs):
+        assert rel(out[:, 2 * k:2 * k + 2], o) <= 1e-3, k
+    assert abs(loss - float(val)) <= 2e-3 * abs(float(val)), (loss, float(val))
+    gv = dict(zip(sd.keys(), eng._views(grads)))
+    for k, ref in zip(P.keys(), grs):
+        if ref is None:
+            assert float(gv[k].abs().max()) == 0.0, k
+        else:
+            assert rel(gv[k], ref) <= 5e-3, (k, rel(gv[k], ref))       # end to end, same band as the 700-row case above
+    _, out2, grads2, loss2 = grad_step(coords, gt, dist)
+    assert torch.equal(out2, out) and torch.equal(grads2, grads) and loss2 == loss
+    perm = torch.randperm(bs, generator=g)
+    _, out_p, grads_p, loss_p = grad_step(coords[perm], gt[perm], dist[perm])
+    assert torch.equal(out_p, out[perm])
+    assert abs(loss_p - loss) <= 1e-5 * abs(loss)
+    assert rel(grads_p, grads) <= 1e-4

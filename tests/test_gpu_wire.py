@@ -256,6 +256,37 @@ def test_wire_full_size_batch_chained_layers(inr):
     assert abs(float(eng.loss_out) - float(val)) <= 2e-3 * abs(float(val)), (float(eng.loss_out), float(val))
 
 
+def test_wire_full_size_batch_row_permutation_invariance(inr):
+    """Size-independent property at BASELINE config 2 size (bs 25 000, HDR, row mask): permuting the rows of the batch
+    (coordinates, targets and mask together) leaves every row's output bit-identical -- a row's value does not depend on the
+    tile, CTA pair or TMEM lane it lands on, nor on the order in which the chained launch hands tiles from layer to layer --
+    and the loss and every gradient unchanged up to the order of the fixed-order reductions."""
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, coords, gt, mask = case_setup("wire_hdr")
+    bs = 25000
+    g = torch.Generator().manual_seed(21)
+    c = torch.rand(bs, 3, generator=g) * 2 - 1
+    y = torch.randn(bs, 2, generator=g) * 0.05
+    m = (torch.arange(bs) % 3 != 0)
+
+    def run(c_, y_, m_):
+        eng = inr.ChainEngine(inr.Plan(model_kind, net, enc_cfg), max_batch=bs, lr=G.LR)
+        eng.load_tensors(list(sd.values()))
+        out = torch.zeros(bs, 2, device="cuda")
+        cd, yd, md = c_.cuda(), y_.cuda(), m_.to(torch.uint8).cuda()
+        for _ in range(2):                                       # second pass: lagged per-layer scales calibrated
+            eng.grad_step(loss_kind, cd, yd, bs, mask=md, loss_opts=opts, out=out)
+        torch.cuda.synchronize()
+        return out.cpu(), float(eng.loss_out), eng.grads.clone()
+
+    out, loss, grads = run(c, y, m)
+    perm = torch.randperm(bs, generator=g)
+    out_p, loss_p, grads_p = run(c[perm], y[perm], m[perm])
+    assert torch.equal(out_p, out[perm])
+    assert abs(loss_p - loss) <= 1e-5 * abs(loss), (loss_p, loss)
+    assert float((grads_p - grads).norm()) <= 1e-4 * float(grads.norm())
+    assert float(grads.norm()) > 0 and torch.isfinite(grads).all()
+
+
 @pytest.mark.parametrize("name", ["wire_l2", "wire_hdr"])
 def test_wire_folded_first_and_last_layer_items_equal_the_separate_kernels(inr, name, monkeypatch):
     """The backward of the final linear rides in the dgrad chain (default) and, opt-in, the real first layer in the forward
