@@ -270,3 +270,58 @@ def test_kgabor_module_ignores_dist_like_the_reference(inr):
     b = GaborNet(dict(G.NET_MFN)).to("cuda")
     with torch.no_grad():
         assert torch.equal(a(x, d), b(x))
+
+
+def test_gabor_full_size_per_coil_tanh_tv_config3(inr):
+    """BASELINE configs[2] size: GaborNet on one whole coil of a 320 x 320 k-space slice per batch (bs 102 400 = 800 row
+    tiles), tanh loss on the sampled rows of a grid-2*1 mask plus TV over all rows (reference src/train.py:172-182).
+    (a) output, loss and every gradient (d mu / d gamma included) against the oracle on the whole batch -- the TV term is
+    sign-based, so it is taken teacher-forced on the engine's own output; (b) size-independent properties: the same step
+    twice gives the same bits, and flipping the image upside down (blocks of W rows reversed) leaves every row's output
+    bit-identical and loss / gradients unchanged up to the order of the fixed-order reductions."""
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, _, _, _ = case_setup("gabor_tanh")
+    for i in range(net["network_depth"] + 1):                    # conditioned state: every envelope is O(1), see _gabor
+        sd[f"filters.{i}.gamma"] = sd[f"filters.{i}.gamma"] * 0.01 + 1e-3
+        sd[f"filters.{i}.mu"] = sd[f"filters.{i}.mu"] * 0.5
+    H = W = 320
+    bs, L, weight = H * W, net["network_depth"], 0.5
+    g = torch.Generator().manual_seed(12)
+    ky, kx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+    coords = torch.stack([torch.full((bs,), 0.2), kx.reshape(-1), ky.reshape(-1)], 1)
+    gt = torch.rand(bs, 2, generator=g) * 0.8 + 0.1
+    mask = ((torch.arange(bs) // W) % 2 == 0)
+    lopts = dict(opts or {})
+    lopts["tv"] = (H, W, weight)
+
+    def grad_step(c, y, m):
+        eng = inr.ChainEngine(inr.Plan("Gabor", net, enc_cfg), max_batch=bs, lr=G.LR)
+        eng.load_tensors(list(sd.values()))
+        eng.set_encoder(encB)
+        out = torch.empty(bs, 2, device="cuda")
+        eng.grad_step(loss_kind, c.cuda(), y.cuda(), bs, mask=m.to(torch.uint8).cuda(), loss_opts=lopts, out=out)
+        torch.cuda.synchronize()
+        return eng, out.cpu(), eng.grads.clone(), float(eng.loss_out)
+
+    eng, out, grads, loss = grad_step(coords, gt, mask)
+    x = O.encode(coords, encB, "gauss")
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.mfn_forward(P, x, L, True)
+    assert rel(out, o.detach()) <= 1.5e-3
+    val_tv, g_tv = O.loss_tv(out, H, W, weight)
+    val, dsel = O.LOSS_TRAIN["tanh"](o.detach()[mask], gt[mask])
+    dout = g_tv.clone()
+    dout[mask] += dsel
+    assert float(g_tv.norm()) > 0.05 * float(dsel.norm())          # the TV term matters in this test
+    assert abs(loss - float(val + val_tv)) <= 1e-3 * abs(float(val + val_tv)), (loss, float(val), float(val_tv))
+    gr = dict(zip(P.keys(), torch.autograd.grad(o, list(P.values()), grad_outputs=dout)))
+    gv = dict(zip(sd.keys(), eng._views(grads)))
+    for k in sd:
+        assert rel(gv[k], gr[k]) <= 2e-3, (k, rel(gv[k], gr[k]))
+    _, out2, grads2, loss2 = grad_step(coords, gt, mask)
+    assert torch.equal(out2, out) and torch.equal(grads2, grads) and loss2 == loss
+    flip = torch.arange(bs).view(H, W).flip(0).reshape(-1)
+    mask_f = mask[flip]
+    _, out_f, grads_f, loss_f = grad_step(coords[flip], gt[flip], mask_f)
+    assert torch.equal(out_f, out[flip])
+    assert abs(loss_f - loss) <= 1e-5 * abs(loss)
+    assert rel(grads_f, grads) <= 1e-4
