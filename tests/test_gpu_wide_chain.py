@@ -152,3 +152,38 @@ def test_every_shipped_reference_config_builds_a_plan(inr):
     for model, net, enc in shipped:
         plan = inr.Plan(model, net, enc)
         assert plan.n_params > 0, (model, net)
+
+
+def test_siren_w512_d8_full_size_batch_properties(inr):
+    """Bench workload size (reference src/config/local/config_siren_kspace_norm.yaml shape: SIREN w512 d8, batch 100 000 =
+    782 row tiles, last one ragged) on the streaming stage GEMMs: output and loss against the oracle on the whole batch, a row
+    permutation of the batch leaves every row's output bit-identical and loss / gradients unchanged up to the order of the
+    fixed-order reductions, the same step twice gives the same bits."""
+    net = {"network_input_size": 512, "network_output_size": 2, "network_depth": 8, "network_width": 512}
+    n = 100000
+    plan, eng0, sd, encB, coords, gt = _setup(inr, "SIREN", net, seed=11, n=n)
+    out_ref = O.model_forward("SIREN", sd, O.encode(coords, encB, "gauss"), net)
+    val, _ = O.loss_l2(out_ref, gt)
+
+    def run(c, y):
+        eng = inr.ChainEngine(inr.Plan("SIREN", net, ENC), max_batch=n, lr=LR)
+        eng.load_tensors(list(sd.values()))
+        eng.set_encoder(encB)
+        out = torch.empty(n, 2, device="cuda")
+        cd, yd = c.cuda(), y.cuda()
+        for _ in range(2):                                       # the first pass calibrates the per-layer gradient scales
+            eng.grad_step("L2", cd, yd, n, out=out)
+        torch.cuda.synchronize()
+        return out.cpu(), float(eng.loss_out), eng.grads.clone()
+
+    out, loss, grads = run(coords, gt)
+    assert rel(out, out_ref) <= 1.5e-3                               # seven chained w512 sine layers, end to end
+    assert abs(loss - float(val)) <= 1e-3 * float(val)
+    out2, loss2, grads2 = run(coords, gt)
+    assert torch.equal(out2, out) and loss2 == loss and torch.equal(grads2, grads)
+    g = torch.Generator().manual_seed(2)
+    perm = torch.randperm(n, generator=g)
+    out_p, loss_p, grads_p = run(coords[perm], gt[perm])
+    assert torch.equal(out_p, out[perm])
+    assert abs(loss_p - loss) <= 1e-5 * abs(loss)
+    assert rel(grads_p, grads) <= 1e-4

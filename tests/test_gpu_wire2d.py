@@ -275,3 +275,39 @@ def test_wire2d_tanh_tail_fused_steps_and_module(inr):
             assert rel(p.grad, Pm[k].grad) <= 5e-2, k
         else:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+
+
+def test_wire2d_full_size_batch_properties(inr):
+    """Bench workload size (WIRE2D d8 w256, bs 25 000 = 196 row tiles through the chained forward / dgrad launches; reference
+    wire2d.py:4-118).  Rows sampled from all over the batch match the fp64 oracle as well as the fp32 oracle does; a row
+    permutation of the batch leaves every row's output bit-identical and loss / gradients unchanged up to the order of the
+    fixed-order reductions; the same step twice gives the same bits."""
+    model_kind, net, enc_cfg, loss_kind, opts, sd, encB, _, _, _ = case_setup("wire2d_l2")
+    bs = 25000
+    g = torch.Generator().manual_seed(5)
+    c = torch.rand(bs, 3, generator=g) * 2 - 1
+    y = torch.randn(bs, 2, generator=g) * 0.05
+
+    def run(c_, y_):
+        eng = inr.ChainEngine(inr.Plan(model_kind, net, enc_cfg), max_batch=bs, lr=G.LR)
+        eng.load_tensors(list(sd.values()))
+        out = torch.zeros(bs, 2, device="cuda")
+        cd, yd = c_.cuda(), y_.cuda()
+        for _ in range(2):                                       # second pass: lagged per-layer scales calibrated
+            eng.grad_step(loss_kind, cd, yd, bs, loss_opts=opts, out=out)
+        torch.cuda.synchronize()
+        return out.cpu(), float(eng.loss_out), eng.grads.clone()
+
+    out, loss, grads = run(c, y)
+    rows = torch.cat([torch.arange(0, 200), torch.randint(200, bs - 200, (300,), generator=g), torch.arange(bs - 200, bs)])
+    o32 = O.model_forward(model_kind, sd, c[rows], net)
+    o64 = O.model_forward(model_kind, to64(sd), c[rows].double(), net)
+    assert rel(out[rows], o64) <= 4 * rel(o32, o64) + 1e-4
+    out2, loss2, grads2 = run(c, y)
+    assert torch.equal(out2, out) and loss2 == loss and torch.equal(grads2, grads)
+    perm = torch.randperm(bs, generator=g)
+    out_p, loss_p, grads_p = run(c[perm], y[perm])
+    assert torch.equal(out_p, out[perm])
+    assert abs(loss_p - loss) <= 1e-5 * abs(loss), (loss_p, loss)
+    assert float((grads_p - grads).norm()) <= 1e-4 * float(grads.norm())
+    assert float(grads.norm()) > 0 and torch.isfinite(grads).all()
