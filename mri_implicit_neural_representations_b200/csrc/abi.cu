@@ -821,6 +821,7 @@ static int wire_backward_impl(const inr_plan* p, const WireWorkspace& w, const L
   }
   fill_wgrad_sched(p, wg);
   wg.n_split = w.n_split; wg.n_tiles = w.n_tiles; wg.n_params = M.gd_floats; wg.ws = W; wg.gpart_off = w.gpart;
+  wg.l2_hints = 1;       // the A sub-images (dZ, read once, by this kernel last) leave L2 first: measured with the chains' policy, lgemm.cu
   e = launch_wgrad(wg, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel(wire)");
 }
@@ -1359,7 +1360,7 @@ static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& l
   cudaError_t e = w.tile_rows == kTileM ? launch_chain_bwd(b, p->n_sm, st) : launch_chain_bwd_t(b, p->n_sm, st);
   if (e != cudaSuccess) return cuda_fail(e, "chain_bwd_kernel");
   if (mid) cudaEventRecord(mid, st);
-  WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g); g.trace = g_trace;
+  WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g); g.trace = g_trace; g.l2_hints = 0;
   e = launch_wgrad(g, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel");
 }

@@ -163,6 +163,7 @@ struct WgradArgs {
   uint8_t* ws;
   uint64_t gpart_off;
   unsigned long long* trace;   // debug: 8 %globaltimer stamps per CTA starting at slot 64 (null in production)
+  int l2_hints;                // bit 0: A sub-images (read once) leave L2 first, bit 1: B chunks too
 };
 
 // Data-parallel gradient exchange over NVLink peer memory, fused into the optimiser kernel: every rank's

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
       long long c_flag = 0, c_empty = 0, c_issue = 0, tq = 0;
       const long long tr_c0 = tr ? clock64() : 0;
       const unsigned long long tr_n0 = tr ? global_ns() : 0;
+      const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();     // LGemmArgs::l2_policy
       for (int item = cta0; item < n_items; item += n_walk) {
         const int layer = item / per_layer, rem = item - layer * per_layer;
         const int tile = PAIR ? 2 * (rem / a.n_nblocks) + static_cast<int>(rank) : rem / a.n_nblocks, nb = rem % a.n_nblocks;
@@ -244,7 +245,10 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
           const LGemmLayer& Lq = a.chain[layer];
           const uint8_t* base = (lane < 2 ? Lq.in_y : Lq.in_ab) + static_cast<size_t>(tile) * kWTileBytes +
                                 static_cast<size_t>(((lane & 1) ? kWP / 8 : 0) + (kWFeatPerBlock / 8) * nb) * 2048;
-          if (!(lane == 3 && Lq.real_first)) bulk_prefetch_l2(base, (kWFeatPerBlock / 8) * 2048);
+          if (!(lane == 3 && Lq.real_first)) {
+            if ((a.l2_policy & 2) && lane >= 2) bulk_prefetch_l2_hint(base, (kWFeatPerBlock / 8) * 2048, pol_first);   // (a, b): dead after this item
+            else bulk_prefetch_l2(base, (kWFeatPerBlock / 8) * 2048);
+          }
         }
         if (has_nogemm && layer == 0) continue;   // top / first-layer items have no operands: nothing to stream, no ring slots used
         if (BRES && layer * a.n_nblocks + nb != cur_b) {
@@ -284,6 +288,10 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
               bytes = a_bytes; dst_off = is_lo ? a_lo_off : 0;
             }
           }
+          // L2 eviction priority of the lines this lane streams (LGemmArgs::l2_policy bit 0): the hi image of an A tile is read
+          // again later in the step -- the forward's H_hi by the dgrad epilogues and by wgrad, the dgrad chain's dZ by wgrad --
+          // so its lines are marked evict_last as they pass; the step's working set (~400 MB of images) is three times the L2
+          const bool hint = (a.l2_policy & 1) && !is_b && !is_lo && src;
           for (int s = 0; s < n_it; ++s) {
             if (tr) tq = clock64();
             mbar_wait(&empty[slot], ph ^ 1);
@@ -293,7 +301,11 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             } else {
               if (lane == 0) mbar_arrive_expect_tx(&full[slot], phantom ? slot_bytes - (PASSES == 3 ? 2 : 1) * a_bytes : slot_bytes);
               __syncwarp();
-              if (src) { bulk_g2s(ring + slot * slot_bytes + dst_off, src, bytes, &full[slot]); src += bytes; }
+              if (src) {
+                if (hint) bulk_g2s_hint(ring + slot * slot_bytes + dst_off, src, bytes, &full[slot], pol_last);
+                else bulk_g2s(ring + slot * slot_bytes + dst_off, src, bytes, &full[slot]);
+                src += bytes;
+              }
             }
             __syncwarp();
             if (++slot == static_cast<uint32_t>(n_slots)) { slot = 0; ph ^= 1; }
@@ -641,6 +653,15 @@ __global__ void __launch_bounds__(kLgThreads, 1) lgemm_kernel(const __grid_const
             for (int i = 0; i < 3; ++i) pre[i][0] = pre[i][1] = pre[i][2] = pre[i][3] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
           } else
 #endif
+          if (a.l2_policy & 2) {  // the (a, b) image is dead after this item -> its lines leave L2 first
+            const uint64_t pf = l2_policy_evict_first();
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              pre[i][0] = ld_global_nc_v4(py + i * 2048); pre[i][1] = ld_global_nc_v4(py + kImOff + i * 2048);
+              pre[i][2] = ld_global_nc_v4_hint(pab + i * 2048, pf);
+              pre[i][3] = real_first ? make_uint4(0u, 0u, 0u, 0u) : ld_global_nc_v4_hint(pab + kImOff + i * 2048, pf);
+            }
+          } else
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             pre[i][0] = ld_global_nc_v4(py + i * 2048); pre[i][1] = ld_global_nc_v4(py + kImOff + i * 2048);
@@ -1099,7 +1120,14 @@ static cudaError_t lgemm_launch_one(const LGemmArgs& a, int n_sm, cudaStream_t s
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-cudaError_t launch_lgemm(const LGemmArgs& a, int n_sm, cudaStream_t stream) {
+cudaError_t launch_lgemm(const LGemmArgs& a_in, int n_sm, cudaStream_t stream) {
+  LGemmArgs a = a_in;
+  {
+    // L2 eviction priorities (see the producer): on for the WIRE chains, where they were measured (backward kernels 110.1 ->
+    // 106.2 us, forward unchanged); INR_LGEMM_L2 overrides per launch (A/B runs, tools/ab_variants.py)
+    const char* env = std::getenv("INR_LGEMM_L2");
+    a.l2_policy = env ? std::atoi(env) : ((a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD) ? 3 : 0);
+  }
   const bool chain = a.mode == LG_WIRE_FWD || a.mode == LG_WIRE_DGRAD || a.mode == LG_W2D_FWD || a.mode == LG_W2D_DGRAD;
   if (chain && (a.chain_len < 1 || a.chain_len > kWMaxDepth || (a.chain_len > 1 && !a.chain_flags))) return cudaErrorInvalidValue;
   if (a.n_tiles <= 0) return cudaSuccess;

@@ -9,6 +9,7 @@
 // L2->SM operand traffic that bounds this kernel by a third compared with square 128 x 128 units.
 // Bias gradients ride along as one extra N=16 MMA against an all-ones operand.
 // The last (out_f-wide) layer is computed transposed: D[in_chunk, 16] = H^T dZ_last.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "inr_ptx.cuh"
 #include "inr_kernels.cuh"
@@ -80,17 +81,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     // for all of its chunks never blocks the in-order prefetch of the following B chunks.
     if (lane == 0) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      const uint64_t pol_first = l2_policy_evict_first();
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&empty[as], aph ^ 1);
         mbar_arrive_expect_tx(&full[as], U.a_bytes);
-        bulk_g2s(ring + as * kWgSlotBytes, a.ws + U.a_off + static_cast<size_t>(t) * U.a_tile_stride + U.a_sub, U.a_bytes, &full[as]);
+        if (a.l2_hints & 1) bulk_g2s_hint(ring + as * kWgSlotBytes, a.ws + U.a_off + static_cast<size_t>(t) * U.a_tile_stride + U.a_sub, U.a_bytes, &full[as], pol_first);
+        else bulk_g2s(ring + as * kWgSlotBytes, a.ws + U.a_off + static_cast<size_t>(t) * U.a_tile_stride + U.a_sub, U.a_bytes, &full[as]);
         if (++as == nA) { as = 0; aph ^= 1; }
         for (int c = 0; c < nch; ++c) {
           const uint32_t slot = nA + bs;
           mbar_wait(&empty[slot], bph ^ 1);
           mbar_arrive_expect_tx(&full[slot], U.b_bytes);
-          bulk_g2s(ring + slot * kWgSlotBytes,
-                   a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub + static_cast<size_t>(c) * U.b_bytes, U.b_bytes, &full[slot]);
+          const uint8_t* bsrc = a.ws + U.b_off + static_cast<size_t>(t) * U.b_tile_stride + U.b_sub + static_cast<size_t>(c) * U.b_bytes;
+          if (a.l2_hints & 2) bulk_g2s_hint(ring + slot * kWgSlotBytes, bsrc, U.b_bytes, &full[slot], pol_first);
+          else bulk_g2s(ring + slot * kWgSlotBytes, bsrc, U.b_bytes, &full[slot]);
           if (++bs == nB) { bs = 0; bph ^= 1; }
         }
       }
@@ -268,7 +272,10 @@ cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  return launch_dependent(wgrad_kernel, dim3(grid), dim3(kWgThreads), kWgSmem, stream, a);
+  WgradArgs b = a;
+  const char* env = std::getenv("INR_WGRAD_L2");       // overrides the caller's choice per launch (A/B runs)
+  if (env) b.l2_hints = std::atoi(env);
+  return launch_dependent(wgrad_kernel, dim3(grid), dim3(kWgThreads), kWgSmem, stream, b);
 }
 
 }  // namespace inr

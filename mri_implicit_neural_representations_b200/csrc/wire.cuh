@@ -131,6 +131,7 @@ struct LGemmArgs {
   const int* row_offset;
   int* step_counter;        // incremented once per launch (by one thread) or null
   uint8_t* ximg;            // coordinate image [tile][2][128 rows][8] fp16: [x_hi(3), 1, x_lo(3), 0 | 0 x 8]
+  int l2_policy;            // set by launch_lgemm: bit 0 hi A images pass as evict_last, bit 1 the dgrad epilogue's (a, b) loads as evict_first
   int dbg;                  // debug (INR_LGEMM_DBG), timing experiments only, results are wrong: bit 0 skip MMAs, bit 1 skip operand copies,
                             // bit 2 skip the proxy fence and bit 3 the hand-over wait of chained layers
   unsigned long long* trace; // debug: 16 %globaltimer stamps per CTA from slot 64 (null in production)
