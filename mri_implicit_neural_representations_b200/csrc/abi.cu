@@ -1360,7 +1360,8 @@ static int run_backward(const inr_plan* p, const Workspace& w, const LossDesc& l
   cudaError_t e = w.tile_rows == kTileM ? launch_chain_bwd(b, p->n_sm, st) : launch_chain_bwd_t(b, p->n_sm, st);
   if (e != cudaSuccess) return cuda_fail(e, "chain_bwd_kernel");
   if (mid) cudaEventRecord(mid, st);
-  WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g); g.trace = g_trace; g.l2_hints = 0;
+  WgradArgs g; fill_wgrad(p, w, static_cast<uint8_t*>(ws), g); g.trace = g_trace;
+  g.l2_hints = 3;        // dZ and H images are read by this kernel last: their lines leave L2 first (bs 100 000: wgrad 88.2 -> 82.6 us; no effect at 10 000, -0.8 % at 300 000)
   e = launch_wgrad(g, st);
   return e == cudaSuccess ? INR_OK : cuda_fail(e, "wgrad_kernel");
 }
