@@ -134,6 +134,7 @@ struct BwdArgs {
   const float* hyper;    // optional (fused step): Adam hyper-parameters, to pre-compute the bias corrections
   const int* step;       // optional: 1-based step count (already incremented by the forward kernel)
   unsigned long long* trace;
+  int l2_hints;          // set by launch_chain_bwd: bit 0 the act' images (read here last) leave L2 first
 };
 
 struct WgradUnit {
